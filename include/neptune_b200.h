@@ -1,0 +1,212 @@
+/* neptune_b200.h -- C ABI of libneptune_b200.so (hand-written sm_100a kernels for NEPTUNE's
+ * function/request placement MIP).
+ *
+ * The reference (Alessandro-Mosconi/neptune-mip) has no FFI of its own: its solve path is Python
+ * calling OR-Tools' `pywraplp` (SWIG) variable by variable.  Each entry point below replaces one
+ * stage of that path; the reference interface it stands in for is cited as file:line relative to
+ * the reference tree.  The reference-facing plugin (Python classes with the reference's names,
+ * `neptune_mip_b200/core/solvers`) binds these with ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns int: 0 ok, <0 invalid argument (NEPTUNE_E_*), >0 a cudaError_t.
+ *   - `*_d` / unmarked pointers are DEVICE pointers (borrowed, never freed here);
+ *     `*_h` pointers are HOST pointers.  `stream` is a cudaStream_t passed as void*.
+ *   - matrices are row-major float64 unless noted:  d[N][N]  node_delay_matrix (i -> j),
+ *     w[F][N] workload_matrix, r[F][N] core_per_req_matrix, m[F] function_memory_matrix,
+ *     Mj[N] node_memory_matrix, Kj[N] node_cores_matrix, old[F][N] old_allocations_matrix,
+ *     maxd[F] max_delay_matrix, cost[N] node_costs  (reference `core/utils/data.py:5-26`).
+ *   - batched calls take B same-shaped instances: every per-instance array gains a leading
+ *     dimension B (dense, no padding).  The CSR *pattern* (row_ptr/col_idx) is identical for
+ *     same-shaped instances and is stored once; values are per instance.
+ *   - no global state; re-entrant per stream; no host allocation is returned to the caller.
+ */
+#ifndef NEPTUNE_B200_H
+#define NEPTUNE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEPTUNE_ABI_VERSION 1
+
+/* objective / model kind (reference classes NeptuneStep1CPUMinDelay / ...MinUtilization /
+ * ...MinDelayAndUtilization, `core/solvers/neptune/neptune_step1.py:38-77`; same numbering is used
+ * for EfttcStep1CPU*, `core/solvers/efttc/efttc_step1.py:344-441`) */
+#define NEPTUNE_KIND_MIN_DELAY      0
+#define NEPTUNE_KIND_MIN_UTIL       1
+#define NEPTUNE_KIND_MIN_DELAY_UTIL 2
+
+/* assembly flags */
+#define NEPTUNE_FLAG_STRENGTHEN 1   /* append the valid rows x[i,f,j] - c[f,j] <= 0 (NOT in the reference
+                                        matrix; kept after every reference row) */
+
+#define NEPTUNE_E_ARG     (-1)
+#define NEPTUNE_E_SIZE    (-2)   /* index does not fit the ABI's integer widths */
+#define NEPTUNE_E_NOMEM   (-3)   /* caller-provided workspace too small */
+
+/* feasibility bits of neptune_check_solution / neptune_eval_placements: bit set <=> check passed
+ * (reference `core/solvers/efttc/utils/constraints_step1.py`: c<->x :5-18, memory :22-33,
+ * handle_all_requests :37-47, CPU :70-80, n<->c :85-95, budget :126-133) */
+#define NEPTUNE_OK_C_X      1
+#define NEPTUNE_OK_MEMORY   2
+#define NEPTUNE_OK_HANDLE   4
+#define NEPTUNE_OK_CPU      8
+#define NEPTUNE_OK_N_C     16
+#define NEPTUNE_OK_BUDGET  32
+#define NEPTUNE_OK_ALL     63
+
+int neptune_abi_version(void);
+
+/* ---- (a) model assembly ------------------------------------------------------------------------
+ * Replaces the Python model builders: init_x/init_c/init_n (`neptune/utils/variables.py:4-17`),
+ * constrain_c_according_to_x / constrain_memory_usage / constrain_handle_all_requests /
+ * constrain_CPU_usage / constrain_n_according_to_c / constrain_budget
+ * (`neptune/utils/constraints_step1.py:5-103`) and minimize_network_delay /
+ * minimize_node_utilization / minimize_node_delay_and_utilization (`neptune/utils/objectives.py:4-52`).
+ * Canonical layout: columns x[i,f,j] -> f*N*N+i*N+j, c[f,j] -> F*N*N+f*N+j, n[j] -> F*N*N+F*N+j;
+ * rows C1a/C1b interleaved (f,j) | C2 (j) | C3 (f,i) | C4 (j) | C5a/C5b interleaved (j) | C6 (j)
+ * [| S (f,i,j) with NEPTUNE_FLAG_STRENGTHEN].  The result is bit-identical to what the reference's
+ * own code hands to pywraplp (tests/test_assemble_gpu.py). */
+int neptune_model_sizes(int N, int F, int kind, int flags,
+                        int64_t* rows, int64_t* cols, int64_t* nnz);
+
+/* Shared CSR pattern of A and of A^T (any pointer may be NULL to skip that output).
+ * row_ptr[rows+1], col_idx[nnz], rowT_ptr[cols+1], colT_idx[nnz] (row ids of A, ascending). */
+int neptune_assemble_pattern(int N, int F, int kind, int flags,
+                             int64_t* row_ptr, int32_t* col_idx,
+                             int64_t* rowT_ptr, int32_t* colT_idx, void* stream);
+
+/* Per-instance numbers: val[B][nnz], valT[B][nnz], obj[B][cols], lo/hi[B][rows],
+ * col_lb/col_ub[B][cols], col_int[cols] (0/1, shared), wmax[B] (the reference's
+ * max_workload_delay, objectives.py:36-44; written for every kind).  NULL skips an output. */
+int neptune_assemble_values(int B, int N, int F, int kind, int flags, double alpha,
+                            const double* d, const double* w, const double* r, const double* m,
+                            const double* Mj, const double* Kj, const double* maxd,
+                            const double* cost, double budget,
+                            double* val, double* valT, double* obj, double* lo, double* hi,
+                            double* col_lb, double* col_ub, uint8_t* col_int, double* wmax,
+                            void* stream);
+
+/* ---- (b) PDHG LP relaxation ----------------------------------------------------------------------
+ * Replaces the LP work inside `pywraplp.Solver.Solve()` (`core/solvers/solver.py:37`).
+ * Diagonally preconditioned, restarted, averaged PDHG on  min obj.x  s.t. lo <= A x <= hi,
+ * lb <= x <= ub, for B same-pattern instances at once. */
+typedef struct neptune_pdhg_params {
+  int     max_iters;        /* hard cap on PDHG iterations */
+  int     check_every;      /* iterations between KKT evaluations / restart decisions */
+  int     ruiz_iters;       /* Ruiz equilibration passes (then one Pock-Chambolle pass) */
+  int     reserved;
+  double  eps_rel;          /* termination: relative KKT tolerance */
+  double  eps_abs;
+} neptune_pdhg_params;
+
+typedef struct neptune_pdhg_result {  /* one per instance, written to device memory */
+  double primal_obj;        /* obj . x  of the returned iterate */
+  double dual_obj;          /* Lagrangian bound of the returned iterate */
+  double primal_res;        /* ||Ax - proj_[lo,hi](Ax)||_2  */
+  double dual_res;          /* ||obj + A^T y - proj(reduced costs)||_2 */
+  double gap;               /* |primal_obj - dual_obj| */
+  double step;              /* final eta */
+  double primal_weight;     /* final omega */
+  int32_t iters;            /* iterations done */
+  int32_t restarts;
+  int32_t converged;        /* 1 iff tolerances met */
+  int32_t pad;
+} neptune_pdhg_result;
+
+/* bytes of device workspace neptune_pdhg_solve needs */
+int neptune_pdhg_workspace_bytes(int B, int64_t rows, int64_t cols, int64_t nnz, int64_t* bytes);
+
+/* x[B][cols], y[B][rows] in/out (warm start; zero them for a cold start). */
+int neptune_pdhg_solve(int B, int64_t rows, int64_t cols, int64_t nnz,
+                       const int64_t* row_ptr, const int32_t* col_idx, const double* val,
+                       const int64_t* rowT_ptr, const int32_t* colT_idx, const double* valT,
+                       const double* obj, const double* lo, const double* hi,
+                       const double* col_lb, const double* col_ub,
+                       const neptune_pdhg_params* params_h,
+                       double* x, double* y, neptune_pdhg_result* result_d,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
+/* The two SpMV building blocks on their own (tests, roofline measurement):
+ * out[B][rows] = A x   and   out[B][cols] = A^T y  for B same-pattern instances. */
+int neptune_spmv(int B, int64_t rows, int64_t cols, const int64_t* row_ptr, const int32_t* col_idx,
+                 const double* val, const double* x, double* out, void* stream);
+int neptune_spmv_t(int B, int64_t rows, int64_t cols, const int64_t* rowT_ptr,
+                   const int32_t* colT_idx, const double* valT, const double* y, double* out,
+                   void* stream);
+
+/* ---- (c) exact evaluation, rounding, local search -------------------------------------------------
+ * neptune_check_solution: the reference's six checkers and three scorers
+ * (`efttc/utils/constraints_step1.py:5-133`, `efttc/utils/objectives.py:23-98`) on dense
+ * x[N][F][N] (index [i][f][j]), c[F][N], n[N] for B solutions of B instances, every sum in the
+ * reference's order.  flags_out[B] (NEPTUNE_OK_* bits), scores_out[B][3] = {delay, util, combined}. */
+int neptune_check_solution(int B, int N, int F, double alpha,
+                           const double* d, const double* w, const double* r, const double* m,
+                           const double* Mj, const double* Kj, const double* maxd,
+                           const double* cost, double budget,
+                           const double* x, const double* c, const double* n,
+                           int32_t* flags_out, double* scores_out, void* stream);
+
+/* neptune_route_placements: closed-form routing of `change_x_one`
+ * (`efttc/efttc_step1.py:196-212`): x[i,f,j] = 1/|B| on the (1e-6-)nearest open pods of f.
+ * c[B][F][N] (uint8 0/1) -> x[B][N][F][N], n[B][N] (float64). */
+int neptune_route_placements(int B, int N, int F, const double* d, const uint8_t* c,
+                             double* x, double* n, void* stream);
+
+/* neptune_eval_placements: P candidate placements per instance, never materialising x:
+ * c[B][P][F][N] (uint8) -> obj_out[B][P][3] {delay, util, combined}, flags_out[B][P],
+ * overload_out[B][P] (sum_j max(0, cpu_load_j - K_j), 0 when the CPU check passes). */
+int neptune_eval_placements(int B, int P, int N, int F, double alpha,
+                            const double* d, const double* w, const double* r, const double* m,
+                            const double* Mj, const double* Kj, const double* maxd,
+                            const double* cost, double budget, const uint8_t* c,
+                            double* obj_out, int32_t* flags_out, double* overload_out,
+                            void* stream);
+
+/* neptune_local_search: per instance, `chains` independent add/drop/swap searches seeded from
+ * seeds[B][S][F][N] (uint8; e.g. EFTTC output, PDHG roundings), `sweeps` best-improvement sweeps
+ * each.  Returns the best feasible placement per instance: best_c[B][F][N] (uint8),
+ * best_obj[B], best_flags[B]. */
+int neptune_local_search(int B, int N, int F, int kind, double alpha, int chains, int sweeps,
+                         uint64_t rng_seed, int S,
+                         const double* d, const double* w, const double* r, const double* m,
+                         const double* Mj, const double* Kj, const double* maxd,
+                         const double* cost, double budget, const double* old,
+                         const uint8_t* seeds, const double* guide /* c-bar [B][F][N] or NULL */,
+                         uint8_t* best_c, double* best_obj, int32_t* best_flags,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+int neptune_local_search_workspace_bytes(int B, int N, int F, int chains, int64_t* bytes);
+
+/* ---- (d) EFTTC greedy -----------------------------------------------------------------------------
+ * Replaces `EfttcStepBase.solve()` (`core/solvers/efttc/efttc_step1.py:39-90` and helpers
+ * :92-312, score_local :356-439).  One thread block per instance; deterministic, same
+ * iteration orders, tie-breaks and tolerances as the reference.
+ * c_out[B][F][N] (uint8), n_out[B][N] (uint8), info_out[B][4] = {ttc iterations, pods,
+ * reference_would_raise_KeyError (efttc_step1.py:118), stop reason}. */
+int neptune_efttc(int B, int N, int F, int kind, double alpha,
+                  const double* d, const double* w, const double* r, const double* m,
+                  const double* Mj, const double* Kj, const double* old,
+                  const double* cost, double budget,
+                  uint8_t* c_out, uint8_t* n_out, int32_t* info_out,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+int neptune_efttc_workspace_bytes(int B, int N, int F, int64_t* bytes);
+
+/* small helper: out[k] = in[k] ? 1.0 : 0.0 (placements travel as uint8, the checkers read float64) */
+int neptune_u8_to_f64(int64_t n, const uint8_t* in, double* out, void* stream);
+
+/* ---- host-buffer convenience (the e2e path of bench.py) -----------------------------------------
+ * Same as neptune_efttc + neptune_route_placements + neptune_check_solution but with HOST
+ * buffers: copies inputs H2D, runs on `stream`, copies c/n/flags/scores D2H and synchronises. */
+int neptune_efttc_host(int B, int N, int F, int kind, double alpha,
+                       const double* d_h, const double* w_h, const double* r_h, const double* m_h,
+                       const double* Mj_h, const double* Kj_h, const double* old_h,
+                       const double* maxd_h, const double* cost_h, double budget,
+                       uint8_t* c_out_h, uint8_t* n_out_h, int32_t* info_out_h,
+                       int32_t* flags_out_h, double* scores_out_h, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEPTUNE_B200_H */

@@ -1,0 +1,688 @@
+// pdhg.cu -- (b) restarted, averaged, diagonally preconditioned PDHG for the LP relaxation of the
+// placement model:   min obj.x   s.t.  lo <= A x <= hi,  lb <= x <= ub.
+//
+// Replaces the LP work inside pywraplp.Solver.Solve() (reference core/solvers/solver.py:37).
+// Two kernels per iteration, each ONE pass over one copy of the matrix with the vector update fused
+// into the SpMV epilogue (so g = A^T y and A x-bar are never materialised):
+//   k_cols<PrimalUpdate> : g = A^T y (CSR of A^T, thread per short column / warp per long one);
+//                          x+ = clip(x - tau*T*(obj + g)); x-bar = 2x+ - x; xsum += x+
+//   k_rows<DualUpdate>   : a = A x-bar (warp per row; block per long row, shuffle + smem reduce);
+//                          v = y + sigma*S*a; y+ = v - sigma*S*clip(v/(sigma*S), lo, hi); ysum += y+
+// T = dc^2, S = dr^2 are the Ruiz + Pock-Chambolle equilibration written as diagonal step sizes, so
+// the assembled (parity-checked) matrix values are never modified.
+// Algorithmic bytes per iteration (fp64 values, int32 indices, int64 row pointers), see DESIGN.md:
+//   24*nnz + 8*(cols+1) + 8*(rows+1)              matrix, both copies
+//   + cols*(8 x + 8 obj + 8 T + 16 lb/ub + 8 x' + 8 xbar + 16 xsum) + 8*rows (y gather)
+//   + rows*(8 y + 8 S + 16 lo/hi + 8 y' + 16 ysum) + 8*cols (xbar gather)
+//   = 24*nnz + 88*cols + 72*rows.
+#include "common.cuh"
+
+namespace neptune {
+
+constexpr int kLongRow = 2048;      // rows longer than this get a whole block
+constexpr int kShortCol = 8;        // columns of A^T up to this length: one thread each
+constexpr int kMaxLongList = 1 << 20;
+
+enum Acc { PRES2 = 0, DRES2, POBJ, DOBJ, NACC_PER = 4 };
+enum { ACC_CUR = 0, ACC_AVG = NACC_PER, ACC_DX2 = 2 * NACC_PER, ACC_DY2, ACC_NB2, ACC_NC2, ACC_NBS2, ACC_NCS2, NACC };
+
+struct Ctl {
+  double tau, sigma, eta, omega;
+  double kkt_restart, kkt_prev;
+  double norm_b, norm_c;
+  double acc[NACC];
+  double best[6];                   // reported numbers of the chosen iterate
+  int iters, since_restart, restarts, converged;
+  int action, avg_count, use_avg, pad;
+};
+
+struct Csr {
+  const int64_t* ptr; const int32_t* idx; const double* val;   // val is [B][nnz]
+  int64_t n_rows, n_cols, nnz;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// SpMV cores.  `Epi` consumes one (instance, row, dot) at a time in the thread that owns it.
+// ---------------------------------------------------------------------------------------------------
+template <class Epi>
+__global__ void __launch_bounds__(256) k_rows_warp(Csr A, const double* __restrict__ xv, Epi epi) {
+  const int b = blockIdx.y;
+  if (epi.skip(b)) return;
+  const double* __restrict__ val = A.val + (int64_t)b * A.nnz;
+  const double* __restrict__ x = xv + (int64_t)b * A.n_cols;
+  const double xs = epi.xscale(b);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < A.n_rows; row += nwarps) {
+    const int64_t p0 = A.ptr[row], p1 = A.ptr[row + 1];
+    if (p1 - p0 > kLongRow) continue;                 // handled by k_rows_long
+    double acc = 0.0;
+    int64_t p = p0 + lane;
+    // 4 independent loads in flight per lane
+    for (; p + 96 < p1; p += 128) {
+      int c0 = __ldcs(A.idx + p), c1 = __ldcs(A.idx + p + 32), c2 = __ldcs(A.idx + p + 64),
+          c3 = __ldcs(A.idx + p + 96);
+      double v0 = __ldcs(val + p), v1 = __ldcs(val + p + 32), v2 = __ldcs(val + p + 64),
+             v3 = __ldcs(val + p + 96);
+      acc += v0 * x[c0]; acc += v1 * x[c1]; acc += v2 * x[c2]; acc += v3 * x[c3];
+    }
+    for (; p < p1; p += 32) acc += __ldcs(val + p) * x[__ldcs(A.idx + p)];
+    acc = warp_sum(acc);
+    if (lane == 0) epi.row(b, row, acc * xs);
+  }
+  epi.finalize(b);
+}
+
+// block per long row; long rows are found by a strided scan over the row list (`long_rows`,
+// `n_long` written once per solve by k_find_long_rows).
+template <class Epi>
+__global__ void __launch_bounds__(256) k_rows_long(Csr A, const double* __restrict__ xv,
+                                                   const int32_t* __restrict__ long_rows,
+                                                   const int32_t* __restrict__ n_long, Epi epi) {
+  const int b = blockIdx.y;
+  if (epi.skip(b)) return;
+  __shared__ double sm[32];
+  const double* __restrict__ val = A.val + (int64_t)b * A.nnz;
+  const double* __restrict__ x = xv + (int64_t)b * A.n_cols;
+  const double xs = epi.xscale(b);
+  const int nl = *n_long;
+  for (int k = blockIdx.x; k < nl; k += gridDim.x) {
+    const int64_t row = long_rows[k];
+    const int64_t p0 = A.ptr[row], p1 = A.ptr[row + 1];
+    double acc = 0.0;
+    int64_t p = p0 + threadIdx.x;
+    for (; p + 3 * 256 < p1; p += 4 * 256) {
+      int c0 = __ldcs(A.idx + p), c1 = __ldcs(A.idx + p + 256), c2 = __ldcs(A.idx + p + 512),
+          c3 = __ldcs(A.idx + p + 768);
+      double v0 = __ldcs(val + p), v1 = __ldcs(val + p + 256), v2 = __ldcs(val + p + 512),
+             v3 = __ldcs(val + p + 768);
+      acc += v0 * x[c0]; acc += v1 * x[c1]; acc += v2 * x[c2]; acc += v3 * x[c3];
+    }
+    for (; p < p1; p += 256) acc += __ldcs(val + p) * x[__ldcs(A.idx + p)];
+    acc = block_sum(acc, sm);
+    if (threadIdx.x == 0) epi.row(b, row, acc * xs);
+  }
+  epi.finalize(b);
+}
+
+__global__ void k_find_long_rows(const int64_t* __restrict__ ptr, int64_t n_rows,
+                                 int32_t* __restrict__ long_rows, int32_t* __restrict__ n_long) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
+       r += (int64_t)gridDim.x * blockDim.x)
+    if (ptr[r + 1] - ptr[r] > kLongRow) {
+      int k = atomicAdd(n_long, 1);
+      if (k < kMaxLongList) long_rows[k] = (int32_t)r;
+    }
+}
+
+// CSR of A^T: thread per column for [0, split), warp per column for [split, n).
+template <class Epi>
+__global__ void __launch_bounds__(256) k_cols_thread(Csr At, int64_t split, const double* __restrict__ yv,
+                                                     Epi epi) {
+  const int b = blockIdx.y;
+  if (epi.skip(b)) return;
+  const double* __restrict__ val = At.val + (int64_t)b * At.nnz;
+  const double* __restrict__ y = yv + (int64_t)b * At.n_cols;   // At.n_cols == rows of A
+  const double ys = epi.xscale(b);
+  for (int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; col < split;
+       col += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p0 = At.ptr[col], p1 = At.ptr[col + 1];
+    double acc = 0.0;
+    if (p1 - p0 == 4 && (p0 & 3) == 0) {             // the x columns: 16B + 32B vector loads
+      const int4 c = __ldcs(reinterpret_cast<const int4*>(At.idx + p0));
+      const double2 v01 = __ldcs(reinterpret_cast<const double2*>(val + p0));
+      const double2 v23 = __ldcs(reinterpret_cast<const double2*>(val + p0 + 2));
+      acc = v01.x * y[c.x];
+      acc += v01.y * y[c.y];
+      acc += v23.x * y[c.z];
+      acc += v23.y * y[c.w];
+    } else {
+      for (int64_t p = p0; p < p1; ++p) acc += __ldcs(val + p) * y[__ldcs(At.idx + p)];
+    }
+    epi.row(b, col, acc * ys);
+  }
+  epi.finalize(b);
+}
+
+template <class Epi>
+__global__ void __launch_bounds__(256) k_cols_warp(Csr At, int64_t split, const double* __restrict__ yv,
+                                                   Epi epi) {
+  const int b = blockIdx.y;
+  if (epi.skip(b)) return;
+  const double* __restrict__ val = At.val + (int64_t)b * At.nnz;
+  const double* __restrict__ y = yv + (int64_t)b * At.n_cols;
+  const double ys = epi.xscale(b);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t col = split + warp0; col < At.n_rows; col += nwarps) {
+    const int64_t p0 = At.ptr[col], p1 = At.ptr[col + 1];
+    double acc = 0.0;
+    for (int64_t p = p0 + lane; p < p1; p += 32) acc += __ldcs(val + p) * y[__ldcs(At.idx + p)];
+    acc = warp_sum(acc);
+    if (lane == 0) epi.row(b, col, acc * ys);
+  }
+  epi.finalize(b);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Epilogues
+// ---------------------------------------------------------------------------------------------------
+struct StoreEpi {            // plain SpMV
+  double* out; int64_t n;
+  __device__ bool skip(int) const { return false; }
+  __device__ double xscale(int) const { return 1.0; }
+  __device__ void row(int b, int64_t r, double v) const { out[(int64_t)b * n + r] = v; }
+  __device__ void finalize(int) const {}
+};
+
+struct PrimalUpdate {        // per column, after g = (A^T y)[col]
+  const Ctl* ctl; int64_t cols;
+  const double *obj, *lb, *ub, *T;
+  double *x, *xbar, *xsum;
+  __device__ bool skip(int b) const { return ctl[b].converged != 0; }
+  __device__ double xscale(int) const { return 1.0; }
+  __device__ void row(int b, int64_t c, double g) const {
+    const int64_t k = (int64_t)b * cols + c;
+    const double tau = ctl[b].tau;
+    const double xo = x[k];
+    double xn = xo - tau * T[k] * (obj[k] + g);
+    xn = fmin(fmax(xn, lb[k]), ub[k]);
+    x[k] = xn;
+    xbar[k] = 2.0 * xn - xo;
+    xsum[k] += xn;
+  }
+  __device__ void finalize(int) const {}
+};
+
+struct DualUpdate {          // per row, after a = (A xbar)[row]
+  const Ctl* ctl; int64_t rows;
+  const double *lo, *hi, *S;
+  double *y, *ysum;
+  __device__ bool skip(int b) const { return ctl[b].converged != 0; }
+  __device__ double xscale(int) const { return 1.0; }
+  __device__ void row(int b, int64_t r, double a) const {
+    const int64_t k = (int64_t)b * rows + r;
+    const double s = ctl[b].sigma * S[k];
+    const double v = y[k] + s * a;
+    const double z = fmin(fmax(v / s, lo[k]), hi[k]);
+    const double yn = v - s * z;
+    y[k] = yn;
+    ysum[k] += yn;
+  }
+  __device__ void finalize(int) const {}
+};
+
+// KKT pieces of a candidate (current iterate or running average) -- rows side:
+//   primal residual ||Ax - clip(Ax, lo, hi)||^2 and the row part of the dual objective -g*(y).
+struct RowsEval {
+  Ctl* ctl; int64_t rows; int which;      // which: 0 current (y), 1 average (ysum / count)
+  const double *lo, *hi, *yv;
+  double pres2, dobj, dres2;
+  __device__ bool skip(int b) const { return ctl[b].converged != 0; }
+  __device__ double xscale(int b) const { return which ? 1.0 / (double)max(ctl[b].avg_count, 1) : 1.0; }
+  __device__ void row(int b, int64_t r, double a) {
+    const int64_t k = (int64_t)b * rows + r;
+    const double l = lo[k], h = hi[k];
+    const double viol = a - fmin(fmax(a, l), h);
+    pres2 += viol * viol;
+    const double yy = yv[k] * xscale(b);
+    if (yy > 0.0) { if (isfinite(h)) dobj -= h * yy; else dres2 += yy * yy; }
+    else if (yy < 0.0) { if (isfinite(l)) dobj -= l * yy; else dres2 += yy * yy; }
+  }
+  __device__ void finalize(int b) {
+    __shared__ double sm[32];
+    double a = block_sum(pres2, sm), c = block_sum(dobj, sm), e = block_sum(dres2, sm);
+    if (threadIdx.x == 0) {
+      double* acc = ctl[b].acc + (which ? ACC_AVG : ACC_CUR);
+      if (a != 0.0) atomicAdd(acc + PRES2, a);
+      if (c != 0.0) atomicAdd(acc + DOBJ, c);
+      if (e != 0.0) atomicAdd(acc + DRES2, e);
+    }
+  }
+};
+
+// columns side: primal objective, reduced-cost part of the dual objective, dual residual.
+struct ColsEval {
+  Ctl* ctl; int64_t cols; int which;
+  const double *obj, *lb, *ub, *xv;
+  double pobj, dobj, dres2;
+  __device__ bool skip(int b) const { return ctl[b].converged != 0; }
+  __device__ double xscale(int b) const { return which ? 1.0 / (double)max(ctl[b].avg_count, 1) : 1.0; }
+  __device__ void row(int b, int64_t c, double g) {
+    const int64_t k = (int64_t)b * cols + c;
+    const double o = obj[k];
+    pobj += o * xv[k] * xscale(b);
+    const double rc = o + g;
+    if (rc > 0.0) { const double l = lb[k]; if (isfinite(l)) dobj += l * rc; else dres2 += rc * rc; }
+    else if (rc < 0.0) { const double u = ub[k]; if (isfinite(u)) dobj += u * rc; else dres2 += rc * rc; }
+  }
+  __device__ void finalize(int b) {
+    __shared__ double sm[32];
+    double a = block_sum(pobj, sm), c = block_sum(dobj, sm), e = block_sum(dres2, sm);
+    if (threadIdx.x == 0) {
+      double* acc = ctl[b].acc + (which ? ACC_AVG : ACC_CUR);
+      if (a != 0.0) atomicAdd(acc + POBJ, a);
+      if (c != 0.0) atomicAdd(acc + DOBJ, c);
+      if (e != 0.0) atomicAdd(acc + DRES2, e);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Equilibration: Ruiz (inf-norm) passes then one Pock-Chambolle (1-norm) pass, as diagonal scalings
+// dr, dc applied on the fly.  One thread per column of A^T; row accumulators via atomics.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scale_pass(Csr At, int use_sum, const double* __restrict__ dr,
+                                                    const double* __restrict__ dc, const double* __restrict__ lo,
+                                                    const double* __restrict__ hi, double* __restrict__ colacc,
+                                                    double* __restrict__ rowacc) {
+  const int b = blockIdx.y;
+  const double* __restrict__ val = At.val + (int64_t)b * At.nnz;
+  const int64_t rows = At.n_cols, cols = At.n_rows;
+  for (int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; col < cols;
+       col += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p0 = At.ptr[col], p1 = At.ptr[col + 1];
+    const double dcj = dc[(int64_t)b * cols + col];
+    double acc = 0.0;
+    for (int64_t p = p0; p < p1; ++p) {
+      const int r = At.idx[p];
+      // a free row (-inf, +inf) never gets a multiplier: it must not distort the equilibration
+      if (isinf(lo[(int64_t)b * rows + r]) && isinf(hi[(int64_t)b * rows + r])) continue;
+      const double mval = fabs(val[p]) * dr[(int64_t)b * rows + r] * dcj;
+      if (use_sum) {
+        acc += mval;
+        if (mval != 0.0) atomicAdd(rowacc + (int64_t)b * rows + r, mval);
+      } else {
+        acc = fmax(acc, mval);
+        atomicMax(reinterpret_cast<unsigned long long*>(rowacc + (int64_t)b * rows + r),
+                  (unsigned long long)__double_as_longlong(mval));
+      }
+    }
+    colacc[(int64_t)b * cols + col] = acc;
+  }
+}
+
+__global__ void k_scale_update(int64_t n, double* __restrict__ dvec, double* __restrict__ acc) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    const double a = acc[k];
+    if (a > 0.0) dvec[k] *= rsqrt(a);
+    acc[k] = 0.0;
+  }
+}
+
+__global__ void k_fill(int64_t n, double* __restrict__ v, double a) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+       k += (int64_t)gridDim.x * blockDim.x) v[k] = a;
+}
+
+__global__ void k_square(int64_t n, double* __restrict__ v) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+       k += (int64_t)gridDim.x * blockDim.x) v[k] = v[k] * v[k];
+}
+
+// ||finite bounds||^2 in the scaled space (per instance) for omega0 and the relative tolerances.
+__global__ void __launch_bounds__(256) k_norms(int64_t rows, int64_t cols, const double* __restrict__ lo,
+                                               const double* __restrict__ hi, const double* __restrict__ obj,
+                                               const double* __restrict__ S, const double* __restrict__ T,
+                                               Ctl* ctl) {
+  const int b = blockIdx.y;
+  __shared__ double sm[32];
+  double nb = 0.0, nc = 0.0, nbs = 0.0, ncs = 0.0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    const double l = lo[(int64_t)b * rows + r], h = hi[(int64_t)b * rows + r];
+    double m = 0.0;
+    if (isfinite(l)) m = fabs(l);
+    if (isfinite(h)) m = fmax(m, fabs(h));
+    nb += m * m;
+    nbs += m * m * S[(int64_t)b * rows + r];
+  }
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cols;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const double o = obj[(int64_t)b * cols + c];
+    nc += o * o;
+    ncs += o * o * T[(int64_t)b * cols + c];
+  }
+  nb = block_sum(nb, sm);
+  nc = block_sum(nc, sm);
+  nbs = block_sum(nbs, sm);
+  ncs = block_sum(ncs, sm);
+  if (threadIdx.x == 0) {
+    if (nb != 0.0) atomicAdd(&ctl[b].acc[ACC_NB2], nb);
+    if (nc != 0.0) atomicAdd(&ctl[b].acc[ACC_NC2], nc);
+    if (nbs != 0.0) atomicAdd(&ctl[b].acc[ACC_NBS2], nbs);
+    if (ncs != 0.0) atomicAdd(&ctl[b].acc[ACC_NCS2], ncs);
+  }
+}
+
+__global__ void k_ctl_init(int B, Ctl* ctl, double eta) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  Ctl& c = ctl[b];
+  c.norm_b = sqrt(c.acc[ACC_NB2]);
+  c.norm_c = sqrt(c.acc[ACC_NC2]);
+  c.eta = eta;
+  // PDLP's initial primal weight ||c|| / ||b||, taken in the equilibrated space
+  const double nbs = sqrt(c.acc[ACC_NBS2]), ncs = sqrt(c.acc[ACC_NCS2]);
+  c.omega = (nbs > 1e-10 && ncs > 1e-10) ? ncs / nbs : 1.0;
+  c.tau = c.eta / c.omega;
+  c.sigma = c.eta * c.omega;
+  c.kkt_restart = INFINITY; c.kkt_prev = INFINITY;
+  for (int k = 0; k < NACC; ++k) c.acc[k] = 0.0;
+  for (int k = 0; k < 6; ++k) c.best[k] = 0.0;
+  c.iters = 0; c.since_restart = 0; c.restarts = 0; c.converged = 0;
+  c.action = 0; c.avg_count = 0; c.use_avg = 0;
+}
+
+__global__ void k_ctl_zero(int B, Ctl* ctl) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) for (int k = 0; k < NACC; ++k) ctl[b].acc[k] = 0.0;
+}
+
+// Restart / termination decision, one thread per instance (PDLP's KKT-error criteria:
+// sufficient decay 0.2, necessary decay 0.8 + no progress, artificial restart at 36 % of the run).
+__global__ void k_ctl_decide(int B, Ctl* ctl, int did_iters, double eps_abs, double eps_rel, int max_iters,
+                             neptune_pdhg_result* res) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  Ctl& c = ctl[b];
+  if (c.converged) return;
+  c.iters += did_iters; c.since_restart += did_iters; c.avg_count += did_iters;
+  double kkt[2]; bool ok[2];
+  for (int w = 0; w < 2; ++w) {
+    const double* a = c.acc + (w ? ACC_AVG : ACC_CUR);
+    const double pres = sqrt(a[PRES2]), dres = sqrt(a[DRES2]);
+    const double gap = fabs(a[POBJ] - a[DOBJ]);
+    kkt[w] = sqrt(c.omega * c.omega * a[PRES2] + a[DRES2] / (c.omega * c.omega) + gap * gap);
+    ok[w] = pres <= eps_abs + eps_rel * c.norm_b && dres <= eps_abs + eps_rel * c.norm_c &&
+            gap <= eps_abs + eps_rel * (fabs(a[POBJ]) + fabs(a[DOBJ]));
+  }
+  const int pick = (ok[1] && !ok[0]) ? 1 : ((ok[0] && !ok[1]) ? 0 : (kkt[1] < kkt[0] ? 1 : 0));
+  const double* a = c.acc + (pick ? ACC_AVG : ACC_CUR);
+  const bool done = ok[0] || ok[1];
+  const bool last = done || c.iters >= max_iters;
+  // restart logic on the better candidate
+  int action = 0;
+  const double cand = kkt[pick];
+  if (!last) {
+    if (cand <= 0.2 * c.kkt_restart) action = 1 + (pick == 0);
+    else if (cand <= 0.8 * c.kkt_restart && cand > c.kkt_prev) action = 1 + (pick == 0);
+    else if (c.since_restart >= 0.36 * c.iters && c.iters > 0 && c.restarts > 0) action = 1 + (pick == 0);
+    else if (c.restarts == 0 && c.since_restart >= 4 * did_iters) action = 1 + (pick == 0);
+  }
+  c.kkt_prev = cand;
+  if (action) { c.kkt_restart = cand; c.restarts += 1; }
+  c.action = action;
+  if (last) {
+    c.converged = done ? 1 : 2;
+    c.use_avg = pick;
+    c.action = pick ? 1 : 0;       // materialise the average into x, y if it is the better iterate
+  }
+  neptune_pdhg_result& r = res[b];
+  r.primal_obj = a[POBJ]; r.dual_obj = a[DOBJ];
+  r.primal_res = sqrt(a[PRES2]); r.dual_res = sqrt(a[DRES2]);
+  r.gap = fabs(a[POBJ] - a[DOBJ]);
+  r.step = c.eta; r.primal_weight = c.omega;
+  r.iters = c.iters; r.restarts = c.restarts; r.converged = done ? 1 : 0; r.pad = 0;
+  for (int k = 0; k < NACC; ++k) c.acc[k] = 0.0;
+}
+
+// Apply the decision: x,y <- average (action 1) or keep current (2); reset sums; measure the
+// movement since the last restart point (for the primal-weight update).
+__global__ void __launch_bounds__(256) k_apply_restart(int64_t n, int is_primal, Ctl* ctl,
+                                                       double* __restrict__ v, double* __restrict__ vsum,
+                                                       double* __restrict__ vrestart,
+                                                       const double* __restrict__ diag) {
+  const int b = blockIdx.y;
+  const int action = ctl[b].action;
+  if (action == 0) return;
+  __shared__ double sm[32];
+  const double inv = 1.0 / (double)max(ctl[b].avg_count, 1);
+  double d2 = 0.0;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = (int64_t)b * n + k;
+    double nv = (action == 1) ? vsum[q] * inv : v[q];
+    const double dlt = nv - vrestart[q];
+    d2 += dlt * dlt / diag[q];                       // scaled-space norm
+    v[q] = nv; vrestart[q] = nv; vsum[q] = 0.0;
+  }
+  d2 = block_sum(d2, sm);
+  if (threadIdx.x == 0 && d2 != 0.0) atomicAdd(&ctl[b].acc[is_primal ? ACC_DX2 : ACC_DY2], d2);
+}
+
+__global__ void k_ctl_after_restart(int B, Ctl* ctl) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  Ctl& c = ctl[b];
+  if (c.action == 0) return;
+  if (c.converged == 0) {
+    const double dx = sqrt(c.acc[ACC_DX2]), dy = sqrt(c.acc[ACC_DY2]);
+    if (dx > 1e-10 && dy > 1e-10 && isfinite(dx) && isfinite(dy)) {
+      // PDLP's smoothed update, limited to a factor 2 per restart (early restarts see dy >> dx
+      // and would otherwise throw the weight off by orders of magnitude)
+      const double nw = exp(0.5 * log(dy / dx) + 0.5 * log(c.omega));
+      c.omega = fmin(fmax(nw, 0.5 * c.omega), 2.0 * c.omega);
+    }
+    c.tau = c.eta / c.omega; c.sigma = c.eta * c.omega;
+  }
+  c.since_restart = 0; c.avg_count = 0; c.action = 0;
+  c.acc[ACC_DX2] = 0.0; c.acc[ACC_DY2] = 0.0;
+}
+
+__global__ void k_all_done(int B, const Ctl* ctl, int* flag) {
+  int done = 1;
+  for (int b = 0; b < B; ++b) if (!ctl[b].converged) { done = 0; break; }
+  *flag = done;
+}
+
+static inline int grid1(int64_t work, int threads, int per_sm) {
+  int64_t g = ceil_div(work, threads);
+  int64_t cap = (int64_t)kNumSMs * per_sm;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+struct Plan {
+  int B; int64_t rows, cols, nnz; int64_t split;
+  Csr A, At;
+  int32_t* long_rows; int32_t* n_long;
+  cudaStream_t s;
+};
+
+template <class Epi>
+static void launch_rows(const Plan& P, const double* xv, Epi epi) {
+  dim3 g(grid1(P.rows * 32, 256, 16), P.B);
+  k_rows_warp<Epi><<<g, 256, 0, P.s>>>(P.A, xv, epi);
+  dim3 gl(kNumSMs * 2, P.B);
+  k_rows_long<Epi><<<gl, 256, 0, P.s>>>(P.A, xv, P.long_rows, P.n_long, epi);
+}
+
+template <class Epi>
+static void launch_cols(const Plan& P, const double* yv, Epi epi) {
+  if (P.split > 0) {
+    dim3 g(grid1(P.split, 256, 16), P.B);
+    k_cols_thread<Epi><<<g, 256, 0, P.s>>>(P.At, P.split, yv, epi);
+  }
+  if (P.split < P.cols) {
+    dim3 g(grid1((P.cols - P.split) * 32, 256, 16), P.B);
+    k_cols_warp<Epi><<<g, 256, 0, P.s>>>(P.At, P.split, yv, epi);
+  }
+}
+
+// first column of A^T whose length exceeds kShortCol (columns are assumed sorted short -> long,
+// which holds for the placement model: x columns, then c, then n); found on device.
+__global__ void k_find_split(const int64_t* __restrict__ ptr, int64_t n, unsigned long long* split) {
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n;
+       c += (int64_t)gridDim.x * blockDim.x)
+    if (ptr[c + 1] - ptr[c] > kShortCol) atomicMin(split, (unsigned long long)c);
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace neptune
+
+using namespace neptune;
+
+extern "C" int neptune_pdhg_workspace_bytes(int B, int64_t rows, int64_t cols, int64_t nnz, int64_t* bytes) {
+  if (B <= 0 || rows <= 0 || cols <= 0 || !bytes) return NEPTUNE_E_ARG;
+  (void)nnz;
+  size_t t = 0;
+  t += 5 * align256((size_t)B * cols * 8);     // xbar, xsum, xrestart, T(dc), colacc
+  t += 4 * align256((size_t)B * rows * 8);     // ysum, yrestart, S(dr), rowacc
+  t += align256((size_t)B * sizeof(Ctl));
+  t += align256((size_t)kMaxLongList * 4) + 256 + 256;
+  *bytes = (int64_t)t;
+  return 0;
+}
+
+extern "C" int neptune_spmv(int B, int64_t rows, int64_t cols, const int64_t* row_ptr, const int32_t* col_idx,
+                            const double* val, const double* x, double* out, void* stream) {
+  if (B <= 0 || !row_ptr || !col_idx || !val || !x || !out) return NEPTUNE_E_ARG;
+  // rows longer than kLongRow need the long-row list; build it in a small temporary
+  cudaStream_t s = (cudaStream_t)stream;
+  int32_t* tmp = nullptr;
+  NEPTUNE_CUDA_OK(cudaMallocAsync(&tmp, (size_t)kMaxLongList * 4 + 256, s));
+  int32_t* n_long = tmp + kMaxLongList;
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(n_long, 0, 4, s));
+  k_find_long_rows<<<grid1(rows, 256, 8), 256, 0, s>>>(row_ptr, rows, tmp, n_long);
+  int64_t nnz = 0;   // per-instance stride of val: read row_ptr[rows] (device) -> need it on host
+  NEPTUNE_CUDA_OK(cudaMemcpyAsync(&nnz, row_ptr + rows, 8, cudaMemcpyDeviceToHost, s));
+  NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
+  Plan P{B, rows, cols, nnz, 0, Csr{row_ptr, col_idx, val, rows, cols, nnz}, Csr{}, tmp, n_long, s};
+  launch_rows(P, x, StoreEpi{out, rows});
+  NEPTUNE_LAUNCH_OK();
+  NEPTUNE_CUDA_OK(cudaFreeAsync(tmp, s));
+  return 0;
+}
+
+extern "C" int neptune_spmv_t(int B, int64_t rows, int64_t cols, const int64_t* rowT_ptr,
+                              const int32_t* colT_idx, const double* valT, const double* y, double* out,
+                              void* stream) {
+  if (B <= 0 || !rowT_ptr || !colT_idx || !valT || !y || !out) return NEPTUNE_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* d_split = nullptr;
+  NEPTUNE_CUDA_OK(cudaMallocAsync(&d_split, 8, s));
+  unsigned long long h_split = (unsigned long long)cols;
+  NEPTUNE_CUDA_OK(cudaMemcpyAsync(d_split, &h_split, 8, cudaMemcpyHostToDevice, s));
+  k_find_split<<<grid1(cols, 256, 8), 256, 0, s>>>(rowT_ptr, cols, d_split);
+  int64_t nnz = 0;
+  NEPTUNE_CUDA_OK(cudaMemcpyAsync(&nnz, rowT_ptr + cols, 8, cudaMemcpyDeviceToHost, s));
+  NEPTUNE_CUDA_OK(cudaMemcpyAsync(&h_split, d_split, 8, cudaMemcpyDeviceToHost, s));
+  NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
+  Plan P{B, rows, cols, nnz, (int64_t)h_split, Csr{}, Csr{rowT_ptr, colT_idx, valT, cols, rows, nnz},
+         nullptr, nullptr, s};
+  launch_cols(P, y, StoreEpi{out, cols});
+  NEPTUNE_LAUNCH_OK();
+  NEPTUNE_CUDA_OK(cudaFreeAsync(d_split, s));
+  return 0;
+}
+
+extern "C" int neptune_pdhg_solve(int B, int64_t rows, int64_t cols, int64_t nnz, const int64_t* row_ptr,
+                                  const int32_t* col_idx, const double* val, const int64_t* rowT_ptr,
+                                  const int32_t* colT_idx, const double* valT, const double* obj,
+                                  const double* lo, const double* hi, const double* col_lb,
+                                  const double* col_ub, const neptune_pdhg_params* prm, double* x, double* y,
+                                  neptune_pdhg_result* result_d, void* workspace, int64_t workspace_bytes,
+                                  void* stream) {
+  if (B <= 0 || rows <= 0 || cols <= 0 || nnz <= 0) return NEPTUNE_E_ARG;
+  if (!row_ptr || !col_idx || !val || !rowT_ptr || !colT_idx || !valT || !obj || !lo || !hi || !col_lb ||
+      !col_ub || !prm || !x || !y || !result_d || !workspace)
+    return NEPTUNE_E_ARG;
+  int64_t need = 0;
+  neptune_pdhg_workspace_bytes(B, rows, cols, nnz, &need);
+  if (workspace_bytes < need) return NEPTUNE_E_NOMEM;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int check_every = prm->check_every > 0 ? prm->check_every : 64;
+  const int max_iters = prm->max_iters > 0 ? prm->max_iters : 20000;
+
+  // carve the workspace
+  char* p = (char*)workspace;
+  auto take = [&](size_t bytes) { char* q = p; p += align256(bytes); return q; };
+  const size_t cb = (size_t)B * cols * 8, rb = (size_t)B * rows * 8;
+  double* xbar = (double*)take(cb); double* xsum = (double*)take(cb); double* xres = (double*)take(cb);
+  double* T = (double*)take(cb); double* colacc = (double*)take(cb);
+  double* ysum = (double*)take(rb); double* yres = (double*)take(rb);
+  double* S = (double*)take(rb); double* rowacc = (double*)take(rb);
+  Ctl* ctl = (Ctl*)take((size_t)B * sizeof(Ctl));
+  int32_t* long_rows = (int32_t*)take((size_t)kMaxLongList * 4);
+  int32_t* n_long = (int32_t*)take(4);
+  unsigned long long* d_split = (unsigned long long*)take(8);
+
+  Csr A{row_ptr, col_idx, val, rows, cols, nnz};
+  Csr At{rowT_ptr, colT_idx, valT, cols, rows, nnz};
+
+  // one-off analysis of the pattern
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(n_long, 0, 4, s));
+  unsigned long long h_split = (unsigned long long)cols;
+  NEPTUNE_CUDA_OK(cudaMemcpyAsync(d_split, &h_split, 8, cudaMemcpyHostToDevice, s));
+  k_find_long_rows<<<grid1(rows, 256, 8), 256, 0, s>>>(row_ptr, rows, long_rows, n_long);
+  k_find_split<<<grid1(cols, 256, 8), 256, 0, s>>>(rowT_ptr, cols, d_split);
+  NEPTUNE_CUDA_OK(cudaMemcpyAsync(&h_split, d_split, 8, cudaMemcpyDeviceToHost, s));
+  NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
+  Plan P{B, rows, cols, nnz, (int64_t)h_split, A, At, long_rows, n_long, s};
+
+  // equilibration: dr = S, dc = T hold the scalings, squared at the end
+  const int g_c = grid1((int64_t)B * cols, 256, 16), g_r = grid1((int64_t)B * rows, 256, 16);
+  k_fill<<<g_c, 256, 0, s>>>((int64_t)B * cols, T, 1.0);
+  k_fill<<<g_r, 256, 0, s>>>((int64_t)B * rows, S, 1.0);
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(rowacc, 0, rb, s));
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(colacc, 0, cb, s));
+  const int ruiz = prm->ruiz_iters >= 0 ? prm->ruiz_iters : 10;
+  for (int it = 0; it <= ruiz; ++it) {
+    const int use_sum = (it == ruiz);           // last pass: Pock-Chambolle alpha = 1
+    dim3 g(grid1(cols, 256, 16), B);
+    k_scale_pass<<<g, 256, 0, s>>>(At, use_sum, S, T, lo, hi, colacc, rowacc);
+    k_scale_update<<<g_c, 256, 0, s>>>((int64_t)B * cols, T, colacc);
+    k_scale_update<<<g_r, 256, 0, s>>>((int64_t)B * rows, S, rowacc);
+  }
+  k_square<<<g_c, 256, 0, s>>>((int64_t)B * cols, T);
+  k_square<<<g_r, 256, 0, s>>>((int64_t)B * rows, S);
+
+  // control block, norms, initial state
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(ctl, 0, (size_t)B * sizeof(Ctl), s));
+  {
+    dim3 g(grid1(cols > rows ? cols : rows, 256, 4), B);
+    k_norms<<<g, 256, 0, s>>>(rows, cols, lo, hi, obj, S, T, ctl);
+  }
+  k_ctl_init<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, 0.99);
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(xsum, 0, cb, s));
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(ysum, 0, rb, s));
+  NEPTUNE_CUDA_OK(cudaMemcpyAsync(xres, x, cb, cudaMemcpyDeviceToDevice, s));
+  NEPTUNE_CUDA_OK(cudaMemcpyAsync(yres, y, rb, cudaMemcpyDeviceToDevice, s));
+  NEPTUNE_LAUNCH_OK();
+
+  int* d_flag = nullptr; int h_flag = 0;
+  NEPTUNE_CUDA_OK(cudaMallocAsync(&d_flag, 4, s));
+
+  PrimalUpdate pu{ctl, cols, obj, col_lb, col_ub, T, x, xbar, xsum};
+  DualUpdate du{ctl, rows, lo, hi, S, y, ysum};
+  for (int it = 0; it < max_iters && !h_flag; it += check_every) {
+    for (int k = 0; k < check_every; ++k) {
+      launch_cols(P, y, pu);
+      launch_rows(P, xbar, du);
+    }
+    // KKT of the current iterate and of the running average
+    for (int w = 0; w < 2; ++w) {
+      launch_rows(P, w ? xsum : x, RowsEval{ctl, rows, w, lo, hi, w ? ysum : y, 0.0, 0.0, 0.0});
+      launch_cols(P, w ? ysum : y, ColsEval{ctl, cols, w, obj, col_lb, col_ub, w ? xsum : x, 0.0, 0.0, 0.0});
+    }
+    k_ctl_decide<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, check_every, prm->eps_abs, prm->eps_rel, max_iters,
+                                                 result_d);
+    {
+      dim3 gc(grid1(cols, 256, 8), B), gr(grid1(rows, 256, 8), B);
+      k_apply_restart<<<gc, 256, 0, s>>>(cols, 1, ctl, x, xsum, xres, T);
+      k_apply_restart<<<gr, 256, 0, s>>>(rows, 0, ctl, y, ysum, yres, S);
+    }
+    k_ctl_after_restart<<<(B + 127) / 128, 128, 0, s>>>(B, ctl);
+    k_all_done<<<1, 1, 0, s>>>(B, ctl, d_flag);
+    NEPTUNE_CUDA_OK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, s));
+    NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
+  }
+  NEPTUNE_LAUNCH_OK();
+  NEPTUNE_CUDA_OK(cudaFreeAsync(d_flag, s));
+  return 0;
+}

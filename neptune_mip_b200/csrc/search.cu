@@ -1,0 +1,494 @@
+// search.cu -- (c2) batched rounding + local search over placements c[F][N].
+//
+// Stands in for SCIP's primal side (branch and bound + heuristics inside pywraplp.Solver.Solve(),
+// reference core/solvers/solver.py:37): once x is eliminated by the nearest-open-pod routing rule
+// (efttc_step1.py:196-212) step 1 is a capacitated facility-location problem in c alone, and the
+// classical add / drop / swap / replace neighbourhood with exact delta evaluation applies.
+//
+// One thread block = one search chain; grid = (chains, instances).  Every chain starts from a seed
+// placement (EFTTC output, a PDHG rounding, ...), optionally perturbed, and runs best-improvement
+// sweeps: each warp evaluates whole moves (exact change of delay, active nodes and CPU overload via a
+// per-warp delta-load array in shared memory), a block argmin picks the move, the touched functions
+// are re-routed.  At a local optimum the chain keeps its best and kicks itself (iterated local search).
+// Thousands of candidate moves are checked per sweep and chain; feasibility of the winner is
+// re-verified by the exact checkers (neptune_check_solution) in the caller.
+#include "common.cuh"
+
+namespace neptune {
+
+struct LsArgs {
+  int N, F, kind, chains, sweeps, S;
+  double alpha, budget;
+  uint64_t rng;
+  const double *d, *w, *r, *m, *Mj, *Kj, *maxd, *cost, *old;
+  const uint8_t* seeds;
+  const double* guide;
+  // workspace
+  double* dT;          // [B][N][N]
+  double* inst_scal;   // [B][4]: wmax, mu, a_d, a_u
+  char* chain_ws;      // [B][chains] blocks
+  int64_t chain_stride;
+  double* chain_cost;  // [B][chains]
+};
+
+struct Chain {
+  uint8_t *c, *best_c;
+  double *b1, *b2, *load, *mem;
+  int *a1, *a2, *cntf, *cntn, *pods;
+};
+
+__device__ __forceinline__ int64_t chain_bytes(int N, int F) {
+  int64_t fn = (int64_t)F * N;
+  int64_t b = 2 * fn + 2 * fn * 8 + 2 * fn * 4 + 2 * (int64_t)N * 8 + (int64_t)F * 4 + (int64_t)N * 4 + fn * 4 + 64;
+  return (b + 255) & ~(int64_t)255;
+}
+static inline int64_t chain_bytes_h(int N, int F) {
+  int64_t fn = (int64_t)F * N;
+  int64_t b = 2 * fn + 2 * fn * 8 + 2 * fn * 4 + 2 * (int64_t)N * 8 + (int64_t)F * 4 + (int64_t)N * 4 + fn * 4 + 64;
+  return (b + 255) & ~(int64_t)255;
+}
+
+__device__ __forceinline__ Chain carve(char* p, int N, int F) {
+  Chain k;
+  const int64_t fn = (int64_t)F * N;
+  k.b1 = (double*)p; p += fn * 8;
+  k.b2 = (double*)p; p += fn * 8;
+  k.load = (double*)p; p += (int64_t)N * 8;
+  k.mem = (double*)p; p += (int64_t)N * 8;
+  k.a1 = (int*)p; p += fn * 4;
+  k.a2 = (int*)p; p += fn * 4;
+  k.pods = (int*)p; p += fn * 4;
+  k.cntf = (int*)p; p += (int64_t)F * 4;
+  k.cntn = (int*)p; p += (int64_t)N * 4;
+  k.c = (uint8_t*)p; p += fn;
+  k.best_c = (uint8_t*)p;
+  return k;
+}
+
+__device__ __forceinline__ uint64_t rng_next(uint64_t& s) {   // xorshift64*
+  s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
+  return s * 2685821657736338717ull;
+}
+
+// nearest / second nearest open pod of f for every source (block-wide, threads over i)
+__device__ void route_f(const LsArgs& a, const Chain& k, const double* d, int f) {
+  const int N = a.N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double* di = d + (int64_t)i * N;
+    double v1 = INFINITY, v2 = INFINITY; int j1 = -1, j2 = -1;
+    for (int j = 0; j < N; ++j) {
+      if (!k.c[(int64_t)f * N + j]) continue;
+      const double v = di[j];
+      if (v < v1) { v2 = v1; j2 = j1; v1 = v; j1 = j; }
+      else if (v < v2) { v2 = v; j2 = j; }
+    }
+    k.b1[(int64_t)f * N + i] = v1; k.a1[(int64_t)f * N + i] = j1;
+    k.b2[(int64_t)f * N + i] = v2; k.a2[(int64_t)f * N + i] = j2;
+  }
+}
+
+// per-node aggregates from scratch (deterministic): pods, memory (f ascending), CPU load
+__device__ void node_state(const LsArgs& a, const Chain& k, const double* w, const double* r, const double* m) {
+  const int N = a.N, F = a.F;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    double mem = 0.0, load = 0.0; int cnt = 0;
+    for (int f = 0; f < F; ++f) {
+      if (!k.c[(int64_t)f * N + j]) continue;
+      mem += m[f]; ++cnt;
+      const double rfj = r[(int64_t)f * N + j];
+      const int* a1 = k.a1 + (int64_t)f * N;
+      const double* wf = w + (int64_t)f * N;
+      double s = 0.0;
+      for (int i = 0; i < N; ++i) if (a1[i] == j) s += wf[i];
+      load += s * rfj;
+    }
+    k.mem[j] = mem; k.load[j] = load; k.cntn[j] = cnt;
+  }
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    int cnt = 0;
+    for (int j = 0; j < N; ++j) cnt += k.c[(int64_t)f * N + j];
+    k.cntf[f] = cnt;
+  }
+}
+
+struct Cost { double delay, util, over; };
+
+// whole-block exact cost of the current state (after route_f for all f and node_state)
+__device__ Cost full_cost(const LsArgs& a, const Chain& k, const double* w, const double* Kj, double* red) {
+  const int N = a.N, F = a.F;
+  double dl = 0.0, ut = 0.0, ov = 0.0;
+  for (int fi = threadIdx.x; fi < F * N; fi += blockDim.x) {
+    const double wv = w[fi];
+    if (wv != 0.0) dl += wv * k.b1[fi];
+  }
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    if (k.cntn[j]) ut += 1.0;
+    const double ex = k.load[j] - Kj[j];
+    if (ex > 1e-9) ov += ex;
+  }
+  Cost c;
+  c.delay = block_sum(dl, red); __syncthreads();
+  c.util = block_sum(ut, red); __syncthreads();
+  c.over = block_sum(ov, red); __syncthreads();
+  __shared__ Cost bc;
+  if (threadIdx.x == 0) bc = c;
+  __syncthreads();
+  return bc;
+}
+
+// One elementary change of function f (remove pod j_out and/or add pod j_in), evaluated by one warp:
+// returns the delay change (valid in every lane) and accumulates CPU-load changes into delta[].
+__device__ double eval_change(const LsArgs& a, const Chain& k, const double* w, const double* r,
+                              const double* dT, int f, int j_out, int j_in, double* delta) {
+  const int N = a.N, lane = threadIdx.x & 31;
+  const double* b1 = k.b1 + (int64_t)f * N; const double* b2 = k.b2 + (int64_t)f * N;
+  const int* a1 = k.a1 + (int64_t)f * N; const int* a2 = k.a2 + (int64_t)f * N;
+  const double* wf = w + (int64_t)f * N; const double* rf = r + (int64_t)f * N;
+  const double* din = j_in >= 0 ? dT + (int64_t)j_in * N : nullptr;
+  double dd = 0.0;
+  for (int i = lane; i < N; i += 32) {
+    const int oa = a1[i];
+    const double ob = b1[i];
+    int na = oa; double nb = ob;
+    if (oa == j_out) { na = a2[i]; nb = b2[i]; }
+    if (din) { const double v = din[i]; if (v < nb) { nb = v; na = j_in; } }
+    if (na != oa) {
+      const double wv = wf[i];
+      if (wv != 0.0) {
+        dd += wv * (nb - ob);
+        if (oa >= 0) atomicAdd(delta + oa, -wv * rf[oa]);
+        if (na >= 0) atomicAdd(delta + na, wv * rf[na]);
+      }
+    }
+  }
+  return warp_sum(dd);
+}
+
+// penalty change for the accumulated load deltas; clears delta[] again.  One warp.
+__device__ double eval_overload_delta(const LsArgs& a, const Chain& k, const double* Kj, double* delta) {
+  const int N = a.N, lane = threadIdx.x & 31;
+  __syncwarp();
+  double dv = 0.0;
+  for (int j = lane; j < N; j += 32) {
+    const double dl = delta[j];
+    if (dl != 0.0) {
+      const double o0 = fmax(k.load[j] - Kj[j], 0.0), o1 = fmax(k.load[j] + dl - Kj[j], 0.0);
+      dv += (o1 > 1e-9 ? o1 : 0.0) - (o0 > 1e-9 ? o0 : 0.0);
+      delta[j] = 0.0;
+    }
+  }
+  __syncwarp();
+  return warp_sum(dv);
+}
+
+enum { MV_NONE = 0, MV_ADD, MV_DROP, MV_SWAP, MV_REPLACE };
+struct Move { int type, f, j, t; };   // ADD(f, j) | DROP(f, j) | SWAP(f, j -> t) | REPLACE(node j: f -> t)
+
+__global__ void __launch_bounds__(256) k_ls_prepare(LsArgs a) {
+  // per instance: dT, wmax, penalty weight, objective weights
+  const int b = blockIdx.x, N = a.N, F = a.F;
+  const double* d = a.d + (int64_t)b * N * N;
+  double* dT = a.dT + (int64_t)b * N * N;
+  for (int k = threadIdx.x; k < N * N; k += blockDim.x) { const int i = k / N, j = k - i * N; dT[(int64_t)j * N + i] = d[k]; }
+  __shared__ double red[32];
+  const double* w = a.w + (int64_t)b * F * N;
+  const double* r = a.r + (int64_t)b * F * N;
+  double wm = 0.0, tw = 0.0, dmax = 0.0, rmin = INFINITY;
+  for (int fi = threadIdx.x; fi < F * N; fi += blockDim.x) {
+    const int f = fi / N, i = fi - f * N;
+    const double md = a.maxd ? a.maxd[(int64_t)b * F + f] : INFINITY;
+    double best = -INFINITY;
+    for (int j = 0; j < N; ++j) { const double v = d[(int64_t)i * N + j]; if (v <= md && v > best) best = v; dmax = fmax(dmax, v); }
+    wm += w[fi] * best; tw += w[fi];
+    if (r[fi] > 0.0) rmin = fmin(rmin, r[fi]);
+  }
+  wm = block_sum(wm, red); __syncthreads();
+  tw = block_sum(tw, red); __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) { dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o)); rmin = fmin(rmin, __shfl_xor_sync(0xffffffffu, rmin, o)); }
+  __shared__ double smx[8], smn[8];
+  if ((threadIdx.x & 31) == 0) { smx[threadIdx.x >> 5] = dmax; smn[threadIdx.x >> 5] = rmin; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < (blockDim.x >> 5); ++q) { dmax = fmax(dmax, smx[q]); rmin = fmin(rmin, smn[q]); }
+    double* s = a.inst_scal + (int64_t)b * 4;
+    double a_d, a_u;
+    if (a.kind == NEPTUNE_KIND_MIN_DELAY) { a_d = 1.0; a_u = 0.0; }
+    else if (a.kind == NEPTUNE_KIND_MIN_UTIL) { a_d = 0.0; a_u = 1.0; }
+    else { a_u = a.alpha / (double)N; a_d = (tw != 0.0 && wm != 0.0) ? (1.0 - a.alpha) / wm : 0.0; }
+    // one unit of CPU overload must cost more than any reroute that could remove it
+    double mu = (isfinite(rmin) ? 4.0 * (dmax + 1.0) / rmin : 1.0) * (a_d > 0.0 ? a_d : 1.0);
+    mu = fmax(mu, 100.0 * a_u);                  // closing a node never pays for an overload
+    s[0] = wm; s[1] = mu; s[2] = a_d; s[3] = a_u;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
+  const int chain = blockIdx.x, b = blockIdx.y, N = a.N, F = a.F;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const double* d = a.d + (int64_t)b * N * N;
+  const double* dT = a.dT + (int64_t)b * N * N;
+  const double* w = a.w + (int64_t)b * F * N;
+  const double* r = a.r + (int64_t)b * F * N;
+  const double* m = a.m + (int64_t)b * F;
+  const double* Mj = a.Mj + (int64_t)b * N;
+  const double* Kj = a.Kj + (int64_t)b * N;
+  const double* scal = a.inst_scal + (int64_t)b * 4;
+  const double mu = scal[1], a_d = scal[2], a_u = scal[3];
+  Chain k = carve(a.chain_ws + ((int64_t)b * a.chains + chain) * a.chain_stride, N, F);
+  extern __shared__ double dyn[];
+  double* delta = dyn + (int64_t)wid * N;          // per-warp load deltas
+  __shared__ double red[32];
+  __shared__ double wbest[8];
+  __shared__ Move wmove[8];
+  __shared__ Move mv;
+  __shared__ int n_pods;
+  __shared__ double best_total;
+  uint64_t rs = a.rng ^ (0x9E3779B97F4A7C15ull * (uint64_t)(chain + 1)) ^ (0xD1B54A32D192ED03ull * (uint64_t)(b + 1));
+  rng_next(rs);
+
+  // ---- start placement: a seed, or a rounding of the LP guide ----------------------------------------
+  const int seed_id = chain % a.S;
+  const uint8_t* seed = a.seeds + ((int64_t)b * a.S + seed_id) * F * N;
+  for (int q = tid; q < F * N; q += blockDim.x) k.c[q] = seed[q];
+  for (int q = tid; q < nw * N; q += blockDim.x) dyn[q] = 0.0;
+  __syncthreads();
+  if (a.guide && chain >= a.S && (chain / a.S) % 2 == 1 && tid == 0) {
+    // threshold rounding of c-bar, then memory repair (drop the weakest pods) and coverage repair
+    const double* g = a.guide + (int64_t)b * F * N;
+    const double thr = 0.15 + 0.1 * (double)((chain / a.S / 2) % 7);
+    for (int q = 0; q < F * N; ++q) k.c[q] = g[q] >= thr;
+    for (int j = 0; j < N; ++j) {
+      while (true) {
+        double mem = 0.0; int worst = -1; double wv = INFINITY;
+        for (int f = 0; f < F; ++f) if (k.c[(int64_t)f * N + j]) { mem += m[f]; if (g[(int64_t)f * N + j] < wv) { wv = g[(int64_t)f * N + j]; worst = f; } }
+        if (mem <= Mj[j] || worst < 0) break;
+        k.c[(int64_t)worst * N + j] = 0;
+      }
+    }
+    for (int f = 0; f < F; ++f) {
+      int any = 0; for (int j = 0; j < N; ++j) any |= k.c[(int64_t)f * N + j];
+      if (!any) {
+        int bj = -1; double bv = -1.0;
+        for (int j = 0; j < N; ++j) {
+          double mem = 0.0; for (int f2 = 0; f2 < F; ++f2) if (k.c[(int64_t)f2 * N + j]) mem += m[f2];
+          if (mem + m[f] <= Mj[j] && g[(int64_t)f * N + j] > bv) { bv = g[(int64_t)f * N + j]; bj = j; }
+        }
+        if (bj >= 0) k.c[(int64_t)f * N + bj] = 1;
+      }
+    }
+  }
+  __syncthreads();
+
+  auto rebuild = [&]() {
+    for (int f = 0; f < F; ++f) route_f(a, k, d, f);
+    __syncthreads();
+    node_state(a, k, w, r, m);
+    __syncthreads();
+  };
+  auto total_of = [&](const Cost& c) { return a_d * c.delay + a_u * c.util + mu * c.over; };
+
+  // random kick: `n` random swap / replace changes that keep memory feasible (thread 0)
+  auto kick = [&](int n) {
+    if (tid == 0) {
+      for (int t = 0; t < n; ++t) {
+        const int f = (int)(rng_next(rs) % (uint64_t)F);
+        int pods[64]; int np = 0;
+        for (int j = 0; j < N && np < 64; ++j) if (k.c[(int64_t)f * N + j]) pods[np++] = j;
+        const int jn = (int)(rng_next(rs) % (uint64_t)N);
+        if (k.c[(int64_t)f * N + jn]) continue;
+        double mem = 0.0; for (int f2 = 0; f2 < F; ++f2) if (k.c[(int64_t)f2 * N + jn]) mem += m[f2];
+        if (mem + m[f] > Mj[jn]) {
+          // replace a random function on jn by f, if that function has another pod
+          int cand[64]; int nc = 0;
+          for (int f2 = 0; f2 < F && nc < 64; ++f2) if (k.c[(int64_t)f2 * N + jn]) cand[nc++] = f2;
+          if (!nc) continue;
+          const int f2 = cand[rng_next(rs) % (uint64_t)nc];
+          int cnt2 = 0; for (int j = 0; j < N; ++j) cnt2 += k.c[(int64_t)f2 * N + j];
+          if (cnt2 < 2 || mem - m[f2] + m[f] > Mj[jn]) continue;
+          k.c[(int64_t)f2 * N + jn] = 0;
+        }
+        k.c[(int64_t)f * N + jn] = 1;
+        if (np > 1 && (rng_next(rs) & 1)) k.c[(int64_t)f * N + pods[rng_next(rs) % (uint64_t)np]] = 0;
+      }
+    }
+    __syncthreads();
+  };
+
+  if (chain >= a.S && !(a.guide && (chain / a.S) % 2 == 1)) kick(1 + (chain / a.S) % 6);
+  rebuild();
+  Cost cur = full_cost(a, k, w, Kj, red);
+  double cur_total = total_of(cur);
+  if (tid == 0) best_total = INFINITY;
+  __syncthreads();
+  auto save_best = [&]() {
+    // a chain's best must be usable: memory ok by construction, every function placed, no overload
+    bool covered = true;
+    for (int f = 0; f < F; ++f) covered = covered && (k.cntf[f] > 0);
+    const double t = (covered && cur.over <= 0.0) ? (a_d * cur.delay + a_u * cur.util) : INFINITY;
+    if (t < best_total) {
+      __syncthreads();
+      for (int q = tid; q < F * N; q += blockDim.x) k.best_c[q] = k.c[q];
+      if (tid == 0) best_total = t;
+    }
+    __syncthreads();
+  };
+  save_best();
+
+  int stall = 0;
+  for (int sweep = 0; sweep < a.sweeps; ++sweep) {
+    // ---- pod list -------------------------------------------------------------------------------------
+    if (tid == 0) n_pods = 0;
+    __syncthreads();
+    for (int q = tid; q < F * N; q += blockDim.x) if (k.c[q]) k.pods[atomicAdd(&n_pods, 1)] = q;
+    __syncthreads();
+    const int P = n_pods;
+    const int64_t n_add = (int64_t)F * N, n_drop = P, n_swap = (int64_t)P * N, n_rep = (int64_t)P * F;
+    const int64_t total = n_add + n_drop + n_swap + n_rep;
+    double my_best = -1e-9 * (1.0 + fabs(cur_total));      // only strictly improving moves
+    Move my_mv{MV_NONE, 0, 0, 0};
+    for (int64_t q = wid; q < total; q += nw) {
+      Move cand; bool ok = false; double dutil = 0.0;
+      if (q < n_add) {
+        const int f = (int)(q / N), j = (int)(q - (int64_t)f * N);
+        ok = !k.c[q] && k.mem[j] + m[f] <= Mj[j];
+        cand = Move{MV_ADD, f, j, -1};
+        if (ok && k.cntn[j] == 0) dutil = 1.0;
+      } else if (q < n_add + n_drop) {
+        const int pq = k.pods[q - n_add], f = pq / N, j = pq - f * N;
+        ok = k.cntf[f] >= 2;
+        cand = Move{MV_DROP, f, j, -1};
+        if (ok && k.cntn[j] == 1) dutil = -1.0;
+      } else if (q < n_add + n_drop + n_swap) {
+        const int64_t t = q - n_add - n_drop;
+        const int pq = k.pods[t / N], f = pq / N, j = pq - f * N, jn = (int)(t % N);
+        ok = !k.c[(int64_t)f * N + jn] && k.mem[jn] + m[f] <= Mj[jn];
+        cand = Move{MV_SWAP, f, j, jn};
+        if (ok) dutil = (k.cntn[jn] == 0 ? 1.0 : 0.0) - (k.cntn[j] == 1 ? 1.0 : 0.0);
+      } else {
+        const int64_t t = q - n_add - n_drop - n_swap;
+        const int pq = k.pods[t / F], f = pq / N, j = pq - f * N, fn = (int)(t % F);
+        ok = fn != f && !k.c[(int64_t)fn * N + j] && k.cntf[f] >= 2 && k.mem[j] - m[f] + m[fn] <= Mj[j];
+        cand = Move{MV_REPLACE, f, j, fn};
+      }
+      if (!ok) continue;
+      double dd = 0.0;
+      if (cand.type == MV_ADD) dd = eval_change(a, k, w, r, dT, cand.f, -1, cand.j, delta);
+      else if (cand.type == MV_DROP) dd = eval_change(a, k, w, r, dT, cand.f, cand.j, -1, delta);
+      else if (cand.type == MV_SWAP) dd = eval_change(a, k, w, r, dT, cand.f, cand.j, cand.t, delta);
+      else { dd = eval_change(a, k, w, r, dT, cand.f, cand.j, -1, delta);
+             dd += eval_change(a, k, w, r, dT, cand.t, -1, cand.j, delta); }
+      const double dov = eval_overload_delta(a, k, Kj, delta);
+      const double dt = a_d * dd + a_u * dutil + mu * dov;
+      if (dt < my_best) { my_best = dt; my_mv = cand; }
+    }
+    if (lane == 0) { wbest[wid] = my_best; wmove[wid] = my_mv; }
+    __syncthreads();
+    if (tid == 0) {
+      int bw = 0;
+      for (int q = 1; q < nw; ++q) if (wbest[q] < wbest[bw]) bw = q;
+      mv = wmove[bw];
+    }
+    __syncthreads();
+    if (mv.type != MV_NONE) {
+      // ---- apply, re-route the touched functions, refresh node state and the exact cost ----------------
+      if (tid == 0) {
+        if (mv.type == MV_ADD) k.c[(int64_t)mv.f * N + mv.j] = 1;
+        else if (mv.type == MV_DROP) k.c[(int64_t)mv.f * N + mv.j] = 0;
+        else if (mv.type == MV_SWAP) { k.c[(int64_t)mv.f * N + mv.j] = 0; k.c[(int64_t)mv.f * N + mv.t] = 1; }
+        else { k.c[(int64_t)mv.f * N + mv.j] = 0; k.c[(int64_t)mv.t * N + mv.j] = 1; }
+      }
+      __syncthreads();
+      route_f(a, k, d, mv.f);
+      if (mv.type == MV_REPLACE) route_f(a, k, d, mv.t);
+      __syncthreads();
+      node_state(a, k, w, r, m);
+      __syncthreads();
+      cur = full_cost(a, k, w, Kj, red);
+      cur_total = total_of(cur);
+      stall = 0;
+    } else {
+      // ---- local optimum: keep the best, restart from it with a kick -----------------------------------
+      save_best();
+      if (best_total < INFINITY) {
+        for (int q = tid; q < F * N; q += blockDim.x) k.c[q] = k.best_c[q];
+        __syncthreads();
+      }
+      ++stall;
+      kick(2 + (int)(rng_next(rs) % 4) + (stall > 8 ? 4 : 0));
+      rebuild();
+      cur = full_cost(a, k, w, Kj, red);
+      cur_total = total_of(cur);
+    }
+  }
+  save_best();
+  if (tid == 0) a.chain_cost[(int64_t)b * a.chains + chain] = best_total;
+}
+
+// pick the best chain per instance and publish its placement / objective
+__global__ void __launch_bounds__(256) k_ls_pick(LsArgs a, uint8_t* __restrict__ best_c, double* __restrict__ best_obj,
+                                                 int32_t* __restrict__ best_flags) {
+  const int b = blockIdx.x, N = a.N, F = a.F;
+  __shared__ int pick;
+  if (threadIdx.x == 0) {
+    int bi = -1; double bv = INFINITY;
+    for (int q = 0; q < a.chains; ++q) { const double v = a.chain_cost[(int64_t)b * a.chains + q]; if (v < bv) { bv = v; bi = q; } }
+    pick = bi;
+    best_obj[b] = bv;
+    best_flags[b] = bi >= 0 ? NEPTUNE_OK_ALL : 0;
+  }
+  __syncthreads();
+  const int src = pick >= 0 ? pick : 0;
+  Chain k = carve(a.chain_ws + ((int64_t)b * a.chains + src) * a.chain_stride, N, F);
+  const uint8_t* from = pick >= 0 ? k.best_c : k.c;
+  for (int q = threadIdx.x; q < F * N; q += blockDim.x) best_c[(int64_t)b * F * N + q] = from[q];
+}
+
+}  // namespace neptune
+
+using namespace neptune;
+
+extern "C" int neptune_local_search_workspace_bytes(int B, int N, int F, int chains, int64_t* bytes) {
+  if (B <= 0 || N <= 0 || F <= 0 || chains <= 0 || !bytes) return NEPTUNE_E_ARG;
+  int64_t t = (int64_t)B * N * N * 8 + 256;
+  t += (int64_t)B * 4 * 8 + 256;
+  t += (int64_t)B * chains * chain_bytes_h(N, F);
+  t += (int64_t)B * chains * 8 + 256;
+  *bytes = t;
+  return 0;
+}
+
+extern "C" int neptune_local_search(int B, int N, int F, int kind, double alpha, int chains, int sweeps,
+                                    uint64_t rng_seed, int S, const double* d, const double* w, const double* r,
+                                    const double* m, const double* Mj, const double* Kj, const double* maxd,
+                                    const double* cost, double budget, const double* old, const uint8_t* seeds,
+                                    const double* guide, uint8_t* best_c, double* best_obj, int32_t* best_flags,
+                                    void* workspace, int64_t workspace_bytes, void* stream) {
+  if (B <= 0 || N <= 0 || F <= 0 || kind < 0 || kind > 2 || chains <= 0 || sweeps < 0 || S <= 0)
+    return NEPTUNE_E_ARG;
+  if (!d || !w || !r || !m || !Mj || !Kj || !seeds || !best_c || !best_obj || !best_flags || !workspace)
+    return NEPTUNE_E_ARG;
+  int64_t need = 0;
+  neptune_local_search_workspace_bytes(B, N, F, chains, &need);
+  if (workspace_bytes < need) return NEPTUNE_E_NOMEM;
+  cudaStream_t s = (cudaStream_t)stream;
+  LsArgs a{};
+  a.N = N; a.F = F; a.kind = kind; a.chains = chains; a.sweeps = sweeps; a.S = S;
+  a.alpha = alpha; a.budget = budget; a.rng = rng_seed ? rng_seed : 0x1234567ull;
+  a.d = d; a.w = w; a.r = r; a.m = m; a.Mj = Mj; a.Kj = Kj; a.maxd = maxd; a.cost = cost; a.old = old;
+  a.seeds = seeds; a.guide = guide;
+  char* p = (char*)workspace;
+  a.dT = (double*)p; p += (((int64_t)B * N * N * 8 + 255) & ~(int64_t)255);
+  a.inst_scal = (double*)p; p += 256 * (((int64_t)B * 32 + 255) / 256);
+  a.chain_cost = (double*)p; p += (((int64_t)B * chains * 8 + 255) & ~(int64_t)255);
+  a.chain_ws = p;
+  a.chain_stride = chain_bytes_h(N, F);
+  if ((p - (char*)workspace) + (int64_t)B * chains * a.chain_stride > workspace_bytes) return NEPTUNE_E_NOMEM;
+  const size_t sm = (size_t)8 * N * 8;
+  if (sm > 200 * 1024) return NEPTUNE_E_SIZE;
+  NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_local_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_ls_prepare<<<B, 256, 0, s>>>(a);
+  k_local_search<<<dim3(chains, B), 256, sm, s>>>(a);
+  k_ls_pick<<<B, 256, 0, s>>>(a, best_c, best_obj, best_flags);
+  NEPTUNE_LAUNCH_OK();
+  return 0;
+}

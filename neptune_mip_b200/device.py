@@ -1,0 +1,315 @@
+"""Device-side plumbing: torch tensors for HBM + streams, ctypes calls into libneptune_b200.so.
+
+Everything numeric happens in the CUDA kernels behind the C ABI (`include/neptune_b200.h`); this
+module only allocates tensors, passes raw device pointers and checks return codes.  A missing
+library or GPU raises -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import KINDS, NeptuneError, PdhgParams, check
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise NeptuneError("neptune_mip_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@dataclass
+class InstanceBatch:
+    """B same-shaped placement instances resident in HBM (float64, row-major, leading dim B)."""
+    B: int
+    N: int
+    F: int
+    d: torch.Tensor        # [B,N,N]
+    w: torch.Tensor        # [B,F,N]
+    r: torch.Tensor        # [B,F,N]
+    m: torch.Tensor        # [B,F]
+    Mj: torch.Tensor       # [B,N]
+    Kj: torch.Tensor       # [B,N]
+    old: torch.Tensor      # [B,F,N]
+    maxd: torch.Tensor     # [B,F]
+    cost: torch.Tensor     # [B,N]
+    budget: float
+
+    FIELDS = ("d", "w", "r", "m", "Mj", "Kj", "old", "maxd", "cost")
+
+    @staticmethod
+    def host_arrays(datas: Sequence) -> dict:
+        """Stack the `Data` fields the kernels read into float64 numpy arrays (host)."""
+        def stack(attr):
+            return np.ascontiguousarray(np.stack([np.asarray(getattr(x, attr), dtype=np.float64) for x in datas]))
+        N, F = len(datas[0].nodes), len(datas[0].functions)
+        for x in datas:
+            if len(x.nodes) != N or len(x.functions) != F:
+                raise ValueError("a batch must hold same-shaped instances")
+        budgets = {float(x.node_budget) for x in datas}
+        if len(budgets) != 1:
+            raise ValueError("a batch must share node_budget")
+        return dict(N=N, F=F, B=len(datas), budget=budgets.pop(),
+                    d=stack("node_delay_matrix").reshape(len(datas), N, N),
+                    w=stack("workload_matrix").reshape(len(datas), F, N),
+                    r=stack("core_per_req_matrix").reshape(len(datas), F, N),
+                    m=stack("function_memory_matrix").reshape(len(datas), F),
+                    Mj=stack("node_memory_matrix").reshape(len(datas), N),
+                    Kj=stack("node_cores_matrix").reshape(len(datas), N),
+                    old=stack("old_allocations_matrix").reshape(len(datas), F, N),
+                    maxd=stack("max_delay_matrix").reshape(len(datas), F),
+                    cost=stack("node_costs").reshape(len(datas), N))
+
+    @classmethod
+    def from_host(cls, h: dict, device="cuda", pinned: Optional[dict] = None) -> "InstanceBatch":
+        """H2D copy (from pinned staging buffers when given) on the current stream."""
+        _require_cuda()
+        kw = {}
+        for k in cls.FIELDS:
+            src = torch.from_numpy(h[k])
+            if pinned is not None:
+                pinned[k].copy_(src)
+                src = pinned[k]
+            kw[k] = src.to(device, non_blocking=True)
+        return cls(B=h["B"], N=h["N"], F=h["F"], budget=h["budget"], **kw)
+
+    @classmethod
+    def from_datas(cls, datas: Sequence, device="cuda") -> "InstanceBatch":
+        return cls.from_host(cls.host_arrays(datas), device)
+
+    def h2d_bytes(self) -> int:
+        return sum(getattr(self, k).numel() * 8 for k in self.FIELDS)
+
+    def inst_ptrs(self):
+        """(d, w, r, m, Mj, Kj, maxd, cost, budget) in the order the C ABI takes them."""
+        return [_ptr(self.d), _ptr(self.w), _ptr(self.r), _ptr(self.m), _ptr(self.Mj), _ptr(self.Kj),
+                _ptr(self.maxd), _ptr(self.cost), C.c_double(self.budget)]
+
+
+@dataclass
+class Model:
+    """Assembled LP/MIP model of a batch: shared CSR pattern (+ transpose) and per-instance values."""
+    B: int
+    N: int
+    F: int
+    kind: int
+    flags: int
+    rows: int
+    cols: int
+    nnz: int
+    row_ptr: torch.Tensor
+    col_idx: torch.Tensor
+    rowT_ptr: torch.Tensor
+    colT_idx: torch.Tensor
+    val: torch.Tensor
+    valT: torch.Tensor
+    obj: torch.Tensor
+    lo: torch.Tensor
+    hi: torch.Tensor
+    col_lb: torch.Tensor
+    col_ub: torch.Tensor
+    col_int: torch.Tensor
+    wmax: torch.Tensor
+
+
+def model_sizes(N, F, kind, flags=0):
+    lib = _lib.load()
+    rows, cols, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+    check(lib.neptune_model_sizes(N, F, kind, flags, C.byref(rows), C.byref(cols), C.byref(nnz)),
+          "neptune_model_sizes")
+    return rows.value, cols.value, nnz.value
+
+
+def assemble(inst: InstanceBatch, kind, alpha=0.5, flags=0, with_transpose=True) -> Model:
+    _require_cuda()
+    lib = _lib.load()
+    kind = KINDS.get(kind, kind)
+    rows, cols, nnz = model_sizes(inst.N, inst.F, kind, flags)
+    dev = inst.d.device
+    B = inst.B
+    f64 = dict(dtype=torch.float64, device=dev)
+    row_ptr = torch.empty(rows + 1, dtype=torch.int64, device=dev)
+    col_idx = torch.empty(nnz, dtype=torch.int32, device=dev)
+    rowT_ptr = torch.empty(cols + 1, dtype=torch.int64, device=dev) if with_transpose else None
+    colT_idx = torch.empty(nnz, dtype=torch.int32, device=dev) if with_transpose else None
+    val = torch.empty((B, nnz), **f64)
+    valT = torch.empty((B, nnz), **f64) if with_transpose else None
+    obj = torch.empty((B, cols), **f64)
+    lo = torch.empty((B, rows), **f64)
+    hi = torch.empty((B, rows), **f64)
+    col_lb = torch.empty((B, cols), **f64)
+    col_ub = torch.empty((B, cols), **f64)
+    col_int = torch.empty(cols, dtype=torch.uint8, device=dev)
+    wmax = torch.zeros(B, **f64)
+    check(lib.neptune_assemble_pattern(inst.N, inst.F, kind, flags, _ptr(row_ptr), _ptr(col_idx),
+                                       _ptr(rowT_ptr), _ptr(colT_idx), _stream()), "neptune_assemble_pattern")
+    check(lib.neptune_assemble_values(B, inst.N, inst.F, kind, flags, C.c_double(alpha), *inst.inst_ptrs(),
+                                      _ptr(val), _ptr(valT), _ptr(obj), _ptr(lo), _ptr(hi), _ptr(col_lb),
+                                      _ptr(col_ub), _ptr(col_int), _ptr(wmax), _stream()),
+          "neptune_assemble_values")
+    return Model(B, inst.N, inst.F, kind, flags, rows, cols, nnz, row_ptr, col_idx, rowT_ptr, colT_idx,
+                 val, valT, obj, lo, hi, col_lb, col_ub, col_int, wmax)
+
+
+def spmv(mdl: Model, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((mdl.B, mdl.rows), dtype=torch.float64, device=x.device)
+    check(lib.neptune_spmv(mdl.B, mdl.rows, mdl.cols, _ptr(mdl.row_ptr), _ptr(mdl.col_idx), _ptr(mdl.val),
+                           _ptr(x), _ptr(out), _stream()), "neptune_spmv")
+    return out
+
+
+def spmv_t(mdl: Model, y: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((mdl.B, mdl.cols), dtype=torch.float64, device=y.device)
+    check(lib.neptune_spmv_t(mdl.B, mdl.rows, mdl.cols, _ptr(mdl.rowT_ptr), _ptr(mdl.colT_idx), _ptr(mdl.valT),
+                             _ptr(y), _ptr(out), _stream()), "neptune_spmv_t")
+    return out
+
+
+_PDHG_DTYPE = np.dtype([("primal_obj", "f8"), ("dual_obj", "f8"), ("primal_res", "f8"), ("dual_res", "f8"),
+                        ("gap", "f8"), ("step", "f8"), ("primal_weight", "f8"), ("iters", "i4"),
+                        ("restarts", "i4"), ("converged", "i4"), ("pad", "i4")])
+
+
+def pdhg_solve(mdl: Model, max_iters=20000, check_every=64, eps_rel=1e-6, eps_abs=1e-8, ruiz_iters=10,
+               x0: Optional[torch.Tensor] = None, y0: Optional[torch.Tensor] = None, workspace=None):
+    """Returns (x[B,cols], y[B,rows], results: numpy structured array of length B)."""
+    lib = _lib.load()
+    dev = mdl.val.device
+    x = torch.zeros((mdl.B, mdl.cols), dtype=torch.float64, device=dev) if x0 is None else x0
+    y = torch.zeros((mdl.B, mdl.rows), dtype=torch.float64, device=dev) if y0 is None else y0
+    need = C.c_int64()
+    check(lib.neptune_pdhg_workspace_bytes(mdl.B, mdl.rows, mdl.cols, mdl.nnz, C.byref(need)),
+          "neptune_pdhg_workspace_bytes")
+    if workspace is None or workspace.numel() < need.value:
+        workspace = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    res = torch.zeros(mdl.B * _PDHG_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    prm = PdhgParams(max_iters, check_every, ruiz_iters, 0, eps_rel, eps_abs)
+    check(lib.neptune_pdhg_solve(mdl.B, mdl.rows, mdl.cols, mdl.nnz, _ptr(mdl.row_ptr), _ptr(mdl.col_idx),
+                                 _ptr(mdl.val), _ptr(mdl.rowT_ptr), _ptr(mdl.colT_idx), _ptr(mdl.valT),
+                                 _ptr(mdl.obj), _ptr(mdl.lo), _ptr(mdl.hi), _ptr(mdl.col_lb), _ptr(mdl.col_ub),
+                                 C.byref(prm), _ptr(x), _ptr(y), _ptr(res), _ptr(workspace),
+                                 workspace.numel(), _stream()), "neptune_pdhg_solve")
+    out = np.frombuffer(res.cpu().numpy().tobytes(), dtype=_PDHG_DTYPE)
+    return x, y, out
+
+
+def check_solution(inst: InstanceBatch, x: torch.Tensor, c: torch.Tensor, n: torch.Tensor, alpha=0.5):
+    """The reference's six checkers + three scorers.  x[B,N,F,N], c[B,F,N], n[B,N] float64 on device.
+    Returns (flags int32[B], scores float64[B,3]) as device tensors."""
+    lib = _lib.load()
+    dev = inst.d.device
+    flags = torch.empty(inst.B, dtype=torch.int32, device=dev)
+    scores = torch.empty((inst.B, 3), dtype=torch.float64, device=dev)
+    check(lib.neptune_check_solution(inst.B, inst.N, inst.F, C.c_double(alpha), *inst.inst_ptrs(),
+                                     _ptr(x), _ptr(c), _ptr(n), _ptr(flags), _ptr(scores), _stream()),
+          "neptune_check_solution")
+    return flags, scores
+
+
+def route_placements(inst: InstanceBatch, c_u8: torch.Tensor):
+    """c[B,F,N] uint8 -> (x[B,N,F,N], n[B,N]) float64 by the nearest-open-pod rule."""
+    lib = _lib.load()
+    dev = inst.d.device
+    x = torch.empty((inst.B, inst.N, inst.F, inst.N), dtype=torch.float64, device=dev)
+    n = torch.empty((inst.B, inst.N), dtype=torch.float64, device=dev)
+    check(lib.neptune_route_placements(inst.B, inst.N, inst.F, _ptr(inst.d), _ptr(c_u8), _ptr(x), _ptr(n),
+                                       _stream()), "neptune_route_placements")
+    return x, n
+
+
+def eval_placements(inst: InstanceBatch, c_u8: torch.Tensor, alpha=0.5):
+    """c[B,P,F,N] uint8 -> (obj[B,P,3], flags[B,P], overload[B,P])."""
+    lib = _lib.load()
+    dev = inst.d.device
+    P = c_u8.shape[1]
+    obj = torch.empty((inst.B, P, 3), dtype=torch.float64, device=dev)
+    flags = torch.empty((inst.B, P), dtype=torch.int32, device=dev)
+    over = torch.empty((inst.B, P), dtype=torch.float64, device=dev)
+    check(lib.neptune_eval_placements(inst.B, P, inst.N, inst.F, C.c_double(alpha), *inst.inst_ptrs(),
+                                      _ptr(c_u8), _ptr(obj), _ptr(flags), _ptr(over), _stream()),
+          "neptune_eval_placements")
+    return obj, flags, over
+
+
+def efttc(inst: InstanceBatch, kind, alpha=0.5, workspace=None):
+    """GPU EFTTC.  Returns (c uint8[B,F,N], n uint8[B,N], info int32[B,4])."""
+    lib = _lib.load()
+    kind = KINDS.get(kind, kind)
+    dev = inst.d.device
+    need = C.c_int64()
+    check(lib.neptune_efttc_workspace_bytes(inst.B, inst.N, inst.F, C.byref(need)), "neptune_efttc_workspace_bytes")
+    if workspace is None or workspace.numel() < need.value:
+        workspace = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    c = torch.empty((inst.B, inst.F, inst.N), dtype=torch.uint8, device=dev)
+    n = torch.empty((inst.B, inst.N), dtype=torch.uint8, device=dev)
+    info = torch.empty((inst.B, 4), dtype=torch.int32, device=dev)
+    check(lib.neptune_efttc(inst.B, inst.N, inst.F, kind, C.c_double(alpha), _ptr(inst.d), _ptr(inst.w),
+                            _ptr(inst.r), _ptr(inst.m), _ptr(inst.Mj), _ptr(inst.Kj), _ptr(inst.old),
+                            _ptr(inst.cost), C.c_double(inst.budget), _ptr(c), _ptr(n), _ptr(info),
+                            _ptr(workspace), workspace.numel(), _stream()), "neptune_efttc")
+    return c, n, info
+
+
+def u8_to_f64(t: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty(t.shape, dtype=torch.float64, device=t.device)
+    check(lib.neptune_u8_to_f64(t.numel(), _ptr(t), _ptr(out), _stream()), "neptune_u8_to_f64")
+    return out
+
+
+def efttc_host(h: dict, kind, alpha=0.5):
+    """Host-buffer entry point (`neptune_efttc_host`): numpy in, numpy out, copies inside the call."""
+    _require_cuda()
+    lib = _lib.load()
+    kind = KINDS.get(kind, kind)
+    B, N, F = h["B"], h["N"], h["F"]
+    c = np.empty((B, F, N), dtype=np.uint8)
+    n = np.empty((B, N), dtype=np.uint8)
+    info = np.empty((B, 4), dtype=np.int32)
+    flags = np.empty(B, dtype=np.int32)
+    scores = np.empty((B, 3), dtype=np.float64)
+    hp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    check(lib.neptune_efttc_host(B, N, F, kind, C.c_double(alpha), hp(h["d"]), hp(h["w"]), hp(h["r"]),
+                                 hp(h["m"]), hp(h["Mj"]), hp(h["Kj"]), hp(h["old"]), hp(h["maxd"]),
+                                 hp(h["cost"]), C.c_double(h["budget"]), hp(c), hp(n), hp(info), hp(flags),
+                                 hp(scores), _stream()), "neptune_efttc_host")
+    return c, n, info, flags, scores
+
+
+def local_search(inst: InstanceBatch, kind, seeds_u8: torch.Tensor, alpha=0.5, chains=296, sweeps=400,
+                 rng_seed=1, guide: Optional[torch.Tensor] = None, workspace=None):
+    """Batched add/drop/swap/replace search.  seeds_u8[B,S,F,N] uint8 -> (best_c uint8[B,F,N],
+    best_obj float64[B], best_flags int32[B]); best_obj is +inf where no chain found a feasible placement."""
+    lib = _lib.load()
+    kind = KINDS.get(kind, kind)
+    dev = inst.d.device
+    S = seeds_u8.shape[1]
+    need = C.c_int64()
+    check(lib.neptune_local_search_workspace_bytes(inst.B, inst.N, inst.F, chains, C.byref(need)),
+          "neptune_local_search_workspace_bytes")
+    if workspace is None or workspace.numel() < need.value:
+        workspace = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    best_c = torch.empty((inst.B, inst.F, inst.N), dtype=torch.uint8, device=dev)
+    best_obj = torch.empty(inst.B, dtype=torch.float64, device=dev)
+    best_flags = torch.empty(inst.B, dtype=torch.int32, device=dev)
+    check(lib.neptune_local_search(inst.B, inst.N, inst.F, kind, C.c_double(alpha), chains, sweeps,
+                                   C.c_uint64(rng_seed), S, *inst.inst_ptrs(), _ptr(inst.old), _ptr(seeds_u8),
+                                   _ptr(guide), _ptr(best_c), _ptr(best_obj), _ptr(best_flags),
+                                   _ptr(workspace), workspace.numel(), _stream()), "neptune_local_search")
+    return best_c, best_obj, best_flags

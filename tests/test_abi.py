@@ -1,0 +1,55 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/neptune_b200.h declares."""
+import ctypes
+import os
+import re
+
+from neptune_mip_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "neptune_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\bint\s+(neptune_\w+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert header_functions() == _lib.declared_symbols()
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in header_functions():
+        assert hasattr(lib, name), name
+    assert _lib.load().neptune_abi_version() == 1
+
+
+def test_model_sizes_without_gpu():
+    """Pure host arithmetic of the ABI (no kernel launch): the SURVEY.md section 8 size table."""
+    lib = _lib.load()
+    r, c, z = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    table = {(3, 2): (24, 24, 90), (50, 10): (1600, 25500, 101500), (500, 50): (76000, 12525000, 50075000),
+             (2000, 200): (1204000, 800400000, 3201200000), (20, 5): (340, 2100, 8300)}
+    for (N, F), want in table.items():
+        assert lib.neptune_model_sizes(N, F, 0, 0, ctypes.byref(r), ctypes.byref(c), ctypes.byref(z)) == 0
+        assert (r.value, c.value, z.value) == want
+    assert lib.neptune_model_sizes(3, 2, 2, 0, ctypes.byref(r), ctypes.byref(c), ctypes.byref(z)) == 0
+    assert (r.value, c.value, z.value) == (33, 27, 111)
+    assert lib.neptune_model_sizes(0, 2, 0, 0, None, None, None) == -1
+    assert lib.neptune_model_sizes(3, 2, 7, 0, None, None, None) == -1
+    # 4000 x 400 would need > 2^31 columns: refused, not truncated
+    assert lib.neptune_model_sizes(4000, 400, 0, 0, None, None, None) == -2
+
+
+def test_no_cpu_fallback_without_gpu():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from neptune_mip_b200 import device, synth
+    from neptune_mip_b200.core.utils import data_to_solver_input
+    data = data_to_solver_input(synth.test_py_payload(), 1, with_db=False)
+    with pytest.raises(_lib.NeptuneError):
+        device.InstanceBatch.from_datas([data])
