@@ -196,6 +196,10 @@ int neptune_efttc_workspace_bytes(int B, int N, int F, int64_t* bytes);
 /* small helper: out[k] = in[k] ? 1.0 : 0.0 (placements travel as uint8, the checkers read float64) */
 int neptune_u8_to_f64(int64_t n, const uint8_t* in, double* out, void* stream);
 
+/* number of kernels this library launched since the last reset (host-side counter; bench.py's
+ * `gpu_launches`) */
+int neptune_launch_count(int64_t* count, int reset);
+
 /* ---- host-buffer convenience (the e2e path of bench.py) -----------------------------------------
  * Same as neptune_efttc + neptune_route_placements + neptune_check_solution but with HOST
  * buffers: copies inputs H2D, runs on `stream`, copies c/n/flags/scores D2H and synchronises. */

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "neptune_efttc": [_i, _i, _i, _i, _d] + [_p] * 8 + [_d] + [_p] * 3 + [_p, _i64, _p],
     "neptune_efttc_workspace_bytes": [_i, _i, _i, C.POINTER(_i64)],
     "neptune_u8_to_f64": [_i64, _p, _p, _p],
+    "neptune_launch_count": [C.POINTER(_i64), _i],
     "neptune_efttc_host": [_i, _i, _i, _i, _d] + [_p] * 9 + [_d] + [_p] * 5 + [_p],
 }
 

@@ -1,0 +1,68 @@
+"""Batched solve path: B same-shaped instances through assembly -> PDHG -> EFTTC -> local search ->
+exact check in one go (what bench.py times, and what a sweep like BASELINE.json's config 5 calls)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import device
+from ._lib import FLAG_STRENGTHEN, KINDS
+
+
+@dataclass
+class BatchParams:
+    kind: str = "min_delay"
+    alpha: float = 0.5
+    lp_iters: int = 2048          # PDHG iterations on the strengthened relaxation (bound + rounding guide)
+    lp_check_every: int = 256
+    chains: int = 16              # local-search chains per instance
+    sweeps: int = 200
+    rng_seed: int = 1
+
+
+@dataclass
+class BatchResult:
+    c: torch.Tensor               # uint8 [B,F,N]
+    x: torch.Tensor               # float64 [B,N,F,N]
+    n: torch.Tensor               # float64 [B,N]
+    flags: torch.Tensor           # int32 [B]
+    scores: torch.Tensor          # float64 [B,3]
+    lp: Optional[np.ndarray]      # PDHG result records (primal/dual objective, residuals, iterations)
+    pdhg_ms: float = 0.0          # device time of the PDHG call (CUDA events on the launch stream)
+    pdhg_iters: int = 0
+    model_dims: tuple = (0, 0, 0)
+
+
+def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = False) -> BatchResult:
+    kind = prm.kind
+    lp_res, guide, pdhg_ms, iters, dims = None, None, 0.0, 0, (0, 0, 0)
+    if prm.lp_iters > 0:
+        lp = device.assemble(inst, kind, prm.alpha, flags=FLAG_STRENGTHEN)
+        dims = (lp.rows, lp.cols, lp.nnz)
+        if time_pdhg:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        xs, ys, lp_res = device.pdhg_solve(lp, max_iters=prm.lp_iters, check_every=prm.lp_check_every,
+                                           eps_rel=1e-6, eps_abs=1e-9)
+        if time_pdhg:
+            e1.record()
+            e1.synchronize()
+            pdhg_ms = e0.elapsed_time(e1)
+        iters = int(lp_res["iters"].max())
+        X = inst.F * inst.N * inst.N
+        guide = xs[:, X:X + inst.F * inst.N].contiguous()
+        del lp, xs, ys
+    seeds = torch.stack([device.efttc(inst, k, prm.alpha)[0] for k in ("min_delay", "min_util", "min_delay_util")],
+                        dim=1).contiguous()
+    best_c, best_obj, _ = device.local_search(inst, kind, seeds, prm.alpha, prm.chains, prm.sweeps,
+                                              prm.rng_seed, guide)
+    fallback = seeds[:, KINDS[kind]]
+    bad = ~torch.isfinite(best_obj)
+    if bool(bad.any()):
+        best_c[bad] = fallback[bad]
+    x, n = device.route_placements(inst, best_c)
+    flags, scores = device.check_solution(inst, x, device.u8_to_f64(best_c), n, prm.alpha)
+    return BatchResult(best_c, x, n, flags, scores, lp_res, pdhg_ms, iters, dims)

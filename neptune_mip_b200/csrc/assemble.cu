@@ -302,9 +302,9 @@ extern "C" int neptune_assemble_pattern(int N, int F, int kind, int flags, int64
   if (rc) return rc;
   Layout L(N, F, kind, flags);
   cudaStream_t s = (cudaStream_t)stream;
-  if (col_idx) k_pattern_csr<<<grid_for(L.nnz), 256, 0, s>>>(L, col_idx);
-  if (row_ptr) k_pattern_rowptr<<<grid_for(L.rows + 1), 256, 0, s>>>(L, row_ptr);
-  if (rowT_ptr || colT_idx) k_pattern_T<<<grid_for(L.cols + 1), 256, 0, s>>>(L, rowT_ptr, colT_idx);
+  if (col_idx) { k_pattern_csr<<<grid_for(L.nnz), 256, 0, s>>>(L, col_idx); NEPTUNE_COUNT(1); }
+  if (row_ptr) { k_pattern_rowptr<<<grid_for(L.rows + 1), 256, 0, s>>>(L, row_ptr); NEPTUNE_COUNT(1); }
+  if (rowT_ptr || colT_idx) { k_pattern_T<<<grid_for(L.cols + 1), 256, 0, s>>>(L, rowT_ptr, colT_idx); NEPTUNE_COUNT(1); }
   NEPTUNE_LAUNCH_OK();
   return 0;
 }
@@ -330,14 +330,14 @@ extern "C" int neptune_assemble_values(int B, int N, int F, int kind, int flags,
     if (!scratch) return NEPTUNE_E_ARG;
     if ((int64_t)F * N > L.nnz) return NEPTUNE_E_ARG;
     // terms for instance b live at scratch + b*F*N  (F*N <= nnz, so they fit in [B][nnz])
-    k_wmax<<<B, 256, 0, s>>>(N, F, in, scratch, wmax);
-    k_wmax_zero_if_no_workload<<<B, 256, 0, s>>>(N, F, w, wmax);
+    { k_wmax<<<B, 256, 0, s>>>(N, F, in, scratch, wmax); NEPTUNE_COUNT(1); }
+    { k_wmax_zero_if_no_workload<<<B, 256, 0, s>>>(N, F, w, wmax); NEPTUNE_COUNT(1); }
   }
   dim3 gc(grid_for(L.cols), B), gr(grid_for(L.rows), B), ge(grid_for(L.nnz), B);
   if (valT || obj || col_lb || col_ub || col_int)
-    k_values_cols<<<gc, 256, 0, s>>>(L, in, wmax, valT, obj, col_lb, col_ub, col_int);
-  if (lo || hi) k_values_rows<<<gr, 256, 0, s>>>(L, in, lo, hi);
-  if (val) k_values_csr<<<ge, 256, 0, s>>>(L, in, val);
+    { k_values_cols<<<gc, 256, 0, s>>>(L, in, wmax, valT, obj, col_lb, col_ub, col_int); NEPTUNE_COUNT(1); }
+  if (lo || hi) { k_values_rows<<<gr, 256, 0, s>>>(L, in, lo, hi); NEPTUNE_COUNT(1); }
+  if (val) { k_values_csr<<<ge, 256, 0, s>>>(L, in, val); NEPTUNE_COUNT(1); }
   NEPTUNE_LAUNCH_OK();
   return 0;
 }

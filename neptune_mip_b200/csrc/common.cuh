@@ -16,6 +16,9 @@
     if (_e != cudaSuccess) return (int)_e;            \
   } while (0)
 
+extern "C" void neptune_count_launches(long long n);   // bench bookkeeping (host-side atomic)
+#define NEPTUNE_COUNT(n) neptune_count_launches((long long)(n))
+
 namespace neptune {
 
 constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs

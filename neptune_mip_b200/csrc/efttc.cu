@@ -401,7 +401,7 @@ extern "C" int neptune_efttc(int B, int N, int F, int kind, double alpha, const 
   const size_t sm = (size_t)(3 * N + F + 5 * (F + N) + 1) * 4 + (size_t)(F + N) + 16;
   if (sm > 200 * 1024) return NEPTUNE_E_SIZE;
   NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_efttc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  k_efttc<<<B, 256, sm, (cudaStream_t)stream>>>(a, per, (char*)workspace);
+  { k_efttc<<<B, 256, sm, (cudaStream_t)stream>>>(a, per, (char*)workspace); NEPTUNE_COUNT(1); }
   NEPTUNE_LAUNCH_OK();
   return 0;
 }

@@ -292,13 +292,13 @@ extern "C" int neptune_check_solution(int B, int N, int F, double alpha, const d
   double* scratch = nullptr;
   NEPTUNE_CUDA_OK(cudaMallocAsync(&scratch, (size_t)B * kScr * 8, s));
   Inst in{N, F, d, w, r, m, Mj, Kj, maxd, cost, budget, alpha};
-  k_check_pre<<<B, 256, 0, s>>>(in, scratch, flags_out);
+  { k_check_pre<<<B, 256, 0, s>>>(in, scratch, flags_out); NEPTUNE_COUNT(1); }
   int64_t work = (int64_t)N * F * N;
   int gx = (int)((work + 255) / 256);
   if (gx > kNumSMs * 8) gx = kNumSMs * 8;
   if (gx < 1) gx = 1;
-  k_check<<<dim3(gx, B), 256, 0, s>>>(in, x, c, n, scratch, flags_out);
-  k_check_fin<<<(B + 127) / 128, 128, 0, s>>>(B, N, alpha, scratch, scores_out);
+  { k_check<<<dim3(gx, B), 256, 0, s>>>(in, x, c, n, scratch, flags_out); NEPTUNE_COUNT(1); }
+  { k_check_fin<<<(B + 127) / 128, 128, 0, s>>>(B, N, alpha, scratch, scores_out); NEPTUNE_COUNT(1); }
   NEPTUNE_LAUNCH_OK();
   NEPTUNE_CUDA_OK(cudaFreeAsync(scratch, s));
   return 0;
@@ -307,7 +307,7 @@ extern "C" int neptune_check_solution(int B, int N, int F, double alpha, const d
 extern "C" int neptune_route_placements(int B, int N, int F, const double* d, const uint8_t* c, double* x,
                                         double* n, void* stream) {
   if (B <= 0 || N <= 0 || F <= 0 || !d || !c || !x) return NEPTUNE_E_ARG;
-  k_route<<<dim3(F, B), 256, 0, (cudaStream_t)stream>>>(N, F, d, c, x, n);
+  { k_route<<<dim3(F, B), 256, 0, (cudaStream_t)stream>>>(N, F, d, c, x, n); NEPTUNE_COUNT(1); }
   NEPTUNE_LAUNCH_OK();
   return 0;
 }
@@ -326,9 +326,9 @@ extern "C" int neptune_eval_placements(int B, int P, int N, int F, double alpha,
   NEPTUNE_CUDA_OK(cudaMallocAsync(&scratch, (size_t)B * kScr * 8, s));
   NEPTUNE_CUDA_OK(cudaMallocAsync(&dummy, (size_t)B * 4, s));
   Inst in{N, F, d, w, r, m, Mj, Kj, maxd, cost, budget, alpha};
-  k_check_pre<<<B, 256, 0, s>>>(in, scratch, dummy);
+  { k_check_pre<<<B, 256, 0, s>>>(in, scratch, dummy); NEPTUNE_COUNT(1); }
   size_t sm = (size_t)N * (8 + 8 + 4);
-  k_eval<<<dim3(P, B), 256, sm, s>>>(in, P, c, scratch, obj_out, flags_out, overload_out);
+  { k_eval<<<dim3(P, B), 256, sm, s>>>(in, P, c, scratch, obj_out, flags_out, overload_out); NEPTUNE_COUNT(1); }
   NEPTUNE_LAUNCH_OK();
   NEPTUNE_CUDA_OK(cudaFreeAsync(scratch, s));
   NEPTUNE_CUDA_OK(cudaFreeAsync(dummy, s));

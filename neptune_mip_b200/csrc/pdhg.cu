@@ -21,6 +21,7 @@ namespace neptune {
 
 constexpr int kLongRow = 2048;      // rows longer than this get a whole block
 constexpr int kShortCol = 8;        // columns of A^T up to this length: one thread each
+constexpr int kShortRow = 8;        // rows of A up to this length (whole 32-row chunk): one thread each
 constexpr int kMaxLongList = 1 << 20;
 
 enum Acc { PRES2 = 0, DRES2, POBJ, DOBJ, NACC_PER = 4 };
@@ -44,6 +45,12 @@ struct Csr {
 // ---------------------------------------------------------------------------------------------------
 // SpMV cores.  `Epi` consumes one (instance, row, dot) at a time in the thread that owns it.
 // ---------------------------------------------------------------------------------------------------
+// Rows are taken in chunks of 32 consecutive rows per warp.  A chunk whose longest row has at most
+// kShortRow entries (C6, the S rows of the strengthened model, ...) runs one THREAD per row -- 32 rows
+// in flight per warp, and because neighbouring rows sit next to each other in the CSR arrays the
+// loads of the warp still cover contiguous memory.  Otherwise the warp walks the 32 rows one by one
+// with its lanes striding over the row (coalesced 128 B / 256 B segments of col_idx / val, 4 loads in
+// flight per lane) and a shuffle reduction.
 template <class Epi>
 __global__ void __launch_bounds__(256) k_rows_warp(Csr A, const double* __restrict__ xv, Epi epi) {
   const int b = blockIdx.y;
@@ -54,22 +61,64 @@ __global__ void __launch_bounds__(256) k_rows_warp(Csr A, const double* __restri
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t row = warp0; row < A.n_rows; row += nwarps) {
-    const int64_t p0 = A.ptr[row], p1 = A.ptr[row + 1];
-    if (p1 - p0 > kLongRow) continue;                 // handled by k_rows_long
-    double acc = 0.0;
-    int64_t p = p0 + lane;
-    // 4 independent loads in flight per lane
-    for (; p + 96 < p1; p += 128) {
-      int c0 = __ldcs(A.idx + p), c1 = __ldcs(A.idx + p + 32), c2 = __ldcs(A.idx + p + 64),
-          c3 = __ldcs(A.idx + p + 96);
-      double v0 = __ldcs(val + p), v1 = __ldcs(val + p + 32), v2 = __ldcs(val + p + 64),
-             v3 = __ldcs(val + p + 96);
-      acc += v0 * x[c0]; acc += v1 * x[c1]; acc += v2 * x[c2]; acc += v3 * x[c3];
+  const int64_t nchunks = (A.n_rows + 31) >> 5;
+  for (int64_t ch = warp0; ch < nchunks; ch += nwarps) {
+    const int64_t myrow = (ch << 5) + lane;
+    int64_t q0 = 0, q1 = 0;
+    if (myrow < A.n_rows) { q0 = A.ptr[myrow]; q1 = A.ptr[myrow + 1]; }
+    const int mylen = (int)(q1 - q0);
+    int maxlen = mylen;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    if (maxlen <= kShortRow) {
+      if (myrow < A.n_rows) {
+        double acc = 0.0;
+        if (mylen == 2 && (q0 & 1) == 0) {
+          const int2 c = __ldcs(reinterpret_cast<const int2*>(A.idx + q0));
+          const double2 v = __ldcs(reinterpret_cast<const double2*>(val + q0));
+          acc = v.x * x[c.x];
+          acc += v.y * x[c.y];
+        } else {
+          for (int64_t p = q0; p < q1; ++p) acc += __ldcs(val + p) * x[__ldcs(A.idx + p)];
+        }
+        epi.row(b, myrow, acc * xs);
+      }
+      continue;
     }
-    for (; p < p1; p += 32) acc += __ldcs(val + p) * x[__ldcs(A.idx + p)];
-    acc = warp_sum(acc);
-    if (lane == 0) epi.row(b, row, acc * xs);
+    // Row-by-row over the chunk, two rows in flight; lane k keeps the dot product of row k so that the
+    // epilogue (vector update: 4 reads + 2 writes per row) runs ONCE per chunk with all lanes busy and
+    // coalesced, instead of 32 times in a single lane.
+    const int nr = (int)min((int64_t)32, A.n_rows - (ch << 5));
+    double myres = 0.0;
+    for (int k = 0; k < nr; k += 2) {
+      const int64_t p0a = __shfl_sync(0xffffffffu, q0, k), p1a = __shfl_sync(0xffffffffu, q1, k);
+      const int kb = (k + 1 < nr) ? k + 1 : k;
+      const int64_t p0b = __shfl_sync(0xffffffffu, q0, kb), p1b = __shfl_sync(0xffffffffu, q1, kb);
+      const bool doa = (p1a - p0a) <= kLongRow, dob = (kb != k) && (p1b - p0b) <= kLongRow;
+      double acca = 0.0, accb = 0.0;
+      int64_t pa = p0a + lane, pb = p0b + lane;
+      if (doa) {
+        for (; pa + 32 < p1a; pa += 64) {
+          const int c0 = __ldcs(A.idx + pa), c1 = __ldcs(A.idx + pa + 32);
+          const double v0 = __ldcs(val + pa), v1 = __ldcs(val + pa + 32);
+          acca += v0 * x[c0]; acca += v1 * x[c1];
+        }
+        if (pa < p1a) acca += __ldcs(val + pa) * x[__ldcs(A.idx + pa)];
+      }
+      if (dob) {
+        for (; pb + 32 < p1b; pb += 64) {
+          const int c0 = __ldcs(A.idx + pb), c1 = __ldcs(A.idx + pb + 32);
+          const double v0 = __ldcs(val + pb), v1 = __ldcs(val + pb + 32);
+          accb += v0 * x[c0]; accb += v1 * x[c1];
+        }
+        if (pb < p1b) accb += __ldcs(val + pb) * x[__ldcs(A.idx + pb)];
+      }
+      acca = warp_sum(acca);
+      accb = warp_sum(accb);
+      if (lane == k) myres = acca;
+      if (lane == kb && kb != k) myres = accb;
+    }
+    if (myrow < A.n_rows && mylen <= kLongRow) epi.row(b, myrow, myres * xs);
   }
   epi.finalize(b);
 }
@@ -495,21 +544,21 @@ struct Plan {
 
 template <class Epi>
 static void launch_rows(const Plan& P, const double* xv, Epi epi) {
-  dim3 g(grid1(P.rows * 32, 256, 16), P.B);
-  k_rows_warp<Epi><<<g, 256, 0, P.s>>>(P.A, xv, epi);
+  dim3 g(grid1(P.rows, 256, 16), P.B);   // one warp per 32-row chunk
+  { k_rows_warp<Epi><<<g, 256, 0, P.s>>>(P.A, xv, epi); NEPTUNE_COUNT(1); }
   dim3 gl(kNumSMs * 2, P.B);
-  k_rows_long<Epi><<<gl, 256, 0, P.s>>>(P.A, xv, P.long_rows, P.n_long, epi);
+  { k_rows_long<Epi><<<gl, 256, 0, P.s>>>(P.A, xv, P.long_rows, P.n_long, epi); NEPTUNE_COUNT(1); }
 }
 
 template <class Epi>
 static void launch_cols(const Plan& P, const double* yv, Epi epi) {
   if (P.split > 0) {
     dim3 g(grid1(P.split, 256, 16), P.B);
-    k_cols_thread<Epi><<<g, 256, 0, P.s>>>(P.At, P.split, yv, epi);
+    { k_cols_thread<Epi><<<g, 256, 0, P.s>>>(P.At, P.split, yv, epi); NEPTUNE_COUNT(1); }
   }
   if (P.split < P.cols) {
     dim3 g(grid1((P.cols - P.split) * 32, 256, 16), P.B);
-    k_cols_warp<Epi><<<g, 256, 0, P.s>>>(P.At, P.split, yv, epi);
+    { k_cols_warp<Epi><<<g, 256, 0, P.s>>>(P.At, P.split, yv, epi); NEPTUNE_COUNT(1); }
   }
 }
 
@@ -548,7 +597,7 @@ extern "C" int neptune_spmv(int B, int64_t rows, int64_t cols, const int64_t* ro
   NEPTUNE_CUDA_OK(cudaMallocAsync(&tmp, (size_t)kMaxLongList * 4 + 256, s));
   int32_t* n_long = tmp + kMaxLongList;
   NEPTUNE_CUDA_OK(cudaMemsetAsync(n_long, 0, 4, s));
-  k_find_long_rows<<<grid1(rows, 256, 8), 256, 0, s>>>(row_ptr, rows, tmp, n_long);
+  { k_find_long_rows<<<grid1(rows, 256, 8), 256, 0, s>>>(row_ptr, rows, tmp, n_long); NEPTUNE_COUNT(1); }
   int64_t nnz = 0;   // per-instance stride of val: read row_ptr[rows] (device) -> need it on host
   NEPTUNE_CUDA_OK(cudaMemcpyAsync(&nnz, row_ptr + rows, 8, cudaMemcpyDeviceToHost, s));
   NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
@@ -568,7 +617,7 @@ extern "C" int neptune_spmv_t(int B, int64_t rows, int64_t cols, const int64_t* 
   NEPTUNE_CUDA_OK(cudaMallocAsync(&d_split, 8, s));
   unsigned long long h_split = (unsigned long long)cols;
   NEPTUNE_CUDA_OK(cudaMemcpyAsync(d_split, &h_split, 8, cudaMemcpyHostToDevice, s));
-  k_find_split<<<grid1(cols, 256, 8), 256, 0, s>>>(rowT_ptr, cols, d_split);
+  { k_find_split<<<grid1(cols, 256, 8), 256, 0, s>>>(rowT_ptr, cols, d_split); NEPTUNE_COUNT(1); }
   int64_t nnz = 0;
   NEPTUNE_CUDA_OK(cudaMemcpyAsync(&nnz, rowT_ptr + cols, 8, cudaMemcpyDeviceToHost, s));
   NEPTUNE_CUDA_OK(cudaMemcpyAsync(&h_split, d_split, 8, cudaMemcpyDeviceToHost, s));
@@ -619,36 +668,36 @@ extern "C" int neptune_pdhg_solve(int B, int64_t rows, int64_t cols, int64_t nnz
   NEPTUNE_CUDA_OK(cudaMemsetAsync(n_long, 0, 4, s));
   unsigned long long h_split = (unsigned long long)cols;
   NEPTUNE_CUDA_OK(cudaMemcpyAsync(d_split, &h_split, 8, cudaMemcpyHostToDevice, s));
-  k_find_long_rows<<<grid1(rows, 256, 8), 256, 0, s>>>(row_ptr, rows, long_rows, n_long);
-  k_find_split<<<grid1(cols, 256, 8), 256, 0, s>>>(rowT_ptr, cols, d_split);
+  { k_find_long_rows<<<grid1(rows, 256, 8), 256, 0, s>>>(row_ptr, rows, long_rows, n_long); NEPTUNE_COUNT(1); }
+  { k_find_split<<<grid1(cols, 256, 8), 256, 0, s>>>(rowT_ptr, cols, d_split); NEPTUNE_COUNT(1); }
   NEPTUNE_CUDA_OK(cudaMemcpyAsync(&h_split, d_split, 8, cudaMemcpyDeviceToHost, s));
   NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
   Plan P{B, rows, cols, nnz, (int64_t)h_split, A, At, long_rows, n_long, s};
 
   // equilibration: dr = S, dc = T hold the scalings, squared at the end
   const int g_c = grid1((int64_t)B * cols, 256, 16), g_r = grid1((int64_t)B * rows, 256, 16);
-  k_fill<<<g_c, 256, 0, s>>>((int64_t)B * cols, T, 1.0);
-  k_fill<<<g_r, 256, 0, s>>>((int64_t)B * rows, S, 1.0);
+  { k_fill<<<g_c, 256, 0, s>>>((int64_t)B * cols, T, 1.0); NEPTUNE_COUNT(1); }
+  { k_fill<<<g_r, 256, 0, s>>>((int64_t)B * rows, S, 1.0); NEPTUNE_COUNT(1); }
   NEPTUNE_CUDA_OK(cudaMemsetAsync(rowacc, 0, rb, s));
   NEPTUNE_CUDA_OK(cudaMemsetAsync(colacc, 0, cb, s));
   const int ruiz = prm->ruiz_iters >= 0 ? prm->ruiz_iters : 10;
   for (int it = 0; it <= ruiz; ++it) {
     const int use_sum = (it == ruiz);           // last pass: Pock-Chambolle alpha = 1
     dim3 g(grid1(cols, 256, 16), B);
-    k_scale_pass<<<g, 256, 0, s>>>(At, use_sum, S, T, lo, hi, colacc, rowacc);
-    k_scale_update<<<g_c, 256, 0, s>>>((int64_t)B * cols, T, colacc);
-    k_scale_update<<<g_r, 256, 0, s>>>((int64_t)B * rows, S, rowacc);
+    { k_scale_pass<<<g, 256, 0, s>>>(At, use_sum, S, T, lo, hi, colacc, rowacc); NEPTUNE_COUNT(1); }
+    { k_scale_update<<<g_c, 256, 0, s>>>((int64_t)B * cols, T, colacc); NEPTUNE_COUNT(1); }
+    { k_scale_update<<<g_r, 256, 0, s>>>((int64_t)B * rows, S, rowacc); NEPTUNE_COUNT(1); }
   }
-  k_square<<<g_c, 256, 0, s>>>((int64_t)B * cols, T);
-  k_square<<<g_r, 256, 0, s>>>((int64_t)B * rows, S);
+  { k_square<<<g_c, 256, 0, s>>>((int64_t)B * cols, T); NEPTUNE_COUNT(1); }
+  { k_square<<<g_r, 256, 0, s>>>((int64_t)B * rows, S); NEPTUNE_COUNT(1); }
 
   // control block, norms, initial state
   NEPTUNE_CUDA_OK(cudaMemsetAsync(ctl, 0, (size_t)B * sizeof(Ctl), s));
   {
     dim3 g(grid1(cols > rows ? cols : rows, 256, 4), B);
-    k_norms<<<g, 256, 0, s>>>(rows, cols, lo, hi, obj, S, T, ctl);
+    { k_norms<<<g, 256, 0, s>>>(rows, cols, lo, hi, obj, S, T, ctl); NEPTUNE_COUNT(1); }
   }
-  k_ctl_init<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, 0.99);
+  { k_ctl_init<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, 0.99); NEPTUNE_COUNT(1); }
   NEPTUNE_CUDA_OK(cudaMemsetAsync(xsum, 0, cb, s));
   NEPTUNE_CUDA_OK(cudaMemsetAsync(ysum, 0, rb, s));
   NEPTUNE_CUDA_OK(cudaMemcpyAsync(xres, x, cb, cudaMemcpyDeviceToDevice, s));
@@ -670,15 +719,15 @@ extern "C" int neptune_pdhg_solve(int B, int64_t rows, int64_t cols, int64_t nnz
       launch_rows(P, w ? xsum : x, RowsEval{ctl, rows, w, lo, hi, w ? ysum : y, 0.0, 0.0, 0.0});
       launch_cols(P, w ? ysum : y, ColsEval{ctl, cols, w, obj, col_lb, col_ub, w ? xsum : x, 0.0, 0.0, 0.0});
     }
-    k_ctl_decide<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, check_every, prm->eps_abs, prm->eps_rel, max_iters,
-                                                 result_d);
+    { k_ctl_decide<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, check_every, prm->eps_abs, prm->eps_rel, max_iters,
+                                                 result_d); NEPTUNE_COUNT(1); }
     {
       dim3 gc(grid1(cols, 256, 8), B), gr(grid1(rows, 256, 8), B);
-      k_apply_restart<<<gc, 256, 0, s>>>(cols, 1, ctl, x, xsum, xres, T);
-      k_apply_restart<<<gr, 256, 0, s>>>(rows, 0, ctl, y, ysum, yres, S);
+      { k_apply_restart<<<gc, 256, 0, s>>>(cols, 1, ctl, x, xsum, xres, T); NEPTUNE_COUNT(1); }
+      { k_apply_restart<<<gr, 256, 0, s>>>(rows, 0, ctl, y, ysum, yres, S); NEPTUNE_COUNT(1); }
     }
-    k_ctl_after_restart<<<(B + 127) / 128, 128, 0, s>>>(B, ctl);
-    k_all_done<<<1, 1, 0, s>>>(B, ctl, d_flag);
+    { k_ctl_after_restart<<<(B + 127) / 128, 128, 0, s>>>(B, ctl); NEPTUNE_COUNT(1); }
+    { k_all_done<<<1, 1, 0, s>>>(B, ctl, d_flag); NEPTUNE_COUNT(1); }
     NEPTUNE_CUDA_OK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, s));
     NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
   }

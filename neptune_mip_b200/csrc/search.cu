@@ -486,9 +486,9 @@ extern "C" int neptune_local_search(int B, int N, int F, int kind, double alpha,
   const size_t sm = (size_t)8 * N * 8;
   if (sm > 200 * 1024) return NEPTUNE_E_SIZE;
   NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_local_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  k_ls_prepare<<<B, 256, 0, s>>>(a);
-  k_local_search<<<dim3(chains, B), 256, sm, s>>>(a);
-  k_ls_pick<<<B, 256, 0, s>>>(a, best_c, best_obj, best_flags);
+  { k_ls_prepare<<<B, 256, 0, s>>>(a); NEPTUNE_COUNT(1); }
+  { k_local_search<<<dim3(chains, B), 256, sm, s>>>(a); NEPTUNE_COUNT(1); }
+  { k_ls_pick<<<B, 256, 0, s>>>(a, best_c, best_obj, best_flags); NEPTUNE_COUNT(1); }
   NEPTUNE_LAUNCH_OK();
   return 0;
 }
