@@ -155,6 +155,15 @@ int neptune_check_solution(int B, int N, int F, double alpha,
 int neptune_route_placements(int B, int N, int F, const double* d, const uint8_t* c,
                              double* x, double* n, void* stream);
 
+/* neptune_route_capacitated: routing of a fixed placement that also honours the CPU rows
+ * (`constrain_CPU_usage`, constraints_step1.py:57-65): nearest open pod first, then per overloaded
+ * node the flows with the smallest delay increase per freed core are moved (the last one split).
+ * Pods left without any request are closed in c_out (C1b, constraints_step1.py:12-15).
+ * c[B][F][N] uint8 -> c_out[B][F][N], x[B][N][F][N], n[B][N], obj_out[B] (sum x*d*w), feas_out[B]. */
+int neptune_route_capacitated(int B, int N, int F, const double* d, const double* w, const double* r,
+                              const double* Kj, const uint8_t* c, uint8_t* c_out, double* x, double* n,
+                              double* obj_out, int32_t* feas_out, void* stream);
+
 /* neptune_eval_placements: P candidate placements per instance, never materialising x:
  * c[B][P][F][N] (uint8) -> obj_out[B][P][3] {delay, util, combined}, flags_out[B][P],
  * overload_out[B][P] (sum_j max(0, cpu_load_j - K_j), 0 when the CPU check passes). */

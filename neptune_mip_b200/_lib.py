@@ -46,6 +46,7 @@ _SIGNATURES = {
     "neptune_spmv_t": [_i, _i64, _i64, _p, _p, _p, _p, _p, _p],
     "neptune_check_solution": [_i, _i, _i, _d] + _INST + [_p] * 5 + [_p],
     "neptune_route_placements": [_i, _i, _i, _p, _p, _p, _p, _p],
+    "neptune_route_capacitated": [_i, _i, _i] + [_p] * 10 + [_p],
     "neptune_eval_placements": [_i, _i, _i, _i, _d] + _INST + [_p] * 4 + [_p],
     "neptune_local_search": [_i, _i, _i, _i, _d, _i, _i, C.c_uint64, _i] + _INST + [_p] * 6 + [_p, _i64, _p],
     "neptune_local_search_workspace_bytes": [_i, _i, _i, _i, C.POINTER(_i64)],

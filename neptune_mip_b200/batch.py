@@ -63,6 +63,7 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
     bad = ~torch.isfinite(best_obj)
     if bool(bad.any()):
         best_c[bad] = fallback[bad]
-    x, n = device.route_placements(inst, best_c)
+    # final routing honours the CPU rows (splits flows on binding nodes) and closes pods nobody uses
+    best_c, x, n, _, _ = device.route_capacitated(inst, best_c)
     flags, scores = device.check_solution(inst, x, device.u8_to_f64(best_c), n, prm.alpha)
     return BatchResult(best_c, x, n, flags, scores, lp_res, pdhg_ms, iters, dims)

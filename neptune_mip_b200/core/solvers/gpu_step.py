@@ -19,10 +19,15 @@ class GpuStepMixin:
     def _alpha(self):
         return float(getattr(self, "alpha", 0.5))
 
-    def _finish(self, c_u8: torch.Tensor):
-        """Exact routing + the reference's checkers/scorers for placement c (uint8 [1,F,N])."""
+    def _finish(self, c_u8: torch.Tensor, capacitated: bool = False):
+        """Exact routing + the reference's checkers/scorers for placement c (uint8 [1,F,N]).
+        `capacitated`: route with the CPU rows honoured (MIP semantics) instead of the plain
+        nearest-open-pod rule (EFTTC semantics)."""
         inst = self.inst
-        x, n = device.route_placements(inst, c_u8)
+        if capacitated:
+            c_u8, x, n, _, _ = device.route_capacitated(inst, c_u8)
+        else:
+            x, n = device.route_placements(inst, c_u8)
         flags, scores = device.check_solution(inst, x, device.u8_to_f64(c_u8), n, self._alpha())
         self._x = x[0].cpu().numpy()
         self._c = c_u8[0].cpu().numpy().astype(np.float64)

@@ -62,7 +62,7 @@ class NeptuneStep1CPUBase(NeptuneStepBase):
                                                   self.rng_seed, guide)
         if not torch.isfinite(best_obj[0]):
             best_c = seeds[:, {"min_delay": 0, "min_util": 1, "min_delay_util": 2}[self.kind]].contiguous()
-        ok = self._finish(best_c)
+        ok = self._finish(best_c, capacitated=True)
         self.log(f"step 1: score {self._kind_score()} flags {self.flags:06b} lp bound {self.lp_bound}")
         return ok
 

@@ -53,7 +53,7 @@ class NeptuneStep2Base(NeptuneStepBase):
             self._obj = 0.0
             return False
         c_u8 = torch.from_numpy((prev_c > 0.001).astype(np.uint8)).cuda()[None].contiguous()
-        ok = self._finish(c_u8)
+        ok = self._finish(c_u8, capacitated=True)
         self._obj = val
         return bool(ok)
 

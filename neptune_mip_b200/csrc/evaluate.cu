@@ -7,6 +7,7 @@
 //  * neptune_route_placements : closed-form routing of change_x_one (efttc_step1.py:196-212).
 //  * neptune_eval_placements  : P candidate placements per instance, never materialising x.
 #include "common.cuh"
+#include "route_cap.cuh"
 
 namespace neptune {
 
@@ -276,9 +277,106 @@ __global__ void __launch_bounds__(256) k_eval(Inst in0, int P, const uint8_t* __
   }
 }
 
+// ---- capacity-aware routing of one placement per instance (block per instance) -----------------------
+__global__ void __launch_bounds__(256) k_route_cap(int N, int F, const double* __restrict__ d0,
+                                                   const double* __restrict__ w0, const double* __restrict__ r0,
+                                                   const double* __restrict__ K0, const uint8_t* __restrict__ c0,
+                                                   uint8_t* __restrict__ cout0, double* __restrict__ x0,
+                                                   double* __restrict__ n0, double* __restrict__ obj,
+                                                   int32_t* __restrict__ feas, char* ws, int64_t ws_stride) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int64_t fn = (int64_t)F * N;
+  char* p = ws + (int64_t)b * ws_stride;
+  CapRoute q;
+  q.N = N; q.F = F;
+  q.d = d0 + (int64_t)b * N * N; q.w = w0 + b * fn; q.r = r0 + b * fn; q.Kj = K0 + (int64_t)b * N;
+  q.c = c0 + b * fn;
+  q.th = (double*)p; p += fn * 8; q.rho = (double*)p; p += fn * 8;
+  q.load = (double*)p; p += (int64_t)N * 8; q.lam = (double*)p; p += (int64_t)N * 8;
+  q.ch = (int*)p; p += fn * 4; q.sec = (int*)p; p += fn * 4; q.alt = (int*)p;
+  __shared__ double red[32];
+  __shared__ double sh[8];
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  const CapResult cr = cap_route(q, 4 * N + 16, red, sh);
+  uint8_t* cout = cout0 + b * fn;
+  double* x = x0 + (int64_t)b * N * fn;
+  for (int64_t k = tid; k < (int64_t)N * fn; k += blockDim.x) x[k] = 0.0;
+  for (int64_t k = tid; k < fn; k += blockDim.x) cout[k] = q.c[k];
+  __syncthreads();
+  if (cr.feasible) {
+    for (int fi = tid; fi < (int)fn; fi += blockDim.x) {
+      const int f = fi / N, i = fi - f * N;
+      double* xr = x + ((int64_t)i * F + f) * N;
+      xr[q.ch[fi]] = q.th[fi];
+      if (q.sec[fi] >= 0) xr[q.sec[fi]] = 1.0 - q.th[fi];
+    }
+    __syncthreads();
+    // A split can leave a pod with a total share below 1 - eps (C1b, constraints_step1.py:12-15).  Sources
+    // without workload for f (w[f,i] == 0) route for free -- no delay cost, no CPU load -- so they top the
+    // starved pod up, exactly what the MIP does with its free x columns.  One thread per function.
+    for (int f = tid; f < F; f += blockDim.x) {
+      for (int j = 0; j < N; ++j) {
+        if (!q.c[(int64_t)f * N + j]) continue;
+        double rc = 0.0;
+        for (int i = 0; i < N; ++i) rc += x[((int64_t)i * F + f) * N + j];
+        if (rc == 0.0 || rc + kEps >= 1.0) continue;
+        double deficit = 1.0 - rc;
+        for (int i = 0; i < N && deficit > 0.0; ++i) {
+          if (q.w[(int64_t)f * N + i] != 0.0) continue;
+          double* xr = x + ((int64_t)i * F + f) * N;
+          for (int p2 = 0; p2 < N && deficit > 0.0; ++p2) {
+            if (p2 == j || xr[p2] <= 0.0) continue;
+            double rp = 0.0;                                  // donor pod must keep a share >= 1
+            for (int i2 = 0; i2 < N; ++i2) rp += x[((int64_t)i2 * F + f) * N + p2];
+            const double amt = fmin(fmin(xr[p2], rp - 1.0), deficit);
+            if (amt <= 0.0) continue;
+            xr[p2] -= amt; xr[j] += amt; deficit -= amt;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // pods that serve nobody are closed (free for the objective); a pod still short of its share is
+    // reported (feas_out = 0) -- the caller falls back to another placement
+    for (int fj = tid; fj < (int)fn; fj += blockDim.x) {
+      if (!q.c[fj]) continue;
+      const int f = fj / N, j = fj - f * N;
+      double rc = 0.0;
+      for (int i = 0; i < N; ++i) rc += x[((int64_t)i * F + f) * N + j];
+      if (rc == 0.0) cout[fj] = 0;
+      else if (rc + kEps < 1.0) bad = 1;
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < N; j += blockDim.x) {
+    int any = 0;
+    for (int f = 0; f < F; ++f) any |= cout[(int64_t)f * N + j];
+    n0[(int64_t)b * N + j] = any ? 1.0 : 0.0;
+  }
+  if (tid == 0) { obj[b] = cr.cost; feas[b] = (cr.feasible && !bad) ? 1 : 0; }
+}
+
 }  // namespace neptune
 
 using namespace neptune;
+
+extern "C" int neptune_route_capacitated(int B, int N, int F, const double* d, const double* w, const double* r,
+                                         const double* Kj, const uint8_t* c, uint8_t* c_out, double* x,
+                                         double* n, double* obj_out, int32_t* feas_out, void* stream) {
+  if (B <= 0 || N <= 0 || F <= 0 || !d || !w || !r || !Kj || !c || !c_out || !x || !n || !obj_out || !feas_out)
+    return NEPTUNE_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t fn = (int64_t)F * N;
+  int64_t stride = 2 * fn * 8 + 2 * (int64_t)N * 8 + 3 * fn * 4;
+  stride = (stride + 255) & ~(int64_t)255;
+  char* ws = nullptr;
+  NEPTUNE_CUDA_OK(cudaMallocAsync(&ws, (size_t)stride * B, s));
+  { k_route_cap<<<B, 256, 0, s>>>(N, F, d, w, r, Kj, c, c_out, x, n, obj_out, feas_out, ws, stride); NEPTUNE_COUNT(1); }
+  NEPTUNE_LAUNCH_OK();
+  NEPTUNE_CUDA_OK(cudaFreeAsync(ws, s));
+  return 0;
+}
 
 extern "C" int neptune_check_solution(int B, int N, int F, double alpha, const double* d, const double* w,
                                       const double* r, const double* m, const double* Mj, const double* Kj,

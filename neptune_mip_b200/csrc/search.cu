@@ -13,6 +13,7 @@
 // Thousands of candidate moves are checked per sweep and chain; feasibility of the winner is
 // re-verified by the exact checkers (neptune_check_solution) in the caller.
 #include "common.cuh"
+#include "route_cap.cuh"
 
 namespace neptune {
 
@@ -35,16 +36,21 @@ struct Chain {
   uint8_t *c, *best_c;
   double *b1, *b2, *load, *mem;
   int *a1, *a2, *cntf, *cntn, *pods;
+  // capacity-aware routing scratch (route_cap.cuh)
+  double *th, *rho, *cload, *lam;
+  int *ch, *sec, *alt;
 };
 
 __device__ __forceinline__ int64_t chain_bytes(int N, int F) {
   int64_t fn = (int64_t)F * N;
   int64_t b = 2 * fn + 2 * fn * 8 + 2 * fn * 4 + 2 * (int64_t)N * 8 + (int64_t)F * 4 + (int64_t)N * 4 + fn * 4 + 64;
+  b += 2 * fn * 8 + 3 * fn * 4 + 2 * (int64_t)N * 8 + 64;
   return (b + 255) & ~(int64_t)255;
 }
 static inline int64_t chain_bytes_h(int N, int F) {
   int64_t fn = (int64_t)F * N;
   int64_t b = 2 * fn + 2 * fn * 8 + 2 * fn * 4 + 2 * (int64_t)N * 8 + (int64_t)F * 4 + (int64_t)N * 4 + fn * 4 + 64;
+  b += 2 * fn * 8 + 3 * fn * 4 + 2 * (int64_t)N * 8 + 64;
   return (b + 255) & ~(int64_t)255;
 }
 
@@ -53,17 +59,27 @@ __device__ __forceinline__ Chain carve(char* p, int N, int F) {
   const int64_t fn = (int64_t)F * N;
   k.b1 = (double*)p; p += fn * 8;
   k.b2 = (double*)p; p += fn * 8;
+  k.th = (double*)p; p += fn * 8;
+  k.rho = (double*)p; p += fn * 8;
+  k.cload = (double*)p; p += (int64_t)N * 8;
+  k.lam = (double*)p; p += (int64_t)N * 8;
   k.load = (double*)p; p += (int64_t)N * 8;
   k.mem = (double*)p; p += (int64_t)N * 8;
   k.a1 = (int*)p; p += fn * 4;
   k.a2 = (int*)p; p += fn * 4;
   k.pods = (int*)p; p += fn * 4;
+  k.ch = (int*)p; p += fn * 4;
+  k.sec = (int*)p; p += fn * 4;
+  k.alt = (int*)p; p += fn * 4;
   k.cntf = (int*)p; p += (int64_t)F * 4;
   k.cntn = (int*)p; p += (int64_t)N * 4;
   k.c = (uint8_t*)p; p += fn;
   k.best_c = (uint8_t*)p;
   return k;
 }
+
+constexpr double kBigDelay = 1e8;     // delay charged to a source whose function has no pod yet
+constexpr double kCoverage = 1e13;    // cost of a function without any pod (dominates everything else)
 
 __device__ __forceinline__ uint64_t rng_next(uint64_t& s) {   // xorshift64*
   s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
@@ -75,7 +91,7 @@ __device__ void route_f(const LsArgs& a, const Chain& k, const double* d, int f)
   const int N = a.N;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     const double* di = d + (int64_t)i * N;
-    double v1 = INFINITY, v2 = INFINITY; int j1 = -1, j2 = -1;
+    double v1 = kBigDelay, v2 = kBigDelay; int j1 = -1, j2 = -1;   // finite: deltas stay finite
     for (int j = 0; j < N; ++j) {
       if (!k.c[(int64_t)f * N + j]) continue;
       const double v = di[j];
@@ -111,12 +127,13 @@ __device__ void node_state(const LsArgs& a, const Chain& k, const double* w, con
   }
 }
 
-struct Cost { double delay, util, over; };
+struct Cost { double delay, util, over, uncov; };
 
 // whole-block exact cost of the current state (after route_f for all f and node_state)
 __device__ Cost full_cost(const LsArgs& a, const Chain& k, const double* w, const double* Kj, double* red) {
   const int N = a.N, F = a.F;
-  double dl = 0.0, ut = 0.0, ov = 0.0;
+  double dl = 0.0, ut = 0.0, ov = 0.0, uc = 0.0;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) if (k.cntf[f] == 0) uc += 1.0;
   for (int fi = threadIdx.x; fi < F * N; fi += blockDim.x) {
     const double wv = w[fi];
     if (wv != 0.0) dl += wv * k.b1[fi];
@@ -130,6 +147,7 @@ __device__ Cost full_cost(const LsArgs& a, const Chain& k, const double* w, cons
   c.delay = block_sum(dl, red); __syncthreads();
   c.util = block_sum(ut, red); __syncthreads();
   c.over = block_sum(ov, red); __syncthreads();
+  c.uncov = block_sum(uc, red); __syncthreads();
   __shared__ Cost bc;
   if (threadIdx.x == 0) bc = c;
   __syncthreads();
@@ -181,8 +199,25 @@ __device__ double eval_overload_delta(const LsArgs& a, const Chain& k, const dou
   return warp_sum(dv);
 }
 
-enum { MV_NONE = 0, MV_ADD, MV_DROP, MV_SWAP, MV_REPLACE };
-struct Move { int type, f, j, t; };   // ADD(f, j) | DROP(f, j) | SWAP(f, j -> t) | REPLACE(node j: f -> t)
+enum { MV_NONE = 0, MV_ADD, MV_DROP, MV_SWAP, MV_REPLACE, MV_EXCH };
+// ADD(f, j) | DROP(f, j) | SWAP(f, j -> t) | REPLACE(node j: f -> t) | EXCH((f, j) <-> pod t = g*N + j2)
+struct Move { int type, f, j, t; };
+constexpr int kMaxTabu = 12;
+constexpr int64_t kMaxExchange = 1 << 17;     // exchange proposals examined per sweep (sampled beyond that)
+constexpr double kUnrepairable = 1e11;        // state whose overload cannot be routed away
+
+__device__ inline void apply_move(const Chain& k, int N, const Move& m, bool undo) {
+  const uint8_t on = undo ? 0 : 1, off = undo ? 1 : 0;
+  if (m.type == MV_ADD) k.c[(int64_t)m.f * N + m.j] = on;
+  else if (m.type == MV_DROP) k.c[(int64_t)m.f * N + m.j] = off;
+  else if (m.type == MV_SWAP) { k.c[(int64_t)m.f * N + m.j] = off; k.c[(int64_t)m.f * N + m.t] = on; }
+  else if (m.type == MV_REPLACE) { k.c[(int64_t)m.f * N + m.j] = off; k.c[(int64_t)m.t * N + m.j] = on; }
+  else if (m.type == MV_EXCH) {
+    const int g = m.t / N, j2 = m.t - g * N;
+    k.c[(int64_t)m.f * N + m.j] = off; k.c[(int64_t)m.f * N + j2] = on;
+    k.c[(int64_t)g * N + j2] = off; k.c[(int64_t)g * N + m.j] = on;
+  }
+}
 
 __global__ void __launch_bounds__(256) k_ls_prepare(LsArgs a) {
   // per instance: dT, wmax, penalty weight, objective weights
@@ -193,7 +228,12 @@ __global__ void __launch_bounds__(256) k_ls_prepare(LsArgs a) {
   __shared__ double red[32];
   const double* w = a.w + (int64_t)b * F * N;
   const double* r = a.r + (int64_t)b * F * N;
-  double wm = 0.0, tw = 0.0, dmax = 0.0, rmin = INFINITY;
+  double wm = 0.0, tw = 0.0, dmax = 0.0, rmin = INFINITY, dsum = 0.0, rsum = 0.0, rcnt = 0.0;
+  for (int k = threadIdx.x; k < N * N; k += blockDim.x) dsum += d[k];
+  for (int fi = threadIdx.x; fi < F * N; fi += blockDim.x) if (r[fi] > 0.0) { rsum += r[fi]; rcnt += 1.0; }
+  dsum = block_sum(dsum, red); __syncthreads();
+  rsum = block_sum(rsum, red); __syncthreads();
+  rcnt = block_sum(rcnt, red); __syncthreads();
   for (int fi = threadIdx.x; fi < F * N; fi += blockDim.x) {
     const int f = fi / N, i = fi - f * N;
     const double md = a.maxd ? a.maxd[(int64_t)b * F + f] : INFINITY;
@@ -215,10 +255,13 @@ __global__ void __launch_bounds__(256) k_ls_prepare(LsArgs a) {
     if (a.kind == NEPTUNE_KIND_MIN_DELAY) { a_d = 1.0; a_u = 0.0; }
     else if (a.kind == NEPTUNE_KIND_MIN_UTIL) { a_d = 0.0; a_u = 1.0; }
     else { a_u = a.alpha / (double)N; a_d = (tw != 0.0 && wm != 0.0) ? (1.0 - a.alpha) / wm : 0.0; }
-    // one unit of CPU overload must cost more than any reroute that could remove it
-    double mu = (isfinite(rmin) ? 4.0 * (dmax + 1.0) / rmin : 1.0) * (a_d > 0.0 ? a_d : 1.0);
-    mu = fmax(mu, 100.0 * a_u);                  // closing a node never pays for an overload
-    s[0] = wm; s[1] = mu; s[2] = a_d; s[3] = a_u;
+    // mu_big: one unit of CPU overload costs more than any reroute that could remove it (used while a
+    // state is not routable at all); mu: proposal weight ~ typical repair cost per core (dmean / rmean / 10)
+    double mu_big = (isfinite(rmin) ? 4.0 * (dmax + 1.0) / rmin : 1.0) * (a_d > 0.0 ? a_d : 1.0);
+    mu_big = fmax(mu_big, 100.0 * a_u);
+    const double dmean = dsum / fmax(1.0, (double)N * (double)(N - 1)), rmean = rcnt > 0.0 ? rsum / rcnt : 1.0;
+    double mu = a_d > 0.0 ? 0.1 * a_d * dmean / fmax(rmean, 1e-9) : 0.01 * a_u;
+    s[0] = mu_big; s[1] = mu; s[2] = a_d; s[3] = a_u;
   }
 }
 
@@ -238,10 +281,13 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
   extern __shared__ double dyn[];
   double* delta = dyn + (int64_t)wid * N;          // per-warp load deltas
   __shared__ double red[32];
+  __shared__ double capsh[8];
   __shared__ double wbest[8];
   __shared__ Move wmove[8];
   __shared__ Move mv;
-  __shared__ int n_pods;
+  __shared__ int n_pods, n_tabu;
+  __shared__ uint64_t s_rand[2];
+  __shared__ Move tabu_list[kMaxTabu];
   __shared__ double best_total;
   uint64_t rs = a.rng ^ (0x9E3779B97F4A7C15ull * (uint64_t)(chain + 1)) ^ (0xD1B54A32D192ED03ull * (uint64_t)(b + 1));
   rng_next(rs);
@@ -285,7 +331,7 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
     node_state(a, k, w, r, m);
     __syncthreads();
   };
-  auto total_of = [&](const Cost& c) { return a_d * c.delay + a_u * c.util + mu * c.over; };
+  auto total_of = [&](const Cost& c) { return a_d * c.delay + a_u * c.util + mu * c.over + kCoverage * c.uncov; };
 
   // random kick: `n` random swap / replace changes that keep memory feasible (thread 0)
   auto kick = [&](int n) {
@@ -320,39 +366,59 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
   double cur_total = total_of(cur);
   if (tid == 0) best_total = INFINITY;
   __syncthreads();
+  const double mu_big = scal[0];
+  // true cost of the current state (block-uniform; all threads must call)
+  auto true_total = [&](const Cost& c) -> double {
+    const double base = a_u * c.util + kCoverage * c.uncov;
+    if (c.uncov > 0.0) return a_d * c.delay + base + mu_big * c.over;
+    if (c.over <= 0.0) return a_d * c.delay + base;
+    CapRoute q{N, F, d, w, r, Kj, k.c, k.ch, k.sec, k.th, k.rho, k.alt, k.cload, k.lam};
+    const CapResult cr = cap_route(q, 48, red, capsh);
+    if (cr.feasible) return a_d * cr.cost + base;
+    return a_d * c.delay + base + mu_big * c.over + kUnrepairable;
+  };
+  double cur_true = true_total(cur);
   auto save_best = [&]() {
-    // a chain's best must be usable: memory ok by construction, every function placed, no overload
-    bool covered = true;
-    for (int f = 0; f < F; ++f) covered = covered && (k.cntf[f] > 0);
-    const double t = (covered && cur.over <= 0.0) ? (a_d * cur.delay + a_u * cur.util) : INFINITY;
-    if (t < best_total) {
+    // a chain's best must be usable: memory ok by construction, every function placed, CPU rows routable
+    if (cur_true < kUnrepairable && cur_true < best_total) {
       __syncthreads();
       for (int q = tid; q < F * N; q += blockDim.x) k.best_c[q] = k.c[q];
-      if (tid == 0) best_total = t;
+      if (tid == 0) best_total = cur_true;
     }
     __syncthreads();
   };
   save_best();
 
+  // Moves are PROPOSED by their penalised delta (overload priced at mu, an estimate of the repair cost per
+  // core) and ACCEPTED on the true cost of the new state: nearest routing if no node overloads, else the
+  // capacity-aware routing of route_cap.cuh.  A rejected proposal is undone and kept tabu until the state
+  // changes or the chain is kicked.
   int stall = 0;
+  n_tabu = 0;
   for (int sweep = 0; sweep < a.sweeps; ++sweep) {
     // ---- pod list -------------------------------------------------------------------------------------
-    if (tid == 0) n_pods = 0;
+    if (tid == 0) { n_pods = 0; s_rand[0] = rng_next(rs); s_rand[1] = rng_next(rs); }   // only thread 0 owns the RNG
     __syncthreads();
     for (int q = tid; q < F * N; q += blockDim.x) if (k.c[q]) k.pods[atomicAdd(&n_pods, 1)] = q;
     __syncthreads();
     const int P = n_pods;
     const int64_t n_add = (int64_t)F * N, n_drop = P, n_swap = (int64_t)P * N, n_rep = (int64_t)P * F;
-    const int64_t total = n_add + n_drop + n_swap + n_rep;
-    double my_best = -1e-9 * (1.0 + fabs(cur_total));      // only strictly improving moves
+    const int64_t pp = (int64_t)P * P;
+    const int64_t n_exch = pp < kMaxExchange ? pp : kMaxExchange;
+    const int64_t ex_off = (int64_t)(s_rand[0] % (uint64_t)(pp > 0 ? pp : 1));        // block-uniform
+    const int64_t ex_stride = pp > kMaxExchange ? (int64_t)(2 * (s_rand[1] % 4096) + 1) : 1;
+    const int64_t total = n_add + n_drop + n_swap + n_rep + n_exch;
+    double my_best = -1e-9 * (1.0 + fabs(cur_total));      // only strictly improving proposals
     Move my_mv{MV_NONE, 0, 0, 0};
+    const int ntb = n_tabu;
     for (int64_t q = wid; q < total; q += nw) {
-      Move cand; bool ok = false; double dutil = 0.0;
+      Move cand; bool ok = false; double dutil = 0.0, dcov = 0.0;
       if (q < n_add) {
         const int f = (int)(q / N), j = (int)(q - (int64_t)f * N);
         ok = !k.c[q] && k.mem[j] + m[f] <= Mj[j];
         cand = Move{MV_ADD, f, j, -1};
         if (ok && k.cntn[j] == 0) dutil = 1.0;
+        if (ok && k.cntf[f] == 0) dcov = -1.0;
       } else if (q < n_add + n_drop) {
         const int pq = k.pods[q - n_add], f = pq / N, j = pq - f * N;
         ok = k.cntf[f] >= 2;
@@ -364,21 +430,41 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
         ok = !k.c[(int64_t)f * N + jn] && k.mem[jn] + m[f] <= Mj[jn];
         cand = Move{MV_SWAP, f, j, jn};
         if (ok) dutil = (k.cntn[jn] == 0 ? 1.0 : 0.0) - (k.cntn[j] == 1 ? 1.0 : 0.0);
-      } else {
+      } else if (q < n_add + n_drop + n_swap + n_rep) {
         const int64_t t = q - n_add - n_drop - n_swap;
         const int pq = k.pods[t / F], f = pq / N, j = pq - f * N, fn = (int)(t % F);
         ok = fn != f && !k.c[(int64_t)fn * N + j] && k.cntf[f] >= 2 && k.mem[j] - m[f] + m[fn] <= Mj[j];
         cand = Move{MV_REPLACE, f, j, fn};
+        if (ok && k.cntf[fn] == 0) dcov = -1.0;
+      } else {
+        // exchange: pods (f, j) and (g, j2) trade nodes -> (f, j2), (g, j); pod counts stay as they are
+        const int64_t t = (ex_off + (q - n_add - n_drop - n_swap - n_rep) * ex_stride) % pp;
+        const int p1 = (int)(t / P), p2 = (int)(t - (int64_t)p1 * P);
+        if (p1 < p2) {
+          const int q1 = k.pods[p1], q2 = k.pods[p2];
+          const int f = q1 / N, j = q1 - f * N, g = q2 / N, j2 = q2 - g * N;
+          ok = f != g && j != j2 && !k.c[(int64_t)f * N + j2] && !k.c[(int64_t)g * N + j] &&
+               k.mem[j] - m[f] + m[g] <= Mj[j] && k.mem[j2] - m[g] + m[f] <= Mj[j2];
+          cand = Move{MV_EXCH, f, j, q2};
+        }
       }
       if (!ok) continue;
+      bool tabu = false;
+      for (int t = 0; t < ntb; ++t)
+        tabu = tabu || (tabu_list[t].type == cand.type && tabu_list[t].f == cand.f && tabu_list[t].j == cand.j &&
+                        tabu_list[t].t == cand.t);
+      if (tabu) continue;
       double dd = 0.0;
       if (cand.type == MV_ADD) dd = eval_change(a, k, w, r, dT, cand.f, -1, cand.j, delta);
       else if (cand.type == MV_DROP) dd = eval_change(a, k, w, r, dT, cand.f, cand.j, -1, delta);
       else if (cand.type == MV_SWAP) dd = eval_change(a, k, w, r, dT, cand.f, cand.j, cand.t, delta);
-      else { dd = eval_change(a, k, w, r, dT, cand.f, cand.j, -1, delta);
-             dd += eval_change(a, k, w, r, dT, cand.t, -1, cand.j, delta); }
+      else if (cand.type == MV_REPLACE) { dd = eval_change(a, k, w, r, dT, cand.f, cand.j, -1, delta);
+                                          dd += eval_change(a, k, w, r, dT, cand.t, -1, cand.j, delta); }
+      else { const int g = cand.t / N, j2 = cand.t - g * N;
+             dd = eval_change(a, k, w, r, dT, cand.f, cand.j, j2, delta);
+             dd += eval_change(a, k, w, r, dT, g, j2, cand.j, delta); }
       const double dov = eval_overload_delta(a, k, Kj, delta);
-      const double dt = a_d * dd + a_u * dutil + mu * dov;
+      const double dt = a_d * dd + a_u * dutil + mu * dov + kCoverage * dcov;
       if (dt < my_best) { my_best = dt; my_mv = cand; }
     }
     if (lane == 0) { wbest[wid] = my_best; wmove[wid] = my_mv; }
@@ -390,23 +476,37 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
     }
     __syncthreads();
     if (mv.type != MV_NONE) {
-      // ---- apply, re-route the touched functions, refresh node state and the exact cost ----------------
-      if (tid == 0) {
-        if (mv.type == MV_ADD) k.c[(int64_t)mv.f * N + mv.j] = 1;
-        else if (mv.type == MV_DROP) k.c[(int64_t)mv.f * N + mv.j] = 0;
-        else if (mv.type == MV_SWAP) { k.c[(int64_t)mv.f * N + mv.j] = 0; k.c[(int64_t)mv.f * N + mv.t] = 1; }
-        else { k.c[(int64_t)mv.f * N + mv.j] = 0; k.c[(int64_t)mv.t * N + mv.j] = 1; }
-      }
+      // ---- apply, re-route the touched functions, refresh node state, price the new state exactly ------
+      const Move m0 = mv;
+      int f2 = -1;                                   // second function touched
+      if (tid == 0) apply_move(k, N, m0, false);
+      if (m0.type == MV_REPLACE) f2 = m0.t; else if (m0.type == MV_EXCH) f2 = m0.t / N;
       __syncthreads();
-      route_f(a, k, d, mv.f);
-      if (mv.type == MV_REPLACE) route_f(a, k, d, mv.t);
+      route_f(a, k, d, m0.f);
+      if (f2 >= 0) route_f(a, k, d, f2);
       __syncthreads();
       node_state(a, k, w, r, m);
       __syncthreads();
-      cur = full_cost(a, k, w, Kj, red);
-      cur_total = total_of(cur);
-      stall = 0;
-    } else {
+      const Cost nc = full_cost(a, k, w, Kj, red);
+      const double nt = true_total(nc);
+      if (nt < cur_true - 1e-9 * (1.0 + fabs(cur_true))) {
+        cur = nc; cur_total = total_of(nc); cur_true = nt;
+        stall = 0;
+        if (tid == 0) n_tabu = 0;
+        __syncthreads();
+      } else {
+        if (tid == 0) { apply_move(k, N, m0, true); if (n_tabu < kMaxTabu) tabu_list[n_tabu++] = m0; }
+        __syncthreads();
+        route_f(a, k, d, m0.f);
+        if (f2 >= 0) route_f(a, k, d, f2);
+        __syncthreads();
+        node_state(a, k, w, r, m);
+        __syncthreads();
+        if (n_tabu < kMaxTabu) continue;            // try the next-best proposal
+        mv.type = MV_NONE;                          // too many rejections: treat as a local optimum
+      }
+    }
+    if (mv.type == MV_NONE) {
       // ---- local optimum: keep the best, restart from it with a kick -----------------------------------
       save_best();
       if (best_total < INFINITY) {
@@ -414,10 +514,13 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
         __syncthreads();
       }
       ++stall;
-      kick(2 + (int)(rng_next(rs) % 4) + (stall > 8 ? 4 : 0));
+      kick(2 + (int)(s_rand[0] % 4) + (stall > 8 ? 4 : 0));
       rebuild();
       cur = full_cost(a, k, w, Kj, red);
       cur_total = total_of(cur);
+      cur_true = true_total(cur);
+      if (tid == 0) n_tabu = 0;
+      __syncthreads();
     }
   }
   save_best();

@@ -313,3 +313,18 @@ def local_search(inst: InstanceBatch, kind, seeds_u8: torch.Tensor, alpha=0.5, c
                                    _ptr(guide), _ptr(best_c), _ptr(best_obj), _ptr(best_flags),
                                    _ptr(workspace), workspace.numel(), _stream()), "neptune_local_search")
     return best_c, best_obj, best_flags
+
+
+def route_capacitated(inst: InstanceBatch, c_u8: torch.Tensor):
+    """CPU-capacity-aware routing.  Returns (c_out uint8[B,F,N], x[B,N,F,N], n[B,N], obj[B], feasible int32[B])."""
+    lib = _lib.load()
+    dev = inst.d.device
+    c_out = torch.empty_like(c_u8)
+    x = torch.empty((inst.B, inst.N, inst.F, inst.N), dtype=torch.float64, device=dev)
+    n = torch.empty((inst.B, inst.N), dtype=torch.float64, device=dev)
+    obj = torch.empty(inst.B, dtype=torch.float64, device=dev)
+    feas = torch.empty(inst.B, dtype=torch.int32, device=dev)
+    check(lib.neptune_route_capacitated(inst.B, inst.N, inst.F, _ptr(inst.d), _ptr(inst.w), _ptr(inst.r),
+                                        _ptr(inst.Kj), _ptr(c_u8), _ptr(c_out), _ptr(x), _ptr(n), _ptr(obj),
+                                        _ptr(feas), _stream()), "neptune_route_capacitated")
+    return c_out, x, n, obj, feas

@@ -131,3 +131,25 @@ def test_eval_placements_matches_route_plus_check():
             assert obj[b, q, 1] == checkers.score_util(a, nn)
             assert np.isclose(obj[b, q, 2], checkers.score_delay_util(a, nn, xr, 0.5), rtol=1e-6, atol=1e-9)
             assert np.isclose(over[b, q], np.maximum(load - a["Kj"], 0)[load > a["Kj"] + 1e-6].sum(), rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_route_capacitated_matches_routing_lp(seed):
+    """CPU-binding placements: the device routing must be feasible for the reference's checkers and
+    (1-2 binding nodes, the regime of the HiGHS optima) hit the exact LP value to 1e-9 relative."""
+    import torch
+    from neptune_mip_b200 import device
+    from oracle import mip as omip, routing
+    payload = synth.config_payload("C5", seed)
+    a = arrays_of(payload)
+    ref = omip.solve_step1(a, "min_delay")
+    c = (ref["c"] > 0.5)
+    lp = routing.lp_routing(a, c)
+    assert lp is not None and abs(lp[0] - ref["objective"]) <= 1e-6 * (1 + abs(ref["objective"]))
+    inst = cuda_batch([payload])
+    c_out, x, n, obj, feas = device.route_capacitated(inst, torch.from_numpy(c.astype(np.uint8)).cuda()[None].contiguous())
+    assert int(feas.cpu()[0]) == 1
+    flags, scores = device.check_solution(inst, x, device.u8_to_f64(c_out), n)
+    assert int(flags.cpu()[0]) == 63
+    assert abs(float(obj.cpu()[0]) - lp[0]) <= 1e-9 * (1 + abs(lp[0])), (float(obj.cpu()[0]), lp[0])
+    assert abs(float(scores.cpu()[0, 0]) - lp[0]) <= 1e-9 * (1 + abs(lp[0]))

@@ -15,7 +15,7 @@ def run(config, seeds, chains, sweeps, kind="min_delay"):
     c0, n0, info = device.efttc(inst, kind)
     seeds_t = c0[:, None].contiguous()
     best_c, best_obj, fl = device.local_search(inst, kind, seeds_t, chains=chains, sweeps=sweeps)
-    x, n = device.route_placements(inst, best_c)
+    best_c, x, n, obj, feas = device.route_capacitated(inst, best_c)
     flags, scores = device.check_solution(inst, x, device.u8_to_f64(best_c), n)
     torch.cuda.synchronize(); dt = time.time() - t0
     out = []
@@ -27,8 +27,8 @@ def run(config, seeds, chains, sweeps, kind="min_delay"):
     return dt, out
 
 if __name__ == "__main__":
-    for chains, sweeps in [(64, 200), (296, 400), (296, 1500)]:
-        dt, out = run("C2", [0, 1], chains, sweeps)
+    for chains, sweeps in [(64, 200), (296, 400), (296, 1200)]:
+        dt, out = run("C2", [0, 1, 2, 3, 4], chains, sweeps)
         print("C2", chains, sweeps, f"{dt:.2f}s", out, flush=True)
     seeds = [s for s in range(64) if ("C5", s) in gold]
     for chains, sweeps in [(8, 100), (32, 300)]:
