@@ -147,8 +147,11 @@ def run_ours(args):
     B = args.batch
     prm = BatchParams(kind="min_delay", lp_iters=args.lp_iters, lp_check_every=args.lp_iters,
                       chains=args.chains, sweeps=args.sweeps)
-    # instances are sharded across ranks by seed: rank r owns seeds [r*B, (r+1)*B) -- no data-path collective
-    host = make_hosts(B, rank * B)
+    # instances are sharded across ranks by seed (weak scaling: B per GPU): rank r owns the contiguous block
+    # sharding.shard_range(world*B, r, world) = [r*B, (r+1)*B) -- no data-path collective
+    from neptune_mip_b200 import sharding
+    lo, hi = sharding.shard_range(world * B, rank, world)
+    host = make_hosts(hi - lo, lo)
     pinned = {k: torch.from_numpy(host[k]).pin_memory() for k in device.InstanceBatch.FIELDS}
     inst = device.InstanceBatch.from_host(host, pinned=pinned)
     torch.cuda.synchronize()
@@ -278,8 +281,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="instances per GPU per step")
     ap.add_argument("--lp-iters", type=int, default=2048)
-    ap.add_argument("--chains", type=int, default=16)
-    ap.add_argument("--sweeps", type=int, default=200)
+    ap.add_argument("--chains", type=int, default=8)
+    ap.add_argument("--sweeps", type=int, default=160)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -16,11 +16,13 @@
 //   + rows*(8 y + 8 S + 16 lo/hi + 8 y' + 16 ysum) + 8*cols (xbar gather)
 //   = 24*nnz + 88*cols + 72*rows.
 #include "common.cuh"
+#include <cub/cub.cuh>
 
 namespace neptune {
 
 constexpr int kLongRow = 2048;      // rows longer than this get a whole block
 constexpr int kShortCol = 8;        // columns of A^T up to this length: one thread each
+constexpr int kTaskNnz = 1024;      // non-zeros per warp task of the row kernel
 constexpr int kShortRow = 8;        // rows of A up to this length (whole 32-row chunk): one thread each
 constexpr int kMaxLongList = 1 << 20;
 
@@ -45,50 +47,88 @@ struct Csr {
 // ---------------------------------------------------------------------------------------------------
 // SpMV cores.  `Epi` consumes one (instance, row, dot) at a time in the thread that owns it.
 // ---------------------------------------------------------------------------------------------------
-// Rows are taken in chunks of 32 consecutive rows per warp.  A chunk whose longest row has at most
-// kShortRow entries (C6, the S rows of the strengthened model, ...) runs one THREAD per row -- 32 rows
-// in flight per warp, and because neighbouring rows sit next to each other in the CSR arrays the
-// loads of the warp still cover contiguous memory.  Otherwise the warp walks the 32 rows one by one
-// with its lanes striding over the row (coalesced 128 B / 256 B segments of col_idx / val, 4 loads in
-// flight per lane) and a shuffle reduction.
+// SpMV over a CSR matrix (A or the stored A^T) whose rows are grouped into warp TASKS: up to 32
+// consecutive rows holding about kTaskNnz non-zeros (build_tasks).  Two kernels share the task list:
+//   k_spmv_short : tasks whose rows all have <= kShortRow entries (the x / c / n columns of A^T, the C6
+//                  and S rows of A): ONE THREAD PER ROW.  Neighbouring rows are neighbours in the CSR
+//                  arrays, so a warp still reads contiguous memory; 8/16 B and 16/32 B vector loads
+//                  for 2- and 4-entry rows; epilogue operands are loaded before the dot product so
+//                  that every load of a row is in flight at once.  Lean (full occupancy).
+//   k_spmv_tasks : the other tasks: the warp walks the rows two at a time, lanes striding over a row
+//                  (coalesced 128 B / 256 B segments of col_idx / val, 4 loads in flight per lane and
+//                  row), shuffle reduction; lane k keeps the dot product of row k and the epilogue
+//                  (vector update) runs once per task with all lanes, coalesced.
+constexpr int32_t kTaskShort = (int32_t)0x80000000;
+
 template <class Epi>
-__global__ void __launch_bounds__(256) k_rows_warp(Csr A, const double* __restrict__ xv, Epi epi) {
+__global__ void __launch_bounds__(256) k_spmv_short(Csr A, const int32_t* __restrict__ tasks,
+                                                    const int32_t* __restrict__ n_tasks,
+                                                    const double* __restrict__ xv, Epi epi) {
   const int b = blockIdx.y;
   if (epi.skip(b)) return;
   const double* __restrict__ val = A.val + (int64_t)b * A.nnz;
   const double* __restrict__ x = xv + (int64_t)b * A.n_cols;
   const double xs = epi.xscale(b);
   const int lane = threadIdx.x & 31;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t nchunks = (A.n_rows + 31) >> 5;
-  for (int64_t ch = warp0; ch < nchunks; ch += nwarps) {
-    const int64_t myrow = (ch << 5) + lane;
-    int64_t q0 = 0, q1 = 0;
-    if (myrow < A.n_rows) { q0 = A.ptr[myrow]; q1 = A.ptr[myrow + 1]; }
+  const int warp0 = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+  const int nt = *n_tasks;
+  for (int ch = warp0; ch < nt; ch += nwarps) {
+    const int32_t t0 = tasks[ch];
+    if (!(t0 & kTaskShort)) continue;
+    const int64_t rb = t0 & ~kTaskShort;
+    const int64_t te = (ch + 1 < nt) ? (int64_t)(tasks[ch + 1] & ~kTaskShort) : A.n_rows;
+    const int64_t myrow = rb + lane;
+    if (myrow >= te) continue;
+    const int64_t q0 = A.ptr[myrow], q1 = A.ptr[myrow + 1];
+    const typename Epi::Pre pre = epi.pre(b, myrow);
     const int mylen = (int)(q1 - q0);
-    int maxlen = mylen;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-    if (maxlen <= kShortRow) {
-      if (myrow < A.n_rows) {
-        double acc = 0.0;
-        if (mylen == 2 && (q0 & 1) == 0) {
-          const int2 c = __ldcs(reinterpret_cast<const int2*>(A.idx + q0));
-          const double2 v = __ldcs(reinterpret_cast<const double2*>(val + q0));
-          acc = v.x * x[c.x];
-          acc += v.y * x[c.y];
-        } else {
-          for (int64_t p = q0; p < q1; ++p) acc += __ldcs(val + p) * x[__ldcs(A.idx + p)];
-        }
-        epi.row(b, myrow, acc * xs);
-      }
-      continue;
+    double acc = 0.0;
+    if (mylen == 2 && (q0 & 1) == 0) {
+      const int2 c = __ldcs(reinterpret_cast<const int2*>(A.idx + q0));
+      const double2 v = __ldcs(reinterpret_cast<const double2*>(val + q0));
+      acc = v.x * x[c.x];
+      acc += v.y * x[c.y];
+    } else if (mylen == 4 && (q0 & 3) == 0) {
+      const int4 c = __ldcs(reinterpret_cast<const int4*>(A.idx + q0));
+      const double2 v01 = __ldcs(reinterpret_cast<const double2*>(val + q0));
+      const double2 v23 = __ldcs(reinterpret_cast<const double2*>(val + q0 + 2));
+      acc = v01.x * x[c.x];
+      acc += v01.y * x[c.y];
+      acc += v23.x * x[c.z];
+      acc += v23.y * x[c.w];
+    } else {
+      for (int64_t p = q0; p < q1; ++p) acc += __ldcs(val + p) * x[__ldcs(A.idx + p)];
     }
-    // Row-by-row over the chunk, two rows in flight; lane k keeps the dot product of row k so that the
-    // epilogue (vector update: 4 reads + 2 writes per row) runs ONCE per chunk with all lanes busy and
-    // coalesced, instead of 32 times in a single lane.
-    const int nr = (int)min((int64_t)32, A.n_rows - (ch << 5));
+    epi.row(b, myrow, acc * xs, pre);
+  }
+  epi.finalize(b);
+}
+
+template <class Epi>
+__global__ void __launch_bounds__(256) k_spmv_tasks(Csr A, const int32_t* __restrict__ tasks,
+                                                    const int32_t* __restrict__ n_tasks,
+                                                    const double* __restrict__ xv, Epi epi) {
+  const int b = blockIdx.y;
+  if (epi.skip(b)) return;
+  const double* __restrict__ val = A.val + (int64_t)b * A.nnz;
+  const double* __restrict__ x = xv + (int64_t)b * A.n_cols;
+  const double xs = epi.xscale(b);
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+  const int nt = *n_tasks;
+  for (int ch = warp0; ch < nt; ch += nwarps) {
+    const int32_t t0 = tasks[ch];
+    if (t0 & kTaskShort) continue;
+    const int64_t rb = t0;
+    const int64_t te = (ch + 1 < nt) ? (int64_t)(tasks[ch + 1] & ~kTaskShort) : A.n_rows;
+    const int nr = (int)(te - rb);
+    const int64_t myrow = rb + lane;
+    const bool mine = lane < nr;
+    int64_t q0 = 0, q1 = 0;
+    if (mine) { q0 = A.ptr[myrow]; q1 = A.ptr[myrow + 1]; }
+    const int mylen = (int)(q1 - q0);
     double myres = 0.0;
     for (int k = 0; k < nr; k += 2) {
       const int64_t p0a = __shfl_sync(0xffffffffu, q0, k), p1a = __shfl_sync(0xffffffffu, q1, k);
@@ -98,27 +138,31 @@ __global__ void __launch_bounds__(256) k_rows_warp(Csr A, const double* __restri
       double acca = 0.0, accb = 0.0;
       int64_t pa = p0a + lane, pb = p0b + lane;
       if (doa) {
-        for (; pa + 32 < p1a; pa += 64) {
-          const int c0 = __ldcs(A.idx + pa), c1 = __ldcs(A.idx + pa + 32);
-          const double v0 = __ldcs(val + pa), v1 = __ldcs(val + pa + 32);
-          acca += v0 * x[c0]; acca += v1 * x[c1];
+        for (; pa + 96 < p1a; pa += 128) {          // 4 index/value loads in flight, then 4 gathers
+          const int c0 = __ldcs(A.idx + pa), c1 = __ldcs(A.idx + pa + 32), c2 = __ldcs(A.idx + pa + 64),
+                    c3 = __ldcs(A.idx + pa + 96);
+          const double v0 = __ldcs(val + pa), v1 = __ldcs(val + pa + 32), v2 = __ldcs(val + pa + 64),
+                       v3 = __ldcs(val + pa + 96);
+          acca += v0 * x[c0]; acca += v1 * x[c1]; acca += v2 * x[c2]; acca += v3 * x[c3];
         }
-        if (pa < p1a) acca += __ldcs(val + pa) * x[__ldcs(A.idx + pa)];
+        for (; pa < p1a; pa += 32) acca += __ldcs(val + pa) * x[__ldcs(A.idx + pa)];
       }
       if (dob) {
-        for (; pb + 32 < p1b; pb += 64) {
-          const int c0 = __ldcs(A.idx + pb), c1 = __ldcs(A.idx + pb + 32);
-          const double v0 = __ldcs(val + pb), v1 = __ldcs(val + pb + 32);
-          accb += v0 * x[c0]; accb += v1 * x[c1];
+        for (; pb + 96 < p1b; pb += 128) {
+          const int c0 = __ldcs(A.idx + pb), c1 = __ldcs(A.idx + pb + 32), c2 = __ldcs(A.idx + pb + 64),
+                    c3 = __ldcs(A.idx + pb + 96);
+          const double v0 = __ldcs(val + pb), v1 = __ldcs(val + pb + 32), v2 = __ldcs(val + pb + 64),
+                       v3 = __ldcs(val + pb + 96);
+          accb += v0 * x[c0]; accb += v1 * x[c1]; accb += v2 * x[c2]; accb += v3 * x[c3];
         }
-        if (pb < p1b) accb += __ldcs(val + pb) * x[__ldcs(A.idx + pb)];
+        for (; pb < p1b; pb += 32) accb += __ldcs(val + pb) * x[__ldcs(A.idx + pb)];
       }
       acca = warp_sum(acca);
       accb = warp_sum(accb);
       if (lane == k) myres = acca;
       if (lane == kb && kb != k) myres = accb;
     }
-    if (myrow < A.n_rows && mylen <= kLongRow) epi.row(b, myrow, myres * xs);
+    if (mine && mylen <= kLongRow) epi.row(b, myrow, myres * xs, epi.pre(b, myrow));
   }
   epi.finalize(b);
 }
@@ -126,7 +170,7 @@ __global__ void __launch_bounds__(256) k_rows_warp(Csr A, const double* __restri
 // block per long row; long rows are found by a strided scan over the row list (`long_rows`,
 // `n_long` written once per solve by k_find_long_rows).
 template <class Epi>
-__global__ void __launch_bounds__(256) k_rows_long(Csr A, const double* __restrict__ xv,
+__global__ void __launch_bounds__(256) k_spmv_long(Csr A, const double* __restrict__ xv,
                                                    const int32_t* __restrict__ long_rows,
                                                    const int32_t* __restrict__ n_long, Epi epi) {
   const int b = blockIdx.y;
@@ -150,9 +194,49 @@ __global__ void __launch_bounds__(256) k_rows_long(Csr A, const double* __restri
     }
     for (; p < p1; p += 256) acc += __ldcs(val + p) * x[__ldcs(A.idx + p)];
     acc = block_sum(acc, sm);
-    if (threadIdx.x == 0) epi.row(b, row, acc * xs);
+    if (threadIdx.x == 0) epi.row(b, row, acc * xs, epi.pre(b, row));
   }
   epi.finalize(b);
+}
+
+// Warp tasks of the row kernel: consecutive rows whose first non-zero falls into the same bucket of
+// kTaskNnz non-zeros form one task (so a task holds about kTaskNnz non-zeros whatever the row lengths;
+// a row longer than a bucket is a task of its own).  tasks[t] = first row of task t.  Built once per
+// solve by an ordered stream compaction (cub::DeviceSelect) -- the pattern is shared by the batch.
+struct TaskStart {
+  const int64_t* ptr;
+  __device__ bool operator()(const int32_t& r) const {
+    // a new task starts where the non-zero bucket changes, and at least every 32 rows
+    return (r & 31) == 0 || (ptr[r] / kTaskNnz) != (ptr[r - 1] / kTaskNnz);
+  }
+};
+
+// mark the tasks whose rows all have <= kShortRow entries (bit 31 of the start row)
+__global__ void k_flag_tasks(const int64_t* __restrict__ ptr, int64_t n_rows, int32_t* __restrict__ tasks,
+                             const int32_t* __restrict__ n_tasks, int32_t* __restrict__ kinds) {
+  const int nt = *n_tasks;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+    const int64_t rb = tasks[t];          // not yet flagged: neighbours are read unflagged or masked below
+    const int64_t re = (t + 1 < nt) ? (int64_t)(tasks[t + 1] & 0x7fffffff) : n_rows;
+    bool sh = true;
+    for (int64_t r = rb; r < re; ++r) sh = sh && (ptr[r + 1] - ptr[r] <= kShortRow);
+    if (sh) { tasks[t] = (int32_t)rb | (int32_t)0x80000000; kinds[0] = 1; } else kinds[1] = 1;
+  }
+}
+
+static int build_tasks(const int64_t* row_ptr, int64_t rows, int32_t* tasks, int32_t* n_tasks, int32_t* kinds,
+                       cudaStream_t s) {
+  cub::CountingInputIterator<int32_t> it(0);
+  size_t tmp_bytes = 0;
+  TaskStart pred{row_ptr};
+  NEPTUNE_CUDA_OK(cub::DeviceSelect::If(nullptr, tmp_bytes, it, tasks, n_tasks, (int)rows, pred, s));
+  void* tmp = nullptr;
+  NEPTUNE_CUDA_OK(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 8, s));
+  NEPTUNE_CUDA_OK(cub::DeviceSelect::If(tmp, tmp_bytes, it, tasks, n_tasks, (int)rows, pred, s));
+  NEPTUNE_COUNT(2);
+  NEPTUNE_CUDA_OK(cudaFreeAsync(tmp, s));
+  { k_flag_tasks<<<kNumSMs * 4, 256, 0, s>>>(row_ptr, rows, tasks, n_tasks, kinds); NEPTUNE_COUNT(1); }
+  return 0;
 }
 
 __global__ void k_find_long_rows(const int64_t* __restrict__ ptr, int64_t n_rows,
@@ -165,64 +249,17 @@ __global__ void k_find_long_rows(const int64_t* __restrict__ ptr, int64_t n_rows
     }
 }
 
-// CSR of A^T: thread per column for [0, split), warp per column for [split, n).
-template <class Epi>
-__global__ void __launch_bounds__(256) k_cols_thread(Csr At, int64_t split, const double* __restrict__ yv,
-                                                     Epi epi) {
-  const int b = blockIdx.y;
-  if (epi.skip(b)) return;
-  const double* __restrict__ val = At.val + (int64_t)b * At.nnz;
-  const double* __restrict__ y = yv + (int64_t)b * At.n_cols;   // At.n_cols == rows of A
-  const double ys = epi.xscale(b);
-  for (int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; col < split;
-       col += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p0 = At.ptr[col], p1 = At.ptr[col + 1];
-    double acc = 0.0;
-    if (p1 - p0 == 4 && (p0 & 3) == 0) {             // the x columns: 16B + 32B vector loads
-      const int4 c = __ldcs(reinterpret_cast<const int4*>(At.idx + p0));
-      const double2 v01 = __ldcs(reinterpret_cast<const double2*>(val + p0));
-      const double2 v23 = __ldcs(reinterpret_cast<const double2*>(val + p0 + 2));
-      acc = v01.x * y[c.x];
-      acc += v01.y * y[c.y];
-      acc += v23.x * y[c.z];
-      acc += v23.y * y[c.w];
-    } else {
-      for (int64_t p = p0; p < p1; ++p) acc += __ldcs(val + p) * y[__ldcs(At.idx + p)];
-    }
-    epi.row(b, col, acc * ys);
-  }
-  epi.finalize(b);
-}
-
-template <class Epi>
-__global__ void __launch_bounds__(256) k_cols_warp(Csr At, int64_t split, const double* __restrict__ yv,
-                                                   Epi epi) {
-  const int b = blockIdx.y;
-  if (epi.skip(b)) return;
-  const double* __restrict__ val = At.val + (int64_t)b * At.nnz;
-  const double* __restrict__ y = yv + (int64_t)b * At.n_cols;
-  const double ys = epi.xscale(b);
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t col = split + warp0; col < At.n_rows; col += nwarps) {
-    const int64_t p0 = At.ptr[col], p1 = At.ptr[col + 1];
-    double acc = 0.0;
-    for (int64_t p = p0 + lane; p < p1; p += 32) acc += __ldcs(val + p) * y[__ldcs(At.idx + p)];
-    acc = warp_sum(acc);
-    if (lane == 0) epi.row(b, col, acc * ys);
-  }
-  epi.finalize(b);
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Epilogues
 // ---------------------------------------------------------------------------------------------------
+struct NoPre {};
 struct StoreEpi {            // plain SpMV
+  typedef NoPre Pre;
   double* out; int64_t n;
   __device__ bool skip(int) const { return false; }
   __device__ double xscale(int) const { return 1.0; }
-  __device__ void row(int b, int64_t r, double v) const { out[(int64_t)b * n + r] = v; }
+  __device__ Pre pre(int, int64_t) const { return Pre{}; }
+  __device__ void row(int b, int64_t r, double v, const Pre&) const { out[(int64_t)b * n + r] = v; }
   __device__ void finalize(int) const {}
 };
 
@@ -232,15 +269,19 @@ struct PrimalUpdate {        // per column, after g = (A^T y)[col]
   double *x, *xbar, *xsum;
   __device__ bool skip(int b) const { return ctl[b].converged != 0; }
   __device__ double xscale(int) const { return 1.0; }
-  __device__ void row(int b, int64_t c, double g) const {
+  struct Pre { double xo, o, t, l, u, s; };
+  __device__ Pre pre(int b, int64_t c) const {
+    const int64_t k = (int64_t)b * cols + c;
+    return Pre{x[k], obj[k], T[k], lb[k], ub[k], xsum[k]};
+  }
+  __device__ void row(int b, int64_t c, double g, const Pre& p) const {
     const int64_t k = (int64_t)b * cols + c;
     const double tau = ctl[b].tau;
-    const double xo = x[k];
-    double xn = xo - tau * T[k] * (obj[k] + g);
-    xn = fmin(fmax(xn, lb[k]), ub[k]);
+    double xn = p.xo - tau * p.t * (p.o + g);
+    xn = fmin(fmax(xn, p.l), p.u);
     x[k] = xn;
-    xbar[k] = 2.0 * xn - xo;
-    xsum[k] += xn;
+    xbar[k] = 2.0 * xn - p.xo;
+    xsum[k] = p.s + xn;
   }
   __device__ void finalize(int) const {}
 };
@@ -251,14 +292,19 @@ struct DualUpdate {          // per row, after a = (A xbar)[row]
   double *y, *ysum;
   __device__ bool skip(int b) const { return ctl[b].converged != 0; }
   __device__ double xscale(int) const { return 1.0; }
-  __device__ void row(int b, int64_t r, double a) const {
+  struct Pre { double yo, sc, l, h, s; };
+  __device__ Pre pre(int b, int64_t r) const {
     const int64_t k = (int64_t)b * rows + r;
-    const double s = ctl[b].sigma * S[k];
-    const double v = y[k] + s * a;
-    const double z = fmin(fmax(v / s, lo[k]), hi[k]);
+    return Pre{y[k], S[k], lo[k], hi[k], ysum[k]};
+  }
+  __device__ void row(int b, int64_t r, double a, const Pre& p) const {
+    const int64_t k = (int64_t)b * rows + r;
+    const double s = ctl[b].sigma * p.sc;
+    const double v = p.yo + s * a;
+    const double z = fmin(fmax(v / s, p.l), p.h);
     const double yn = v - s * z;
     y[k] = yn;
-    ysum[k] += yn;
+    ysum[k] = p.s + yn;
   }
   __device__ void finalize(int) const {}
 };
@@ -271,7 +317,9 @@ struct RowsEval {
   double pres2, dobj, dres2;
   __device__ bool skip(int b) const { return ctl[b].converged != 0; }
   __device__ double xscale(int b) const { return which ? 1.0 / (double)max(ctl[b].avg_count, 1) : 1.0; }
-  __device__ void row(int b, int64_t r, double a) {
+  typedef NoPre Pre;
+  __device__ Pre pre(int, int64_t) const { return Pre{}; }
+  __device__ void row(int b, int64_t r, double a, const Pre&) {
     const int64_t k = (int64_t)b * rows + r;
     const double l = lo[k], h = hi[k];
     const double viol = a - fmin(fmax(a, l), h);
@@ -299,7 +347,9 @@ struct ColsEval {
   double pobj, dobj, dres2;
   __device__ bool skip(int b) const { return ctl[b].converged != 0; }
   __device__ double xscale(int b) const { return which ? 1.0 / (double)max(ctl[b].avg_count, 1) : 1.0; }
-  __device__ void row(int b, int64_t c, double g) {
+  typedef NoPre Pre;
+  __device__ Pre pre(int, int64_t) const { return Pre{}; }
+  __device__ void row(int b, int64_t c, double g, const Pre&) {
     const int64_t k = (int64_t)b * cols + c;
     const double o = obj[k];
     pobj += o * xv[k] * xscale(b);
@@ -535,39 +585,50 @@ static inline int grid1(int64_t work, int threads, int per_sm) {
   return (int)(g < 1 ? 1 : g);
 }
 
+struct Side {              // one matrix (A or A^T) with its launch schedule
+  Csr M;
+  int32_t* tasks; int32_t* n_tasks;       // warp tasks (device)
+  int32_t* long_rows; int32_t* n_long;    // rows longer than kLongRow (device list)
+  int n_long_h;                           // ... and their number on the host (0: that launch is skipped)
+  int has_short, has_wide;                // which task kinds exist (a launch without work is skipped)
+};
+
 struct Plan {
-  int B; int64_t rows, cols, nnz; int64_t split;
-  Csr A, At;
-  int32_t* long_rows; int32_t* n_long;
+  int B; int64_t rows, cols, nnz;
+  Side A, At;
   cudaStream_t s;
 };
 
 template <class Epi>
-static void launch_rows(const Plan& P, const double* xv, Epi epi) {
-  dim3 g(grid1(P.rows, 256, 16), P.B);   // one warp per 32-row chunk
-  { k_rows_warp<Epi><<<g, 256, 0, P.s>>>(P.A, xv, epi); NEPTUNE_COUNT(1); }
-  dim3 gl(kNumSMs * 2, P.B);
-  { k_rows_long<Epi><<<gl, 256, 0, P.s>>>(P.A, xv, P.long_rows, P.n_long, epi); NEPTUNE_COUNT(1); }
-}
-
-template <class Epi>
-static void launch_cols(const Plan& P, const double* yv, Epi epi) {
-  if (P.split > 0) {
-    dim3 g(grid1(P.split, 256, 16), P.B);
-    { k_cols_thread<Epi><<<g, 256, 0, P.s>>>(P.At, P.split, yv, epi); NEPTUNE_COUNT(1); }
-  }
-  if (P.split < P.cols) {
-    dim3 g(grid1((P.cols - P.split) * 32, 256, 16), P.B);
-    { k_cols_warp<Epi><<<g, 256, 0, P.s>>>(P.At, P.split, yv, epi); NEPTUNE_COUNT(1); }
+static void launch_side(const Plan& P, const Side& S, const double* v, Epi epi) {
+  dim3 g(grid1(S.M.n_rows, 256, 16), P.B);     // warps stride over the task list
+  if (S.has_short) { k_spmv_short<Epi><<<g, 256, 0, P.s>>>(S.M, S.tasks, S.n_tasks, v, epi); NEPTUNE_COUNT(1); }
+  if (S.has_wide) { k_spmv_tasks<Epi><<<g, 256, 0, P.s>>>(S.M, S.tasks, S.n_tasks, v, epi); NEPTUNE_COUNT(1); }
+  if (S.n_long_h > 0) {
+    dim3 gl(S.n_long_h < kNumSMs * 2 ? S.n_long_h : kNumSMs * 2, P.B);
+    { k_spmv_long<Epi><<<gl, 256, 0, P.s>>>(S.M, v, S.long_rows, S.n_long, epi); NEPTUNE_COUNT(1); }
   }
 }
+template <class Epi> static void launch_rows(const Plan& P, const double* xv, Epi epi) { launch_side(P, P.A, xv, epi); }
+template <class Epi> static void launch_cols(const Plan& P, const double* yv, Epi epi) { launch_side(P, P.At, yv, epi); }
 
-// first column of A^T whose length exceeds kShortCol (columns are assumed sorted short -> long,
-// which holds for the placement model: x columns, then c, then n); found on device.
-__global__ void k_find_split(const int64_t* __restrict__ ptr, int64_t n, unsigned long long* split) {
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n;
-       c += (int64_t)gridDim.x * blockDim.x)
-    if (ptr[c + 1] - ptr[c] > kShortCol) atomicMin(split, (unsigned long long)c);
+// pattern analysis of one matrix: warp tasks + long-row list (device scratch carved from `mem`)
+static size_t side_scratch_bytes(int64_t n_rows) { return (size_t)(n_rows + 2) * 4 + (size_t)kMaxLongList * 4 + 512; }
+
+static int analyse_side(Side& S, char* mem, cudaStream_t s) {
+  S.tasks = (int32_t*)mem; mem += (((size_t)(S.M.n_rows + 2) * 4 + 255) & ~(size_t)255);
+  S.long_rows = (int32_t*)mem; mem += (size_t)kMaxLongList * 4;
+  S.n_tasks = (int32_t*)mem; S.n_long = S.n_tasks + 1;
+  int32_t* kinds = S.n_tasks + 2;
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(S.n_tasks, 0, 16, s));
+  { int rc = build_tasks(S.M.ptr, S.M.n_rows, S.tasks, S.n_tasks, kinds, s); if (rc) return rc; }
+  { k_find_long_rows<<<grid1(S.M.n_rows, 256, 8), 256, 0, s>>>(S.M.ptr, S.M.n_rows, S.long_rows, S.n_long); NEPTUNE_COUNT(1); }
+  int h[3] = {0, 0, 0};
+  NEPTUNE_CUDA_OK(cudaMemcpyAsync(h, S.n_long, 12, cudaMemcpyDeviceToHost, s));
+  NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
+  S.n_long_h = h[0] < kMaxLongList ? h[0] : kMaxLongList;
+  S.has_short = h[1]; S.has_wide = h[2];
+  return 0;
 }
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -583,25 +644,30 @@ extern "C" int neptune_pdhg_workspace_bytes(int B, int64_t rows, int64_t cols, i
   t += 5 * align256((size_t)B * cols * 8);     // xbar, xsum, xrestart, T(dc), colacc
   t += 4 * align256((size_t)B * rows * 8);     // ysum, yrestart, S(dr), rowacc
   t += align256((size_t)B * sizeof(Ctl));
-  t += align256((size_t)kMaxLongList * 4) + 256 + 256;
+  t += align256(side_scratch_bytes(rows)) + align256(side_scratch_bytes(cols));
+  t += 1024;
   *bytes = (int64_t)t;
+  return 0;
+}
+
+static int nnz_of(const int64_t* ptr, int64_t n, int64_t* nnz, cudaStream_t s) {
+  NEPTUNE_CUDA_OK(cudaMemcpyAsync(nnz, ptr + n, 8, cudaMemcpyDeviceToHost, s));
+  NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
   return 0;
 }
 
 extern "C" int neptune_spmv(int B, int64_t rows, int64_t cols, const int64_t* row_ptr, const int32_t* col_idx,
                             const double* val, const double* x, double* out, void* stream) {
-  if (B <= 0 || !row_ptr || !col_idx || !val || !x || !out) return NEPTUNE_E_ARG;
-  // rows longer than kLongRow need the long-row list; build it in a small temporary
+  if (B <= 0 || rows <= 0 || cols <= 0 || !row_ptr || !col_idx || !val || !x || !out) return NEPTUNE_E_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  int32_t* tmp = nullptr;
-  NEPTUNE_CUDA_OK(cudaMallocAsync(&tmp, (size_t)kMaxLongList * 4 + 256, s));
-  int32_t* n_long = tmp + kMaxLongList;
-  NEPTUNE_CUDA_OK(cudaMemsetAsync(n_long, 0, 4, s));
-  { k_find_long_rows<<<grid1(rows, 256, 8), 256, 0, s>>>(row_ptr, rows, tmp, n_long); NEPTUNE_COUNT(1); }
-  int64_t nnz = 0;   // per-instance stride of val: read row_ptr[rows] (device) -> need it on host
-  NEPTUNE_CUDA_OK(cudaMemcpyAsync(&nnz, row_ptr + rows, 8, cudaMemcpyDeviceToHost, s));
-  NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
-  Plan P{B, rows, cols, nnz, 0, Csr{row_ptr, col_idx, val, rows, cols, nnz}, Csr{}, tmp, n_long, s};
+  int64_t nnz = 0;
+  { int rc = nnz_of(row_ptr, rows, &nnz, s); if (rc) return rc; }
+  char* tmp = nullptr;
+  NEPTUNE_CUDA_OK(cudaMallocAsync(&tmp, side_scratch_bytes(rows), s));
+  Plan P{};
+  P.B = B; P.rows = rows; P.cols = cols; P.nnz = nnz; P.s = s;
+  P.A.M = Csr{row_ptr, col_idx, val, rows, cols, nnz};
+  { int rc = analyse_side(P.A, tmp, s); if (rc) return rc; }
   launch_rows(P, x, StoreEpi{out, rows});
   NEPTUNE_LAUNCH_OK();
   NEPTUNE_CUDA_OK(cudaFreeAsync(tmp, s));
@@ -611,22 +677,19 @@ extern "C" int neptune_spmv(int B, int64_t rows, int64_t cols, const int64_t* ro
 extern "C" int neptune_spmv_t(int B, int64_t rows, int64_t cols, const int64_t* rowT_ptr,
                               const int32_t* colT_idx, const double* valT, const double* y, double* out,
                               void* stream) {
-  if (B <= 0 || !rowT_ptr || !colT_idx || !valT || !y || !out) return NEPTUNE_E_ARG;
+  if (B <= 0 || rows <= 0 || cols <= 0 || !rowT_ptr || !colT_idx || !valT || !y || !out) return NEPTUNE_E_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  unsigned long long* d_split = nullptr;
-  NEPTUNE_CUDA_OK(cudaMallocAsync(&d_split, 8, s));
-  unsigned long long h_split = (unsigned long long)cols;
-  NEPTUNE_CUDA_OK(cudaMemcpyAsync(d_split, &h_split, 8, cudaMemcpyHostToDevice, s));
-  { k_find_split<<<grid1(cols, 256, 8), 256, 0, s>>>(rowT_ptr, cols, d_split); NEPTUNE_COUNT(1); }
   int64_t nnz = 0;
-  NEPTUNE_CUDA_OK(cudaMemcpyAsync(&nnz, rowT_ptr + cols, 8, cudaMemcpyDeviceToHost, s));
-  NEPTUNE_CUDA_OK(cudaMemcpyAsync(&h_split, d_split, 8, cudaMemcpyDeviceToHost, s));
-  NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
-  Plan P{B, rows, cols, nnz, (int64_t)h_split, Csr{}, Csr{rowT_ptr, colT_idx, valT, cols, rows, nnz},
-         nullptr, nullptr, s};
+  { int rc = nnz_of(rowT_ptr, cols, &nnz, s); if (rc) return rc; }
+  char* tmp = nullptr;
+  NEPTUNE_CUDA_OK(cudaMallocAsync(&tmp, side_scratch_bytes(cols), s));
+  Plan P{};
+  P.B = B; P.rows = rows; P.cols = cols; P.nnz = nnz; P.s = s;
+  P.At.M = Csr{rowT_ptr, colT_idx, valT, cols, rows, nnz};
+  { int rc = analyse_side(P.At, tmp, s); if (rc) return rc; }
   launch_cols(P, y, StoreEpi{out, cols});
   NEPTUNE_LAUNCH_OK();
-  NEPTUNE_CUDA_OK(cudaFreeAsync(d_split, s));
+  NEPTUNE_CUDA_OK(cudaFreeAsync(tmp, s));
   return 0;
 }
 
@@ -657,22 +720,18 @@ extern "C" int neptune_pdhg_solve(int B, int64_t rows, int64_t cols, int64_t nnz
   double* ysum = (double*)take(rb); double* yres = (double*)take(rb);
   double* S = (double*)take(rb); double* rowacc = (double*)take(rb);
   Ctl* ctl = (Ctl*)take((size_t)B * sizeof(Ctl));
-  int32_t* long_rows = (int32_t*)take((size_t)kMaxLongList * 4);
-  int32_t* n_long = (int32_t*)take(4);
-  unsigned long long* d_split = (unsigned long long*)take(8);
+  char* scrA = take(side_scratch_bytes(rows));
+  char* scrT = take(side_scratch_bytes(cols));
 
   Csr A{row_ptr, col_idx, val, rows, cols, nnz};
   Csr At{rowT_ptr, colT_idx, valT, cols, rows, nnz};
 
-  // one-off analysis of the pattern
-  NEPTUNE_CUDA_OK(cudaMemsetAsync(n_long, 0, 4, s));
-  unsigned long long h_split = (unsigned long long)cols;
-  NEPTUNE_CUDA_OK(cudaMemcpyAsync(d_split, &h_split, 8, cudaMemcpyHostToDevice, s));
-  { k_find_long_rows<<<grid1(rows, 256, 8), 256, 0, s>>>(row_ptr, rows, long_rows, n_long); NEPTUNE_COUNT(1); }
-  { k_find_split<<<grid1(cols, 256, 8), 256, 0, s>>>(rowT_ptr, cols, d_split); NEPTUNE_COUNT(1); }
-  NEPTUNE_CUDA_OK(cudaMemcpyAsync(&h_split, d_split, 8, cudaMemcpyDeviceToHost, s));
-  NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
-  Plan P{B, rows, cols, nnz, (int64_t)h_split, A, At, long_rows, n_long, s};
+  // one-off analysis of the (batch-shared) pattern: warp tasks and long-row lists of both copies
+  Plan P{};
+  P.B = B; P.rows = rows; P.cols = cols; P.nnz = nnz; P.s = s;
+  P.A.M = A; P.At.M = At;
+  { int rc = analyse_side(P.A, scrA, s); if (rc) return rc; }
+  { int rc = analyse_side(P.At, scrT, s); if (rc) return rc; }
 
   // equilibration: dr = S, dc = T hold the scalings, squared at the end
   const int g_c = grid1((int64_t)B * cols, 256, 16), g_r = grid1((int64_t)B * rows, 256, 16);

@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
   // capacity-aware routing of route_cap.cuh.  A rejected proposal is undone and kept tabu until the state
   // changes or the chain is kicked.
   int stall = 0;
+  bool stage2 = false;
   n_tabu = 0;
   for (int sweep = 0; sweep < a.sweeps; ++sweep) {
     // ---- pod list -------------------------------------------------------------------------------------
@@ -407,7 +408,9 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
     const int64_t n_exch = pp < kMaxExchange ? pp : kMaxExchange;
     const int64_t ex_off = (int64_t)(s_rand[0] % (uint64_t)(pp > 0 ? pp : 1));        // block-uniform
     const int64_t ex_stride = pp > kMaxExchange ? (int64_t)(2 * (s_rand[1] % 4096) + 1) : 1;
-    const int64_t total = n_add + n_drop + n_swap + n_rep + n_exch;
+    // two-stage neighbourhood: the (quadratic) exchange moves are only examined once the basic
+    // add / drop / swap / replace neighbourhood has no improving proposal left
+    const int64_t total = n_add + n_drop + n_swap + n_rep + (stage2 ? n_exch : 0);
     double my_best = -1e-9 * (1.0 + fabs(cur_total));      // only strictly improving proposals
     Move my_mv{MV_NONE, 0, 0, 0};
     const int ntb = n_tabu;
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
       const double nt = true_total(nc);
       if (nt < cur_true - 1e-9 * (1.0 + fabs(cur_true))) {
         cur = nc; cur_total = total_of(nc); cur_true = nt;
-        stall = 0;
+        stall = 0; stage2 = false;
         if (tid == 0) n_tabu = 0;
         __syncthreads();
       } else {
@@ -506,7 +509,9 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
         mv.type = MV_NONE;                          // too many rejections: treat as a local optimum
       }
     }
+    if (mv.type == MV_NONE && !stage2) { stage2 = true; if (tid == 0) n_tabu = 0; __syncthreads(); continue; }
     if (mv.type == MV_NONE) {
+      stage2 = false;
       // ---- local optimum: keep the best, restart from it with a kick -----------------------------------
       save_best();
       if (best_total < INFINITY) {
