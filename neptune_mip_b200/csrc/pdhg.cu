@@ -707,7 +707,16 @@ extern "C" int neptune_pdhg_solve(int B, int64_t rows, int64_t cols, int64_t nnz
   int64_t need = 0;
   neptune_pdhg_workspace_bytes(B, rows, cols, nnz, &need);
   if (workspace_bytes < need) return NEPTUNE_E_NOMEM;
-  cudaStream_t s = (cudaStream_t)stream;
+  // work on an internal stream (the caller's may be the legacy default stream, which cannot be
+  // captured into a graph); ordered after / before the caller's stream with events
+  cudaStream_t caller = (cudaStream_t)stream;
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  NEPTUNE_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  NEPTUNE_CUDA_OK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+  NEPTUNE_CUDA_OK(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
+  NEPTUNE_CUDA_OK(cudaEventRecord(ev_in, caller));
+  NEPTUNE_CUDA_OK(cudaStreamWaitEvent(s, ev_in, 0));
   const int check_every = prm->check_every > 0 ? prm->check_every : 64;
   const int max_iters = prm->max_iters > 0 ? prm->max_iters : 20000;
 
@@ -768,8 +777,34 @@ extern "C" int neptune_pdhg_solve(int B, int64_t rows, int64_t cols, int64_t nnz
 
   PrimalUpdate pu{ctl, cols, obj, col_lb, col_ub, T, x, xbar, xsum};
   DualUpdate du{ctl, rows, lo, hi, S, y, ysum};
+  // The inner loop is launch-bound for small batches and exposed to host jitter otherwise: `inner`
+  // iterations (2-6 launches each) are captured once into a CUDA graph and replayed; step sizes, restart
+  // flags and convergence live in device memory (Ctl), so the graph never changes.
+  const int inner = check_every < 32 ? check_every : 32;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  int64_t per_graph = 0;
+  {
+    int64_t c0 = 0, c1 = 0;
+    neptune_launch_count(&c0, 0);
+    NEPTUNE_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    for (int k = 0; k < inner; ++k) {
+      launch_cols(P, y, pu);
+      launch_rows(P, xbar, du);
+    }
+    NEPTUNE_CUDA_OK(cudaStreamEndCapture(s, &graph));
+    NEPTUNE_CUDA_OK(cudaGraphInstantiate(&gexec, graph, 0));
+    neptune_launch_count(&c1, 0);
+    per_graph = c1 - c0;
+    NEPTUNE_COUNT(-per_graph);                      // the capture itself ran nothing
+  }
   for (int it = 0; it < max_iters && !h_flag; it += check_every) {
-    for (int k = 0; k < check_every; ++k) {
+    int done = 0;
+    for (; done + inner <= check_every; done += inner) {
+      NEPTUNE_CUDA_OK(cudaGraphLaunch(gexec, s));
+      NEPTUNE_COUNT(per_graph);
+    }
+    for (; done < check_every; ++done) {
       launch_cols(P, y, pu);
       launch_rows(P, xbar, du);
     }
@@ -790,7 +825,14 @@ extern "C" int neptune_pdhg_solve(int B, int64_t rows, int64_t cols, int64_t nnz
     NEPTUNE_CUDA_OK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, s));
     NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
   }
+  cudaGraphExecDestroy(gexec);
+  cudaGraphDestroy(graph);
   NEPTUNE_LAUNCH_OK();
   NEPTUNE_CUDA_OK(cudaFreeAsync(d_flag, s));
+  NEPTUNE_CUDA_OK(cudaEventRecord(ev_out, s));
+  NEPTUNE_CUDA_OK(cudaStreamWaitEvent(caller, ev_out, 0));
+  NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
+  cudaEventDestroy(ev_in); cudaEventDestroy(ev_out);
+  cudaStreamDestroy(s);
   return 0;
 }
