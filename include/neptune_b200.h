@@ -137,6 +137,33 @@ int neptune_spmv_t(int B, int64_t rows, int64_t cols, const int64_t* rowT_ptr,
                    const int32_t* colT_idx, const double* valT, const double* y, double* out,
                    void* stream);
 
+/* ---- (b') step-wise PDHG building blocks for the function-block-sharded solver (one process per GPU,
+ * SURVEY.md section 8(e)): GPU g owns the functions of its block, i.e. the x / c columns and the C1 / C3
+ * rows of those functions; the coupling rows (C2 memory, C4 CPU) are replicated, every GPU computes
+ * their partial activity over its own columns, the caller all-reduces (NCCL) and applies the update.
+ * Step sizes are host scalars.  `plan` / `meta_h` come from neptune_spmv_plan (pattern analysed once). */
+int neptune_spmv_plan_bytes(int64_t n_rows, int64_t* bytes);
+int neptune_spmv_plan(int64_t n_rows, const int64_t* ptr, void* plan, int32_t* meta_h, void* stream);
+int neptune_pdhg_primal_step(int B, int64_t rows, int64_t cols, int64_t nnz, const int64_t* rowT_ptr,
+                             const int32_t* colT_idx, const double* valT, void* planT, const int32_t* metaT_h,
+                             const double* obj, const double* col_lb, const double* col_ub, const double* T,
+                             double tau, const double* y, double* x, double* xbar, double* xsum, void* stream);
+/* rows in [d0,d1) and [d2,d3) are deferred: their activity (A xbar)[r] is written to
+ * act[B][(d1-d0)+(d3-d2)] instead of being applied */
+int neptune_pdhg_dual_step(int B, int64_t rows, int64_t cols, int64_t nnz, const int64_t* row_ptr,
+                           const int32_t* col_idx, const double* val, void* plan, const int32_t* meta_h,
+                           const double* lo, const double* hi, const double* S, double sigma, const double* xbar,
+                           double* y, double* ysum, int64_t d0, int64_t d1, int64_t d2, int64_t d3, double* act,
+                           void* stream);
+int neptune_pdhg_dual_rows(int B, int64_t rows, int64_t d0, int64_t d1, int64_t d2, int64_t d3, double sigma,
+                           const double* act, const double* lo, const double* hi, const double* S, double* y,
+                           double* ysum, void* stream);
+/* |A| column sums / row sums (use_sum=1) or maxima (use_sum=0) under the scalings dr, dc; rowacc is
+ * accumulated with atomics (zero it first); free rows (-inf,+inf) are ignored */
+int neptune_abs_sums(int B, int64_t rows, int64_t cols, int64_t nnz, const int64_t* rowT_ptr,
+                     const int32_t* colT_idx, const double* valT, const double* lo, const double* hi,
+                     const double* dr, const double* dc, int use_sum, double* colacc, double* rowacc, void* stream);
+
 /* ---- (c) exact evaluation, rounding, local search -------------------------------------------------
  * neptune_check_solution: the reference's six checkers and three scorers
  * (`efttc/utils/constraints_step1.py:5-133`, `efttc/utils/objectives.py:23-98`) on dense

@@ -1,0 +1,57 @@
+"""torchrun entry: function-block-sharded PDHG vs the unsharded iteration (parity) and timing.
+  python -m torch.distributed.run --nproc-per-node 2 tools/sharded_run.py parity|time N F [iters]"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch, torch.distributed as dist
+from neptune_mip_b200 import synth, sharding
+from neptune_mip_b200.core.utils import data_to_solver_input
+from neptune_mip_b200.sharded import ShardedLP
+
+mode, N, F = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+iters = int(sys.argv[4]) if len(sys.argv) > 4 else 100
+backend = os.environ.get("NEPTUNE_DIST_BACKEND", "nccl")
+rank, ws, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+ngpu = torch.cuda.device_count()
+torch.cuda.set_device(local % ngpu)
+dist.init_process_group(backend, **({"device_id": torch.device("cuda", local)} if backend == "nccl" else {}))
+data = data_to_solver_input(synth.random_payload(N, F, 0, node_cores=None), 1, with_db=False)
+lp = ShardedLP(data)
+if mode == "parity":
+    lp.iterate(iters)
+    obj = lp.primal_objective()
+    # gather x blocks (x columns of this rank's functions) and the replicated coupling multipliers
+    xloc = lp.x[0, : lp.Fg * N * N].reshape(lp.Fg, N * N).contiguous()
+    if backend != "nccl":
+        xall = sharding.gather_rows(xloc.cpu(), F)
+    else:
+        xall = sharding.gather_rows(xloc, F).cpu()
+    ycoup = lp._coupling(lp.y).cpu()
+    if rank == 0:
+        # reference: the same iteration with every function on one rank (no exchange)
+        import neptune_mip_b200.sharded as sh
+        sh.world = lambda: (0, 1)
+        ref = ShardedLP(data)
+        ref.iterate(iters)
+        xr = ref.x[0, : F * N * N].reshape(F, N * N).cpu()
+        yr = ref._coupling(ref.y).cpu()
+        robj = float((ref.model.obj * ref.x).sum())
+        dx = float((xall - xr).abs().max()); dy = float((ycoup - yr).abs().max())
+        print(f"PARITY world={ws} N={N} F={F} iters={iters} max|dx|={dx:.3e} max|dy_coupling|={dy:.3e} "
+              f"obj sharded={obj:.9g} single={robj:.9g}", flush=True)
+        assert dx <= 1e-8 * (1 + float(xr.abs().max())) and dy <= 1e-8 * (1 + float(yr.abs().max()))
+        assert abs(obj - robj) <= 1e-9 * (1 + abs(robj))
+else:
+    lp.iterate(5)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); lp.iterate(iters); e1.record(); e1.synchronize()
+    ms = sharding.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    by, ex = lp.bytes_per_iteration()
+    obj_avg = lp.primal_objective(True)          # collective: every rank must call it
+    if rank == 0:
+        m = lp.model
+        print(f"TIME world={ws} N={N} F={F} (Fg={lp.Fg}) local rows={m.rows} cols={m.cols} nnz={m.nnz} "
+              f"{ms / iters * 1e3:.1f} us/iter  {by * iters / ms / 1e6:.1f} GB/s per GPU  exchange {ex} B/iter "
+              f"obj={obj_avg:.6g}", flush=True)
+dist.destroy_process_group()
