@@ -215,6 +215,20 @@ int neptune_local_search(int B, int N, int F, int kind, double alpha, int chains
                          void* workspace, int64_t workspace_bytes, void* stream);
 int neptune_local_search_workspace_bytes(int B, int N, int F, int chains, int64_t* bytes);
 
+/* neptune_disruption_search: step 2 "minimise disruption" (reference NeptuneStep2*, neptune_step2.py:5-93,
+ * constraints_step2.py:5-89, objectives.py:55-63) as a search over placements with the step-2 objective in
+ * closed form: W*|c xor old| - (W+1)*(sum_old - sum_c) for mode 1 ("delete", needs sum_c <= sum_old),
+ * W*|c xor old| - (W-1)*(sum_c - sum_old) for mode 2 ("create"), W = F*N, subject to the step-1 rows and
+ * to step-1 objective(kind) <= bound[b] (= soften_step1_sol * step-1 score).  Same workspace as
+ * neptune_local_search.  best_obj[b] = +inf when no chain found a placement satisfying mode and bound. */
+int neptune_disruption_search(int B, int N, int F, int kind, double alpha, int mode, const double* bound,
+                              int chains, int sweeps, uint64_t rng_seed, int S,
+                              const double* d, const double* w, const double* r, const double* m,
+                              const double* Mj, const double* Kj, const double* maxd,
+                              const double* cost, double budget, const double* old,
+                              const uint8_t* seeds, uint8_t* best_c, double* best_obj, int32_t* best_flags,
+                              void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- (d) EFTTC greedy -----------------------------------------------------------------------------
  * Replaces `EfttcStepBase.solve()` (`core/solvers/efttc/efttc_step1.py:39-90` and helpers
  * :92-312, score_local :356-439).  One thread block per instance; deterministic, same

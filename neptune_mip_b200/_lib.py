@@ -57,6 +57,7 @@ _SIGNATURES = {
     "neptune_route_capacitated": [_i, _i, _i] + [_p] * 10 + [_p],
     "neptune_eval_placements": [_i, _i, _i, _i, _d] + _INST + [_p] * 4 + [_p],
     "neptune_local_search": [_i, _i, _i, _i, _d, _i, _i, C.c_uint64, _i] + _INST + [_p] * 6 + [_p, _i64, _p],
+    "neptune_disruption_search": [_i, _i, _i, _i, _d, _i, _p, _i, _i, C.c_uint64, _i] + _INST + [_p] * 5 + [_p, _i64, _p],
     "neptune_local_search_workspace_bytes": [_i, _i, _i, _i, C.POINTER(_i64)],
     "neptune_efttc": [_i, _i, _i, _i, _d] + [_p] * 8 + [_d] + [_p] * 3 + [_p, _i64, _p],
     "neptune_efttc_workspace_bytes": [_i, _i, _i, C.POINTER(_i64)],

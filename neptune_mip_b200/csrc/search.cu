@@ -24,6 +24,8 @@ struct LsArgs {
   const double *d, *w, *r, *m, *Mj, *Kj, *maxd, *cost, *old;
   const uint8_t* seeds;
   const double* guide;
+  int step2_mode;            // 0: step-1 objective; 1 "delete" / 2 "create": minimise disruption (step 2)
+  const double* bound;       // [B] step 2: the step-1 objective of the placement must stay <= bound[b]
   // workspace
   double* dT;          // [B][N][N]
   double* inst_scal;   // [B][4]: wmax, mu, a_d, a_u
@@ -127,27 +129,41 @@ __device__ void node_state(const LsArgs& a, const Chain& k, const double* w, con
   }
 }
 
-struct Cost { double delay, util, over, uncov; };
+struct Cost { double delay, util, over, uncov, flips, pods, memover; };
 
 // whole-block exact cost of the current state (after route_f for all f and node_state)
 __device__ Cost full_cost(const LsArgs& a, const Chain& k, const double* w, const double* Kj, double* red) {
   const int N = a.N, F = a.F;
-  double dl = 0.0, ut = 0.0, ov = 0.0, uc = 0.0;
+  double dl = 0.0, ut = 0.0, ov = 0.0, uc = 0.0, fl = 0.0, pd = 0.0;
   for (int f = threadIdx.x; f < F; f += blockDim.x) if (k.cntf[f] == 0) uc += 1.0;
+  if (a.step2_mode) {
+    const double* old = a.old + (int64_t)blockIdx.y * F * N;
+    for (int q = threadIdx.x; q < F * N; q += blockDim.x) {
+      const bool on = k.c[q] != 0, was = old[q] > 0.0;
+      if (on != was) fl += 1.0;
+      if (on) pd += 1.0;
+    }
+  }
   for (int fi = threadIdx.x; fi < F * N; fi += blockDim.x) {
     const double wv = w[fi];
     if (wv != 0.0) dl += wv * k.b1[fi];
   }
+  double mo = 0.0;
+  const double* Mj = a.Mj + (int64_t)blockIdx.y * N;
   for (int j = threadIdx.x; j < N; j += blockDim.x) {
     if (k.cntn[j]) ut += 1.0;
     const double ex = k.load[j] - Kj[j];
     if (ex > 1e-9) ov += ex;
+    if (k.mem[j] > Mj[j]) mo += k.mem[j] - Mj[j];       // only a seed can bring this in; moves never add to it
   }
   Cost c;
   c.delay = block_sum(dl, red); __syncthreads();
   c.util = block_sum(ut, red); __syncthreads();
   c.over = block_sum(ov, red); __syncthreads();
   c.uncov = block_sum(uc, red); __syncthreads();
+  c.flips = block_sum(fl, red); __syncthreads();
+  c.pods = block_sum(pd, red); __syncthreads();
+  c.memover = block_sum(mo, red); __syncthreads();
   __shared__ Cost bc;
   if (threadIdx.x == 0) bc = c;
   __syncthreads();
@@ -331,7 +347,29 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
     node_state(a, k, w, r, m);
     __syncthreads();
   };
-  auto total_of = [&](const Cost& c) { return a_d * c.delay + a_u * c.util + mu * c.over + kCoverage * c.uncov; };
+  // step 2 (reference neptune_step2.py / constraints_step2.py / objectives.py:55-63), closed form for a
+  // fixed placement: W*|c xor old| - (W+1)*(sum_old - sum_c) in "delete" mode (needs sum_c <= sum_old),
+  // W*|c xor old| - (W-1)*(sum_c - sum_old) in "create" mode (needs sum_c >= sum_old); the step-1
+  // objective must stay below bound = soften_step1_sol * step-1 score.
+  const int mode2 = a.step2_mode;
+  const double Wd = (double)F * (double)N;
+  double sold = 0.0;
+  if (mode2) { const double* old = a.old + (int64_t)b * F * N; for (int q = 0; q < F * N; ++q) sold += old[q] > 0.0; }
+  const double bound2 = mode2 ? a.bound[b] : 0.0;
+  const double pen_unit = 4.0 * Wd * Wd + 1.0;      // larger than any feasible step-2 objective value
+  auto disruption = [&](double flips, double pods) -> double {
+    const double delta = sold - pods;
+    if (mode2 == 1) return Wd * flips + (delta >= 0.0 ? -(Wd + 1.0) * delta : pen_unit * (-delta));
+    return Wd * flips + (delta <= 0.0 ? (Wd - 1.0) * delta : pen_unit * delta);
+  };
+  auto objective = [&](double delay, double util, double over, double uncov, double flips, double pods, double mu_) {
+    const double o1 = a_d * delay + a_u * util;
+    if (!mode2) return o1 + mu_ * over + kCoverage * uncov;
+    const double ex = o1 - bound2 * (1.0 + 1e-12);
+    return disruption(flips, pods) + (ex > 0.0 ? 10.0 * pen_unit * (1.0 + ex / fmax(fabs(bound2), 1e-9)) : 0.0) +
+           mu_ * over + kCoverage * uncov;
+  };
+  auto total_of = [&](const Cost& c) { return objective(c.delay, c.util, c.over, c.uncov, c.flips, c.pods, mu) + kCoverage * c.memover; };
 
   // random kick: `n` random swap / replace changes that keep memory feasible (thread 0)
   auto kick = [&](int n) {
@@ -369,18 +407,18 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
   const double mu_big = scal[0];
   // true cost of the current state (block-uniform; all threads must call)
   auto true_total = [&](const Cost& c) -> double {
-    const double base = a_u * c.util + kCoverage * c.uncov;
-    if (c.uncov > 0.0) return a_d * c.delay + base + mu_big * c.over;
-    if (c.over <= 0.0) return a_d * c.delay + base;
+    if (c.uncov > 0.0 || c.memover > 0.0)
+      return objective(c.delay, c.util, c.over, c.uncov, c.flips, c.pods, mu_big) + kCoverage * c.memover;
+    if (c.over <= 0.0) return objective(c.delay, c.util, 0.0, 0.0, c.flips, c.pods, 0.0);
     CapRoute q{N, F, d, w, r, Kj, k.c, k.ch, k.sec, k.th, k.rho, k.alt, k.cload, k.lam};
     const CapResult cr = cap_route(q, 48, red, capsh);
-    if (cr.feasible) return a_d * cr.cost + base;
-    return a_d * c.delay + base + mu_big * c.over + kUnrepairable;
+    if (cr.feasible) return objective(cr.cost, c.util, 0.0, 0.0, c.flips, c.pods, 0.0);
+    return objective(c.delay, c.util, c.over, 0.0, c.flips, c.pods, mu_big) + (mode2 ? 1000.0 * pen_unit : kUnrepairable);
   };
   double cur_true = true_total(cur);
   auto save_best = [&]() {
     // a chain's best must be usable: memory ok by construction, every function placed, CPU rows routable
-    if (cur_true < kUnrepairable && cur_true < best_total) {
+    if (cur_true < (mode2 ? pen_unit : kUnrepairable) && cur_true < best_total) {
       __syncthreads();
       for (int q = tid; q < F * N; q += blockDim.x) k.best_c[q] = k.c[q];
       if (tid == 0) best_total = cur_true;
@@ -415,7 +453,8 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
     Move my_mv{MV_NONE, 0, 0, 0};
     const int ntb = n_tabu;
     for (int64_t q = wid; q < total; q += nw) {
-      Move cand; bool ok = false; double dutil = 0.0, dcov = 0.0;
+      Move cand; bool ok = false; double dutil = 0.0, dcov = 0.0, dflip = 0.0, dpods = 0.0, dmem = 0.0;
+      auto relief = [&](int j_, double dm) { return fmax(k.mem[j_] + dm - Mj[j_], 0.0) - fmax(k.mem[j_] - Mj[j_], 0.0); };
       if (q < n_add) {
         const int f = (int)(q / N), j = (int)(q - (int64_t)f * N);
         ok = !k.c[q] && k.mem[j] + m[f] <= Mj[j];
@@ -427,12 +466,14 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
         ok = k.cntf[f] >= 2;
         cand = Move{MV_DROP, f, j, -1};
         if (ok && k.cntn[j] == 1) dutil = -1.0;
+        if (ok) dmem = relief(j, -m[f]);
       } else if (q < n_add + n_drop + n_swap) {
         const int64_t t = q - n_add - n_drop;
         const int pq = k.pods[t / N], f = pq / N, j = pq - f * N, jn = (int)(t % N);
         ok = !k.c[(int64_t)f * N + jn] && k.mem[jn] + m[f] <= Mj[jn];
         cand = Move{MV_SWAP, f, j, jn};
         if (ok) dutil = (k.cntn[jn] == 0 ? 1.0 : 0.0) - (k.cntn[j] == 1 ? 1.0 : 0.0);
+        if (ok) dmem = relief(j, -m[f]);
       } else if (q < n_add + n_drop + n_swap + n_rep) {
         const int64_t t = q - n_add - n_drop - n_swap;
         const int pq = k.pods[t / F], f = pq / N, j = pq - f * N, fn = (int)(t % F);
@@ -467,7 +508,20 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
              dd = eval_change(a, k, w, r, dT, cand.f, cand.j, j2, delta);
              dd += eval_change(a, k, w, r, dT, g, j2, cand.j, delta); }
       const double dov = eval_overload_delta(a, k, Kj, delta);
-      const double dt = a_d * dd + a_u * dutil + mu * dov + kCoverage * dcov;
+      double dt;
+      if (!mode2) dt = a_d * dd + a_u * dutil + mu * dov + kCoverage * (dcov + dmem);
+      else {
+        const double* old = a.old + (int64_t)b * F * N;
+        auto on = [&](int f_, int j_) { dflip += old[(int64_t)f_ * N + j_] > 0.0 ? -1.0 : 1.0; dpods += 1.0; };
+        auto off = [&](int f_, int j_) { dflip += old[(int64_t)f_ * N + j_] > 0.0 ? 1.0 : -1.0; dpods -= 1.0; };
+        if (cand.type == MV_ADD) on(cand.f, cand.j);
+        else if (cand.type == MV_DROP) off(cand.f, cand.j);
+        else if (cand.type == MV_SWAP) { off(cand.f, cand.j); on(cand.f, cand.t); }
+        else if (cand.type == MV_REPLACE) { off(cand.f, cand.j); on(cand.t, cand.j); }
+        else { const int g = cand.t / N, j2 = cand.t - g * N; off(cand.f, cand.j); on(cand.f, j2); off(g, j2); on(g, cand.j); }
+        dt = objective(cur.delay + dd, cur.util + dutil, cur.over + dov, cur.uncov + dcov, cur.flips + dflip,
+                       cur.pods + dpods, mu) + kCoverage * (cur.memover + dmem) - cur_total;
+      }
       if (dt < my_best) { my_best = dt; my_mv = cand; }
     }
     if (lane == 0) { wbest[wid] = my_best; wmove[wid] = my_mv; }
@@ -565,7 +619,7 @@ extern "C" int neptune_local_search_workspace_bytes(int B, int N, int F, int cha
   return 0;
 }
 
-extern "C" int neptune_local_search(int B, int N, int F, int kind, double alpha, int chains, int sweeps,
+static int local_search_impl(int step2_mode, const double* bound, int B, int N, int F, int kind, double alpha, int chains, int sweeps,
                                     uint64_t rng_seed, int S, const double* d, const double* w, const double* r,
                                     const double* m, const double* Mj, const double* Kj, const double* maxd,
                                     const double* cost, double budget, const double* old, const uint8_t* seeds,
@@ -575,6 +629,7 @@ extern "C" int neptune_local_search(int B, int N, int F, int kind, double alpha,
     return NEPTUNE_E_ARG;
   if (!d || !w || !r || !m || !Mj || !Kj || !seeds || !best_c || !best_obj || !best_flags || !workspace)
     return NEPTUNE_E_ARG;
+  if (step2_mode && (!bound || !old)) return NEPTUNE_E_ARG;
   int64_t need = 0;
   neptune_local_search_workspace_bytes(B, N, F, chains, &need);
   if (workspace_bytes < need) return NEPTUNE_E_NOMEM;
@@ -583,7 +638,7 @@ extern "C" int neptune_local_search(int B, int N, int F, int kind, double alpha,
   a.N = N; a.F = F; a.kind = kind; a.chains = chains; a.sweeps = sweeps; a.S = S;
   a.alpha = alpha; a.budget = budget; a.rng = rng_seed ? rng_seed : 0x1234567ull;
   a.d = d; a.w = w; a.r = r; a.m = m; a.Mj = Mj; a.Kj = Kj; a.maxd = maxd; a.cost = cost; a.old = old;
-  a.seeds = seeds; a.guide = guide;
+  a.seeds = seeds; a.guide = guide; a.step2_mode = step2_mode; a.bound = bound;
   char* p = (char*)workspace;
   a.dT = (double*)p; p += (((int64_t)B * N * N * 8 + 255) & ~(int64_t)255);
   a.inst_scal = (double*)p; p += 256 * (((int64_t)B * 32 + 255) / 256);
@@ -599,4 +654,27 @@ extern "C" int neptune_local_search(int B, int N, int F, int kind, double alpha,
   { k_ls_pick<<<B, 256, 0, s>>>(a, best_c, best_obj, best_flags); NEPTUNE_COUNT(1); }
   NEPTUNE_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int neptune_local_search(int B, int N, int F, int kind, double alpha, int chains, int sweeps,
+                                    uint64_t rng_seed, int S, const double* d, const double* w, const double* r,
+                                    const double* m, const double* Mj, const double* Kj, const double* maxd,
+                                    const double* cost, double budget, const double* old, const uint8_t* seeds,
+                                    const double* guide, uint8_t* best_c, double* best_obj, int32_t* best_flags,
+                                    void* workspace, int64_t workspace_bytes, void* stream) {
+  return local_search_impl(0, nullptr, B, N, F, kind, alpha, chains, sweeps, rng_seed, S, d, w, r, m, Mj, Kj, maxd,
+                           cost, budget, old, seeds, guide, best_c, best_obj, best_flags, workspace, workspace_bytes,
+                           stream);
+}
+
+extern "C" int neptune_disruption_search(int B, int N, int F, int kind, double alpha, int mode, const double* bound,
+                                         int chains, int sweeps, uint64_t rng_seed, int S, const double* d,
+                                         const double* w, const double* r, const double* m, const double* Mj,
+                                         const double* Kj, const double* maxd, const double* cost, double budget,
+                                         const double* old, const uint8_t* seeds, uint8_t* best_c, double* best_obj,
+                                         int32_t* best_flags, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (mode != 1 && mode != 2) return NEPTUNE_E_ARG;
+  return local_search_impl(mode, bound, B, N, F, kind, alpha, chains, sweeps, rng_seed, S, d, w, r, m, Mj, Kj, maxd,
+                           cost, budget, old, seeds, nullptr, best_c, best_obj, best_flags, workspace,
+                           workspace_bytes, stream);
 }

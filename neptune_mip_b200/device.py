@@ -328,3 +328,27 @@ def route_capacitated(inst: InstanceBatch, c_u8: torch.Tensor):
                                         _ptr(inst.Kj), _ptr(c_u8), _ptr(c_out), _ptr(x), _ptr(n), _ptr(obj),
                                         _ptr(feas), _stream()), "neptune_route_capacitated")
     return c_out, x, n, obj, feas
+
+
+def disruption_search(inst: InstanceBatch, kind, mode: str, bound: torch.Tensor, seeds_u8: torch.Tensor, alpha=0.5,
+                      chains=64, sweeps=300, rng_seed=1, workspace=None):
+    """Step-2 search (`neptune_disruption_search`): mode "delete" | "create", bound[B] float64 on device.
+    Returns (best_c uint8[B,F,N], best_obj float64[B] = step-2 objective or +inf, flags int32[B])."""
+    lib = _lib.load()
+    kind = KINDS.get(kind, kind)
+    dev = inst.d.device
+    S = seeds_u8.shape[1]
+    need = C.c_int64()
+    check(lib.neptune_local_search_workspace_bytes(inst.B, inst.N, inst.F, chains, C.byref(need)),
+          "neptune_local_search_workspace_bytes")
+    if workspace is None or workspace.numel() < need.value:
+        workspace = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    best_c = torch.empty((inst.B, inst.F, inst.N), dtype=torch.uint8, device=dev)
+    best_obj = torch.empty(inst.B, dtype=torch.float64, device=dev)
+    best_flags = torch.empty(inst.B, dtype=torch.int32, device=dev)
+    check(lib.neptune_disruption_search(inst.B, inst.N, inst.F, kind, C.c_double(alpha),
+                                        {"delete": 1, "create": 2}[mode], _ptr(bound), chains, sweeps,
+                                        C.c_uint64(rng_seed), S, *inst.inst_ptrs(), _ptr(inst.old), _ptr(seeds_u8),
+                                        _ptr(best_c), _ptr(best_obj), _ptr(best_flags), _ptr(workspace),
+                                        workspace.numel(), _stream()), "neptune_disruption_search")
+    return best_c, best_obj, best_flags
