@@ -219,6 +219,7 @@ enum { MV_NONE = 0, MV_ADD, MV_DROP, MV_SWAP, MV_REPLACE, MV_EXCH };
 // ADD(f, j) | DROP(f, j) | SWAP(f, j -> t) | REPLACE(node j: f -> t) | EXCH((f, j) <-> pod t = g*N + j2)
 struct Move { int type, f, j, t; };
 constexpr int kMaxTabu = 12;
+constexpr int kMaxBatch = 8;                  // disjoint proposals applied together in one sweep
 constexpr int64_t kMaxExchange = 1 << 17;     // exchange proposals examined per sweep (sampled beyond that)
 constexpr double kUnrepairable = 1e11;        // state whose overload cannot be routed away
 
@@ -301,6 +302,8 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
   __shared__ double wbest[8];
   __shared__ Move wmove[8];
   __shared__ Move mv;
+  __shared__ Move batch[kMaxBatch];
+  __shared__ int n_batch;
   __shared__ int n_pods, n_tabu;
   __shared__ uint64_t s_rand[2];
   __shared__ Move tabu_list[kMaxTabu];
@@ -527,37 +530,68 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
     if (lane == 0) { wbest[wid] = my_best; wmove[wid] = my_mv; }
     __syncthreads();
     if (tid == 0) {
-      int bw = 0;
-      for (int q = 1; q < nw; ++q) if (wbest[q] < wbest[bw]) bw = q;
-      mv = wmove[bw];
+      // the warps' best proposals, best first; keep those that touch pairwise disjoint functions and nodes
+      // (their delay changes are then independent and their memory checks stay valid together)
+      int order[8];
+      for (int q = 0; q < nw; ++q) order[q] = q;
+      for (int q = 1; q < nw; ++q) { const int v = order[q]; int p2 = q - 1; while (p2 >= 0 && wbest[order[p2]] > wbest[v]) { order[p2 + 1] = order[p2]; --p2; } order[p2 + 1] = v; }
+      int nb = 0;
+      int uf[16], un[16], nuf = 0, nun = 0;
+      for (int q = 0; q < nw && nb < kMaxBatch; ++q) {
+        const Move c = wmove[order[q]];
+        if (c.type == MV_NONE) continue;
+        int fs[2] = {c.f, -1}, ns[2] = {c.j, -1};
+        if (c.type == MV_SWAP) ns[1] = c.t;
+        else if (c.type == MV_REPLACE) fs[1] = c.t;
+        else if (c.type == MV_EXCH) { fs[1] = c.t / N; ns[1] = c.t - (c.t / N) * N; }
+        bool clash = false;
+        for (int z = 0; z < 2; ++z) {
+          for (int y2 = 0; y2 < nuf; ++y2) clash = clash || (fs[z] >= 0 && uf[y2] == fs[z]);
+          for (int y2 = 0; y2 < nun; ++y2) clash = clash || (ns[z] >= 0 && un[y2] == ns[z]);
+        }
+        if (clash) continue;
+        for (int z = 0; z < 2; ++z) { if (fs[z] >= 0) uf[nuf++] = fs[z]; if (ns[z] >= 0) un[nun++] = ns[z]; }
+        batch[nb++] = c;
+      }
+      n_batch = nb;
+      mv = nb ? batch[0] : Move{MV_NONE, 0, 0, 0};
     }
     __syncthreads();
     if (mv.type != MV_NONE) {
-      // ---- apply, re-route the touched functions, refresh node state, price the new state exactly ------
-      const Move m0 = mv;
-      int f2 = -1;                                   // second function touched
-      if (tid == 0) apply_move(k, N, m0, false);
-      if (m0.type == MV_REPLACE) f2 = m0.t; else if (m0.type == MV_EXCH) f2 = m0.t / N;
-      __syncthreads();
-      route_f(a, k, d, m0.f);
-      if (f2 >= 0) route_f(a, k, d, f2);
-      __syncthreads();
-      node_state(a, k, w, r, m);
-      __syncthreads();
-      const Cost nc = full_cost(a, k, w, Kj, red);
-      const double nt = true_total(nc);
-      if (nt < cur_true - 1e-9 * (1.0 + fabs(cur_true))) {
-        cur = nc; cur_total = total_of(nc); cur_true = nt;
+      // ---- apply (the whole disjoint batch first, the single best proposal if that does not pay), re-route
+      // the touched functions, refresh node state, price the new state exactly --------------------------
+      auto second_f = [&](const Move& m_) { return m_.type == MV_REPLACE ? m_.t : (m_.type == MV_EXCH ? m_.t / N : -1); };
+      auto apply_n = [&](int cnt, bool undo) {
+        if (tid == 0) for (int z = 0; z < cnt; ++z) apply_move(k, N, batch[z], undo);
+        __syncthreads();
+        for (int z = 0; z < cnt; ++z) {
+          route_f(a, k, d, batch[z].f);
+          const int f2 = second_f(batch[z]);
+          if (f2 >= 0) route_f(a, k, d, f2);
+        }
+        __syncthreads();
+        node_state(a, k, w, r, m);
+        __syncthreads();
+      };
+      bool accepted = false;
+      for (int attempt = (n_batch > 1 ? 0 : 1); attempt < 2 && !accepted; ++attempt) {
+        const int cnt = attempt == 0 ? n_batch : 1;
+        apply_n(cnt, false);
+        const Cost nc = full_cost(a, k, w, Kj, red);
+        const double nt = true_total(nc);
+        if (nt < cur_true - 1e-9 * (1.0 + fabs(cur_true))) {
+          cur = nc; cur_total = total_of(nc); cur_true = nt;
+          accepted = true;
+        } else {
+          apply_n(cnt, true);
+        }
+      }
+      if (accepted) {
         stall = 0; stage2 = false;
         if (tid == 0) n_tabu = 0;
         __syncthreads();
       } else {
-        if (tid == 0) { apply_move(k, N, m0, true); if (n_tabu < kMaxTabu) tabu_list[n_tabu++] = m0; }
-        __syncthreads();
-        route_f(a, k, d, m0.f);
-        if (f2 >= 0) route_f(a, k, d, f2);
-        __syncthreads();
-        node_state(a, k, w, r, m);
+        if (tid == 0 && n_tabu < kMaxTabu) tabu_list[n_tabu++] = batch[0];
         __syncthreads();
         if (n_tabu < kMaxTabu) continue;            // try the next-best proposal
         mv.type = MV_NONE;                          // too many rejections: treat as a local optimum
