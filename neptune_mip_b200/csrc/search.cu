@@ -219,6 +219,7 @@ enum { MV_NONE = 0, MV_ADD, MV_DROP, MV_SWAP, MV_REPLACE, MV_EXCH };
 // ADD(f, j) | DROP(f, j) | SWAP(f, j -> t) | REPLACE(node j: f -> t) | EXCH((f, j) <-> pod t = g*N + j2)
 struct Move { int type, f, j, t; };
 constexpr int kMaxTabu = 12;
+constexpr int kSwapWindow = 96;                // swap targets examined per pod and sweep when N is larger
 constexpr int kMaxBatch = 8;                  // disjoint proposals applied together in one sweep
 constexpr int64_t kMaxExchange = 1 << 17;     // exchange proposals examined per sweep (sampled beyond that)
 constexpr double kUnrepairable = 1e11;        // state whose overload cannot be routed away
@@ -444,7 +445,10 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
     for (int q = tid; q < F * N; q += blockDim.x) if (k.c[q]) k.pods[atomicAdd(&n_pods, 1)] = q;
     __syncthreads();
     const int P = n_pods;
-    const int64_t n_add = (int64_t)F * N, n_drop = P, n_swap = (int64_t)P * N, n_rep = (int64_t)P * F;
+    // swap targets: all nodes for small N, a window of kSwapWindow nodes (rotating with the sweep) beyond
+    const int swin = N <= kSwapWindow ? N : kSwapWindow;
+    const int swoff = N <= kSwapWindow ? 0 : (int)(s_rand[1] % (uint64_t)N);
+    const int64_t n_add = (int64_t)F * N, n_drop = P, n_swap = (int64_t)P * swin, n_rep = (int64_t)P * F;
     const int64_t pp = (int64_t)P * P;
     const int64_t n_exch = pp < kMaxExchange ? pp : kMaxExchange;
     const int64_t ex_off = (int64_t)(s_rand[0] % (uint64_t)(pp > 0 ? pp : 1));        // block-uniform
@@ -472,7 +476,7 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
         if (ok) dmem = relief(j, -m[f]);
       } else if (q < n_add + n_drop + n_swap) {
         const int64_t t = q - n_add - n_drop;
-        const int pq = k.pods[t / N], f = pq / N, j = pq - f * N, jn = (int)(t % N);
+        const int pq = k.pods[t / swin], f = pq / N, j = pq - f * N, jn = (int)((swoff + t % swin) % N);
         ok = !k.c[(int64_t)f * N + jn] && k.mem[jn] + m[f] <= Mj[jn];
         cand = Move{MV_SWAP, f, j, jn};
         if (ok) dutil = (k.cntn[jn] == 0 ? 1.0 : 0.0) - (k.cntn[j] == 1 ? 1.0 : 0.0);
