@@ -215,8 +215,9 @@ __device__ double eval_overload_delta(const LsArgs& a, const Chain& k, const dou
   return warp_sum(dv);
 }
 
-enum { MV_NONE = 0, MV_ADD, MV_DROP, MV_SWAP, MV_REPLACE, MV_EXCH };
+enum { MV_NONE = 0, MV_ADD, MV_DROP, MV_SWAP, MV_REPLACE, MV_EXCH, MV_NODE };
 // ADD(f, j) | DROP(f, j) | SWAP(f, j -> t) | REPLACE(node j: f -> t) | EXCH((f, j) <-> pod t = g*N + j2)
+// | NODE(every pod of node j moves to the empty node t; f = number of functions, step 2 only)
 struct Move { int type, f, j, t; };
 constexpr int kMaxTabu = 12;
 constexpr int kSwapWindow = 96;                // swap targets examined per pod and sweep when N is larger
@@ -234,6 +235,10 @@ __device__ inline void apply_move(const Chain& k, int N, const Move& m, bool und
     const int g = m.t / N, j2 = m.t - g * N;
     k.c[(int64_t)m.f * N + m.j] = off; k.c[(int64_t)m.f * N + j2] = on;
     k.c[(int64_t)g * N + j2] = off; k.c[(int64_t)g * N + m.j] = on;
+  } else if (m.type == MV_NODE) {
+    const int from = undo ? m.t : m.j, to = undo ? m.j : m.t;      // `to` is empty before the move
+    for (int f = 0; f < m.f; ++f)
+      if (k.c[(int64_t)f * N + from]) { k.c[(int64_t)f * N + from] = 0; k.c[(int64_t)f * N + to] = 1; }
   }
 }
 
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(256) k_ls_prepare(LsArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
+__global__ void __launch_bounds__(256, 3) k_local_search(LsArgs a) {
   const int chain = blockIdx.x, b = blockIdx.y, N = a.N, F = a.F;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
   const double* d = a.d + (int64_t)b * N * N;
@@ -455,7 +460,8 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
     const int64_t ex_stride = pp > kMaxExchange ? (int64_t)(2 * (s_rand[1] % 4096) + 1) : 1;
     // two-stage neighbourhood: the (quadratic) exchange moves are only examined once the basic
     // add / drop / swap / replace neighbourhood has no improving proposal left
-    const int64_t total = n_add + n_drop + n_swap + n_rep + (stage2 ? n_exch : 0);
+    const int64_t n_node = mode2 ? (int64_t)N * N : 0;          // whole-node relocation (step 2 only)
+    const int64_t total = n_add + n_drop + n_swap + n_rep + n_node + (stage2 ? n_exch : 0);
     double my_best = -1e-9 * (1.0 + fabs(cur_total));      // only strictly improving proposals
     Move my_mv{MV_NONE, 0, 0, 0};
     const int ntb = n_tabu;
@@ -487,9 +493,14 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
         ok = fn != f && !k.c[(int64_t)fn * N + j] && k.cntf[f] >= 2 && k.mem[j] - m[f] + m[fn] <= Mj[j];
         cand = Move{MV_REPLACE, f, j, fn};
         if (ok && k.cntf[fn] == 0) dcov = -1.0;
+      } else if (q < n_add + n_drop + n_swap + n_rep + n_node) {
+        const int64_t t = q - n_add - n_drop - n_swap - n_rep;
+        const int j = (int)(t / N), j2 = (int)(t - (int64_t)j * N);
+        ok = j != j2 && k.cntn[j] > 0 && k.cntn[j2] == 0 && k.mem[j] <= Mj[j2];
+        cand = Move{MV_NODE, F, j, j2};
       } else {
         // exchange: pods (f, j) and (g, j2) trade nodes -> (f, j2), (g, j); pod counts stay as they are
-        const int64_t t = (ex_off + (q - n_add - n_drop - n_swap - n_rep) * ex_stride) % pp;
+        const int64_t t = (ex_off + (q - n_add - n_drop - n_swap - n_rep - n_node) * ex_stride) % pp;
         const int p1 = (int)(t / P), p2 = (int)(t - (int64_t)p1 * P);
         if (p1 < p2) {
           const int q1 = k.pods[p1], q2 = k.pods[p2];
@@ -511,6 +522,10 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
       else if (cand.type == MV_SWAP) dd = eval_change(a, k, w, r, dT, cand.f, cand.j, cand.t, delta);
       else if (cand.type == MV_REPLACE) { dd = eval_change(a, k, w, r, dT, cand.f, cand.j, -1, delta);
                                           dd += eval_change(a, k, w, r, dT, cand.t, -1, cand.j, delta); }
+      else if (cand.type == MV_NODE) {
+        for (int f = 0; f < F; ++f)
+          if (k.c[(int64_t)f * N + cand.j]) dd += eval_change(a, k, w, r, dT, f, cand.j, cand.t, delta);
+      }
       else { const int g = cand.t / N, j2 = cand.t - g * N;
              dd = eval_change(a, k, w, r, dT, cand.f, cand.j, j2, delta);
              dd += eval_change(a, k, w, r, dT, g, j2, cand.j, delta); }
@@ -525,6 +540,9 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
         else if (cand.type == MV_DROP) off(cand.f, cand.j);
         else if (cand.type == MV_SWAP) { off(cand.f, cand.j); on(cand.f, cand.t); }
         else if (cand.type == MV_REPLACE) { off(cand.f, cand.j); on(cand.t, cand.j); }
+        else if (cand.type == MV_NODE) {
+          for (int f = 0; f < F; ++f) if (k.c[(int64_t)f * N + cand.j]) { off(f, cand.j); on(f, cand.t); }
+        }
         else { const int g = cand.t / N, j2 = cand.t - g * N; off(cand.f, cand.j); on(cand.f, j2); off(g, j2); on(g, cand.j); }
         dt = objective(cur.delay + dd, cur.util + dutil, cur.over + dov, cur.uncov + dcov, cur.flips + dflip,
                        cur.pods + dpods, mu) + kCoverage * (cur.memover + dmem) - cur_total;
@@ -544,6 +562,7 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
       for (int q = 0; q < nw && nb < kMaxBatch; ++q) {
         const Move c = wmove[order[q]];
         if (c.type == MV_NONE) continue;
+        if (c.type == MV_NODE) { if (nb == 0) batch[nb++] = c; else continue; break; }
         int fs[2] = {c.f, -1}, ns[2] = {c.j, -1};
         if (c.type == MV_SWAP) ns[1] = c.t;
         else if (c.type == MV_REPLACE) fs[1] = c.t;
@@ -569,6 +588,11 @@ __global__ void __launch_bounds__(256) k_local_search(LsArgs a) {
         if (tid == 0) for (int z = 0; z < cnt; ++z) apply_move(k, N, batch[z], undo);
         __syncthreads();
         for (int z = 0; z < cnt; ++z) {
+          if (batch[z].type == MV_NODE) {
+            for (int f = 0; f < F; ++f)
+              if (k.c[(int64_t)f * N + batch[z].j] || k.c[(int64_t)f * N + batch[z].t]) route_f(a, k, d, f);
+            continue;
+          }
           route_f(a, k, d, batch[z].f);
           const int f2 = second_f(batch[z]);
           if (f2 >= 0) route_f(a, k, d, f2);
