@@ -124,6 +124,102 @@ class ShardedLP:
                   "neptune_pdhg_dual_rows")
         self.iters += n
 
+    # -- restarted solve: KKT pieces are reduced over ranks, so every rank takes the same decisions --------
+    def _kkt(self, x, y):
+        """(primal residual^2, dual residual^2, primal objective, dual objective) of (x, y), global."""
+        m = self.model
+        d0, d1, d2, d3 = self.d
+        a = device.spmv(m, x)                                 # local activities; coupling rows are partial
+        coup = self._coupling(a)
+        self.allreduce(coup)
+        self._set_coupling(a, coup)
+        lo, hi = m.lo, m.hi
+        viol = a - torch.minimum(torch.maximum(a, lo), hi)
+        own = torch.ones_like(a)
+        if self.rank != 0:                                    # replicated rows are counted once (rank 0)
+            own[:, d0:d1] = 0.0
+            own[:, d2:d3] = 0.0
+        pres2 = (viol * viol * own).sum()
+        pos, neg = torch.clamp(y, min=0.0), torch.clamp(y, max=0.0)
+        fin_h, fin_l = torch.isfinite(hi), torch.isfinite(lo)
+        dobj = -(torch.where(fin_h, hi, torch.zeros_like(hi)) * pos * own).sum() \
+               - (torch.where(fin_l, lo, torch.zeros_like(lo)) * neg * own).sum()
+        dres2 = ((pos * (~fin_h)) ** 2 * own).sum() + ((neg * (~fin_l)) ** 2 * own).sum()
+        rc = m.obj + device.spmv_t(m, y)
+        rpos, rneg = torch.clamp(rc, min=0.0), torch.clamp(rc, max=0.0)
+        fin_u = torch.isfinite(m.col_ub)
+        dobj = dobj + (m.col_lb * rpos).sum() + (torch.where(fin_u, m.col_ub, torch.zeros_like(rc)) * rneg).sum()
+        dres2 = dres2 + ((rneg * (~fin_u)) ** 2).sum()
+        pobj = (m.obj * x).sum()
+        v = torch.stack([pres2, dres2, pobj, dobj]).reshape(1, 4).contiguous()
+        self.allreduce(v)
+        return [float(t) for t in v[0].cpu()]
+
+    def _norm2(self, vx, vy):
+        """Squared preconditioned norms of a primal / dual displacement, global."""
+        own = torch.ones_like(vy)
+        if self.rank != 0:
+            d0, d1, d2, d3 = self.d
+            own[:, d0:d1] = 0.0
+            own[:, d2:d3] = 0.0
+        v = torch.stack([(vx * vx / self.T).sum(), (vy * vy / self.S * own).sum()]).reshape(1, 2).contiguous()
+        self.allreduce(v)
+        return float(v[0, 0]), float(v[0, 1])
+
+    def solve(self, max_iters=20000, check_every=128, eps_rel=1e-6, eps_abs=1e-9, eta=0.99):
+        """Restarted, averaged PDHG with the decisions of csrc/pdhg.cu (KKT-error restarts 0.2 / 0.8 / 0.36,
+        primal weight clamped to a factor 2 per restart), taken identically on every rank."""
+        m = self.model
+        fb = torch.maximum(torch.where(torch.isfinite(m.lo), m.lo.abs(), torch.zeros_like(m.lo)),
+                           torch.where(torch.isfinite(m.hi), m.hi.abs(), torch.zeros_like(m.hi)))
+        zx = torch.zeros_like(self.x)
+        nc2, nb2 = self._norm2(m.obj * self.T, fb * self.S)          # ||D_c c||^2, ||D_r b||^2 (T = dc^2, S = dr^2)
+        _, nb_plain = self._norm2(zx, fb * torch.sqrt(self.S))
+        nc_plain, _ = self._norm2(m.obj * torch.sqrt(self.T), torch.zeros_like(self.y))
+        norm_b, norm_c = nb_plain ** 0.5, nc_plain ** 0.5
+        omega = (nc2 ** 0.5) / (nb2 ** 0.5) if nb2 > 1e-20 and nc2 > 1e-20 else 1.0
+        kkt_restart = kkt_prev = float("inf")
+        xr, yr = self.x.clone(), self.y.clone()
+        since = restarts = 0
+        self.xsum.zero_(); self.ysum.zero_()
+        total = 0
+        info = {}
+        while total < max_iters:
+            self.tau, self.sigma = eta / omega, eta * omega
+            self.iterate(check_every)
+            total += check_every; since += check_every
+            cands = []
+            for (cx, cy) in ((self.x, self.y), (self.xsum / since, self.ysum / since)):
+                p2, d2, po, do = self._kkt(cx, cy)
+                gap = abs(po - do)
+                k = (omega * omega * p2 + d2 / (omega * omega) + gap * gap) ** 0.5
+                ok = p2 ** 0.5 <= eps_abs + eps_rel * norm_b and d2 ** 0.5 <= eps_abs + eps_rel * norm_c and \
+                    gap <= eps_abs + eps_rel * (abs(po) + abs(do))
+                cands.append((k, ok, po, do, p2 ** 0.5, d2 ** 0.5))
+            pick = 1 if (cands[1][1] and not cands[0][1]) else (0 if (cands[0][1] and not cands[1][1])
+                                                                 else (1 if cands[1][0] < cands[0][0] else 0))
+            k, ok, po, do, pr, dr = cands[pick]
+            info = dict(primal_obj=po, dual_obj=do, primal_res=pr, dual_res=dr, iters=total, restarts=restarts,
+                        converged=bool(cands[0][1] or cands[1][1]), primal_weight=omega)
+            if info["converged"] or total >= max_iters:
+                if pick == 1:
+                    self.x.copy_(self.xsum / since); self.y.copy_(self.ysum / since)
+                break
+            act = k <= 0.2 * kkt_restart or (k <= 0.8 * kkt_restart and k > kkt_prev) or \
+                (since >= 0.36 * total and restarts > 0)
+            kkt_prev = k
+            if act:
+                kkt_restart = k; restarts += 1
+                if pick == 1:
+                    self.x.copy_(self.xsum / since); self.y.copy_(self.ysum / since)
+                dx2, dy2 = self._norm2(self.x - xr, self.y - yr)
+                if dx2 > 1e-20 and dy2 > 1e-20:
+                    nw = (dy2 / dx2) ** 0.25 * omega ** 0.5           # exp(0.5 log(dy/dx) + 0.5 log omega)
+                    omega = min(max(nw, 0.5 * omega), 2.0 * omega)
+                xr.copy_(self.x); yr.copy_(self.y)
+                self.xsum.zero_(); self.ysum.zero_(); since = 0
+        return info
+
     def primal_objective(self, average=False):
         x = self.xsum / max(self.iters, 1) if average else self.x
         v = (self.model.obj * x).sum().reshape(1)

@@ -15,7 +15,8 @@ rank, ws, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os
 ngpu = torch.cuda.device_count()
 torch.cuda.set_device(local % ngpu)
 dist.init_process_group(backend, **({"device_id": torch.device("cuda", local)} if backend == "nccl" else {}))
-data = data_to_solver_input(synth.random_payload(N, F, 0, node_cores=None), 1, with_db=False)
+_nc = os.environ.get("NEPTUNE_NODE_CORES")
+data = data_to_solver_input(synth.random_payload(N, F, 1 if _nc else 0, node_cores=int(_nc) if _nc else None), 1, with_db=False)
 lp = ShardedLP(data)
 if mode == "parity":
     lp.iterate(iters)
@@ -41,6 +42,17 @@ if mode == "parity":
               f"obj sharded={obj:.9g} single={robj:.9g}", flush=True)
         assert dx <= 1e-8 * (1 + float(xr.abs().max())) and dy <= 1e-8 * (1 + float(yr.abs().max()))
         assert abs(obj - robj) <= 1e-9 * (1 + abs(robj))
+elif mode == "solve":
+    # restarted solve to the LP optimum; rank 0 compares with the single-GPU solver on the same model
+    info = lp.solve(max_iters=iters, check_every=128, eps_rel=1e-6)
+    if rank == 0:
+        from neptune_mip_b200 import device
+        full = device.assemble(device.InstanceBatch.from_datas([data]), "min_delay")
+        _, _, res = device.pdhg_solve(full, max_iters=iters, eps_rel=1e-6, eps_abs=1e-9)
+        print(f"SOLVE world={ws} N={N} F={F} sharded: {info} | single GPU: primal={res[0]['primal_obj']:.9g} "
+              f"dual={res[0]['dual_obj']:.9g} iters={res[0]['iters']} converged={res[0]['converged']}", flush=True)
+        ref = float(res[0]["primal_obj"])
+        assert info["converged"] and abs(info["primal_obj"] - ref) <= 1e-4 * (1 + abs(ref))
 else:
     lp.iterate(5)
     torch.cuda.synchronize(); dist.barrier()
