@@ -51,8 +51,10 @@ elif mode == "solve":
         _, _, res = device.pdhg_solve(full, max_iters=iters, eps_rel=1e-6, eps_abs=1e-9)
         print(f"SOLVE world={ws} N={N} F={F} sharded: {info} | single GPU: primal={res[0]['primal_obj']:.9g} "
               f"dual={res[0]['dual_obj']:.9g} iters={res[0]['iters']} converged={res[0]['converged']}", flush=True)
-        ref = float(res[0]["primal_obj"])
-        assert info["converged"] and abs(info["primal_obj"] - ref) <= 1e-4 * (1 + abs(ref))
+        # the optimum lies between the single-GPU solver's dual and primal values (it may not have converged)
+        lo_b, hi_b = float(res[0]["dual_obj"]), float(res[0]["primal_obj"])
+        tol = 1e-4 * (1 + abs(hi_b))
+        assert info["converged"] and lo_b - tol <= info["primal_obj"] <= hi_b + tol
 else:
     lp.iterate(5)
     torch.cuda.synchronize(); dist.barrier()
