@@ -221,6 +221,7 @@ enum { MV_NONE = 0, MV_ADD, MV_DROP, MV_SWAP, MV_REPLACE, MV_EXCH, MV_NODE };
 struct Move { int type, f, j, t; };
 constexpr int kMaxTabu = 12;
 constexpr int kSwapWindow = 96;                // swap targets examined per pod and sweep when N is larger
+constexpr int kSubsample = 4;                  // sampled sweeps look at 1/kSubsample of the moves
 constexpr int kMaxBatch = 8;                  // disjoint proposals applied together in one sweep
 constexpr int64_t kMaxExchange = 1 << 17;     // exchange proposals examined per sweep (sampled beyond that)
 constexpr double kUnrepairable = 1e11;        // state whose overload cannot be routed away
@@ -442,6 +443,7 @@ __global__ void __launch_bounds__(256, 3) k_local_search(LsArgs a) {
   // changes or the chain is kicked.
   int stall = 0;
   bool stage2 = false;
+  bool sampled = true;       // examine a random quarter of the neighbourhood while that still finds improvements
   n_tabu = 0;
   for (int sweep = 0; sweep < a.sweeps; ++sweep) {
     // ---- pod list -------------------------------------------------------------------------------------
@@ -465,7 +467,9 @@ __global__ void __launch_bounds__(256, 3) k_local_search(LsArgs a) {
     double my_best = -1e-9 * (1.0 + fabs(cur_total));      // only strictly improving proposals
     Move my_mv{MV_NONE, 0, 0, 0};
     const int ntb = n_tabu;
-    for (int64_t q = wid; q < total; q += nw) {
+    const int sub = sampled ? kSubsample : 1;
+    const int64_t q_first = (int64_t)wid + (int64_t)nw * (int64_t)(sampled ? (s_rand[1] >> 20) % kSubsample : 0);
+    for (int64_t q = q_first; q < total; q += (int64_t)nw * sub) {
       Move cand; bool ok = false; double dutil = 0.0, dcov = 0.0, dflip = 0.0, dpods = 0.0, dmem = 0.0;
       auto relief = [&](int j_, double dm) { return fmax(k.mem[j_] + dm - Mj[j_], 0.0) - fmax(k.mem[j_] - Mj[j_], 0.0); };
       if (q < n_add) {
@@ -615,7 +619,7 @@ __global__ void __launch_bounds__(256, 3) k_local_search(LsArgs a) {
         }
       }
       if (accepted) {
-        stall = 0; stage2 = false;
+        stall = 0; stage2 = false; sampled = true;
         if (tid == 0) n_tabu = 0;
         __syncthreads();
       } else {
@@ -625,9 +629,10 @@ __global__ void __launch_bounds__(256, 3) k_local_search(LsArgs a) {
         mv.type = MV_NONE;                          // too many rejections: treat as a local optimum
       }
     }
+    if (mv.type == MV_NONE && sampled) { sampled = false; continue; }        // nothing in the sample: look at everything
     if (mv.type == MV_NONE && !stage2) { stage2 = true; if (tid == 0) n_tabu = 0; __syncthreads(); continue; }
     if (mv.type == MV_NONE) {
-      stage2 = false;
+      stage2 = false; sampled = true;
       // ---- local optimum: keep the best, restart from it with a kick -----------------------------------
       save_best();
       if (best_total < INFINITY) {
