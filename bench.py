@@ -241,11 +241,15 @@ def run_ours(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     rows, cols, nnz = pd["dims"]
     bytes_iter = B * (8 * nnz * 2 + 88 * cols + 72 * rows) + 8 * nnz + 8 * (rows + cols + 2)   # pattern stored once
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01b_pdhg_traffic.json")
+    if os.path.exists(tpath):          # dram__bytes_read+write of one iteration from the ncu --set full capture (B = 64)
+        traffic = json.load(open(tpath))["per_instance_dram_bytes"] * B
     roof = None
     if pd["iters"]:
         ach = bytes_iter * pd["iters"] / (pd["ms"] / 1e3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "kernel": "PDHG iteration = k_cols_thread<PrimalUpdate> + k_rows_warp<DualUpdate> (+ long-row/col variants)",
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "kernel": "PDHG iteration = k_spmv_short/k_spmv_tasks<PrimalUpdate> over A^T + k_spmv_short/k_spmv_tasks<DualUpdate> over A",
                 "bytes_per_iteration": bytes_iter, "iterations_timed": pd["iters"], "pdhg_ms": pd["ms"],
                 "pdhg_share_of_step": pd["ms"] / ms_total, "peak_source": peak_src}
 
@@ -282,7 +286,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="instances per GPU per step")
     ap.add_argument("--lp-iters", type=int, default=2048)
     ap.add_argument("--chains", type=int, default=8)
-    ap.add_argument("--sweeps", type=int, default=160)
+    ap.add_argument("--sweeps", type=int, default=240)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
