@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import device
-from ._lib import FLAG_STRENGTHEN, KINDS
+from ._lib import FLAG_STRENGTHEN, KINDS, OK_ALL
 
 
 @dataclass
@@ -66,4 +66,17 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
     # final routing honours the CPU rows (splits flows on binding nodes) and closes pods nobody uses
     best_c, x, n, _, _ = device.route_capacitated(inst, best_c)
     flags, scores = device.check_solution(inst, x, device.u8_to_f64(best_c), n, prm.alpha)
+    bad = flags != OK_ALL
+    if bool(bad.any()):
+        # rare (a pod starved by a split flow that no free source can top up): fall back, per instance, to the
+        # first EFTTC seed that passes every check -- a worse objective, never an infeasible answer
+        for k in (KINDS[kind], 1, 2, 0):
+            cf, xf, nf, _, _ = device.route_capacitated(inst, seeds[:, k].contiguous())
+            ff, sf = device.check_solution(inst, xf, device.u8_to_f64(cf), nf, prm.alpha)
+            take = bad & (ff == OK_ALL)
+            if bool(take.any()):
+                best_c[take], x[take], n[take], flags[take], scores[take] = cf[take], xf[take], nf[take], ff[take], sf[take]
+                bad = flags != OK_ALL
+            if not bool(bad.any()):
+                break
     return BatchResult(best_c, x, n, flags, scores, lp_res, pdhg_ms, iters, dims)

@@ -63,6 +63,11 @@ class NeptuneStep1CPUBase(NeptuneStepBase):
         if not torch.isfinite(best_obj[0]):
             best_c = seeds[:, {"min_delay": 0, "min_util": 1, "min_delay_util": 2}[self.kind]].contiguous()
         ok = self._finish(best_c, capacitated=True)
+        if not ok:      # rare: fall back to the first EFTTC seed that passes every check
+            for k in ({"min_delay": 0, "min_util": 1, "min_delay_util": 2}[self.kind], 1, 2, 0):
+                if self._finish(seeds[:, k].contiguous(), capacitated=True):
+                    ok = True
+                    break
         self.log(f"step 1: score {self._kind_score()} flags {self.flags:06b} lp bound {self.lp_bound}")
         return ok
 
