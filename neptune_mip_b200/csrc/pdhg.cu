@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) k_spmv_short(Csr A, const int32_t* __rest
 }
 
 template <class Epi>
-__global__ void __launch_bounds__(256) k_spmv_tasks(Csr A, const int32_t* __restrict__ tasks,
+__global__ void __launch_bounds__(256, 3) k_spmv_tasks(Csr A, const int32_t* __restrict__ tasks,
                                                     const int32_t* __restrict__ n_tasks,
                                                     const double* __restrict__ xv, Epi epi) {
   const int b = blockIdx.y;
@@ -129,40 +129,48 @@ __global__ void __launch_bounds__(256) k_spmv_tasks(Csr A, const int32_t* __rest
     int64_t q0 = 0, q1 = 0;
     if (mine) { q0 = A.ptr[myrow]; q1 = A.ptr[myrow + 1]; }
     const int mylen = (int)(q1 - q0);
+    // four rows at a time, 64 entries of each per pass: 8 index + 8 value loads of a lane are in flight
+    // together, then the 8 gathers, then four shuffle reductions -- two memory round trips per four rows of
+    // up to 64 entries (the C1 / C3 rows at N = 50), instead of one load -> gather chain per 32 entries.
     double myres = 0.0;
-    for (int k = 0; k < nr; k += 2) {
-      const int64_t p0a = __shfl_sync(0xffffffffu, q0, k), p1a = __shfl_sync(0xffffffffu, q1, k);
-      const int kb = (k + 1 < nr) ? k + 1 : k;
-      const int64_t p0b = __shfl_sync(0xffffffffu, q0, kb), p1b = __shfl_sync(0xffffffffu, q1, kb);
-      const bool doa = (p1a - p0a) <= kLongRow, dob = (kb != k) && (p1b - p0b) <= kLongRow;
-      double acca = 0.0, accb = 0.0;
-      int64_t pa = p0a + lane, pb = p0b + lane;
-      if (doa) {
-        for (; pa + 96 < p1a; pa += 128) {          // 4 index/value loads in flight, then 4 gathers
-          const int c0 = __ldcs(A.idx + pa), c1 = __ldcs(A.idx + pa + 32), c2 = __ldcs(A.idx + pa + 64),
-                    c3 = __ldcs(A.idx + pa + 96);
-          const double v0 = __ldcs(val + pa), v1 = __ldcs(val + pa + 32), v2 = __ldcs(val + pa + 64),
-                       v3 = __ldcs(val + pa + 96);
-          acca += v0 * x[c0]; acca += v1 * x[c1]; acca += v2 * x[c2]; acca += v3 * x[c3];
-        }
-        for (; pa < p1a; pa += 32) acca += __ldcs(val + pa) * x[__ldcs(A.idx + pa)];
+    const typename Epi::Pre pre = (mine && mylen <= kLongRow) ? epi.pre(b, myrow) : typename Epi::Pre{};
+    const int64_t tbase = __shfl_sync(0xffffffffu, q0, 0);
+    const int32_t* __restrict__ tidx = A.idx + tbase;
+    const double* __restrict__ tval = val + tbase;
+    for (int k = 0; k < nr; k += 4) {
+      int p0[4], p1[4];                                 // offsets relative to the first row of the task
+      int maxl = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kk = (k + u < nr) ? k + u : k;
+        p0[u] = (int)(__shfl_sync(0xffffffffu, q0, kk) - tbase);
+        p1[u] = (int)(__shfl_sync(0xffffffffu, q1, kk) - tbase);
+        if (k + u >= nr || p1[u] - p0[u] > kLongRow) p1[u] = p0[u];      // nothing to do for this slot
+        maxl = max(maxl, p1[u] - p0[u]);
       }
-      if (dob) {
-        for (; pb + 96 < p1b; pb += 128) {
-          const int c0 = __ldcs(A.idx + pb), c1 = __ldcs(A.idx + pb + 32), c2 = __ldcs(A.idx + pb + 64),
-                    c3 = __ldcs(A.idx + pb + 96);
-          const double v0 = __ldcs(val + pb), v1 = __ldcs(val + pb + 32), v2 = __ldcs(val + pb + 64),
-                       v3 = __ldcs(val + pb + 96);
-          accb += v0 * x[c0]; accb += v1 * x[c1]; accb += v2 * x[c2]; accb += v3 * x[c3];
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int off = 0; off < maxl; off += 64) {
+        int ci[8]; double vv[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pa = p0[u] + off + lane, pb = pa + 32;
+          const bool va = pa < p1[u], vb = pb < p1[u];
+          ci[2 * u] = va ? __ldcs(tidx + pa) : 0;       ci[2 * u + 1] = vb ? __ldcs(tidx + pb) : 0;
+          vv[2 * u] = va ? __ldcs(tval + pa) : 0.0;     vv[2 * u + 1] = vb ? __ldcs(tval + pb) : 0.0;
         }
-        for (; pb < p1b; pb += 32) accb += __ldcs(val + pb) * x[__ldcs(A.idx + pb)];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc[u] += vv[2 * u] * x[ci[2 * u]];
+          acc[u] += vv[2 * u + 1] * x[ci[2 * u + 1]];
+        }
       }
-      acca = warp_sum(acca);
-      accb = warp_sum(accb);
-      if (lane == k) myres = acca;
-      if (lane == kb && kb != k) myres = accb;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double r_ = warp_sum(acc[u]);
+        if (lane == k + u) myres = r_;
+      }
     }
-    if (mine && mylen <= kLongRow) epi.row(b, myrow, myres * xs, epi.pre(b, myrow));
+    if (mine && mylen <= kLongRow) epi.row(b, myrow, myres * xs, pre);
   }
   epi.finalize(b);
 }
