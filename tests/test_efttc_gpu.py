@@ -68,3 +68,23 @@ def test_efttc_alibaba_golden(solver):
             if c[0, f, j]:
                 got.setdefault(fname, {})[node] = True
     assert got == want
+
+
+def test_efttc_host_buffer_entry_point():
+    """`neptune_efttc_host` (host pointers in, host pointers out) == device path + checkers."""
+    import numpy as np
+    from helpers import data_of
+    from neptune_mip_b200 import device
+    from oracle import checkers
+    payloads = [synth.random_payload(12, 5, s, node_cores=25) for s in range(6)]
+    host = device.InstanceBatch.host_arrays([data_of(p) for p in payloads])
+    for kind in KIND_NAMES:
+        c, n, info, flags, scores = device.efttc_host(host, kind, 0.3)
+        cd, nd, infod = _run_gpu(payloads, kind, 0.3)
+        assert np.array_equal(c, cd) and np.array_equal(n, nd) and np.array_equal(info, infod)
+        for b, p in enumerate(payloads):
+            a = arrays_of(p)
+            ref = oefttc.solve(a, kind, 0.3, strict=False)
+            assert flags[b] == checkers.flags_to_mask(checkers.check_all(a, ref.x, ref.c, ref.n))
+            assert np.isclose(scores[b, 0], checkers.score_delay(a, ref.x), rtol=1e-12, atol=1e-12)
+            assert scores[b, 1] == checkers.score_util(a, ref.n)
