@@ -104,7 +104,7 @@ __device__ inline CapResult cap_route(const CapRoute& q, int max_rounds, double*
     double my_max = 0.0, my_mov = 0.0;
     for (int fi = tid; fi < F * N; fi += blockDim.x) {
       q.rho[fi] = -1.0;                                   // not a candidate
-      if (q.ch[fi] != js || q.sec[fi] >= 0) continue;
+      if (q.ch[fi] != js || q.sec[fi] != -1) continue;       // split (>= 0) and frozen (-2) flows stay put
       const int f = fi / N, i = fi - f * N;
       const double rfj = q.r[(int64_t)f * N + js], wv = q.w[fi];
       if (!(wv * rfj > 0.0)) continue;
@@ -200,8 +200,12 @@ __device__ inline CapResult cap_route(const CapRoute& q, int max_rounds, double*
             if (inflow >= 2.0) starve = false;
           }
         }
-        if (starve) q.ch[fi] = q.alt[fi];
-        else { q.sec[fi] = q.alt[fi]; q.th[fi] = 1.0 - mv; }
+        if (starve) {
+          // most of the flow has to leave anyway: move all of it (the emptied pod is closed afterwards);
+          // otherwise keep it whole on js and let the next-cheapest flows make room in the next round
+          if (mv > 0.5) q.ch[fi] = q.alt[fi];
+          else q.sec[fi] = -2;
+        } else { q.sec[fi] = q.alt[fi]; q.th[fi] = 1.0 - mv; }
       }
     }
     if (tid == 0) q.lam[js] = hi;
