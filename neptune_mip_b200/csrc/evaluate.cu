@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(256) k_route_cap(int N, int F, const double* _
   q.load = (double*)p; p += (int64_t)N * 8; q.lam = (double*)p; p += (int64_t)N * 8;
   q.ch = (int*)p; p += fn * 4; q.sec = (int*)p; p += fn * 4; q.alt = (int*)p;
   __shared__ double red[32];
-  __shared__ double sh[8];
+  __shared__ double sh[32];
   __shared__ int bad;
   if (tid == 0) bad = 0;
   const CapResult cr = cap_route(q, 4 * N + 16, red, sh);

@@ -51,7 +51,8 @@ __device__ inline void cap_loads(const CapRoute& q) {
   }
 }
 
-// `red` needs 32 doubles of shared memory; `sh` 8 doubles.  All threads of the block must call.
+// `red` needs 32 doubles of shared memory, `sh` 32 doubles (first 16: one int per warp; rest: scalars).
+// All threads of the block (up to 32 warps) must call.
 __device__ inline CapResult cap_route(const CapRoute& q, int max_rounds, double* red, double* sh) {
   const int N = q.N, F = q.F, tid = threadIdx.x;
   __shared__ int s_j, s_ok;
@@ -94,11 +95,11 @@ __device__ inline CapResult cap_route(const CapRoute& q, int max_rounds, double*
         if (v > bw || (v == bw && jj >= 0 && (bj < 0 || jj < bj))) { bw = v; bj = jj; }
       }
       s_j = (bw > 1e-9) ? bj : -1;
-      sh[4] = bw;
+      sh[20] = bw;
     }
     __syncthreads();
     const int js = s_j;
-    const double need = sh[4];
+    const double need = sh[20];
     if (js < 0) break;
     // candidates: unsplit flows on js; rho = delay increase per freed core at current prices
     double my_max = 0.0, my_mov = 0.0;
@@ -124,14 +125,14 @@ __device__ inline CapResult cap_route(const CapRoute& q, int max_rounds, double*
     for (int o = 16; o > 0; o >>= 1) my_max = fmax(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
     if ((tid & 31) == 0) red[tid >> 5] = my_max;
     __syncthreads();
-    if (tid == 0) { double m = 0.0; for (int k = 0; k < (int)(blockDim.x >> 5); ++k) m = fmax(m, red[k]); sh[5] = m; }
+    if (tid == 0) { double m = 0.0; for (int k = 0; k < (int)(blockDim.x >> 5); ++k) m = fmax(m, red[k]); sh[21] = m; }
     __syncthreads();
-    const double rho_max = sh[5];
+    const double rho_max = sh[21];
     const double movable = block_sum(my_mov, red);
     __syncthreads();
-    if (tid == 0) sh[6] = movable;
+    if (tid == 0) sh[22] = movable;
     __syncthreads();
-    if (sh[6] < need * (1.0 - 1e-12)) { if (tid == 0) s_ok = 0; __syncthreads(); break; }
+    if (sh[22] < need * (1.0 - 1e-12)) { if (tid == 0) s_ok = 0; __syncthreads(); break; }
     // threshold t*: smallest t with freed(t) = sum_{rho <= t} w*r >= need   (bisection on a step function)
     double lo = -1e-300, hi = rho_max;                    // freed(lo) = 0 < need <= freed(hi)
     for (int it = 0; it < 64; ++it) {
@@ -143,9 +144,9 @@ __device__ inline CapResult cap_route(const CapRoute& q, int max_rounds, double*
       }
       fr = block_sum(fr, red);
       __syncthreads();
-      if (tid == 0) sh[7] = fr;
+      if (tid == 0) sh[23] = fr;
       __syncthreads();
-      if (sh[7] >= need) hi = mid; else lo = mid;
+      if (sh[23] >= need) hi = mid; else lo = mid;
       if (hi - lo <= 1e-14 * fmax(1.0, hi)) break;
     }
     // flows with rho <= lo move completely, flows in (lo, hi] share the remainder
@@ -157,13 +158,13 @@ __device__ inline CapResult cap_route(const CapRoute& q, int max_rounds, double*
       if (rh <= lo) fr_lo += amt; else if (rh <= hi) fr_mg += amt;
     }
     fr_lo = block_sum(fr_lo, red); __syncthreads();
-    if (tid == 0) sh[2] = fr_lo;
+    if (tid == 0) sh[18] = fr_lo;
     __syncthreads();
     fr_mg = block_sum(fr_mg, red); __syncthreads();
-    if (tid == 0) sh[3] = fr_mg;
+    if (tid == 0) sh[19] = fr_mg;
     __syncthreads();
-    const double rest = need - sh[2];
-    const double mv = sh[3] > 0.0 ? fmin(fmax(rest / sh[3], 0.0), 1.0) : 0.0;   // moved share of marginal flows
+    const double rest = need - sh[18];
+    const double mv = sh[19] > 0.0 ? fmin(fmax(rest / sh[19], 0.0), 1.0) : 0.0;   // moved share of marginal flows
     for (int fi = tid; fi < F * N; fi += blockDim.x) {
       const double rh = q.rho[fi];
       if (rh >= 0.0 && (rh <= lo || (rh <= hi && mv >= 1.0))) q.ch[fi] = q.alt[fi];
@@ -225,9 +226,9 @@ __device__ inline CapResult cap_route(const CapRoute& q, int max_rounds, double*
   }
   cost = block_sum(cost, red);
   __syncthreads();
-  if (tid == 0) sh[0] = cost;
+  if (tid == 0) sh[16] = cost;
   __syncthreads();
-  res.cost = sh[0]; res.feasible = 1; res.rounds = round;
+  res.cost = sh[16]; res.feasible = 1; res.rounds = round;
   return res;
 }
 

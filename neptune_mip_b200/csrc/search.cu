@@ -289,7 +289,10 @@ __global__ void __launch_bounds__(256) k_ls_prepare(LsArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(256, 3) k_local_search(LsArgs a) {
+// THREADS = 256 (3 blocks per SM) for small instances, 768 (one block per SM, 24 warps evaluating moves)
+// when a sweep has 10^5+ moves (N > 128)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1) k_local_search(LsArgs a) {
   const int chain = blockIdx.x, b = blockIdx.y, N = a.N, F = a.F;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
   const double* d = a.d + (int64_t)b * N * N;
@@ -305,9 +308,9 @@ __global__ void __launch_bounds__(256, 3) k_local_search(LsArgs a) {
   extern __shared__ double dyn[];
   double* delta = dyn + (int64_t)wid * N;          // per-warp load deltas
   __shared__ double red[32];
-  __shared__ double capsh[8];
-  __shared__ double wbest[8];
-  __shared__ Move wmove[8];
+  __shared__ double capsh[32];
+  __shared__ double wbest[THREADS / 32];
+  __shared__ Move wmove[THREADS / 32];
   __shared__ Move mv;
   __shared__ Move batch[kMaxBatch];
   __shared__ int n_batch;
@@ -558,7 +561,7 @@ __global__ void __launch_bounds__(256, 3) k_local_search(LsArgs a) {
     if (tid == 0) {
       // the warps' best proposals, best first; keep those that touch pairwise disjoint functions and nodes
       // (their delay changes are then independent and their memory checks stay valid together)
-      int order[8];
+      int order[THREADS / 32];
       for (int q = 0; q < nw; ++q) order[q] = q;
       for (int q = 1; q < nw; ++q) { const int v = order[q]; int p2 = q - 1; while (p2 >= 0 && wbest[order[p2]] > wbest[v]) { order[p2 + 1] = order[p2]; --p2; } order[p2 + 1] = v; }
       int nb = 0;
@@ -713,11 +716,16 @@ static int local_search_impl(int step2_mode, const double* bound, int B, int N, 
   a.chain_ws = p;
   a.chain_stride = chain_bytes_h(N, F);
   if ((p - (char*)workspace) + (int64_t)B * chains * a.chain_stride > workspace_bytes) return NEPTUNE_E_NOMEM;
-  const size_t sm = (size_t)8 * N * 8;
+  const int threads = N > 128 ? 768 : 256;
+  const size_t sm = (size_t)(threads / 32) * N * 8;
   if (sm > 200 * 1024) return NEPTUNE_E_SIZE;
-  NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_local_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  if (threads == 256)
+    NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_local_search<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  else
+    NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_local_search<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   { k_ls_prepare<<<B, 256, 0, s>>>(a); NEPTUNE_COUNT(1); }
-  { k_local_search<<<dim3(chains, B), 256, sm, s>>>(a); NEPTUNE_COUNT(1); }
+  if (threads == 256) { k_local_search<256><<<dim3(chains, B), 256, sm, s>>>(a); NEPTUNE_COUNT(1); }
+  else { k_local_search<768><<<dim3(chains, B), 768, sm, s>>>(a); NEPTUNE_COUNT(1); }
   { k_ls_pick<<<B, 256, 0, s>>>(a, best_c, best_obj, best_flags); NEPTUNE_COUNT(1); }
   NEPTUNE_LAUNCH_OK();
   return 0;
