@@ -230,8 +230,11 @@ def run_ours(args):
                            within_1e4=int(sum(g <= 1e-4 for g in gaps)))
     if last.lp is not None:
         lp = last.lp
+        # dual objective of the strengthened relaxation (x <= 1 stated, so it is finite): a lower bound on the
+        # MIP optimum up to the remaining dual residual, which is reported next to it
         quality.update(lp_bound_mean=float(np.mean(lp["dual_obj"])), lp_primal_mean=float(np.mean(lp["primal_obj"])),
-                       lp_converged=int(lp["converged"].sum()))
+                       lp_dual_residual_mean=float(np.mean(lp["dual_res"])), lp_converged=int(lp["converged"].sum()),
+                       mean_gap_to_lp_bound=float(np.mean((delay - lp["dual_obj"]) / np.maximum(np.abs(delay), 1e-9))))
 
     # ---- roofline of the dominant kernels (the PDHG iteration pair) -----------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -204,7 +204,9 @@ __global__ void __launch_bounds__(256) k_values_cols(Layout L, Inputs in0, const
       if (L.kind == NEPTUNE_KIND_MIN_DELAY) o = __dmul_rn(dij, wfi);
       else if (L.kind == NEPTUNE_KIND_MIN_DELAY_UTIL && wm != 0.0)   // delay term only if sum(w) != 0
         o = __ddiv_rn(__dmul_rn(__dmul_rn(1.0 - alpha, wfi), dij), wm);
-      ub = INFINITY;
+      // x <= 1 is implied by C3 (sum_j x = 1, x >= 0); stating it in the strengthened model keeps the dual
+      // objective finite, i.e. a valid lower bound at every PDHG iterate (the as-written model keeps +inf)
+      ub = L.strengthen ? 1.0 : INFINITY;
     } else if (col < L.X + L.C) {
       int64_t fj = col - L.X, f = fj / n;
       if (valT) {
