@@ -37,6 +37,10 @@ class EfttcStepBase(GpuStepMixin, Solver):
         self._finish(c)
 
     def results(self):
+        # the reference stores prev_x / prev_c only in the utilisation classes (:380-387); the step-2 search
+        # seeds itself from the step-1 placement, so every EFTTC step publishes it
+        self.data.prev_x = self._x
+        self.data.prev_c = self._c
         return self._x, self._c
 
     def score(self):
