@@ -133,3 +133,22 @@ def config_payload(name, seed=0, **kw):
     if name == "C5":
         return random_payload(20, 5, seed, node_cores=100, **kw)
     raise ValueError(name)
+
+
+def payload_json_sample():
+    """The shape of the reference's `payload.json` (5 nodes incl. one GPU node, 4 functions incl. one GPU
+    function, no matrices at all -> every default of `input_to_data.py:151-183` kicks in), with the `//`
+    comments of the shipped file removed and `with_db` set to false.  SURVEY.md section 8(c): the reference
+    answers score {'step1': 0.2, 'step2': 39.0} with all four functions on one node."""
+    nodes = ["node_a", "node_b", "node_c", "node_d", "gpu_node_e"]
+    funcs = ["ns/fn_1", "ns/fn_2", "ns/fn_3", "ns/gpu_fn_4"]
+    p = _base(nodes, funcs, [40, 40, 30, 30, 30], [10] * 5, [10] * 4, max_delay=100,
+              allocations={"ns/fn_1": {"node_a": True}, "ns/fn_2": {"node_b": True, "node_c": True},
+                           "ns/fn_3": {"node_b": True}, "ns/gpu_fn_4": {"node_b": True}},
+              solver={"type": "NeptuneMinDelayAndUtilization", "args": {"alpha": 1.0, "verbose": False}})
+    p["gpu_node_names"] = ["gpu_node_e"]
+    p["gpu_node_memories"] = [100]
+    p["gpu_function_names"] = ["ns/gpu_fn_4"]
+    p["gpu_function_memories"] = [50]
+    p.pop("workload_coeff")
+    return p

@@ -12,6 +12,7 @@ Sources of truth written into the fixtures
                        builders emit (through the shim) for C1, C2, 20x5 and the Alibaba case
   random_small.json    unmodified reference on random-workload instances: EFTTC placements (with the
                        documented discard fallback where it raises KeyError) and Neptune* scores
+  payload_json.json    the reference's payload.json sample (no matrices: every default) through six solvers
   mip_optima.json      step-1 optima by HiGHS on the oracle model (C2 seeds, C5 subsample)
 """
 from __future__ import annotations
@@ -91,6 +92,21 @@ def make_c1():
             r.pop("processing_time")
             out["per_solver"][f"{s}|{alpha}"] = _np_to_py(r)
     _dump("c1_test_py.json", out)
+
+
+def make_payload_json():
+    """payload.json of the reference (comments stripped, with_db false): no matrices -> all defaults."""
+    from neptune_mip_b200 import synth
+    from oracle.refshim import load_reference as L
+    out = {}
+    for s in ["NeptuneMinDelayAndUtilization", "NeptuneMinDelay", "NeptuneMinUtilization",
+              "EfttcMinDelay", "EfttcMinUtilization", "EfttcMinDelayAndUtilization"]:
+        p = synth.payload_json_sample()
+        p["solver"] = {"type": s, "args": {"alpha": 1.0, "verbose": False}}
+        r = _clean(L.serve(p))
+        r.pop("processing_time")
+        out[s] = _np_to_py(r)
+    _dump("payload_json.json", out)
 
 
 PDF_SCORES = {   # testing/simulated/simulated_report_finale.pdf "Score Table" (SURVEY.md section 6)
@@ -258,7 +274,7 @@ if __name__ == "__main__":
     ap.add_argument("--only", default=None)
     ap.add_argument("--jobs", type=int, default=4)
     a = ap.parse_args()
-    steps = {"alibaba": make_alibaba, "c1": make_c1, "simulated": lambda: make_simulated(a.jobs),
+    steps = {"alibaba": make_alibaba, "c1": make_c1, "payload_json": make_payload_json, "simulated": lambda: make_simulated(a.jobs),
              "model_hashes": make_model_hashes, "random_small": lambda: make_random_small(a.jobs),
              "mip_optima": lambda: make_mip_optima(a.jobs)}
     for name, fn in steps.items():
