@@ -289,7 +289,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="instances per GPU per step")
     ap.add_argument("--lp-iters", type=int, default=2048)
     ap.add_argument("--chains", type=int, default=8)
-    ap.add_argument("--sweeps", type=int, default=240)
+    ap.add_argument("--sweeps", type=int, default=400)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

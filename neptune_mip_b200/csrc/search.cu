@@ -24,6 +24,7 @@ struct LsArgs {
   const double *d, *w, *r, *m, *Mj, *Kj, *maxd, *cost, *old;
   const uint8_t* seeds;
   const double* guide;
+  int use_smem;              // small instances: d, dT, w, r and the nearest/second-nearest tables live in shared memory
   int step2_mode;            // 0: step-1 objective; 1 "delete" / 2 "create": minimise disruption (step 2)
   const double* bound;       // [B] step 2: the step-1 objective of the placement must stay <= bound[b]
   // workspace
@@ -223,7 +224,7 @@ constexpr int kMaxTabu = 12;
 constexpr int kSwapWindow = 96;                // swap targets examined per pod and sweep when N is larger
 constexpr int kSubsample = 4;                  // sampled sweeps look at 1/kSubsample of the moves
 constexpr int kMaxBatch = 8;                  // disjoint proposals applied together in one sweep
-constexpr int64_t kMaxExchange = 1 << 17;     // exchange proposals examined per sweep (sampled beyond that)
+constexpr int64_t kMaxExchange = 1 << 12;     // exchange proposals examined per sweep (sampled beyond that)
 constexpr double kUnrepairable = 1e11;        // state whose overload cannot be routed away
 
 __device__ inline void apply_move(const Chain& k, int N, const Move& m, bool undo) {
@@ -307,6 +308,33 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1) k_local_searc
   Chain k = carve(a.chain_ws + ((int64_t)b * a.chains + chain) * a.chain_stride, N, F);
   extern __shared__ double dyn[];
   double* delta = dyn + (int64_t)wid * N;          // per-warp load deltas
+  if (a.use_smem) {
+    // every move evaluation walks d^T, w, r and the nearest / second-nearest tables of one function: at
+    // 50x10 all of it (~60 KB) fits next to three resident blocks per SM, so these reads become
+    // shared-memory reads instead of L2 round trips
+    double* p = dyn + (int64_t)nw * N;
+    double* s_d = p; p += (int64_t)N * N;
+    double* s_dT = p; p += (int64_t)N * N;
+    double* s_w = p; p += (int64_t)F * N;
+    double* s_r = p; p += (int64_t)F * N;
+    double* s_b1 = p; p += (int64_t)F * N;
+    double* s_b2 = p; p += (int64_t)F * N;
+    double* s_load = p; p += N; double* s_mem = p; p += N; double* s_K = p; p += N; double* s_M = p; p += N;
+    double* s_m = p; p += F;
+    int* s_a1 = reinterpret_cast<int*>(p);
+    int* s_a2 = s_a1 + (int64_t)F * N;
+    int* s_pods = s_a2 + (int64_t)F * N;
+    int* s_cntf = s_pods + (int64_t)F * N;
+    int* s_cntn = s_cntf + F;
+    uint8_t* s_c = reinterpret_cast<uint8_t*>(s_cntn + N);
+    for (int q = tid; q < N * N; q += blockDim.x) { s_d[q] = d[q]; s_dT[q] = dT[q]; }
+    for (int q = tid; q < F * N; q += blockDim.x) { s_w[q] = w[q]; s_r[q] = r[q]; }
+    for (int q = tid; q < N; q += blockDim.x) { s_K[q] = Kj[q]; s_M[q] = Mj[q]; }
+    for (int q = tid; q < F; q += blockDim.x) s_m[q] = m[q];
+    d = s_d; dT = s_dT; w = s_w; r = s_r; Kj = s_K; Mj = s_M; m = s_m;
+    k.b1 = s_b1; k.b2 = s_b2; k.a1 = s_a1; k.a2 = s_a2;
+    k.load = s_load; k.mem = s_mem; k.pods = s_pods; k.cntf = s_cntf; k.cntn = s_cntn; k.c = s_c;
+  }
   __shared__ double red[32];
   __shared__ double capsh[32];
   __shared__ double wbest[THREADS / 32];
@@ -671,7 +699,7 @@ __global__ void __launch_bounds__(256) k_ls_pick(LsArgs a, uint8_t* __restrict__
   __syncthreads();
   const int src = pick >= 0 ? pick : 0;
   Chain k = carve(a.chain_ws + ((int64_t)b * a.chains + src) * a.chain_stride, N, F);
-  const uint8_t* from = pick >= 0 ? k.best_c : k.c;
+  const uint8_t* from = pick >= 0 ? k.best_c : a.seeds + (int64_t)b * a.S * F * N;   // no feasible chain: first seed
   for (int q = threadIdx.x; q < F * N; q += blockDim.x) best_c[(int64_t)b * F * N + q] = from[q];
 }
 
@@ -717,7 +745,11 @@ static int local_search_impl(int step2_mode, const double* bound, int B, int N, 
   a.chain_stride = chain_bytes_h(N, F);
   if ((p - (char*)workspace) + (int64_t)B * chains * a.chain_stride > workspace_bytes) return NEPTUNE_E_NOMEM;
   const int threads = N > 128 ? 768 : 256;
-  const size_t sm = (size_t)(threads / 32) * N * 8;
+  size_t sm = (size_t)(threads / 32) * N * 8;
+  const size_t tables = (size_t)2 * N * N * 8 + (size_t)4 * F * N * 8 + (size_t)3 * F * N * 4 + (size_t)(4 * N + F) * 8 +
+                        (size_t)(F + N) * 4 + (size_t)F * N + 64;
+  a.use_smem = (threads == 256 && sm + tables <= 72 * 1024) ? 1 : 0;      // 3 blocks per SM must still fit
+  if (a.use_smem) sm += tables;
   if (sm > 200 * 1024) return NEPTUNE_E_SIZE;
   if (threads == 256)
     NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_local_search<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
