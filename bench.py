@@ -102,8 +102,8 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 10))
-    n_inst = max(procs, 4)
-    limit = 20.0
+    n_inst = args.ref_instances if args.ref_instances > 0 else max(procs, 4)
+    limit = args.ref_limit
     walls = []
     recs = []
     for it in range(args.warmup + args.steps):
@@ -291,6 +291,8 @@ def main():
     ap.add_argument("--chains", type=int, default=8)
     ap.add_argument("--sweeps", type=int, default=400)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-limit", type=float, default=20.0, help="--impl reference: HiGHS cap per instance (s)")
+    ap.add_argument("--ref-instances", type=int, default=0, help="--impl reference: instances per step (0 = one per worker)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
