@@ -137,6 +137,22 @@ int neptune_spmv_t(int B, int64_t rows, int64_t cols, const int64_t* rowT_ptr,
                    const int32_t* colT_idx, const double* valT, const double* y, double* out,
                    void* stream);
 
+/* ---- (b, matrix-free) the same PDHG without the matrix ----------------------------------------------
+ * The LP relaxation of the STRENGTHENED min-delay model (what neptune_assemble_* builds with kind =
+ * NEPTUNE_KIND_MIN_DELAY, flags = NEPTUNE_FLAG_STRENGTHEN: rows of `neptune/utils/constraints_step1.py:5-65`
+ * with the C1a rows free, plus x[i,f,j] <= c[f,j] and x <= 1; objective `objectives.py:4-11`), solved by the
+ * algorithm of neptune_pdhg_solve with ruiz_iters = 0 (Pock-Chambolle step sizes), but every coefficient is
+ * regenerated from d, w, r, m instead of being read from CSR arrays: one streaming pass over x / yS and their
+ * running sums per iteration.  x[B][cols], y[B][rows] are the canonical vectors of that model (in/out, warm
+ * start; the multipliers of the free C1a rows are returned as 0).  Other kinds return NEPTUNE_E_ARG. */
+int neptune_pdhg_mf_workspace_bytes(int B, int N, int F, int64_t* bytes);
+int neptune_pdhg_mf_solve(int B, int N, int F, int kind,
+                          const double* d, const double* w, const double* r, const double* m,
+                          const double* Mj, const double* Kj,
+                          const neptune_pdhg_params* params_h,
+                          double* x, double* y, neptune_pdhg_result* result_d,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- (b') step-wise PDHG building blocks for the function-block-sharded solver (one process per GPU,
  * SURVEY.md section 8(e)): GPU g owns the functions of its block, i.e. the x / c columns and the C1 / C3
  * rows of those functions; the coupling rows (C2 memory, C4 CPU) are replicated, every GPU computes

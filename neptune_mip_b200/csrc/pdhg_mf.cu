@@ -1,0 +1,761 @@
+// pdhg_mf.cu -- (b) MATRIX-FREE restarted, averaged, diagonally preconditioned PDHG for the LP relaxation
+// of the strengthened min-delay placement model (same LP as assemble.cu builds with
+// NEPTUNE_FLAG_STRENGTHEN, same algorithm and control logic as pdhg.cu with ruiz_iters = 0).
+//
+// Replaces the LP work inside pywraplp.Solver.Solve() (reference core/solvers/solver.py:37) for the model
+// of neptune/utils/constraints_step1.py:5-65 + objectives.py:4-11.  Every coefficient of that model is a
+// closed formula of (w, r, m, d), so nothing of the CSR matrix is read: one PDHG iteration is ONE streaming
+// pass over the x-shaped arrays plus O(F*N) work on the small vectors.
+//
+//   columns  x[f,i,j] in [0,1]  (canonical f*N*N + i*N + j),  c[f,j] in [0,1]
+//   rows     C1b (f,j): sum_i x - c >= -eps      y1      C3 (f,i): sum_j x = 1              y3
+//            C2  (j)  : sum_f m c <= Mj          y2      C4 (j)  : sum_{f,i} w r x <= Kj     y4
+//            S (f,i,j): x - c <= 0               yS      (C1a is a free row in the strengthened model: y = 0)
+//   g_x = d*w + y1[f,j] + y3[f,i] + w[f,i] r[f,j] y4[j] + yS[f,i,j]       g_c = -y1 + m[f] y2[j] - sum_i yS
+//   Pock-Chambolle (alpha = 1) step sizes generated on the fly:  T_x = 1/(3 + w r),  T_c = 1/(1 + m[f] + N),
+//   S_1b = 1/(N+1), S_2 = 1/sum m, S_3 = 1/N, S_4[j] = 1/sum_{f,i} w r, S_S = 1/2.
+//
+// k_mf_iter (the dominant kernel): per element  x+ = clip(x - tau T_x g_x, 0, 1), xbar = 2x+ - x,
+//   yS+ = max(yS + sigma/2 (xbar - cbar[f,j]), 0), running sums; per tile the partial column sums of xbar,
+//   w*xbar and yS+ and the row sums of xbar go to small buffers (no atomics, fixed summation order).
+// k_mf_small: the F*N-sized updates -- duals y1/y3/y4 from the partial sums (POST), then the c columns of the
+//   next iteration (PREC) and the C2 dual (Y2).
+// Algorithmic bytes per iteration and instance: X*(8 x + 8 yS + 8 xsum + 8 ysum read, the same written)
+//   = 64*X, + 8*N*N (d, re-read per function from L2) + O(F*N)  [X = F*N*N]; the CSR solver moves
+//   16*nnz + 88*cols + 72*rows ~ 260*X for the same iteration.
+#include "common.cuh"
+#include "pdhg_ctl.cuh"
+
+namespace neptune {
+
+struct MfGeo {
+  int N, F, K, JT, ct, RT, rt, tiles_inst;
+  int64_t X, C, cols, rows, r2, r3, r4, rs;
+};
+
+static MfGeo make_geo(int N, int F) {
+  MfGeo G;
+  G.N = N; G.F = F;
+  G.K = N <= 32 ? 1 : (N <= 64 ? 2 : 4);        // columns per lane
+  G.JT = 32 * G.K; G.ct = (N + G.JT - 1) / G.JT;
+  G.RT = N <= 64 ? N : 64; G.rt = (N + G.RT - 1) / G.RT;
+  G.tiles_inst = F * G.rt * G.ct;
+  Layout L(N, F, NEPTUNE_KIND_MIN_DELAY, NEPTUNE_FLAG_STRENGTHEN);
+  G.X = L.X; G.C = L.C; G.cols = L.cols; G.rows = L.rows;
+  G.r2 = L.r2; G.r3 = L.r3; G.r4 = L.r4; G.rs = L.rs;
+  return G;
+}
+
+struct MfIn { const double *d, *w, *r, *m, *Mj, *Kj; };
+
+struct MfSt {
+  double *x, *y, *xsum, *ysum;   // canonical vectors [B][cols] / [B][rows]
+  double *cbar;                  // [B][C]        2c+ - c of the running iteration
+  double *P1, *P4, *PS;          // [B][F][rt][N] partial column sums (xbar, r*w*xbar, yS+) per row tile
+  double *P3;                    // [B][C][ct]    partial row sums of xbar per column tile
+  double *S4;                    // [B][N]        1 / sum_{f,i} |w r|
+  double *S2;                    // [B]           1 / sum_f |m|
+  double *scal;                  // [B][tiles_inst][4] per-tile scalars of the KKT evaluation / setup
+};
+
+constexpr int kMfThreads = 256;
+constexpr int kMfWarps = kMfThreads / 32;
+
+struct Tile { int b, f, it, jt; };
+__device__ __forceinline__ Tile decode_tile(const MfGeo& G, int64_t tile) {
+  Tile t;
+  t.b = (int)(tile / G.tiles_inst);
+  int k = (int)(tile - (int64_t)t.b * G.tiles_inst);
+  t.jt = k % G.ct; k /= G.ct;
+  t.it = k % G.rt; t.f = k / G.rt;
+  return t;
+}
+
+// cross-warp sum of per-lane column accumulators; thread c < 32*K then owns column c of the tile
+template <int K>
+__device__ __forceinline__ double column_total(double (*sm)[32 * K], int c) {
+  double s = 0.0;
+#pragma unroll
+  for (int w = 0; w < kMfWarps; ++w) s += sm[w][c];
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the iteration pass
+// ---------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kMfThreads, (K == 4 ? 2 : 3))
+k_mf_iter(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
+  __shared__ double sm[3][kMfWarps][32 * K];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = G.N;
+  const int64_t NN = (int64_t)N * N;
+  const int64_t total = (int64_t)B * G.tiles_inst;
+  for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const Tile t = decode_tile(G, tile);
+    const int b = t.b, f = t.f;
+    if (ctl[b].converged) continue;
+    const double tau = ctl[b].tau, shalf = 0.5 * ctl[b].sigma;
+    const double* __restrict__ d = in.d + (int64_t)b * NN;
+    const double* __restrict__ w = in.w + ((int64_t)b * G.F + f) * N;
+    const double* __restrict__ r = in.r + ((int64_t)b * G.F + f) * N;
+    const double* __restrict__ y = st.y + (int64_t)b * G.rows;
+    double* __restrict__ xp = st.x + (int64_t)b * G.cols + (int64_t)f * NN;
+    double* __restrict__ xsp = st.xsum + (int64_t)b * G.cols + (int64_t)f * NN;
+    double* __restrict__ sp = st.y + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
+    double* __restrict__ ssp = st.ysum + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
+    const double* __restrict__ cbar = st.cbar + (int64_t)b * G.C + (int64_t)f * N;
+
+    int jj[K]; bool vj[K];
+    double y1j[K], rj[K], rr4[K], cb[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int j = t.jt * G.JT + k * 32 + lane;
+      vj[k] = j < N; jj[k] = vj[k] ? j : 0;
+      y1j[k] = y[2 * ((int64_t)f * N + jj[k]) + 1];
+      rj[k] = __ldg(r + jj[k]);
+      rr4[k] = rj[k] * y[G.r4 + jj[k]];
+      cb[k] = cbar[jj[k]];
+    }
+    double a1[K], a4[K], aS[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { a1[k] = 0.0; a4[k] = 0.0; aS[k] = 0.0; }
+
+    const int i0 = t.it * G.RT, i1 = min(N, i0 + G.RT);
+    for (int i = i0 + warp; i < i1; i += kMfWarps) {
+      const double wfi = __ldg(w + i), y3i = y[G.r3 + (int64_t)f * N + i];
+      const int64_t ro = (int64_t)i * N;
+      double xv[K], sv[K], xs[K], ss[K], dv[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (vj[k]) {
+          xv[k] = xp[ro + jj[k]]; sv[k] = sp[ro + jj[k]];
+          xs[k] = xsp[ro + jj[k]]; ss[k] = ssp[ro + jj[k]];
+          dv[k] = __ldg(d + ro + jj[k]);
+        }
+      }
+      double rsum = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (vj[k]) {
+          const double wr = fabs(wfi * rj[k]);
+          const double g = __dmul_rn(dv[k], wfi) + y1j[k] + y3i + wfi * rr4[k] + sv[k];
+          double xn = xv[k] - tau * g / (3.0 + wr);
+          xn = fmin(fmax(xn, 0.0), 1.0);
+          const double xb = 2.0 * xn - xv[k];
+          const double sn = fmax(sv[k] + shalf * (xb - cb[k]), 0.0);
+          xp[ro + jj[k]] = xn; sp[ro + jj[k]] = sn;
+          xsp[ro + jj[k]] = xs[k] + xn; ssp[ro + jj[k]] = ss[k] + sn;
+          a1[k] += xb; a4[k] += wfi * xb; aS[k] += sn; rsum += xb;
+        }
+      }
+      rsum = warp_sum(rsum);
+      if (lane == 0) st.P3[((int64_t)b * G.C + (int64_t)f * N + i) * G.ct + t.jt] = rsum;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      sm[0][warp][k * 32 + lane] = a1[k]; sm[1][warp][k * 32 + lane] = a4[k]; sm[2][warp][k * 32 + lane] = aS[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 32 * K; c += kMfThreads) {
+      const int j = t.jt * G.JT + c;
+      if (j < N) {
+        const int64_t o = (((int64_t)b * G.F + f) * G.rt + t.it) * N + j;
+        st.P1[o] = column_total<K>(sm[0], c);
+        st.P4[o] = __ldg(r + j) * column_total<K>(sm[1], c);
+        st.PS[o] = column_total<K>(sm[2], c);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// KKT pieces of a candidate (which = 0: current iterate, 1: running average): the same partial sums from a
+// read-only pass, plus per tile {obj.x, sum min(rc_x, 0), sum max(x - c, 0)^2}.  mode 1: only the column
+// sums of yS (refreshes PS after a restart / at the start).
+// ---------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kMfThreads, (K == 4 ? 2 : 3))
+k_mf_eval(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, int which, int only_ps) {
+  __shared__ double sm[3][kMfWarps][32 * K];
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = G.N;
+  const int64_t NN = (int64_t)N * N;
+  const int64_t total = (int64_t)B * G.tiles_inst;
+  for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const Tile t = decode_tile(G, tile);
+    const int b = t.b, f = t.f;
+    if (ctl[b].converged) continue;
+    const double sc = which ? 1.0 / (double)max(ctl[b].avg_count, 1) : 1.0;
+    const double* __restrict__ d = in.d + (int64_t)b * NN;
+    const double* __restrict__ w = in.w + ((int64_t)b * G.F + f) * N;
+    const double* __restrict__ r = in.r + ((int64_t)b * G.F + f) * N;
+    const double* __restrict__ xvec = (which ? st.xsum : st.x) + (int64_t)b * G.cols;
+    const double* __restrict__ yvec = (which ? st.ysum : st.y) + (int64_t)b * G.rows;
+    const double* __restrict__ xp = xvec + (int64_t)f * NN;
+    const double* __restrict__ sp = yvec + G.rs + (int64_t)f * NN;
+
+    int jj[K]; bool vj[K];
+    double y1j[K], rj[K], rr4[K], cc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int j = t.jt * G.JT + k * 32 + lane;
+      vj[k] = j < N; jj[k] = vj[k] ? j : 0;
+      y1j[k] = yvec[2 * ((int64_t)f * N + jj[k]) + 1] * sc;
+      rj[k] = __ldg(r + jj[k]);
+      rr4[k] = rj[k] * yvec[G.r4 + jj[k]] * sc;
+      cc[k] = xvec[G.X + (int64_t)f * N + jj[k]] * sc;
+    }
+    double a1[K], a4[K], aS[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { a1[k] = 0.0; a4[k] = 0.0; aS[k] = 0.0; }
+    double pobj = 0.0, rcneg = 0.0, ps2 = 0.0;
+
+    const int i0 = t.it * G.RT, i1 = min(N, i0 + G.RT);
+    for (int i = i0 + warp; i < i1; i += kMfWarps) {
+      const int64_t ro = (int64_t)i * N;
+      if (only_ps) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) if (vj[k]) aS[k] += sp[ro + jj[k]] * sc;
+        continue;
+      }
+      const double wfi = __ldg(w + i), y3i = yvec[G.r3 + (int64_t)f * N + i] * sc;
+      double rsum = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (vj[k]) {
+          const double xv = xp[ro + jj[k]] * sc, sv = sp[ro + jj[k]] * sc;
+          const double o = __dmul_rn(__ldg(d + ro + jj[k]), wfi);
+          const double rc = o + y1j[k] + y3i + wfi * rr4[k] + sv;
+          pobj += o * xv;
+          rcneg += fmin(rc, 0.0);
+          const double viol = fmax(xv - cc[k], 0.0);
+          ps2 += viol * viol;
+          a1[k] += xv; a4[k] += wfi * xv; aS[k] += sv; rsum += xv;
+        }
+      }
+      rsum = warp_sum(rsum);
+      if (lane == 0) st.P3[((int64_t)b * G.C + (int64_t)f * N + i) * G.ct + t.jt] = rsum;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      sm[0][warp][k * 32 + lane] = a1[k]; sm[1][warp][k * 32 + lane] = a4[k]; sm[2][warp][k * 32 + lane] = aS[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 32 * K; c += kMfThreads) {
+      const int j = t.jt * G.JT + c;
+      if (j < N) {
+        const int64_t o = (((int64_t)b * G.F + f) * G.rt + t.it) * N + j;
+        if (!only_ps) {
+          st.P1[o] = column_total<K>(sm[0], c);
+          st.P4[o] = __ldg(r + j) * column_total<K>(sm[1], c);
+        }
+        st.PS[o] = column_total<K>(sm[2], c);
+      }
+    }
+    if (!only_ps) {
+      const double s0 = block_sum(pobj, red), s1 = block_sum(rcneg, red), s2 = block_sum(ps2, red);
+      if (threadIdx.x == 0) {
+        double* q = st.scal + tile * 4;
+        q[0] = s0; q[1] = s1; q[2] = s2; q[3] = 0.0;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the small vectors
+// ---------------------------------------------------------------------------------------------------
+enum { PH_POST = 1, PH_PREC = 2, PH_Y2 = 4 };
+
+__global__ void __launch_bounds__(256)
+k_mf_small(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int mask, const int* __restrict__ skip_post,
+           int fused) {
+  const int b = blockIdx.y;
+  if (ctl[b].converged) return;
+  if (skip_post && *skip_post) mask &= ~PH_POST;
+  const int N = G.N, F = G.F, rt = G.rt, ct = G.ct;
+  const int64_t C = G.C;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const double tau = ctl[b].tau, sigma = ctl[b].sigma;
+  double* __restrict__ y = st.y + (int64_t)b * G.rows;
+  double* __restrict__ ys = st.ysum + (int64_t)b * G.rows;
+  double* __restrict__ c = st.x + (int64_t)b * G.cols + G.X;
+  double* __restrict__ cs = st.xsum + (int64_t)b * G.cols + G.X;
+  double* __restrict__ cbar = st.cbar + (int64_t)b * C;
+  const double* __restrict__ P1 = st.P1 + (int64_t)b * F * rt * N;
+  const double* __restrict__ P4 = st.P4 + (int64_t)b * F * rt * N;
+  const double* __restrict__ PS = st.PS + (int64_t)b * F * rt * N;
+  const double* __restrict__ P3 = st.P3 + (int64_t)b * C * ct;
+  const double* __restrict__ m = in.m + (int64_t)b * F;
+
+  if (mask & PH_POST) {
+    const double s1 = sigma / (double)(N + 1), s3 = sigma / (double)N;
+    for (int64_t q = tid; q < C; q += nth) {
+      const int f = (int)(q / N), j = (int)(q - (int64_t)f * N);
+      double a = 0.0;
+      for (int it = 0; it < rt; ++it) a += P1[((int64_t)f * rt + it) * N + j];
+      a -= cbar[q];
+      double v = y[2 * q + 1] + s1 * a;
+      double yn = v - s1 * fmax(v / s1, -kEps);                  // C1b: [-eps, +inf)
+      y[2 * q + 1] = yn; ys[2 * q + 1] += yn;
+      a = 0.0;
+      for (int jt = 0; jt < ct; ++jt) a += P3[q * ct + jt];
+      v = y[G.r3 + q] + s3 * a;
+      yn = v - s3;                                               // C3: [1, 1]
+      y[G.r3 + q] = yn; ys[G.r3 + q] += yn;
+    }
+    const double* __restrict__ Kj = in.Kj + (int64_t)b * N;
+    for (int64_t j = tid; j < N; j += nth) {
+      double a = 0.0;
+      for (int f = 0; f < F; ++f) {
+        double pa = 0.0;
+        for (int it = 0; it < rt; ++it) pa += P4[((int64_t)f * rt + it) * N + j];
+        a += pa;
+      }
+      const double s = sigma * st.S4[(int64_t)b * N + j];
+      const double v = y[G.r4 + j] + s * a;
+      const double yn = v - s * fmin(v / s, Kj[j]);              // C4: (-inf, Kj]
+      y[G.r4 + j] = yn; ys[G.r4 + j] += yn;
+    }
+  }
+  if (mask & PH_PREC) {
+    for (int64_t q = tid; q < C; q += nth) {
+      const int f = (int)(q / N), j = (int)(q - (int64_t)f * N);
+      double sS = 0.0;
+      for (int it = 0; it < rt; ++it) sS += PS[((int64_t)f * rt + it) * N + j];
+      const double mf = m[f];
+      const double gc = -y[2 * q + 1] + mf * y[G.r2 + j] - sS;
+      const double co = c[q];
+      double cn = co - tau * gc / (1.0 + mf + (double)N);
+      cn = fmin(fmax(cn, 0.0), 1.0);
+      cbar[q] = 2.0 * cn - co;
+      c[q] = cn; cs[q] += cn;
+    }
+  }
+  if (mask & PH_Y2) {
+    if (fused) __syncthreads();
+    const double* __restrict__ Mj = in.Mj + (int64_t)b * N;
+    const double s = sigma * st.S2[b];
+    for (int64_t j = tid; j < N; j += nth) {
+      double a = 0.0;
+      for (int f = 0; f < F; ++f) a += m[f] * cbar[(int64_t)f * N + j];
+      const double v = y[G.r2 + j] + s * a;
+      const double yn = v - s * fmin(v / s, Mj[j]);              // C2: (-inf, Mj]
+      y[G.r2 + j] = yn; ys[G.r2 + j] += yn;
+    }
+  }
+}
+
+// rows / c-columns part of the KKT evaluation from the partial sums of k_mf_eval; one block per instance,
+// fixed summation order.  Writes ctl[b].acc[ACC_CUR / ACC_AVG + {PRES2, DRES2, POBJ, DOBJ}].
+__global__ void __launch_bounds__(256)
+k_mf_eval_small(MfGeo G, MfIn in, MfSt st, Ctl* __restrict__ ctl, int which) {
+  const int b = blockIdx.x;
+  if (ctl[b].converged) return;
+  __shared__ double red[32];
+  const int N = G.N, F = G.F, rt = G.rt, ct = G.ct;
+  const int64_t C = G.C;
+  const double sc = which ? 1.0 / (double)max(ctl[b].avg_count, 1) : 1.0;
+  const double* __restrict__ xvec = (which ? st.xsum : st.x) + (int64_t)b * G.cols;
+  const double* __restrict__ yv = (which ? st.ysum : st.y) + (int64_t)b * G.rows;
+  const double* __restrict__ cv = xvec + G.X;
+  const double* __restrict__ P1 = st.P1 + (int64_t)b * F * rt * N;
+  const double* __restrict__ P4 = st.P4 + (int64_t)b * F * rt * N;
+  const double* __restrict__ PS = st.PS + (int64_t)b * F * rt * N;
+  const double* __restrict__ P3 = st.P3 + (int64_t)b * C * ct;
+  const double* __restrict__ m = in.m + (int64_t)b * F;
+  const double* __restrict__ Mj = in.Mj + (int64_t)b * N;
+  const double* __restrict__ Kj = in.Kj + (int64_t)b * N;
+  double pres2 = 0.0, dres2 = 0.0, pobj = 0.0, dobj = 0.0;
+  for (int64_t q = threadIdx.x; q < C; q += blockDim.x) {
+    const int f = (int)(q / N), j = (int)(q - (int64_t)f * N);
+    const double y1 = yv[2 * q + 1] * sc, cq = cv[q] * sc;
+    double a = 0.0, sS = 0.0;
+    for (int it = 0; it < rt; ++it) { a += P1[((int64_t)f * rt + it) * N + j]; sS += PS[((int64_t)f * rt + it) * N + j]; }
+    double viol = fmin(a - cq + kEps, 0.0);
+    pres2 += viol * viol;
+    if (y1 > 0.0) dres2 += y1 * y1; else dobj += kEps * y1;
+    a = 0.0;
+    for (int jt = 0; jt < ct; ++jt) a += P3[q * ct + jt];
+    viol = a - 1.0;
+    pres2 += viol * viol;
+    dobj -= yv[G.r3 + q] * sc;
+    const double rcc = -y1 + m[f] * yv[G.r2 + j] * sc - sS;
+    dobj += fmin(rcc, 0.0);                                       // c in [0, 1]
+  }
+  for (int64_t j = threadIdx.x; j < N; j += blockDim.x) {
+    double a2 = 0.0, a4 = 0.0;
+    for (int f = 0; f < F; ++f) {
+      a2 += m[f] * cv[(int64_t)f * N + j] * sc;
+      double pa = 0.0;
+      for (int it = 0; it < rt; ++it) pa += P4[((int64_t)f * rt + it) * N + j];
+      a4 += pa;
+    }
+    double viol = fmax(a2 - Mj[j], 0.0);
+    pres2 += viol * viol;
+    viol = fmax(a4 - Kj[j], 0.0);
+    pres2 += viol * viol;
+    const double y2 = yv[G.r2 + j] * sc, y4 = yv[G.r4 + j] * sc;
+    if (y2 > 0.0) dobj -= Mj[j] * y2; else dres2 += y2 * y2;
+    if (y4 > 0.0) dobj -= Kj[j] * y4; else dres2 += y4 * y4;
+  }
+  const double* __restrict__ sq = st.scal + (int64_t)b * G.tiles_inst * 4;
+  for (int t = threadIdx.x; t < G.tiles_inst; t += blockDim.x) {
+    pobj += sq[t * 4 + 0]; dobj += sq[t * 4 + 1]; pres2 += sq[t * 4 + 2];
+  }
+  const double s0 = block_sum(pres2, red), s1 = block_sum(dres2, red), s2 = block_sum(pobj, red),
+               s3 = block_sum(dobj, red);
+  if (threadIdx.x == 0) {
+    double* acc = ctl[b].acc + (which ? ACC_AVG : ACC_CUR);
+    acc[PRES2] = s0; acc[DRES2] = s1; acc[POBJ] = s2; acc[DOBJ] = s3;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// setup: step-size vectors S4, S2, the norms behind omega0 and the tolerances (same definitions as k_norms
+// of pdhg.cu), multipliers of the free C1a rows zeroed.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mf_setup(MfGeo G, MfIn in, MfSt st, int nblk) {
+  const int b = blockIdx.y;
+  __shared__ double red[32];
+  const int N = G.N, F = G.F;
+  const int64_t NN = (int64_t)N * N;
+  const double* __restrict__ d = in.d + (int64_t)b * NN;
+  const double* __restrict__ w = in.w + (int64_t)b * F * N;
+  const double* __restrict__ r = in.r + (int64_t)b * F * N;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = tid; j < N; j += nth) {
+    double s = 0.0;
+    for (int f = 0; f < F; ++f) {
+      const double rfj = r[(int64_t)f * N + j];
+      for (int i = 0; i < N; ++i) s += fabs(__dmul_rn(w[(int64_t)f * N + i], rfj));
+    }
+    st.S4[(int64_t)b * N + j] = s > 0.0 ? 1.0 / s : 1.0;
+  }
+  if (tid == 0) {
+    double s = 0.0;
+    for (int f = 0; f < F; ++f) s += fabs(in.m[(int64_t)b * F + f]);
+    st.S2[b] = s > 0.0 ? 1.0 / s : 1.0;
+  }
+  double* __restrict__ y = st.y + (int64_t)b * G.rows;
+  for (int64_t q = tid; q < G.C; q += nth) y[2 * q] = 0.0;
+  double nc2 = 0.0, ncs2 = 0.0;
+  for (int64_t q = tid; q < G.X; q += nth) {
+    const int f = (int)(q / NN);
+    const int64_t rem = q - (int64_t)f * NN;
+    const int i = (int)(rem / N), j = (int)(rem - (int64_t)i * N);
+    const double wfi = w[(int64_t)f * N + i];
+    const double o = __dmul_rn(d[rem], wfi);
+    nc2 += o * o;
+    ncs2 += o * o / (3.0 + fabs(wfi * r[(int64_t)f * N + j]));
+  }
+  const double s0 = block_sum(nc2, red), s1 = block_sum(ncs2, red);
+  if (threadIdx.x == 0) {
+    double* q = st.scal + ((int64_t)b * G.tiles_inst + blockIdx.x) * 4;
+    q[0] = s0; q[1] = s1;
+  }
+  (void)nblk;
+}
+
+__global__ void k_mf_setup_norms(MfGeo G, MfIn in, MfSt st, Ctl* __restrict__ ctl, int B, int nblk) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int N = G.N;
+  const double C = (double)G.C;
+  double nc2 = 0.0, ncs2 = 0.0;
+  for (int k = 0; k < nblk; ++k) {
+    nc2 += st.scal[((int64_t)b * G.tiles_inst + k) * 4 + 0];
+    ncs2 += st.scal[((int64_t)b * G.tiles_inst + k) * 4 + 1];
+  }
+  double m2 = 0.0, k2 = 0.0, k2s = 0.0;
+  for (int j = 0; j < N; ++j) {
+    const double mj = in.Mj[(int64_t)b * N + j], kj = in.Kj[(int64_t)b * N + j];
+    if (isfinite(mj)) m2 += mj * mj;
+    if (isfinite(kj)) { k2 += kj * kj; k2s += kj * kj * st.S4[(int64_t)b * N + j]; }
+  }
+  double* acc = ctl[b].acc;
+  acc[ACC_NB2] = kEps * kEps * C + m2 + C + k2;
+  acc[ACC_NC2] = nc2;
+  acc[ACC_NBS2] = kEps * kEps * C / (double)(N + 1) + m2 * st.S2[b] + C / (double)N + k2s;
+  acc[ACC_NCS2] = ncs2;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// restart: x, y <- running average (action 1) or keep (2); sums reset; movement since the last restart
+// point in the preconditioned norms (per-block partials, summed in order by k_mf_restart_norms).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_mf_apply_restart(MfGeo G, MfIn in, MfSt st, double* __restrict__ xres, double* __restrict__ yres,
+                   const Ctl* __restrict__ ctl, double* __restrict__ part) {
+  const int b = blockIdx.y;
+  double* out = part + ((int64_t)b * gridDim.x + blockIdx.x) * 2;
+  const int action = ctl[b].action;
+  if (action == 0) { if (threadIdx.x == 0) { out[0] = 0.0; out[1] = 0.0; } return; }
+  __shared__ double red[32];
+  const int N = G.N, F = G.F;
+  const int64_t NN = (int64_t)N * N;
+  const double inv = 1.0 / (double)max(ctl[b].avg_count, 1);
+  const double* __restrict__ w = in.w + (int64_t)b * F * N;
+  const double* __restrict__ r = in.r + (int64_t)b * F * N;
+  const double* __restrict__ m = in.m + (int64_t)b * F;
+  double dx2 = 0.0, dy2 = 0.0;
+  const int64_t n = G.cols + G.rows;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    if (k < G.cols) {
+      double diag;
+      if (k < G.X) {
+        const int f = (int)(k / NN);
+        const int64_t rem = k - (int64_t)f * NN;
+        const int i = (int)(rem / N), j = (int)(rem - (int64_t)i * N);
+        diag = 1.0 / (3.0 + fabs(w[(int64_t)f * N + i] * r[(int64_t)f * N + j]));
+      } else {
+        const int f = (int)((k - G.X) / N);
+        diag = 1.0 / (1.0 + fabs(m[f]) + (double)N);
+      }
+      const int64_t q = (int64_t)b * G.cols + k;
+      const double nv = (action == 1) ? st.xsum[q] * inv : st.x[q];
+      const double dl = nv - xres[q];
+      dx2 += dl * dl / diag;
+      st.x[q] = nv; xres[q] = nv; st.xsum[q] = 0.0;
+    } else {
+      const int64_t row = k - G.cols;
+      double diag;
+      if (row < G.r2) diag = (row & 1) ? 1.0 / (double)(N + 1) : 1.0;
+      else if (row < G.r3) diag = st.S2[b];
+      else if (row < G.r4) diag = 1.0 / (double)N;
+      else if (row < G.rs) diag = st.S4[(int64_t)b * N + (row - G.r4)];
+      else diag = 0.5;
+      const int64_t q = (int64_t)b * G.rows + row;
+      const double nv = (action == 1) ? st.ysum[q] * inv : st.y[q];
+      const double dl = nv - yres[q];
+      dy2 += dl * dl / diag;
+      st.y[q] = nv; yres[q] = nv; st.ysum[q] = 0.0;
+    }
+  }
+  const double s0 = block_sum(dx2, red), s1 = block_sum(dy2, red);
+  if (threadIdx.x == 0) { out[0] = s0; out[1] = s1; }
+}
+
+__global__ void k_mf_restart_norms(int B, int nblk, const double* __restrict__ part, Ctl* __restrict__ ctl) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double dx2 = 0.0, dy2 = 0.0;
+  for (int k = 0; k < nblk; ++k) { dx2 += part[((int64_t)b * nblk + k) * 2]; dy2 += part[((int64_t)b * nblk + k) * 2 + 1]; }
+  ctl[b].acc[ACC_DX2] = dx2; ctl[b].acc[ACC_DY2] = dy2;
+}
+
+static inline size_t mf_align(size_t v) { return (v + 255) & ~(size_t)255; }
+constexpr int kMfRestartBlocks = 64;       // blocks per instance of k_mf_apply_restart / k_mf_setup (upper bound)
+
+struct MfWs {
+  size_t xsum, xres, ysum, yres, cbar, P1, P4, PS, P3, S4, S2, scal, part, ctl, flag, total;
+};
+
+static MfWs mf_layout(int B, const MfGeo& G) {
+  MfWs W; size_t t = 0;
+  auto take = [&](size_t bytes) { size_t o = t; t += mf_align(bytes); return o; };
+  const size_t cb = (size_t)B * G.cols * 8, rb = (size_t)B * G.rows * 8;
+  const size_t pb = (size_t)B * G.F * G.rt * G.N * 8;
+  W.xsum = take(cb); W.xres = take(cb); W.ysum = take(rb); W.yres = take(rb);
+  W.cbar = take((size_t)B * G.C * 8);
+  W.P1 = take(pb); W.P4 = take(pb); W.PS = take(pb);
+  W.P3 = take((size_t)B * G.C * G.ct * 8);
+  W.S4 = take((size_t)B * G.N * 8); W.S2 = take((size_t)B * 8);
+  const size_t per_inst = (size_t)(G.tiles_inst > kMfRestartBlocks ? G.tiles_inst : kMfRestartBlocks);
+  W.scal = take((size_t)B * per_inst * 4 * 8);
+  W.part = take((size_t)B * kMfRestartBlocks * 2 * 8);
+  W.ctl = take((size_t)B * sizeof(Ctl));
+  W.flag = take(256);
+  W.total = t + 256;
+  return W;
+}
+
+template <int K> static int mf_grid(bool eval) {
+  int occ = 0;
+  if (eval) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mf_eval<K>, kMfThreads, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mf_iter<K>, kMfThreads, 0);
+  if (occ < 1) occ = 1;
+  return kNumSMs * occ;
+}
+
+struct MfPlan {
+  int B; MfGeo G; MfIn in; MfSt st; Ctl* ctl; cudaStream_t s;
+  int grid_iter, grid_eval, small_blocks, fused;
+};
+
+static void mf_launch_iter(const MfPlan& P) {
+  const int64_t total = (int64_t)P.B * P.G.tiles_inst;
+  const int g = (int)(total < P.grid_iter ? total : P.grid_iter);
+  switch (P.G.K) {
+    case 1: k_mf_iter<1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+    case 2: k_mf_iter<2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+    default: k_mf_iter<4><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+  }
+  NEPTUNE_COUNT(1);
+}
+
+static void mf_launch_eval(const MfPlan& P, int which, int only_ps) {
+  const int64_t total = (int64_t)P.B * P.G.tiles_inst;
+  const int g = (int)(total < P.grid_eval ? total : P.grid_eval);
+  switch (P.G.K) {
+    case 1: k_mf_eval<1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, which, only_ps); break;
+    case 2: k_mf_eval<2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, which, only_ps); break;
+    default: k_mf_eval<4><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, which, only_ps); break;
+  }
+  NEPTUNE_COUNT(1);
+}
+
+// the small updates around one pass: `mask` of PH_*; in the unfused (large instance) case the C2 dual needs
+// every cbar of the instance, so it is a launch of its own
+static void mf_launch_small(const MfPlan& P, int mask, const int* skip_post) {
+  dim3 g(P.small_blocks, P.B);
+  if (P.fused) {
+    k_mf_small<<<g, 256, 0, P.s>>>(P.G, P.in, P.st, P.ctl, mask, skip_post, 1); NEPTUNE_COUNT(1);
+  } else {
+    if (mask & (PH_POST | PH_PREC)) {
+      k_mf_small<<<g, 256, 0, P.s>>>(P.G, P.in, P.st, P.ctl, mask & (PH_POST | PH_PREC), skip_post, 0); NEPTUNE_COUNT(1);
+    }
+    if (mask & PH_Y2) { k_mf_small<<<g, 256, 0, P.s>>>(P.G, P.in, P.st, P.ctl, PH_Y2, nullptr, 0); NEPTUNE_COUNT(1); }
+  }
+}
+
+}  // namespace neptune
+
+using namespace neptune;
+
+extern "C" int neptune_pdhg_mf_workspace_bytes(int B, int N, int F, int64_t* bytes) {
+  if (B <= 0 || N <= 0 || F <= 0 || !bytes) return NEPTUNE_E_ARG;
+  Layout L(N, F, NEPTUNE_KIND_MIN_DELAY, NEPTUNE_FLAG_STRENGTHEN);
+  if (L.cols >= (int64_t)INT32_MAX || L.rows >= (int64_t)INT32_MAX) return NEPTUNE_E_SIZE;
+  const MfGeo G = make_geo(N, F);
+  *bytes = (int64_t)mf_layout(B, G).total;
+  return 0;
+}
+
+extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double* d, const double* w,
+                                     const double* r, const double* m, const double* Mj, const double* Kj,
+                                     const neptune_pdhg_params* prm, double* x, double* y,
+                                     neptune_pdhg_result* result_d, void* workspace, int64_t workspace_bytes,
+                                     void* stream) {
+  if (B <= 0 || N <= 0 || F <= 0) return NEPTUNE_E_ARG;
+  if (kind != NEPTUNE_KIND_MIN_DELAY) return NEPTUNE_E_ARG;      // the n columns / C5 / C6 rows are not stated here
+  if (!d || !w || !r || !m || !Mj || !Kj || !prm || !x || !y || !result_d || !workspace) return NEPTUNE_E_ARG;
+  int64_t need = 0;
+  { int rc = neptune_pdhg_mf_workspace_bytes(B, N, F, &need); if (rc) return rc; }
+  if (workspace_bytes < need) return NEPTUNE_E_NOMEM;
+  if ((int64_t)B * make_geo(N, F).tiles_inst >= (int64_t)INT32_MAX) return NEPTUNE_E_SIZE;
+
+  cudaStream_t caller = (cudaStream_t)stream;
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  NEPTUNE_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  NEPTUNE_CUDA_OK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+  NEPTUNE_CUDA_OK(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
+  NEPTUNE_CUDA_OK(cudaEventRecord(ev_in, caller));
+  NEPTUNE_CUDA_OK(cudaStreamWaitEvent(s, ev_in, 0));
+  const int check_every = prm->check_every > 0 ? prm->check_every : 64;
+  const int max_iters = prm->max_iters > 0 ? prm->max_iters : 20000;
+
+  MfPlan P{};
+  P.B = B; P.G = make_geo(N, F); P.s = s;
+  P.in = MfIn{d, w, r, m, Mj, Kj};
+  const MfGeo& G = P.G;
+  const MfWs W = mf_layout(B, G);
+  char* base = (char*)workspace;
+  double* xres = (double*)(base + W.xres); double* yres = (double*)(base + W.yres);
+  double* part = (double*)(base + W.part);
+  int* d_flag = (int*)(base + W.flag);          // [0] all done, [1] skip-POST flag of the graph's first node
+  Ctl* ctl = (Ctl*)(base + W.ctl);
+  P.ctl = ctl;
+  P.st = MfSt{x, y, (double*)(base + W.xsum), (double*)(base + W.ysum), (double*)(base + W.cbar),
+              (double*)(base + W.P1), (double*)(base + W.P4), (double*)(base + W.PS), (double*)(base + W.P3),
+              (double*)(base + W.S4), (double*)(base + W.S2), (double*)(base + W.scal)};
+  switch (G.K) {
+    case 1: P.grid_iter = mf_grid<1>(false); P.grid_eval = mf_grid<1>(true); break;
+    case 2: P.grid_iter = mf_grid<2>(false); P.grid_eval = mf_grid<2>(true); break;
+    default: P.grid_iter = mf_grid<4>(false); P.grid_eval = mf_grid<4>(true); break;
+  }
+  // small vectors: one block per instance does POST + PREC + Y2 in one launch while F*N is small; larger
+  // instances spread over several blocks and take the C2 dual in a second launch
+  P.fused = G.C <= 4096;
+  P.small_blocks = P.fused ? 1 : (int)((G.C + 1023) / 1024 < 4 * kNumSMs ? (G.C + 1023) / 1024 : 4 * kNumSMs);
+
+  const size_t cb = (size_t)B * G.cols * 8, rb = (size_t)B * G.rows * 8;
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(ctl, 0, (size_t)B * sizeof(Ctl), s));
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(d_flag, 0, 8, s));
+  const int nblk = G.tiles_inst < kMfRestartBlocks ? G.tiles_inst : kMfRestartBlocks;
+  { k_mf_setup<<<dim3(nblk, B), 256, 0, s>>>(G, P.in, P.st, nblk); NEPTUNE_COUNT(1); }
+  { k_mf_setup_norms<<<(B + 127) / 128, 128, 0, s>>>(G, P.in, P.st, ctl, B, nblk); NEPTUNE_COUNT(1); }
+  { k_ctl_init<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, 0.99); NEPTUNE_COUNT(1); }
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(P.st.xsum, 0, cb, s));
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(P.st.ysum, 0, rb, s));
+  NEPTUNE_CUDA_OK(cudaMemcpyAsync(xres, x, cb, cudaMemcpyDeviceToDevice, s));
+  NEPTUNE_CUDA_OK(cudaMemcpyAsync(yres, y, rb, cudaMemcpyDeviceToDevice, s));
+  mf_launch_eval(P, 0, 1);                      // PS <- column sums of the starting yS
+  NEPTUNE_LAUNCH_OK();
+
+  // `inner` iterations = {small(POST unless first of the chunk, PREC, Y2); pass} captured once and replayed;
+  // the chunk ends with small(POST).  Step sizes, restart flags and convergence live in device memory.
+  const int inner = check_every < 32 ? check_every : 32;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  int64_t per_graph = 0;
+  {
+    int64_t c0 = 0, c1 = 0;
+    neptune_launch_count(&c0, 0);
+    NEPTUNE_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    for (int k = 0; k < inner; ++k) {
+      mf_launch_small(P, PH_POST | PH_PREC | PH_Y2, k == 0 ? d_flag + 1 : nullptr);
+      mf_launch_iter(P);
+    }
+    NEPTUNE_CUDA_OK(cudaStreamEndCapture(s, &graph));
+    NEPTUNE_CUDA_OK(cudaGraphInstantiate(&gexec, graph, 0));
+    neptune_launch_count(&c1, 0);
+    per_graph = c1 - c0;
+    NEPTUNE_COUNT(-per_graph);
+  }
+  int h_flag = 0;
+  for (int it = 0; it < max_iters && !h_flag; it += check_every) {
+    int done = 0;
+    bool first = true;
+    for (; done + inner <= check_every; done += inner) {
+      NEPTUNE_CUDA_OK(cudaMemsetAsync(d_flag + 1, first ? 1 : 0, 1, s));     // int 1 / 0 (little endian)
+      NEPTUNE_CUDA_OK(cudaGraphLaunch(gexec, s));
+      NEPTUNE_COUNT(per_graph);
+      first = false;
+    }
+    for (; done < check_every; ++done) {
+      mf_launch_small(P, (first ? 0 : PH_POST) | PH_PREC | PH_Y2, nullptr);
+      mf_launch_iter(P);
+      first = false;
+    }
+    mf_launch_small(P, PH_POST, nullptr);
+    // KKT of the current iterate and of the running average
+    for (int wch = 0; wch < 2; ++wch) {
+      mf_launch_eval(P, wch, 0);
+      { k_mf_eval_small<<<B, 256, 0, s>>>(G, P.in, P.st, ctl, wch); NEPTUNE_COUNT(1); }
+    }
+    { k_ctl_decide<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, check_every, prm->eps_abs, prm->eps_rel, max_iters,
+                                                 result_d); NEPTUNE_COUNT(1); }
+    { k_mf_apply_restart<<<dim3(kMfRestartBlocks, B), 256, 0, s>>>(G, P.in, P.st, xres, yres, ctl, part); NEPTUNE_COUNT(1); }
+    { k_mf_restart_norms<<<(B + 127) / 128, 128, 0, s>>>(B, kMfRestartBlocks, part, ctl); NEPTUNE_COUNT(1); }
+    { k_ctl_after_restart<<<(B + 127) / 128, 128, 0, s>>>(B, ctl); NEPTUNE_COUNT(1); }
+    mf_launch_eval(P, 0, 1);                    // PS of the (possibly replaced) yS for the next PREC
+    { k_all_done<<<1, 1, 0, s>>>(B, ctl, d_flag); NEPTUNE_COUNT(1); }
+    NEPTUNE_CUDA_OK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, s));
+    NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
+  }
+  cudaGraphExecDestroy(gexec);
+  cudaGraphDestroy(graph);
+  NEPTUNE_LAUNCH_OK();
+  NEPTUNE_CUDA_OK(cudaEventRecord(ev_out, s));
+  NEPTUNE_CUDA_OK(cudaStreamWaitEvent(caller, ev_out, 0));
+  NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
+  cudaEventDestroy(ev_in); cudaEventDestroy(ev_out);
+  cudaStreamDestroy(s);
+  return 0;
+}

@@ -209,6 +209,32 @@ def pdhg_solve(mdl: Model, max_iters=20000, check_every=64, eps_rel=1e-6, eps_ab
     return x, y, out
 
 
+def pdhg_mf_solve(inst: InstanceBatch, max_iters=20000, check_every=64, eps_rel=1e-6, eps_abs=1e-8,
+                  x0: Optional[torch.Tensor] = None, y0: Optional[torch.Tensor] = None, workspace=None):
+    """Matrix-free PDHG on the strengthened min-delay relaxation (`neptune_pdhg_mf_solve`): nothing is
+    assembled, every coefficient is regenerated from the instance arrays.  Returns (x[B,cols], y[B,rows],
+    results) in the canonical layout of `assemble(inst, "min_delay", flags=FLAG_STRENGTHEN)`."""
+    _require_cuda()
+    lib = _lib.load()
+    from ._lib import FLAG_STRENGTHEN
+    rows, cols, _ = model_sizes(inst.N, inst.F, 0, FLAG_STRENGTHEN)
+    dev = inst.d.device
+    x = torch.zeros((inst.B, cols), dtype=torch.float64, device=dev) if x0 is None else x0
+    y = torch.zeros((inst.B, rows), dtype=torch.float64, device=dev) if y0 is None else y0
+    need = C.c_int64()
+    check(lib.neptune_pdhg_mf_workspace_bytes(inst.B, inst.N, inst.F, C.byref(need)), "neptune_pdhg_mf_workspace_bytes")
+    if workspace is None or workspace.numel() < need.value:
+        workspace = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    res = torch.zeros(inst.B * _PDHG_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    prm = PdhgParams(max_iters, check_every, 0, 0, eps_rel, eps_abs)
+    check(lib.neptune_pdhg_mf_solve(inst.B, inst.N, inst.F, 0, _ptr(inst.d), _ptr(inst.w), _ptr(inst.r),
+                                    _ptr(inst.m), _ptr(inst.Mj), _ptr(inst.Kj), C.byref(prm), _ptr(x), _ptr(y),
+                                    _ptr(res), _ptr(workspace), workspace.numel(), _stream()),
+          "neptune_pdhg_mf_solve")
+    out = np.frombuffer(res.cpu().numpy().tobytes(), dtype=_PDHG_DTYPE)
+    return x, y, out
+
+
 def check_solution(inst: InstanceBatch, x: torch.Tensor, c: torch.Tensor, n: torch.Tensor, alpha=0.5):
     """The reference's six checkers + three scorers.  x[B,N,F,N], c[B,F,N], n[B,N] float64 on device.
     Returns (flags int32[B], scores float64[B,3]) as device tensors."""

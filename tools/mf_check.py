@@ -1,0 +1,145 @@
+"""GPU experiment: matrix-free PDHG (neptune_pdhg_mf_solve) against the CSR solver (neptune_pdhg_solve with
+ruiz_iters = 0, i.e. the same Pock-Chambolle step sizes) -- iterate equality after a fixed number of
+iterations, converged objectives, and time per iteration / achieved GB/s at C2 (batch), C3 and the per-GPU
+share of C4.  Writes gpurun_out/mf_check.json.   python tools/mf_check.py [--quick] [--profile]"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+from neptune_mip_b200 import device, synth
+from neptune_mip_b200._lib import FLAG_STRENGTHEN
+from neptune_mip_b200.core.utils import data_to_solver_input
+
+out = {"equality": [], "converged": [], "timing": []}
+
+
+def batch_of(N, F, B, cores, seed0=0):
+    datas = [data_to_solver_input(synth.random_payload(N, F, seed0 + s, node_cores=cores), 1, with_db=False)
+             for s in range(B)]
+    return device.InstanceBatch.from_datas(datas)
+
+
+def synth_batch(N, F, B, seed=0):
+    """random instance arrays made on the device (large shapes: no payload round trip)"""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    D = torch.randint(1, 50, (B, N, N), generator=g, device="cuda").to(torch.float64)
+    D = torch.floor((D + D.transpose(1, 2)) / 2)
+    D.diagonal(dim1=1, dim2=2).zero_()
+    W = torch.randint(0, 20, (B, F, N), generator=g, device="cuda").to(torch.float64)
+    cores = torch.randint(1, 5, (B, F, N), generator=g, device="cuda").to(torch.float64)
+    dest = torch.randint(1, 10, (B, F, N), generator=g, device="cuda").to(torch.float64)
+    r = cores / dest
+    load = (W.sum(dim=2, keepdim=True) * r).sum(dim=1).mean(dim=1, keepdim=True)     # mean CPU need per node
+    Kj = torch.ceil(2.5 * load).expand(B, N).contiguous()
+    return device.InstanceBatch(B=B, N=N, F=F, d=D.contiguous(), w=W, r=r, m=torch.full((B, F), 30.0, **f64),
+                                Mj=torch.full((B, N), 100.0, **f64), Kj=Kj, old=torch.ones((B, F, N), **f64),
+                                maxd=torch.full((B, F), 1000.0, **f64), cost=torch.full((B, N), 5.0, **f64),
+                                budget=300.0)
+
+
+def timed(fn):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    e1.synchronize()
+    return r, e0.elapsed_time(e1)
+
+
+def equality(N, F, B, cores, K):
+    inst = batch_of(N, F, B, cores)
+    mdl = device.assemble(inst, "min_delay", flags=FLAG_STRENGTHEN)
+    xa, ya, ra = device.pdhg_solve(mdl, max_iters=K, check_every=K, ruiz_iters=0, eps_rel=1e-12, eps_abs=1e-14)
+    xb, yb, rb = device.pdhg_mf_solve(inst, max_iters=K, check_every=K, eps_rel=1e-12, eps_abs=1e-14)
+    sx = float(xa.abs().max()) + 1e-300
+    sy = float(ya.abs().max()) + 1e-300
+    rec = dict(N=N, F=F, B=B, K=K, dx=float((xa - xb).abs().max()), dy=float((ya - yb).abs().max()), xmax=sx, ymax=sy,
+               pobj=[float(ra[0]["primal_obj"]), float(rb[0]["primal_obj"])],
+               dobj=[float(ra[0]["dual_obj"]), float(rb[0]["dual_obj"])],
+               pres=[float(ra[0]["primal_res"]), float(rb[0]["primal_res"])],
+               omega=[float(ra[0]["primal_weight"]), float(rb[0]["primal_weight"])])
+    out["equality"].append(rec)
+    print("EQ", json.dumps(rec), flush=True)
+
+
+def converged(N, F, B, cores):
+    inst = batch_of(N, F, B, cores)
+    mdl = device.assemble(inst, "min_delay", flags=FLAG_STRENGTHEN)
+    (xa, ya, ra), ta = timed(lambda: device.pdhg_solve(mdl, max_iters=40000, check_every=128, ruiz_iters=0, eps_rel=1e-6, eps_abs=1e-9))
+    (xb, yb, rb), tb = timed(lambda: device.pdhg_mf_solve(inst, max_iters=40000, check_every=128, eps_rel=1e-6, eps_abs=1e-9))
+    (xc, yc, rc), tc = timed(lambda: device.pdhg_solve(mdl, max_iters=40000, check_every=128, ruiz_iters=10, eps_rel=1e-6, eps_abs=1e-9))
+    rec = dict(N=N, F=F, B=B, csr_pc=dict(ms=ta, iters=ra["iters"].tolist(), conv=ra["converged"].tolist(), pobj=ra["primal_obj"].tolist(), dobj=ra["dual_obj"].tolist()),
+               mf=dict(ms=tb, iters=rb["iters"].tolist(), conv=rb["converged"].tolist(), pobj=rb["primal_obj"].tolist(), dobj=rb["dual_obj"].tolist()),
+               csr_ruiz=dict(ms=tc, iters=rc["iters"].tolist(), conv=rc["converged"].tolist(), pobj=rc["primal_obj"].tolist(), dobj=rc["dual_obj"].tolist()))
+    out["converged"].append(rec)
+    print("CONV", json.dumps(rec), flush=True)
+
+
+def timing(name, inst, iters, with_csr):
+    N, F, B = inst.N, inst.F, inst.B
+    X = F * N * N
+    device.pdhg_mf_solve(inst, max_iters=64, check_every=64)          # warm-up (graph instantiation, page-in)
+    (_, _, rb), tb = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14))
+    bytes_iter = B * (64 * X + 8 * N * N + 8 * (12 * F * N + 6 * N))
+    rec = dict(name=name, N=N, F=F, B=B, iters=iters, mf_ms=tb, mf_us_per_iter=1e3 * tb / iters,
+               mf_bytes_per_iter=bytes_iter, mf_gbs=bytes_iter * iters / (tb / 1e3) / 1e9)
+    if with_csr:
+        mdl = device.assemble(inst, "min_delay", flags=FLAG_STRENGTHEN)
+        device.pdhg_solve(mdl, max_iters=64, check_every=64)
+        (_, _, ra), ta = timed(lambda: device.pdhg_solve(mdl, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14))
+        csr_bytes = B * (16 * mdl.nnz + 88 * mdl.cols + 72 * mdl.rows) + 8 * mdl.nnz + 8 * (mdl.rows + mdl.cols + 2)
+        rec.update(csr_ms=ta, csr_us_per_iter=1e3 * ta / iters, csr_gbs=csr_bytes * iters / (ta / 1e3) / 1e9,
+                   speedup_per_iter=ta / tb)
+        del mdl
+    out["timing"].append(rec)
+    print("TIME", json.dumps(rec), flush=True)
+    torch.cuda.empty_cache()
+
+
+def main():
+    quick = "--quick" in sys.argv
+    profile = "--profile" in sys.argv
+    torch.cuda.set_device(0)
+    if profile:                       # under ncu: one short C2-batch run only
+        inst = synth_batch(50, 10, 256)
+        device.pdhg_mf_solve(inst, max_iters=64, check_every=64)
+        torch.cuda.synchronize()
+        return
+    for (N, F, B, cores, K) in [(8, 4, 1, 30, 64), (12, 5, 3, 25, 96), (20, 5, 2, 100, 40), (50, 10, 2, 200, 64),
+                                (33, 3, 1, 60, 64), (70, 3, 2, 60, 64), (130, 2, 1, 60, 33)]:
+        try:
+            equality(N, F, B, cores, K)
+        except Exception as e:        # keep going: every section reports on its own
+            print("EQ-FAIL", N, F, B, repr(e), flush=True)
+            out["equality"].append(dict(N=N, F=F, B=B, error=repr(e)))
+    try:
+        converged(12, 5, 4, 25)
+        if not quick:
+            converged(50, 10, 2, 200)
+    except Exception as e:
+        print("CONV-FAIL", repr(e), flush=True)
+    try:
+        timing("C2 batch 256", synth_batch(50, 10, 256), 1024, True)
+        timing("C2 batch 64", synth_batch(50, 10, 64), 1024, False)
+        if not quick:
+            timing("C3 500x50", synth_batch(500, 50, 1), 256, False)
+            timing("C4 share 2000x25", synth_batch(2000, 25, 1), 64, False)
+            timing("C5 20x5 x4096", synth_batch(20, 5, 4096), 512, False)
+    except Exception as e:
+        print("TIME-FAIL", repr(e), flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "mf_check.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    t0 = time.time()
+    main()
+    print("mf_check done in %.1f s" % (time.time() - t0))
