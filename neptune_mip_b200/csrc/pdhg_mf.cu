@@ -30,16 +30,22 @@ namespace neptune {
 
 struct MfGeo {
   int N, F, K, JT, ct, RT, rt, tiles_inst;
+  int cti;                       // column segments of the iteration kernel in use (layout of P3i)
   int64_t X, C, cols, rows, r2, r3, r4, rs;
 };
 
-static MfGeo make_geo(int N, int F) {
+static MfGeo make_geo(int N, int F, int B) {
   MfGeo G;
   G.N = N; G.F = F;
   G.K = N <= 32 ? 1 : (N <= 64 ? 2 : 4);        // columns per lane
   G.JT = 32 * G.K; G.ct = (N + G.JT - 1) / G.JT;
-  G.RT = N <= 64 ? N : 64; G.rt = (N + G.RT - 1) / G.RT;
+  // row-tile height: the tallest of 64/32/16/8 that still gives every resident block several tiles (the
+  // partial column sums cost 24 bytes per column and row tile)
+  G.RT = N <= 64 ? N : 64;
+  while (N > 64 && G.RT > 8 && (int64_t)B * F * ((N + G.RT - 1) / G.RT) < (int64_t)12 * kNumSMs) G.RT >>= 1;
+  G.rt = (N + G.RT - 1) / G.RT;
   G.tiles_inst = F * G.rt * G.ct;
+  G.cti = G.ct;
   Layout L(N, F, NEPTUNE_KIND_MIN_DELAY, NEPTUNE_FLAG_STRENGTHEN);
   G.X = L.X; G.C = L.C; G.cols = L.cols; G.rows = L.rows;
   G.r2 = L.r2; G.r3 = L.r3; G.r4 = L.r4; G.rs = L.rs;
@@ -52,7 +58,8 @@ struct MfSt {
   double *x, *y, *xsum, *ysum;   // canonical vectors [B][cols] / [B][rows]
   double *cbar;                  // [B][C]        2c+ - c of the running iteration
   double *P1, *P4, *PS;          // [B][F][rt][N] partial column sums (xbar, r*w*xbar, yS+) per row tile
-  double *P3;                    // [B][C][ct]    partial row sums of xbar per column tile
+  double *P3;                    // [B][C][ct]    partial row sums per column tile (KKT evaluation pass)
+  double *P3i;                   // [B][C][cti]   ... of xbar, written by the iteration pass
   double *S4;                    // [B][N]        1 / sum_{f,i} |w r|
   double *S2;                    // [B]           1 / sum_f |m|
   double *scal;                  // [B][tiles_inst][4] per-tile scalars of the KKT evaluation / setup
@@ -150,7 +157,7 @@ k_mf_iter(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
         }
       }
       rsum = warp_sum(rsum);
-      if (lane == 0) st.P3[((int64_t)b * G.C + (int64_t)f * N + i) * G.ct + t.jt] = rsum;
+      if (lane == 0) st.P3i[((int64_t)b * G.C + (int64_t)f * N + i) * G.cti + t.jt] = rsum;
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -169,6 +176,267 @@ k_mf_iter(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
     __syncthreads();
   }
 }
+
+// ---------------------------------------------------------------------------------------------------
+// the iteration pass, TMA version (even N): the four streams (x, yS, xsum, ysum) of a tile are contiguous in
+// memory, so they are staged in shared memory by 1-D bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP),
+// updated in place and written back by bulk stores; three stages per block, two tiles of loads in flight
+// while one is computed -- the bytes in flight no longer live in registers.
+//   super-tile = (instance, function, row tile `it` of RT rows, column segment `js` of JS columns): owns the
+//                column sums written to P1 / P4 / PS; processed as tiles of RS rows (RS*JS <= kTmaChunk)
+//   thread -> fixed column(s) of the segment, so the column constants (y1, r, r*y4, cbar) and the three column
+//             accumulators live in registers; JS <= 256: G = 256/JS row groups; else CPT columns per thread
+//   row sums of xbar: xbar goes to a shared tile, a warp per row adds it up after the barrier.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kTmaStages = 3;
+constexpr int kTmaChunk = 1024;                 // doubles per stream and stage (8 KB)
+constexpr int kTmaMaxCPT = 4;
+
+struct TmaGeo { int JS, cts, RS, G, CPT, supers_inst; };
+
+static bool tma_geo(const MfGeo& G, TmaGeo& T) {
+  const int N = G.N;
+  if (N & 1) return false;                      // 16-byte alignment of every row start needs an even N
+  int cts = (N + kTmaChunk - 1) / kTmaChunk;
+  int JS = (N + cts - 1) / cts; JS += JS & 1;   // even segment width
+  cts = (N + JS - 1) / JS;
+  T.JS = JS; T.cts = cts;
+  T.RS = cts > 1 ? 1 : kTmaChunk / N;           // full rows per tile (one row segment when the row is split)
+  if (T.RS > G.RT) T.RS = G.RT;
+  if (T.RS < 1) return false;
+  T.G = JS <= kMfThreads ? kMfThreads / JS : 1;
+  T.CPT = JS <= kMfThreads ? 1 : (JS + kMfThreads - 1) / kMfThreads;
+  if (T.CPT > kTmaMaxCPT) return false;
+  T.supers_inst = G.F * G.rt * cts;
+  return true;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MF_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MF_DONE_%=;\n"
+      "bra MF_WAIT_%=;\n"
+      "MF_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct TmaCursor { int64_t su; int tk; };       // super-tile of this block, tile inside it
+
+struct TmaTile {
+  int b, f, it, js;
+  int i0, nr, j0, jw, ntiles;                   // rows [i0, i0+nr) x columns [j0, j0+jw); tiles of the super-tile
+  int64_t off;                                  // element offset of the tile inside the function's N x N slab
+};
+
+__device__ __forceinline__ TmaTile tma_tile(const MfGeo& G, const TmaGeo& T, const TmaCursor& c) {
+  TmaTile t;
+  t.b = (int)(c.su / T.supers_inst);
+  int k = (int)(c.su - (int64_t)t.b * T.supers_inst);
+  t.js = k % T.cts; k /= T.cts;
+  t.it = k % G.rt; t.f = k / G.rt;
+  const int r0 = t.it * G.RT, r1 = min(G.N, r0 + G.RT);
+  t.ntiles = (r1 - r0 + T.RS - 1) / T.RS;
+  t.i0 = r0 + c.tk * T.RS; t.nr = min(T.RS, r1 - t.i0);
+  t.j0 = t.js * T.JS; t.jw = min(T.JS, G.N - t.j0);
+  t.off = (int64_t)t.i0 * G.N + t.j0;
+  return t;
+}
+
+// next (super-tile, tile) of this block, skipping converged instances; su >= total when exhausted
+__device__ __forceinline__ void tma_skip(const MfGeo&, const TmaGeo& T, const Ctl* __restrict__ ctl, int64_t total,
+                                         TmaCursor& c) {
+  while (c.su < total && ctl[(int)(c.su / T.supers_inst)].converged) c.su += gridDim.x;
+}
+__device__ __forceinline__ void tma_next(const MfGeo& G, const TmaGeo& T, const Ctl* __restrict__ ctl, int64_t total,
+                                         TmaCursor& c) {
+  const TmaTile t = tma_tile(G, T, c);
+  if (c.tk + 1 < t.ntiles) { c.tk += 1; return; }
+  c.tk = 0; c.su += gridDim.x;
+  tma_skip(G, T, ctl, total, c);
+}
+
+template <int CPT>
+__global__ void __launch_bounds__(kMfThreads, 2)
+k_mf_iter_tma(MfGeo G, TmaGeo T, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stage = reinterpret_cast<double*>(smem_raw);                   // [kTmaStages][4][kTmaChunk]
+  double* xb = stage + kTmaStages * 4 * kTmaChunk;                       // [kTmaChunk]
+  double* red = xb + kTmaChunk;                                          // [3][kMfThreads]
+  double* rowtab = red + 3 * kMfThreads;                                 // [2][64]  w[f,i], y3[f,i]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rowtab + 2 * 64);         // [kTmaStages]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = G.N;
+  const int64_t NN = (int64_t)N * N;
+  const int64_t total = (int64_t)B * T.supers_inst;
+
+  if (tid == 0) {
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue_load = [&](const TmaCursor& c, int n) {                     // thread 0 only
+    const TmaTile t = tma_tile(G, T, c);
+    const int s = n % kTmaStages;
+    const uint32_t bytes = (uint32_t)(t.nr * t.jw) * 8u;
+    double* dst = stage + (size_t)s * 4 * kTmaChunk;
+    const int64_t xo = (int64_t)t.b * G.cols + (int64_t)t.f * NN + t.off;
+    const int64_t yo = (int64_t)t.b * G.rows + G.rs + (int64_t)t.f * NN + t.off;
+    mbar_expect_tx(bars + s, 4u * bytes);
+    bulk_g2s(dst + 0 * kTmaChunk, st.x + xo, bytes, bars + s);
+    bulk_g2s(dst + 1 * kTmaChunk, st.y + yo, bytes, bars + s);
+    bulk_g2s(dst + 2 * kTmaChunk, st.xsum + xo, bytes, bars + s);
+    bulk_g2s(dst + 3 * kTmaChunk, st.ysum + yo, bytes, bars + s);
+  };
+
+  TmaCursor cons{(int64_t)blockIdx.x, 0};
+  tma_skip(G, T, ctl, total, cons);
+  TmaCursor prod = cons;
+  int n_prod = 0;
+  if (tid == 0) {
+    for (; n_prod < kTmaStages - 1 && prod.su < total; ++n_prod) { issue_load(prod, n_prod); tma_next(G, T, ctl, total, prod); }
+  }
+
+  // thread -> column(s)
+  const int grp = (CPT == 1) ? tid / T.JS : 0;
+  const int jl0 = (CPT == 1) ? tid - grp * T.JS : tid;
+  double y1j[CPT], rj[CPT], rr4[CPT], cb[CPT], a1[CPT], a4[CPT], aS[CPT];
+  bool act[CPT];
+  double tau = 0.0, shalf = 0.0;
+
+  for (int n = 0; cons.su < total; ++n) {
+    const TmaTile t = tma_tile(G, T, cons);
+    const int b = t.b, f = t.f;
+    const double* __restrict__ y = st.y + (int64_t)b * G.rows;
+    if (cons.tk == 0) {                                                  // new super-tile: constants, accumulators
+      tau = ctl[b].tau; shalf = 0.5 * ctl[b].sigma;
+      const double* __restrict__ r = in.r + ((int64_t)b * G.F + f) * N;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        const int jl = jl0 + c * kMfThreads;
+        act[c] = (CPT > 1 || grp < T.G) && jl < t.jw;
+        const int j = act[c] ? t.j0 + jl : 0;
+        y1j[c] = y[2 * ((int64_t)f * N + j) + 1];
+        rj[c] = __ldg(r + j);
+        rr4[c] = rj[c] * y[G.r4 + j];
+        cb[c] = st.cbar[(int64_t)b * G.C + (int64_t)f * N + j];
+        a1[c] = 0.0; a4[c] = 0.0; aS[c] = 0.0;
+      }
+      const int r0 = t.it * G.RT, nrows = min(N, r0 + G.RT) - r0;
+      if (tid < nrows) {
+        rowtab[tid] = __ldg(in.w + ((int64_t)b * G.F + f) * N + r0 + tid);
+        rowtab[64 + tid] = y[G.r3 + (int64_t)f * N + r0 + tid];
+      }
+      __syncthreads();
+    }
+    const int s = n % kTmaStages;
+    double* __restrict__ sx = stage + (size_t)s * 4 * kTmaChunk;
+    double* __restrict__ sy = sx + kTmaChunk;
+    double* __restrict__ sxs = sx + 2 * kTmaChunk;
+    double* __restrict__ sys = sx + 3 * kTmaChunk;
+    mbar_wait(bars + s, (uint32_t)((n / kTmaStages) & 1));
+
+    const double* __restrict__ d = in.d + (int64_t)b * NN;
+    const int rbase = t.i0 - t.it * G.RT;                                // row of the tile inside the super-tile
+    const int rstep = (CPT == 1) ? T.G : 1;
+    for (int ii = grp; ii < t.nr; ii += rstep) {
+      const double wfi = rowtab[rbase + ii], y3i = rowtab[64 + rbase + ii];
+      const int64_t drow = (int64_t)(t.i0 + ii) * N + t.j0;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        if (act[c]) {
+          const int jl = jl0 + c * kMfThreads;
+          const int e = ii * t.jw + jl;
+          const double xv = sx[e], sv = sy[e];
+          const double dv = __ldg(d + drow + jl);
+          const double wr = fabs(wfi * rj[c]);
+          const double g = __dmul_rn(dv, wfi) + y1j[c] + y3i + wfi * rr4[c] + sv;
+          double xn = xv - tau * g / (3.0 + wr);
+          xn = fmin(fmax(xn, 0.0), 1.0);
+          const double xbar = 2.0 * xn - xv;
+          const double sn = fmax(sv + shalf * (xbar - cb[c]), 0.0);
+          sx[e] = xn; sy[e] = sn;
+          sxs[e] += xn; sys[e] += sn;
+          xb[e] = xbar;
+          a1[c] += xbar; a4[c] += wfi * xbar; aS[c] += sn;
+        }
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_wait_read0();                                                 // the previous tile's stores have left smem
+      const uint32_t bytes = (uint32_t)(t.nr * t.jw) * 8u;
+      const int64_t xo = (int64_t)b * G.cols + (int64_t)f * NN + t.off;
+      const int64_t yo = (int64_t)b * G.rows + G.rs + (int64_t)f * NN + t.off;
+      bulk_s2g(st.x + xo, sx, bytes);
+      bulk_s2g(st.y + yo, sy, bytes);
+      bulk_s2g(st.xsum + xo, sxs, bytes);
+      bulk_s2g(st.ysum + yo, sys, bytes);
+      bulk_commit();
+      if (prod.su < total) { issue_load(prod, n_prod); ++n_prod; tma_next(G, T, ctl, total, prod); }
+    }
+    // row sums of xbar (complete over the column segment)
+    for (int ii = warp; ii < t.nr; ii += kMfWarps) {
+      double rs = 0.0;
+      for (int jl = lane; jl < t.jw; jl += 32) rs += xb[ii * t.jw + jl];
+      rs = warp_sum(rs);
+      if (lane == 0) st.P3i[((int64_t)b * G.C + (int64_t)f * N + t.i0 + ii) * G.cti + t.js] = rs;
+    }
+    if (cons.tk + 1 == t.ntiles) {                                       // super-tile complete: column sums out
+      const int64_t o = (((int64_t)b * G.F + f) * G.rt + t.it) * N + t.j0;
+      if (CPT == 1) {
+        red[tid] = a1[0]; red[kMfThreads + tid] = a4[0]; red[2 * kMfThreads + tid] = aS[0];
+        __syncthreads();
+        if (tid < t.jw) {
+          double s1 = 0.0, s4 = 0.0, sS = 0.0;
+          for (int g2 = 0; g2 < T.G; ++g2) {
+            const int k = g2 * T.JS + tid;
+            s1 += red[k]; s4 += red[kMfThreads + k]; sS += red[2 * kMfThreads + k];
+          }
+          const double rr = __ldg(in.r + ((int64_t)b * G.F + f) * N + t.j0 + tid);
+          st.P1[o + tid] = s1; st.P4[o + tid] = rr * s4; st.PS[o + tid] = sS;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          if (act[c]) {
+            const int jl = jl0 + c * kMfThreads;
+            st.P1[o + jl] = a1[c]; st.P4[o + jl] = rj[c] * a4[c]; st.PS[o + jl] = aS[c];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    tma_next(G, T, ctl, total, cons);
+  }
+  if (tid == 0) bulk_wait_all();
+}
+
+constexpr size_t kTmaSmemBytes = (size_t)(kTmaStages * 4 * kTmaChunk + kTmaChunk + 3 * kMfThreads + 2 * 64) * 8 +
+                                 kTmaStages * 8 + 64;
 
 // ---------------------------------------------------------------------------------------------------
 // KKT pieces of a candidate (which = 0: current iterate, 1: running average): the same partial sums from a
@@ -271,15 +539,28 @@ k_mf_eval(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, int whi
 // ---------------------------------------------------------------------------------------------------
 enum { PH_POST = 1, PH_PREC = 2, PH_Y2 = 4 };
 
-__global__ void __launch_bounds__(256)
+// sum of n values p[0], p[stride], p[2*stride], ... in index order, eight loads in flight at a time
+__device__ __forceinline__ double strided_sum(const double* __restrict__ p, int n, int64_t stride) {
+  double a = 0.0;
+  for (int k0 = 0; k0 < n; k0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (k0 + u < n) ? p[(int64_t)(k0 + u) * stride] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a += v[u];
+  }
+  return a;
+}
+
+__global__ void __launch_bounds__(512)
 k_mf_small(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int mask, const int* __restrict__ skip_post,
            int fused) {
   const int b = blockIdx.y;
   if (ctl[b].converged) return;
   if (skip_post && *skip_post) mask &= ~PH_POST;
-  const int N = G.N, F = G.F, rt = G.rt, ct = G.ct;
-  const int64_t C = G.C;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const int N = G.N, F = G.F, rt = G.rt, ct = G.cti;
+  const int C = (int)G.C;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   const double tau = ctl[b].tau, sigma = ctl[b].sigma;
   double* __restrict__ y = st.y + (int64_t)b * G.rows;
   double* __restrict__ ys = st.ysum + (int64_t)b * G.rows;
@@ -289,62 +570,64 @@ k_mf_small(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int mask, con
   const double* __restrict__ P1 = st.P1 + (int64_t)b * F * rt * N;
   const double* __restrict__ P4 = st.P4 + (int64_t)b * F * rt * N;
   const double* __restrict__ PS = st.PS + (int64_t)b * F * rt * N;
-  const double* __restrict__ P3 = st.P3 + (int64_t)b * C * ct;
+  const double* __restrict__ P3 = st.P3i + (int64_t)b * C * ct;
   const double* __restrict__ m = in.m + (int64_t)b * F;
+  const bool post = mask & PH_POST, prec = mask & PH_PREC;
 
-  if (mask & PH_POST) {
-    const double s1 = sigma / (double)(N + 1), s3 = sigma / (double)N;
-    for (int64_t q = tid; q < C; q += nth) {
-      const int f = (int)(q / N), j = (int)(q - (int64_t)f * N);
-      double a = 0.0;
-      for (int it = 0; it < rt; ++it) a += P1[((int64_t)f * rt + it) * N + j];
-      a -= cbar[q];
-      double v = y[2 * q + 1] + s1 * a;
-      double yn = v - s1 * fmax(v / s1, -kEps);                  // C1b: [-eps, +inf)
-      y[2 * q + 1] = yn; ys[2 * q + 1] += yn;
-      a = 0.0;
-      for (int jt = 0; jt < ct; ++jt) a += P3[q * ct + jt];
-      v = y[G.r3 + q] + s3 * a;
-      yn = v - s3;                                               // C3: [1, 1]
-      y[G.r3 + q] = yn; ys[G.r3 + q] += yn;
-    }
+  // C4 dual: every load of a thread is issued before the first use (the sums are short and latency-bound)
+  if (post) {
     const double* __restrict__ Kj = in.Kj + (int64_t)b * N;
-    for (int64_t j = tid; j < N; j += nth) {
-      double a = 0.0;
-      for (int f = 0; f < F; ++f) {
-        double pa = 0.0;
-        for (int it = 0; it < rt; ++it) pa += P4[((int64_t)f * rt + it) * N + j];
-        a += pa;
-      }
+    for (int j = tid; j < N; j += nth) {
+      const double a = strided_sum(P4 + j, F * rt, N);            // P4 already carries r[f,j]
       const double s = sigma * st.S4[(int64_t)b * N + j];
       const double v = y[G.r4 + j] + s * a;
-      const double yn = v - s * fmin(v / s, Kj[j]);              // C4: (-inf, Kj]
+      const double yn = v - s * fmin(v / s, Kj[j]);               // C4: (-inf, Kj]
       y[G.r4 + j] = yn; ys[G.r4 + j] += yn;
     }
   }
-  if (mask & PH_PREC) {
-    for (int64_t q = tid; q < C; q += nth) {
-      const int f = (int)(q / N), j = (int)(q - (int64_t)f * N);
-      double sS = 0.0;
-      for (int it = 0; it < rt; ++it) sS += PS[((int64_t)f * rt + it) * N + j];
-      const double mf = m[f];
-      const double gc = -y[2 * q + 1] + mf * y[G.r2 + j] - sS;
-      const double co = c[q];
-      double cn = co - tau * gc / (1.0 + mf + (double)N);
-      cn = fmin(fmax(cn, 0.0), 1.0);
-      cbar[q] = 2.0 * cn - co;
-      c[q] = cn; cs[q] += cn;
+  if (post || prec) {
+    const double s1 = sigma / (double)(N + 1), s3 = sigma / (double)N;
+    for (int q = tid; q < C; q += nth) {
+      const int f = q / N, j = q - f * N;
+      const int64_t po = (int64_t)f * rt * N + j;
+      double y1 = y[2 * q + 1];
+      if (post) {
+        const double a1 = strided_sum(P1 + po, rt, N) - cbar[q];
+        const double a3 = strided_sum(P3 + (int64_t)q * ct, ct, 1);
+        const double y3 = y[G.r3 + q], ys1 = ys[2 * q + 1], ys3 = ys[G.r3 + q];
+        const double v1 = y1 + s1 * a1;
+        y1 = v1 - s1 * fmax(v1 / s1, -kEps);                      // C1b: [-eps, +inf)
+        y[2 * q + 1] = y1; ys[2 * q + 1] = ys1 + y1;
+        const double y3n = y3 + s3 * a3 - s3;                     // C3: [1, 1]
+        y[G.r3 + q] = y3n; ys[G.r3 + q] = ys3 + y3n;
+      }
+      if (prec) {
+        const double sS = strided_sum(PS + po, rt, N);
+        const double mf = m[f];
+        const double gc = -y1 + mf * y[G.r2 + j] - sS;
+        const double co = c[q];
+        double cn = co - tau * gc / (1.0 + mf + (double)N);
+        cn = fmin(fmax(cn, 0.0), 1.0);
+        cbar[q] = 2.0 * cn - co;
+        c[q] = cn; cs[q] += cn;
+      }
     }
   }
   if (mask & PH_Y2) {
     if (fused) __syncthreads();
     const double* __restrict__ Mj = in.Mj + (int64_t)b * N;
     const double s = sigma * st.S2[b];
-    for (int64_t j = tid; j < N; j += nth) {
+    for (int j = tid; j < N; j += nth) {
       double a = 0.0;
-      for (int f = 0; f < F; ++f) a += m[f] * cbar[(int64_t)f * N + j];
-      const double v = y[G.r2 + j] + s * a;
-      const double yn = v - s * fmin(v / s, Mj[j]);              // C2: (-inf, Mj]
+      for (int f0 = 0; f0 < F; f0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (f0 + u < F) ? m[f0 + u] * cbar[(int64_t)(f0 + u) * N + j] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a += v[u];
+      }
+      const double vv = y[G.r2 + j] + s * a;
+      const double yn = vv - s * fmin(vv / s, Mj[j]);             // C2: (-inf, Mj]
       y[G.r2 + j] = yn; ys[G.r2 + j] += yn;
     }
   }
@@ -552,7 +835,7 @@ static inline size_t mf_align(size_t v) { return (v + 255) & ~(size_t)255; }
 constexpr int kMfRestartBlocks = 64;       // blocks per instance of k_mf_apply_restart / k_mf_setup (upper bound)
 
 struct MfWs {
-  size_t xsum, xres, ysum, yres, cbar, P1, P4, PS, P3, S4, S2, scal, part, ctl, flag, total;
+  size_t xsum, xres, ysum, yres, cbar, P1, P4, PS, P3, P3i, S4, S2, scal, part, ctl, flag, total;
 };
 
 static MfWs mf_layout(int B, const MfGeo& G) {
@@ -564,6 +847,7 @@ static MfWs mf_layout(int B, const MfGeo& G) {
   W.cbar = take((size_t)B * G.C * 8);
   W.P1 = take(pb); W.P4 = take(pb); W.PS = take(pb);
   W.P3 = take((size_t)B * G.C * G.ct * 8);
+  W.P3i = take((size_t)B * G.C * G.ct * 8);     // cti <= ct (TMA column segments are wider)
   W.S4 = take((size_t)B * G.N * 8); W.S2 = take((size_t)B * 8);
   const size_t per_inst = (size_t)(G.tiles_inst > kMfRestartBlocks ? G.tiles_inst : kMfRestartBlocks);
   W.scal = take((size_t)B * per_inst * 4 * 8);
@@ -585,9 +869,21 @@ template <int K> static int mf_grid(bool eval) {
 struct MfPlan {
   int B; MfGeo G; MfIn in; MfSt st; Ctl* ctl; cudaStream_t s;
   int grid_iter, grid_eval, small_blocks, fused;
+  int use_tma; TmaGeo T;
 };
 
 static void mf_launch_iter(const MfPlan& P) {
+  if (P.use_tma) {
+    const int64_t supers = (int64_t)P.B * P.T.supers_inst;
+    const int g = (int)(supers < 2 * kNumSMs ? supers : 2 * kNumSMs);
+    switch (P.T.CPT) {
+      case 1: k_mf_iter_tma<1><<<g, kMfThreads, kTmaSmemBytes, P.s>>>(P.G, P.T, P.in, P.st, P.ctl, P.B); break;
+      case 2: k_mf_iter_tma<2><<<g, kMfThreads, kTmaSmemBytes, P.s>>>(P.G, P.T, P.in, P.st, P.ctl, P.B); break;
+      default: k_mf_iter_tma<4><<<g, kMfThreads, kTmaSmemBytes, P.s>>>(P.G, P.T, P.in, P.st, P.ctl, P.B); break;
+    }
+    NEPTUNE_COUNT(1);
+    return;
+  }
   const int64_t total = (int64_t)P.B * P.G.tiles_inst;
   const int g = (int)(total < P.grid_iter ? total : P.grid_iter);
   switch (P.G.K) {
@@ -614,7 +910,7 @@ static void mf_launch_eval(const MfPlan& P, int which, int only_ps) {
 static void mf_launch_small(const MfPlan& P, int mask, const int* skip_post) {
   dim3 g(P.small_blocks, P.B);
   if (P.fused) {
-    k_mf_small<<<g, 256, 0, P.s>>>(P.G, P.in, P.st, P.ctl, mask, skip_post, 1); NEPTUNE_COUNT(1);
+    k_mf_small<<<g, 512, 0, P.s>>>(P.G, P.in, P.st, P.ctl, mask, skip_post, 1); NEPTUNE_COUNT(1);
   } else {
     if (mask & (PH_POST | PH_PREC)) {
       k_mf_small<<<g, 256, 0, P.s>>>(P.G, P.in, P.st, P.ctl, mask & (PH_POST | PH_PREC), skip_post, 0); NEPTUNE_COUNT(1);
@@ -631,7 +927,7 @@ extern "C" int neptune_pdhg_mf_workspace_bytes(int B, int N, int F, int64_t* byt
   if (B <= 0 || N <= 0 || F <= 0 || !bytes) return NEPTUNE_E_ARG;
   Layout L(N, F, NEPTUNE_KIND_MIN_DELAY, NEPTUNE_FLAG_STRENGTHEN);
   if (L.cols >= (int64_t)INT32_MAX || L.rows >= (int64_t)INT32_MAX) return NEPTUNE_E_SIZE;
-  const MfGeo G = make_geo(N, F);
+  const MfGeo G = make_geo(N, F, B);
   *bytes = (int64_t)mf_layout(B, G).total;
   return 0;
 }
@@ -647,7 +943,7 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
   int64_t need = 0;
   { int rc = neptune_pdhg_mf_workspace_bytes(B, N, F, &need); if (rc) return rc; }
   if (workspace_bytes < need) return NEPTUNE_E_NOMEM;
-  if ((int64_t)B * make_geo(N, F).tiles_inst >= (int64_t)INT32_MAX) return NEPTUNE_E_SIZE;
+  if ((int64_t)B * make_geo(N, F, B).tiles_inst >= (int64_t)INT32_MAX) return NEPTUNE_E_SIZE;
 
   cudaStream_t caller = (cudaStream_t)stream;
   cudaStream_t s = nullptr;
@@ -661,7 +957,7 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
   const int max_iters = prm->max_iters > 0 ? prm->max_iters : 20000;
 
   MfPlan P{};
-  P.B = B; P.G = make_geo(N, F); P.s = s;
+  P.B = B; P.G = make_geo(N, F, B); P.s = s;
   P.in = MfIn{d, w, r, m, Mj, Kj};
   const MfGeo& G = P.G;
   const MfWs W = mf_layout(B, G);
@@ -673,11 +969,27 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
   P.ctl = ctl;
   P.st = MfSt{x, y, (double*)(base + W.xsum), (double*)(base + W.ysum), (double*)(base + W.cbar),
               (double*)(base + W.P1), (double*)(base + W.P4), (double*)(base + W.PS), (double*)(base + W.P3),
+              (double*)(base + W.P3i),
               (double*)(base + W.S4), (double*)(base + W.S2), (double*)(base + W.scal)};
   switch (G.K) {
     case 1: P.grid_iter = mf_grid<1>(false); P.grid_eval = mf_grid<1>(true); break;
     case 2: P.grid_iter = mf_grid<2>(false); P.grid_eval = mf_grid<2>(true); break;
     default: P.grid_iter = mf_grid<4>(false); P.grid_eval = mf_grid<4>(true); break;
+  }
+  // TMA-staged iteration pass when every tile is 16-byte aligned (even N, aligned vectors); reduced_flags bit 0
+  // of params->reserved forces the register kernel (tests)
+  P.use_tma = 0;
+  if (!(prm->reserved & 1) && tma_geo(G, P.T) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
+    if (P.T.CPT == 3) P.T.CPT = 4;
+    cudaError_t e;
+    switch (P.T.CPT) {
+      case 1: e = cudaFuncSetAttribute(k_mf_iter_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes); break;
+      case 2: e = cudaFuncSetAttribute(k_mf_iter_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes); break;
+      default: e = cudaFuncSetAttribute(k_mf_iter_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes); break;
+    }
+    NEPTUNE_CUDA_OK(e);
+    P.use_tma = 1;
+    P.G.cti = P.T.cts;
   }
   // small vectors: one block per instance does POST + PREC + Y2 in one launch while F*N is small; larger
   // instances spread over several blocks and take the C2 dual in a second launch

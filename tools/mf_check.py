@@ -59,9 +59,12 @@ def equality(N, F, B, cores, K):
     mdl = device.assemble(inst, "min_delay", flags=FLAG_STRENGTHEN)
     xa, ya, ra = device.pdhg_solve(mdl, max_iters=K, check_every=K, ruiz_iters=0, eps_rel=1e-12, eps_abs=1e-14)
     xb, yb, rb = device.pdhg_mf_solve(inst, max_iters=K, check_every=K, eps_rel=1e-12, eps_abs=1e-14)
+    xr, yr, rr = device.pdhg_mf_solve(inst, max_iters=K, check_every=K, eps_rel=1e-12, eps_abs=1e-14, register_kernel=True)
     sx = float(xa.abs().max()) + 1e-300
     sy = float(ya.abs().max()) + 1e-300
-    rec = dict(N=N, F=F, B=B, K=K, dx=float((xa - xb).abs().max()), dy=float((ya - yb).abs().max()), xmax=sx, ymax=sy,
+    rec = dict(N=N, F=F, B=B, K=K, tma_vs_reg_dx=float((xr - xb).abs().max()), tma_vs_reg_dy=float((yr - yb).abs().max()),
+               pobj_reg=float(rr[0]["primal_obj"]), dobj_reg=float(rr[0]["dual_obj"]),
+               dx=float((xa - xb).abs().max()), dy=float((ya - yb).abs().max()), xmax=sx, ymax=sy,
                pobj=[float(ra[0]["primal_obj"]), float(rb[0]["primal_obj"])],
                dobj=[float(ra[0]["dual_obj"]), float(rb[0]["dual_obj"])],
                pres=[float(ra[0]["primal_res"]), float(rb[0]["primal_res"])],
@@ -88,9 +91,12 @@ def timing(name, inst, iters, with_csr):
     X = F * N * N
     device.pdhg_mf_solve(inst, max_iters=64, check_every=64)          # warm-up (graph instantiation, page-in)
     (_, _, rb), tb = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14))
+    device.pdhg_mf_solve(inst, max_iters=64, check_every=64, register_kernel=True)
+    (_, _, rr), tr = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14, register_kernel=True))
     bytes_iter = B * (64 * X + 8 * N * N + 8 * (12 * F * N + 6 * N))
     rec = dict(name=name, N=N, F=F, B=B, iters=iters, mf_ms=tb, mf_us_per_iter=1e3 * tb / iters,
-               mf_bytes_per_iter=bytes_iter, mf_gbs=bytes_iter * iters / (tb / 1e3) / 1e9)
+               mf_bytes_per_iter=bytes_iter, mf_gbs=bytes_iter * iters / (tb / 1e3) / 1e9,
+               reg_us_per_iter=1e3 * tr / iters, reg_gbs=bytes_iter * iters / (tr / 1e3) / 1e9)
     if with_csr:
         mdl = device.assemble(inst, "min_delay", flags=FLAG_STRENGTHEN)
         device.pdhg_solve(mdl, max_iters=64, check_every=64)
@@ -114,25 +120,37 @@ def main():
         torch.cuda.synchronize()
         return
     for (N, F, B, cores, K) in [(8, 4, 1, 30, 64), (12, 5, 3, 25, 96), (20, 5, 2, 100, 40), (50, 10, 2, 200, 64),
-                                (33, 3, 1, 60, 64), (70, 3, 2, 60, 64), (130, 2, 1, 60, 33)]:
+                                (33, 3, 1, 60, 64), (70, 3, 2, 60, 64), (130, 2, 1, 60, 33), (300, 2, 1, 60, 33)]:
         try:
             equality(N, F, B, cores, K)
         except Exception as e:        # keep going: every section reports on its own
             print("EQ-FAIL", N, F, B, repr(e), flush=True)
             out["equality"].append(dict(N=N, F=F, B=B, error=repr(e)))
-    try:
-        converged(12, 5, 4, 25)
-        if not quick:
+    for (N, F, B, K) in [(1100, 2, 1, 33), (64, 3, 5, 64), (2, 1, 1, 64)]:      # TMA vs register kernel only (split rows / edge widths)
+        try:
+            inst = synth_batch(N, F, B, seed=3)
+            xb, yb, rb = device.pdhg_mf_solve(inst, max_iters=K, check_every=K, eps_rel=1e-12, eps_abs=1e-14)
+            xr, yr, rr = device.pdhg_mf_solve(inst, max_iters=K, check_every=K, eps_rel=1e-12, eps_abs=1e-14, register_kernel=True)
+            rec = dict(N=N, F=F, B=B, K=K, tma_vs_reg_dx=float((xr - xb).abs().max()), tma_vs_reg_dy=float((yr - yb).abs().max()),
+                       ymax=float(yr.abs().max()), pobj=[float(rb[0]["primal_obj"]), float(rr[0]["primal_obj"])])
+            out["equality"].append(rec)
+            print("EQ2", json.dumps(rec), flush=True)
+        except Exception as e:
+            print("EQ2-FAIL", N, F, B, repr(e), flush=True)
+    if "--converge" in sys.argv:
+        try:
+            converged(12, 5, 4, 25)
             converged(50, 10, 2, 200)
-    except Exception as e:
-        print("CONV-FAIL", repr(e), flush=True)
+        except Exception as e:
+            print("CONV-FAIL", repr(e), flush=True)
     try:
-        timing("C2 batch 256", synth_batch(50, 10, 256), 1024, True)
+        timing("C2 batch 256", synth_batch(50, 10, 256), 1024, "--csr" in sys.argv)
         timing("C2 batch 64", synth_batch(50, 10, 64), 1024, False)
         if not quick:
             timing("C3 500x50", synth_batch(500, 50, 1), 256, False)
             timing("C4 share 2000x25", synth_batch(2000, 25, 1), 64, False)
-            timing("C5 20x5 x4096", synth_batch(20, 5, 4096), 512, False)
+            if "--c5" in sys.argv:
+                timing("C5 20x5 x4096", synth_batch(20, 5, 4096), 512, False)
     except Exception as e:
         print("TIME-FAIL", repr(e), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
