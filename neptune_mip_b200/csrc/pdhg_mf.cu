@@ -28,6 +28,8 @@
 
 namespace neptune {
 
+constexpr int kGeoSeg = 1024;          // widest column segment of the TMA pass (= kTmaChunk)
+
 struct MfGeo {
   int N, F, K, JT, ct, RT, rt, tiles_inst;
   int cti;                       // column segments of the iteration kernel in use (layout of P3i)
@@ -39,10 +41,20 @@ static MfGeo make_geo(int N, int F, int B) {
   G.N = N; G.F = F;
   G.K = N <= 32 ? 1 : (N <= 64 ? 2 : 4);        // columns per lane
   G.JT = 32 * G.K; G.ct = (N + G.JT - 1) / G.JT;
-  // row-tile height: the tallest of 64/32/16/8 that still gives every resident block several tiles (the
-  // partial column sums cost 24 bytes per column and row tile)
+  // row-tile height: the tallest of 64/32/16/8 whose tiles fill the resident blocks evenly (>= 88 % busy in the
+  // last round); the partial column sums cost 24 bytes per column and row tile, so taller is cheaper
   G.RT = N <= 64 ? N : 64;
-  while (N > 64 && G.RT > 8 && (int64_t)B * F * ((N + G.RT - 1) / G.RT) < (int64_t)12 * kNumSMs) G.RT >>= 1;
+  if (N > 64) {
+    const int64_t slots = 2 * kNumSMs;
+    int best = 64; double best_eff = 0.0;
+    for (int rt_h = 64; rt_h >= 8; rt_h >>= 1) {
+      const int64_t units = (int64_t)B * F * ((N + rt_h - 1) / rt_h) * ((N + kGeoSeg - 1) / kGeoSeg);
+      const double eff = (double)units / (double)(((units + slots - 1) / slots) * slots);
+      if (eff > best_eff + 1e-9) { best_eff = eff; best = rt_h; }
+      if (eff >= 0.88) { best = rt_h; break; }
+    }
+    G.RT = best;
+  }
   G.rt = (N + G.RT - 1) / G.RT;
   G.tiles_inst = F * G.rt * G.ct;
   G.cti = G.ct;
@@ -297,25 +309,27 @@ k_mf_iter_tma(MfGeo G, TmaGeo T, MfIn in, MfSt st, const Ctl* __restrict__ ctl, 
   }
   __syncthreads();
 
-  auto issue_load = [&](const TmaCursor& c, int n) {                     // thread 0 only
+  // the four streams are moved by lanes 0..3 of warp 0, one stream each (bulk async-groups are per thread, so
+  // the lane that stores a stream is also the one that waits for that store before the stage is reloaded)
+  const bool mover = warp == 0 && lane < 4;
+  auto stream_ptr = [&](int which, const TmaTile& t) -> double* {
+    const int64_t xo = (int64_t)t.b * G.cols + (int64_t)t.f * NN + t.off;
+    const int64_t yo = (int64_t)t.b * G.rows + G.rs + (int64_t)t.f * NN + t.off;
+    return which == 0 ? st.x + xo : (which == 1 ? st.y + yo : (which == 2 ? st.xsum + xo : st.ysum + yo));
+  };
+  auto issue_load = [&](const TmaCursor& c, int n) {                     // movers only
     const TmaTile t = tma_tile(G, T, c);
     const int s = n % kTmaStages;
     const uint32_t bytes = (uint32_t)(t.nr * t.jw) * 8u;
-    double* dst = stage + (size_t)s * 4 * kTmaChunk;
-    const int64_t xo = (int64_t)t.b * G.cols + (int64_t)t.f * NN + t.off;
-    const int64_t yo = (int64_t)t.b * G.rows + G.rs + (int64_t)t.f * NN + t.off;
-    mbar_expect_tx(bars + s, 4u * bytes);
-    bulk_g2s(dst + 0 * kTmaChunk, st.x + xo, bytes, bars + s);
-    bulk_g2s(dst + 1 * kTmaChunk, st.y + yo, bytes, bars + s);
-    bulk_g2s(dst + 2 * kTmaChunk, st.xsum + xo, bytes, bars + s);
-    bulk_g2s(dst + 3 * kTmaChunk, st.ysum + yo, bytes, bars + s);
+    if (lane == 0) mbar_expect_tx(bars + s, 4u * bytes);
+    bulk_g2s(stage + ((size_t)s * 4 + lane) * kTmaChunk, stream_ptr(lane, t), bytes, bars + s);
   };
 
   TmaCursor cons{(int64_t)blockIdx.x, 0};
   tma_skip(G, T, ctl, total, cons);
   TmaCursor prod = cons;
   int n_prod = 0;
-  if (tid == 0) {
+  if (mover) {
     for (; n_prod < kTmaStages - 1 && prod.su < total; ++n_prod) { issue_load(prod, n_prod); tma_next(G, T, ctl, total, prod); }
   }
 
@@ -361,40 +375,50 @@ k_mf_iter_tma(MfGeo G, TmaGeo T, MfIn in, MfSt st, const Ctl* __restrict__ ctl, 
     const double* __restrict__ d = in.d + (int64_t)b * NN;
     const int rbase = t.i0 - t.it * G.RT;                                // row of the tile inside the super-tile
     const int rstep = (CPT == 1) ? T.G : 1;
-    for (int ii = grp; ii < t.nr; ii += rstep) {
-      const double wfi = rowtab[rbase + ii], y3i = rowtab[64 + rbase + ii];
-      const int64_t drow = (int64_t)(t.i0 + ii) * N + t.j0;
+    constexpr int U = (CPT == 1) ? 4 : (CPT == 2 ? 2 : 1);               // rows in flight per thread
+    for (int ib = grp; ib < t.nr; ib += U * rstep) {
+      double xv[U][CPT], sv[U][CPT], dv[U][CPT], wfi[U], y3i[U];
+      bool ok[U];
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) {
-        if (act[c]) {
-          const int jl = jl0 + c * kMfThreads;
-          const int e = ii * t.jw + jl;
-          const double xv = sx[e], sv = sy[e];
-          const double dv = __ldg(d + drow + jl);
-          const double wr = fabs(wfi * rj[c]);
-          const double g = __dmul_rn(dv, wfi) + y1j[c] + y3i + wfi * rr4[c] + sv;
-          double xn = xv - tau * g / (3.0 + wr);
-          xn = fmin(fmax(xn, 0.0), 1.0);
-          const double xbar = 2.0 * xn - xv;
-          const double sn = fmax(sv + shalf * (xbar - cb[c]), 0.0);
-          sx[e] = xn; sy[e] = sn;
-          sxs[e] += xn; sys[e] += sn;
-          xb[e] = xbar;
-          a1[c] += xbar; a4[c] += wfi * xbar; aS[c] += sn;
+      for (int u = 0; u < U; ++u) {
+        const int ii = ib + u * rstep;
+        ok[u] = ii < t.nr;
+        const int ir = ok[u] ? ii : 0;
+        wfi[u] = rowtab[rbase + ir]; y3i[u] = rowtab[64 + rbase + ir];
+        const int64_t drow = (int64_t)(t.i0 + ir) * N + t.j0;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const int jl = act[c] ? jl0 + c * kMfThreads : 0;
+          const int e = ir * t.jw + jl;
+          xv[u][c] = sx[e]; sv[u][c] = sy[e];
+          dv[u][c] = __ldg(d + drow + jl);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          if (ok[u] && act[c]) {
+            const int e = (ib + u * rstep) * t.jw + jl0 + c * kMfThreads;
+            const double wr = fabs(wfi[u] * rj[c]);
+            const double g = __dmul_rn(dv[u][c], wfi[u]) + y1j[c] + y3i[u] + wfi[u] * rr4[c] + sv[u][c];
+            double xn = xv[u][c] - tau * g / (3.0 + wr);
+            xn = fmin(fmax(xn, 0.0), 1.0);
+            const double xbar = 2.0 * xn - xv[u][c];
+            const double sn = fmax(sv[u][c] + shalf * (xbar - cb[c]), 0.0);
+            sx[e] = xn; sy[e] = sn;
+            sxs[e] += xn; sys[e] += sn;
+            xb[e] = xbar;
+            a1[c] += xbar; a4[c] += wfi[u] * xbar; aS[c] += sn;
+          }
         }
       }
     }
     fence_async_smem();
     __syncthreads();
-    if (tid == 0) {
-      bulk_wait_read0();                                                 // the previous tile's stores have left smem
-      const uint32_t bytes = (uint32_t)(t.nr * t.jw) * 8u;
-      const int64_t xo = (int64_t)b * G.cols + (int64_t)f * NN + t.off;
-      const int64_t yo = (int64_t)b * G.rows + G.rs + (int64_t)f * NN + t.off;
-      bulk_s2g(st.x + xo, sx, bytes);
-      bulk_s2g(st.y + yo, sy, bytes);
-      bulk_s2g(st.xsum + xo, sxs, bytes);
-      bulk_s2g(st.ysum + yo, sys, bytes);
+    if (mover) {
+      bulk_wait_read0();                                                 // this lane's previous store has left smem
+      bulk_s2g(stream_ptr(lane, t), sx + (size_t)lane * kTmaChunk, (uint32_t)(t.nr * t.jw) * 8u);
       bulk_commit();
       if (prod.su < total) { issue_load(prod, n_prod); ++n_prod; tma_next(G, T, ctl, total, prod); }
     }
@@ -432,7 +456,7 @@ k_mf_iter_tma(MfGeo G, TmaGeo T, MfIn in, MfSt st, const Ctl* __restrict__ ctl, 
     __syncthreads();
     tma_next(G, T, ctl, total, cons);
   }
-  if (tid == 0) bulk_wait_all();
+  if (mover) bulk_wait_all();
 }
 
 constexpr size_t kTmaSmemBytes = (size_t)(kTmaStages * 4 * kTmaChunk + kTmaChunk + 3 * kMfThreads + 2 * 64) * 8 +
@@ -574,15 +598,40 @@ k_mf_small(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int mask, con
   const double* __restrict__ m = in.m + (int64_t)b * F;
   const bool post = mask & PH_POST, prec = mask & PH_PREC;
 
-  // C4 dual: every load of a thread is issued before the first use (the sums are short and latency-bound)
+  // C4 dual: every load of a thread is issued before the first use (the sums are latency-bound); long sums
+  // (large instances: F * rt partials per column) are cut into 16 slices per column and combined in order
   if (post) {
     const double* __restrict__ Kj = in.Kj + (int64_t)b * N;
-    for (int j = tid; j < N; j += nth) {
-      const double a = strided_sum(P4 + j, F * rt, N);            // P4 already carries r[f,j]
-      const double s = sigma * st.S4[(int64_t)b * N + j];
-      const double v = y[G.r4 + j] + s * a;
-      const double yn = v - s * fmin(v / s, Kj[j]);               // C4: (-inf, Kj]
-      y[G.r4 + j] = yn; ys[G.r4 + j] += yn;
+    const int K4 = F * rt;
+    if (K4 <= 64) {
+      for (int j = tid; j < N; j += nth) {
+        const double a = strided_sum(P4 + j, K4, N);              // P4 already carries r[f,j]
+        const double s = sigma * st.S4[(int64_t)b * N + j];
+        const double v = y[G.r4 + j] + s * a;
+        const double yn = v - s * fmin(v / s, Kj[j]);             // C4: (-inf, Kj]
+        y[G.r4 + j] = yn; ys[G.r4 + j] += yn;
+      }
+    } else {
+      __shared__ double slice[512];
+      const int cpb = blockDim.x / 16;
+      const int jl = threadIdx.x % cpb, sl = threadIdx.x / cpb;
+      const int L = (K4 + 15) / 16;
+      for (int jb = blockIdx.x; jb * cpb < N; jb += gridDim.x) {
+        const int j = jb * cpb + jl;
+        const int k0 = sl * L, n = min(L, K4 - k0);
+        slice[sl * cpb + jl] = (j < N && n > 0) ? strided_sum(P4 + (int64_t)k0 * N + j, n, N) : 0.0;
+        __syncthreads();
+        if (sl == 0 && j < N) {
+          double a = 0.0;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) a += slice[q * cpb + jl];
+          const double s = sigma * st.S4[(int64_t)b * N + j];
+          const double v = y[G.r4 + j] + s * a;
+          const double yn = v - s * fmin(v / s, Kj[j]);
+          y[G.r4 + j] = yn; ys[G.r4 + j] += yn;
+        }
+        __syncthreads();
+      }
     }
   }
   if (post || prec) {
