@@ -190,17 +190,21 @@ k_mf_iter(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// the iteration pass, TMA version (even N): the four streams (x, yS, xsum, ysum) of a tile are contiguous in
-// memory, so they are staged in shared memory by 1-D bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP),
-// updated in place and written back by bulk stores; three stages per block, two tiles of loads in flight
-// while one is computed -- the bytes in flight no longer live in registers.
+// the iteration pass, TMA version (even N): x and yS of a tile are contiguous in memory, so they are staged
+// in shared memory by 1-D bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP), five stages deep -- those bytes
+// in flight do not live in registers; the running sums (xsum, ysum) and d are read with ordinary loads issued
+// BEFORE the wait on the bulk copy, and all four results are stored from registers, so a stage is free again
+// as soon as the block has read it (measured on B200: staging all four streams and writing them back with
+// bulk stores is bounded by the per-SM bulk-copy rate, ~3.4 TB/s of loads chip-wide, and serialises compute
+// with the copies -- gpurun_out/mf_diag.log, profiles/r01f_*).
 //   super-tile = (instance, function, row tile `it` of RT rows, column segment `js` of JS columns): owns the
 //                column sums written to P1 / P4 / PS; processed as tiles of RS rows (RS*JS <= kTmaChunk)
 //   thread -> fixed column(s) of the segment, so the column constants (y1, r, r*y4, cbar) and the three column
-//             accumulators live in registers; JS <= 256: G = 256/JS row groups; else CPT columns per thread
+//             accumulators live in registers; JS <= 256: G = 256/JS row groups; else CPT columns per thread;
+//             four (CPT = 1) rows of a column are in flight per thread (independent dependency chains)
 //   row sums of xbar: xbar goes to a shared tile, a warp per row adds it up after the barrier.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kTmaStages = 3;
+constexpr int kTmaStages = 5;
 constexpr int kTmaChunk = 1024;                 // doubles per stream and stage (8 KB)
 constexpr int kTmaMaxCPT = 4;
 
@@ -291,10 +295,10 @@ __device__ __forceinline__ void tma_next(const MfGeo& G, const TmaGeo& T, const 
 
 template <int CPT>
 __global__ void __launch_bounds__(kMfThreads, 2)
-k_mf_iter_tma(MfGeo G, TmaGeo T, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
+k_mf_iter_tma(MfGeo G, TmaGeo T, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, int diag) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* stage = reinterpret_cast<double*>(smem_raw);                   // [kTmaStages][4][kTmaChunk]
-  double* xb = stage + kTmaStages * 4 * kTmaChunk;                       // [kTmaChunk]
+  double* stage = reinterpret_cast<double*>(smem_raw);                   // [kTmaStages][2][kTmaChunk]  x, yS
+  double* xb = stage + kTmaStages * 2 * kTmaChunk;                       // [kTmaChunk]
   double* red = xb + kTmaChunk;                                          // [3][kMfThreads]
   double* rowtab = red + 3 * kMfThreads;                                 // [2][64]  w[f,i], y3[f,i]
   uint64_t* bars = reinterpret_cast<uint64_t*>(rowtab + 2 * 64);         // [kTmaStages]
@@ -309,20 +313,17 @@ k_mf_iter_tma(MfGeo G, TmaGeo T, MfIn in, MfSt st, const Ctl* __restrict__ ctl, 
   }
   __syncthreads();
 
-  // the four streams are moved by lanes 0..3 of warp 0, one stream each (bulk async-groups are per thread, so
-  // the lane that stores a stream is also the one that waits for that store before the stage is reloaded)
-  const bool mover = warp == 0 && lane < 4;
-  auto stream_ptr = [&](int which, const TmaTile& t) -> double* {
-    const int64_t xo = (int64_t)t.b * G.cols + (int64_t)t.f * NN + t.off;
-    const int64_t yo = (int64_t)t.b * G.rows + G.rs + (int64_t)t.f * NN + t.off;
-    return which == 0 ? st.x + xo : (which == 1 ? st.y + yo : (which == 2 ? st.xsum + xo : st.ysum + yo));
-  };
+  // x and yS of a tile arrive by bulk copy (lanes 0 and 1 of warp 0 issue one stream each); the running sums
+  // and the results travel through registers (LDG / STG), so a stage is free again as soon as it has been read
+  const bool mover = warp == 0 && lane < 2;
   auto issue_load = [&](const TmaCursor& c, int n) {                     // movers only
     const TmaTile t = tma_tile(G, T, c);
     const int s = n % kTmaStages;
     const uint32_t bytes = (uint32_t)(t.nr * t.jw) * 8u;
-    if (lane == 0) mbar_expect_tx(bars + s, 4u * bytes);
-    bulk_g2s(stage + ((size_t)s * 4 + lane) * kTmaChunk, stream_ptr(lane, t), bytes, bars + s);
+    const int64_t xo = (int64_t)t.b * G.cols + (int64_t)t.f * NN + t.off;
+    const int64_t yo = (int64_t)t.b * G.rows + G.rs + (int64_t)t.f * NN + t.off;
+    if (lane == 0) mbar_expect_tx(bars + s, 2u * bytes);
+    bulk_g2s(stage + ((size_t)s * 2 + lane) * kTmaChunk, lane == 0 ? st.x + xo : st.y + yo, bytes, bars + s);
   };
 
   TmaCursor cons{(int64_t)blockIdx.x, 0};
@@ -330,12 +331,14 @@ k_mf_iter_tma(MfGeo G, TmaGeo T, MfIn in, MfSt st, const Ctl* __restrict__ ctl, 
   TmaCursor prod = cons;
   int n_prod = 0;
   if (mover) {
-    for (; n_prod < kTmaStages - 1 && prod.su < total; ++n_prod) { issue_load(prod, n_prod); tma_next(G, T, ctl, total, prod); }
+    for (; n_prod < kTmaStages && prod.su < total; ++n_prod) { issue_load(prod, n_prod); tma_next(G, T, ctl, total, prod); }
   }
 
   // thread -> column(s)
   const int grp = (CPT == 1) ? tid / T.JS : 0;
   const int jl0 = (CPT == 1) ? tid - grp * T.JS : tid;
+  const int rstep = (CPT == 1) ? T.G : 1;
+  constexpr int U = (CPT == 1) ? 4 : (CPT == 2 ? 2 : 1);                 // rows in flight per thread
   double y1j[CPT], rj[CPT], rr4[CPT], cb[CPT], a1[CPT], a4[CPT], aS[CPT];
   bool act[CPT];
   double tau = 0.0, shalf = 0.0;
@@ -366,32 +369,50 @@ k_mf_iter_tma(MfGeo G, TmaGeo T, MfIn in, MfSt st, const Ctl* __restrict__ ctl, 
       __syncthreads();
     }
     const int s = n % kTmaStages;
-    double* __restrict__ sx = stage + (size_t)s * 4 * kTmaChunk;
-    double* __restrict__ sy = sx + kTmaChunk;
-    double* __restrict__ sxs = sx + 2 * kTmaChunk;
-    double* __restrict__ sys = sx + 3 * kTmaChunk;
-    mbar_wait(bars + s, (uint32_t)((n / kTmaStages) & 1));
-
-    const double* __restrict__ d = in.d + (int64_t)b * NN;
+    const double* __restrict__ sx = stage + (size_t)s * 2 * kTmaChunk;
+    const double* __restrict__ sy = sx + kTmaChunk;
+    const int64_t xo = (int64_t)b * G.cols + (int64_t)f * NN + t.off;
+    const int64_t yo = (int64_t)b * G.rows + G.rs + (int64_t)f * NN + t.off;
+    double* __restrict__ gx = st.x + xo;
+    double* __restrict__ gs = st.y + yo;
+    double* __restrict__ gxs = st.xsum + xo;
+    double* __restrict__ gys = st.ysum + yo;
+    const double* __restrict__ d = in.d + (int64_t)b * NN + (int64_t)t.i0 * N + t.j0;
     const int rbase = t.i0 - t.it * G.RT;                                // row of the tile inside the super-tile
-    const int rstep = (CPT == 1) ? T.G : 1;
-    constexpr int U = (CPT == 1) ? 4 : (CPT == 2 ? 2 : 1);               // rows in flight per thread
-    for (int ib = grp; ib < t.nr; ib += U * rstep) {
-      double xv[U][CPT], sv[U][CPT], dv[U][CPT], wfi[U], y3i[U];
-      bool ok[U];
+    const int nr = (diag & 1) ? 0 : t.nr;
+
+    double xs[U][CPT], ysm[U][CPT], dv[U][CPT];
+    auto load_lsu = [&](int ib) {                                        // the register-path streams of one batch
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int ii = ib + u * rstep;
-        ok[u] = ii < t.nr;
-        const int ir = ok[u] ? ii : 0;
-        wfi[u] = rowtab[rbase + ir]; y3i[u] = rowtab[64 + rbase + ir];
-        const int64_t drow = (int64_t)(t.i0 + ir) * N + t.j0;
+        const int ir = ii < nr ? ii : 0;
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
           const int jl = act[c] ? jl0 + c * kMfThreads : 0;
           const int e = ir * t.jw + jl;
+          xs[u][c] = gxs[e]; ysm[u][c] = gys[e];
+          dv[u][c] = __ldg(d + (int64_t)ir * N + jl);
+        }
+      }
+    };
+    if (grp < nr) load_lsu(grp);                                         // in flight while the bulk copy lands
+    mbar_wait(bars + s, (uint32_t)((n / kTmaStages) & 1));
+
+    for (int ib = grp; ib < nr; ib += U * rstep) {
+      if (ib != grp) load_lsu(ib);
+      double xv[U][CPT], sv[U][CPT], wfi[U], y3i[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int ii = ib + u * rstep;
+        ok[u] = ii < nr;
+        const int ir = ok[u] ? ii : 0;
+        wfi[u] = rowtab[rbase + ir]; y3i[u] = rowtab[64 + rbase + ir];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const int e = ir * t.jw + (act[c] ? jl0 + c * kMfThreads : 0);
           xv[u][c] = sx[e]; sv[u][c] = sy[e];
-          dv[u][c] = __ldg(d + drow + jl);
         }
       }
 #pragma unroll
@@ -406,24 +427,18 @@ k_mf_iter_tma(MfGeo G, TmaGeo T, MfIn in, MfSt st, const Ctl* __restrict__ ctl, 
             xn = fmin(fmax(xn, 0.0), 1.0);
             const double xbar = 2.0 * xn - xv[u][c];
             const double sn = fmax(sv[u][c] + shalf * (xbar - cb[c]), 0.0);
-            sx[e] = xn; sy[e] = sn;
-            sxs[e] += xn; sys[e] += sn;
+            gx[e] = xn; gs[e] = sn;
+            gxs[e] = xs[u][c] + xn; gys[e] = ysm[u][c] + sn;
             xb[e] = xbar;
             a1[c] += xbar; a4[c] += wfi[u] * xbar; aS[c] += sn;
           }
         }
       }
     }
-    fence_async_smem();
-    __syncthreads();
-    if (mover) {
-      bulk_wait_read0();                                                 // this lane's previous store has left smem
-      bulk_s2g(stream_ptr(lane, t), sx + (size_t)lane * kTmaChunk, (uint32_t)(t.nr * t.jw) * 8u);
-      bulk_commit();
-      if (prod.su < total) { issue_load(prod, n_prod); ++n_prod; tma_next(G, T, ctl, total, prod); }
-    }
+    __syncthreads();                                                     // stage read by everybody, xbar tile complete
+    if (mover && prod.su < total) { issue_load(prod, n_prod); ++n_prod; tma_next(G, T, ctl, total, prod); }
     // row sums of xbar (complete over the column segment)
-    for (int ii = warp; ii < t.nr; ii += kMfWarps) {
+    for (int ii = warp; ii < ((diag & 2) ? 0 : t.nr); ii += kMfWarps) {
       double rs = 0.0;
       for (int jl = lane; jl < t.jw; jl += 32) rs += xb[ii * t.jw + jl];
       rs = warp_sum(rs);
@@ -456,10 +471,9 @@ k_mf_iter_tma(MfGeo G, TmaGeo T, MfIn in, MfSt st, const Ctl* __restrict__ ctl, 
     __syncthreads();
     tma_next(G, T, ctl, total, cons);
   }
-  if (mover) bulk_wait_all();
 }
 
-constexpr size_t kTmaSmemBytes = (size_t)(kTmaStages * 4 * kTmaChunk + kTmaChunk + 3 * kMfThreads + 2 * 64) * 8 +
+constexpr size_t kTmaSmemBytes = (size_t)(kTmaStages * 2 * kTmaChunk + kTmaChunk + 3 * kMfThreads + 2 * 64) * 8 +
                                  kTmaStages * 8 + 64;
 
 // ---------------------------------------------------------------------------------------------------
@@ -919,6 +933,7 @@ struct MfPlan {
   int B; MfGeo G; MfIn in; MfSt st; Ctl* ctl; cudaStream_t s;
   int grid_iter, grid_eval, small_blocks, fused;
   int use_tma; TmaGeo T;
+  int diag;                      // tools only: bits of params->reserved >> 4 switch parts of the TMA pass off
 };
 
 static void mf_launch_iter(const MfPlan& P) {
@@ -926,9 +941,9 @@ static void mf_launch_iter(const MfPlan& P) {
     const int64_t supers = (int64_t)P.B * P.T.supers_inst;
     const int g = (int)(supers < 2 * kNumSMs ? supers : 2 * kNumSMs);
     switch (P.T.CPT) {
-      case 1: k_mf_iter_tma<1><<<g, kMfThreads, kTmaSmemBytes, P.s>>>(P.G, P.T, P.in, P.st, P.ctl, P.B); break;
-      case 2: k_mf_iter_tma<2><<<g, kMfThreads, kTmaSmemBytes, P.s>>>(P.G, P.T, P.in, P.st, P.ctl, P.B); break;
-      default: k_mf_iter_tma<4><<<g, kMfThreads, kTmaSmemBytes, P.s>>>(P.G, P.T, P.in, P.st, P.ctl, P.B); break;
+      case 1: k_mf_iter_tma<1><<<g, kMfThreads, kTmaSmemBytes, P.s>>>(P.G, P.T, P.in, P.st, P.ctl, P.B, P.diag); break;
+      case 2: k_mf_iter_tma<2><<<g, kMfThreads, kTmaSmemBytes, P.s>>>(P.G, P.T, P.in, P.st, P.ctl, P.B, P.diag); break;
+      default: k_mf_iter_tma<4><<<g, kMfThreads, kTmaSmemBytes, P.s>>>(P.G, P.T, P.in, P.st, P.ctl, P.B, P.diag); break;
     }
     NEPTUNE_COUNT(1);
     return;
@@ -1028,6 +1043,7 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
   // TMA-staged iteration pass when every tile is 16-byte aligned (even N, aligned vectors); reduced_flags bit 0
   // of params->reserved forces the register kernel (tests)
   P.use_tma = 0;
+  P.diag = (prm->reserved >> 4) & 7;
   if (!(prm->reserved & 1) && tma_geo(G, P.T) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
     if (P.T.CPT == 3) P.T.CPT = 4;
     cudaError_t e;

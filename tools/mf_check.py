@@ -111,6 +111,15 @@ def timing(name, inst, iters, with_csr):
 
 
 def main():
+    if "--diag" in sys.argv:          # which part of the TMA pass costs what (results are garbage with diag != 0)
+        torch.cuda.set_device(0)
+        for name, inst, iters in (("C2 batch 256", synth_batch(50, 10, 256), 512), ("C4 share 2000x25", synth_batch(2000, 25, 1), 32)):
+            X = inst.F * inst.N * inst.N
+            for diag, what in ((0, "full"), (1, "no compute (bulk loads only)"), (2, "no row sums")):
+                device.pdhg_mf_solve(inst, max_iters=32, check_every=32, _diag=diag)
+                _, ms = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14, _diag=diag))
+                print("DIAG", name, what, "us/iter %.1f" % (1e3 * ms / iters), "GB/s (64 B per element) %.0f" % (inst.B * 64 * X * iters / ms / 1e6), flush=True)
+        return
     quick = "--quick" in sys.argv
     profile = "--profile" in sys.argv
     torch.cuda.set_device(0)
