@@ -102,8 +102,9 @@ __device__ __forceinline__ double column_total(double (*sm)[32 * K], int c) {
 // ---------------------------------------------------------------------------------------------------
 // the iteration pass
 // ---------------------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(kMfThreads, (K == 4 ? 2 : 3))
+// U rows of a warp are in flight together (independent dependency chains; U*K elements per lane)
+template <int K, int U>
+__global__ void __launch_bounds__(kMfThreads, (K * U >= 4 ? 2 : 3))
 k_mf_iter(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
   __shared__ double sm[3][kMfWarps][32 * K];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -119,11 +120,13 @@ k_mf_iter(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
     const double* __restrict__ w = in.w + ((int64_t)b * G.F + f) * N;
     const double* __restrict__ r = in.r + ((int64_t)b * G.F + f) * N;
     const double* __restrict__ y = st.y + (int64_t)b * G.rows;
+    const double* __restrict__ y3 = y + G.r3 + (int64_t)f * N;
     double* __restrict__ xp = st.x + (int64_t)b * G.cols + (int64_t)f * NN;
     double* __restrict__ xsp = st.xsum + (int64_t)b * G.cols + (int64_t)f * NN;
     double* __restrict__ sp = st.y + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
     double* __restrict__ ssp = st.ysum + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
     const double* __restrict__ cbar = st.cbar + (int64_t)b * G.C + (int64_t)f * N;
+    double* __restrict__ P3 = st.P3i + ((int64_t)b * G.C + (int64_t)f * N) * G.cti + t.jt;
 
     int jj[K]; bool vj[K];
     double y1j[K], rj[K], rr4[K], cb[K];
@@ -141,35 +144,44 @@ k_mf_iter(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
     for (int k = 0; k < K; ++k) { a1[k] = 0.0; a4[k] = 0.0; aS[k] = 0.0; }
 
     const int i0 = t.it * G.RT, i1 = min(N, i0 + G.RT);
-    for (int i = i0 + warp; i < i1; i += kMfWarps) {
-      const double wfi = __ldg(w + i), y3i = y[G.r3 + (int64_t)f * N + i];
-      const int64_t ro = (int64_t)i * N;
-      double xv[K], sv[K], xs[K], ss[K], dv[K];
+    for (int ib = i0 + warp; ib < i1; ib += U * kMfWarps) {
+      double xv[U][K], sv[U][K], xs[U][K], ss[U][K], dv[U][K], wfi[U], y3i[U];
+      int ro[U]; bool ok[U];
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        if (vj[k]) {
-          xv[k] = xp[ro + jj[k]]; sv[k] = sp[ro + jj[k]];
-          xs[k] = xsp[ro + jj[k]]; ss[k] = ssp[ro + jj[k]];
-          dv[k] = __ldg(d + ro + jj[k]);
+      for (int u = 0; u < U; ++u) {
+        const int i = ib + u * kMfWarps;
+        ok[u] = i < i1;
+        const int ir = ok[u] ? i : ib;
+        ro[u] = ir * N;
+        wfi[u] = __ldg(w + ir); y3i[u] = y3[ir];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int o = ro[u] + jj[k];
+          xv[u][k] = xp[o]; sv[u][k] = sp[o]; xs[u][k] = xsp[o]; ss[u][k] = ssp[o];
+          dv[u][k] = __ldg(d + o);
         }
       }
-      double rsum = 0.0;
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        if (vj[k]) {
-          const double wr = fabs(wfi * rj[k]);
-          const double g = __dmul_rn(dv[k], wfi) + y1j[k] + y3i + wfi * rr4[k] + sv[k];
-          double xn = xv[k] - tau * g / (3.0 + wr);
-          xn = fmin(fmax(xn, 0.0), 1.0);
-          const double xb = 2.0 * xn - xv[k];
-          const double sn = fmax(sv[k] + shalf * (xb - cb[k]), 0.0);
-          xp[ro + jj[k]] = xn; sp[ro + jj[k]] = sn;
-          xsp[ro + jj[k]] = xs[k] + xn; ssp[ro + jj[k]] = ss[k] + sn;
-          a1[k] += xb; a4[k] += wfi * xb; aS[k] += sn; rsum += xb;
+      for (int u = 0; u < U; ++u) {
+        double rsum = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (ok[u] && vj[k]) {
+            const int o = ro[u] + jj[k];
+            const double wr = fabs(wfi[u] * rj[k]);
+            const double g = __dmul_rn(dv[u][k], wfi[u]) + y1j[k] + y3i[u] + wfi[u] * rr4[k] + sv[u][k];
+            double xn = xv[u][k] - tau * g / (3.0 + wr);
+            xn = fmin(fmax(xn, 0.0), 1.0);
+            const double xb = 2.0 * xn - xv[u][k];
+            const double sn = fmax(sv[u][k] + shalf * (xb - cb[k]), 0.0);
+            xp[o] = xn; sp[o] = sn;
+            xsp[o] = xs[u][k] + xn; ssp[o] = ss[u][k] + sn;
+            a1[k] += xb; a4[k] += wfi[u] * xb; aS[k] += sn; rsum += xb;
+          }
         }
+        rsum = warp_sum(rsum);
+        if (lane == 0 && ok[u]) P3[(int64_t)(ib + u * kMfWarps) * G.cti] = rsum;
       }
-      rsum = warp_sum(rsum);
-      if (lane == 0) st.P3i[((int64_t)b * G.C + (int64_t)f * N + i) * G.cti + t.jt] = rsum;
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -921,10 +933,9 @@ static MfWs mf_layout(int B, const MfGeo& G) {
   return W;
 }
 
-template <int K> static int mf_grid(bool eval) {
+template <class Kern> static int mf_grid(Kern kern) {
   int occ = 0;
-  if (eval) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mf_eval<K>, kMfThreads, 0);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mf_iter<K>, kMfThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kMfThreads, 0);
   if (occ < 1) occ = 1;
   return kNumSMs * occ;
 }
@@ -933,10 +944,12 @@ struct MfPlan {
   int B; MfGeo G; MfIn in; MfSt st; Ctl* ctl; cudaStream_t s;
   int grid_iter, grid_eval, small_blocks, fused;
   int use_tma; TmaGeo T;
+  int rows_in_flight;            // U of k_mf_iter<K, U>
   int diag;                      // tools only: bits of params->reserved >> 4 switch parts of the TMA pass off
 };
 
 static void mf_launch_iter(const MfPlan& P) {
+  if (P.diag & 4) return;          // tools: time the small-vector kernel alone
   if (P.use_tma) {
     const int64_t supers = (int64_t)P.B * P.T.supers_inst;
     const int g = (int)(supers < 2 * kNumSMs ? supers : 2 * kNumSMs);
@@ -950,10 +963,14 @@ static void mf_launch_iter(const MfPlan& P) {
   }
   const int64_t total = (int64_t)P.B * P.G.tiles_inst;
   const int g = (int)(total < P.grid_iter ? total : P.grid_iter);
-  switch (P.G.K) {
-    case 1: k_mf_iter<1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
-    case 2: k_mf_iter<2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
-    default: k_mf_iter<4><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+  switch (P.G.K * 10 + P.rows_in_flight) {
+    case 11: k_mf_iter<1, 1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+    case 12: k_mf_iter<1, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+    case 14: k_mf_iter<1, 4><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+    case 21: k_mf_iter<2, 1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+    case 22: k_mf_iter<2, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+    case 41: k_mf_iter<4, 1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+    default: k_mf_iter<4, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
   }
   NEPTUNE_COUNT(1);
 }
@@ -1035,16 +1052,29 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
               (double*)(base + W.P1), (double*)(base + W.P4), (double*)(base + W.PS), (double*)(base + W.P3),
               (double*)(base + W.P3i),
               (double*)(base + W.S4), (double*)(base + W.S2), (double*)(base + W.scal)};
-  switch (G.K) {
-    case 1: P.grid_iter = mf_grid<1>(false); P.grid_eval = mf_grid<1>(true); break;
-    case 2: P.grid_iter = mf_grid<2>(false); P.grid_eval = mf_grid<2>(true); break;
-    default: P.grid_iter = mf_grid<4>(false); P.grid_eval = mf_grid<4>(true); break;
+  // rows in flight per warp of the register pass: reserved bits 8..10 override (tools), default by K
+  P.rows_in_flight = (prm->reserved >> 8) & 7;
+  if (P.rows_in_flight != 1 && P.rows_in_flight != 2 && !(P.rows_in_flight == 4 && G.K == 1))
+    P.rows_in_flight = G.K == 4 ? 1 : 2;
+  switch (G.K * 10 + P.rows_in_flight) {
+    case 11: P.grid_iter = mf_grid(k_mf_iter<1, 1>); break;
+    case 12: P.grid_iter = mf_grid(k_mf_iter<1, 2>); break;
+    case 14: P.grid_iter = mf_grid(k_mf_iter<1, 4>); break;
+    case 21: P.grid_iter = mf_grid(k_mf_iter<2, 1>); break;
+    case 22: P.grid_iter = mf_grid(k_mf_iter<2, 2>); break;
+    case 41: P.grid_iter = mf_grid(k_mf_iter<4, 1>); break;
+    default: P.grid_iter = mf_grid(k_mf_iter<4, 2>); break;
   }
-  // TMA-staged iteration pass when every tile is 16-byte aligned (even N, aligned vectors); reduced_flags bit 0
-  // of params->reserved forces the register kernel (tests)
+  switch (G.K) {
+    case 1: P.grid_eval = mf_grid(k_mf_eval<1>); break;
+    case 2: P.grid_eval = mf_grid(k_mf_eval<2>); break;
+    default: P.grid_eval = mf_grid(k_mf_eval<4>); break;
+  }
+  // bulk-copy-staged iteration pass: opt-in (bit 0 of params->reserved) where every tile is 16-byte aligned
+  // (even N, aligned vectors); measured slower than the register pass on B200 at every BASELINE shape
   P.use_tma = 0;
   P.diag = (prm->reserved >> 4) & 7;
-  if (!(prm->reserved & 1) && tma_geo(G, P.T) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
+  if ((prm->reserved & 1) && tma_geo(G, P.T) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
     if (P.T.CPT == 3) P.T.CPT = 4;
     cudaError_t e;
     switch (P.T.CPT) {

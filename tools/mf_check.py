@@ -59,7 +59,7 @@ def equality(N, F, B, cores, K):
     mdl = device.assemble(inst, "min_delay", flags=FLAG_STRENGTHEN)
     xa, ya, ra = device.pdhg_solve(mdl, max_iters=K, check_every=K, ruiz_iters=0, eps_rel=1e-12, eps_abs=1e-14)
     xb, yb, rb = device.pdhg_mf_solve(inst, max_iters=K, check_every=K, eps_rel=1e-12, eps_abs=1e-14)
-    xr, yr, rr = device.pdhg_mf_solve(inst, max_iters=K, check_every=K, eps_rel=1e-12, eps_abs=1e-14, register_kernel=True)
+    xr, yr, rr = device.pdhg_mf_solve(inst, max_iters=K, check_every=K, eps_rel=1e-12, eps_abs=1e-14, bulk_copy_kernel=True)
     sx = float(xa.abs().max()) + 1e-300
     sy = float(ya.abs().max()) + 1e-300
     rec = dict(N=N, F=F, B=B, K=K, tma_vs_reg_dx=float((xr - xb).abs().max()), tma_vs_reg_dy=float((yr - yb).abs().max()),
@@ -91,8 +91,8 @@ def timing(name, inst, iters, with_csr):
     X = F * N * N
     device.pdhg_mf_solve(inst, max_iters=64, check_every=64)          # warm-up (graph instantiation, page-in)
     (_, _, rb), tb = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14))
-    device.pdhg_mf_solve(inst, max_iters=64, check_every=64, register_kernel=True)
-    (_, _, rr), tr = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14, register_kernel=True))
+    device.pdhg_mf_solve(inst, max_iters=64, check_every=64, bulk_copy_kernel=True)
+    (_, _, rr), tr = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14, bulk_copy_kernel=True))
     bytes_iter = B * (64 * X + 8 * N * N + 8 * (12 * F * N + 6 * N))
     rec = dict(name=name, N=N, F=F, B=B, iters=iters, mf_ms=tb, mf_us_per_iter=1e3 * tb / iters,
                mf_bytes_per_iter=bytes_iter, mf_gbs=bytes_iter * iters / (tb / 1e3) / 1e9,
@@ -111,6 +111,23 @@ def timing(name, inst, iters, with_csr):
 
 
 def main():
+    if "--variants" in sys.argv:      # register pass: rows in flight per warp; the small-vector kernel alone
+        torch.cuda.set_device(0)
+        for name, inst, iters in (("C2 batch 256", synth_batch(50, 10, 256), 512), ("C3 500x50", synth_batch(500, 50, 1), 128),
+                                  ("C4 share 2000x25", synth_batch(2000, 25, 1), 32), ("C5 20x5 x4096", synth_batch(20, 5, 4096), 256)):
+            X = inst.F * inst.N * inst.N
+            ref = None
+            for u in ((1, 2, 4) if inst.N <= 32 else (1, 2)):
+                device.pdhg_mf_solve(inst, max_iters=32, check_every=32, rows_in_flight=u)
+                (xu, yu, _), ms = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14, rows_in_flight=u))
+                if ref is None:
+                    ref = (xu, yu)
+                print("VAR", name, "rows in flight", u, "us/iter %.1f" % (1e3 * ms / iters), "GB/s %.0f" % (inst.B * 64 * X * iters / ms / 1e6),
+                      "max |dx| vs U=1 %.1e" % float((xu - ref[0]).abs().max()), flush=True)
+            device.pdhg_mf_solve(inst, max_iters=32, check_every=32, _diag=4)
+            _, ms = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14, _diag=4))
+            print("VAR", name, "small-vector kernel alone us/iter %.1f" % (1e3 * ms / iters), flush=True)
+        return
     if "--diag" in sys.argv:          # which part of the TMA pass costs what (results are garbage with diag != 0)
         torch.cuda.set_device(0)
         for name, inst, iters in (("C2 batch 256", synth_batch(50, 10, 256), 512), ("C4 share 2000x25", synth_batch(2000, 25, 1), 32)):
@@ -139,7 +156,7 @@ def main():
         try:
             inst = synth_batch(N, F, B, seed=3)
             xb, yb, rb = device.pdhg_mf_solve(inst, max_iters=K, check_every=K, eps_rel=1e-12, eps_abs=1e-14)
-            xr, yr, rr = device.pdhg_mf_solve(inst, max_iters=K, check_every=K, eps_rel=1e-12, eps_abs=1e-14, register_kernel=True)
+            xr, yr, rr = device.pdhg_mf_solve(inst, max_iters=K, check_every=K, eps_rel=1e-12, eps_abs=1e-14, bulk_copy_kernel=True)
             rec = dict(N=N, F=F, B=B, K=K, tma_vs_reg_dx=float((xr - xb).abs().max()), tma_vs_reg_dy=float((yr - yb).abs().max()),
                        ymax=float(yr.abs().max()), pobj=[float(rb[0]["primal_obj"]), float(rr[0]["primal_obj"])])
             out["equality"].append(rec)
