@@ -2,8 +2,9 @@
 """bench.py -- placement instances/sec on BASELINE.json's config 2 (50 nodes x 10 functions, min-delay).
 
 A step = one pass of the whole hot path over one batch of B synthetic C2 instances:
-model assembly (a) -> PDHG on the strengthened LP relaxation (b) -> EFTTC seeds (d) -> batched local
-search (c2) -> exact routing + the reference's checkers/scorers (c1).  `value` is instances/s with the
+PDHG on the strengthened LP relaxation (b; matrix-free for the min-delay model: the coefficients of (a)'s
+matrix are regenerated inside the iteration kernels, nothing is assembled) -> EFTTC seeds (d) -> batched
+local search (c2) -> exact routing + the reference's checkers/scorers (c1).  `value` is instances/s with the
 inputs already in HBM; `e2e` repeats the measurement from pinned HOST buffers through the batched
 plugin call, with the H2D copy of every input and the D2H read of placements, routing, flags and
 scores inside the timed region.  `--impl reference` times the reference's CPU path (oracle port:
@@ -182,13 +183,14 @@ def run_ours(args):
         return float(t.item()), outs, int(cnt.value)
 
     # ---- device-resident throughput ("value") + live roofline of the PDHG kernels --------------------
-    pd = {"ms": 0.0, "iters": 0, "dims": (0, 0, 0)}
+    pd = {"ms": 0.0, "iters": 0, "dims": (0, 0, 0), "bytes": 0, "path": ""}
 
     def step_resident():
         res = solve_batch(inst, prm, time_pdhg=True)
         pd["ms"] += res.pdhg_ms
         pd["iters"] += res.pdhg_iters
         pd["dims"] = res.model_dims
+        pd["bytes"], pd["path"] = res.pdhg_bytes_per_iter, res.pdhg_path
         return res
 
     sampler = ClockSampler(local)
@@ -243,25 +245,36 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     rows, cols, nnz = pd["dims"]
-    bytes_iter = B * (8 * nnz * 2 + 88 * cols + 72 * rows) + 8 * nnz + 8 * (rows + cols + 2)   # pattern stored once
+    X = N_FUNCS * N_NODES * N_NODES
+    # algorithmic bytes of one PDHG iteration of the batch: matrix-free = the x-shaped
+    # streams x, yS, xsum, ysum read and written once (64 B per x column) + the F*N-sized vectors + d
+    bytes_iter = pd["bytes"]
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01b_pdhg_traffic.json")
-    if os.path.exists(tpath):          # dram__bytes_read+write of one iteration from the ncu --set full capture (B = 64)
+    tpath = os.path.join(ROOT, "profiles", "r01f_pdhg_mf_traffic.json")
+    if pd["path"] == "matrix-free" and os.path.exists(tpath):
+        # dram__bytes_read+write of one iteration (k_mf_iter + k_mf_small) from the ncu --set full capture (B = 256)
         traffic = json.load(open(tpath))["per_instance_dram_bytes"] * B
     roof = None
     if pd["iters"]:
         ach = bytes_iter * pd["iters"] / (pd["ms"] / 1e3) / 1e9
+        kernel = ("PDHG iteration (matrix-free) = k_mf_iter (one streaming pass over x, yS and their running sums) + "
+                  "k_mf_small (F*N-sized vectors)" if pd["path"] == "matrix-free" else
+                  "PDHG iteration = k_spmv_short/k_spmv_tasks<PrimalUpdate> over A^T + k_spmv_short/k_spmv_tasks<DualUpdate> over A")
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "kernel": "PDHG iteration = k_spmv_short/k_spmv_tasks<PrimalUpdate> over A^T + k_spmv_short/k_spmv_tasks<DualUpdate> over A",
-                "bytes_per_iteration": bytes_iter, "iterations_timed": pd["iters"], "pdhg_ms": pd["ms"],
-                "pdhg_share_of_step": pd["ms"] / ms_total, "peak_source": peak_src}
+                "kernel": kernel, "bytes_per_iteration": bytes_iter, "iterations_timed": pd["iters"], "pdhg_ms": pd["ms"],
+                "us_per_iteration": 1e3 * pd["ms"] / pd["iters"], "pdhg_share_of_step": pd["ms"] / ms_total,
+                "peak_source": peak_src,
+                "note": "one iteration of the CSR solver on the same model moved %d bytes (%.1fx)" %
+                        (B * (16 * nnz + 88 * cols + 72 * rows), B * (16 * nnz + 88 * cols + 72 * rows) / max(bytes_iter, 1))}
 
     line = {"metric": "placement instances/sec", "value": value, "unit": "instances/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "lp_iters": args.lp_iters, "ls_chains": args.chains,
-                       "ls_sweeps": args.sweeps, "l2": "batch working set (CSR values of B instances) exceeds L2"
-                       if B * nnz * 16 > 126e6 else "working set smaller than L2: flush not applicable, see DESIGN.md"},
+                       "ls_sweeps": args.sweeps, "lp_path": pd["path"],
+                       "l2": "PDHG working set of the batch (x, yS and their running sums: %d MB) exceeds the 126 MB L2"
+                             % (B * 32 * X // 1000000) if B * 32 * X > 126e6 else
+                             "working set smaller than L2: flush not applicable, see DESIGN.md"},
             "e2e": {"value": e2e_value, "unit": "instances/s", "h2d_bytes_per_step": inst.h2d_bytes(),
                     "d2h_bytes_per_step": d2h.get("bytes", 0), "ms_per_step": ms_e2e},
             "gpu_launches": launches, "clocks": clocks, "quality": quality}

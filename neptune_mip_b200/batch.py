@@ -1,5 +1,5 @@
-"""Batched solve path: B same-shaped instances through assembly -> PDHG -> EFTTC -> local search ->
-exact check in one go (what bench.py times, and what a sweep like BASELINE.json's config 5 calls)."""
+"""Batched solve path: B same-shaped instances through the LP relaxation (PDHG: matrix-free for the min-delay
+model, assembly + CSR otherwise) -> EFTTC -> local search -> exact check in one go (what bench.py times, and what a sweep like BASELINE.json's config 5 calls)."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -34,27 +34,45 @@ class BatchResult:
     pdhg_ms: float = 0.0          # device time of the PDHG call (CUDA events on the launch stream)
     pdhg_iters: int = 0
     model_dims: tuple = (0, 0, 0)
+    pdhg_bytes_per_iter: int = 0  # algorithmic bytes one PDHG iteration of the whole batch moves
+    pdhg_path: str = ""           # "matrix-free" | "csr"
 
 
 def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = False) -> BatchResult:
     kind = prm.kind
     lp_res, guide, pdhg_ms, iters, dims = None, None, 0.0, 0, (0, 0, 0)
+    bytes_iter, path = 0, ""
     if prm.lp_iters > 0:
-        lp = device.assemble(inst, kind, prm.alpha, flags=FLAG_STRENGTHEN)
-        dims = (lp.rows, lp.cols, lp.nnz)
+        N, F, B = inst.N, inst.F, inst.B
+        X = F * N * N
         if time_pdhg:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        xs, ys, lp_res = device.pdhg_solve(lp, max_iters=prm.lp_iters, check_every=prm.lp_check_every,
-                                           eps_rel=1e-6, eps_abs=1e-9)
+        if KINDS.get(kind, kind) == 0:
+            # min-delay: the relaxation is solved matrix-free (nothing is assembled; every coefficient of the
+            # strengthened model is regenerated from d, w, r, m inside the iteration kernels)
+            rows, cols, nnz = device.model_sizes(N, F, 0, FLAG_STRENGTHEN)
+            if time_pdhg:
+                e0.record()
+            xs, ys, lp_res = device.pdhg_mf_solve(inst, max_iters=prm.lp_iters, check_every=prm.lp_check_every,
+                                                  eps_rel=1e-6, eps_abs=1e-9)
+            bytes_iter, path = B * (64 * X + 112 * F * N + 8 * N * N), "matrix-free"
+        else:
+            lp = device.assemble(inst, kind, prm.alpha, flags=FLAG_STRENGTHEN)
+            rows, cols, nnz = lp.rows, lp.cols, lp.nnz
+            if time_pdhg:
+                e0.record()
+            xs, ys, lp_res = device.pdhg_solve(lp, max_iters=prm.lp_iters, check_every=prm.lp_check_every,
+                                               eps_rel=1e-6, eps_abs=1e-9)
+            bytes_iter, path = B * (16 * nnz + 88 * cols + 72 * rows) + 8 * nnz + 8 * (rows + cols + 2), "csr"
+            del lp
         if time_pdhg:
             e1.record()
             e1.synchronize()
             pdhg_ms = e0.elapsed_time(e1)
+        dims = (rows, cols, nnz)
         iters = int(lp_res["iters"].max())
-        X = inst.F * inst.N * inst.N
-        guide = xs[:, X:X + inst.F * inst.N].contiguous()
-        del lp, xs, ys
+        guide = xs[:, X:X + F * N].contiguous()
+        del xs, ys
     seeds = torch.stack([device.efttc(inst, k, prm.alpha)[0] for k in ("min_delay", "min_util", "min_delay_util")],
                         dim=1).contiguous()
     best_c, best_obj, _ = device.local_search(inst, kind, seeds, prm.alpha, prm.chains, prm.sweeps,
@@ -79,4 +97,4 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
                 bad = flags != OK_ALL
             if not bool(bad.any()):
                 break
-    return BatchResult(best_c, x, n, flags, scores, lp_res, pdhg_ms, iters, dims)
+    return BatchResult(best_c, x, n, flags, scores, lp_res, pdhg_ms, iters, dims, bytes_iter, path)

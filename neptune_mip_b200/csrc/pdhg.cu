@@ -298,7 +298,9 @@ struct DualUpdate {          // per row, after a = (A xbar)[row]
     const double s = ctl[b].sigma * p.sc;
     const double v = p.yo + s * a;
     const double z = fmin(fmax(v / s, p.l), p.h);
-    const double yn = v - s * z;
+    // a free row keeps a zero multiplier exactly: v - s*(v/s) leaves rounding noise that the 1e6 coefficients of
+    // the freed C1a rows amplify to ~1e-6 relative in the iterates (seen against the matrix-free solver)
+    const double yn = (isinf(p.l) && isinf(p.h)) ? 0.0 : v - s * z;
     y[k] = yn;
     ysum[k] = p.s + yn;
   }
@@ -783,7 +785,7 @@ struct DualStep {            // dual update, except rows in [d0,d1) u [d2,d3): t
     const int64_t k = (int64_t)b * rows + r;
     const double s = sigma * p.sc;
     const double v = p.yo + s * a;
-    const double yn = v - s * fmin(fmax(v / s, p.l), p.h);
+    const double yn = (isinf(p.l) && isinf(p.h)) ? 0.0 : v - s * fmin(fmax(v / s, p.l), p.h);   // free row: exactly 0
     y[k] = yn; ysum[k] = p.s + yn;
   }
   __device__ void finalize(int) const {}

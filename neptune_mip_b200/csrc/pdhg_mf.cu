@@ -74,6 +74,7 @@ struct MfSt {
   double *P3i;                   // [B][C][cti]   ... of xbar, written by the iteration pass
   double *S4;                    // [B][N]        1 / sum_{f,i} |w r|
   double *S2;                    // [B]           1 / sum_f |m|
+  double *wsum;                  // [B][F]        sum_i |w[f,i]|
   double *scal;                  // [B][tiles_inst][4] per-tile scalars of the KKT evaluation / setup
 };
 
@@ -732,13 +733,12 @@ k_mf_eval_small(MfGeo G, MfIn in, MfSt st, Ctl* __restrict__ ctl, int which) {
   for (int64_t q = threadIdx.x; q < C; q += blockDim.x) {
     const int f = (int)(q / N), j = (int)(q - (int64_t)f * N);
     const double y1 = yv[2 * q + 1] * sc, cq = cv[q] * sc;
-    double a = 0.0, sS = 0.0;
-    for (int it = 0; it < rt; ++it) { a += P1[((int64_t)f * rt + it) * N + j]; sS += PS[((int64_t)f * rt + it) * N + j]; }
+    double a = strided_sum(P1 + (int64_t)f * rt * N + j, rt, N);
+    const double sS = strided_sum(PS + (int64_t)f * rt * N + j, rt, N);
     double viol = fmin(a - cq + kEps, 0.0);
     pres2 += viol * viol;
     if (y1 > 0.0) dres2 += y1 * y1; else dobj += kEps * y1;
-    a = 0.0;
-    for (int jt = 0; jt < ct; ++jt) a += P3[q * ct + jt];
+    a = strided_sum(P3 + q * ct, ct, 1);
     viol = a - 1.0;
     pres2 += viol * viol;
     dobj -= yv[G.r3 + q] * sc;
@@ -746,13 +746,9 @@ k_mf_eval_small(MfGeo G, MfIn in, MfSt st, Ctl* __restrict__ ctl, int which) {
     dobj += fmin(rcc, 0.0);                                       // c in [0, 1]
   }
   for (int64_t j = threadIdx.x; j < N; j += blockDim.x) {
-    double a2 = 0.0, a4 = 0.0;
-    for (int f = 0; f < F; ++f) {
-      a2 += m[f] * cv[(int64_t)f * N + j] * sc;
-      double pa = 0.0;
-      for (int it = 0; it < rt; ++it) pa += P4[((int64_t)f * rt + it) * N + j];
-      a4 += pa;
-    }
+    double a2 = 0.0;
+    for (int f = 0; f < F; ++f) a2 += m[f] * cv[(int64_t)f * N + j] * sc;
+    const double a4 = strided_sum(P4 + j, F * rt, N);
     double viol = fmax(a2 - Mj[j], 0.0);
     pres2 += viol * viol;
     viol = fmax(a4 - Kj[j], 0.0);
@@ -777,6 +773,17 @@ k_mf_eval_small(MfGeo G, MfIn in, MfSt st, Ctl* __restrict__ ctl, int which) {
 // setup: step-size vectors S4, S2, the norms behind omega0 and the tolerances (same definitions as k_norms
 // of pdhg.cu), multipliers of the free C1a rows zeroed.
 // ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mf_wsum(int N, int64_t n_rows, const double* __restrict__ w,
+                                                 double* __restrict__ wsum) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // warp per (instance, function)
+  if (row >= n_rows) return;
+  double s = 0.0;
+  for (int i = lane; i < N; i += 32) s += fabs(w[row * N + i]);
+  s = warp_sum(s);
+  if (lane == 0) wsum[row] = s;
+}
+
 __global__ void __launch_bounds__(256) k_mf_setup(MfGeo G, MfIn in, MfSt st, int nblk) {
   const int b = blockIdx.y;
   __shared__ double red[32];
@@ -786,12 +793,9 @@ __global__ void __launch_bounds__(256) k_mf_setup(MfGeo G, MfIn in, MfSt st, int
   const double* __restrict__ w = in.w + (int64_t)b * F * N;
   const double* __restrict__ r = in.r + (int64_t)b * F * N;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t j = tid; j < N; j += nth) {
+  for (int64_t j = tid; j < N; j += nth) {                       // sum_{f,i} |w[f,i] r[f,j]| = sum_f |r[f,j]| * sum_i |w[f,i]|
     double s = 0.0;
-    for (int f = 0; f < F; ++f) {
-      const double rfj = r[(int64_t)f * N + j];
-      for (int i = 0; i < N; ++i) s += fabs(__dmul_rn(w[(int64_t)f * N + i], rfj));
-    }
+    for (int f = 0; f < F; ++f) s += fabs(r[(int64_t)f * N + j]) * st.wsum[(int64_t)b * F + f];
     st.S4[(int64_t)b * N + j] = s > 0.0 ? 1.0 / s : 1.0;
   }
   if (tid == 0) {
@@ -910,7 +914,7 @@ static inline size_t mf_align(size_t v) { return (v + 255) & ~(size_t)255; }
 constexpr int kMfRestartBlocks = 64;       // blocks per instance of k_mf_apply_restart / k_mf_setup (upper bound)
 
 struct MfWs {
-  size_t xsum, xres, ysum, yres, cbar, P1, P4, PS, P3, P3i, S4, S2, scal, part, ctl, flag, total;
+  size_t xsum, xres, ysum, yres, cbar, P1, P4, PS, P3, P3i, S4, S2, wsum, scal, part, ctl, flag, total;
 };
 
 static MfWs mf_layout(int B, const MfGeo& G) {
@@ -923,7 +927,7 @@ static MfWs mf_layout(int B, const MfGeo& G) {
   W.P1 = take(pb); W.P4 = take(pb); W.PS = take(pb);
   W.P3 = take((size_t)B * G.C * G.ct * 8);
   W.P3i = take((size_t)B * G.C * G.ct * 8);     // cti <= ct (TMA column segments are wider)
-  W.S4 = take((size_t)B * G.N * 8); W.S2 = take((size_t)B * 8);
+  W.S4 = take((size_t)B * G.N * 8); W.S2 = take((size_t)B * 8); W.wsum = take((size_t)B * G.F * 8);
   const size_t per_inst = (size_t)(G.tiles_inst > kMfRestartBlocks ? G.tiles_inst : kMfRestartBlocks);
   W.scal = take((size_t)B * per_inst * 4 * 8);
   W.part = take((size_t)B * kMfRestartBlocks * 2 * 8);
@@ -991,7 +995,8 @@ static void mf_launch_eval(const MfPlan& P, int which, int only_ps) {
 static void mf_launch_small(const MfPlan& P, int mask, const int* skip_post) {
   dim3 g(P.small_blocks, P.B);
   if (P.fused) {
-    k_mf_small<<<g, 512, 0, P.s>>>(P.G, P.in, P.st, P.ctl, mask, skip_post, 1); NEPTUNE_COUNT(1);
+    const int threads = P.G.C >= 512 ? 512 : (P.G.C <= 64 ? 64 : (int)((P.G.C + 31) / 32) * 32);
+    k_mf_small<<<g, threads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, mask, skip_post, 1); NEPTUNE_COUNT(1);
   } else {
     if (mask & (PH_POST | PH_PREC)) {
       k_mf_small<<<g, 256, 0, P.s>>>(P.G, P.in, P.st, P.ctl, mask & (PH_POST | PH_PREC), skip_post, 0); NEPTUNE_COUNT(1);
@@ -1051,7 +1056,7 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
   P.st = MfSt{x, y, (double*)(base + W.xsum), (double*)(base + W.ysum), (double*)(base + W.cbar),
               (double*)(base + W.P1), (double*)(base + W.P4), (double*)(base + W.PS), (double*)(base + W.P3),
               (double*)(base + W.P3i),
-              (double*)(base + W.S4), (double*)(base + W.S2), (double*)(base + W.scal)};
+              (double*)(base + W.S4), (double*)(base + W.S2), (double*)(base + W.wsum), (double*)(base + W.scal)};
   // rows in flight per warp of the register pass: reserved bits 8..10 override (tools), default by K
   P.rows_in_flight = (prm->reserved >> 8) & 7;
   if (P.rows_in_flight != 1 && P.rows_in_flight != 2 && !(P.rows_in_flight == 4 && G.K == 1))
@@ -1095,6 +1100,7 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
   NEPTUNE_CUDA_OK(cudaMemsetAsync(ctl, 0, (size_t)B * sizeof(Ctl), s));
   NEPTUNE_CUDA_OK(cudaMemsetAsync(d_flag, 0, 8, s));
   const int nblk = G.tiles_inst < kMfRestartBlocks ? G.tiles_inst : kMfRestartBlocks;
+  { k_mf_wsum<<<(int)(((int64_t)B * F * 32 + 255) / 256), 256, 0, s>>>(N, (int64_t)B * F, w, P.st.wsum); NEPTUNE_COUNT(1); }
   { k_mf_setup<<<dim3(nblk, B), 256, 0, s>>>(G, P.in, P.st, nblk); NEPTUNE_COUNT(1); }
   { k_mf_setup_norms<<<(B + 127) / 128, 128, 0, s>>>(G, P.in, P.st, ctl, B, nblk); NEPTUNE_COUNT(1); }
   { k_ctl_init<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, 0.99); NEPTUNE_COUNT(1); }

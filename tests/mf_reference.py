@@ -1,0 +1,250 @@
+"""TEST INFRASTRUCTURE -- numpy reference of the MATRIX-FREE PDHG iteration of csrc/pdhg_mf.cu.
+
+The constraint matrix of the strengthened min-delay placement model (reference rows
+`core/solvers/neptune/utils/constraints_step1.py:5-65`, objective `objectives.py:4-11`, plus the valid rows
+x[i,f,j] <= c[f,j]) is a closed formula of (N, F, w, r, m), so one PDHG iteration can be written as one pass
+over the x-shaped arrays plus O(F*N) work on the small vectors.  This module states
+  * `MatrixFree`  -- that iteration, in the order the CUDA kernels take it, and
+  * `Generic`     -- the same algorithm on the oracle's CSR matrix (the matrix the reference's own builders
+                     emit, `oracle/model.py`) with the same Pock-Chambolle step sizes,
+so that tests can prove (on the CPU) that the matrix-free form IS the CSR iteration, and (on the GPU) that
+the kernels reproduce it.  Used by tests/ and tools/ only.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+EPS = 1e-6
+
+
+def strengthened(a, kind="min_delay", alpha=0.5):
+    from oracle import model as omodel
+    m = omodel.build_step1(a, kind, alpha)
+    N, F = a["N"], a["F"]; X = F * N * N
+    q = np.arange(X); f = q // (N * N); j = q % N
+    S = sp.csr_matrix((np.tile([1.0, -1.0], X), np.stack([q, X + f * N + j], 1).reshape(-1),
+                       np.arange(0, 2 * X + 1, 2)), shape=(X, m["A"].shape[1]))
+    m2 = dict(m); m2["A"] = sp.vstack([m["A"], S]).tocsr()
+    m2["lo"] = np.concatenate([m["lo"], np.full(X, -np.inf)]); m2["hi"] = np.concatenate([m["hi"], np.zeros(X)])
+    # as csrc/assemble.cu with NEPTUNE_FLAG_STRENGTHEN: C1a rows (even rows of the first 2*F*N) are free, x <= 1
+    C = F * N
+    m2["hi"][0:2 * C:2] = np.inf
+    m2["ub"] = m2["ub"].copy(); m2["ub"][:X] = 1.0
+    return m2
+
+
+def pc_diag(m):
+    """T = 1/colsum|A|, S = 1/rowsum|A| over the non-free rows (what pdhg.cu does with ruiz_iters = 0)."""
+    A = abs(m["A"]).tocsr()
+    free = np.isinf(m["lo"]) & np.isinf(m["hi"])
+    A = sp.diags((~free).astype(float)) @ A
+    rs = np.asarray(A.sum(axis=1)).ravel(); cs = np.asarray(A.sum(axis=0)).ravel()
+    return np.where(cs > 0, 1 / np.where(cs > 0, cs, 1), 1.0), np.where(rs > 0, 1 / np.where(rs > 0, rs, 1), 1.0)
+
+
+class Generic:
+    """PDHG on the CSR matrix, the control logic of pdhg.cu (k_ctl_decide / k_ctl_after_restart)."""
+
+    def __init__(self, m, T, S):
+        self.m, self.A, self.At, self.T, self.S = m, m["A"].tocsr(), m["A"].T.tocsr(), T, S
+        fb = np.where(np.isfinite(m["lo"]), np.abs(m["lo"]), 0)
+        fb = np.maximum(fb, np.where(np.isfinite(m["hi"]), np.abs(m["hi"]), 0))
+        self.nb, self.nc = np.linalg.norm(fb), np.linalg.norm(m["obj"])
+        nbs, ncs = np.sqrt(np.sum(fb * fb * S)), np.sqrt(np.sum(m["obj"] ** 2 * T))
+        self.omega = ncs / nbs if nbs > 1e-10 and ncs > 1e-10 else 1.0
+        self.eta = 0.99
+        self.x = np.zeros(self.A.shape[1]); self.y = np.zeros(self.A.shape[0])
+
+    def step(self):
+        m = self.m
+        tau, sig = self.eta / self.omega, self.eta * self.omega
+        g = self.At @ self.y
+        xn = np.clip(self.x - tau * self.T * (m["obj"] + g), m["lb"], m["ub"])
+        xb = 2 * xn - self.x
+        s = sig * self.S
+        v = self.y + s * (self.A @ xb)
+        yn = v - s * np.clip(v / s, m["lo"], m["hi"])
+        self.x, self.y = xn, yn
+
+    def kkt(self, x, y):
+        m = self.m
+        ax = self.A @ x
+        p2 = np.sum((ax - np.clip(ax, m["lo"], m["hi"])) ** 2)
+        dobj = 0.0; d2 = 0.0
+        pos, neg = y > 0, y < 0
+        fh, fl = np.isfinite(m["hi"]), np.isfinite(m["lo"])
+        dobj -= np.sum(m["hi"][pos & fh] * y[pos & fh]); d2 += np.sum(y[pos & ~fh] ** 2)
+        dobj -= np.sum(m["lo"][neg & fl] * y[neg & fl]); d2 += np.sum(y[neg & ~fl] ** 2)
+        rc = m["obj"] + self.At @ y
+        p, n = rc > 0, rc < 0
+        fu = np.isfinite(m["ub"])
+        dobj += np.sum(m["lb"][p] * rc[p]) + np.sum(m["ub"][n & fu] * rc[n & fu]); d2 += np.sum(rc[n & ~fu] ** 2)
+        return p2, d2, float(m["obj"] @ x), dobj
+
+
+class MatrixFree:
+    """The same iteration without the matrix.  State in the canonical order: x[F,N,N] (f,i,j), c[F,N];
+    y1[F,N] (C1b; C1a multipliers stay 0), y2[N], y3[F,N] (f,i), y4[N], yS[F,N,N]."""
+
+    def __init__(self, a):
+        N, F = a["N"], a["F"]
+        self.N, self.F, self.a = N, F, a
+        d, w, r, mm = a["d"], a["w"], a["r"], a["m"]
+        self.wr = w[:, :, None] * r[:, None, :]                   # [f,i,j]
+        self.obj = d[None, :, :] * w[:, :, None]
+        self.Tx = 1.0 / (3.0 + self.wr)
+        self.Tc = np.repeat((1.0 / (1.0 + mm + N))[:, None], N, 1)
+        self.S1 = 1.0 / (N + 1); self.S3 = 1.0 / N; self.SS = 0.5
+        sm = mm.sum(); self.S2 = 1.0 / sm if sm > 0 else 1.0
+        s4 = self.wr.sum(axis=(0, 1)); self.S4 = np.where(s4 > 0, 1 / np.where(s4 > 0, s4, 1), 1.0)
+        Mj, Kj = a["Mj"], a["Kj"]
+        self.nb = np.sqrt(EPS ** 2 * F * N + np.sum(Mj ** 2) + F * N + np.sum(Kj ** 2))
+        self.nc = np.linalg.norm(self.obj)
+        nbs = np.sqrt(EPS ** 2 * self.S1 * F * N + np.sum(Mj ** 2) * self.S2 + self.S3 * F * N + np.sum(Kj ** 2 * self.S4))
+        ncs = np.sqrt(np.sum(self.obj ** 2 * self.Tx))
+        self.omega = ncs / nbs if nbs > 1e-10 and ncs > 1e-10 else 1.0
+        self.eta = 0.99
+        z = np.zeros
+        self.x, self.c = z((F, N, N)), z((F, N))
+        self.y1, self.y2, self.y3, self.y4, self.yS = z((F, N)), z(N), z((F, N)), z(N), z((F, N, N))
+        self.sS = z((F, N))                                       # sum_i yS[f,i,j], maintained by the big pass
+
+    def step(self):
+        a, N = self.a, self.N
+        tau, sig = self.eta / self.omega, self.eta * self.omega
+        # ---- small kernel, part 1: c update (needs y of the previous iteration only) ----
+        gc = -self.y1 + a["m"][:, None] * self.y2[None, :] - self.sS
+        cn = np.clip(self.c - tau * self.Tc * gc, 0.0, 1.0)
+        cb = 2 * cn - self.c
+        self.c = cn
+        # C2 dual (depends on c-bar only)
+        s = sig * self.S2
+        v = self.y2 + s * (a["m"] @ cb)
+        y2n = v - s * np.minimum(v / s, a["Mj"])
+        # ---- big fused pass over (f,i,j) ----
+        g = self.obj + self.y1[:, None, :] + self.y3[:, :, None] + self.wr * self.y4[None, None, :] + self.yS
+        xn = np.clip(self.x - tau * self.Tx * g, 0.0, 1.0)
+        xb = 2 * xn - self.x
+        s = sig * self.SS
+        self.yS = np.maximum(self.yS + s * (xb - cb[:, None, :]), 0.0)
+        self.x = xn
+        A1 = xb.sum(axis=1)                      # [f,j]   sum over i
+        A3 = xb.sum(axis=2)                      # [f,i]   sum over j
+        A4 = (self.wr * xb).sum(axis=(0, 1))     # [j]
+        self.sS = self.yS.sum(axis=1)
+        # ---- small kernel, part 2 (start of the next launch): the remaining duals ----
+        s = sig * self.S1
+        v = self.y1 + s * (A1 - cb)
+        self.y1 = v - s * np.maximum(v / s, -EPS)
+        s = sig * self.S3
+        v = self.y3 + s * A3
+        self.y3 = v - s * 1.0
+        s = sig * self.S4
+        v = self.y4 + s * A4
+        self.y4 = v - s * np.minimum(v / s, a["Kj"])
+        self.y2 = y2n
+
+    def pack(self):
+        """canonical x / y vectors of the strengthened model"""
+        F, N = self.F, self.N
+        y1 = np.zeros((F * N, 2)); y1[:, 1] = self.y1.reshape(-1)
+        return (np.concatenate([self.x.reshape(-1), self.c.reshape(-1)]),
+                np.concatenate([y1.reshape(-1), self.y2, self.y3.reshape(-1), self.y4, self.yS.reshape(-1)]))
+
+    def kkt(self, st):
+        """closed-form KKT pieces of a state tuple (x,c,y1,y2,y3,y4,yS)"""
+        a = self.a
+        x, c, y1, y2, y3, y4, yS = st
+        p2 = np.sum(np.minimum(x.sum(axis=1) - c + EPS, 0) ** 2) + np.sum(np.maximum(a["m"] @ c - a["Mj"], 0) ** 2)
+        p2 += np.sum((x.sum(axis=2) - 1) ** 2) + np.sum(np.maximum((self.wr * x).sum(axis=(0, 1)) - a["Kj"], 0) ** 2)
+        p2 += np.sum(np.maximum(x - c[:, None, :], 0) ** 2)
+        d2 = np.sum(np.maximum(y1, 0) ** 2) + np.sum(np.minimum(y2, 0) ** 2) + np.sum(np.minimum(y4, 0) ** 2) + np.sum(np.minimum(yS, 0) ** 2)
+        dobj = EPS * np.sum(np.minimum(y1, 0)) - np.sum(a["Mj"] * np.maximum(y2, 0)) - np.sum(y3) - np.sum(a["Kj"] * np.maximum(y4, 0))
+        rcx = self.obj + y1[:, None, :] + y3[:, :, None] + self.wr * y4[None, None, :] + yS
+        rcc = -y1 + a["m"][:, None] * y2[None, :] - yS.sum(axis=1)
+        dobj += np.sum(np.minimum(rcx, 0)) + np.sum(np.minimum(rcc, 0))
+        return p2, d2, float(np.sum(self.obj * x)), dobj
+
+    def state(self):
+        return (self.x, self.c, self.y1, self.y2, self.y3, self.y4, self.yS)
+
+    def set_state(self, st):
+        self.x, self.c, self.y1, self.y2, self.y3, self.y4, self.yS = [np.array(t, dtype=float) for t in st]
+        self.sS = self.yS.sum(axis=1)
+
+
+def solve(mf: MatrixFree, max_iters=20000, check=64, eps=1e-6, verbose=False):
+    """restart logic of pdhg.cu on the matrix-free state"""
+    sums = [np.zeros_like(t) for t in mf.state()]
+    rst = [np.array(t) for t in mf.state()]
+    diag = None
+    cnt = since = restarts = it = 0
+    kr = kp = np.inf
+    while it < max_iters:
+        for _ in range(check):
+            mf.step()
+            for s_, t in zip(sums, mf.state()):
+                s_ += t
+            cnt += 1
+        it += check; since += check
+        cands = []
+        for st in (mf.state(), tuple(s_ / cnt for s_ in sums)):
+            p2, d2, po, do = mf.kkt(st)
+            gap = abs(po - do)
+            k = np.sqrt(mf.omega ** 2 * p2 + d2 / mf.omega ** 2 + gap ** 2)
+            ok = np.sqrt(p2) <= 1e-9 + eps * mf.nb and np.sqrt(d2) <= 1e-9 + eps * mf.nc and gap <= 1e-9 + eps * (abs(po) + abs(do))
+            cands.append((k, ok, p2, d2, po, do))
+        pick = 1 if (cands[1][1] and not cands[0][1]) else (0 if (cands[0][1] and not cands[1][1]) else (1 if cands[1][0] < cands[0][0] else 0))
+        if cands[0][1] or cands[1][1]:
+            if pick == 1:
+                mf.set_state(tuple(s_ / cnt for s_ in sums))
+            return dict(primal=cands[pick][4], dual=cands[pick][5], iters=it, restarts=restarts, converged=True)
+        cand = cands[pick][0]
+        act = False
+        if cand <= 0.2 * kr: act = True
+        elif cand <= 0.8 * kr and cand > kp: act = True
+        elif since >= 0.36 * it and restarts > 0: act = True
+        elif restarts == 0 and since >= 4 * check: act = True
+        kp = cand
+        if verbose and (it // check) % 20 == 0:
+            print(it, pick, f"kkt={cand:.3e} pres={np.sqrt(cands[pick][2]):.2e} dres={np.sqrt(cands[pick][3]):.2e} "
+                  f"po={cands[pick][4]:.4f} do={cands[pick][5]:.4f} om={mf.omega:.3e} r={restarts}")
+        if act:
+            kr = cand; restarts += 1
+            if pick == 1:
+                mf.set_state(tuple(s_ / cnt for s_ in sums))
+            st = mf.state()
+            Td = (mf.Tx, mf.Tc); Sd = (mf.S1, mf.S2, mf.S3, mf.S4, mf.SS)
+            dx = np.sqrt(sum(np.sum((st[k] - rst[k]) ** 2 / Td[k]) for k in range(2)))
+            dy = np.sqrt(sum(np.sum((st[2 + k] - rst[2 + k]) ** 2 / Sd[k]) for k in range(5)))
+            if dx > 1e-10 and dy > 1e-10:
+                nw = np.exp(0.5 * np.log(dy / dx) + 0.5 * np.log(mf.omega))
+                mf.omega = min(max(nw, 0.5 * mf.omega), 2.0 * mf.omega)
+            rst = [np.array(t) for t in st]
+            for s_ in sums: s_[:] = 0
+            cnt = since = 0
+    return dict(primal=cands[pick][4], dual=cands[pick][5], iters=it, restarts=restarts, converged=False)
+
+
+
+
+def run_fixed(a, iters):
+    """What `neptune_pdhg_mf_solve(max_iters = check_every = iters)` returns with unreachable tolerances:
+    `iters` iterations, then the better (smaller KKT error) of the current iterate and the running average.
+    Returns (x, y, info) with x / y in the canonical layout of the strengthened model."""
+    mf = MatrixFree(a)
+    sums = [np.zeros_like(t) for t in mf.state()]
+    for _ in range(iters):
+        mf.step()
+        for s_, t in zip(sums, mf.state()):
+            s_ += t
+    cands = []
+    for st in (mf.state(), tuple(s_ / iters for s_ in sums)):
+        p2, d2, po, do = mf.kkt(st)
+        cands.append((np.sqrt(mf.omega ** 2 * p2 + d2 / mf.omega ** 2 + (po - do) ** 2), p2, d2, po, do))
+    pick = 1 if cands[1][0] < cands[0][0] else 0
+    if pick:
+        mf.set_state(tuple(s_ / iters for s_ in sums))
+    x, y = mf.pack()
+    _, p2, d2, po, do = cands[pick]
+    return x, y, dict(pick=pick, primal_obj=po, dual_obj=do, primal_res=float(np.sqrt(p2)), dual_res=float(np.sqrt(d2)),
+                      omega=mf.omega, kkt=(cands[0][0], cands[1][0]))

@@ -1,0 +1,60 @@
+"""CPU: the matrix-free statement of the PDHG iteration (tests/mf_reference.py, what csrc/pdhg_mf.cu implements)
+IS the CSR iteration on the oracle's strengthened matrix, and it converges to the HiGHS LP optimum."""
+import numpy as np
+import pytest
+
+from helpers import arrays_of, float_payload
+from mf_reference import Generic, MatrixFree, pc_diag, run_fixed, solve, strengthened
+from neptune_mip_b200 import synth
+from oracle import mip as omip
+
+CASES = [("C1", lambda: synth.test_py_payload()), ("r8x4", lambda: synth.random_payload(8, 4, 0, node_cores=30)),
+         ("r12x5", lambda: synth.random_payload(12, 5, 1, node_cores=25)), ("r7x3float", lambda: float_payload(7, 3, 5))]
+
+
+@pytest.mark.parametrize("name,make", CASES, ids=[c[0] for c in CASES])
+def test_matrix_free_iteration_equals_csr_iteration(name, make):
+    a = arrays_of(make())
+    m = strengthened(a)
+    T, S = pc_diag(m)
+    g, mf = Generic(m, T, S), MatrixFree(a)
+    assert abs(g.omega - mf.omega) <= 1e-12 * g.omega          # same initial primal weight
+    assert abs(g.nb - mf.nb) <= 1e-12 * (1 + g.nb) and abs(g.nc - mf.nc) <= 1e-12 * (1 + g.nc)
+    for _ in range(150):
+        g.step(); mf.step()
+    x, y = mf.pack()
+    assert np.abs(x - g.x).max() <= 1e-10 * (1 + np.abs(g.x).max())
+    assert np.abs(y - g.y).max() <= 1e-10 * (1 + np.abs(g.y).max())
+    kg, km = g.kkt(g.x, g.y), mf.kkt(mf.state())
+    for u, v in zip(kg, km):                                    # primal/dual residuals, objectives in closed form
+        assert abs(u - v) <= 1e-9 * (1 + abs(u))
+
+
+def test_closed_form_step_sizes_are_the_pock_chambolle_sums():
+    a = arrays_of(synth.random_payload(8, 4, 2, node_cores=30))
+    m = strengthened(a)
+    T, S = pc_diag(m)
+    mf = MatrixFree(a)
+    N, F = a["N"], a["F"]; X, C = F * N * N, F * N
+    assert np.allclose(T[:X], mf.Tx.reshape(-1), rtol=1e-14) and np.allclose(T[X:X + C], mf.Tc.reshape(-1), rtol=1e-14)
+    rows = np.concatenate([np.stack([np.ones(C), np.full(C, mf.S1)], 1).reshape(-1), np.full(N, mf.S2), np.full(C, mf.S3),
+                           mf.S4, np.full(X, mf.SS)])
+    assert np.allclose(S, rows, rtol=1e-14)
+
+
+def test_matrix_free_pdhg_reaches_the_highs_lp_optimum():
+    a = arrays_of(synth.random_payload(8, 4, 1, node_cores=30))
+    lp = omip.solve_model(strengthened(a), relax=True)
+    out = solve(MatrixFree(a), max_iters=40000, check=64, eps=1e-6)
+    assert out["converged"]
+    assert abs(out["primal"] - lp["objective"]) <= 1e-4 * (1 + abs(lp["objective"]))
+    assert abs(out["dual"] - lp["objective"]) <= 1e-4 * (1 + abs(lp["objective"]))
+
+
+def test_run_fixed_reports_the_better_candidate():
+    a = arrays_of(synth.random_payload(8, 4, 0, node_cores=30))
+    x, y, info = run_fixed(a, 64)
+    assert info["pick"] == (1 if info["kkt"][1] < info["kkt"][0] else 0)
+    N, F = a["N"], a["F"]
+    assert x.shape == (F * N * N + F * N,) and y.shape == (3 * F * N + 2 * N + F * N * N,)
+    assert np.all(y[0:2 * F * N:2] == 0.0)                      # free C1a rows carry no multiplier

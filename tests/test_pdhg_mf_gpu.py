@@ -1,0 +1,133 @@
+"""(b) matrix-free PDHG (`neptune_pdhg_mf_solve`): the kernels reproduce the numpy statement of the iteration
+(tests/mf_reference.py, proven equal to the CSR iteration on the oracle's matrix in tests/test_mf_reference.py),
+agree with the CSR solver on the assembled matrix, and reach the HiGHS LP optimum."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from helpers import arrays_of, cuda_batch, float_payload
+from mf_reference import run_fixed, strengthened
+from neptune_mip_b200 import synth
+from oracle import mip as omip
+
+pytestmark = pytest.mark.gpu
+
+# (name, payload factory, iterations): odd and even N, N <= 32 / <= 64 / > 64 (1, 2, 4 columns per lane; one and
+# several row / column tiles), iteration counts that are one graph replay, several, and replay + remainder
+CASES = [
+    ("C1-3x2", lambda s: synth.test_py_payload(), 64),
+    ("8x4", lambda s: synth.random_payload(8, 4, s, node_cores=30), 64),
+    ("12x5", lambda s: synth.random_payload(12, 5, s, node_cores=25), 96),
+    ("20x5", lambda s: synth.random_payload(20, 5, s, node_cores=100), 40),
+    ("33x3", lambda s: synth.random_payload(33, 3, s, node_cores=60), 33),
+    ("50x10", lambda s: synth.random_payload(50, 10, s, node_cores=200), 64),
+    ("70x3", lambda s: synth.random_payload(70, 3, s, node_cores=60), 64),
+    ("7x3-float", lambda s: float_payload(7, 3, 5 + s), 64),
+]
+
+
+def _close(got, want, tol):
+    scale = 1.0 + np.abs(want).max()
+    return np.abs(got - want).max() <= tol * scale
+
+
+@pytest.mark.parametrize("name,make,iters", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("bulk", [False, True], ids=["register-pass", "bulk-copy-pass"])
+def test_iterates_equal_the_numpy_reference(name, make, iters, bulk):
+    """After `iters` iterations (no restart inside) the returned candidate -- current iterate or running
+    average, whichever has the smaller KKT error -- equals the reference's.  Tolerance 1e-9 relative to the
+    largest entry: the kernels only differ from numpy in summation order and FMA contraction."""
+    from neptune_mip_b200 import device
+    payloads = [make(s) for s in range(2)]
+    inst = cuda_batch(payloads)
+    x, y, res = device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-13, eps_abs=1e-15,
+                                     bulk_copy_kernel=bulk)
+    for b, p in enumerate(payloads):
+        xr, yr, info = run_fixed(arrays_of(p), iters)
+        assert _close(x[b].cpu().numpy(), xr, 1e-9), (name, b)
+        assert _close(y[b].cpu().numpy(), yr, 1e-9), (name, b)
+        assert abs(res[b]["primal_obj"] - info["primal_obj"]) <= 1e-9 * (1 + abs(info["primal_obj"]))
+        assert abs(res[b]["dual_obj"] - info["dual_obj"]) <= 1e-9 * (1 + abs(info["dual_obj"]))
+        assert abs(res[b]["primal_res"] - info["primal_res"]) <= 1e-9 * (1 + info["primal_res"])
+        assert abs(res[b]["primal_weight"] - info["omega"]) <= 1e-12 * info["omega"]
+        assert res[b]["iters"] == iters and res[b]["converged"] == 0
+        assert np.all(y[b].cpu().numpy()[0:2 * inst.F * inst.N:2] == 0.0)      # free C1a rows
+
+
+@pytest.mark.parametrize("shape", [(130, 2), (300, 2), (64, 3)])
+def test_bulk_copy_pass_equals_register_pass(shape):
+    """wider shapes (2 and 4 columns per thread of the bulk-copy pass; several row tiles): the two iteration
+    kernels are the same arithmetic in a different order"""
+    from neptune_mip_b200 import device
+    inst = cuda_batch([synth.random_payload(shape[0], shape[1], 1, node_cores=60)])
+    xa, ya, ra = device.pdhg_mf_solve(inst, max_iters=33, check_every=33, eps_rel=1e-13, eps_abs=1e-15)
+    xb, yb, rb = device.pdhg_mf_solve(inst, max_iters=33, check_every=33, eps_rel=1e-13, eps_abs=1e-15, bulk_copy_kernel=True)
+    assert _close(xb.cpu().numpy(), xa.cpu().numpy(), 1e-11) and _close(yb.cpu().numpy(), ya.cpu().numpy(), 1e-11)
+    assert abs(ra[0]["primal_obj"] - rb[0]["primal_obj"]) <= 1e-11 * (1 + abs(ra[0]["primal_obj"]))
+
+
+def test_agrees_with_the_csr_solver_on_the_assembled_matrix():
+    """same algorithm on the assembled (reference-identical + strengthening rows) CSR matrix with the same step
+    sizes (ruiz_iters = 0); 1e-6: the CSR kernels square a reciprocal square root where the closed form divides"""
+    from neptune_mip_b200 import device
+    from neptune_mip_b200._lib import FLAG_STRENGTHEN
+    inst = cuda_batch([synth.random_payload(20, 5, s, node_cores=100) for s in range(3)])
+    mdl = device.assemble(inst, "min_delay", flags=FLAG_STRENGTHEN)
+    xa, ya, ra = device.pdhg_solve(mdl, max_iters=64, check_every=64, ruiz_iters=0, eps_rel=1e-13, eps_abs=1e-15)
+    xb, yb, rb = device.pdhg_mf_solve(inst, max_iters=64, check_every=64, eps_rel=1e-13, eps_abs=1e-15)
+    assert _close(xb.cpu().numpy(), xa.cpu().numpy(), 1e-6) and _close(yb.cpu().numpy(), ya.cpu().numpy(), 1e-6)
+    assert np.allclose(ra["primal_obj"], rb["primal_obj"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("shape,cores", [((12, 5), 25), ((8, 4), 12), ((10, 3), 20)])
+def test_reaches_the_highs_lp_optimum(shape, cores):
+    """LP value of the strengthened relaxation: |obj - obj_highs| <= 1e-4 * (1 + |obj_highs|) (BASELINE.json's
+    1e-4 relative), primal and dual side, with the convergence flag set."""
+    from neptune_mip_b200 import device
+    p = synth.random_payload(shape[0], shape[1], 1, node_cores=cores)
+    lp = omip.solve_model(strengthened(arrays_of(p)), relax=True)
+    x, y, res = device.pdhg_mf_solve(cuda_batch([p]), max_iters=30000, check_every=128, eps_rel=1e-6, eps_abs=1e-9)
+    assert res[0]["converged"] == 1
+    assert abs(res[0]["primal_obj"] - lp["objective"]) <= 1e-4 * (1 + abs(lp["objective"]))
+    assert abs(res[0]["dual_obj"] - lp["objective"]) <= 1e-4 * (1 + abs(lp["objective"]))
+    xs = x[0].cpu().numpy()
+    assert xs.min() >= 0.0 and xs.max() <= 1.0
+
+
+def test_instances_of_a_batch_converge_independently():
+    """per-instance step sizes, restarts and convergence: every instance of a batch takes exactly the trajectory
+    it takes alone (a converged instance is frozen while the others run on)"""
+    from neptune_mip_b200 import device
+    ps = [synth.random_payload(8, 4, 1, node_cores=200), synth.random_payload(8, 4, 1, node_cores=12),
+          synth.random_payload(8, 4, 2, node_cores=30)]
+    kw = dict(max_iters=20000, check_every=128, eps_rel=1e-6, eps_abs=1e-9)
+    x, y, res = device.pdhg_mf_solve(cuda_batch(ps), **kw)
+    assert len(set(res["iters"].tolist())) > 1                       # they do stop at different times
+    for b, p in enumerate(ps):
+        xs, ys, rs = device.pdhg_mf_solve(cuda_batch([p]), **kw)
+        assert res[b]["converged"] == 1 and res[b]["iters"] == rs[0]["iters"] and res[b]["restarts"] == rs[0]["restarts"]
+        assert np.array_equal(x[b].cpu().numpy(), xs[0].cpu().numpy())
+        assert np.array_equal(y[b].cpu().numpy(), ys[0].cpu().numpy())
+
+
+def test_other_model_kinds_are_refused():
+    """only the min-delay model is stated in closed form; the n-column models go through the CSR solver"""
+    import torch
+    from neptune_mip_b200 import _lib, device
+    lib = _lib.load()
+    inst = cuda_batch([synth.random_payload(8, 4, 0, node_cores=30)])
+    need = ctypes.c_int64()
+    assert lib.neptune_pdhg_mf_workspace_bytes(1, 8, 4, ctypes.byref(need)) == 0 and need.value > 0
+    ws = torch.empty(need.value, dtype=torch.uint8, device="cuda")
+    rows, cols, _ = device.model_sizes(8, 4, 0, 1)
+    x = torch.zeros(cols, dtype=torch.float64, device="cuda")
+    y = torch.zeros(rows, dtype=torch.float64, device="cuda")
+    res = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    prm = _lib.PdhgParams(64, 64, 0, 0, 1e-6, 1e-9)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    args = [p(inst.d), p(inst.w), p(inst.r), p(inst.m), p(inst.Mj), p(inst.Kj), ctypes.byref(prm), p(x), p(y), p(res), p(ws)]
+    for kind in (1, 2):
+        assert lib.neptune_pdhg_mf_solve(1, 8, 4, kind, *args, ws.numel(), None) == -1
+    assert lib.neptune_pdhg_mf_solve(1, 8, 4, 0, *args, 16, None) == -3          # workspace too small
+    assert lib.neptune_pdhg_mf_solve(1, 8, 4, 0, *args, ws.numel(), None) == 0
