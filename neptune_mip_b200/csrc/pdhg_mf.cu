@@ -202,6 +202,131 @@ k_mf_iter(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
   }
 }
 
+// the iteration pass with 16-byte accesses (even N > 32): a lane owns KV pairs of adjacent columns (double2 loads
+// and stores of all four streams and of d), U rows of a warp in flight -- half the memory instructions and address
+// arithmetic of k_mf_iter for the same bytes, twice the bytes in flight per instruction.  Same tiles, same
+// partial-sum layout and the same summation order per column as k_mf_iter<2*KV, .>.
+template <int KV, int U>
+__global__ void __launch_bounds__(kMfThreads, 2)
+k_mf_iter_vec(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
+  constexpr int K = 2 * KV;
+  __shared__ double sm[3][kMfWarps][32 * K];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = G.N;
+  const int64_t NN = (int64_t)N * N;
+  const int64_t total = (int64_t)B * G.tiles_inst;
+  for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const Tile t = decode_tile(G, tile);
+    const int b = t.b, f = t.f;
+    if (ctl[b].converged) continue;
+    const double tau = ctl[b].tau, shalf = 0.5 * ctl[b].sigma;
+    const double* __restrict__ d = in.d + (int64_t)b * NN;
+    const double* __restrict__ w = in.w + ((int64_t)b * G.F + f) * N;
+    const double* __restrict__ r = in.r + ((int64_t)b * G.F + f) * N;
+    const double* __restrict__ y = st.y + (int64_t)b * G.rows;
+    const double* __restrict__ y3 = y + G.r3 + (int64_t)f * N;
+    double* __restrict__ xp = st.x + (int64_t)b * G.cols + (int64_t)f * NN;
+    double* __restrict__ xsp = st.xsum + (int64_t)b * G.cols + (int64_t)f * NN;
+    double* __restrict__ sp = st.y + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
+    double* __restrict__ ssp = st.ysum + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
+    const double* __restrict__ cbar = st.cbar + (int64_t)b * G.C + (int64_t)f * N;
+    double* __restrict__ P3 = st.P3i + ((int64_t)b * G.C + (int64_t)f * N) * G.cti + t.jt;
+
+    int jj[KV]; bool vj[KV];
+    double y1j[K], rj[K], rr4[K], cb[K];
+#pragma unroll
+    for (int k = 0; k < KV; ++k) {
+      const int j = t.jt * G.JT + k * 64 + 2 * lane;
+      vj[k] = j < N; jj[k] = vj[k] ? j : 0;                      // N even: a pair is valid or not as a whole
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = 2 * k + h, jc = jj[k] + h;
+        y1j[c] = y[2 * ((int64_t)f * N + jc) + 1];
+        rj[c] = __ldg(r + jc);
+        rr4[c] = rj[c] * y[G.r4 + jc];
+        cb[c] = cbar[jc];
+      }
+    }
+    double a1[K], a4[K], aS[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) { a1[c] = 0.0; a4[c] = 0.0; aS[c] = 0.0; }
+
+    const int i0 = t.it * G.RT, i1 = min(N, i0 + G.RT);
+    for (int ib = i0 + warp; ib < i1; ib += U * kMfWarps) {
+      double2 xv[U][KV], sv[U][KV], xs[U][KV], ss[U][KV];
+      double wfi[U], y3i[U];
+      int ro[U]; bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = ib + u * kMfWarps;
+        ok[u] = i < i1;
+        const int ir = ok[u] ? i : ib;
+        ro[u] = ir * N;
+        wfi[u] = __ldg(w + ir); y3i[u] = y3[ir];
+#pragma unroll
+        for (int k = 0; k < KV; ++k) {
+          const int o = ro[u] + jj[k];
+          xv[u][k] = *reinterpret_cast<const double2*>(xp + o);
+          sv[u][k] = *reinterpret_cast<const double2*>(sp + o);
+          xs[u][k] = *reinterpret_cast<const double2*>(xsp + o);
+          ss[u][k] = *reinterpret_cast<const double2*>(ssp + o);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        double rsum = 0.0;
+#pragma unroll
+        for (int k = 0; k < KV; ++k) {
+          if (ok[u] && vj[k]) {
+            const int o = ro[u] + jj[k];
+            double xin[2] = {xv[u][k].x, xv[u][k].y}, sin_[2] = {sv[u][k].x, sv[u][k].y};
+            const double2 dd = __ldg(reinterpret_cast<const double2*>(d + o));     // L1 / L2 resident
+            double din[2] = {dd.x, dd.y};
+            double xo[2], so[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int c = 2 * k + h;
+              const double wr = fabs(wfi[u] * rj[c]);
+              const double g = __dmul_rn(din[h], wfi[u]) + y1j[c] + y3i[u] + wfi[u] * rr4[c] + sin_[h];
+              double xn = xin[h] - tau * g / (3.0 + wr);
+              xn = fmin(fmax(xn, 0.0), 1.0);
+              const double xb = 2.0 * xn - xin[h];
+              const double sn = fmax(sin_[h] + shalf * (xb - cb[c]), 0.0);
+              xo[h] = xn; so[h] = sn;
+              a1[c] += xb; a4[c] += wfi[u] * xb; aS[c] += sn; rsum += xb;
+            }
+            *reinterpret_cast<double2*>(xp + o) = make_double2(xo[0], xo[1]);
+            *reinterpret_cast<double2*>(sp + o) = make_double2(so[0], so[1]);
+            *reinterpret_cast<double2*>(xsp + o) = make_double2(xs[u][k].x + xo[0], xs[u][k].y + xo[1]);
+            *reinterpret_cast<double2*>(ssp + o) = make_double2(ss[u][k].x + so[0], ss[u][k].y + so[1]);
+          }
+        }
+        rsum = warp_sum(rsum);
+        if (lane == 0 && ok[u]) P3[(int64_t)(ib + u * kMfWarps) * G.cti] = rsum;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KV; ++k) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = 2 * k + h, col = k * 64 + 2 * lane + h;
+        sm[0][warp][col] = a1[c]; sm[1][warp][col] = a4[c]; sm[2][warp][col] = aS[c];
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 32 * K; c += kMfThreads) {
+      const int j = t.jt * G.JT + c;
+      if (j < N) {
+        const int64_t o = (((int64_t)b * G.F + f) * G.rt + t.it) * N + j;
+        st.P1[o] = column_total<K>(sm[0], c);
+        st.P4[o] = __ldg(r + j) * column_total<K>(sm[1], c);
+        st.PS[o] = column_total<K>(sm[2], c);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // the iteration pass, TMA version (even N): x and yS of a tile are contiguous in memory, so they are staged
 // in shared memory by 1-D bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP), five stages deep -- those bytes
@@ -949,6 +1074,7 @@ struct MfPlan {
   int grid_iter, grid_eval, small_blocks, fused;
   int use_tma; TmaGeo T;
   int rows_in_flight;            // U of k_mf_iter<K, U>
+  int vec;                       // k_mf_iter_vec (16-byte accesses) instead of k_mf_iter
   int diag;                      // tools only: bits of params->reserved >> 4 switch parts of the TMA pass off
 };
 
@@ -967,6 +1093,16 @@ static void mf_launch_iter(const MfPlan& P) {
   }
   const int64_t total = (int64_t)P.B * P.G.tiles_inst;
   const int g = (int)(total < P.grid_iter ? total : P.grid_iter);
+  if (P.vec) {
+    switch (P.G.K * 10 + P.rows_in_flight) {
+      case 22: k_mf_iter_vec<1, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+      case 24: k_mf_iter_vec<1, 4><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+      case 41: k_mf_iter_vec<2, 1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+      default: k_mf_iter_vec<2, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+    }
+    NEPTUNE_COUNT(1);
+    return;
+  }
   switch (P.G.K * 10 + P.rows_in_flight) {
     case 11: k_mf_iter<1, 1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
     case 12: k_mf_iter<1, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
@@ -1057,18 +1193,32 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
               (double*)(base + W.P1), (double*)(base + W.P4), (double*)(base + W.PS), (double*)(base + W.P3),
               (double*)(base + W.P3i),
               (double*)(base + W.S4), (double*)(base + W.S2), (double*)(base + W.wsum), (double*)(base + W.scal)};
-  // rows in flight per warp of the register pass: reserved bits 8..10 override (tools), default by K
+  // register pass variant: 16-byte accesses (k_mf_iter_vec) where every row start is 16-byte aligned (even N > 32,
+  // aligned vectors) unless reserved bit 11 switches it off; rows in flight per warp: reserved bits 8..10 override
+  // (tools), default by K
+  P.vec = !(prm->reserved & 0x800) && !(N & 1) && G.K >= 2 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
   P.rows_in_flight = (prm->reserved >> 8) & 7;
-  if (P.rows_in_flight != 1 && P.rows_in_flight != 2 && !(P.rows_in_flight == 4 && G.K == 1))
-    P.rows_in_flight = G.K == 4 ? 1 : 2;
-  switch (G.K * 10 + P.rows_in_flight) {
-    case 11: P.grid_iter = mf_grid(k_mf_iter<1, 1>); break;
-    case 12: P.grid_iter = mf_grid(k_mf_iter<1, 2>); break;
-    case 14: P.grid_iter = mf_grid(k_mf_iter<1, 4>); break;
-    case 21: P.grid_iter = mf_grid(k_mf_iter<2, 1>); break;
-    case 22: P.grid_iter = mf_grid(k_mf_iter<2, 2>); break;
-    case 41: P.grid_iter = mf_grid(k_mf_iter<4, 1>); break;
-    default: P.grid_iter = mf_grid(k_mf_iter<4, 2>); break;
+  if (P.vec) {
+    if (G.K == 2 && P.rows_in_flight != 2 && P.rows_in_flight != 4) P.rows_in_flight = 4;
+    if (G.K == 4 && P.rows_in_flight != 1 && P.rows_in_flight != 2) P.rows_in_flight = 2;
+    switch (G.K * 10 + P.rows_in_flight) {
+      case 22: P.grid_iter = mf_grid(k_mf_iter_vec<1, 2>); break;
+      case 24: P.grid_iter = mf_grid(k_mf_iter_vec<1, 4>); break;
+      case 41: P.grid_iter = mf_grid(k_mf_iter_vec<2, 1>); break;
+      default: P.grid_iter = mf_grid(k_mf_iter_vec<2, 2>); break;
+    }
+  } else {
+    if (P.rows_in_flight != 1 && P.rows_in_flight != 2 && !(P.rows_in_flight == 4 && G.K == 1))
+      P.rows_in_flight = G.K == 4 ? 1 : 2;
+    switch (G.K * 10 + P.rows_in_flight) {
+      case 11: P.grid_iter = mf_grid(k_mf_iter<1, 1>); break;
+      case 12: P.grid_iter = mf_grid(k_mf_iter<1, 2>); break;
+      case 14: P.grid_iter = mf_grid(k_mf_iter<1, 4>); break;
+      case 21: P.grid_iter = mf_grid(k_mf_iter<2, 1>); break;
+      case 22: P.grid_iter = mf_grid(k_mf_iter<2, 2>); break;
+      case 41: P.grid_iter = mf_grid(k_mf_iter<4, 1>); break;
+      default: P.grid_iter = mf_grid(k_mf_iter<4, 2>); break;
+    }
   }
   switch (G.K) {
     case 1: P.grid_eval = mf_grid(k_mf_eval<1>); break;

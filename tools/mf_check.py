@@ -113,17 +113,22 @@ def timing(name, inst, iters, with_csr):
 def main():
     if "--variants" in sys.argv:      # register pass: rows in flight per warp; the small-vector kernel alone
         torch.cuda.set_device(0)
-        for name, inst, iters in (("C2 batch 256", synth_batch(50, 10, 256), 512), ("C3 500x50", synth_batch(500, 50, 1), 128),
-                                  ("C4 share 2000x25", synth_batch(2000, 25, 1), 32), ("C5 20x5 x4096", synth_batch(20, 5, 4096), 256)):
+        for name, inst, iters in (("C2 batch 256", synth_batch(50, 10, 256), 512), ("C3 500x50", synth_batch(500, 50, 1), 256),
+                                  ("C4 share 2000x25", synth_batch(2000, 25, 1), 64)):
             X = inst.F * inst.N * inst.N
             ref = None
-            for u in ((1, 2, 4) if inst.N <= 32 else (1, 2)):
-                device.pdhg_mf_solve(inst, max_iters=32, check_every=32, rows_in_flight=u)
-                (xu, yu, _), ms = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14, rows_in_flight=u))
+            variants = [(True, 1), (True, 2)] + ([(True, 4)] if inst.N <= 32 else [])
+            if inst.N > 32 and inst.N % 2 == 0:
+                variants += [(False, 2), (False, 4)] if inst.N <= 64 else [(False, 1), (False, 2)]
+            for scalar, u in variants:
+                kw = dict(rows_in_flight=u, scalar_kernel=scalar)
+                device.pdhg_mf_solve(inst, max_iters=32, check_every=32, **kw)
+                (xu, yu, _), ms = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14, **kw))
                 if ref is None:
                     ref = (xu, yu)
-                print("VAR", name, "rows in flight", u, "us/iter %.1f" % (1e3 * ms / iters), "GB/s %.0f" % (inst.B * 64 * X * iters / ms / 1e6),
-                      "max |dx| vs U=1 %.1e" % float((xu - ref[0]).abs().max()), flush=True)
+                print("VAR", name, "8-byte" if scalar else "16-byte", "accesses, rows in flight", u, "us/iter %.1f" % (1e3 * ms / iters),
+                      "GB/s %.0f" % (inst.B * 64 * X * iters / ms / 1e6), "max |dx| vs first %.1e" % float((xu - ref[0]).abs().max()),
+                      "max |dy| %.1e" % float((yu - ref[1]).abs().max()), flush=True)
             device.pdhg_mf_solve(inst, max_iters=32, check_every=32, _diag=4)
             _, ms = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14, _diag=4))
             print("VAR", name, "small-vector kernel alone us/iter %.1f" % (1e3 * ms / iters), flush=True)
