@@ -1193,14 +1193,14 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
               (double*)(base + W.P1), (double*)(base + W.P4), (double*)(base + W.PS), (double*)(base + W.P3),
               (double*)(base + W.P3i),
               (double*)(base + W.S4), (double*)(base + W.S2), (double*)(base + W.wsum), (double*)(base + W.scal)};
-  // register pass variant: 16-byte accesses (k_mf_iter_vec) where every row start is 16-byte aligned (even N > 32,
-  // aligned vectors) unless reserved bit 11 switches it off; rows in flight per warp: reserved bits 8..10 override
-  // (tools), default by K
-  P.vec = !(prm->reserved & 0x800) && !(N & 1) && G.K >= 2 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  // register pass variant: 16-byte accesses (k_mf_iter_vec) are opt-in (reserved bit 11; even N > 32, aligned
+  // vectors) -- measured equal or slower than the 8-byte pass on B200 (profiles/r01f_summary.md); rows in flight
+  // per warp: reserved bits 8..10 override (tools), default by K
+  P.vec = (prm->reserved & 0x800) && !(N & 1) && G.K >= 2 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
   P.rows_in_flight = (prm->reserved >> 8) & 7;
   if (P.vec) {
-    if (G.K == 2 && P.rows_in_flight != 2 && P.rows_in_flight != 4) P.rows_in_flight = 4;
-    if (G.K == 4 && P.rows_in_flight != 1 && P.rows_in_flight != 2) P.rows_in_flight = 2;
+    if (G.K == 2 && P.rows_in_flight != 2 && P.rows_in_flight != 4) P.rows_in_flight = 2;
+    if (G.K == 4 && P.rows_in_flight != 1 && P.rows_in_flight != 2) P.rows_in_flight = 1;
     switch (G.K * 10 + P.rows_in_flight) {
       case 22: P.grid_iter = mf_grid(k_mf_iter_vec<1, 2>); break;
       case 24: P.grid_iter = mf_grid(k_mf_iter_vec<1, 4>); break;

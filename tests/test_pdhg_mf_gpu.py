@@ -33,8 +33,8 @@ def _close(got, want, tol):
 
 
 @pytest.mark.parametrize("name,make,iters", CASES, ids=[c[0] for c in CASES])
-@pytest.mark.parametrize("bulk", [False, True], ids=["register-pass", "bulk-copy-pass"])
-def test_iterates_equal_the_numpy_reference(name, make, iters, bulk):
+@pytest.mark.parametrize("variant", ["register-pass", "bulk-copy-pass", "16-byte-pass"])
+def test_iterates_equal_the_numpy_reference(name, make, iters, variant):
     """After `iters` iterations (no restart inside) the returned candidate -- current iterate or running
     average, whichever has the smaller KKT error -- equals the reference's.  Tolerance 1e-9 relative to the
     largest entry: the kernels only differ from numpy in summation order and FMA contraction."""
@@ -42,7 +42,8 @@ def test_iterates_equal_the_numpy_reference(name, make, iters, bulk):
     payloads = [make(s) for s in range(2)]
     inst = cuda_batch(payloads)
     x, y, res = device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-13, eps_abs=1e-15,
-                                     bulk_copy_kernel=bulk)
+                                     bulk_copy_kernel=variant == "bulk-copy-pass",
+                                     vector_kernel=variant == "16-byte-pass")
     for b, p in enumerate(payloads):
         xr, yr, info = run_fixed(arrays_of(p), iters)
         assert _close(x[b].cpu().numpy(), xr, 1e-9), (name, b)
@@ -56,15 +57,19 @@ def test_iterates_equal_the_numpy_reference(name, make, iters, bulk):
 
 
 @pytest.mark.parametrize("shape", [(130, 2), (300, 2), (64, 3)])
-def test_bulk_copy_pass_equals_register_pass(shape):
-    """wider shapes (2 and 4 columns per thread of the bulk-copy pass; several row tiles): the two iteration
-    kernels are the same arithmetic in a different order"""
+def test_bulk_copy_and_16_byte_passes_equal_the_register_pass(shape):
+    """wider shapes (2 and 4 columns per thread of the bulk-copy pass; several row tiles): the iteration kernels
+    are the same arithmetic in a different order"""
     from neptune_mip_b200 import device
     inst = cuda_batch([synth.random_payload(shape[0], shape[1], 1, node_cores=60)])
     xa, ya, ra = device.pdhg_mf_solve(inst, max_iters=33, check_every=33, eps_rel=1e-13, eps_abs=1e-15)
     xb, yb, rb = device.pdhg_mf_solve(inst, max_iters=33, check_every=33, eps_rel=1e-13, eps_abs=1e-15, bulk_copy_kernel=True)
     assert _close(xb.cpu().numpy(), xa.cpu().numpy(), 1e-11) and _close(yb.cpu().numpy(), ya.cpu().numpy(), 1e-11)
     assert abs(ra[0]["primal_obj"] - rb[0]["primal_obj"]) <= 1e-11 * (1 + abs(ra[0]["primal_obj"]))
+    for u in (1, 2):
+        xc, yc, rc = device.pdhg_mf_solve(inst, max_iters=33, check_every=33, eps_rel=1e-13, eps_abs=1e-15, vector_kernel=True,
+                                          rows_in_flight=u)
+        assert _close(xc.cpu().numpy(), xa.cpu().numpy(), 1e-11) and _close(yc.cpu().numpy(), ya.cpu().numpy(), 1e-11)
 
 
 def test_agrees_with_the_csr_solver_on_the_assembled_matrix():

@@ -111,6 +111,25 @@ def timing(name, inst, iters, with_csr):
 
 
 def main():
+    if "--ceiling" in sys.argv:       # what plain torch kernels reach on this box for copy / read-modify-write streams
+        torch.cuda.set_device(0)
+        n = 256 * 25000                                            # one x-shaped stream of the C2 batch (51 MB)
+        a, b2, c2, d2 = (torch.rand(n, dtype=torch.float64, device="cuda") for _ in range(4))
+        big_a, big_b = torch.rand(1 << 27, dtype=torch.float64, device="cuda"), torch.empty(1 << 27, dtype=torch.float64, device="cuda")
+        def rate(fn, nbytes, reps=20):
+            fn(); torch.cuda.synchronize()
+            _, ms = timed(lambda: [fn() for _ in range(reps)])
+            return nbytes * reps / ms / 1e6
+        print("CEIL copy 1 GiB f64 (read + write) GB/s %.0f" % rate(lambda: big_b.copy_(big_a), 2 * 8 * (1 << 27)), flush=True)
+        print("CEIL a.add_(b) on 51 MB streams, 4 arrays round robin (2 reads + 1 write) GB/s %.0f" %
+              rate(lambda: (a.add_(b2), c2.add_(d2)), 2 * 24 * n), flush=True)
+        print("CEIL torch._foreach_add_ of two 51 MB pairs GB/s %.0f" % rate(lambda: torch._foreach_add_([a, c2], [b2, d2]), 2 * 24 * n), flush=True)
+        for name, inst, iters in (("C3 500x50", synth_batch(500, 50, 1), 1024), ("C4 share 2000x25", synth_batch(2000, 25, 1), 256)):
+            X = inst.F * inst.N * inst.N
+            device.pdhg_mf_solve(inst, max_iters=32, check_every=32)
+            _, ms = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14))
+            print("LONG", name, "iters", iters, "us/iter %.1f" % (1e3 * ms / iters), "GB/s %.0f" % (inst.B * (64 * X + 112 * inst.F * inst.N + 8 * inst.N ** 2) * iters / ms / 1e6), flush=True)
+        return
     if "--variants" in sys.argv:      # register pass: rows in flight per warp; the small-vector kernel alone
         torch.cuda.set_device(0)
         for name, inst, iters in (("C2 batch 256", synth_batch(50, 10, 256), 512), ("C3 500x50", synth_batch(500, 50, 1), 256),
@@ -121,7 +140,7 @@ def main():
             if inst.N > 32 and inst.N % 2 == 0:
                 variants += [(False, 2), (False, 4)] if inst.N <= 64 else [(False, 1), (False, 2)]
             for scalar, u in variants:
-                kw = dict(rows_in_flight=u, scalar_kernel=scalar)
+                kw = dict(rows_in_flight=u, vector_kernel=not scalar)
                 device.pdhg_mf_solve(inst, max_iters=32, check_every=32, **kw)
                 (xu, yu, _), ms = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14, **kw))
                 if ref is None:
