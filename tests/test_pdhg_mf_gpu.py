@@ -74,15 +74,17 @@ def test_bulk_copy_and_16_byte_passes_equal_the_register_pass(shape):
 
 def test_agrees_with_the_csr_solver_on_the_assembled_matrix():
     """same algorithm on the assembled (reference-identical + strengthening rows) CSR matrix with the same step
-    sizes (ruiz_iters = 0); 1e-6: the CSR kernels square a reciprocal square root where the closed form divides"""
+    sizes (ruiz_iters = 0).  Bound 5e-5 relative (BASELINE.json's 1e-4 with margin): the CSR kernels square a
+    reciprocal square root where the closed form divides, and sum every row in another order"""
     from neptune_mip_b200 import device
     from neptune_mip_b200._lib import FLAG_STRENGTHEN
     inst = cuda_batch([synth.random_payload(20, 5, s, node_cores=100) for s in range(3)])
     mdl = device.assemble(inst, "min_delay", flags=FLAG_STRENGTHEN)
     xa, ya, ra = device.pdhg_solve(mdl, max_iters=64, check_every=64, ruiz_iters=0, eps_rel=1e-13, eps_abs=1e-15)
     xb, yb, rb = device.pdhg_mf_solve(inst, max_iters=64, check_every=64, eps_rel=1e-13, eps_abs=1e-15)
-    assert _close(xb.cpu().numpy(), xa.cpu().numpy(), 1e-6) and _close(yb.cpu().numpy(), ya.cpu().numpy(), 1e-6)
-    assert np.allclose(ra["primal_obj"], rb["primal_obj"], rtol=1e-6)
+    assert _close(xb.cpu().numpy(), xa.cpu().numpy(), 5e-5) and _close(yb.cpu().numpy(), ya.cpu().numpy(), 5e-5)
+    assert np.allclose(ra["primal_obj"], rb["primal_obj"], rtol=5e-5)
+    print("csr vs matrix-free after 64 iterations: max |dx| %.2e, max |dy| %.2e" % (float((xa - xb).abs().max()), float((ya - yb).abs().max())))
 
 
 @pytest.mark.parametrize("shape,cores", [((12, 5), 25), ((8, 4), 12), ((10, 3), 20)])
