@@ -709,6 +709,7 @@ extern "C" int neptune_pdhg_solve(int B, int64_t rows, int64_t cols, int64_t nnz
       launch_cols(P, y, pu);
       launch_rows(P, xbar, du);
     }
+    { k_ctl_advance<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, check_every); NEPTUNE_COUNT(1); }
     // KKT of the current iterate and of the running average
     for (int w = 0; w < 2; ++w) {
       launch_rows(P, w ? xsum : x, RowsEval{ctl, rows, w, lo, hi, w ? ysum : y, 0.0, 0.0, 0.0});

@@ -44,6 +44,18 @@ static __global__ void k_ctl_zero(int B, Ctl* ctl) {
   if (b < B) for (int k = 0; k < NACC; ++k) ctl[b].acc[k] = 0.0;
 }
 
+// Count the iterations of the chunk that just ran.  Launched BEFORE the KKT evaluation passes: they scale the
+// running sums by 1 / avg_count, which must already include the chunk (counting it only in k_ctl_decide made
+// the averaged candidate look `check_every` times too large at the first check after every restart, so the
+// average was almost never the restart point -- found against the numpy statement of the iteration).
+static __global__ void k_ctl_advance(int B, Ctl* ctl, int did_iters) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  Ctl& c = ctl[b];
+  if (c.converged) return;
+  c.iters += did_iters; c.since_restart += did_iters; c.avg_count += did_iters;
+}
+
 // Restart / termination decision, one thread per instance (PDLP's KKT-error criteria:
 // sufficient decay 0.2, necessary decay 0.8 + no progress, artificial restart at 36 % of the run).
 static __global__ void k_ctl_decide(int B, Ctl* ctl, int did_iters, double eps_abs, double eps_rel, int max_iters,
@@ -52,7 +64,6 @@ static __global__ void k_ctl_decide(int B, Ctl* ctl, int did_iters, double eps_a
   if (b >= B) return;
   Ctl& c = ctl[b];
   if (c.converged) return;
-  c.iters += did_iters; c.since_restart += did_iters; c.avg_count += did_iters;
   double kkt[2]; bool ok[2];
   for (int w = 0; w < 2; ++w) {
     const double* a = c.acc + (w ? ACC_AVG : ACC_CUR);

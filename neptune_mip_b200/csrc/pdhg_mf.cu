@@ -1297,6 +1297,7 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
       first = false;
     }
     mf_launch_small(P, PH_POST, nullptr);
+    { k_ctl_advance<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, check_every); NEPTUNE_COUNT(1); }
     // KKT of the current iterate and of the running average
     for (int wch = 0; wch < 2; ++wch) {
       mf_launch_eval(P, wch, 0);
