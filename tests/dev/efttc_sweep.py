@@ -2,7 +2,7 @@
 GPU: one launch per objective (device-resident and host-buffer entry points); CPU: the oracle's
 restatement of the reference's greedy on a bounded sample.  Prints one JSON line."""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from neptune_mip_b200 import device, synth

@@ -1,5 +1,5 @@
 """Development driver for the matrix-free PDHG reference (tests/mf_reference.py): iterate equality with the
-CSR iteration, LP optimum against HiGHS, convergence.   python tools/pdhg_mf_proto.py [N F cores]"""
+CSR iteration, LP optimum against HiGHS, convergence.   python tests/dev/pdhg_mf_proto.py [N F cores]"""
 import sys
 import time
 
