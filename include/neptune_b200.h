@@ -97,7 +97,9 @@ typedef struct neptune_pdhg_params {
   int     max_iters;        /* hard cap on PDHG iterations */
   int     check_every;      /* iterations between KKT evaluations / restart decisions */
   int     ruiz_iters;       /* Ruiz equilibration passes (then one Pock-Chambolle pass) */
-  int     reserved;
+  int     reserved;         /* 0.  neptune_pdhg_mf_solve reads it as switches for measurements and tests:
+                             * bit 0 = bulk-copy (cp.async.bulk) staged iteration pass, bit 11 = 16-byte accesses,
+                             * bits 8..10 = rows of a warp in flight (0 = default), bits 4..6 = tool diagnostics */
   double  eps_rel;          /* termination: relative KKT tolerance */
   double  eps_abs;
 } neptune_pdhg_params;

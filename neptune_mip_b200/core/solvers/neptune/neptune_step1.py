@@ -49,13 +49,18 @@ class NeptuneStep1CPUBase(NeptuneStepBase):
         inst, alpha = self.inst, self._alpha()
         guide = None
         if self.lp_iters > 0:
-            lp = device.assemble(inst, self.kind, alpha, flags=FLAG_STRENGTHEN)
-            xs, ys, res = device.pdhg_solve(lp, max_iters=self.lp_iters, eps_rel=1e-5)
+            if self.kind == "min_delay":
+                # matrix-free relaxation of the strengthened min-delay model (nothing is assembled)
+                xs, ys, res = device.pdhg_mf_solve(inst, max_iters=self.lp_iters, eps_rel=1e-5)
+            else:
+                lp = device.assemble(inst, self.kind, alpha, flags=FLAG_STRENGTHEN)
+                xs, ys, res = device.pdhg_solve(lp, max_iters=self.lp_iters, eps_rel=1e-5)
+                del lp
             X = inst.F * inst.N * inst.N
             guide = xs[:, X:X + inst.F * inst.N].contiguous()
             self.lp_result = res[0]
             self.lp_bound = float(res[0]["dual_obj"])
-            del lp, xs, ys
+            del xs, ys
         seeds = [device.efttc(inst, k, alpha)[0] for k in ("min_delay", "min_util", "min_delay_util")]
         seeds = torch.stack(seeds, dim=1).contiguous()                       # [1, 3, F, N]
         best_c, best_obj, _ = device.local_search(inst, self.kind, seeds, alpha, self.chains, self.sweeps,
