@@ -248,3 +248,108 @@ def run_fixed(a, iters):
     _, p2, d2, po, do = cands[pick]
     return x, y, dict(pick=pick, primal_obj=po, dual_obj=do, primal_res=float(np.sqrt(p2)), dual_res=float(np.sqrt(d2)),
                       omega=mf.omega, kkt=(cands[0][0], cands[1][0]))
+
+
+class ShardedMatrixFree:
+    """Function-block-sharded form of `MatrixFree` (the plan for C4 on 8 GPUs): a rank
+    owns the functions [f0, f1), i.e. x[f,:,:], c[f,:], y1[f,:], y3[f,:], yS[f,:,:] of those functions; the 2N
+    multipliers of the coupling rows (y2: memory, y4: CPU) are replicated.  ONE exchange per iteration: the
+    all-reduce of [sum_{own f,i} w r xbar (N) | sum_{own f} m cbar (N)] -- the C4 activity of the pass that just
+    ran and the C2 activity of the c columns just updated.  `allreduce(vec)` sums a numpy vector over the ranks
+    in place.  The KKT evaluation all-reduces the two activity vectors and four scalars; the replicated rows'
+    terms are added once (by the rank with f0 == 0)."""
+
+    def __init__(self, a, f0, f1, allreduce):
+        self.full = MatrixFree(a)                      # closed-form tables and norms of the whole instance (host)
+        self.f0, self.f1, self.allreduce = f0, f1, allreduce
+        self.a, self.N = a, a["N"]
+        sl = slice(f0, f1)
+        F = self.full
+        self.wr, self.obj, self.Tx, self.Tc = F.wr[sl], F.obj[sl], F.Tx[sl], F.Tc[sl]
+        self.m = a["m"][sl]
+        self.S1, self.S2, self.S3, self.S4, self.SS = F.S1, F.S2, F.S3, F.S4, F.SS
+        self.omega, self.eta, self.nb, self.nc = F.omega, F.eta, F.nb, F.nc   # global numbers: every rank computes them alike
+        Fg, N = f1 - f0, self.N
+        z = np.zeros
+        self.x, self.c = z((Fg, N, N)), z((Fg, N))
+        self.y1, self.y3, self.yS = z((Fg, N)), z((Fg, N)), z((Fg, N, N))
+        self.y2, self.y4 = z(N), z(N)                 # replicated
+        self.sS = z((Fg, N))
+        self.a4_part = z(N)                           # C4 activity of the last pass, own functions
+        self.first = True
+        self.exchanged_doubles = 0
+
+    def step(self):
+        a, N = self.a, self.N
+        tau, sig = self.eta / self.omega, self.eta * self.omega
+        # boundary work of the previous pass that is local: nothing pending on the very first step
+        # c columns of this iteration (y1, sS local; y2 replicated and already global)
+        gc = -self.y1 + self.m[:, None] * self.y2[None, :] - self.sS
+        cn = np.clip(self.c - tau * self.Tc * gc, 0.0, 1.0)
+        cb = 2 * cn - self.c
+        self.c = cn
+        # the one exchange: C4 activity of the previous pass | C2 activity of the new c columns
+        buf = np.concatenate([self.a4_part, self.m @ cb])
+        self.allreduce(buf)
+        self.exchanged_doubles += buf.size
+        a4, a2 = buf[:N], buf[N:]
+        if not self.first:                            # y4 of the previous iteration (replicated update)
+            s = self._sig_prev * self.S4
+            v = self.y4 + s * a4
+            self.y4 = v - s * np.minimum(v / s, a["Kj"])
+        s = sig * self.S2
+        v = self.y2 + s * a2
+        y2n = v - s * np.minimum(v / s, a["Mj"])
+        # the pass over the own functions
+        g = self.obj + self.y1[:, None, :] + self.y3[:, :, None] + self.wr * self.y4[None, None, :] + self.yS
+        xn = np.clip(self.x - tau * self.Tx * g, 0.0, 1.0)
+        xb = 2 * xn - self.x
+        self.yS = np.maximum(self.yS + sig * self.SS * (xb - cb[:, None, :]), 0.0)
+        self.x = xn
+        self.sS = self.yS.sum(axis=1)
+        # local duals of this iteration; the C4 activity waits for the next exchange
+        s = sig * self.S1
+        v = self.y1 + s * (xb.sum(axis=1) - cb)
+        self.y1 = v - s * np.maximum(v / s, -EPS)
+        s = sig * self.S3
+        self.y3 = self.y3 + s * xb.sum(axis=2) - s
+        self.a4_part = (self.wr * xb).sum(axis=(0, 1))
+        self.y2 = y2n
+        self._sig_prev = sig
+        self.first = False
+
+    def flush(self):
+        """apply the pending C4 dual update (end of a chunk: the state becomes a consistent PDHG iterate)"""
+        if self.first:
+            return
+        buf = self.a4_part.copy()
+        self.allreduce(buf)
+        self.exchanged_doubles += buf.size
+        s = self._sig_prev * self.S4
+        v = self.y4 + s * buf
+        self.y4 = v - s * np.minimum(v / s, self.a["Kj"])
+        self.a4_part[:] = 0.0
+        self.first = True
+
+    def kkt(self):
+        """global KKT pieces of the current iterate (same numbers on every rank)"""
+        a = self.a
+        x, c, y1, y2, y3, y4, yS = self.x, self.c, self.y1, self.y2, self.y3, self.y4, self.yS
+        act = np.concatenate([(self.wr * x).sum(axis=(0, 1)), self.m @ c])
+        self.allreduce(act)
+        a4, a2 = act[:self.N], act[self.N:]
+        p2 = np.sum(np.minimum(x.sum(axis=1) - c + EPS, 0) ** 2) + np.sum((x.sum(axis=2) - 1) ** 2)
+        p2 += np.sum(np.maximum(x - c[:, None, :], 0) ** 2)
+        d2 = np.sum(np.maximum(y1, 0) ** 2) + np.sum(np.minimum(yS, 0) ** 2)
+        dobj = EPS * np.sum(np.minimum(y1, 0)) - np.sum(y3)
+        rcx = self.obj + y1[:, None, :] + y3[:, :, None] + self.wr * y4[None, None, :] + yS
+        rcc = -y1 + self.m[:, None] * y2[None, :] - yS.sum(axis=1)
+        dobj += np.sum(np.minimum(rcx, 0)) + np.sum(np.minimum(rcc, 0))
+        pobj = float(np.sum(self.obj * x))
+        if self.f0 == 0:                              # replicated rows: counted once
+            p2 += np.sum(np.maximum(a2 - a["Mj"], 0) ** 2) + np.sum(np.maximum(a4 - a["Kj"], 0) ** 2)
+            d2 += np.sum(np.minimum(y2, 0) ** 2) + np.sum(np.minimum(y4, 0) ** 2)
+            dobj += -np.sum(a["Mj"] * np.maximum(y2, 0)) - np.sum(a["Kj"] * np.maximum(y4, 0))
+        v = np.array([p2, d2, pobj, dobj])
+        self.allreduce(v)
+        return tuple(float(t) for t in v)
