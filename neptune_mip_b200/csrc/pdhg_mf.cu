@@ -327,6 +327,149 @@ k_mf_iter_vec(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
   }
 }
 
+// EXPERIMENTAL (opt-in, reserved bit 12; written after the round's GPU budget was spent -- parity tests are
+// gated by NEPTUNE_EXPERIMENTAL until it has run on a B200): the register pass with its four streams prefetched
+// by cp.async (LDGSTS, 16 bytes per lane) into a per-thread ring of D rows in shared memory.  A lane copies
+// and later reads only its own 16-byte slots, so no barrier is involved: shared memory acts as an asynchronous
+// extension of the register file -- D-1 rows of loads stay in flight while a row is computed (the ncu profile
+// of k_mf_iter shows a pass that waits on its own loads with 16-24 resident warps).  Results are stored from
+// registers.  Same tiles, partial-sum layout and per-column summation order as k_mf_iter<2*KV, .> (even N > 32).
+constexpr int kAsyncDepth = 3;
+
+template <int KV>
+__global__ void __launch_bounds__(kMfThreads, (KV == 1 ? 3 : 2))
+k_mf_iter_async(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
+  constexpr int K = 2 * KV, JT = 64 * KV, D = kAsyncDepth;
+  extern __shared__ __align__(16) double ring[];                         // [warps][D][4][JT]
+  __shared__ double sm[3][kMfWarps][32 * K];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = G.N;
+  const int64_t NN = (int64_t)N * N;
+  const int64_t total = (int64_t)B * G.tiles_inst;
+  double* const myring = ring + (size_t)warp * D * 4 * JT;
+  for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const Tile t = decode_tile(G, tile);
+    const int b = t.b, f = t.f;
+    if (ctl[b].converged) continue;
+    const double tau = ctl[b].tau, shalf = 0.5 * ctl[b].sigma;
+    const double* __restrict__ d = in.d + (int64_t)b * NN;
+    const double* __restrict__ w = in.w + ((int64_t)b * G.F + f) * N;
+    const double* __restrict__ r = in.r + ((int64_t)b * G.F + f) * N;
+    const double* __restrict__ y = st.y + (int64_t)b * G.rows;
+    const double* __restrict__ y3 = y + G.r3 + (int64_t)f * N;
+    double* __restrict__ xp = st.x + (int64_t)b * G.cols + (int64_t)f * NN;
+    double* __restrict__ xsp = st.xsum + (int64_t)b * G.cols + (int64_t)f * NN;
+    double* __restrict__ sp = st.y + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
+    double* __restrict__ ssp = st.ysum + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
+    const double* __restrict__ cbar = st.cbar + (int64_t)b * G.C + (int64_t)f * N;
+    double* __restrict__ P3 = st.P3i + ((int64_t)b * G.C + (int64_t)f * N) * G.cti + t.jt;
+
+    int jj[KV]; bool vj[KV];
+    double y1j[K], rj[K], rr4[K], cb[K];
+#pragma unroll
+    for (int k = 0; k < KV; ++k) {
+      const int j = t.jt * G.JT + k * 64 + 2 * lane;
+      vj[k] = j < N; jj[k] = vj[k] ? j : 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = 2 * k + h, jc = jj[k] + h;
+        y1j[c] = y[2 * ((int64_t)f * N + jc) + 1];
+        rj[c] = __ldg(r + jc);
+        rr4[c] = rj[c] * y[G.r4 + jc];
+        cb[c] = cbar[jc];
+      }
+    }
+    double a1[K], a4[K], aS[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) { a1[c] = 0.0; a4[c] = 0.0; aS[c] = 0.0; }
+
+    const int i0 = t.it * G.RT, i1 = min(N, i0 + G.RT);
+    const int nrows = (i1 - i0 - warp + kMfWarps - 1) / kMfWarps;          // rows of this warp: i0 + warp + 8 n
+    auto issue = [&](int n) {                                              // copies of row n into slot n % D
+      if (n < nrows) {
+        const int o = (i0 + warp + n * kMfWarps) * N;
+        double* slot = myring + (size_t)(n % D) * 4 * JT;
+#pragma unroll
+        for (int k = 0; k < KV; ++k) {
+          if (vj[k]) {
+            const int c = k * 64 + 2 * lane;
+            const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(slot + c);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0), "l"(xp + o + jj[k]) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + JT * 8), "l"(sp + o + jj[k]) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 2 * JT * 8), "l"(xsp + o + jj[k]) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 3 * JT * 8), "l"(ssp + o + jj[k]) : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");                 // one group per row, empty ones included
+    };
+#pragma unroll
+    for (int n = 0; n < D - 1; ++n) issue(n);
+    for (int n = 0; n < nrows; ++n) {
+      issue(n + D - 1);
+      asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");     // this thread's copies of row n have landed
+      const int i = i0 + warp + n * kMfWarps;
+      const int o = i * N;
+      const double wfi = __ldg(w + i), y3i = y3[i];
+      const double* slot = myring + (size_t)(n % D) * 4 * JT;
+      double rsum = 0.0;
+#pragma unroll
+      for (int k = 0; k < KV; ++k) {
+        if (vj[k]) {
+          const int c0 = k * 64 + 2 * lane;
+          const double2 xv = *reinterpret_cast<const double2*>(slot + c0);
+          const double2 sv = *reinterpret_cast<const double2*>(slot + JT + c0);
+          const double2 xs = *reinterpret_cast<const double2*>(slot + 2 * JT + c0);
+          const double2 ss = *reinterpret_cast<const double2*>(slot + 3 * JT + c0);
+          const double2 dd = __ldg(reinterpret_cast<const double2*>(d + o + jj[k]));
+          const double xin[2] = {xv.x, xv.y}, sin_[2] = {sv.x, sv.y}, din[2] = {dd.x, dd.y};
+          double xo[2], so[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = 2 * k + h;
+            const double wr = fabs(wfi * rj[c]);
+            const double g = __dmul_rn(din[h], wfi) + y1j[c] + y3i + wfi * rr4[c] + sin_[h];
+            double xn = xin[h] - tau * g / (3.0 + wr);
+            xn = fmin(fmax(xn, 0.0), 1.0);
+            const double xb = 2.0 * xn - xin[h];
+            const double sn = fmax(sin_[h] + shalf * (xb - cb[c]), 0.0);
+            xo[h] = xn; so[h] = sn;
+            a1[c] += xb; a4[c] += wfi * xb; aS[c] += sn; rsum += xb;
+          }
+          *reinterpret_cast<double2*>(xp + o + jj[k]) = make_double2(xo[0], xo[1]);
+          *reinterpret_cast<double2*>(sp + o + jj[k]) = make_double2(so[0], so[1]);
+          *reinterpret_cast<double2*>(xsp + o + jj[k]) = make_double2(xs.x + xo[0], xs.y + xo[1]);
+          *reinterpret_cast<double2*>(ssp + o + jj[k]) = make_double2(ss.x + so[0], ss.y + so[1]);
+        }
+      }
+      rsum = warp_sum(rsum);
+      if (lane == 0) P3[(int64_t)i * G.cti] = rsum;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < KV; ++k) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = 2 * k + h, col = k * 64 + 2 * lane + h;
+        sm[0][warp][col] = a1[c]; sm[1][warp][col] = a4[c]; sm[2][warp][col] = aS[c];
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 32 * K; c += kMfThreads) {
+      const int j = t.jt * G.JT + c;
+      if (j < N) {
+        const int64_t o = (((int64_t)b * G.F + f) * G.rt + t.it) * N + j;
+        st.P1[o] = column_total<K>(sm[0], c);
+        st.P4[o] = __ldg(r + j) * column_total<K>(sm[1], c);
+        st.PS[o] = column_total<K>(sm[2], c);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int KV> constexpr size_t async_smem_bytes() { return (size_t)kMfWarps * kAsyncDepth * 4 * 64 * KV * 8; }
+
 // ---------------------------------------------------------------------------------------------------
 // the iteration pass, TMA version (even N): x and yS of a tile are contiguous in memory, so they are staged
 // in shared memory by 1-D bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP), five stages deep -- those bytes
@@ -1075,6 +1218,7 @@ struct MfPlan {
   int use_tma; TmaGeo T;
   int rows_in_flight;            // U of k_mf_iter<K, U>
   int vec;                       // k_mf_iter_vec (16-byte accesses) instead of k_mf_iter
+  int async_copy;                // k_mf_iter_async (experimental)
   int diag;                      // tools only: bits of params->reserved >> 4 switch parts of the TMA pass off
 };
 
@@ -1093,6 +1237,12 @@ static void mf_launch_iter(const MfPlan& P) {
   }
   const int64_t total = (int64_t)P.B * P.G.tiles_inst;
   const int g = (int)(total < P.grid_iter ? total : P.grid_iter);
+  if (P.async_copy) {
+    if (P.G.K == 2) k_mf_iter_async<1><<<g, kMfThreads, async_smem_bytes<1>(), P.s>>>(P.G, P.in, P.st, P.ctl, P.B);
+    else k_mf_iter_async<2><<<g, kMfThreads, async_smem_bytes<2>(), P.s>>>(P.G, P.in, P.st, P.ctl, P.B);
+    NEPTUNE_COUNT(1);
+    return;
+  }
   if (P.vec) {
     switch (P.G.K * 10 + P.rows_in_flight) {
       case 22: k_mf_iter_vec<1, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
@@ -1198,7 +1348,19 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
   // per warp: reserved bits 8..10 override (tools), default by K
   P.vec = (prm->reserved & 0x800) && !(N & 1) && G.K >= 2 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
   P.rows_in_flight = (prm->reserved >> 8) & 7;
-  if (P.vec) {
+  P.async_copy = (prm->reserved & 0x1000) && !(N & 1) && G.K >= 2 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  if (P.async_copy) {
+    P.vec = 0;
+    int occ = 0;
+    if (G.K == 2) {
+      NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_mf_iter_async<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)async_smem_bytes<1>()));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mf_iter_async<1>, kMfThreads, async_smem_bytes<1>());
+    } else {
+      NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_mf_iter_async<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)async_smem_bytes<2>()));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mf_iter_async<2>, kMfThreads, async_smem_bytes<2>());
+    }
+    P.grid_iter = kNumSMs * (occ < 1 ? 1 : occ);
+  } else if (P.vec) {
     if (G.K == 2 && P.rows_in_flight != 2 && P.rows_in_flight != 4) P.rows_in_flight = 2;
     if (G.K == 4 && P.rows_in_flight != 1 && P.rows_in_flight != 2) P.rows_in_flight = 1;
     switch (G.K * 10 + P.rows_in_flight) {
