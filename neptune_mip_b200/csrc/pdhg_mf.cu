@@ -21,8 +21,13 @@
 // k_mf_small: the F*N-sized updates -- duals y1/y3/y4 from the partial sums (POST), then the c columns of the
 //   next iteration (PREC) and the C2 dual (Y2).
 // Algorithmic bytes per iteration and instance: X*(8 x + 8 yS + 8 xsum + 8 ysum read, the same written)
-//   = 64*X, + 8*N*N (d, re-read per function from L2) + O(F*N)  [X = F*N*N]; the CSR solver moves
-//   16*nnz + 88*cols + 72*rows ~ 260*X for the same iteration.
+//   = 64*X, + 112*F*N (small vectors) + 8*N*N (d, re-read per function from L1/L2)  [X = F*N*N]; the CSR solver
+//   moves 16*nnz + 88*cols + 72*rows ~ 260*X for the same iteration.
+//
+// Iteration-pass variants (all parity-tested against the numpy statement, tests/test_pdhg_mf_gpu.py; measurements in
+// profiles/r01f_summary.md): k_mf_iter<K, U> (default: lanes own K columns, U rows of a warp in flight),
+// k_mf_iter_vec (16-byte accesses), k_mf_iter_tma (cp.async.bulk + mbarrier staging), k_mf_iter_async
+// (experimental cp.async ring) -- selected by bits of params.reserved, see include/neptune_b200.h.
 #include "common.cuh"
 #include "pdhg_ctl.cuh"
 
