@@ -58,3 +58,20 @@ def test_run_fixed_reports_the_better_candidate():
     N, F = a["N"], a["F"]
     assert x.shape == (F * N * N + F * N,) and y.shape == (3 * F * N + 2 * N + F * N * N,)
     assert np.all(y[0:2 * F * N:2] == 0.0)                      # free C1a rows carry no multiplier
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_lp_value_sweep_against_highs(seed):
+    """random shapes (odd / even N, slack and binding CPU rows): the restarted, averaged iteration in its
+    matrix-free form converges to the HiGHS optimum of the oracle's strengthened matrix, primal and dual side"""
+    rng = np.random.default_rng(100 + seed)
+    N, F = int(rng.integers(3, 14)), int(rng.integers(1, 6))
+    cores = int(rng.choice([8, 15, 30, 200]))
+    a = arrays_of(synth.random_payload(N, F, seed, node_cores=cores))
+    lp = omip.solve_model(strengthened(a), relax=True)
+    if not lp["optimal"]:
+        pytest.skip("relaxation infeasible for this draw")
+    out = solve(MatrixFree(a), max_iters=80000, check=64, eps=1e-6)
+    assert out["converged"], (N, F, cores, out)
+    tol = 1e-4 * (1 + abs(lp["objective"]))
+    assert abs(out["primal"] - lp["objective"]) <= tol and abs(out["dual"] - lp["objective"]) <= tol, (N, F, cores, out, lp["objective"])
