@@ -147,7 +147,7 @@ def run_ours(args):
 
     B = args.batch
     prm = BatchParams(kind="min_delay", lp_iters=args.lp_iters, lp_check_every=args.lp_iters,
-                      chains=args.chains, sweeps=args.sweeps)
+                      chains=args.chains, sweeps=args.sweeps, lp_path=args.lp_path)
     # instances are sharded across ranks by seed (weak scaling: B per GPU): rank r owns the contiguous block
     # sharding.shard_range(world*B, r, world) = [r*B, (r+1)*B) -- no data-path collective
     from neptune_mip_b200 import sharding
@@ -303,6 +303,8 @@ def main():
     ap.add_argument("--lp-iters", type=int, default=2048)
     ap.add_argument("--chains", type=int, default=8)
     ap.add_argument("--sweeps", type=int, default=400)
+    ap.add_argument("--lp-path", default="auto", choices=["auto", "csr"],
+                    help="auto: matrix-free PDHG (default); csr: assemble the model and run the CSR solver (round-1 a-e path)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ref-limit", type=float, default=20.0, help="--impl reference: HiGHS cap per instance (s)")
     ap.add_argument("--ref-instances", type=int, default=0, help="--impl reference: instances per step (0 = one per worker)")

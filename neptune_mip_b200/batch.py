@@ -18,6 +18,7 @@ class BatchParams:
     alpha: float = 0.5
     lp_iters: int = 2048          # PDHG iterations on the strengthened relaxation (bound + rounding guide)
     lp_check_every: int = 256
+    lp_path: str = "auto"         # "auto": matrix-free PDHG for the min-delay model, assembled CSR otherwise; "csr": always CSR
     chains: int = 16              # local-search chains per instance
     sweeps: int = 200
     rng_seed: int = 1
@@ -47,7 +48,7 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
         X = F * N * N
         if time_pdhg:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if KINDS.get(kind, kind) == 0:
+        if KINDS.get(kind, kind) == 0 and prm.lp_path != "csr":
             # min-delay: the relaxation is solved matrix-free (nothing is assembled; every coefficient of the
             # strengthened model is regenerated from d, w, r, m inside the iteration kernels)
             rows, cols, nnz = device.model_sizes(N, F, 0, FLAG_STRENGTHEN)
