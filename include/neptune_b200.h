@@ -156,6 +156,31 @@ int neptune_pdhg_mf_solve(int B, int N, int F, int kind,
                           double* x, double* y, neptune_pdhg_result* result_d,
                           void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- (b, matrix-free, sharded) EXPERIMENTAL: step-wise building blocks of the matrix-free iteration for the
+ * function-block-sharded solver (neptune_mip_b200/sharded_mf.py, one process per GPU).  Not yet
+ * run on a GPU (written after round 1's GPU budget was spent); the numpy statement they follow is
+ * tests/mf_reference.ShardedMatrixFree.  F = functions of THIS rank; x / y / xsum / ysum are the canonical vectors of
+ * the rank's local model; S4[B][N], S2[B] are the GLOBAL Pock-Chambolle row scalings (caller all-reduces the sums);
+ * coupling[B][2N] = [C4 activity of the pending pass | C2 activity of the new cbar] over the own functions.
+ *   column_sums : once before the first local step (and after y was replaced): column sums of yS
+ *   local_step  : y1, y3 of the pending pass (have_pass), c columns of the next iteration (do_prec), coupling out
+ *   (caller: all-reduce of coupling)
+ *   pass        : y4 (have_pass, step sigma_prev) and y2 (run_pass, step sigma) from the global activities, then the
+ *                 iteration pass over the own functions (run_pass) */
+int neptune_pdhg_mf_step_bytes(int B, int N, int F, int64_t* bytes);
+int neptune_pdhg_mf_column_sums(int B, int N, int F, const double* w, const double* r, const double* m,
+                                double* x, double* y, double* xsum, double* ysum, const double* S4, const double* S2,
+                                void* workspace, int64_t workspace_bytes, void* stream);
+int neptune_pdhg_mf_local_step(int B, int N, int F, const double* w, const double* r, const double* m,
+                               double tau, double sigma_prev, int have_pass, int do_prec,
+                               double* x, double* y, double* xsum, double* ysum, const double* S4, const double* S2,
+                               void* workspace, int64_t workspace_bytes, double* coupling, void* stream);
+int neptune_pdhg_mf_pass(int B, int N, int F, const double* d, const double* w, const double* r, const double* m,
+                         const double* Mj, const double* Kj, double tau, double sigma, double sigma_prev,
+                         int have_pass, int run_pass, double* x, double* y, double* xsum, double* ysum,
+                         const double* S4, const double* S2, void* workspace, int64_t workspace_bytes,
+                         const double* coupling_sum, void* stream);
+
 /* ---- (b') step-wise PDHG building blocks for the function-block-sharded solver (one process per GPU,
  * SURVEY.md section 8(e)): GPU g owns the functions of its block, i.e. the x / c columns and the C1 / C3
  * rows of those functions; the coupling rows (C2 memory, C4 CPU) are replicated, every GPU computes

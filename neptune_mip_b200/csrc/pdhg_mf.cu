@@ -1490,3 +1490,218 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
   cudaStreamDestroy(s);
   return 0;
 }
+
+// ===================================================================================================
+// EXPERIMENTAL -- step-wise building blocks for the function-block-sharded matrix-free PDHG (SURVEY.md
+// section 8(e); one process per GPU, neptune_mip_b200/sharded_mf.py owns the loop and the all-reduce).
+// Written after the round's GPU budget was spent: NOT YET RUN on a GPU; the numpy statement it follows
+// (tests/mf_reference.ShardedMatrixFree) is proven equal to the unsharded iteration on 2 gloo ranks.
+// A rank holds the functions of its block (F = functions of this rank); the 2N multipliers of the coupling
+// rows (y2: C2 memory, y4: C4 CPU) are replicated.  Per iteration:
+//   neptune_pdhg_mf_local_step : y1, y3 of the pass that just ran (local), c columns of the next iteration
+//                                (local), coupling[2N] = [C4 activity of that pass | C2 activity of the new cbar]
+//   (caller: all-reduce of coupling over the ranks -- 2N doubles)
+//   neptune_pdhg_mf_pass       : y4, y2 from the global activities (replicated), then the iteration pass
+//                                (k_mf_iter, unchanged) over the own functions.
+// Step sizes are host scalars; S4[N], S2[1] (global Pock-Chambolle row sums) come from the caller.
+// ===================================================================================================
+namespace neptune {
+
+struct MfStepWs { size_t cbar, P1, P4, PS, P3i, ctl, total; };
+
+static MfStepWs mf_step_layout(int B, const MfGeo& G) {
+  MfStepWs W; size_t t = 0;
+  auto take = [&](size_t bytes) { size_t o = t; t += mf_align(bytes); return o; };
+  const size_t pb = (size_t)B * G.F * G.rt * G.N * 8;
+  W.cbar = take((size_t)B * G.C * 8);
+  W.P1 = take(pb); W.P4 = take(pb); W.PS = take(pb);
+  W.P3i = take((size_t)B * G.C * G.ct * 8);
+  W.ctl = take((size_t)B * sizeof(Ctl));
+  W.total = t + 256;
+  return W;
+}
+
+__global__ void k_mf_set_steps(int B, Ctl* ctl, double tau, double sigma) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  ctl[b].tau = tau; ctl[b].sigma = sigma; ctl[b].converged = 0;
+}
+
+// local part of the small-vector work of a rank: POST without the C4 dual (have_pass), PREC always
+__global__ void __launch_bounds__(256)
+k_mf_shard_local(MfGeo G, MfIn in, MfSt st, double tau, double sigma_prev, int have_pass, int do_prec) {
+  const int b = blockIdx.y;
+  const int N = G.N, rt = G.rt, ct = G.cti;
+  const int C = (int)G.C;
+  double* __restrict__ y = st.y + (int64_t)b * G.rows;
+  double* __restrict__ ys = st.ysum + (int64_t)b * G.rows;
+  double* __restrict__ c = st.x + (int64_t)b * G.cols + G.X;
+  double* __restrict__ cs = st.xsum + (int64_t)b * G.cols + G.X;
+  double* __restrict__ cbar = st.cbar + (int64_t)b * C;
+  const double* __restrict__ P1 = st.P1 + (int64_t)b * G.F * rt * N;
+  const double* __restrict__ PS = st.PS + (int64_t)b * G.F * rt * N;
+  const double* __restrict__ P3 = st.P3i + (int64_t)b * C * ct;
+  const double* __restrict__ m = in.m + (int64_t)b * G.F;
+  const double s1 = sigma_prev / (double)(N + 1), s3 = sigma_prev / (double)N;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < C; q += gridDim.x * blockDim.x) {
+    const int f = q / N, j = q - f * N;
+    const int64_t po = (int64_t)f * rt * N + j;
+    double y1 = y[2 * q + 1];
+    double sS = 0.0;
+    if (have_pass) {
+      const double a1 = strided_sum(P1 + po, rt, N) - cbar[q];
+      const double a3 = strided_sum(P3 + (int64_t)q * ct, ct, 1);
+      const double v1 = y1 + s1 * a1;
+      y1 = v1 - s1 * fmax(v1 / s1, -kEps);
+      y[2 * q + 1] = y1; ys[2 * q + 1] += y1;
+      const double y3n = y[G.r3 + q] + s3 * a3 - s3;
+      y[G.r3 + q] = y3n; ys[G.r3 + q] += y3n;
+      sS = strided_sum(PS + po, rt, N);
+    } else {
+      sS = strided_sum(PS + po, rt, N);            // PS of the starting yS (filled by neptune_pdhg_mf_column_sums)
+    }
+    if (!do_prec) continue;                        // end of a chunk: the c columns stay where they are
+    const double mf = m[f];
+    const double gc = -y1 + mf * y[G.r2 + j] - sS;
+    const double co = c[q];
+    double cn = co - tau * gc / (1.0 + mf + (double)N);
+    cn = fmin(fmax(cn, 0.0), 1.0);
+    cbar[q] = 2.0 * cn - co;
+    c[q] = cn; cs[q] += cn;
+  }
+}
+
+// coupling[b][0:N] = C4 activity of the pending pass over the own functions (0 without one),
+// coupling[b][N:2N] = C2 activity of the new cbar over the own functions
+__global__ void __launch_bounds__(256)
+k_mf_shard_coupling(MfGeo G, MfIn in, MfSt st, int have_pass, double* __restrict__ coupling) {
+  const int b = blockIdx.y;
+  const int N = G.N, F = G.F;
+  const double* __restrict__ P4 = st.P4 + (int64_t)b * F * G.rt * N;
+  const double* __restrict__ cbar = st.cbar + (int64_t)b * G.C;
+  const double* __restrict__ m = in.m + (int64_t)b * F;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+    coupling[(int64_t)b * 2 * N + j] = have_pass ? strided_sum(P4 + j, F * G.rt, N) : 0.0;
+    double a = 0.0;
+    for (int f0 = 0; f0 < F; f0 += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (f0 + u < F) ? m[f0 + u] * cbar[(int64_t)(f0 + u) * N + j] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a += v[u];
+    }
+    coupling[(int64_t)b * 2 * N + N + j] = a;
+  }
+}
+
+// replicated dual updates from the all-reduced activities: y4 with the step of the pass it belongs to
+// (apply_y4), y2 with the current one (apply_y2)
+__global__ void __launch_bounds__(256)
+k_mf_shard_apply(MfGeo G, MfIn in, MfSt st, double sigma4, double sigma2, int apply_y4, int apply_y2,
+                 const double* __restrict__ coupling) {
+  const int b = blockIdx.y;
+  const int N = G.N;
+  double* __restrict__ y = st.y + (int64_t)b * G.rows;
+  double* __restrict__ ys = st.ysum + (int64_t)b * G.rows;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+    if (apply_y4) {
+      const double s = sigma4 * st.S4[(int64_t)b * N + j];
+      const double v = y[G.r4 + j] + s * coupling[(int64_t)b * 2 * N + j];
+      const double yn = v - s * fmin(v / s, in.Kj[(int64_t)b * N + j]);
+      y[G.r4 + j] = yn; ys[G.r4 + j] += yn;
+    }
+    if (apply_y2) {
+      const double s = sigma2 * st.S2[b];
+      const double v = y[G.r2 + j] + s * coupling[(int64_t)b * 2 * N + N + j];
+      const double yn = v - s * fmin(v / s, in.Mj[(int64_t)b * N + j]);
+      y[G.r2 + j] = yn; ys[G.r2 + j] += yn;
+    }
+  }
+}
+
+static int mf_step_plan(MfPlan& P, int B, int N, int F, const double* d, const double* w, const double* r,
+                        const double* m, const double* Mj, const double* Kj, double* x, double* y, double* xsum,
+                        double* ysum, const double* S4, const double* S2, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  if (B <= 0 || N <= 0 || F <= 0 || !w || !r || !m || !x || !y || !xsum || !ysum || !S4 || !S2 || !ws) return NEPTUNE_E_ARG;
+  P = MfPlan{};
+  P.B = B; P.G = make_geo(N, F, B); P.s = s;
+  const MfStepWs W = mf_step_layout(B, P.G);
+  if (ws_bytes < (int64_t)W.total) return NEPTUNE_E_NOMEM;
+  char* base = (char*)ws;
+  P.in = MfIn{d, w, r, m, Mj, Kj};
+  P.ctl = (Ctl*)(base + W.ctl);
+  P.st = MfSt{x, y, xsum, ysum, (double*)(base + W.cbar), (double*)(base + W.P1), (double*)(base + W.P4),
+              (double*)(base + W.PS), nullptr, (double*)(base + W.P3i), const_cast<double*>(S4),
+              const_cast<double*>(S2), nullptr, nullptr};
+  P.rows_in_flight = P.G.K == 4 ? 1 : 2;
+  switch (P.G.K * 10 + P.rows_in_flight) {
+    case 12: P.grid_iter = mf_grid(k_mf_iter<1, 2>); break;
+    case 22: P.grid_iter = mf_grid(k_mf_iter<2, 2>); break;
+    default: P.grid_iter = mf_grid(k_mf_iter<4, 1>); break;
+  }
+  switch (P.G.K) {
+    case 1: P.grid_eval = mf_grid(k_mf_eval<1>); break;
+    case 2: P.grid_eval = mf_grid(k_mf_eval<2>); break;
+    default: P.grid_eval = mf_grid(k_mf_eval<4>); break;
+  }
+  P.small_blocks = (int)((P.G.C + 255) / 256 < 4 * kNumSMs ? (P.G.C + 255) / 256 : 4 * kNumSMs);
+  return 0;
+}
+
+}  // namespace neptune
+
+extern "C" int neptune_pdhg_mf_step_bytes(int B, int N, int F, int64_t* bytes) {
+  if (B <= 0 || N <= 0 || F <= 0 || !bytes) return NEPTUNE_E_ARG;
+  Layout L(N, F, NEPTUNE_KIND_MIN_DELAY, NEPTUNE_FLAG_STRENGTHEN);
+  if (L.cols >= (int64_t)INT32_MAX || L.rows >= (int64_t)INT32_MAX) return NEPTUNE_E_SIZE;
+  *bytes = (int64_t)mf_step_layout(B, make_geo(N, F, B)).total;
+  return 0;
+}
+
+// PS <- column sums of the current yS (call once before the first local step, and after y was replaced)
+extern "C" int neptune_pdhg_mf_column_sums(int B, int N, int F, const double* w, const double* r, const double* m,
+                                           double* x, double* y, double* xsum, double* ysum, const double* S4,
+                                           const double* S2, void* ws, int64_t ws_bytes, void* stream) {
+  MfPlan P;
+  { int rc = mf_step_plan(P, B, N, F, nullptr, w, r, m, nullptr, nullptr, x, y, xsum, ysum, S4, S2, ws, ws_bytes,
+                          (cudaStream_t)stream); if (rc) return rc; }
+  { k_mf_set_steps<<<(B + 127) / 128, 128, 0, P.s>>>(B, P.ctl, 0.0, 0.0); NEPTUNE_COUNT(1); }
+  mf_launch_eval(P, 0, 1);
+  NEPTUNE_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int neptune_pdhg_mf_local_step(int B, int N, int F, const double* w, const double* r, const double* m,
+                                          double tau, double sigma_prev, int have_pass, int do_prec, double* x, double* y,
+                                          double* xsum, double* ysum, const double* S4, const double* S2, void* ws,
+                                          int64_t ws_bytes, double* coupling, void* stream) {
+  if (!coupling) return NEPTUNE_E_ARG;
+  MfPlan P;
+  { int rc = mf_step_plan(P, B, N, F, nullptr, w, r, m, nullptr, nullptr, x, y, xsum, ysum, S4, S2, ws, ws_bytes,
+                          (cudaStream_t)stream); if (rc) return rc; }
+  dim3 g(P.small_blocks, B), gn((N + 255) / 256, B);
+  { k_mf_shard_local<<<g, 256, 0, P.s>>>(P.G, P.in, P.st, tau, sigma_prev, have_pass, do_prec); NEPTUNE_COUNT(1); }
+  { k_mf_shard_coupling<<<gn, 256, 0, P.s>>>(P.G, P.in, P.st, have_pass, coupling); NEPTUNE_COUNT(1); }
+  NEPTUNE_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int neptune_pdhg_mf_pass(int B, int N, int F, const double* d, const double* w, const double* r,
+                                    const double* m, const double* Mj, const double* Kj, double tau, double sigma,
+                                    double sigma_prev, int have_pass, int run_pass, double* x, double* y, double* xsum,
+                                    double* ysum, const double* S4, const double* S2, void* ws, int64_t ws_bytes,
+                                    const double* coupling_sum, void* stream) {
+  if (!d || !Mj || !Kj || !coupling_sum) return NEPTUNE_E_ARG;
+  MfPlan P;
+  { int rc = mf_step_plan(P, B, N, F, d, w, r, m, Mj, Kj, x, y, xsum, ysum, S4, S2, ws, ws_bytes,
+                          (cudaStream_t)stream); if (rc) return rc; }
+  dim3 gn((N + 255) / 256, B);
+  // run_pass = 0: end of a chunk -- only the pending C4 dual is applied (the C2 half of coupling_sum is ignored)
+  { k_mf_shard_apply<<<gn, 256, 0, P.s>>>(P.G, P.in, P.st, sigma_prev, sigma, have_pass, run_pass, coupling_sum); NEPTUNE_COUNT(1); }
+  if (run_pass) {
+    { k_mf_set_steps<<<(B + 127) / 128, 128, 0, P.s>>>(B, P.ctl, tau, sigma); NEPTUNE_COUNT(1); }
+    mf_launch_iter(P);
+  }
+  NEPTUNE_LAUNCH_OK();
+  return 0;
+}
