@@ -81,6 +81,7 @@ struct MfSt {
   double *S2;                    // [B]           1 / sum_f |m|
   double *wsum;                  // [B][F]        sum_i |w[f,i]|
   double *scal;                  // [B][tiles_inst][4] per-tile scalars of the KKT evaluation / setup
+  int *cnt;                      // [B][2] fused pass only: tiles finished in this launch, iterations done in the chunk
 };
 
 constexpr int kMfThreads = 256;
@@ -474,6 +475,195 @@ k_mf_iter_async(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
 }
 
 template <int KV> constexpr size_t async_smem_bytes() { return (size_t)kMfWarps * kAsyncDepth * 4 * 64 * KV * 8; }
+
+// EXPERIMENTAL (opt-in, reserved bit 13; not yet run on a GPU): k_mf_iter<K, U> with the small-vector work
+// folded in.  Every block counts the tiles it finishes per instance; the block that finishes the LAST tile of an
+// instance does that instance's POST (and, unless the chunk ends here, PREC + Y2 of the next iteration) while
+// the other blocks stream other instances -- one launch per iteration instead of two, and the ~11 us of the
+// separate k_mf_small launch disappear into the pass.  Partial sums written by other blocks are read with
+// ld.global.cg after a __threadfence() on both sides of the counter.
+__device__ __forceinline__ double strided_sum_cg(const double* __restrict__ p, int n, int64_t stride) {
+  double a = 0.0;
+  for (int k0 = 0; k0 < n; k0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (k0 + u < n) ? __ldcg(p + (int64_t)(k0 + u) * stride) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a += v[u];
+  }
+  return a;
+}
+
+// block-wide: the work of k_mf_small (same arithmetic, same summation order) for instance b
+__device__ void mf_small_block(const MfGeo& G, const MfIn& in, const MfSt& st, int b, double tau, double sigma,
+                               bool do_next) {
+  const int N = G.N, F = G.F, rt = G.rt, ct = G.cti;
+  const int C = (int)G.C;
+  double* __restrict__ y = st.y + (int64_t)b * G.rows;
+  double* __restrict__ ys = st.ysum + (int64_t)b * G.rows;
+  double* __restrict__ c = st.x + (int64_t)b * G.cols + G.X;
+  double* __restrict__ cs = st.xsum + (int64_t)b * G.cols + G.X;
+  double* __restrict__ cbar = st.cbar + (int64_t)b * C;
+  const double* __restrict__ P1 = st.P1 + (int64_t)b * F * rt * N;
+  const double* __restrict__ P4 = st.P4 + (int64_t)b * F * rt * N;
+  const double* __restrict__ PS = st.PS + (int64_t)b * F * rt * N;
+  const double* __restrict__ P3 = st.P3i + (int64_t)b * C * ct;
+  const double* __restrict__ m = in.m + (int64_t)b * F;
+  const double* __restrict__ Kj = in.Kj + (int64_t)b * N;
+  const double* __restrict__ Mj = in.Mj + (int64_t)b * N;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  for (int j = tid; j < N; j += nth) {                           // C4 dual
+    const double a = strided_sum_cg(P4 + j, F * rt, N);
+    const double s = sigma * st.S4[(int64_t)b * N + j];
+    const double v = y[G.r4 + j] + s * a;
+    const double yn = v - s * fmin(v / s, Kj[j]);
+    y[G.r4 + j] = yn; ys[G.r4 + j] += yn;
+  }
+  const double s1 = sigma / (double)(N + 1), s3 = sigma / (double)N;
+  for (int q = tid; q < C; q += nth) {
+    const int f = q / N, j = q - f * N;
+    const int64_t po = (int64_t)f * rt * N + j;
+    const double a1 = strided_sum_cg(P1 + po, rt, N) - cbar[q];
+    const double a3 = strided_sum_cg(P3 + (int64_t)q * ct, ct, 1);
+    const double v1 = y[2 * q + 1] + s1 * a1;
+    const double y1 = v1 - s1 * fmax(v1 / s1, -kEps);
+    y[2 * q + 1] = y1; ys[2 * q + 1] += y1;
+    const double y3n = y[G.r3 + q] + s3 * a3 - s3;
+    y[G.r3 + q] = y3n; ys[G.r3 + q] += y3n;
+    if (do_next) {                                               // c columns of the next iteration
+      const double sS = strided_sum_cg(PS + po, rt, N);
+      const double mf = m[f];
+      const double gc = -y1 + mf * y[G.r2 + j] - sS;
+      const double co = c[q];
+      double cn = co - tau * gc / (1.0 + mf + (double)N);
+      cn = fmin(fmax(cn, 0.0), 1.0);
+      cbar[q] = 2.0 * cn - co;
+      c[q] = cn; cs[q] += cn;
+    }
+  }
+  if (do_next) {
+    __syncthreads();                                             // every cbar of the instance is written
+    const double s = sigma * st.S2[b];
+    for (int j = tid; j < N; j += nth) {
+      double a = 0.0;
+      for (int f = 0; f < F; ++f) a += m[f] * cbar[(int64_t)f * N + j];
+      const double v = y[G.r2 + j] + s * a;
+      const double yn = v - s * fmin(v / s, Mj[j]);
+      y[G.r2 + j] = yn; ys[G.r2 + j] += yn;
+    }
+  }
+}
+
+template <int K, int U>
+__global__ void __launch_bounds__(kMfThreads, (K * U >= 4 ? 2 : 3))
+k_mf_iter_fused(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, int chunk_len) {
+  __shared__ double sm[3][kMfWarps][32 * K];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = G.N;
+  const int64_t NN = (int64_t)N * N;
+  const int64_t total = (int64_t)B * G.tiles_inst;
+  for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const Tile t = decode_tile(G, tile);
+    const int b = t.b, f = t.f;
+    if (ctl[b].converged) continue;
+    const double tau = ctl[b].tau, sigma = ctl[b].sigma, shalf = 0.5 * sigma;
+    const double* __restrict__ d = in.d + (int64_t)b * NN;
+    const double* __restrict__ w = in.w + ((int64_t)b * G.F + f) * N;
+    const double* __restrict__ r = in.r + ((int64_t)b * G.F + f) * N;
+    const double* __restrict__ y = st.y + (int64_t)b * G.rows;
+    const double* __restrict__ y3 = y + G.r3 + (int64_t)f * N;
+    double* __restrict__ xp = st.x + (int64_t)b * G.cols + (int64_t)f * NN;
+    double* __restrict__ xsp = st.xsum + (int64_t)b * G.cols + (int64_t)f * NN;
+    double* __restrict__ sp = st.y + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
+    double* __restrict__ ssp = st.ysum + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
+    const double* __restrict__ cbar = st.cbar + (int64_t)b * G.C + (int64_t)f * N;
+    double* __restrict__ P3 = st.P3i + ((int64_t)b * G.C + (int64_t)f * N) * G.cti + t.jt;
+
+    int jj[K]; bool vj[K];
+    double y1j[K], rj[K], rr4[K], cb[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int j = t.jt * G.JT + k * 32 + lane;
+      vj[k] = j < N; jj[k] = vj[k] ? j : 0;
+      y1j[k] = y[2 * ((int64_t)f * N + jj[k]) + 1];
+      rj[k] = __ldg(r + jj[k]);
+      rr4[k] = rj[k] * y[G.r4 + jj[k]];
+      cb[k] = cbar[jj[k]];
+    }
+    double a1[K], a4[K], aS[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { a1[k] = 0.0; a4[k] = 0.0; aS[k] = 0.0; }
+
+    const int i0 = t.it * G.RT, i1 = min(N, i0 + G.RT);
+    for (int ib = i0 + warp; ib < i1; ib += U * kMfWarps) {
+      double xv[U][K], sv[U][K], xs[U][K], ss[U][K], dv[U][K], wfi[U], y3i[U];
+      int ro[U]; bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = ib + u * kMfWarps;
+        ok[u] = i < i1;
+        const int ir = ok[u] ? i : ib;
+        ro[u] = ir * N;
+        wfi[u] = __ldg(w + ir); y3i[u] = y3[ir];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int o = ro[u] + jj[k];
+          xv[u][k] = xp[o]; sv[u][k] = sp[o]; xs[u][k] = xsp[o]; ss[u][k] = ssp[o];
+          dv[u][k] = __ldg(d + o);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        double rsum = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (ok[u] && vj[k]) {
+            const int o = ro[u] + jj[k];
+            const double wr = fabs(wfi[u] * rj[k]);
+            const double g = __dmul_rn(dv[u][k], wfi[u]) + y1j[k] + y3i[u] + wfi[u] * rr4[k] + sv[u][k];
+            double xn = xv[u][k] - tau * g / (3.0 + wr);
+            xn = fmin(fmax(xn, 0.0), 1.0);
+            const double xb = 2.0 * xn - xv[u][k];
+            const double sn = fmax(sv[u][k] + shalf * (xb - cb[k]), 0.0);
+            xp[o] = xn; sp[o] = sn;
+            xsp[o] = xs[u][k] + xn; ssp[o] = ss[u][k] + sn;
+            a1[k] += xb; a4[k] += wfi[u] * xb; aS[k] += sn; rsum += xb;
+          }
+        }
+        rsum = warp_sum(rsum);
+        if (lane == 0 && ok[u]) P3[(int64_t)(ib + u * kMfWarps) * G.cti] = rsum;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      sm[0][warp][k * 32 + lane] = a1[k]; sm[1][warp][k * 32 + lane] = a4[k]; sm[2][warp][k * 32 + lane] = aS[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 32 * K; c += kMfThreads) {
+      const int j = t.jt * G.JT + c;
+      if (j < N) {
+        const int64_t o = (((int64_t)b * G.F + f) * G.rt + t.it) * N + j;
+        st.P1[o] = column_total<K>(sm[0], c);
+        st.P4[o] = __ldg(r + j) * column_total<K>(sm[1], c);
+        st.PS[o] = column_total<K>(sm[2], c);
+      }
+    }
+    // ---- tile done: is it the last one of this instance in this launch? ----
+    __threadfence();                                             // the partial sums above are visible device-wide ...
+    __syncthreads();                                             // ... for every thread of the block, before the count
+    if (threadIdx.x == 0) s_last = (atomicAdd(st.cnt + 2 * b, 1) == G.tiles_inst - 1);
+    __syncthreads();
+    if (s_last) {                                                // block-uniform
+      __threadfence();
+      const int done = st.cnt[2 * b + 1] + 1;                    // iterations of the chunk including this one
+      mf_small_block(G, in, st, b, tau, sigma, done < chunk_len);
+      __syncthreads();
+      if (threadIdx.x == 0) { st.cnt[2 * b] = 0; st.cnt[2 * b + 1] = done < chunk_len ? done : 0; }
+    }
+    __syncthreads();
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------
 // the iteration pass, TMA version (even N): x and yS of a tile are contiguous in memory, so they are staged
@@ -1187,7 +1377,7 @@ static inline size_t mf_align(size_t v) { return (v + 255) & ~(size_t)255; }
 constexpr int kMfRestartBlocks = 64;       // blocks per instance of k_mf_apply_restart / k_mf_setup (upper bound)
 
 struct MfWs {
-  size_t xsum, xres, ysum, yres, cbar, P1, P4, PS, P3, P3i, S4, S2, wsum, scal, part, ctl, flag, total;
+  size_t xsum, xres, ysum, yres, cbar, P1, P4, PS, P3, P3i, S4, S2, wsum, scal, part, ctl, flag, cnt, total;
 };
 
 static MfWs mf_layout(int B, const MfGeo& G) {
@@ -1206,6 +1396,7 @@ static MfWs mf_layout(int B, const MfGeo& G) {
   W.part = take((size_t)B * kMfRestartBlocks * 2 * 8);
   W.ctl = take((size_t)B * sizeof(Ctl));
   W.flag = take(256);
+  W.cnt = take((size_t)B * 2 * sizeof(int));
   W.total = t + 256;
   return W;
 }
@@ -1309,6 +1500,204 @@ extern "C" int neptune_pdhg_mf_workspace_bytes(int B, int N, int F, int64_t* byt
   return 0;
 }
 
+// EXPERIMENTAL (reserved bit 13): the solve loop with k_mf_iter_fused -- a copy of neptune_pdhg_mf_solve whose chunk is
+// small(PREC, Y2) once, then check_every launches of the fused pass.  Kept separate so that the default loop
+// below stays exactly what ran on the GPU in round 1.
+static int mf_solve_fused(int B, int N, int F, int kind, const double* d, const double* w,
+                                     const double* r, const double* m, const double* Mj, const double* Kj,
+                                     const neptune_pdhg_params* prm, double* x, double* y,
+                                     neptune_pdhg_result* result_d, void* workspace, int64_t workspace_bytes,
+                                     void* stream) {
+  if (B <= 0 || N <= 0 || F <= 0) return NEPTUNE_E_ARG;
+  if (kind != NEPTUNE_KIND_MIN_DELAY) return NEPTUNE_E_ARG;      // the n columns / C5 / C6 rows are not stated here
+  if (!d || !w || !r || !m || !Mj || !Kj || !prm || !x || !y || !result_d || !workspace) return NEPTUNE_E_ARG;
+  int64_t need = 0;
+  { int rc = neptune_pdhg_mf_workspace_bytes(B, N, F, &need); if (rc) return rc; }
+  if (workspace_bytes < need) return NEPTUNE_E_NOMEM;
+  if ((int64_t)B * make_geo(N, F, B).tiles_inst >= (int64_t)INT32_MAX) return NEPTUNE_E_SIZE;
+
+  cudaStream_t caller = (cudaStream_t)stream;
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  NEPTUNE_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  NEPTUNE_CUDA_OK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+  NEPTUNE_CUDA_OK(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
+  NEPTUNE_CUDA_OK(cudaEventRecord(ev_in, caller));
+  NEPTUNE_CUDA_OK(cudaStreamWaitEvent(s, ev_in, 0));
+  const int check_every = prm->check_every > 0 ? prm->check_every : 64;
+  const int max_iters = prm->max_iters > 0 ? prm->max_iters : 20000;
+
+  MfPlan P{};
+  P.B = B; P.G = make_geo(N, F, B); P.s = s;
+  P.in = MfIn{d, w, r, m, Mj, Kj};
+  const MfGeo& G = P.G;
+  const MfWs W = mf_layout(B, G);
+  char* base = (char*)workspace;
+  double* xres = (double*)(base + W.xres); double* yres = (double*)(base + W.yres);
+  double* part = (double*)(base + W.part);
+  int* d_flag = (int*)(base + W.flag);          // [0] all done, [1] skip-POST flag of the graph's first node
+  Ctl* ctl = (Ctl*)(base + W.ctl);
+  P.ctl = ctl;
+  P.st = MfSt{x, y, (double*)(base + W.xsum), (double*)(base + W.ysum), (double*)(base + W.cbar),
+              (double*)(base + W.P1), (double*)(base + W.P4), (double*)(base + W.PS), (double*)(base + W.P3),
+              (double*)(base + W.P3i),
+              (double*)(base + W.S4), (double*)(base + W.S2), (double*)(base + W.wsum), (double*)(base + W.scal)};
+  // register pass variant: 16-byte accesses (k_mf_iter_vec) are opt-in (reserved bit 11; even N > 32, aligned
+  // vectors) -- measured equal or slower than the 8-byte pass on B200 (profiles/r01f_summary.md); rows in flight
+  // per warp: reserved bits 8..10 override (tools), default by K
+  P.vec = (prm->reserved & 0x800) && !(N & 1) && G.K >= 2 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  P.rows_in_flight = (prm->reserved >> 8) & 7;
+  P.async_copy = (prm->reserved & 0x1000) && !(N & 1) && G.K >= 2 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  if (P.async_copy) {
+    P.vec = 0;
+    int occ = 0;
+    if (G.K == 2) {
+      NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_mf_iter_async<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)async_smem_bytes<1>()));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mf_iter_async<1>, kMfThreads, async_smem_bytes<1>());
+    } else {
+      NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_mf_iter_async<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)async_smem_bytes<2>()));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mf_iter_async<2>, kMfThreads, async_smem_bytes<2>());
+    }
+    P.grid_iter = kNumSMs * (occ < 1 ? 1 : occ);
+  } else if (P.vec) {
+    if (G.K == 2 && P.rows_in_flight != 2 && P.rows_in_flight != 4) P.rows_in_flight = 2;
+    if (G.K == 4 && P.rows_in_flight != 1 && P.rows_in_flight != 2) P.rows_in_flight = 1;
+    switch (G.K * 10 + P.rows_in_flight) {
+      case 22: P.grid_iter = mf_grid(k_mf_iter_vec<1, 2>); break;
+      case 24: P.grid_iter = mf_grid(k_mf_iter_vec<1, 4>); break;
+      case 41: P.grid_iter = mf_grid(k_mf_iter_vec<2, 1>); break;
+      default: P.grid_iter = mf_grid(k_mf_iter_vec<2, 2>); break;
+    }
+  } else {
+    if (P.rows_in_flight != 1 && P.rows_in_flight != 2 && !(P.rows_in_flight == 4 && G.K == 1))
+      P.rows_in_flight = G.K == 4 ? 1 : 2;
+    switch (G.K * 10 + P.rows_in_flight) {
+      case 11: P.grid_iter = mf_grid(k_mf_iter<1, 1>); break;
+      case 12: P.grid_iter = mf_grid(k_mf_iter<1, 2>); break;
+      case 14: P.grid_iter = mf_grid(k_mf_iter<1, 4>); break;
+      case 21: P.grid_iter = mf_grid(k_mf_iter<2, 1>); break;
+      case 22: P.grid_iter = mf_grid(k_mf_iter<2, 2>); break;
+      case 41: P.grid_iter = mf_grid(k_mf_iter<4, 1>); break;
+      default: P.grid_iter = mf_grid(k_mf_iter<4, 2>); break;
+    }
+  }
+  switch (G.K) {
+    case 1: P.grid_eval = mf_grid(k_mf_eval<1>); break;
+    case 2: P.grid_eval = mf_grid(k_mf_eval<2>); break;
+    default: P.grid_eval = mf_grid(k_mf_eval<4>); break;
+  }
+  // bulk-copy-staged iteration pass: opt-in (bit 0 of params->reserved) where every tile is 16-byte aligned
+  // (even N, aligned vectors); measured slower than the register pass on B200 at every BASELINE shape
+  P.use_tma = 0;
+  P.diag = (prm->reserved >> 4) & 7;
+  if ((prm->reserved & 1) && tma_geo(G, P.T) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
+    if (P.T.CPT == 3) P.T.CPT = 4;
+    cudaError_t e;
+    switch (P.T.CPT) {
+      case 1: e = cudaFuncSetAttribute(k_mf_iter_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes); break;
+      case 2: e = cudaFuncSetAttribute(k_mf_iter_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes); break;
+      default: e = cudaFuncSetAttribute(k_mf_iter_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes); break;
+    }
+    NEPTUNE_CUDA_OK(e);
+    P.use_tma = 1;
+    P.G.cti = P.T.cts;
+  }
+  // fused pass: 8-byte register pass with the default rows in flight; counters zeroed once (the kernel resets them)
+  P.use_tma = 0; P.vec = 0; P.async_copy = 0; P.G.cti = P.G.ct;
+  P.rows_in_flight = G.K == 4 ? 1 : 2;
+  P.st.cnt = (int*)(base + W.cnt);
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(P.st.cnt, 0, (size_t)B * 2 * sizeof(int), s));
+  switch (G.K) {
+    case 1: P.grid_iter = mf_grid(k_mf_iter_fused<1, 2>); break;
+    case 2: P.grid_iter = mf_grid(k_mf_iter_fused<2, 2>); break;
+    default: P.grid_iter = mf_grid(k_mf_iter_fused<4, 1>); break;
+  }
+  auto launch_fused = [&]() {
+    const int64_t total = (int64_t)B * G.tiles_inst;
+    const int g = (int)(total < P.grid_iter ? total : P.grid_iter);
+    switch (G.K) {
+      case 1: k_mf_iter_fused<1, 2><<<g, kMfThreads, 0, s>>>(P.G, P.in, P.st, ctl, B, check_every); break;
+      case 2: k_mf_iter_fused<2, 2><<<g, kMfThreads, 0, s>>>(P.G, P.in, P.st, ctl, B, check_every); break;
+      default: k_mf_iter_fused<4, 1><<<g, kMfThreads, 0, s>>>(P.G, P.in, P.st, ctl, B, check_every); break;
+    }
+    NEPTUNE_COUNT(1);
+  };
+  // small vectors: one block per instance does POST + PREC + Y2 in one launch while F*N is small; larger
+  // instances spread over several blocks and take the C2 dual in a second launch
+  P.fused = G.C <= 4096;
+  P.small_blocks = P.fused ? 1 : (int)((G.C + 1023) / 1024 < 4 * kNumSMs ? (G.C + 1023) / 1024 : 4 * kNumSMs);
+
+  const size_t cb = (size_t)B * G.cols * 8, rb = (size_t)B * G.rows * 8;
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(ctl, 0, (size_t)B * sizeof(Ctl), s));
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(d_flag, 0, 8, s));
+  const int nblk = G.tiles_inst < kMfRestartBlocks ? G.tiles_inst : kMfRestartBlocks;
+  { k_mf_wsum<<<(int)(((int64_t)B * F * 32 + 255) / 256), 256, 0, s>>>(N, (int64_t)B * F, w, P.st.wsum); NEPTUNE_COUNT(1); }
+  { k_mf_setup<<<dim3(nblk, B), 256, 0, s>>>(G, P.in, P.st, nblk); NEPTUNE_COUNT(1); }
+  { k_mf_setup_norms<<<(B + 127) / 128, 128, 0, s>>>(G, P.in, P.st, ctl, B, nblk); NEPTUNE_COUNT(1); }
+  { k_ctl_init<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, 0.99); NEPTUNE_COUNT(1); }
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(P.st.xsum, 0, cb, s));
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(P.st.ysum, 0, rb, s));
+  NEPTUNE_CUDA_OK(cudaMemcpyAsync(xres, x, cb, cudaMemcpyDeviceToDevice, s));
+  NEPTUNE_CUDA_OK(cudaMemcpyAsync(yres, y, rb, cudaMemcpyDeviceToDevice, s));
+  mf_launch_eval(P, 0, 1);                      // PS <- column sums of the starting yS
+  NEPTUNE_LAUNCH_OK();
+
+  // `inner` iterations = {small(POST unless first of the chunk, PREC, Y2); pass} captured once and replayed;
+  // the chunk ends with small(POST).  Step sizes, restart flags and convergence live in device memory.
+  const int inner = check_every < 32 ? check_every : 32;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  int64_t per_graph = 0;
+  {
+    int64_t c0 = 0, c1 = 0;
+    neptune_launch_count(&c0, 0);
+    NEPTUNE_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    for (int k = 0; k < inner; ++k) {
+      launch_fused();
+    }
+    NEPTUNE_CUDA_OK(cudaStreamEndCapture(s, &graph));
+    NEPTUNE_CUDA_OK(cudaGraphInstantiate(&gexec, graph, 0));
+    neptune_launch_count(&c1, 0);
+    per_graph = c1 - c0;
+    NEPTUNE_COUNT(-per_graph);
+  }
+  int h_flag = 0;
+  for (int it = 0; it < max_iters && !h_flag; it += check_every) {
+    int done = 0;
+    mf_launch_small(P, PH_PREC | PH_Y2, nullptr);          // c columns and C2 dual of the chunk's first iteration
+    for (; done + inner <= check_every; done += inner) {
+      NEPTUNE_CUDA_OK(cudaGraphLaunch(gexec, s));
+      NEPTUNE_COUNT(per_graph);
+    }
+    for (; done < check_every; ++done) launch_fused();      // the last block of each instance does POST (+ PREC, Y2)
+    { k_ctl_advance<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, check_every); NEPTUNE_COUNT(1); }
+    // KKT of the current iterate and of the running average
+    for (int wch = 0; wch < 2; ++wch) {
+      mf_launch_eval(P, wch, 0);
+      { k_mf_eval_small<<<B, 256, 0, s>>>(G, P.in, P.st, ctl, wch); NEPTUNE_COUNT(1); }
+    }
+    { k_ctl_decide<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, check_every, prm->eps_abs, prm->eps_rel, max_iters,
+                                                 result_d); NEPTUNE_COUNT(1); }
+    { k_mf_apply_restart<<<dim3(kMfRestartBlocks, B), 256, 0, s>>>(G, P.in, P.st, xres, yres, ctl, part); NEPTUNE_COUNT(1); }
+    { k_mf_restart_norms<<<(B + 127) / 128, 128, 0, s>>>(B, kMfRestartBlocks, part, ctl); NEPTUNE_COUNT(1); }
+    { k_ctl_after_restart<<<(B + 127) / 128, 128, 0, s>>>(B, ctl); NEPTUNE_COUNT(1); }
+    mf_launch_eval(P, 0, 1);                    // PS of the (possibly replaced) yS for the next PREC
+    { k_all_done<<<1, 1, 0, s>>>(B, ctl, d_flag); NEPTUNE_COUNT(1); }
+    NEPTUNE_CUDA_OK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, s));
+    NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
+  }
+  cudaGraphExecDestroy(gexec);
+  cudaGraphDestroy(graph);
+  NEPTUNE_LAUNCH_OK();
+  NEPTUNE_CUDA_OK(cudaEventRecord(ev_out, s));
+  NEPTUNE_CUDA_OK(cudaStreamWaitEvent(caller, ev_out, 0));
+  NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
+  cudaEventDestroy(ev_in); cudaEventDestroy(ev_out);
+  cudaStreamDestroy(s);
+  return 0;
+}
+
+
 extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double* d, const double* w,
                                      const double* r, const double* m, const double* Mj, const double* Kj,
                                      const neptune_pdhg_params* prm, double* x, double* y,
@@ -1321,6 +1710,9 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
   { int rc = neptune_pdhg_mf_workspace_bytes(B, N, F, &need); if (rc) return rc; }
   if (workspace_bytes < need) return NEPTUNE_E_NOMEM;
   if ((int64_t)B * make_geo(N, F, B).tiles_inst >= (int64_t)INT32_MAX) return NEPTUNE_E_SIZE;
+  if ((prm->reserved & 0x2000) && (int64_t)N * F <= 4096)   // experimental fused pass (not yet run on a GPU); larger
+                                                             // instances would serialise their small vectors in one block
+    return mf_solve_fused(B, N, F, kind, d, w, r, m, Mj, Kj, prm, x, y, result_d, workspace, workspace_bytes, stream);
 
   cudaStream_t caller = (cudaStream_t)stream;
   cudaStream_t s = nullptr;
