@@ -149,6 +149,8 @@ int neptune_spmv_t(int B, int64_t rows, int64_t cols, const int64_t* rowT_ptr,
  * running sums per iteration.  x[B][cols], y[B][rows] are the canonical vectors of that model (in/out, warm
  * start; the multipliers of the free C1a rows are returned as 0).  Other kinds return NEPTUNE_E_ARG. */
 int neptune_pdhg_mf_workspace_bytes(int B, int N, int F, int64_t* bytes);
+/* host-only: tile geometry of the passes for (B, N, F); out[16] (see csrc/pdhg_mf.cu) */
+int neptune_pdhg_mf_geometry(int B, int N, int F, int32_t* out);
 int neptune_pdhg_mf_solve(int B, int N, int F, int kind,
                           const double* d, const double* w, const double* r, const double* m,
                           const double* Mj, const double* Kj,

@@ -1491,6 +1491,21 @@ static void mf_launch_small(const MfPlan& P, int mask, const int* skip_post) {
 
 using namespace neptune;
 
+// host-only: the tile geometry the solver would use (tests, tools).  out[0..7] = {K columns per lane, JT columns per
+// tile, ct column tiles, RT rows per tile, rt row tiles, tiles per instance, F*N <= 4096 (single-block small
+// kernel), 0}; out[8..15] = bulk-copy pass {applicable, JS, cts, RS, G, CPT, super-tiles per instance, 0}
+extern "C" int neptune_pdhg_mf_geometry(int B, int N, int F, int32_t* out) {
+  if (B <= 0 || N <= 0 || F <= 0 || !out) return NEPTUNE_E_ARG;
+  const MfGeo G = make_geo(N, F, B);
+  out[0] = G.K; out[1] = G.JT; out[2] = G.ct; out[3] = G.RT; out[4] = G.rt; out[5] = G.tiles_inst;
+  out[6] = G.C <= 4096; out[7] = 0;
+  TmaGeo T{};
+  const bool ok = tma_geo(G, T);
+  out[8] = ok; out[9] = T.JS; out[10] = T.cts; out[11] = T.RS; out[12] = T.G; out[13] = T.CPT == 3 ? 4 : T.CPT;
+  out[14] = T.supers_inst; out[15] = 0;
+  return 0;
+}
+
 extern "C" int neptune_pdhg_mf_workspace_bytes(int B, int N, int F, int64_t* bytes) {
   if (B <= 0 || N <= 0 || F <= 0 || !bytes) return NEPTUNE_E_ARG;
   Layout L(N, F, NEPTUNE_KIND_MIN_DELAY, NEPTUNE_FLAG_STRENGTHEN);
