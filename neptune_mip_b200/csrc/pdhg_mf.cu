@@ -208,6 +208,116 @@ k_mf_iter(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
   }
 }
 
+// EXPERIMENTAL (opt-in, reserved bit 14; not yet run on a GPU): k_mf_iter<K, U> with bumped pointers.  The SASS of
+// k_mf_iter<2,2> spends ~45 % of its row loop on 64-bit address arithmetic (each of the 20 loads and 16 stores
+// rebuilds base + 8*(row*N + column)); here a lane keeps one pointer per stream at (row ib, its first column), the
+// other columns are +32 elements (an immediate), the other rows of the batch +8*N elements, and the pointers
+// advance once per batch.  Same arithmetic and summation order as k_mf_iter<K, U>.
+template <int K, int U>
+__global__ void __launch_bounds__(kMfThreads, (K * U >= 4 ? 2 : 3))
+k_mf_iter_lean(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
+  __shared__ double sm[3][kMfWarps][32 * K];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = G.N;
+  const int64_t NN = (int64_t)N * N;
+  const int64_t total = (int64_t)B * G.tiles_inst;
+  const int64_t rstep = (int64_t)kMfWarps * N;                   // elements between consecutive rows of a warp
+  for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const Tile t = decode_tile(G, tile);
+    const int b = t.b, f = t.f;
+    if (ctl[b].converged) continue;
+    const double tau = ctl[b].tau, shalf = 0.5 * ctl[b].sigma;
+    const double* __restrict__ w = in.w + ((int64_t)b * G.F + f) * N;
+    const double* __restrict__ r = in.r + ((int64_t)b * G.F + f) * N;
+    const double* __restrict__ y = st.y + (int64_t)b * G.rows;
+    const double* __restrict__ cbar = st.cbar + (int64_t)b * G.C + (int64_t)f * N;
+    const int i0 = t.it * G.RT, i1 = min(N, i0 + G.RT);
+    const int j0 = t.jt * G.JT + lane;                           // first column of this lane; the others are +32*k
+    const int64_t e0 = (int64_t)(i0 + warp) * N + j0;            // element of (first row of the warp, first column)
+    double* px = st.x + (int64_t)b * G.cols + (int64_t)f * NN + e0;
+    double* pxs = st.xsum + (int64_t)b * G.cols + (int64_t)f * NN + e0;
+    double* ps = st.y + (int64_t)b * G.rows + G.rs + (int64_t)f * NN + e0;
+    double* pss = st.ysum + (int64_t)b * G.rows + G.rs + (int64_t)f * NN + e0;
+    const double* pd = in.d + (int64_t)b * NN + e0;
+    const double* pw = w + i0 + warp;
+    const double* py3 = y + G.r3 + (int64_t)f * N + i0 + warp;
+    double* pP3 = st.P3i + ((int64_t)b * G.C + (int64_t)f * N + i0 + warp) * G.cti + t.jt;
+
+    bool vj[K];
+    double y1j[K], rj[K], rr4[K], cb[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int j = j0 + 32 * k;
+      vj[k] = j < N;
+      const int jc = vj[k] ? j : 0;
+      y1j[k] = y[2 * ((int64_t)f * N + jc) + 1];
+      rj[k] = __ldg(r + jc);
+      rr4[k] = rj[k] * y[G.r4 + jc];
+      cb[k] = cbar[jc];
+    }
+    double a1[K], a4[K], aS[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { a1[k] = 0.0; a4[k] = 0.0; aS[k] = 0.0; }
+
+    for (int ib = i0 + warp; ib < i1; ib += U * kMfWarps) {
+      double xv[U][K], sv[U][K], xs[U][K], ss[U][K], dv[U][K], wfi[U], y3i[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        ok[u] = ib + u * kMfWarps < i1;
+        wfi[u] = ok[u] ? __ldg(pw + u * kMfWarps) : 0.0;
+        y3i[u] = ok[u] ? py3[u * kMfWarps] : 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const bool on = ok[u] && vj[k];
+          const int64_t o = u * rstep + 32 * k;
+          xv[u][k] = on ? px[o] : 0.0; sv[u][k] = on ? ps[o] : 0.0;
+          xs[u][k] = on ? pxs[o] : 0.0; ss[u][k] = on ? pss[o] : 0.0;
+          dv[u][k] = on ? __ldg(pd + o) : 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        double rsum = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (ok[u] && vj[k]) {
+            const int64_t o = u * rstep + 32 * k;
+            const double wr = fabs(wfi[u] * rj[k]);
+            const double g = __dmul_rn(dv[u][k], wfi[u]) + y1j[k] + y3i[u] + wfi[u] * rr4[k] + sv[u][k];
+            double xn = xv[u][k] - tau * g / (3.0 + wr);
+            xn = fmin(fmax(xn, 0.0), 1.0);
+            const double xb = 2.0 * xn - xv[u][k];
+            const double sn = fmax(sv[u][k] + shalf * (xb - cb[k]), 0.0);
+            px[o] = xn; ps[o] = sn;
+            pxs[o] = xs[u][k] + xn; pss[o] = ss[u][k] + sn;
+            a1[k] += xb; a4[k] += wfi[u] * xb; aS[k] += sn; rsum += xb;
+          }
+        }
+        rsum = warp_sum(rsum);
+        if (lane == 0 && ok[u]) pP3[(int64_t)u * kMfWarps * G.cti] = rsum;
+      }
+      px += U * rstep; ps += U * rstep; pxs += U * rstep; pss += U * rstep; pd += U * rstep;
+      pw += U * kMfWarps; py3 += U * kMfWarps; pP3 += (int64_t)U * kMfWarps * G.cti;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      sm[0][warp][k * 32 + lane] = a1[k]; sm[1][warp][k * 32 + lane] = a4[k]; sm[2][warp][k * 32 + lane] = aS[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 32 * K; c += kMfThreads) {
+      const int j = t.jt * G.JT + c;
+      if (j < N) {
+        const int64_t o = (((int64_t)b * G.F + f) * G.rt + t.it) * N + j;
+        st.P1[o] = column_total<K>(sm[0], c);
+        st.P4[o] = __ldg(r + j) * column_total<K>(sm[1], c);
+        st.PS[o] = column_total<K>(sm[2], c);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // the iteration pass with 16-byte accesses (even N > 32): a lane owns KV pairs of adjacent columns (double2 loads
 // and stores of all four streams and of d), U rows of a warp in flight -- half the memory instructions and address
 // arithmetic of k_mf_iter for the same bytes, twice the bytes in flight per instruction.  Same tiles, same
@@ -1415,6 +1525,7 @@ struct MfPlan {
   int rows_in_flight;            // U of k_mf_iter<K, U>
   int vec;                       // k_mf_iter_vec (16-byte accesses) instead of k_mf_iter
   int async_copy;                // k_mf_iter_async (experimental)
+  int lean;                      // k_mf_iter_lean (experimental)
   int diag;                      // tools only: bits of params->reserved >> 4 switch parts of the TMA pass off
 };
 
@@ -1436,6 +1547,15 @@ static void mf_launch_iter(const MfPlan& P) {
   if (P.async_copy) {
     if (P.G.K == 2) k_mf_iter_async<1><<<g, kMfThreads, async_smem_bytes<1>(), P.s>>>(P.G, P.in, P.st, P.ctl, P.B);
     else k_mf_iter_async<2><<<g, kMfThreads, async_smem_bytes<2>(), P.s>>>(P.G, P.in, P.st, P.ctl, P.B);
+    NEPTUNE_COUNT(1);
+    return;
+  }
+  if (P.lean) {
+    switch (P.G.K) {
+      case 1: k_mf_iter_lean<1, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+      case 2: k_mf_iter_lean<2, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+      default: k_mf_iter_lean<4, 1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+    }
     NEPTUNE_COUNT(1);
     return;
   }
@@ -1792,6 +1912,14 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
       case 22: P.grid_iter = mf_grid(k_mf_iter<2, 2>); break;
       case 41: P.grid_iter = mf_grid(k_mf_iter<4, 1>); break;
       default: P.grid_iter = mf_grid(k_mf_iter<4, 2>); break;
+    }
+  }
+  P.lean = (prm->reserved & 0x4000) && !P.async_copy && !P.vec;        // experimental pointer-bumped register pass
+  if (P.lean) {
+    switch (G.K) {
+      case 1: P.grid_iter = mf_grid(k_mf_iter_lean<1, 2>); break;
+      case 2: P.grid_iter = mf_grid(k_mf_iter_lean<2, 2>); break;
+      default: P.grid_iter = mf_grid(k_mf_iter_lean<4, 1>); break;
     }
   }
   switch (G.K) {

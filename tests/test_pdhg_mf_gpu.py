@@ -174,3 +174,16 @@ def test_experimental_fused_pass_equals_two_kernel_iteration(shape, iters):
     _, _, r1 = device.pdhg_mf_solve(inst, **kw)
     _, _, r2 = device.pdhg_mf_solve(inst, fused_kernel=True, **kw)
     assert r1["iters"].tolist() == r2["iters"].tolist() and np.allclose(r1["primal_obj"], r2["primal_obj"], rtol=1e-10)
+
+
+@pytest.mark.skipif(not os.environ.get("NEPTUNE_EXPERIMENTAL"), reason="pointer-bumped register pass: written after the round's GPU "
+                    "budget was spent; run with NEPTUNE_EXPERIMENTAL=1 on a B200 first")
+@pytest.mark.parametrize("shape,iters", [((3, 2), 64), ((20, 5), 40), ((33, 3), 33), ((50, 10), 64), ((70, 3), 64), ((130, 2), 33)])
+def test_experimental_lean_pass_equals_register_pass(shape, iters):
+    """same arithmetic and summation order as k_mf_iter<K, U> with U = default: bitwise equal results are expected"""
+    from neptune_mip_b200 import device
+    inst = cuda_batch([synth.random_payload(shape[0], shape[1], s, node_cores=60) for s in range(2)])
+    kw = dict(max_iters=iters, check_every=iters, eps_rel=1e-13, eps_abs=1e-15)
+    xa, ya, _ = device.pdhg_mf_solve(inst, **kw)
+    xb, yb, _ = device.pdhg_mf_solve(inst, lean_kernel=True, **kw)
+    assert _close(xb.cpu().numpy(), xa.cpu().numpy(), 1e-12) and _close(yb.cpu().numpy(), ya.cpu().numpy(), 1e-12)
