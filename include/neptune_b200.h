@@ -276,6 +276,36 @@ int neptune_disruption_search(int B, int N, int F, int kind, double alpha, int m
                               const uint8_t* seeds, uint8_t* best_c, double* best_obj, int32_t* best_flags,
                               void* workspace, int64_t workspace_bytes, void* stream);
 
+/* neptune_route_lp: EXACT routing of fixed placements -- the LP the reference's step-1 MIP reduces to once c
+ * is fixed (rows constraints_step1.py:47-65, objective objectives.py:4-11), solved per placement by a
+ * dense-tableau dual simplex started from the nearest-open-pod routing and restricted to the sources of the
+ * nodes whose CPU row binds (csrc/route_lp.cu).  P placements per instance: c[B][P][F][N] (uint8) ->
+ * obj_out[B][P] (sum x*d*w of the LP optimum), status_out[B][P] (1 = optimal and every open pod keeps a share
+ * >= 1 - eps, 0 = infeasible, 2 = the tableau does not fit `tableau_doubles`: use neptune_route_capacitated),
+ * optional c_out[B][P][F][N] (pods nobody uses closed), x[B][P][N][F][N], n[B][P][N], info_out[B][P][2]
+ * (pivots, nodes priced).  Workspace from neptune_route_lp_workspace_bytes. */
+int neptune_route_lp(int B, int P, int N, int F, const double* d, const double* w, const double* r,
+                     const double* Kj, const uint8_t* c, uint8_t* c_out, double* x, double* n,
+                     double* obj_out, int32_t* status_out, int32_t* info_out, int64_t tableau_doubles,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+int neptune_route_lp_workspace_bytes(int B, int P, int N, int F, int64_t tableau_doubles, int64_t* bytes);
+
+/* neptune_lns_search: step-1 search for the models with a delay term (kind 0 and 2) when every function needs
+ * the same memory (the memory row is then a slot count per node): `chains` warp-sized chains per instance, each
+ * `rounds` exact k-node re-optimisations (dynamic programme over functions with the slot counters as state) on
+ * the priced nearest-pod cost, node prices on the CPU rows kept at their coordinate-wise dual optimum, annealed
+ * cost perturbation of relative size `noise_coef` (csrc/lns.cu).  Chains start from randomised roundings of
+ * guide[B][F][N] (c-bar of the LP relaxation) and lam0[B][N] (its CPU-row duals), and/or from
+ * seeds[B][S][F][N]; any of the three may be NULL.  Returns every chain's record: out_c[B][chains][F][N],
+ * out_g[B][chains] (priced objective, a lower bound of the record's true objective; +inf = none),
+ * out_round[B][chains].  Price the records with neptune_route_lp. */
+int neptune_lns_search(int B, int N, int F, int kind, double alpha, int chains, int rounds, int k,
+                       double noise_coef, uint64_t rng_seed,
+                       const double* d, const double* w, const double* r, const double* m,
+                       const double* Mj, const double* Kj, const double* maxd,
+                       const double* guide, const double* lam0, int S, const uint8_t* seeds,
+                       uint8_t* out_c, double* out_g, int32_t* out_round, void* stream);
+
 /* ---- (d) EFTTC greedy -----------------------------------------------------------------------------
  * Replaces `EfttcStepBase.solve()` (`core/solvers/efttc/efttc_step1.py:39-90` and helpers
  * :92-312, score_local :356-439).  One thread block per instance; deterministic, same

@@ -19,9 +19,16 @@ class BatchParams:
     lp_iters: int = 2048          # PDHG iterations on the strengthened relaxation (bound + rounding guide)
     lp_check_every: int = 256
     lp_path: str = "auto"         # "auto": matrix-free PDHG for the min-delay model, assembled CSR otherwise; "csr": always CSR
-    chains: int = 16              # local-search chains per instance
+    chains: int = 16              # local-search chains per instance (add/drop/swap search)
     sweeps: int = 200
     rng_seed: int = 1
+    search: str = "auto"          # "auto": slot-count LNS (csrc/lns.cu) where it applies, else the add/drop/swap search; "local": always the latter
+    lp_cut: bool = True           # relax with the Chvatal-Gomory rounding of the memory rows (one memory size per instance)
+    lns_chains: int = 32          # warp-sized chains per instance
+    lns_rounds: int = 6000        # k-node re-optimisations per chain
+    lns_k: int = 3
+    lns_noise: float = 0.06
+    elites: int = 8               # chain records priced exactly (routing LP) per instance
 
 
 @dataclass
@@ -37,12 +44,17 @@ class BatchResult:
     model_dims: tuple = (0, 0, 0)
     pdhg_bytes_per_iter: int = 0  # algorithmic bytes one PDHG iteration of the whole batch moves
     pdhg_path: str = ""           # "matrix-free" | "csr"
+    search_path: str = ""         # "lns" | "local"
+    lns_round: Optional[torch.Tensor] = None     # [B] round at which the returned placement was recorded by its chain
+    lns_ms: float = 0.0
 
 
 def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = False) -> BatchResult:
     kind = prm.kind
-    lp_res, guide, pdhg_ms, iters, dims = None, None, 0.0, 0, (0, 0, 0)
+    lp_res, guide, lam0, pdhg_ms, iters, dims = None, None, None, 0.0, 0, (0, 0, 0)
     bytes_iter, path = 0, ""
+    use_lns = prm.search == "auto" and device.lns_supported(inst, kind)
+    inst_lp = device.slot_relaxation(inst) if (use_lns and prm.lp_cut) else inst
     if prm.lp_iters > 0:
         N, F, B = inst.N, inst.F, inst.B
         X = F * N * N
@@ -54,8 +66,9 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
             rows, cols, nnz = device.model_sizes(N, F, 0, FLAG_STRENGTHEN)
             if time_pdhg:
                 e0.record()
-            xs, ys, lp_res = device.pdhg_mf_solve(inst, max_iters=prm.lp_iters, check_every=prm.lp_check_every,
+            xs, ys, lp_res = device.pdhg_mf_solve(inst_lp, max_iters=prm.lp_iters, check_every=prm.lp_check_every,
                                                   eps_rel=1e-6, eps_abs=1e-9)
+            lam0 = ys[:, 3 * F * N + N:3 * F * N + 2 * N].contiguous()       # duals of the CPU rows C4
             bytes_iter, path = B * (64 * X + 112 * F * N + 8 * N * N), "matrix-free"
         else:
             lp = device.assemble(inst, kind, prm.alpha, flags=FLAG_STRENGTHEN)
@@ -76,15 +89,19 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
         del xs, ys
     seeds = torch.stack([device.efttc(inst, k, prm.alpha)[0] for k in ("min_delay", "min_util", "min_delay_util")],
                         dim=1).contiguous()
-    best_c, best_obj, _ = device.local_search(inst, kind, seeds, prm.alpha, prm.chains, prm.sweeps,
-                                              prm.rng_seed, guide)
     fallback = seeds[:, KINDS[kind]]
-    bad = ~torch.isfinite(best_obj)
-    if bool(bad.any()):
-        best_c[bad] = fallback[bad]
-    # final routing honours the CPU rows (splits flows on binding nodes) and closes pods nobody uses
-    best_c, x, n, _, _ = device.route_capacitated(inst, best_c)
-    flags, scores = device.check_solution(inst, x, device.u8_to_f64(best_c), n, prm.alpha)
+    lns_round, lns_ms = None, 0.0
+    if use_lns:
+        best_c, x, n, flags, scores, lns_round, lns_ms = lns_step1(inst, kind, prm, guide, lam0, seeds, time_it=time_pdhg)
+    else:
+        best_c, best_obj, _ = device.local_search(inst, kind, seeds, prm.alpha, prm.chains, prm.sweeps,
+                                                  prm.rng_seed, guide)
+        bad = ~torch.isfinite(best_obj)
+        if bool(bad.any()):
+            best_c[bad] = fallback[bad]
+        # final routing honours the CPU rows (splits flows on binding nodes) and closes pods nobody uses
+        best_c, x, n, _, _ = device.route_capacitated(inst, best_c)
+        flags, scores = device.check_solution(inst, x, device.u8_to_f64(best_c), n, prm.alpha)
     bad = flags != OK_ALL
     if bool(bad.any()):
         # rare (a pod starved by a split flow that no free source can top up): fall back, per instance, to the
@@ -98,4 +115,68 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
                 bad = flags != OK_ALL
             if not bool(bad.any()):
                 break
-    return BatchResult(best_c, x, n, flags, scores, lp_res, pdhg_ms, iters, dims, bytes_iter, path)
+    return BatchResult(best_c, x, n, flags, scores, lp_res, pdhg_ms, iters, dims, bytes_iter, path,
+                       "lns" if use_lns else "local", lns_round, lns_ms)
+
+
+def objective_weights(inst: device.InstanceBatch, kind, alpha):
+    """(a_d[B], a_u[B]): objective = a_d * delay + a_u * active nodes (reference objectives.py:4-52)."""
+    k = KINDS.get(kind, kind)
+    one = torch.ones(inst.B, dtype=torch.float64, device=inst.d.device)
+    if k == 0:
+        return one, 0 * one
+    if k == 1:
+        return 0 * one, one
+    far = torch.where(inst.d[:, None, :, :] <= inst.maxd[:, :, None, None], inst.d[:, None, :, :],
+                      torch.full_like(inst.d[:, None, :, :], -float("inf"))).amax(dim=-1)          # [B,F,N]
+    wmax = (inst.w * far).sum(dim=(1, 2))
+    wsum = inst.w.sum(dim=(1, 2))
+    a_d = torch.where((wsum != 0) & (wmax != 0), (1.0 - alpha) / wmax, 0 * one)
+    return a_d, one * (alpha / inst.N)
+
+
+def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0, seeds, time_it=False):
+    """Slot-count LNS -> exact pricing of the best chain records (routing LP) -> exact routing + checkers of the
+    winner.  Returns (c uint8[B,F,N], x, n, flags, scores, round[B], search ms)."""
+    B, N, F = inst.B, inst.N, inst.F
+    if time_it:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    out_c, out_g, out_round = device.lns_search(inst, kind, prm.alpha, prm.lns_chains, prm.lns_rounds, prm.lns_k,
+                                                prm.lns_noise, prm.rng_seed, guide, lam0, seeds)
+    E = max(1, min(prm.elites, prm.lns_chains))
+    _, idx = torch.topk(out_g, E, dim=1, largest=False)                       # lowest priced objective first
+    elite = torch.gather(out_c, 1, idx[:, :, None, None].expand(B, E, F, N)).contiguous()
+    pr = device.route_lp(inst, elite)
+    a_d, a_u = objective_weights(inst, kind, prm.alpha)
+    val = a_d[:, None] * pr["obj"] + a_u[:, None] * pr["n"].sum(dim=-1)
+    val = torch.where(pr["status"] == 1, val, torch.full_like(val, float("inf")))
+    order = torch.argsort(val, dim=1, stable=True)
+    ar = torch.arange(B, device=val.device)
+    best_c = x = n = flags = scores = rnd = None
+    for rank in range(E):
+        pick = order[:, rank]
+        cand = elite[ar, pick].contiguous()
+        fin = device.route_lp(inst, cand[:, None].contiguous(), want_x=True)
+        cx, cc, cn = fin["x"][:, 0].contiguous(), fin["c_out"][:, 0].contiguous(), fin["n"][:, 0].contiguous()
+        st = fin["status"][:, 0]
+        big = st == 2
+        if bool(big.any()):       # tableau larger than the slab: the heuristic capacity-aware routing stands in
+            hc, hx, hn, _, _ = device.route_capacitated(inst, cand)
+            cc[big], cx[big], cn[big] = hc[big], hx[big], hn[big]
+        fl, sc = device.check_solution(inst, cx, device.u8_to_f64(cc), cn, prm.alpha)
+        if best_c is None:
+            best_c, x, n, flags, scores = cc, cx, cn, fl, sc
+            rnd = torch.gather(out_round, 1, torch.gather(idx, 1, pick[:, None]))[:, 0]
+        else:
+            take = (flags != OK_ALL) & (fl == OK_ALL)
+            if bool(take.any()):
+                best_c[take], x[take], n[take], flags[take], scores[take] = cc[take], cx[take], cn[take], fl[take], sc[take]
+        if bool((flags == OK_ALL).all()):
+            break
+    ms = 0.0
+    if time_it:
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+    return best_c, x, n, flags, scores, rnd, ms

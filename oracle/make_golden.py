@@ -13,7 +13,8 @@ Sources of truth written into the fixtures
   random_small.json    unmodified reference on random-workload instances: EFTTC placements (with the
                        documented discard fallback where it raises KeyError) and Neptune* scores
   payload_json.json    the reference's payload.json sample (no matrices: every default) through six solvers
-  mip_optima.json      step-1 optima by HiGHS on the oracle model (C2 seeds, C5 subsample)
+  mip_optima.json      step-1 optima by HiGHS on the oracle model (C2 seeds, C5 subsample), with the placements
+  lp_cut.json          HiGHS optima of the slot-cut LP relaxation (oracle.relax) the matrix-free PDHG solves
 """
 from __future__ import annotations
 
@@ -251,10 +252,12 @@ def _mip_case(args):
     o = mip.solve_step1(a, kind, 0.5, time_limit=tl)
     return {"config": name, "seed": seed, "kind": kind, "objective": o["objective"], "optimal": bool(o["optimal"]),
             "seconds": o["seconds"], "dual_bound": o["dual_bound"], "gap": o["gap"],
-            "pods": int((o["c"] > 0.5).sum()) if o["sol"] is not None else None, "time_limit": tl}
+            "pods": int((o["c"] > 0.5).sum()) if o["sol"] is not None else None, "time_limit": tl,
+            # the incumbent placement as [f, j] pairs: lets a test price a known-optimal placement with the device routing
+            "placement": [[int(f), int(j)] for f, j in zip(*np.nonzero(o["c"] > 0.5))] if o["sol"] is not None else None}
 
 
-def make_mip_optima(jobs, c2_seeds=8, c5_seeds=64):
+def make_mip_optima(jobs, c2_seeds=16, c5_seeds=64):
     path = os.path.join(GOLD, "mip_optima.json")
     have = {}
     if os.path.exists(path):
@@ -269,6 +272,24 @@ def make_mip_optima(jobs, c2_seeds=8, c5_seeds=64):
             _dump("mip_optima.json", sorted(have.values(), key=lambda r: (r["config"], r["kind"], r["seed"])))
 
 
+def make_lp_cut():
+    """HiGHS optima of the slot-cut relaxation (oracle.relax) for the C2 seeds and a C5 subsample: pins the
+    bound the matrix-free PDHG reports."""
+    from neptune_mip_b200 import synth
+    from neptune_mip_b200.core.utils import data_to_solver_input
+    from oracle import model, relax
+    out = []
+    for name, seeds in (("C2", range(16)), ("C5", range(8))):
+        for s in seeds:
+            a = model.arrays_from_data(data_to_solver_input(synth.config_payload(name, s), 1, with_db=False))
+            v1, _, lam = relax.strengthened_lp(a, slot_cut=True)
+            v0, _, _ = relax.strengthened_lp(a, slot_cut=False)
+            out.append({"config": name, "seed": s, "lp_slot_cut": v1, "lp_memory_rows": v0,
+                        "cpu_duals": [float(x) for x in lam]})
+            print(name, s, v1, v0, flush=True)
+    _dump("lp_cut.json", out)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -276,7 +297,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     steps = {"alibaba": make_alibaba, "c1": make_c1, "payload_json": make_payload_json, "simulated": lambda: make_simulated(a.jobs),
              "model_hashes": make_model_hashes, "random_small": lambda: make_random_small(a.jobs),
-             "mip_optima": lambda: make_mip_optima(a.jobs)}
+             "mip_optima": lambda: make_mip_optima(a.jobs), "lp_cut": make_lp_cut}
     for name, fn in steps.items():
         if a.only in (None, name):
             fn()
