@@ -47,6 +47,7 @@ class BatchResult:
     search_path: str = ""         # "lns" | "local"
     lns_round: Optional[torch.Tensor] = None     # [B] round at which the returned placement was recorded by its chain
     lns_ms: float = 0.0
+    lns_diag: Optional[dict] = None              # elite_g[B,E] priced objective, elite_val[B,E] exact objective (inf: infeasible)
 
 
 def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = False) -> BatchResult:
@@ -90,9 +91,9 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
     seeds = torch.stack([device.efttc(inst, k, prm.alpha)[0] for k in ("min_delay", "min_util", "min_delay_util")],
                         dim=1).contiguous()
     fallback = seeds[:, KINDS[kind]]
-    lns_round, lns_ms = None, 0.0
+    lns_round, lns_ms, lns_diag = None, 0.0, None
     if use_lns:
-        best_c, x, n, flags, scores, lns_round, lns_ms = lns_step1(inst, kind, prm, guide, lam0, seeds, time_it=time_pdhg)
+        best_c, x, n, flags, scores, lns_round, lns_ms, lns_diag = lns_step1(inst, kind, prm, guide, lam0, seeds, time_it=time_pdhg)
     else:
         best_c, best_obj, _ = device.local_search(inst, kind, seeds, prm.alpha, prm.chains, prm.sweeps,
                                                   prm.rng_seed, guide)
@@ -116,7 +117,7 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
             if not bool(bad.any()):
                 break
     return BatchResult(best_c, x, n, flags, scores, lp_res, pdhg_ms, iters, dims, bytes_iter, path,
-                       "lns" if use_lns else "local", lns_round, lns_ms)
+                       "lns" if use_lns else "local", lns_round, lns_ms, lns_diag)
 
 
 def objective_weights(inst: device.InstanceBatch, kind, alpha):
@@ -179,4 +180,5 @@ def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0,
         e1.record()
         e1.synchronize()
         ms = e0.elapsed_time(e1)
-    return best_c, x, n, flags, scores, rnd, ms
+    diag = dict(elite_g=torch.gather(out_g, 1, idx), elite_val=val, pivots=pr["info"][..., 0])
+    return best_c, x, n, flags, scores, rnd, ms, diag

@@ -29,6 +29,10 @@ class GpuStepMixin:
         else:
             x, n = device.route_placements(inst, c_u8)
         flags, scores = device.check_solution(inst, x, device.u8_to_f64(c_u8), n, self._alpha())
+        return self._take(c_u8, x, n, flags, scores)
+
+    def _take(self, c_u8, x, n, flags, scores):
+        """Host copies of an evaluated placement (first instance of the batch)."""
         self._x = x[0].cpu().numpy()
         self._c = c_u8[0].cpu().numpy().astype(np.float64)
         self._n = n[0].cpu().numpy()

@@ -10,19 +10,27 @@ import numpy as np
 import torch
 
 from .... import device
-from ...._lib import FLAG_STRENGTHEN
 from ..gpu_step import GpuStepMixin
 from ..solver import Solver
 
 
 class NeptuneStepBase(GpuStepMixin, Solver):
-    def __init__(self, chains: int = 296, sweeps: int = 300, lp_iters: int = 0, rng_seed: int = 1,
-                 keep_model: bool = True, **kwargs):
+    """`lp_iters` > 0 by default: the drop-in path always solves the LP relaxation (matrix-free PDHG) and reports
+    its bound and the gap of the returned placement (`lp_bound`, `mip_gap`).  `keep_model=True` additionally
+    assembles the reference's matrix on device in `load_data` (kernel group (a)); nothing on the solve path reads
+    it, so it is off by default (C4 would need 2 x 38 GB for it)."""
+
+    def __init__(self, chains: int = 64, sweeps: int = 300, lp_iters: int = 20000, rng_seed: int = 1,
+                 keep_model: bool = False, lns_chains: int = 256, lns_rounds: int = 6000, lns_k: int = 3,
+                 lns_noise: float = 0.06, elites: int = 16, search: str = "auto", **kwargs):
         super().__init__(**kwargs)
         self.chains, self.sweeps, self.lp_iters, self.rng_seed = chains, sweeps, lp_iters, rng_seed
+        self.lns_chains, self.lns_rounds, self.lns_k, self.lns_noise = lns_chains, lns_rounds, lns_k, lns_noise
+        self.elites, self.search = elites, search
         self.keep_model = keep_model
         self.model = None
         self.lp_bound = None
+        self.mip_gap = None
         self.lp_result = None
         self._x = self._c = self._n = None
 
@@ -30,7 +38,7 @@ class NeptuneStepBase(GpuStepMixin, Solver):
         self._upload()
 
     def init_constraints(self):
-        # the reference builds rows here; so do we (on device), flags=0 is the as-written matrix
+        # the reference builds rows here; on request so do we (on device), flags=0 is the as-written matrix
         if self.keep_model:
             self.model = device.assemble(self.inst, self.kind, self._alpha())
 
@@ -45,36 +53,25 @@ class NeptuneStepBase(GpuStepMixin, Solver):
 
 class NeptuneStep1CPUBase(NeptuneStepBase):
     def solve(self):
+        """LP relaxation (bound, rounding guide, CPU-row prices) -> search -> exact routing LP -> the reference's
+        checkers, all through `batch.solve_batch` (the path bench.py times) with a batch of one."""
+        from ....batch import BatchParams, solve_batch
         self.init_objective()
-        inst, alpha = self.inst, self._alpha()
-        guide = None
-        if self.lp_iters > 0:
-            if self.kind == "min_delay":
-                # matrix-free relaxation of the strengthened min-delay model (nothing is assembled)
-                xs, ys, res = device.pdhg_mf_solve(inst, max_iters=self.lp_iters, eps_rel=1e-5)
-            else:
-                lp = device.assemble(inst, self.kind, alpha, flags=FLAG_STRENGTHEN)
-                xs, ys, res = device.pdhg_solve(lp, max_iters=self.lp_iters, eps_rel=1e-5)
-                del lp
-            X = inst.F * inst.N * inst.N
-            guide = xs[:, X:X + inst.F * inst.N].contiguous()
-            self.lp_result = res[0]
-            self.lp_bound = float(res[0]["dual_obj"])
-            del xs, ys
-        seeds = [device.efttc(inst, k, alpha)[0] for k in ("min_delay", "min_util", "min_delay_util")]
-        seeds = torch.stack(seeds, dim=1).contiguous()                       # [1, 3, F, N]
-        best_c, best_obj, _ = device.local_search(inst, self.kind, seeds, alpha, self.chains, self.sweeps,
-                                                  self.rng_seed, guide)
-        if not torch.isfinite(best_obj[0]):
-            best_c = seeds[:, {"min_delay": 0, "min_util": 1, "min_delay_util": 2}[self.kind]].contiguous()
-        ok = self._finish(best_c, capacitated=True)
-        if not ok:      # rare: fall back to the first EFTTC seed that passes every check
-            for k in ({"min_delay": 0, "min_util": 1, "min_delay_util": 2}[self.kind], 1, 2, 0):
-                if self._finish(seeds[:, k].contiguous(), capacitated=True):
-                    ok = True
-                    break
-        self.log(f"step 1: score {self._kind_score()} flags {self.flags:06b} lp bound {self.lp_bound}")
-        return ok
+        prm = BatchParams(kind=self.kind, alpha=self._alpha(), lp_iters=self.lp_iters, lp_check_every=256,
+                          chains=self.chains, sweeps=self.sweeps, rng_seed=self.rng_seed, search=self.search,
+                          lns_chains=self.lns_chains, lns_rounds=self.lns_rounds, lns_k=self.lns_k,
+                          lns_noise=self.lns_noise, elites=self.elites)
+        res = solve_batch(self.inst, prm)
+        self._take(res.c, res.x, res.n, res.flags, res.scores)
+        if res.lp is not None:
+            self.lp_result = res.lp[0]
+            # a dual bound only once the dual residual is small; PDHG's dual objective is a bound at convergence
+            self.lp_bound = float(res.lp[0]["dual_obj"])
+            sc = float(self._kind_score())
+            self.mip_gap = (sc - self.lp_bound) / max(abs(sc), 1e-12) if self.kind == "min_delay" else None
+        self.log(f"step 1 ({res.search_path}): score {self._kind_score()} flags {self.flags:06b} "
+                 f"lp bound {self.lp_bound} gap {self.mip_gap}")
+        return self.feasible
 
     def score(self):
         return self._kind_score()

@@ -53,39 +53,62 @@ __device__ __forceinline__ uint64_t lns_mix(uint64_t z) {        // splitmix64 f
 __device__ __forceinline__ double lns_u01(uint64_t h) { return (double)(h >> 11) * (1.0 / 9007199254740992.0); }
 __device__ __forceinline__ uint64_t lns_next(uint64_t& s) { s ^= s >> 12; s ^= s << 25; s ^= s >> 27; return s * 2685821657736338717ull; }
 
-struct LnsWarp {            // per-warp shared-memory state
-  double *lam, *base, *costT, *cur, *nxt;
-  unsigned long long* loadfx;
-  float* th;
-  uint8_t *asg, *c, *podlist, *choice;
-  int *npods, *misc;        // misc: J[4] rad[4] mul[4] incT[16] fl[...]
-};
-
+// ---- shared-memory layout -----------------------------------------------------------------------------------
+// block: dT[N][N] (delay, transposed: the hot loops fix a destination j and run the lanes over sources i),
+//        w[F][N], r[F][N], K[N], slots[N]
+// warp : lam[N] | loadfx[N] | bestv[F*N] | scratch (costT | cur | nxt  /  th  /  exception list) | ints | bytes
 __host__ __device__ inline size_t lns_block_shared(int N, int F) {
   return ((size_t)N * N + 2 * (size_t)F * N + (size_t)N) * 8 + (size_t)N * 4 + 64;
 }
-__host__ __device__ inline size_t lns_warp_shared(int N, int F, int k, int smax) {
+__host__ __device__ inline size_t lns_scratch_bytes(int N, int F, int k, int smax) {
   const size_t fn = (size_t)F * N, nT = (size_t)1 << k;
+  size_t dp = (size_t)F * nT * 8 + 2 * (size_t)smax * 8;      // costT, cur, nxt
+  size_t th = fn * 4;                                         // thresholds (float) / exception list (u16)
+  return ((dp > th ? dp : th) + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t lns_warp_shared(int N, int F, int k, int smax) {
+  const size_t fn = (size_t)F * N;
   size_t b = 0;
   b += (size_t)N * 8;               // lam
   b += (size_t)N * 8;               // loadfx
-  b += fn * 8;                      // base
-  b += (size_t)F * nT * 8;          // costT
-  b += 2 * (size_t)smax * 8;        // cur, nxt
-  b += fn * 4;                      // th
-  b += ((size_t)F + 64 + (size_t)F) * 4;   // npods, misc (J, rad, mul, incT, fl)
+  b += fn * 8;                      // bestv
+  b += lns_scratch_bytes(N, F, k, smax);
+  b += ((size_t)F + 64 + (size_t)F) * 4;   // npods, misc (J, rad, mul, incT), fl
   b += 3 * fn;                      // asg, c, podlist
   b += (size_t)F * smax;            // choice
+  b += (size_t)smax + 2 * (size_t)F + 16;  // supp table, oldT, newT
   return (b + 15) & ~(size_t)15;
 }
 
-__global__ void __launch_bounds__(256) k_lns(LnsArgs a) {
+// reduce NT per-lane accumulators over the warp: afterwards lane L holds the warp total of accumulator
+// t(L) = the top log2(NT) bits of L's 5-bit index read as a number (NT = 8: L >> 2; NT = 16: L >> 1)
+template <int NT>
+__device__ __forceinline__ double lns_multi_reduce(double (&acc)[NT], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = NT; n > 1; n >>= 1, off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int t = 0; t < n / 2; ++t) {
+      const double keep = hi ? acc[t + n / 2] : acc[t];
+      const double send = hi ? acc[t] : acc[t + n / 2];
+      acc[t] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  double v = acc[0];
+  for (; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+template <int KK>
+__global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
+  constexpr int NT = 1 << KK;
   const int N = a.N, F = a.F, b = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int chain = blockIdx.x * a.wpb + wid;
-  const int fn = F * N, K_ = a.k, nT = 1 << K_, smax = a.smax;
+  const int fn = F * N, smax = a.smax;
   extern __shared__ __align__(16) unsigned char smem[];
-  double* s_d = (double*)smem;
-  double* s_w = s_d + (size_t)N * N;
+  double* s_dT = (double*)smem;
+  double* s_w = s_dT + (size_t)N * N;
   double* s_r = s_w + fn;
   double* s_K = s_r + fn;
   int* s_slots = (int*)(s_K + N);
@@ -94,7 +117,7 @@ __global__ void __launch_bounds__(256) k_lns(LnsArgs a) {
     const double* d = a.d + (int64_t)b * N * N;
     const double* w = a.w + (int64_t)b * fn;
     const double* r = a.r + (int64_t)b * fn;
-    for (int q = threadIdx.x; q < N * N; q += blockDim.x) s_d[q] = d[q];
+    for (int q = threadIdx.x; q < N * N; q += blockDim.x) { const int i = q / N, j = q - i * N; s_dT[j * N + i] = d[q]; }
     for (int q = threadIdx.x; q < fn; q += blockDim.x) { s_w[q] = w[q]; s_r[q] = r[q]; }
     const double m0 = a.m[(int64_t)b * F];
     for (int j = threadIdx.x; j < N; j += blockDim.x) {
@@ -108,12 +131,12 @@ __global__ void __launch_bounds__(256) k_lns(LnsArgs a) {
     // instance scalars: mean workload, mean off-diagonal delay (noise scale), objective weights
     double sw = 0.0, sd = 0.0, wm = 0.0;
     for (int q = lane; q < fn; q += 32) sw += s_w[q];
-    for (int q = lane; q < N * N; q += 32) sd += s_d[q];
+    for (int q = lane; q < N * N; q += 32) sd += s_dT[q];
     for (int fi = lane; fi < fn; fi += 32) {
       const int f = fi / N, i = fi - f * N;
       const double md = a.maxd ? a.maxd[(int64_t)b * F + f] : INFINITY;
       double best = -INFINITY;
-      for (int j = 0; j < N; ++j) { const double v = s_d[i * N + j]; if (v <= md && v > best) best = v; }
+      for (int j = 0; j < N; ++j) { const double v = s_dT[j * N + i]; if (v <= md && v > best) best = v; }
       wm += s_w[fi] * best;
     }
     sw = warp_sum(sw); sd = warp_sum(sd); wm = warp_sum(wm);
@@ -131,21 +154,26 @@ __global__ void __launch_bounds__(256) k_lns(LnsArgs a) {
   const double noise0 = s_scal[0], u = s_scal[1], a_d = s_scal[2];
 
   // ---- per-warp state ------------------------------------------------------------------------------------
-  unsigned char* wp = smem + ((lns_block_shared(N, F) + 15) & ~(size_t)15) + (size_t)wid * lns_warp_shared(N, F, K_, smax);
+  unsigned char* wp = smem + ((lns_block_shared(N, F) + 15) & ~(size_t)15) + (size_t)wid * lns_warp_shared(N, F, KK, smax);
   double* lam = (double*)wp; wp += (size_t)N * 8;
   unsigned long long* loadfx = (unsigned long long*)wp; wp += (size_t)N * 8;
-  double* base = (double*)wp; wp += (size_t)fn * 8;
-  double* costT = (double*)wp; wp += (size_t)F * nT * 8;
-  double* cur = (double*)wp; wp += (size_t)smax * 8;
-  double* nxt = (double*)wp; wp += (size_t)smax * 8;
-  float* th = (float*)wp; wp += (size_t)fn * 4;
+  double* bestv = (double*)wp; wp += (size_t)fn * 8;
+  unsigned char* scratch = wp; wp += lns_scratch_bytes(N, F, KK, smax);
+  double* costT = (double*)scratch;                       // [F][NT]
+  double* cur = costT + (size_t)F * NT;
+  double* nxt = cur + smax;
+  float* th = (float*)scratch;                            // aliases the DP arrays (never live together)
+  unsigned short* exl = (unsigned short*)scratch;         // exception list, ditto
   int* npods = (int*)wp; wp += (size_t)F * 4;
   int* misc = (int*)wp; wp += 64 * 4;
   int* fl = (int*)wp; wp += (size_t)F * 4;
   uint8_t* asg = wp; wp += fn;
   uint8_t* c = wp; wp += fn;
   uint8_t* podlist = wp; wp += fn;
-  uint8_t* choice = wp;
+  uint8_t* choice = wp; wp += (size_t)F * smax;
+  uint8_t* suppT = wp; wp += smax;
+  uint8_t* oldT = wp; wp += F;
+  uint8_t* newT = wp;
   int* Jn = misc; int* rad = misc + 4; int* mul = misc + 8; int* incT = misc + 12;      // incT[16]
 
   uint64_t rs = a.rng ^ (0x9E3779B97F4A7C15ull * (uint64_t)(chain + 1)) ^ (0xD1B54A32D192ED03ull * (uint64_t)(b + 1));
@@ -200,15 +228,41 @@ __global__ void __launch_bounds__(256) k_lns(LnsArgs a) {
     }
   }
   __syncwarp();
-  auto rebuild_pods = [&]() {
-    for (int f = lane; f < F; f += 32) {
-      int n = 0;
-      for (int j = 0; j < N; ++j) if (c[f * N + j]) podlist[f * N + n++] = (uint8_t)j;
-      npods[f] = n;
+
+  // pod list of one function, ascending (ballot compaction; warp-uniform call)
+  auto rebuild_pods = [&](int f) {
+    int n = 0;
+    for (int jb = 0; jb < N; jb += 32) {
+      const int j = jb + lane;
+      const bool on = j < N && c[f * N + j];
+      const unsigned bal = __ballot_sync(0xffffffffu, on);
+      if (on) podlist[f * N + n + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)j;
+      n += __popc(bal);
     }
+    if (lane == 0) npods[f] = n;
     __syncwarp();
   };
-  rebuild_pods();
+  // nearest priced pod of every source of f (lanes over sources, pods in a warp-uniform loop); `skip` < 0: none excluded
+  auto scan_function = [&](int f) {
+    const int np = npods[f];
+    const uint8_t* pl = podlist + f * N;
+    const double* rf = s_r + f * N;
+    for (int ib = 0; ib < N; ib += 32) {
+      const int i = ib + lane;
+      double best = kLnsBig; int bj = 255;
+      if (i < N) {
+        for (int q = 0; q < np; ++q) {
+          const int j = pl[q];
+          const double v = s_dT[j * N + i] + lam[j] * rf[j];
+          if (v < best) { best = v; bj = j; }
+        }
+        bestv[f * N + i] = best; asg[f * N + i] = (uint8_t)bj;
+      }
+    }
+  };
+  for (int f = 0; f < F; ++f) rebuild_pods(f);
+  for (int f = 0; f < F; ++f) scan_function(f);
+  __syncwarp();
 
   double bestg = INFINITY; int best_round = -1;
   uint8_t* outc = a.out_c + ((int64_t)b * a.chains + chain) * fn;
@@ -216,78 +270,72 @@ __global__ void __launch_bounds__(256) k_lns(LnsArgs a) {
 
   for (int round = 0; round <= a.rounds; ++round) {
     // ---- neighbourhood: a random node and k-1 nodes near it (tournaments on d), or k random nodes ----------
-    int kk = K_;
+    int kk = KK;
     uint64_t jm0 = 0, jm1 = 0;
     {
-      int J[kLnsMaxK];
+      int J[KK];
       const uint64_t h0 = lns_next(rs);
-      J[0] = (int)(h0 % (uint64_t)N);
+      J[0] = (int)(((h0 & 0xffffffffull) * (uint64_t)N) >> 32);
       const bool local = ((h0 >> 40) & 3) != 0;
       int have = 1;
-      for (int tries = 0; have < K_ && tries < 16 * K_; ++tries) {
+      for (int tries = 0; have < KK && tries < 16 * KK; ++tries) {
         int bj = -1; double bd = INFINITY;
         const uint64_t h = lns_next(rs);
         const int tsize = local ? 1 + (int)((h >> 50) & 3) : 1;
         uint64_t hh = h;
         for (int t = 0; t < tsize; ++t) {
           hh = lns_mix(hh + t);
-          const int j = (int)(hh % (uint64_t)N);
+          const int j = (int)(((hh & 0xffffffffull) * (uint64_t)N) >> 32);
           bool dup = false;
-          for (int q = 0; q < have; ++q) dup = dup || J[q] == j;
+#pragma unroll
+          for (int q = 0; q < KK; ++q) dup = dup || (q < have && J[q] == j);
           if (dup) continue;
-          const double dv = s_d[J[(hh >> 33) % (uint64_t)have] * N + j];
+          const int pick = (int)((((hh >> 32) & 0xffffull) * (uint64_t)have) >> 16);
+          int jp = J[0];
+#pragma unroll
+          for (int q = 1; q < KK; ++q) if (q == pick) jp = J[q];
+          const double dv = s_dT[j * N + jp];
           if (dv < bd) { bd = dv; bj = j; }
         }
-        if (bj >= 0) J[have++] = bj;
+        if (bj >= 0) {
+#pragma unroll
+          for (int q = 1; q < KK; ++q) if (q == have) J[q] = bj;
+          ++have;
+        }
       }
       kk = have;
       // state space of the slot counters must fit: drop trailing nodes otherwise
       int S_ = 1, fit = 0;
-      for (int q = 0; q < kk; ++q) { const int rd = s_slots[J[q]] + 1; if ((int64_t)S_ * rd > smax) break; S_ *= rd; ++fit; }
+#pragma unroll
+      for (int q = 0; q < KK; ++q) {
+        if (q < kk && fit == q) { const int rd = s_slots[J[q]] + 1; if ((int64_t)S_ * rd <= smax) { S_ *= rd; ++fit; } }
+      }
       kk = fit;
       if (lane == 0) {
         int mu_ = 1;
-        for (int q = 0; q < kk; ++q) { Jn[q] = J[q]; rad[q] = s_slots[J[q]] + 1; mul[q] = mu_; mu_ *= rad[q]; }
+#pragma unroll
+        for (int q = 0; q < KK; ++q) if (q < kk) { Jn[q] = J[q]; rad[q] = s_slots[J[q]] + 1; mul[q] = mu_; mu_ *= rad[q]; }
         misc[32] = mu_;                                    // number of states
       }
-      for (int q = 0; q < kk; ++q) { if (J[q] < 64) jm0 |= 1ull << J[q]; else jm1 |= 1ull << (J[q] - 64); }
+#pragma unroll
+      for (int q = 0; q < KK; ++q) if (q < kk) { if (J[q] < 64) jm0 |= 1ull << J[q]; else jm1 |= 1ull << (J[q] - 64); }
     }
     __syncwarp();
-    if (kk == 0) continue;
-    const int nTk = 1 << kk;
-    for (int T = lane; T < nTk; T += 32) { int s = 0; for (int q = 0; q < kk; ++q) if ((T >> q) & 1) s += mul[q]; incT[T] = s; }
+    auto inJ = [&](int j) -> bool { return j < 64 ? (jm0 >> j) & 1 : (j < 128 ? (jm1 >> (j - 64)) & 1 : false); };
 
-    // ---- priced routing of the current placement + dual ascent on the node prices ---------------------------
-    double g = 0.0; bool overloaded = false;
+    // ---- CPU loads at the current prices; dual ascent on the prices of overloaded / priced nodes -----------------
+    bool overloaded = false;
     for (int pass = 0; pass < 4; ++pass) {
       for (int j = lane; j < N; j += 32) loadfx[j] = 0ull;
       __syncwarp();
-      double gp = 0.0;
       for (int fi = lane; fi < fn; fi += 32) {
-        const int f = fi / N, i = fi - f * N;
-        const double* di = s_d + i * N;
-        const double* rf = s_r + f * N;
-        const uint8_t* pl = podlist + f * N;
-        const int np = npods[f];
-        double best = kLnsBig, bout = kLnsBig; int bj = 0;
-        for (int q = 0; q < np; ++q) {
-          const int j = pl[q];
-          const double v = di[j] + lam[j] * rf[j];
-          if (v < best) { best = v; bj = j; }
-          const bool inJ = j < 64 ? (jm0 >> j) & 1 : (jm1 >> (j - 64)) & 1;
-          if (!inJ && v < bout) bout = v;
-        }
-        asg[fi] = (uint8_t)bj; base[fi] = bout;
-        const double wv = s_w[fi];
-        if (wv > 0.0) {
-          gp += wv * best;
-          const double ld = wv * rf[bj];
-          if (ld > 0.0) atomicAdd(&loadfx[bj], (unsigned long long)(fmin(ld, 1e9) * kFxScale + 0.5));
-        }
+        const int bj = asg[fi];
+        if (bj == 255) continue;
+        const int f = fi / N;
+        const double ld = s_w[fi] * s_r[f * N + bj];
+        if (ld > 0.0) atomicAdd(&loadfx[bj], (unsigned long long)(fmin(ld, 1e9) * kFxScale + 0.5));
       }
-      g = warp_sum(gp);
       __syncwarp();
-      // nodes to (re)price: overloaded at the current prices, or carrying a price
       bool changed = false; overloaded = false;
       for (int jb = 0; jb < N; jb += 32) {
         const int j = jb + lane;
@@ -306,107 +354,169 @@ __global__ void __launch_bounds__(256) k_lns(LnsArgs a) {
           int nf = 0;
           for (int f = 0; f < F; ++f) if (c[f * N + jj]) { if (lane == 0) fl[nf] = f; ++nf; }
           __syncwarp();
-          const int M = nf * N;
           double tot = 0.0;
-          for (int t = lane; t < M; t += 32) {
-            const int f = fl[t / N], i = t % N;
-            const double rfj = s_r[f * N + jj], av = s_w[f * N + i] * rfj;
-            float tv = 0.0f;
-            if (av > 0.0) {
-              const double* di = s_d + i * N; const double* rf = s_r + f * N; const uint8_t* pl = podlist + f * N;
-              double alt = kLnsBig;
-              for (int q = 0; q < npods[f]; ++q) { const int j2 = pl[q]; if (j2 == jj) continue; const double v = di[j2] + lam[j2] * rf[j2]; if (v < alt) alt = v; }
-              const double tq = (alt - di[jj]) / rfj;
-              if (tq > 0.0) { tv = (float)fmin(tq, 1e30); tot += av; }
+          for (int z = 0; z < nf; ++z) {
+            const int f = fl[z];
+            const double rfj = s_r[f * N + jj];
+            const double* rf = s_r + f * N; const uint8_t* pl = podlist + f * N; const int np = npods[f];
+            for (int ib = 0; ib < N; ib += 32) {
+              const int i = ib + lane;
+              if (i >= N) continue;
+              const double av = s_w[f * N + i] * rfj;
+              float tv = 0.0f;
+              if (av > 0.0) {
+                double alt = kLnsBig;
+                for (int q = 0; q < np; ++q) { const int j2 = pl[q]; if (j2 == jj) continue; const double v = s_dT[j2 * N + i] + lam[j2] * rf[j2]; if (v < alt) alt = v; }
+                const double tq = (alt - s_dT[jj * N + i]) / rfj;
+                if (tq > 0.0) { tv = (float)fmin(tq, 1e30); tot += av; }
+              }
+              th[z * N + i] = tv;                           // 0: never uses jj
             }
-            th[t] = tv;                                     // 0: never uses jj
           }
+          const int M = nf * N;
           tot = warp_sum(tot);
           __syncwarp();
           double nl = 0.0;
           if (tot > s_K[jj] + 1e-9) {
             // flows leave in ascending threshold order until the rest fits; the price is the last threshold
             float last = 0.0f;
-            for (int it = 0; it < 4 * N * 8 && tot > s_K[jj] + 1e-9; ++it) {
+            for (int it = 0; it < M && tot > s_K[jj] + 1e-9; ++it) {
               unsigned mn = 0xffffffffu;
               for (int t = lane; t < M; t += 32) { const float tv = th[t]; if (tv > last) mn = min(mn, __float_as_uint(tv)); }
               mn = __reduce_min_sync(0xffffffffu, mn);
               if (mn == 0xffffffffu) break;                 // nothing left to move: stays overloaded
               last = __uint_as_float(mn);
               double rem = 0.0;
-              for (int t = lane; t < M; t += 32) if (th[t] == last) rem += s_w[fl[t / N] * N + t % N] * s_r[fl[t / N] * N + jj];
+              for (int t = lane; t < M; t += 32) if (th[t] == last) { const int z = t / N; rem += s_w[fl[z] * N + (t - z * N)] * s_r[fl[z] * N + jj]; }
               tot -= warp_sum(rem);
             }
             nl = (double)last * (1.0 + 2e-6) + 1e-12;
           }
-          if (fabs(nl - lam[jj]) > 1e-10 * (1.0 + nl)) changed = true;
+          const bool ch = fabs(nl - lam[jj]) > 1e-10 * (1.0 + nl);
           __syncwarp();
-          if (lane == 0) lam[jj] = nl;
-          __syncwarp();
+          if (ch) {
+            changed = true;
+            if (lane == 0) lam[jj] = nl;
+            __syncwarp();
+            for (int z = 0; z < nf; ++z) scan_function(fl[z]);      // their sources see a new price on jj
+            __syncwarp();
+          }
         }
       }
       if (!changed) break;
     }
+    // ---- priced objective of the current placement, record ------------------------------------------------------
     {
-      double lk = 0.0;
-      for (int j = lane; j < N; j += 32) lk += lam[j] * s_K[j];
-      g -= warp_sum(lk);
+      double gp = 0.0;
+      for (int fi = lane; fi < fn; fi += 32) { const double wv = s_w[fi]; if (wv > 0.0) gp += wv * bestv[fi]; }
+      for (int j = lane; j < N; j += 32) gp -= lam[j] * s_K[j];
+      double g = warp_sum(gp);
       if (u != 0.0) {
         int act = 0;
         for (int j = lane; j < N; j += 32) { int any = 0; for (int f = 0; f < F; ++f) any |= c[f * N + j]; act += any; }
         act = __reduce_add_sync(0xffffffffu, act);
         g += u * (double)act;
       }
-    }
-    // ---- record ------------------------------------------------------------------------------------------
-    if (!overloaded && g < bestg - 1e-9 * (1.0 + fabs(g))) {
-      bestg = g; best_round = round;
-      for (int q = lane; q < fn; q += 32) outc[q] = c[q];
+      if (!overloaded && g < bestg - 1e-9 * (1.0 + fabs(g))) {
+        bestg = g; best_round = round;
+        for (int q = lane; q < fn; q += 32) outc[q] = c[q];
+      }
     }
     if (round == a.rounds) break;
+    if (kk == 0) continue;
 
-    // ---- cost of every subset T of the k nodes, per function -------------------------------------------------
+    // ---- sources served from the k nodes: their nearest pod OUTSIDE the k nodes (compacted list, then a scan) ------
+    int nex = 0;
+    for (int fb = 0; fb < fn; fb += 32) {
+      const int fi = fb + lane;
+      const bool ex = fi < fn && asg[fi] != 255 && inJ(asg[fi]);
+      const unsigned bal = __ballot_sync(0xffffffffu, ex);
+      if (ex) exl[nex + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)fi;
+      nex += __popc(bal);
+    }
+    __syncwarp();
+    for (int e = lane; e < nex; e += 32) {
+      const int fi = exl[e], f = fi / N, i = fi - f * N;
+      const uint8_t* pl = podlist + f * N; const double* rf = s_r + f * N; const int np = npods[f];
+      double best = kLnsBig; int bj = 255;
+      for (int q = 0; q < np; ++q) {
+        const int j = pl[q];
+        if (inJ(j)) continue;
+        const double v = s_dT[j * N + i] + lam[j] * rf[j];
+        if (v < best) { best = v; bj = j; }
+      }
+      bestv[fi] = best; asg[fi] = (uint8_t)bj;             // (bestv, asg) now describe "the k nodes closed" for every source
+    }
+    __syncwarp();
+
+    // ---- cost of every subset T of the k nodes, per function (lanes over sources, NT accumulators per lane) ------
     const double temp = round < anneal_rounds ? noise0 * (1.0 - (double)round / (double)anneal_rounds) : 0.0;
-    const int groups = 32 / nTk, T = lane & (nTk - 1), ig = lane / nTk;
     const uint64_t rround = lns_next(rs);
-    for (int f = 0; f < F; ++f) {
-      double pj[kLnsMaxK];
+    const int Tvalid = (1 << kk) - 1;
+    int Jr[KK];
 #pragma unroll
-      for (int q = 0; q < kLnsMaxK; ++q) pj[q] = q < kk ? lam[Jn[q]] * s_r[f * N + Jn[q]] : 0.0;
-      double acc = 0.0; int outside = 0;
-      for (int q = 0; q < npods[f]; ++q) { const int j = podlist[f * N + q]; outside |= !(j < 64 ? (jm0 >> j) & 1 : (jm1 >> (j - 64)) & 1); }
-      for (int i = ig; i < N; i += groups) {
+    for (int q = 0; q < KK; ++q) Jr[q] = q < kk ? Jn[q] : 0;
+    for (int f = lane; f < F; f += 32) {
+      int ot = 0;
+#pragma unroll
+      for (int q = 0; q < KK; ++q) if (q < kk && c[f * N + Jr[q]]) ot |= 1 << q;
+      oldT[f] = (uint8_t)ot;
+    }
+    __syncwarp();
+    for (int f = 0; f < F; ++f) {
+      double pj[KK];
+#pragma unroll
+      for (int q = 0; q < KK; ++q) pj[q] = q < kk ? lam[Jr[q]] * s_r[f * N + Jr[q]] : kLnsBig;
+      double acc[NT];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) acc[t] = 0.0;
+      for (int ib = 0; ib < N; ib += 32) {
+        const int i = ib + lane;
+        if (i >= N) continue;
         const double wv = s_w[f * N + i];
         if (wv == 0.0) continue;
-        double val = base[f * N + i];
+        double val[NT];
+        val[0] = bestv[f * N + i];
+        double vq[KK];
 #pragma unroll
-        for (int q = 0; q < kLnsMaxK; ++q) if (q < kk && ((T >> q) & 1)) val = fmin(val, s_d[i * N + Jn[q]] + pj[q]);
-        acc += wv * val;
+        for (int q = 0; q < KK; ++q) vq[q] = s_dT[Jr[q] * N + i] + pj[q];
+#pragma unroll
+        for (int t = 1; t < NT; ++t) val[t] = fmin(val[t & (t - 1)], vq[__ffs(t) - 1]);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc[t] += wv * val[t];
       }
-      for (int o = nTk; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane < nTk) {
-        double v = acc;
+      const double tot = lns_multi_reduce<NT>(acc, lane);
+      const int T = lane >> (5 - KK);
+      if ((lane & ((32 >> KK) - 1)) == 0) {
+        double v = tot;
         if (temp > 0.0) v += temp * lns_u01(lns_mix(rround ^ ((uint64_t)(f * 64 + T) << 8))) * (double)__popc(T);
-        if (T == 0 && !outside) v = INFINITY;               // the function would lose its last pod
-        costT[f * nT + T] = v;
+        const bool outside = npods[f] - __popc((unsigned)oldT[f]) > 0;
+        if ((T & ~Tvalid) != 0 || (T == 0 && !outside)) v = INFINITY;     // dropped node / the function would lose its last pod
+        costT[f * NT + T] = v;
       }
     }
     __syncwarp();
 
     // ---- DP over functions, state = slot counters of the k nodes -----------------------------------------------
     const int S_ = misc[32];
-    for (int s = lane; s < S_; s += 32) cur[s] = s == 0 ? 0.0 : INFINITY;
+    for (int T = lane; T < NT; T += 32) { int s = 0; for (int q = 0; q < kk; ++q) if ((T >> q) & 1) s += mul[q]; incT[T] = s; }
+    for (int s = lane; s < S_; s += 32) {
+      int supp = 0;
+      for (int q = 0; q < kk; ++q) if ((s / mul[q]) % rad[q] > 0) supp |= 1 << q;
+      suppT[s] = (uint8_t)supp;
+      cur[s] = s == 0 ? 0.0 : INFINITY;
+    }
     __syncwarp();
     double* pc = cur; double* pn = nxt;
     for (int f = 0; f < F; ++f) {
+      const double* ct = costT + f * NT;
       for (int s2 = lane; s2 < S_; s2 += 32) {
-        int supp = 0;
-        for (int q = 0; q < kk; ++q) if ((s2 / mul[q]) % rad[q] > 0) supp |= 1 << q;
+        const int supp = suppT[s2];
         double best = INFINITY; int bt = 0;
         int Ts = supp;
         while (true) {
-          const double v = pc[s2 - incT[Ts]] + costT[f * nT + Ts];
-          if (v < best || (v == best && Ts < bt)) { best = v; bt = Ts; }
+          const double v = pc[s2 - incT[Ts]] + ct[Ts];
+          if (v < best) { best = v; bt = Ts; }
           if (Ts == 0) break;
           Ts = (Ts - 1) & supp;
         }
@@ -419,23 +529,46 @@ __global__ void __launch_bounds__(256) k_lns(LnsArgs a) {
     double bv = INFINITY; int bs = 0x7fffffff;
     for (int s = lane; s < S_; s += 32) {
       double v = pc[s];
-      if (u != 0.0) { int used = 0; for (int q = 0; q < kk; ++q) used += (s / mul[q]) % rad[q] > 0; v += u * (double)used; }
+      if (u != 0.0) v += u * (double)__popc((unsigned)suppT[s]);
       if (v < bv) { bv = v; bs = s; }
     }
     for (int o = 16; o > 0; o >>= 1) {
       const double v2 = __shfl_xor_sync(0xffffffffu, bv, o); const int s2 = __shfl_xor_sync(0xffffffffu, bs, o);
       if (v2 < bv || (v2 == bv && s2 < bs)) { bv = v2; bs = s2; }
     }
-    if (bv < INFINITY && lane == 0) {
-      int s = bs;
-      for (int f = F - 1; f >= 0; --f) {
-        const int Tc = choice[f * smax + s];
-        for (int q = 0; q < kk; ++q) c[f * N + Jn[q]] = (Tc >> q) & 1;
-        s -= incT[Tc];
+    if (lane == 0) {
+      if (bv < INFINITY) {
+        int s = bs;
+        for (int f = F - 1; f >= 0; --f) { const int Tc = choice[f * smax + s]; newT[f] = (uint8_t)Tc; s -= incT[Tc]; }
+      } else {
+        for (int f = 0; f < F; ++f) newT[f] = oldT[f];
       }
     }
     __syncwarp();
-    rebuild_pods();
+    // ---- apply: pods of the k nodes, then the nearest pod of every source of the functions that use them ---------
+    for (int f = 0; f < F; ++f) {
+      const int nt_ = newT[f], ot_ = oldT[f];
+      if (nt_ != ot_) {
+        if (lane < kk) c[f * N + Jn[lane]] = (nt_ >> lane) & 1;
+        __syncwarp();
+        rebuild_pods(f);
+      }
+      if (nt_ == 0) continue;
+      double pj[KK];
+#pragma unroll
+      for (int q = 0; q < KK; ++q) pj[q] = q < kk ? lam[Jr[q]] * s_r[f * N + Jr[q]] : kLnsBig;
+      for (int ib = 0; ib < N; ib += 32) {
+        const int i = ib + lane;
+        if (i >= N) continue;
+        double best = bestv[f * N + i]; int bj = asg[f * N + i];
+#pragma unroll
+        for (int q = 0; q < KK; ++q) {
+          if (q < kk && ((nt_ >> q) & 1)) { const double v = s_dT[Jr[q] * N + i] + pj[q]; if (v < best || (v == best && Jr[q] < bj)) { best = v; bj = Jr[q]; } }
+        }
+        bestv[f * N + i] = best; asg[f * N + i] = (uint8_t)bj;
+      }
+    }
+    __syncwarp();
   }
   if (lane == 0) {
     a.out_g[(int64_t)b * a.chains + chain] = bestg < INFINITY ? a_d * bestg : INFINITY;
@@ -454,7 +587,7 @@ extern "C" int neptune_lns_search(int B, int N, int F, int kind, double alpha, i
                                   const double* maxd, const double* guide, const double* lam0, int S,
                                   const uint8_t* seeds, uint8_t* out_c, double* out_g, int32_t* out_round,
                                   void* stream) {
-  if (B <= 0 || N <= 0 || F <= 0 || chains <= 0 || rounds < 0 || k < 1 || k > kLnsMaxK || !d || !w || !r || !m || !Mj ||
+  if (B <= 0 || N <= 0 || F <= 0 || chains <= 0 || rounds < 0 || k < 2 || k > kLnsMaxK || !d || !w || !r || !m || !Mj ||
       !Kj || !out_c || !out_g || !out_round)
     return NEPTUNE_E_ARG;
   if (kind != NEPTUNE_KIND_MIN_DELAY && kind != NEPTUNE_KIND_MIN_DELAY_UTIL) return NEPTUNE_E_ARG;
@@ -470,13 +603,23 @@ extern "C" int neptune_lns_search(int B, int N, int F, int kind, double alpha, i
   const size_t blk = (lns_block_shared(N, F) + 15) & ~(size_t)15;
   int wpb = 8;
   size_t per = lns_warp_shared(N, F, k, smax);
-  while (wpb > 1 && blk + wpb * per > 100 * 1024) wpb >>= 1;          // aim at two blocks per SM
+  while (wpb > 1 && blk + wpb * per > 110 * 1024) wpb >>= 1;          // aim at two blocks per SM
   if (blk + wpb * per > 200 * 1024) return NEPTUNE_E_SIZE;
   if (wpb > chains) { wpb = 1; while (wpb * 2 <= chains) wpb *= 2; }
   a.smax = smax; a.wpb = wpb;
   const size_t sm = blk + wpb * per;
-  NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_lns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  { k_lns<<<dim3((chains + wpb - 1) / wpb, B), wpb * 32, sm, (cudaStream_t)stream>>>(a); NEPTUNE_COUNT(1); }
+  const dim3 grid((chains + wpb - 1) / wpb, B);
+  if (k == 3) {
+    NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_lns<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_lns<3><<<grid, wpb * 32, sm, (cudaStream_t)stream>>>(a);
+  } else if (k == 4) {
+    NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_lns<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_lns<4><<<grid, wpb * 32, sm, (cudaStream_t)stream>>>(a);
+  } else {
+    NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_lns<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_lns<2><<<grid, wpb * 32, sm, (cudaStream_t)stream>>>(a);
+  }
+  NEPTUNE_COUNT(1);
   NEPTUNE_LAUNCH_OK();
   return 0;
 }

@@ -170,8 +170,10 @@ __device__ inline CapResult cap_route(const CapRoute& q, int max_rounds, double*
       if (rh >= 0.0 && (rh <= lo || (rh <= hi && mv >= 1.0))) q.ch[fi] = q.alt[fi];
     }
     __syncthreads();
-    if (mv > 0.0 && mv < 1.0) {
-      for (int fi = tid; fi < F * N; fi += blockDim.x) {
+    if (mv > 0.0 && mv < 1.0 && tid == 0) {
+      // the marginal flows (usually one) are handled one after the other by a single thread, in ascending index
+      // order: each decision reads the shares its predecessors left behind, so tied thresholds cannot race
+      for (int fi = 0; fi < F * N; ++fi) {
         const double rh = q.rho[fi];
         if (rh < 0.0 || rh <= lo || rh > hi) continue;
         // C1b (constraints_step1.py:12-15): the pod (f, js) must keep a total share >= 1 - eps.  If this

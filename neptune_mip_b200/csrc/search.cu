@@ -173,8 +173,14 @@ __device__ Cost full_cost(const LsArgs& a, const Chain& k, const double* w, cons
 
 // One elementary change of function f (remove pod j_out and/or add pod j_in), evaluated by one warp:
 // returns the delay change (valid in every lane) and accumulates CPU-load changes into delta[].
+// Load deltas are accumulated in fixed point (2^-30 cores): integer adds commute, so the sum does not depend on
+// the order in which the lanes' atomics land and a run is bit-reproducible.
+constexpr double kFxLoad = 1073741824.0;
+__device__ __forceinline__ void fx_add(unsigned long long* p, double v) {
+  atomicAdd(p, (unsigned long long)(long long)llrint(fmax(fmin(v, 4e9), -4e9) * kFxLoad));
+}
 __device__ double eval_change(const LsArgs& a, const Chain& k, const double* w, const double* r,
-                              const double* dT, int f, int j_out, int j_in, double* delta) {
+                              const double* dT, int f, int j_out, int j_in, unsigned long long* delta) {
   const int N = a.N, lane = threadIdx.x & 31;
   const double* b1 = k.b1 + (int64_t)f * N; const double* b2 = k.b2 + (int64_t)f * N;
   const int* a1 = k.a1 + (int64_t)f * N; const int* a2 = k.a2 + (int64_t)f * N;
@@ -191,8 +197,8 @@ __device__ double eval_change(const LsArgs& a, const Chain& k, const double* w, 
       const double wv = wf[i];
       if (wv != 0.0) {
         dd += wv * (nb - ob);
-        if (oa >= 0) atomicAdd(delta + oa, -wv * rf[oa]);
-        if (na >= 0) atomicAdd(delta + na, wv * rf[na]);
+        if (oa >= 0) fx_add(delta + oa, -wv * rf[oa]);
+        if (na >= 0) fx_add(delta + na, wv * rf[na]);
       }
     }
   }
@@ -200,16 +206,17 @@ __device__ double eval_change(const LsArgs& a, const Chain& k, const double* w, 
 }
 
 // penalty change for the accumulated load deltas; clears delta[] again.  One warp.
-__device__ double eval_overload_delta(const LsArgs& a, const Chain& k, const double* Kj, double* delta) {
+__device__ double eval_overload_delta(const LsArgs& a, const Chain& k, const double* Kj, unsigned long long* delta) {
   const int N = a.N, lane = threadIdx.x & 31;
   __syncwarp();
   double dv = 0.0;
   for (int j = lane; j < N; j += 32) {
-    const double dl = delta[j];
-    if (dl != 0.0) {
+    const unsigned long long raw = delta[j];
+    if (raw != 0ull) {
+      const double dl = (double)(long long)raw * (1.0 / kFxLoad);
       const double o0 = fmax(k.load[j] - Kj[j], 0.0), o1 = fmax(k.load[j] + dl - Kj[j], 0.0);
       dv += (o1 > 1e-9 ? o1 : 0.0) - (o0 > 1e-9 ? o0 : 0.0);
-      delta[j] = 0.0;
+      delta[j] = 0ull;
     }
   }
   __syncwarp();
@@ -307,7 +314,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1) k_local_searc
   const double mu = scal[1], a_d = scal[2], a_u = scal[3];
   Chain k = carve(a.chain_ws + ((int64_t)b * a.chains + chain) * a.chain_stride, N, F);
   extern __shared__ double dyn[];
-  double* delta = dyn + (int64_t)wid * N;          // per-warp load deltas
+  unsigned long long* delta = reinterpret_cast<unsigned long long*>(dyn) + (int64_t)wid * N;   // per-warp load deltas (fixed point)
   if (a.use_smem) {
     // every move evaluation walks d^T, w, r and the nearest / second-nearest tables of one function: at
     // 50x10 all of it (~60 KB) fits next to three resident blocks per SM, so these reads become
@@ -342,6 +349,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1) k_local_searc
   __shared__ Move mv;
   __shared__ Move batch[kMaxBatch];
   __shared__ int n_batch;
+  __shared__ int scan_sh[THREADS];
   __shared__ int n_pods, n_tabu;
   __shared__ uint64_t s_rand[2];
   __shared__ Move tabu_list[kMaxTabu];
@@ -353,7 +361,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1) k_local_searc
   const int seed_id = chain % a.S;
   const uint8_t* seed = a.seeds + ((int64_t)b * a.S + seed_id) * F * N;
   for (int q = tid; q < F * N; q += blockDim.x) k.c[q] = seed[q];
-  for (int q = tid; q < nw * N; q += blockDim.x) dyn[q] = 0.0;
+  for (int q = tid; q < nw * N; q += blockDim.x) reinterpret_cast<unsigned long long*>(dyn)[q] = 0ull;
   __syncthreads();
   if (a.guide && chain >= a.S && (chain / a.S) % 2 == 1 && tid == 0) {
     // threshold rounding of c-bar, then memory repair (drop the weakest pods) and coverage repair
@@ -480,7 +488,25 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1) k_local_searc
     // ---- pod list -------------------------------------------------------------------------------------
     if (tid == 0) { n_pods = 0; s_rand[0] = rng_next(rs); s_rand[1] = rng_next(rs); }   // only thread 0 owns the RNG
     __syncthreads();
-    for (int q = tid; q < F * N; q += blockDim.x) if (k.c[q]) k.pods[atomicAdd(&n_pods, 1)] = q;
+    {
+      // ordered compaction (ascending q): every thread counts a contiguous chunk, an exclusive scan of the counts
+      // over the block gives its write offset -- the pod list does not depend on thread timing
+      const int chunk = (F * N + (int)blockDim.x - 1) / (int)blockDim.x;
+      const int q0 = tid * chunk, q1 = min(F * N, q0 + chunk);
+      int cnt = 0;
+      for (int q = q0; q < q1; ++q) cnt += k.c[q] != 0;
+      scan_sh[tid] = cnt;
+      __syncthreads();
+      for (int o = 1; o < (int)blockDim.x; o <<= 1) {
+        const int v = tid >= o ? scan_sh[tid - o] : 0;
+        __syncthreads();
+        scan_sh[tid] += v;
+        __syncthreads();
+      }
+      int at = scan_sh[tid] - cnt;
+      for (int q = q0; q < q1; ++q) if (k.c[q]) k.pods[at++] = q;
+      if (tid == (int)blockDim.x - 1) n_pods = scan_sh[tid];
+    }
     __syncthreads();
     const int P = n_pods;
     // swap targets: all nodes for small N, a window of kSwapWindow nodes (rotating with the sweep) beyond

@@ -55,6 +55,8 @@ def main():
                           "lp_bound_gap": [float(f"{(gold[s]['objective'] - lp[k]['dual_obj']) / gold[s]['objective']:.2e}") for k, s in enumerate(seeds)] if lp is not None else None,
                           "lp_iters": [int(v) for v in lp["iters"]] if lp is not None else None,
                           "lp_converged": int(lp["converged"].sum()) if lp is not None else None,
+                          "elite_g_minus_opt": [[round(float(v) - gold[s]["objective"], 2) for v in res.lns_diag["elite_g"][k].cpu()[:4]] for k, s in enumerate(seeds)] if res.lns_diag else None,
+                          "elite_val_minus_opt": [[round(float(v) - gold[s]["objective"], 2) for v in res.lns_diag["elite_val"][k].cpu()[:4]] for k, s in enumerate(seeds)] if res.lns_diag else None,
                           "rounds_of_best": res.lns_round.cpu().tolist() if res.lns_round is not None else None}))
         sys.stdout.flush()
 
