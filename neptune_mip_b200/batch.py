@@ -28,7 +28,7 @@ class BatchParams:
     lns_rounds: int = 6000        # k-node re-optimisations per chain
     lns_k: int = 3
     lns_noise: float = 0.06
-    elites: int = 8               # chain records priced exactly (routing LP) per instance
+    elites: int = 16              # chain records priced exactly (routing LP) per instance
 
 
 @dataclass

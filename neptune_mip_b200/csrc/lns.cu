@@ -63,7 +63,7 @@ __host__ __device__ inline size_t lns_block_shared(int N, int F) {
 __host__ __device__ inline size_t lns_scratch_bytes(int N, int F, int k, int smax) {
   const size_t fn = (size_t)F * N, nT = (size_t)1 << k;
   size_t dp = (size_t)F * nT * 8 + 2 * (size_t)smax * 8;      // costT, cur, nxt
-  size_t th = fn * 4;                                         // thresholds (float) / exception list (u16)
+  size_t th = fn * 4 + fn * 2;                                // thresholds (float) + their scan list (u16) / exception list (u16)
   return ((dp > th ? dp : th) + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t lns_warp_shared(int N, int F, int k, int smax) {
@@ -71,6 +71,7 @@ __host__ __device__ inline size_t lns_warp_shared(int N, int F, int k, int smax)
   size_t b = 0;
   b += (size_t)N * 8;               // lam
   b += (size_t)N * 8;               // loadfx
+  b += (size_t)N * 8;               // lastload
   b += fn * 8;                      // bestv
   b += lns_scratch_bytes(N, F, k, smax);
   b += ((size_t)F + 64 + (size_t)F) * 4;   // npods, misc (J, rad, mul, incT), fl
@@ -157,12 +158,14 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
   unsigned char* wp = smem + ((lns_block_shared(N, F) + 15) & ~(size_t)15) + (size_t)wid * lns_warp_shared(N, F, KK, smax);
   double* lam = (double*)wp; wp += (size_t)N * 8;
   unsigned long long* loadfx = (unsigned long long*)wp; wp += (size_t)N * 8;
+  unsigned long long* lastload = (unsigned long long*)wp; wp += (size_t)N * 8;   // load of a priced node when its price was last settled
   double* bestv = (double*)wp; wp += (size_t)fn * 8;
   unsigned char* scratch = wp; wp += lns_scratch_bytes(N, F, KK, smax);
   double* costT = (double*)scratch;                       // [F][NT]
   double* cur = costT + (size_t)F * NT;
   double* nxt = cur + smax;
   float* th = (float*)scratch;                            // aliases the DP arrays (never live together)
+  unsigned short* thl = (unsigned short*)(scratch + (size_t)fn * 4);   // sources whose threshold needs a pod scan
   unsigned short* exl = (unsigned short*)scratch;         // exception list, ditto
   int* npods = (int*)wp; wp += (size_t)F * 4;
   int* misc = (int*)wp; wp += 64 * 4;
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
 
   // ---- start placement -----------------------------------------------------------------------------------
   for (int q = lane; q < fn; q += 32) c[q] = 0;
-  for (int j = lane; j < N; j += 32) lam[j] = a.lam0 ? fmax(a.lam0[(int64_t)b * N + j], 0.0) : 0.0;
+  for (int j = lane; j < N; j += 32) { lam[j] = a.lam0 ? fmax(a.lam0[(int64_t)b * N + j], 0.0) : 0.0; lastload[j] = ~0ull; }
   __syncwarp();
   const bool from_seed = a.seeds && (!a.guide || chain < a.S);
   if (from_seed) {
@@ -324,7 +327,11 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
     auto inJ = [&](int j) -> bool { return j < 64 ? (jm0 >> j) & 1 : (j < 128 ? (jm1 >> (j - 64)) & 1 : false); };
 
     // ---- CPU loads at the current prices; dual ascent on the prices of overloaded / priced nodes -----------------
-    bool overloaded = false;
+    // A node is (re)priced when it is overloaded, or when it carries a price and its load moved since that price
+    // was settled.  Price of node jj = the threshold at which enough of its flows leave:  a source (f,i) uses jj
+    // while  lam_jj < th = (best priced alternative - d[i,jj]) / r[f,jj];  flows leave in ascending th until the
+    // rest fits K_jj; ties with the alternative (th = 0) leave first, at a price of 1e-9.
+    bool overloaded = false, settled = false;
     for (int pass = 0; pass < 4; ++pass) {
       for (int j = lane; j < N; j += 32) loadfx[j] = 0ull;
       __syncwarp();
@@ -343,43 +350,60 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
         if (j < N) {
           const double ld = (double)loadfx[j] * (1.0 / kFxScale);
           over = ld > s_K[j] + 1e-7;
-          need = over || lam[j] > 0.0;
+          need = over || (lam[j] > 0.0 && loadfx[j] != lastload[j]);
         }
         unsigned todo = __ballot_sync(0xffffffffu, need);
         overloaded = overloaded || __any_sync(0xffffffffu, over);
         if (pass == 3) continue;                           // last pass only evaluates
         while (todo) {
           const int jj = jb + (__ffs(todo) - 1); todo &= todo - 1;
-          // thresholds of the sources that can use node jj:  th = (priced alternative - d[i,jj]) / r[f,jj]
           int nf = 0;
-          for (int f = 0; f < F; ++f) if (c[f * N + jj]) { if (lane == 0) fl[nf] = f; ++nf; }
-          __syncwarp();
-          double tot = 0.0;
-          for (int z = 0; z < nf; ++z) {
-            const int f = fl[z];
-            const double rfj = s_r[f * N + jj];
-            const double* rf = s_r + f * N; const uint8_t* pl = podlist + f * N; const int np = npods[f];
-            for (int ib = 0; ib < N; ib += 32) {
-              const int i = ib + lane;
-              if (i >= N) continue;
-              const double av = s_w[f * N + i] * rfj;
-              float tv = 0.0f;
-              if (av > 0.0) {
-                double alt = kLnsBig;
-                for (int q = 0; q < np; ++q) { const int j2 = pl[q]; if (j2 == jj) continue; const double v = s_dT[j2 * N + i] + lam[j2] * rf[j2]; if (v < alt) alt = v; }
-                const double tq = (alt - s_dT[jj * N + i]) / rfj;
-                if (tq > 0.0) { tv = (float)fmin(tq, 1e30); tot += av; }
-              }
-              th[z * N + i] = tv;                           // 0: never uses jj
-            }
+          for (int fb = 0; fb < F; fb += 32) {
+            const int f = fb + lane;
+            const bool on = f < F && c[f * N + jj];
+            const unsigned bal = __ballot_sync(0xffffffffu, on);
+            if (on) fl[nf + __popc(bal & ((1u << lane) - 1u))] = f;
+            nf += __popc(bal);
           }
+          __syncwarp();
           const int M = nf * N;
+          // thresholds: a source whose nearest priced pod is not jj has that pod as its alternative; the sources
+          // currently ON jj need their second-best pod -- a pod scan, done for the compacted list of them only
+          double tot = 0.0; int nscan = 0;
+          for (int tb = 0; tb < M; tb += 32) {
+            const int t = tb + lane;
+            bool scan = false;
+            if (t < M) {
+              const int z = t / N, i = t - z * N, f = fl[z];
+              const double rfj = s_r[f * N + jj], av = s_w[f * N + i] * rfj;
+              float tv = -1.0f;                              // never uses jj
+              if (av > 0.0) {
+                if (asg[f * N + i] != jj) {
+                  const double tq = (bestv[f * N + i] - s_dT[jj * N + i]) / rfj;
+                  if (tq >= 0.0) { tv = (float)fmin(tq, 1e30); tot += av; }
+                } else scan = true;
+              }
+              th[t] = tv;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, scan);
+            if (scan) thl[nscan + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)t;
+            nscan += __popc(bal);
+          }
+          __syncwarp();
+          for (int e = lane; e < nscan; e += 32) {
+            const int t = thl[e], z = t / N, i = t - z * N, f = fl[z];
+            const double* rf = s_r + f * N; const uint8_t* pl = podlist + f * N; const int np = npods[f];
+            const double rfj = rf[jj];
+            double alt = kLnsBig;
+            for (int q = 0; q < np; ++q) { const int j2 = pl[q]; if (j2 == jj) continue; const double v = s_dT[j2 * N + i] + lam[j2] * rf[j2]; if (v < alt) alt = v; }
+            const double tq = (alt - s_dT[jj * N + i]) / rfj;
+            if (tq >= 0.0) { th[t] = (float)fmin(tq, 1e30); tot += s_w[f * N + i] * rfj; }
+          }
           tot = warp_sum(tot);
           __syncwarp();
           double nl = 0.0;
           if (tot > s_K[jj] + 1e-9) {
-            // flows leave in ascending threshold order until the rest fits; the price is the last threshold
-            float last = 0.0f;
+            float last = -1.0f;
             for (int it = 0; it < M && tot > s_K[jj] + 1e-9; ++it) {
               unsigned mn = 0xffffffffu;
               for (int t = lane; t < M; t += 32) { const float tv = th[t]; if (tv > last) mn = min(mn, __float_as_uint(tv)); }
@@ -390,7 +414,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
               for (int t = lane; t < M; t += 32) if (th[t] == last) { const int z = t / N; rem += s_w[fl[z] * N + (t - z * N)] * s_r[fl[z] * N + jj]; }
               tot -= warp_sum(rem);
             }
-            nl = (double)last * (1.0 + 2e-6) + 1e-12;
+            nl = (double)fmaxf(last, 0.0f) * (1.0 + 2e-6) + 1e-9;
           }
           const bool ch = fabs(nl - lam[jj]) > 1e-10 * (1.0 + nl);
           __syncwarp();
@@ -403,8 +427,10 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
           }
         }
       }
-      if (!changed) break;
+      if (!changed) { settled = true; break; }
     }
+    for (int j = lane; j < N; j += 32) lastload[j] = settled && lam[j] > 0.0 ? loadfx[j] : ~0ull;
+    __syncwarp();
     // ---- priced objective of the current placement, record ------------------------------------------------------
     {
       double gp = 0.0;
@@ -417,7 +443,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
         act = __reduce_add_sync(0xffffffffu, act);
         g += u * (double)act;
       }
-      if (!overloaded && g < bestg - 1e-9 * (1.0 + fabs(g))) {
+      if (!overloaded && settled && g < bestg - 1e-9 * (1.0 + fabs(g))) {
         bestg = g; best_round = round;
         for (int q = lane; q < fn; q += 32) outc[q] = c[q];
       }
@@ -603,9 +629,9 @@ extern "C" int neptune_lns_search(int B, int N, int F, int kind, double alpha, i
   const size_t blk = (lns_block_shared(N, F) + 15) & ~(size_t)15;
   int wpb = 8;
   size_t per = lns_warp_shared(N, F, k, smax);
-  while (wpb > 1 && blk + wpb * per > 110 * 1024) wpb >>= 1;          // aim at two blocks per SM
+  while (wpb > 1 && blk + wpb * per > 112 * 1024) --wpb;              // two blocks per SM (227 KB, 1 KB reserved per block)
   if (blk + wpb * per > 200 * 1024) return NEPTUNE_E_SIZE;
-  if (wpb > chains) { wpb = 1; while (wpb * 2 <= chains) wpb *= 2; }
+  if (wpb > chains) wpb = chains;
   a.smax = smax; a.wpb = wpb;
   const size_t sm = blk + wpb * per;
   const dim3 grid((chains + wpb - 1) / wpb, B);

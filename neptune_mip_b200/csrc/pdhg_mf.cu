@@ -44,7 +44,7 @@ struct MfGeo {
 static MfGeo make_geo(int N, int F, int B) {
   MfGeo G;
   G.N = N; G.F = F;
-  G.K = N <= 32 ? 1 : (N <= 64 ? 2 : 4);        // columns per lane
+  G.K = N <= 32 ? 1 : ((N & 1) == 0 || N <= 64 ? 2 : 4);        // columns per lane (even N: one pair of adjacent columns, 16-byte accesses)
   G.JT = 32 * G.K; G.ct = (N + G.JT - 1) / G.JT;
   // row-tile height: the tallest of 64/32/16/8 whose tiles fill the resident blocks evenly (>= 88 % busy in the
   // last round); the partial column sums cost 24 bytes per column and row tile, so taller is cheaper
@@ -193,6 +193,146 @@ k_mf_iter(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       sm[0][warp][k * 32 + lane] = a1[k]; sm[1][warp][k * 32 + lane] = a4[k]; sm[2][warp][k * 32 + lane] = aS[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 32 * K; c += kMfThreads) {
+      const int j = t.jt * G.JT + c;
+      if (j < N) {
+        const int64_t o = (((int64_t)b * G.F + f) * G.rt + t.it) * N + j;
+        st.P1[o] = column_total<K>(sm[0], c);
+        st.P4[o] = __ldg(r + j) * column_total<K>(sm[1], c);
+        st.PS[o] = column_total<K>(sm[2], c);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the iteration pass, pair version (even N > 32): a lane owns KP pairs of ADJACENT columns, so every stream moves
+// in 16-byte accesses; one unsigned element offset per row (the five streams share it, the bases are uniform);
+// 1/(3 + w r) by a float reciprocal + two Newton steps in double (7 instructions instead of the ~30 of an IEEE
+// division; relative error < 1e-15, deterministic); U rows of a warp in flight.  Same tiles, same partial-sum
+// buffers and the same summation order per column as k_mf_iter<2*KP, U>, so the rest of the solver is shared.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double mf_rcp(double a) {
+  float rf;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(__double2float_rn(a)));
+  double r = (double)rf;
+  double e = fma(-a, r, 1.0); r = fma(r, e, r);
+  e = fma(-a, r, 1.0); r = fma(r, e, r);
+  return r;
+}
+
+template <int KP, int U>
+__global__ void __launch_bounds__(kMfThreads, (KP * U >= 2 ? 2 : 3))
+k_mf_iter2(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
+  constexpr int K = 2 * KP;
+  __shared__ double sm[3][kMfWarps][32 * K];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = G.N;
+  const int64_t NN = (int64_t)N * N;
+  const int64_t total = (int64_t)B * G.tiles_inst;
+  for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const Tile t = decode_tile(G, tile);
+    const int b = t.b, f = t.f;
+    if (ctl[b].converged) continue;
+    const double tau = ctl[b].tau, shalf = 0.5 * ctl[b].sigma;
+    const double* __restrict__ d = in.d + (int64_t)b * NN;
+    const double* __restrict__ w = in.w + ((int64_t)b * G.F + f) * N;
+    const double* __restrict__ r = in.r + ((int64_t)b * G.F + f) * N;
+    const double* __restrict__ y = st.y + (int64_t)b * G.rows;
+    const double* __restrict__ y3 = y + G.r3 + (int64_t)f * N;
+    double* __restrict__ xp = st.x + (int64_t)b * G.cols + (int64_t)f * NN;
+    double* __restrict__ xsp = st.xsum + (int64_t)b * G.cols + (int64_t)f * NN;
+    double* __restrict__ sp = st.y + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
+    double* __restrict__ ssp = st.ysum + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
+    const double* __restrict__ cbar = st.cbar + (int64_t)b * G.C + (int64_t)f * N;
+    double* __restrict__ P3 = st.P3i + ((int64_t)b * G.C + (int64_t)f * N) * G.cti + t.jt;
+
+    // columns of this lane: pair k covers columns jc[k], jc[k] + 1 (both valid or both invalid: N is even)
+    unsigned jc[KP]; bool vj[KP];
+    double y1j[K], rj[K], rr4[K], cb[K];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int j = t.jt * G.JT + k * 64 + 2 * lane;
+      vj[k] = j < N; jc[k] = vj[k] ? (unsigned)j : 0u;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const unsigned je = jc[k] + e;
+        y1j[2 * k + e] = y[2 * ((int64_t)f * N + je) + 1];
+        rj[2 * k + e] = __ldg(r + je);
+        rr4[2 * k + e] = rj[2 * k + e] * y[G.r4 + je];
+        cb[2 * k + e] = cbar[je];
+      }
+    }
+    double a1[K], a4[K], aS[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { a1[k] = 0.0; a4[k] = 0.0; aS[k] = 0.0; }
+
+    const int i0 = t.it * G.RT, i1 = min(N, i0 + G.RT);
+    for (int ib = i0 + warp; ib < i1; ib += U * kMfWarps) {
+      double2 xv[U][KP], sv[U][KP], xs[U][KP], ss[U][KP], dv[U][KP];
+      double wfi[U], y3i[U];
+      unsigned ro[U]; bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = ib + u * kMfWarps;
+        ok[u] = i < i1;
+        const unsigned ir = ok[u] ? (unsigned)i : (unsigned)ib;
+        ro[u] = ir * (unsigned)N;
+        wfi[u] = __ldg(w + ir); y3i[u] = y3[ir];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          const unsigned o = ro[u] + jc[k];
+          xv[u][k] = __ldcs(reinterpret_cast<const double2*>(xp + o));
+          sv[u][k] = __ldcs(reinterpret_cast<const double2*>(sp + o));
+          xs[u][k] = __ldcs(reinterpret_cast<const double2*>(xsp + o));
+          ss[u][k] = __ldcs(reinterpret_cast<const double2*>(ssp + o));
+          dv[u][k] = __ldg(reinterpret_cast<const double2*>(d + o));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        double rsum = 0.0;
+        const double ty = y3i[u];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          if (ok[u] && vj[k]) {
+            const unsigned o = ro[u] + jc[k];
+            double xn[2], sn[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int q = 2 * k + e;
+              const double xo = e ? xv[u][k].y : xv[u][k].x, so = e ? sv[u][k].y : sv[u][k].x;
+              const double de = e ? dv[u][k].y : dv[u][k].x;
+              const double wr = fabs(wfi[u] * rj[q]);
+              const double g = __dmul_rn(de, wfi[u]) + y1j[q] + ty + wfi[u] * rr4[q] + so;
+              double x1 = xo - tau * g * mf_rcp(3.0 + wr);
+              x1 = fmin(fmax(x1, 0.0), 1.0);
+              const double xb = 2.0 * x1 - xo;
+              const double s1 = fmax(so + shalf * (xb - cb[q]), 0.0);
+              xn[e] = x1; sn[e] = s1;
+              a1[q] += xb; a4[q] += wfi[u] * xb; aS[q] += s1; rsum += xb;
+            }
+            __stcs(reinterpret_cast<double2*>(xp + o), make_double2(xn[0], xn[1]));
+            __stcs(reinterpret_cast<double2*>(sp + o), make_double2(sn[0], sn[1]));
+            __stcs(reinterpret_cast<double2*>(xsp + o), make_double2(xs[u][k].x + xn[0], xs[u][k].y + xn[1]));
+            __stcs(reinterpret_cast<double2*>(ssp + o), make_double2(ss[u][k].x + sn[0], ss[u][k].y + sn[1]));
+          }
+        }
+        rsum = warp_sum(rsum);
+        if (lane == 0 && ok[u]) P3[(int64_t)(ib + u * kMfWarps) * G.cti] = rsum;
+      }
+    }
+    // column c of the tile lives in lane (c % 64) / 2, slot 2 * (c / 64) + (c & 1)
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = k * 64 + 2 * lane + e;
+        sm[0][warp][c] = a1[2 * k + e]; sm[1][warp][c] = a4[2 * k + e]; sm[2][warp][c] = aS[2 * k + e];
+      }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < 32 * K; c += kMfThreads) {
@@ -1526,6 +1666,7 @@ struct MfPlan {
   int vec;                       // k_mf_iter_vec (16-byte accesses) instead of k_mf_iter
   int async_copy;                // k_mf_iter_async (experimental)
   int lean;                      // k_mf_iter_lean (experimental)
+  int pair;                      // k_mf_iter2 (pair version: 16-byte accesses, cheap reciprocal)
   int diag;                      // tools only: bits of params->reserved >> 4 switch parts of the TMA pass off
 };
 
@@ -1547,6 +1688,16 @@ static void mf_launch_iter(const MfPlan& P) {
   if (P.async_copy) {
     if (P.G.K == 2) k_mf_iter_async<1><<<g, kMfThreads, async_smem_bytes<1>(), P.s>>>(P.G, P.in, P.st, P.ctl, P.B);
     else k_mf_iter_async<2><<<g, kMfThreads, async_smem_bytes<2>(), P.s>>>(P.G, P.in, P.st, P.ctl, P.B);
+    NEPTUNE_COUNT(1);
+    return;
+  }
+  if (P.pair) {
+    switch (P.G.K * 10 + P.rows_in_flight) {
+      case 21: k_mf_iter2<1, 1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+      case 22: k_mf_iter2<1, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+      case 41: k_mf_iter2<2, 1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+      default: k_mf_iter2<2, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
+    }
     NEPTUNE_COUNT(1);
     return;
   }
@@ -1914,7 +2065,19 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
       default: P.grid_iter = mf_grid(k_mf_iter<4, 2>); break;
     }
   }
-  P.lean = (prm->reserved & 0x4000) && !P.async_copy && !P.vec;        // experimental pointer-bumped register pass
+  // pair version (reserved bit 15): even N > 32 and 16-byte aligned vectors
+  P.pair = (prm->reserved & 0x8000) && !(N & 1) && G.K >= 2 && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)d) & 15) == 0 &&
+           !P.async_copy && !P.vec;
+  if (P.pair) {
+    if (P.rows_in_flight != 1 && P.rows_in_flight != 2) P.rows_in_flight = G.K == 4 ? 1 : 2;
+    switch (G.K * 10 + P.rows_in_flight) {
+      case 21: P.grid_iter = mf_grid(k_mf_iter2<1, 1>); break;
+      case 22: P.grid_iter = mf_grid(k_mf_iter2<1, 2>); break;
+      case 41: P.grid_iter = mf_grid(k_mf_iter2<2, 1>); break;
+      default: P.grid_iter = mf_grid(k_mf_iter2<2, 2>); break;
+    }
+  }
+  P.lean = (prm->reserved & 0x4000) && !P.async_copy && !P.vec && !P.pair;        // experimental pointer-bumped register pass
   if (P.lean) {
     switch (G.K) {
       case 1: P.grid_iter = mf_grid(k_mf_iter_lean<1, 2>); break;
