@@ -27,7 +27,10 @@ class BatchParams:
     lns_chains: int = 32          # warp-sized chains per instance
     lns_rounds: int = 6000        # k-node re-optimisations per chain
     lns_k: int = 3
-    lns_noise: float = 0.06
+    lns_noise: float = 0.1
+    lns_phases: int = 1           # > 1: population restarts from the best records between phases (lns_rounds is the total)
+    lns_cooling: float = 0.6      # temperature factor from one phase to the next
+    lns_restart_pool: int = 16    # records a restart phase draws its start placements from
     elites: int = 16              # chain records priced exactly (routing LP) per instance
 
 
@@ -143,9 +146,27 @@ def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0,
     if time_it:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    out_c, out_g, out_round = device.lns_search(inst, kind, prm.alpha, prm.lns_chains, prm.lns_rounds, prm.lns_k,
-                                                prm.lns_noise, prm.rng_seed, guide, lam0, seeds)
-    E = max(1, min(prm.elites, prm.lns_chains))
+    # phase 0 starts from roundings of the relaxation; every later phase restarts ALL chains from the best records so
+    # far (population restarts: "go with the winners") at a lower temperature
+    phases = max(1, prm.lns_phases)
+    rounds = max(1, prm.lns_rounds // phases)
+    out_c = out_g = out_round = None
+    for ph in range(phases):
+        noise = prm.lns_noise * (prm.lns_cooling ** ph)
+        if ph == 0:
+            pc, pg, pr_ = device.lns_search(inst, kind, prm.alpha, prm.lns_chains, rounds, prm.lns_k, noise,
+                                            prm.rng_seed, guide, lam0, seeds)
+        else:
+            S = min(prm.lns_restart_pool, out_g.shape[1])
+            _, top = torch.topk(out_g, S, dim=1, largest=False)
+            pool = torch.gather(out_c, 1, top[:, :, None, None].expand(B, S, F, N)).contiguous()
+            pc, pg, pr_ = device.lns_search(inst, kind, prm.alpha, prm.lns_chains, rounds, prm.lns_k, noise,
+                                            prm.rng_seed + 7919 * ph, None, lam0, pool)
+            pr_ = pr_ + ph * rounds
+        out_c = pc if out_c is None else torch.cat([out_c, pc], dim=1)
+        out_g = pg if out_g is None else torch.cat([out_g, pg], dim=1)
+        out_round = pr_ if out_round is None else torch.cat([out_round, pr_], dim=1)
+    E = max(1, min(prm.elites, out_g.shape[1]))
     _, idx = torch.topk(out_g, E, dim=1, largest=False)                       # lowest priced objective first
     elite = torch.gather(out_c, 1, idx[:, :, None, None].expand(B, E, F, N)).contiguous()
     pr = device.route_lp(inst, elite)
@@ -180,5 +201,6 @@ def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0,
         e1.record()
         e1.synchronize()
         ms = e0.elapsed_time(e1)
-    diag = dict(elite_g=torch.gather(out_g, 1, idx), elite_val=val, pivots=pr["info"][..., 0])
+    diag = dict(elite_g=torch.gather(out_g, 1, idx), elite_val=val, pivots=pr["info"][..., 0], status=pr["status"],
+                fell_back=(flags != OK_ALL))
     return best_c, x, n, flags, scores, rnd, ms, diag

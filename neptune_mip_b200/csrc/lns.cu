@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
               if (av > 0.0) {
                 if (asg[f * N + i] != jj) {
                   const double tq = (bestv[f * N + i] - s_dT[jj * N + i]) / rfj;
-                  if (tq >= 0.0) { tv = (float)fmin(tq, 1e30); tot += av; }
+                  if (tq >= 0.0) { tv = bestv[f * N + i] >= 0.5 * kLnsBig ? INFINITY : (float)fmin(tq, 1e30); tot += av; }
                 } else scan = true;
               }
               th[t] = tv;
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
             double alt = kLnsBig;
             for (int q = 0; q < np; ++q) { const int j2 = pl[q]; if (j2 == jj) continue; const double v = s_dT[j2 * N + i] + lam[j2] * rf[j2]; if (v < alt) alt = v; }
             const double tq = (alt - s_dT[jj * N + i]) / rfj;
-            if (tq >= 0.0) { th[t] = (float)fmin(tq, 1e30); tot += s_w[f * N + i] * rfj; }
+            if (tq >= 0.0) { th[t] = alt >= 0.5 * kLnsBig ? INFINITY : (float)fmin(tq, 1e30); tot += s_w[f * N + i] * rfj; }   // no other pod: cannot leave
           }
           tot = warp_sum(tot);
           __syncwarp();
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
               unsigned mn = 0xffffffffu;
               for (int t = lane; t < M; t += 32) { const float tv = th[t]; if (tv > last) mn = min(mn, __float_as_uint(tv)); }
               mn = __reduce_min_sync(0xffffffffu, mn);
-              if (mn == 0xffffffffu) break;                 // nothing left to move: stays overloaded
+              if (mn >= 0x7f800000u) break;                 // nothing movable left: the node stays overloaded (never recorded)
               last = __uint_as_float(mn);
               double rem = 0.0;
               for (int t = lane; t < M; t += 32) if (th[t] == last) { const int z = t / N; rem += s_w[fl[z] * N + (t - z * N)] * s_r[fl[z] * N + jj]; }
@@ -443,7 +443,10 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
         act = __reduce_add_sync(0xffffffffu, act);
         g += u * (double)act;
       }
-      if (!overloaded && settled && g < bestg - 1e-9 * (1.0 + fabs(g))) {
+      bool unserved = false;
+      for (int fi = lane; fi < fn; fi += 32) unserved = unserved || asg[fi] == 255;
+      unserved = __any_sync(0xffffffffu, unserved);
+      if (!overloaded && settled && !unserved && g < bestg - 1e-9 * (1.0 + fabs(g))) {
         bestg = g; best_round = round;
         for (int q = lane; q < fn; q += 32) outc[q] = c[q];
       }

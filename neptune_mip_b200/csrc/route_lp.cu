@@ -42,7 +42,7 @@ constexpr double kRlpPivTol = 1e-11;    // smallest admissible pivot magnitude
 __host__ __device__ inline int64_t rlp_fixed_bytes(int N, int F) {
   const int64_t fn = (int64_t)F * N;
   // near, src, coloff (fn+1), podlist: 4 * fn ints (+1); colsrc / basis live after the tableau sizing below
-  int64_t b = (4 * fn + 8 + F + N) * 4;
+  int64_t b = (4 * fn + 8 + F + N) * 4 + ((fn + 7) & ~(int64_t)7);   // + working copy of the placement
   b = (b + 7) & ~(int64_t)7;
   b += ((int64_t)2 * N + fn + N) * 8;          // load, colq bound (rows <= fn + N), ...
   b += (int64_t)N * fn * 8;                    // dense x scratch
@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(256) k_route_lp(RlpArgs a) {
   int* podlist = (int*)p; p += fn * 4;
   int* npods = (int*)p; p += (int64_t)F * 4;
   int* inA = (int*)p; p += (int64_t)N * 4;
+  uint8_t* cw = (uint8_t*)p; p += fn;       // working copy of the placement: starved pods are closed and the LP re-solved
   p = (char*)(((uintptr_t)p + 7) & ~(uintptr_t)7);
   double* load = (double*)p; p += (int64_t)N * 8;
   p += (int64_t)N * 8;
@@ -89,13 +90,16 @@ __global__ void __launch_bounds__(256) k_route_lp(RlpArgs a) {
   // tableau region: T[R][C] | red[C] | colsrc[C] (int) | basis[R] (int)
   double* Treg = (double*)p;
 
-  for (int64_t job = blockIdx.x; job < (int64_t)a.B * a.P; job += gridDim.x) {
+  int attempt = 0;
+  for (int64_t job = blockIdx.x; job < (int64_t)a.B * a.P;) {
     const int b = (int)(job / a.P);
     const double* d = a.d + (int64_t)b * N * N;
     const double* w = a.w + b * fn;
     const double* r = a.r + b * fn;
     const double* K = a.Kj + (int64_t)b * N;
-    const uint8_t* c = a.c + job * fn;
+    __syncthreads();
+    if (attempt == 0) for (int q = tid; q < (int)fn; q += nt) cw[q] = a.c[job * fn + q];
+    const uint8_t* c = cw;
     __syncthreads();
     if (tid == 0) s_flag = 1;
     __syncthreads();
@@ -329,6 +333,20 @@ __global__ void __launch_bounds__(256) k_route_lp(RlpArgs a) {
       }
       __syncthreads();
       bad = s_flag;
+      if (bad && attempt < 4) {
+        // C1b cannot be met for some pod at this routing (constraints_step1.py:12-15): close the starved pods and
+        // solve the LP of the smaller placement -- still a feasible point of the MIP, at the LP value of that placement
+        for (int fj = tid; fj < (int)fn; fj += nt) {
+          if (!cw[fj]) continue;
+          const int f = fj / N, j = fj - f * N;
+          double rc = 0.0;
+          for (int i = 0; i < N; ++i) rc += xs[((int64_t)i * F + f) * N + j];
+          if (rc == 0.0 || rc + kEps < 1.0) cw[fj] = 0;
+        }
+        ++attempt;
+        __syncthreads();
+        continue;
+      }
       if (a.x_out) {
         double* xo = a.x_out + job * (int64_t)N * fn;
         for (int64_t k = tid; k < (int64_t)N * fn; k += nt) xo[k] = xs[k];
@@ -356,6 +374,7 @@ __global__ void __launch_bounds__(256) k_route_lp(RlpArgs a) {
       if (a.info) { a.info[job * 2] = pivots; a.info[job * 2 + 1] = status == 1 ? s_nA : -1; }
     }
     __syncthreads();
+    job += gridDim.x; attempt = 0;
   }
 }
 

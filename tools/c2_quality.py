@@ -24,7 +24,10 @@ def main():
     ap.add_argument("--rounds", type=int, default=6000)
     ap.add_argument("--k", type=int, default=3)
     ap.add_argument("--noise", type=float, default=0.06)
-    ap.add_argument("--elites", type=int, default=8)
+    ap.add_argument("--elites", type=int, default=16)
+    ap.add_argument("--phases", type=int, default=1)
+    ap.add_argument("--cooling", type=float, default=0.6)
+    ap.add_argument("--pool", type=int, default=16)
     ap.add_argument("--lp-iters", type=int, default=20000)
     ap.add_argument("--no-cut", action="store_true")
     ap.add_argument("--search", default="auto")
@@ -37,7 +40,7 @@ def main():
     datas = [data_to_solver_input(synth.config_payload(a.config, s), 1, with_db=False) for s in seeds]
     inst = device.InstanceBatch.from_datas(datas)
     prm = BatchParams(lp_iters=a.lp_iters, lp_check_every=256, lns_chains=a.chains, lns_rounds=a.rounds, lns_k=a.k,
-                      lns_noise=a.noise, elites=a.elites, lp_cut=not a.no_cut, search=a.search, rng_seed=a.rng,
+                      lns_noise=a.noise, elites=a.elites, lns_phases=a.phases, lns_cooling=a.cooling, lns_restart_pool=a.pool, lp_cut=not a.no_cut, search=a.search, rng_seed=a.rng,
                       chains=16, sweeps=400)
     for rep in range(a.repeat):
         prm.rng_seed = a.rng + rep
@@ -48,7 +51,7 @@ def main():
         gaps = np.array([(sc[k] - gold[s]["objective"]) / gold[s]["objective"] for k, s in enumerate(seeds)])
         lp = res.lp
         print(json.dumps({"config": a.config, "B": len(seeds), "search": res.search_path, "chains": a.chains, "rounds": a.rounds,
-                          "k": a.k, "noise": a.noise, "wall_s": round(dt, 3), "pdhg_ms": round(res.pdhg_ms, 1),
+                          "k": a.k, "noise": a.noise, "phases": a.phases, "cooling": a.cooling, "wall_s": round(dt, 3), "pdhg_ms": round(res.pdhg_ms, 1),
                           "lns_ms": round(res.lns_ms, 1), "feasible": int((fl == 63).sum()),
                           "within_1e4": int((gaps <= 1e-4).sum()), "max_gap": float(gaps.max()),
                           "gaps": [float(f"{g:.2e}") for g in gaps],
@@ -57,6 +60,9 @@ def main():
                           "lp_converged": int(lp["converged"].sum()) if lp is not None else None,
                           "elite_g_minus_opt": [[round(float(v) - gold[s]["objective"], 2) for v in res.lns_diag["elite_g"][k].cpu()[:4]] for k, s in enumerate(seeds)] if res.lns_diag else None,
                           "elite_val_minus_opt": [[round(float(v) - gold[s]["objective"], 2) for v in res.lns_diag["elite_val"][k].cpu()[:4]] for k, s in enumerate(seeds)] if res.lns_diag else None,
+                          "bad": {str(seeds[k]): {"gap": float(f"{gaps[k]:.3g}"), "status": res.lns_diag["status"][k].cpu().tolist()[:8], "fell_back": bool(res.lns_diag["fell_back"][k]),
+                                                  "g": [round(float(v), 1) for v in res.lns_diag["elite_g"][k].cpu()[:4]], "opt": gold[seeds[k]]["objective"]}
+                                  for k in range(len(seeds)) if gaps[k] > 1e-2} if res.lns_diag else None,
                           "rounds_of_best": res.lns_round.cpu().tolist() if res.lns_round is not None else None}))
         sys.stdout.flush()
 

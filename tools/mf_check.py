@@ -144,14 +144,16 @@ def main():
             if "--experimental" in sys.argv:
                 variants.append(("fused", 0))
                 variants.append(("lean", 0))
+            if "--pair" in sys.argv and inst.N > 32 and inst.N % 2 == 0:
+                variants = [(True, 1), (True, 2), ("pair", 1), ("pair", 2)]
             for scalar, u in variants:
-                kw = (dict(async_kernel=True) if scalar == "async" else dict(fused_kernel=True) if scalar == "fused" else dict(lean_kernel=True) if scalar == "lean"
+                kw = (dict(pair_kernel=True, rows_in_flight=u) if scalar == "pair" else dict(async_kernel=True) if scalar == "async" else dict(fused_kernel=True) if scalar == "fused" else dict(lean_kernel=True) if scalar == "lean"
                       else dict(rows_in_flight=u, vector_kernel=not scalar))
                 device.pdhg_mf_solve(inst, max_iters=32, check_every=32, **kw)
                 (xu, yu, _), ms = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14, **kw))
                 if ref is None:
                     ref = (xu, yu)
-                print("VAR", name, "cp.async ring" if scalar == "async" else "fused small vectors, 8-byte" if scalar == "fused" else "pointer-bumped, 8-byte" if scalar == "lean" else ("8-byte" if scalar else "16-byte"), "accesses, rows in flight", u, "us/iter %.1f" % (1e3 * ms / iters),
+                print("VAR", name, "pair version, 16-byte" if scalar == "pair" else "cp.async ring" if scalar == "async" else "fused small vectors, 8-byte" if scalar == "fused" else "pointer-bumped, 8-byte" if scalar == "lean" else ("8-byte" if scalar else "16-byte"), "accesses, rows in flight", u, "us/iter %.1f" % (1e3 * ms / iters),
                       "GB/s %.0f" % (inst.B * 64 * X * iters / ms / 1e6), "max |dx| vs first %.1e" % float((xu - ref[0]).abs().max()),
                       "max |dy| %.1e" % float((yu - ref[1]).abs().max()), flush=True)
             device.pdhg_mf_solve(inst, max_iters=32, check_every=32, _diag=4)
