@@ -296,15 +296,17 @@ int neptune_route_lp_workspace_bytes(int B, int P, int N, int F, int64_t tableau
  * the priced nearest-pod cost, node prices on the CPU rows kept at their coordinate-wise dual optimum, annealed
  * cost perturbation of relative size `noise_coef` (csrc/lns.cu).  Chains start from randomised roundings of
  * guide[B][F][N] (c-bar of the LP relaxation) and lam0[B][N] (its CPU-row duals), and/or from
- * seeds[B][S][F][N]; any of the three may be NULL.  Returns every chain's record: out_c[B][chains][F][N],
- * out_g[B][chains] (priced objective, a lower bound of the record's true objective; +inf = none),
- * out_round[B][chains].  Price the records with neptune_route_lp. */
+ * seeds[B][S][F][N]; any of the three may be NULL (no guide: every chain starts from a seed).  Returns every
+ * chain's record: out_c[B][chains][F][N], out_g[B][chains] = objective of the record with every source routed
+ * whole to its nearest priced pod (feasible, so an UPPER bound of the record's true objective; +inf = none),
+ * out_lb[B][chains] (optional) = the priced objective at the record (a lower bound), out_round[B][chains].
+ * Price the records exactly with neptune_route_lp. */
 int neptune_lns_search(int B, int N, int F, int kind, double alpha, int chains, int rounds, int k,
                        double noise_coef, uint64_t rng_seed,
                        const double* d, const double* w, const double* r, const double* m,
                        const double* Mj, const double* Kj, const double* maxd,
                        const double* guide, const double* lam0, int S, const uint8_t* seeds,
-                       uint8_t* out_c, double* out_g, int32_t* out_round, void* stream);
+                       uint8_t* out_c, double* out_g, double* out_lb, int32_t* out_round, void* stream);
 
 /* ---- (d) EFTTC greedy -----------------------------------------------------------------------------
  * Replaces `EfttcStepBase.solve()` (`core/solvers/efttc/efttc_step1.py:39-90` and helpers

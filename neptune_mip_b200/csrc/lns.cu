@@ -36,7 +36,8 @@ struct LnsArgs {
   const double* lam0;      // [B][N] CPU-row duals of the relaxation (delay units), or null
   const uint8_t* seeds;    // [B][S][F][N] or null
   uint8_t* out_c;          // [B][chains][F][N]
-  double* out_g;           // [B][chains] priced objective of the record (+inf: none)
+  double* out_g;           // [B][chains] objective of the record's whole-flow routing: an upper bound of its true objective (+inf: none)
+  double* out_lb;          // [B][chains] priced (dual) objective at the record: a lower bound; may be null
   int32_t* out_round;      // [B][chains] round of the record
 };
 
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
   for (int f = 0; f < F; ++f) scan_function(f);
   __syncwarp();
 
-  double bestg = INFINITY; int best_round = -1;
+  double bestu = INFINITY, bestg = -INFINITY; int best_round = -1;
   uint8_t* outc = a.out_c + ((int64_t)b * a.chains + chain) * fn;
   const int anneal_rounds = a.rounds - a.rounds / 8;
 
@@ -332,16 +333,21 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
     // while  lam_jj < th = (best priced alternative - d[i,jj]) / r[f,jj];  flows leave in ascending th until the
     // rest fits K_jj; ties with the alternative (th = 0) leave first, at a price of 1e-9.
     bool overloaded = false, settled = false;
+    double ucost = 0.0;
     for (int pass = 0; pass < 4; ++pass) {
       for (int j = lane; j < N; j += 32) loadfx[j] = 0ull;
       __syncwarp();
+      double up = 0.0;
       for (int fi = lane; fi < fn; fi += 32) {
         const int bj = asg[fi];
         if (bj == 255) continue;
-        const int f = fi / N;
-        const double ld = s_w[fi] * s_r[f * N + bj];
+        const int f = fi / N, i = fi - f * N;
+        const double wv = s_w[fi];
+        const double ld = wv * s_r[f * N + bj];
         if (ld > 0.0) atomicAdd(&loadfx[bj], (unsigned long long)(fmin(ld, 1e9) * kFxScale + 0.5));
+        if (wv > 0.0) up += wv * s_dT[bj * N + i];
       }
+      ucost = warp_sum(up);                              // delay of the whole-flow routing at the current prices
       __syncwarp();
       bool changed = false; overloaded = false;
       for (int jb = 0; jb < N; jb += 32) {
@@ -431,23 +437,28 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
     }
     for (int j = lane; j < N; j += 32) lastload[j] = settled && lam[j] > 0.0 ? loadfx[j] : ~0ull;
     __syncwarp();
-    // ---- priced objective of the current placement, record ------------------------------------------------------
+    // ---- record ---------------------------------------------------------------------------------------------------
+    // With no node overloaded, routing every source WHOLE to its nearest priced pod is a feasible point of the MIP
+    // (pods that end up unused are closed, the others serve at least one whole source: C1b holds), so its delay
+    // `ucost` is an upper bound of the placement's true objective and the priced cost g a lower bound; they differ
+    // by sum_j lam_j (K_j - load_j).  Chains record by the upper bound: it can only be improved by the exact routing
+    // LP afterwards (split flows), never be a mirage of loose prices.
     {
       double gp = 0.0;
       for (int fi = lane; fi < fn; fi += 32) { const double wv = s_w[fi]; if (wv > 0.0) gp += wv * bestv[fi]; }
       for (int j = lane; j < N; j += 32) gp -= lam[j] * s_K[j];
-      double g = warp_sum(gp);
+      double g = warp_sum(gp), uval = ucost;
       if (u != 0.0) {
         int act = 0;
         for (int j = lane; j < N; j += 32) { int any = 0; for (int f = 0; f < F; ++f) any |= c[f * N + j]; act += any; }
         act = __reduce_add_sync(0xffffffffu, act);
-        g += u * (double)act;
+        g += u * (double)act; uval += u * (double)act;
       }
       bool unserved = false;
       for (int fi = lane; fi < fn; fi += 32) unserved = unserved || asg[fi] == 255;
       unserved = __any_sync(0xffffffffu, unserved);
-      if (!overloaded && settled && !unserved && g < bestg - 1e-9 * (1.0 + fabs(g))) {
-        bestg = g; best_round = round;
+      if (!overloaded && !unserved && uval < bestu - 1e-9 * (1.0 + fabs(uval))) {
+        bestu = uval; bestg = g; best_round = round;
         for (int q = lane; q < fn; q += 32) outc[q] = c[q];
       }
     }
@@ -600,7 +611,8 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
     __syncwarp();
   }
   if (lane == 0) {
-    a.out_g[(int64_t)b * a.chains + chain] = bestg < INFINITY ? a_d * bestg : INFINITY;
+    a.out_g[(int64_t)b * a.chains + chain] = bestu < INFINITY ? a_d * bestu : INFINITY;
+    if (a.out_lb) a.out_lb[(int64_t)b * a.chains + chain] = bestu < INFINITY ? a_d * bestg : -INFINITY;
     a.out_round[(int64_t)b * a.chains + chain] = best_round;
   }
   if (best_round < 0) for (int q = lane; q < fn; q += 32) outc[q] = c[q];
@@ -614,8 +626,8 @@ extern "C" int neptune_lns_search(int B, int N, int F, int kind, double alpha, i
                                   double noise_coef, uint64_t rng_seed, const double* d, const double* w,
                                   const double* r, const double* m, const double* Mj, const double* Kj,
                                   const double* maxd, const double* guide, const double* lam0, int S,
-                                  const uint8_t* seeds, uint8_t* out_c, double* out_g, int32_t* out_round,
-                                  void* stream) {
+                                  const uint8_t* seeds, uint8_t* out_c, double* out_g, double* out_lb,
+                                  int32_t* out_round, void* stream) {
   if (B <= 0 || N <= 0 || F <= 0 || chains <= 0 || rounds < 0 || k < 2 || k > kLnsMaxK || !d || !w || !r || !m || !Mj ||
       !Kj || !out_c || !out_g || !out_round)
     return NEPTUNE_E_ARG;
@@ -626,7 +638,7 @@ extern "C" int neptune_lns_search(int B, int N, int F, int kind, double alpha, i
   a.B = B; a.N = N; a.F = F; a.kind = kind; a.chains = chains; a.rounds = rounds; a.k = k; a.S = seeds ? S : 0;
   a.alpha = alpha; a.noise_coef = noise_coef; a.rng = rng_seed ? rng_seed : 0x1234567ull;
   a.d = d; a.w = w; a.r = r; a.m = m; a.Mj = Mj; a.Kj = Kj; a.maxd = maxd; a.guide = guide; a.lam0 = lam0; a.seeds = seeds;
-  a.out_c = out_c; a.out_g = out_g; a.out_round = out_round;
+  a.out_c = out_c; a.out_g = out_g; a.out_lb = out_lb; a.out_round = out_round;
   // states of the slot counters: (slots+1)^k for the common 3-slot nodes, capped by shared memory
   int smax = 1; for (int q = 0; q < k; ++q) smax *= 4;
   const size_t blk = (lns_block_shared(N, F) + 15) & ~(size_t)15;

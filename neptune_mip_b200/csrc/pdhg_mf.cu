@@ -1911,7 +1911,7 @@ static int mf_solve_fused(int B, int N, int F, int kind, const double* d, const 
   // small vectors: one block per instance does POST + PREC + Y2 in one launch while F*N is small; larger
   // instances spread over several blocks and take the C2 dual in a second launch
   P.fused = G.C <= 4096;
-  P.small_blocks = P.fused ? 1 : (int)((G.C + 1023) / 1024 < 4 * kNumSMs ? (G.C + 1023) / 1024 : 4 * kNumSMs);
+  P.small_blocks = P.fused ? 1 : (int)((G.C + 255) / 256 < 8 * kNumSMs ? (G.C + 255) / 256 : 8 * kNumSMs);   // one item per thread: the sums are latency-bound
 
   const size_t cb = (size_t)B * G.cols * 8, rb = (size_t)B * G.rows * 8;
   NEPTUNE_CUDA_OK(cudaMemsetAsync(ctl, 0, (size_t)B * sizeof(Ctl), s));
@@ -2109,7 +2109,7 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
   // small vectors: one block per instance does POST + PREC + Y2 in one launch while F*N is small; larger
   // instances spread over several blocks and take the C2 dual in a second launch
   P.fused = G.C <= 4096;
-  P.small_blocks = P.fused ? 1 : (int)((G.C + 1023) / 1024 < 4 * kNumSMs ? (G.C + 1023) / 1024 : 4 * kNumSMs);
+  P.small_blocks = P.fused ? 1 : (int)((G.C + 255) / 256 < 8 * kNumSMs ? (G.C + 255) / 256 : 8 * kNumSMs);   // one item per thread: the sums are latency-bound
 
   const size_t cb = (size_t)B * G.cols * 8, rb = (size_t)B * G.rows * 8;
   NEPTUNE_CUDA_OK(cudaMemsetAsync(ctl, 0, (size_t)B * sizeof(Ctl), s));
