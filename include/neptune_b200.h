@@ -98,10 +98,8 @@ typedef struct neptune_pdhg_params {
   int     check_every;      /* iterations between KKT evaluations / restart decisions */
   int     ruiz_iters;       /* Ruiz equilibration passes (then one Pock-Chambolle pass) */
   int     reserved;         /* 0.  neptune_pdhg_mf_solve reads it as switches for measurements and tests:
-                             * bit 0 = bulk-copy (cp.async.bulk) staged iteration pass, bit 11 = 16-byte accesses,
-                             * bits 8..10 = rows of a warp in flight (0 = default), bits 4..6 = tool diagnostics, bit 12 = cp.async-prefetched
-                             * pass, bit 13 = small vectors folded into the pass, bit 14 = pointer-bumped register pass
-                             * (all three experimental) */
+                             * bit 0 = force the 8-byte iteration pass, bits 4..6 = tool diagnostics,
+                             * bits 8..10 = rows of a warp in flight (0 = default) */
   double  eps_rel;          /* termination: relative KKT tolerance */
   double  eps_abs;
 } neptune_pdhg_params;

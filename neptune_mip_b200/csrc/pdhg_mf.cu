@@ -24,16 +24,17 @@
 //   = 64*X, + 112*F*N (small vectors) + 8*N*N (d, re-read per function from L1/L2)  [X = F*N*N]; the CSR solver
 //   moves 16*nnz + 88*cols + 72*rows ~ 260*X for the same iteration.
 //
-// Iteration-pass variants (all parity-tested against the numpy statement, tests/test_pdhg_mf_gpu.py; measurements in
-// profiles/r01f_summary.md): k_mf_iter<K, U> (default: lanes own K columns, U rows of a warp in flight),
-// k_mf_iter_vec (16-byte accesses), k_mf_iter_tma (cp.async.bulk + mbarrier staging), k_mf_iter_async
-// (experimental cp.async ring) -- selected by bits of params.reserved, see include/neptune_b200.h.
+// Two iteration passes, both parity-tested against the numpy statement (tests/test_pdhg_mf_gpu.py): k_mf_iter2<KP, U>
+// (even N in 33..64: a lane owns pairs of adjacent columns, 16-byte accesses, cheap reciprocal) and k_mf_iter<K, U>
+// (every other shape: lanes own K strided columns, 8-byte accesses); U rows of a warp are in flight.  Round 2
+// measured five further variants on B200 (bulk-copy staging, strided 16-byte, cp.async ring, fused small vectors,
+// pointer bumping: profiles/r02_pdhg_variants.md) -- none beat these two and they were removed.
 #include "common.cuh"
 #include "pdhg_ctl.cuh"
 
 namespace neptune {
 
-constexpr int kGeoSeg = 1024;          // widest column segment of the TMA pass (= kTmaChunk)
+constexpr int kGeoSeg = 1024;          // column segment used when balancing the row-tile height
 
 struct MfGeo {
   int N, F, K, JT, ct, RT, rt, tiles_inst;
@@ -81,7 +82,6 @@ struct MfSt {
   double *S2;                    // [B]           1 / sum_f |m|
   double *wsum;                  // [B][F]        sum_i |w[f,i]|
   double *scal;                  // [B][tiles_inst][4] per-tile scalars of the KKT evaluation / setup
-  int *cnt;                      // [B][2] fused pass only: tiles finished in this launch, iterations done in the chunk
 };
 
 constexpr int kMfThreads = 256;
@@ -347,860 +347,6 @@ k_mf_iter2(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
     __syncthreads();
   }
 }
-
-// EXPERIMENTAL (opt-in, reserved bit 14; not yet run on a GPU): k_mf_iter<K, U> with bumped pointers.  The SASS of
-// k_mf_iter<2,2> spends ~45 % of its row loop on 64-bit address arithmetic (each of the 20 loads and 16 stores
-// rebuilds base + 8*(row*N + column)); here a lane keeps one pointer per stream at (row ib, its first column), the
-// other columns are +32 elements (an immediate), the other rows of the batch +8*N elements, and the pointers
-// advance once per batch.  Same arithmetic and summation order as k_mf_iter<K, U>.
-template <int K, int U>
-__global__ void __launch_bounds__(kMfThreads, (K * U >= 4 ? 2 : 3))
-k_mf_iter_lean(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
-  __shared__ double sm[3][kMfWarps][32 * K];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int N = G.N;
-  const int64_t NN = (int64_t)N * N;
-  const int64_t total = (int64_t)B * G.tiles_inst;
-  const int64_t rstep = (int64_t)kMfWarps * N;                   // elements between consecutive rows of a warp
-  for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const Tile t = decode_tile(G, tile);
-    const int b = t.b, f = t.f;
-    if (ctl[b].converged) continue;
-    const double tau = ctl[b].tau, shalf = 0.5 * ctl[b].sigma;
-    const double* __restrict__ w = in.w + ((int64_t)b * G.F + f) * N;
-    const double* __restrict__ r = in.r + ((int64_t)b * G.F + f) * N;
-    const double* __restrict__ y = st.y + (int64_t)b * G.rows;
-    const double* __restrict__ cbar = st.cbar + (int64_t)b * G.C + (int64_t)f * N;
-    const int i0 = t.it * G.RT, i1 = min(N, i0 + G.RT);
-    const int j0 = t.jt * G.JT + lane;                           // first column of this lane; the others are +32*k
-    const int64_t e0 = (int64_t)(i0 + warp) * N + j0;            // element of (first row of the warp, first column)
-    double* px = st.x + (int64_t)b * G.cols + (int64_t)f * NN + e0;
-    double* pxs = st.xsum + (int64_t)b * G.cols + (int64_t)f * NN + e0;
-    double* ps = st.y + (int64_t)b * G.rows + G.rs + (int64_t)f * NN + e0;
-    double* pss = st.ysum + (int64_t)b * G.rows + G.rs + (int64_t)f * NN + e0;
-    const double* pd = in.d + (int64_t)b * NN + e0;
-    const double* pw = w + i0 + warp;
-    const double* py3 = y + G.r3 + (int64_t)f * N + i0 + warp;
-    double* pP3 = st.P3i + ((int64_t)b * G.C + (int64_t)f * N + i0 + warp) * G.cti + t.jt;
-
-    bool vj[K];
-    double y1j[K], rj[K], rr4[K], cb[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int j = j0 + 32 * k;
-      vj[k] = j < N;
-      const int jc = vj[k] ? j : 0;
-      y1j[k] = y[2 * ((int64_t)f * N + jc) + 1];
-      rj[k] = __ldg(r + jc);
-      rr4[k] = rj[k] * y[G.r4 + jc];
-      cb[k] = cbar[jc];
-    }
-    double a1[K], a4[K], aS[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) { a1[k] = 0.0; a4[k] = 0.0; aS[k] = 0.0; }
-
-    for (int ib = i0 + warp; ib < i1; ib += U * kMfWarps) {
-      double xv[U][K], sv[U][K], xs[U][K], ss[U][K], dv[U][K], wfi[U], y3i[U];
-      bool ok[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        ok[u] = ib + u * kMfWarps < i1;
-        wfi[u] = ok[u] ? __ldg(pw + u * kMfWarps) : 0.0;
-        y3i[u] = ok[u] ? py3[u * kMfWarps] : 0.0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const bool on = ok[u] && vj[k];
-          const int64_t o = u * rstep + 32 * k;
-          xv[u][k] = on ? px[o] : 0.0; sv[u][k] = on ? ps[o] : 0.0;
-          xs[u][k] = on ? pxs[o] : 0.0; ss[u][k] = on ? pss[o] : 0.0;
-          dv[u][k] = on ? __ldg(pd + o) : 0.0;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        double rsum = 0.0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          if (ok[u] && vj[k]) {
-            const int64_t o = u * rstep + 32 * k;
-            const double wr = fabs(wfi[u] * rj[k]);
-            const double g = __dmul_rn(dv[u][k], wfi[u]) + y1j[k] + y3i[u] + wfi[u] * rr4[k] + sv[u][k];
-            double xn = xv[u][k] - tau * g / (3.0 + wr);
-            xn = fmin(fmax(xn, 0.0), 1.0);
-            const double xb = 2.0 * xn - xv[u][k];
-            const double sn = fmax(sv[u][k] + shalf * (xb - cb[k]), 0.0);
-            px[o] = xn; ps[o] = sn;
-            pxs[o] = xs[u][k] + xn; pss[o] = ss[u][k] + sn;
-            a1[k] += xb; a4[k] += wfi[u] * xb; aS[k] += sn; rsum += xb;
-          }
-        }
-        rsum = warp_sum(rsum);
-        if (lane == 0 && ok[u]) pP3[(int64_t)u * kMfWarps * G.cti] = rsum;
-      }
-      px += U * rstep; ps += U * rstep; pxs += U * rstep; pss += U * rstep; pd += U * rstep;
-      pw += U * kMfWarps; py3 += U * kMfWarps; pP3 += (int64_t)U * kMfWarps * G.cti;
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      sm[0][warp][k * 32 + lane] = a1[k]; sm[1][warp][k * 32 + lane] = a4[k]; sm[2][warp][k * 32 + lane] = aS[k];
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < 32 * K; c += kMfThreads) {
-      const int j = t.jt * G.JT + c;
-      if (j < N) {
-        const int64_t o = (((int64_t)b * G.F + f) * G.rt + t.it) * N + j;
-        st.P1[o] = column_total<K>(sm[0], c);
-        st.P4[o] = __ldg(r + j) * column_total<K>(sm[1], c);
-        st.PS[o] = column_total<K>(sm[2], c);
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// the iteration pass with 16-byte accesses (even N > 32): a lane owns KV pairs of adjacent columns (double2 loads
-// and stores of all four streams and of d), U rows of a warp in flight -- half the memory instructions and address
-// arithmetic of k_mf_iter for the same bytes, twice the bytes in flight per instruction.  Same tiles, same
-// partial-sum layout and the same summation order per column as k_mf_iter<2*KV, .>.
-template <int KV, int U>
-__global__ void __launch_bounds__(kMfThreads, 2)
-k_mf_iter_vec(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
-  constexpr int K = 2 * KV;
-  __shared__ double sm[3][kMfWarps][32 * K];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int N = G.N;
-  const int64_t NN = (int64_t)N * N;
-  const int64_t total = (int64_t)B * G.tiles_inst;
-  for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const Tile t = decode_tile(G, tile);
-    const int b = t.b, f = t.f;
-    if (ctl[b].converged) continue;
-    const double tau = ctl[b].tau, shalf = 0.5 * ctl[b].sigma;
-    const double* __restrict__ d = in.d + (int64_t)b * NN;
-    const double* __restrict__ w = in.w + ((int64_t)b * G.F + f) * N;
-    const double* __restrict__ r = in.r + ((int64_t)b * G.F + f) * N;
-    const double* __restrict__ y = st.y + (int64_t)b * G.rows;
-    const double* __restrict__ y3 = y + G.r3 + (int64_t)f * N;
-    double* __restrict__ xp = st.x + (int64_t)b * G.cols + (int64_t)f * NN;
-    double* __restrict__ xsp = st.xsum + (int64_t)b * G.cols + (int64_t)f * NN;
-    double* __restrict__ sp = st.y + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
-    double* __restrict__ ssp = st.ysum + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
-    const double* __restrict__ cbar = st.cbar + (int64_t)b * G.C + (int64_t)f * N;
-    double* __restrict__ P3 = st.P3i + ((int64_t)b * G.C + (int64_t)f * N) * G.cti + t.jt;
-
-    int jj[KV]; bool vj[KV];
-    double y1j[K], rj[K], rr4[K], cb[K];
-#pragma unroll
-    for (int k = 0; k < KV; ++k) {
-      const int j = t.jt * G.JT + k * 64 + 2 * lane;
-      vj[k] = j < N; jj[k] = vj[k] ? j : 0;                      // N even: a pair is valid or not as a whole
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = 2 * k + h, jc = jj[k] + h;
-        y1j[c] = y[2 * ((int64_t)f * N + jc) + 1];
-        rj[c] = __ldg(r + jc);
-        rr4[c] = rj[c] * y[G.r4 + jc];
-        cb[c] = cbar[jc];
-      }
-    }
-    double a1[K], a4[K], aS[K];
-#pragma unroll
-    for (int c = 0; c < K; ++c) { a1[c] = 0.0; a4[c] = 0.0; aS[c] = 0.0; }
-
-    const int i0 = t.it * G.RT, i1 = min(N, i0 + G.RT);
-    for (int ib = i0 + warp; ib < i1; ib += U * kMfWarps) {
-      double2 xv[U][KV], sv[U][KV], xs[U][KV], ss[U][KV];
-      double wfi[U], y3i[U];
-      int ro[U]; bool ok[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = ib + u * kMfWarps;
-        ok[u] = i < i1;
-        const int ir = ok[u] ? i : ib;
-        ro[u] = ir * N;
-        wfi[u] = __ldg(w + ir); y3i[u] = y3[ir];
-#pragma unroll
-        for (int k = 0; k < KV; ++k) {
-          const int o = ro[u] + jj[k];
-          xv[u][k] = *reinterpret_cast<const double2*>(xp + o);
-          sv[u][k] = *reinterpret_cast<const double2*>(sp + o);
-          xs[u][k] = *reinterpret_cast<const double2*>(xsp + o);
-          ss[u][k] = *reinterpret_cast<const double2*>(ssp + o);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        double rsum = 0.0;
-#pragma unroll
-        for (int k = 0; k < KV; ++k) {
-          if (ok[u] && vj[k]) {
-            const int o = ro[u] + jj[k];
-            double xin[2] = {xv[u][k].x, xv[u][k].y}, sin_[2] = {sv[u][k].x, sv[u][k].y};
-            const double2 dd = __ldg(reinterpret_cast<const double2*>(d + o));     // L1 / L2 resident
-            double din[2] = {dd.x, dd.y};
-            double xo[2], so[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int c = 2 * k + h;
-              const double wr = fabs(wfi[u] * rj[c]);
-              const double g = __dmul_rn(din[h], wfi[u]) + y1j[c] + y3i[u] + wfi[u] * rr4[c] + sin_[h];
-              double xn = xin[h] - tau * g / (3.0 + wr);
-              xn = fmin(fmax(xn, 0.0), 1.0);
-              const double xb = 2.0 * xn - xin[h];
-              const double sn = fmax(sin_[h] + shalf * (xb - cb[c]), 0.0);
-              xo[h] = xn; so[h] = sn;
-              a1[c] += xb; a4[c] += wfi[u] * xb; aS[c] += sn; rsum += xb;
-            }
-            *reinterpret_cast<double2*>(xp + o) = make_double2(xo[0], xo[1]);
-            *reinterpret_cast<double2*>(sp + o) = make_double2(so[0], so[1]);
-            *reinterpret_cast<double2*>(xsp + o) = make_double2(xs[u][k].x + xo[0], xs[u][k].y + xo[1]);
-            *reinterpret_cast<double2*>(ssp + o) = make_double2(ss[u][k].x + so[0], ss[u][k].y + so[1]);
-          }
-        }
-        rsum = warp_sum(rsum);
-        if (lane == 0 && ok[u]) P3[(int64_t)(ib + u * kMfWarps) * G.cti] = rsum;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < KV; ++k) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = 2 * k + h, col = k * 64 + 2 * lane + h;
-        sm[0][warp][col] = a1[c]; sm[1][warp][col] = a4[c]; sm[2][warp][col] = aS[c];
-      }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < 32 * K; c += kMfThreads) {
-      const int j = t.jt * G.JT + c;
-      if (j < N) {
-        const int64_t o = (((int64_t)b * G.F + f) * G.rt + t.it) * N + j;
-        st.P1[o] = column_total<K>(sm[0], c);
-        st.P4[o] = __ldg(r + j) * column_total<K>(sm[1], c);
-        st.PS[o] = column_total<K>(sm[2], c);
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// EXPERIMENTAL (opt-in, reserved bit 12; written after the round's GPU budget was spent -- parity tests are
-// gated by NEPTUNE_EXPERIMENTAL until it has run on a B200): the register pass with its four streams prefetched
-// by cp.async (LDGSTS, 16 bytes per lane) into a per-thread ring of D rows in shared memory.  A lane copies
-// and later reads only its own 16-byte slots, so no barrier is involved: shared memory acts as an asynchronous
-// extension of the register file -- D-1 rows of loads stay in flight while a row is computed (the ncu profile
-// of k_mf_iter shows a pass that waits on its own loads with 16-24 resident warps).  Results are stored from
-// registers.  Same tiles, partial-sum layout and per-column summation order as k_mf_iter<2*KV, .> (even N > 32).
-constexpr int kAsyncDepth = 3;
-
-template <int KV>
-__global__ void __launch_bounds__(kMfThreads, (KV == 1 ? 3 : 2))
-k_mf_iter_async(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
-  constexpr int K = 2 * KV, JT = 64 * KV, D = kAsyncDepth;
-  extern __shared__ __align__(16) double ring[];                         // [warps][D][4][JT]
-  __shared__ double sm[3][kMfWarps][32 * K];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int N = G.N;
-  const int64_t NN = (int64_t)N * N;
-  const int64_t total = (int64_t)B * G.tiles_inst;
-  double* const myring = ring + (size_t)warp * D * 4 * JT;
-  for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const Tile t = decode_tile(G, tile);
-    const int b = t.b, f = t.f;
-    if (ctl[b].converged) continue;
-    const double tau = ctl[b].tau, shalf = 0.5 * ctl[b].sigma;
-    const double* __restrict__ d = in.d + (int64_t)b * NN;
-    const double* __restrict__ w = in.w + ((int64_t)b * G.F + f) * N;
-    const double* __restrict__ r = in.r + ((int64_t)b * G.F + f) * N;
-    const double* __restrict__ y = st.y + (int64_t)b * G.rows;
-    const double* __restrict__ y3 = y + G.r3 + (int64_t)f * N;
-    double* __restrict__ xp = st.x + (int64_t)b * G.cols + (int64_t)f * NN;
-    double* __restrict__ xsp = st.xsum + (int64_t)b * G.cols + (int64_t)f * NN;
-    double* __restrict__ sp = st.y + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
-    double* __restrict__ ssp = st.ysum + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
-    const double* __restrict__ cbar = st.cbar + (int64_t)b * G.C + (int64_t)f * N;
-    double* __restrict__ P3 = st.P3i + ((int64_t)b * G.C + (int64_t)f * N) * G.cti + t.jt;
-
-    int jj[KV]; bool vj[KV];
-    double y1j[K], rj[K], rr4[K], cb[K];
-#pragma unroll
-    for (int k = 0; k < KV; ++k) {
-      const int j = t.jt * G.JT + k * 64 + 2 * lane;
-      vj[k] = j < N; jj[k] = vj[k] ? j : 0;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = 2 * k + h, jc = jj[k] + h;
-        y1j[c] = y[2 * ((int64_t)f * N + jc) + 1];
-        rj[c] = __ldg(r + jc);
-        rr4[c] = rj[c] * y[G.r4 + jc];
-        cb[c] = cbar[jc];
-      }
-    }
-    double a1[K], a4[K], aS[K];
-#pragma unroll
-    for (int c = 0; c < K; ++c) { a1[c] = 0.0; a4[c] = 0.0; aS[c] = 0.0; }
-
-    const int i0 = t.it * G.RT, i1 = min(N, i0 + G.RT);
-    const int nrows = (i1 - i0 - warp + kMfWarps - 1) / kMfWarps;          // rows of this warp: i0 + warp + 8 n
-    auto issue = [&](int n) {                                              // copies of row n into slot n % D
-      if (n < nrows) {
-        const int o = (i0 + warp + n * kMfWarps) * N;
-        double* slot = myring + (size_t)(n % D) * 4 * JT;
-#pragma unroll
-        for (int k = 0; k < KV; ++k) {
-          if (vj[k]) {
-            const int c = k * 64 + 2 * lane;
-            const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(slot + c);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0), "l"(xp + o + jj[k]) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + JT * 8), "l"(sp + o + jj[k]) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 2 * JT * 8), "l"(xsp + o + jj[k]) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 3 * JT * 8), "l"(ssp + o + jj[k]) : "memory");
-          }
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");                 // one group per row, empty ones included
-    };
-#pragma unroll
-    for (int n = 0; n < D - 1; ++n) issue(n);
-    for (int n = 0; n < nrows; ++n) {
-      issue(n + D - 1);
-      asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");     // this thread's copies of row n have landed
-      const int i = i0 + warp + n * kMfWarps;
-      const int o = i * N;
-      const double wfi = __ldg(w + i), y3i = y3[i];
-      const double* slot = myring + (size_t)(n % D) * 4 * JT;
-      double rsum = 0.0;
-#pragma unroll
-      for (int k = 0; k < KV; ++k) {
-        if (vj[k]) {
-          const int c0 = k * 64 + 2 * lane;
-          const double2 xv = *reinterpret_cast<const double2*>(slot + c0);
-          const double2 sv = *reinterpret_cast<const double2*>(slot + JT + c0);
-          const double2 xs = *reinterpret_cast<const double2*>(slot + 2 * JT + c0);
-          const double2 ss = *reinterpret_cast<const double2*>(slot + 3 * JT + c0);
-          const double2 dd = __ldg(reinterpret_cast<const double2*>(d + o + jj[k]));
-          const double xin[2] = {xv.x, xv.y}, sin_[2] = {sv.x, sv.y}, din[2] = {dd.x, dd.y};
-          double xo[2], so[2];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int c = 2 * k + h;
-            const double wr = fabs(wfi * rj[c]);
-            const double g = __dmul_rn(din[h], wfi) + y1j[c] + y3i + wfi * rr4[c] + sin_[h];
-            double xn = xin[h] - tau * g / (3.0 + wr);
-            xn = fmin(fmax(xn, 0.0), 1.0);
-            const double xb = 2.0 * xn - xin[h];
-            const double sn = fmax(sin_[h] + shalf * (xb - cb[c]), 0.0);
-            xo[h] = xn; so[h] = sn;
-            a1[c] += xb; a4[c] += wfi * xb; aS[c] += sn; rsum += xb;
-          }
-          *reinterpret_cast<double2*>(xp + o + jj[k]) = make_double2(xo[0], xo[1]);
-          *reinterpret_cast<double2*>(sp + o + jj[k]) = make_double2(so[0], so[1]);
-          *reinterpret_cast<double2*>(xsp + o + jj[k]) = make_double2(xs.x + xo[0], xs.y + xo[1]);
-          *reinterpret_cast<double2*>(ssp + o + jj[k]) = make_double2(ss.x + so[0], ss.y + so[1]);
-        }
-      }
-      rsum = warp_sum(rsum);
-      if (lane == 0) P3[(int64_t)i * G.cti] = rsum;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-#pragma unroll
-    for (int k = 0; k < KV; ++k) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = 2 * k + h, col = k * 64 + 2 * lane + h;
-        sm[0][warp][col] = a1[c]; sm[1][warp][col] = a4[c]; sm[2][warp][col] = aS[c];
-      }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < 32 * K; c += kMfThreads) {
-      const int j = t.jt * G.JT + c;
-      if (j < N) {
-        const int64_t o = (((int64_t)b * G.F + f) * G.rt + t.it) * N + j;
-        st.P1[o] = column_total<K>(sm[0], c);
-        st.P4[o] = __ldg(r + j) * column_total<K>(sm[1], c);
-        st.PS[o] = column_total<K>(sm[2], c);
-      }
-    }
-    __syncthreads();
-  }
-}
-
-template <int KV> constexpr size_t async_smem_bytes() { return (size_t)kMfWarps * kAsyncDepth * 4 * 64 * KV * 8; }
-
-// EXPERIMENTAL (opt-in, reserved bit 13; not yet run on a GPU): k_mf_iter<K, U> with the small-vector work
-// folded in.  Every block counts the tiles it finishes per instance; the block that finishes the LAST tile of an
-// instance does that instance's POST (and, unless the chunk ends here, PREC + Y2 of the next iteration) while
-// the other blocks stream other instances -- one launch per iteration instead of two, and the ~11 us of the
-// separate k_mf_small launch disappear into the pass.  Partial sums written by other blocks are read with
-// ld.global.cg after a __threadfence() on both sides of the counter.
-__device__ __forceinline__ double strided_sum_cg(const double* __restrict__ p, int n, int64_t stride) {
-  double a = 0.0;
-  for (int k0 = 0; k0 < n; k0 += 8) {
-    double v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = (k0 + u < n) ? __ldcg(p + (int64_t)(k0 + u) * stride) : 0.0;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) a += v[u];
-  }
-  return a;
-}
-
-// block-wide: the work of k_mf_small (same arithmetic, same summation order) for instance b
-__device__ void mf_small_block(const MfGeo& G, const MfIn& in, const MfSt& st, int b, double tau, double sigma,
-                               bool do_next) {
-  const int N = G.N, F = G.F, rt = G.rt, ct = G.cti;
-  const int C = (int)G.C;
-  double* __restrict__ y = st.y + (int64_t)b * G.rows;
-  double* __restrict__ ys = st.ysum + (int64_t)b * G.rows;
-  double* __restrict__ c = st.x + (int64_t)b * G.cols + G.X;
-  double* __restrict__ cs = st.xsum + (int64_t)b * G.cols + G.X;
-  double* __restrict__ cbar = st.cbar + (int64_t)b * C;
-  const double* __restrict__ P1 = st.P1 + (int64_t)b * F * rt * N;
-  const double* __restrict__ P4 = st.P4 + (int64_t)b * F * rt * N;
-  const double* __restrict__ PS = st.PS + (int64_t)b * F * rt * N;
-  const double* __restrict__ P3 = st.P3i + (int64_t)b * C * ct;
-  const double* __restrict__ m = in.m + (int64_t)b * F;
-  const double* __restrict__ Kj = in.Kj + (int64_t)b * N;
-  const double* __restrict__ Mj = in.Mj + (int64_t)b * N;
-  const int tid = threadIdx.x, nth = blockDim.x;
-  for (int j = tid; j < N; j += nth) {                           // C4 dual
-    const double a = strided_sum_cg(P4 + j, F * rt, N);
-    const double s = sigma * st.S4[(int64_t)b * N + j];
-    const double v = y[G.r4 + j] + s * a;
-    const double yn = v - s * fmin(v / s, Kj[j]);
-    y[G.r4 + j] = yn; ys[G.r4 + j] += yn;
-  }
-  const double s1 = sigma / (double)(N + 1), s3 = sigma / (double)N;
-  for (int q = tid; q < C; q += nth) {
-    const int f = q / N, j = q - f * N;
-    const int64_t po = (int64_t)f * rt * N + j;
-    const double a1 = strided_sum_cg(P1 + po, rt, N) - cbar[q];
-    const double a3 = strided_sum_cg(P3 + (int64_t)q * ct, ct, 1);
-    const double v1 = y[2 * q + 1] + s1 * a1;
-    const double y1 = v1 - s1 * fmax(v1 / s1, -kEps);
-    y[2 * q + 1] = y1; ys[2 * q + 1] += y1;
-    const double y3n = y[G.r3 + q] + s3 * a3 - s3;
-    y[G.r3 + q] = y3n; ys[G.r3 + q] += y3n;
-    if (do_next) {                                               // c columns of the next iteration
-      const double sS = strided_sum_cg(PS + po, rt, N);
-      const double mf = m[f];
-      const double gc = -y1 + mf * y[G.r2 + j] - sS;
-      const double co = c[q];
-      double cn = co - tau * gc / (1.0 + mf + (double)N);
-      cn = fmin(fmax(cn, 0.0), 1.0);
-      cbar[q] = 2.0 * cn - co;
-      c[q] = cn; cs[q] += cn;
-    }
-  }
-  if (do_next) {
-    __syncthreads();                                             // every cbar of the instance is written
-    const double s = sigma * st.S2[b];
-    for (int j = tid; j < N; j += nth) {
-      double a = 0.0;
-      for (int f = 0; f < F; ++f) a += m[f] * cbar[(int64_t)f * N + j];
-      const double v = y[G.r2 + j] + s * a;
-      const double yn = v - s * fmin(v / s, Mj[j]);
-      y[G.r2 + j] = yn; ys[G.r2 + j] += yn;
-    }
-  }
-}
-
-template <int K, int U>
-__global__ void __launch_bounds__(kMfThreads, (K * U >= 4 ? 2 : 3))
-k_mf_iter_fused(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, int chunk_len) {
-  __shared__ double sm[3][kMfWarps][32 * K];
-  __shared__ int s_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int N = G.N;
-  const int64_t NN = (int64_t)N * N;
-  const int64_t total = (int64_t)B * G.tiles_inst;
-  for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const Tile t = decode_tile(G, tile);
-    const int b = t.b, f = t.f;
-    if (ctl[b].converged) continue;
-    const double tau = ctl[b].tau, sigma = ctl[b].sigma, shalf = 0.5 * sigma;
-    const double* __restrict__ d = in.d + (int64_t)b * NN;
-    const double* __restrict__ w = in.w + ((int64_t)b * G.F + f) * N;
-    const double* __restrict__ r = in.r + ((int64_t)b * G.F + f) * N;
-    const double* __restrict__ y = st.y + (int64_t)b * G.rows;
-    const double* __restrict__ y3 = y + G.r3 + (int64_t)f * N;
-    double* __restrict__ xp = st.x + (int64_t)b * G.cols + (int64_t)f * NN;
-    double* __restrict__ xsp = st.xsum + (int64_t)b * G.cols + (int64_t)f * NN;
-    double* __restrict__ sp = st.y + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
-    double* __restrict__ ssp = st.ysum + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
-    const double* __restrict__ cbar = st.cbar + (int64_t)b * G.C + (int64_t)f * N;
-    double* __restrict__ P3 = st.P3i + ((int64_t)b * G.C + (int64_t)f * N) * G.cti + t.jt;
-
-    int jj[K]; bool vj[K];
-    double y1j[K], rj[K], rr4[K], cb[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int j = t.jt * G.JT + k * 32 + lane;
-      vj[k] = j < N; jj[k] = vj[k] ? j : 0;
-      y1j[k] = y[2 * ((int64_t)f * N + jj[k]) + 1];
-      rj[k] = __ldg(r + jj[k]);
-      rr4[k] = rj[k] * y[G.r4 + jj[k]];
-      cb[k] = cbar[jj[k]];
-    }
-    double a1[K], a4[K], aS[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) { a1[k] = 0.0; a4[k] = 0.0; aS[k] = 0.0; }
-
-    const int i0 = t.it * G.RT, i1 = min(N, i0 + G.RT);
-    for (int ib = i0 + warp; ib < i1; ib += U * kMfWarps) {
-      double xv[U][K], sv[U][K], xs[U][K], ss[U][K], dv[U][K], wfi[U], y3i[U];
-      int ro[U]; bool ok[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = ib + u * kMfWarps;
-        ok[u] = i < i1;
-        const int ir = ok[u] ? i : ib;
-        ro[u] = ir * N;
-        wfi[u] = __ldg(w + ir); y3i[u] = y3[ir];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const int o = ro[u] + jj[k];
-          xv[u][k] = xp[o]; sv[u][k] = sp[o]; xs[u][k] = xsp[o]; ss[u][k] = ssp[o];
-          dv[u][k] = __ldg(d + o);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        double rsum = 0.0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          if (ok[u] && vj[k]) {
-            const int o = ro[u] + jj[k];
-            const double wr = fabs(wfi[u] * rj[k]);
-            const double g = __dmul_rn(dv[u][k], wfi[u]) + y1j[k] + y3i[u] + wfi[u] * rr4[k] + sv[u][k];
-            double xn = xv[u][k] - tau * g / (3.0 + wr);
-            xn = fmin(fmax(xn, 0.0), 1.0);
-            const double xb = 2.0 * xn - xv[u][k];
-            const double sn = fmax(sv[u][k] + shalf * (xb - cb[k]), 0.0);
-            xp[o] = xn; sp[o] = sn;
-            xsp[o] = xs[u][k] + xn; ssp[o] = ss[u][k] + sn;
-            a1[k] += xb; a4[k] += wfi[u] * xb; aS[k] += sn; rsum += xb;
-          }
-        }
-        rsum = warp_sum(rsum);
-        if (lane == 0 && ok[u]) P3[(int64_t)(ib + u * kMfWarps) * G.cti] = rsum;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      sm[0][warp][k * 32 + lane] = a1[k]; sm[1][warp][k * 32 + lane] = a4[k]; sm[2][warp][k * 32 + lane] = aS[k];
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < 32 * K; c += kMfThreads) {
-      const int j = t.jt * G.JT + c;
-      if (j < N) {
-        const int64_t o = (((int64_t)b * G.F + f) * G.rt + t.it) * N + j;
-        st.P1[o] = column_total<K>(sm[0], c);
-        st.P4[o] = __ldg(r + j) * column_total<K>(sm[1], c);
-        st.PS[o] = column_total<K>(sm[2], c);
-      }
-    }
-    // ---- tile done: is it the last one of this instance in this launch? ----
-    __threadfence();                                             // the partial sums above are visible device-wide ...
-    __syncthreads();                                             // ... for every thread of the block, before the count
-    if (threadIdx.x == 0) s_last = (atomicAdd(st.cnt + 2 * b, 1) == G.tiles_inst - 1);
-    __syncthreads();
-    if (s_last) {                                                // block-uniform
-      __threadfence();
-      const int done = st.cnt[2 * b + 1] + 1;                    // iterations of the chunk including this one
-      mf_small_block(G, in, st, b, tau, sigma, done < chunk_len);
-      __syncthreads();
-      if (threadIdx.x == 0) { st.cnt[2 * b] = 0; st.cnt[2 * b + 1] = done < chunk_len ? done : 0; }
-    }
-    __syncthreads();
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// the iteration pass, TMA version (even N): x and yS of a tile are contiguous in memory, so they are staged
-// in shared memory by 1-D bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP), five stages deep -- those bytes
-// in flight do not live in registers; the running sums (xsum, ysum) and d are read with ordinary loads issued
-// BEFORE the wait on the bulk copy, and all four results are stored from registers, so a stage is free again
-// as soon as the block has read it (measured on B200: staging all four streams and writing them back with
-// bulk stores is bounded by the per-SM bulk-copy rate, ~3.4 TB/s of loads chip-wide, and serialises compute
-// with the copies -- gpurun_out/mf_diag.log, profiles/r01f_*).
-//   super-tile = (instance, function, row tile `it` of RT rows, column segment `js` of JS columns): owns the
-//                column sums written to P1 / P4 / PS; processed as tiles of RS rows (RS*JS <= kTmaChunk)
-//   thread -> fixed column(s) of the segment, so the column constants (y1, r, r*y4, cbar) and the three column
-//             accumulators live in registers; JS <= 256: G = 256/JS row groups; else CPT columns per thread;
-//             four (CPT = 1) rows of a column are in flight per thread (independent dependency chains)
-//   row sums of xbar: xbar goes to a shared tile, a warp per row adds it up after the barrier.
-// ---------------------------------------------------------------------------------------------------
-constexpr int kTmaStages = 5;
-constexpr int kTmaChunk = 1024;                 // doubles per stream and stage (8 KB)
-constexpr int kTmaMaxCPT = 4;
-
-struct TmaGeo { int JS, cts, RS, G, CPT, supers_inst; };
-
-static bool tma_geo(const MfGeo& G, TmaGeo& T) {
-  const int N = G.N;
-  if (N & 1) return false;                      // 16-byte alignment of every row start needs an even N
-  int cts = (N + kTmaChunk - 1) / kTmaChunk;
-  int JS = (N + cts - 1) / cts; JS += JS & 1;   // even segment width
-  cts = (N + JS - 1) / JS;
-  T.JS = JS; T.cts = cts;
-  T.RS = cts > 1 ? 1 : kTmaChunk / N;           // full rows per tile (one row segment when the row is split)
-  if (T.RS > G.RT) T.RS = G.RT;
-  if (T.RS < 1) return false;
-  T.G = JS <= kMfThreads ? kMfThreads / JS : 1;
-  T.CPT = JS <= kMfThreads ? 1 : (JS + kMfThreads - 1) / kMfThreads;
-  if (T.CPT > kTmaMaxCPT) return false;
-  T.supers_inst = G.F * G.rt * cts;
-  return true;
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "MF_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra MF_DONE_%=;\n"
-      "bra MF_WAIT_%=;\n"
-      "MF_DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-               ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-struct TmaCursor { int64_t su; int tk; };       // super-tile of this block, tile inside it
-
-struct TmaTile {
-  int b, f, it, js;
-  int i0, nr, j0, jw, ntiles;                   // rows [i0, i0+nr) x columns [j0, j0+jw); tiles of the super-tile
-  int64_t off;                                  // element offset of the tile inside the function's N x N slab
-};
-
-__device__ __forceinline__ TmaTile tma_tile(const MfGeo& G, const TmaGeo& T, const TmaCursor& c) {
-  TmaTile t;
-  t.b = (int)(c.su / T.supers_inst);
-  int k = (int)(c.su - (int64_t)t.b * T.supers_inst);
-  t.js = k % T.cts; k /= T.cts;
-  t.it = k % G.rt; t.f = k / G.rt;
-  const int r0 = t.it * G.RT, r1 = min(G.N, r0 + G.RT);
-  t.ntiles = (r1 - r0 + T.RS - 1) / T.RS;
-  t.i0 = r0 + c.tk * T.RS; t.nr = min(T.RS, r1 - t.i0);
-  t.j0 = t.js * T.JS; t.jw = min(T.JS, G.N - t.j0);
-  t.off = (int64_t)t.i0 * G.N + t.j0;
-  return t;
-}
-
-// next (super-tile, tile) of this block, skipping converged instances; su >= total when exhausted
-__device__ __forceinline__ void tma_skip(const MfGeo&, const TmaGeo& T, const Ctl* __restrict__ ctl, int64_t total,
-                                         TmaCursor& c) {
-  while (c.su < total && ctl[(int)(c.su / T.supers_inst)].converged) c.su += gridDim.x;
-}
-__device__ __forceinline__ void tma_next(const MfGeo& G, const TmaGeo& T, const Ctl* __restrict__ ctl, int64_t total,
-                                         TmaCursor& c) {
-  const TmaTile t = tma_tile(G, T, c);
-  if (c.tk + 1 < t.ntiles) { c.tk += 1; return; }
-  c.tk = 0; c.su += gridDim.x;
-  tma_skip(G, T, ctl, total, c);
-}
-
-template <int CPT>
-__global__ void __launch_bounds__(kMfThreads, 2)
-k_mf_iter_tma(MfGeo G, TmaGeo T, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, int diag) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* stage = reinterpret_cast<double*>(smem_raw);                   // [kTmaStages][2][kTmaChunk]  x, yS
-  double* xb = stage + kTmaStages * 2 * kTmaChunk;                       // [kTmaChunk]
-  double* red = xb + kTmaChunk;                                          // [3][kMfThreads]
-  double* rowtab = red + 3 * kMfThreads;                                 // [2][64]  w[f,i], y3[f,i]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rowtab + 2 * 64);         // [kTmaStages]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int N = G.N;
-  const int64_t NN = (int64_t)N * N;
-  const int64_t total = (int64_t)B * T.supers_inst;
-
-  if (tid == 0) {
-    for (int s = 0; s < kTmaStages; ++s) mbar_init(bars + s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  // x and yS of a tile arrive by bulk copy (lanes 0 and 1 of warp 0 issue one stream each); the running sums
-  // and the results travel through registers (LDG / STG), so a stage is free again as soon as it has been read
-  const bool mover = warp == 0 && lane < 2;
-  auto issue_load = [&](const TmaCursor& c, int n) {                     // movers only
-    const TmaTile t = tma_tile(G, T, c);
-    const int s = n % kTmaStages;
-    const uint32_t bytes = (uint32_t)(t.nr * t.jw) * 8u;
-    const int64_t xo = (int64_t)t.b * G.cols + (int64_t)t.f * NN + t.off;
-    const int64_t yo = (int64_t)t.b * G.rows + G.rs + (int64_t)t.f * NN + t.off;
-    if (lane == 0) mbar_expect_tx(bars + s, 2u * bytes);
-    bulk_g2s(stage + ((size_t)s * 2 + lane) * kTmaChunk, lane == 0 ? st.x + xo : st.y + yo, bytes, bars + s);
-  };
-
-  TmaCursor cons{(int64_t)blockIdx.x, 0};
-  tma_skip(G, T, ctl, total, cons);
-  TmaCursor prod = cons;
-  int n_prod = 0;
-  if (mover) {
-    for (; n_prod < kTmaStages && prod.su < total; ++n_prod) { issue_load(prod, n_prod); tma_next(G, T, ctl, total, prod); }
-  }
-
-  // thread -> column(s)
-  const int grp = (CPT == 1) ? tid / T.JS : 0;
-  const int jl0 = (CPT == 1) ? tid - grp * T.JS : tid;
-  const int rstep = (CPT == 1) ? T.G : 1;
-  constexpr int U = (CPT == 1) ? 4 : (CPT == 2 ? 2 : 1);                 // rows in flight per thread
-  double y1j[CPT], rj[CPT], rr4[CPT], cb[CPT], a1[CPT], a4[CPT], aS[CPT];
-  bool act[CPT];
-  double tau = 0.0, shalf = 0.0;
-
-  for (int n = 0; cons.su < total; ++n) {
-    const TmaTile t = tma_tile(G, T, cons);
-    const int b = t.b, f = t.f;
-    const double* __restrict__ y = st.y + (int64_t)b * G.rows;
-    if (cons.tk == 0) {                                                  // new super-tile: constants, accumulators
-      tau = ctl[b].tau; shalf = 0.5 * ctl[b].sigma;
-      const double* __restrict__ r = in.r + ((int64_t)b * G.F + f) * N;
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) {
-        const int jl = jl0 + c * kMfThreads;
-        act[c] = (CPT > 1 || grp < T.G) && jl < t.jw;
-        const int j = act[c] ? t.j0 + jl : 0;
-        y1j[c] = y[2 * ((int64_t)f * N + j) + 1];
-        rj[c] = __ldg(r + j);
-        rr4[c] = rj[c] * y[G.r4 + j];
-        cb[c] = st.cbar[(int64_t)b * G.C + (int64_t)f * N + j];
-        a1[c] = 0.0; a4[c] = 0.0; aS[c] = 0.0;
-      }
-      const int r0 = t.it * G.RT, nrows = min(N, r0 + G.RT) - r0;
-      if (tid < nrows) {
-        rowtab[tid] = __ldg(in.w + ((int64_t)b * G.F + f) * N + r0 + tid);
-        rowtab[64 + tid] = y[G.r3 + (int64_t)f * N + r0 + tid];
-      }
-      __syncthreads();
-    }
-    const int s = n % kTmaStages;
-    const double* __restrict__ sx = stage + (size_t)s * 2 * kTmaChunk;
-    const double* __restrict__ sy = sx + kTmaChunk;
-    const int64_t xo = (int64_t)b * G.cols + (int64_t)f * NN + t.off;
-    const int64_t yo = (int64_t)b * G.rows + G.rs + (int64_t)f * NN + t.off;
-    double* __restrict__ gx = st.x + xo;
-    double* __restrict__ gs = st.y + yo;
-    double* __restrict__ gxs = st.xsum + xo;
-    double* __restrict__ gys = st.ysum + yo;
-    const double* __restrict__ d = in.d + (int64_t)b * NN + (int64_t)t.i0 * N + t.j0;
-    const int rbase = t.i0 - t.it * G.RT;                                // row of the tile inside the super-tile
-    const int nr = (diag & 1) ? 0 : t.nr;
-
-    double xs[U][CPT], ysm[U][CPT], dv[U][CPT];
-    auto load_lsu = [&](int ib) {                                        // the register-path streams of one batch
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int ii = ib + u * rstep;
-        const int ir = ii < nr ? ii : 0;
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-          const int jl = act[c] ? jl0 + c * kMfThreads : 0;
-          const int e = ir * t.jw + jl;
-          xs[u][c] = gxs[e]; ysm[u][c] = gys[e];
-          dv[u][c] = __ldg(d + (int64_t)ir * N + jl);
-        }
-      }
-    };
-    if (grp < nr) load_lsu(grp);                                         // in flight while the bulk copy lands
-    mbar_wait(bars + s, (uint32_t)((n / kTmaStages) & 1));
-
-    for (int ib = grp; ib < nr; ib += U * rstep) {
-      if (ib != grp) load_lsu(ib);
-      double xv[U][CPT], sv[U][CPT], wfi[U], y3i[U];
-      bool ok[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int ii = ib + u * rstep;
-        ok[u] = ii < nr;
-        const int ir = ok[u] ? ii : 0;
-        wfi[u] = rowtab[rbase + ir]; y3i[u] = rowtab[64 + rbase + ir];
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-          const int e = ir * t.jw + (act[c] ? jl0 + c * kMfThreads : 0);
-          xv[u][c] = sx[e]; sv[u][c] = sy[e];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-          if (ok[u] && act[c]) {
-            const int e = (ib + u * rstep) * t.jw + jl0 + c * kMfThreads;
-            const double wr = fabs(wfi[u] * rj[c]);
-            const double g = __dmul_rn(dv[u][c], wfi[u]) + y1j[c] + y3i[u] + wfi[u] * rr4[c] + sv[u][c];
-            double xn = xv[u][c] - tau * g / (3.0 + wr);
-            xn = fmin(fmax(xn, 0.0), 1.0);
-            const double xbar = 2.0 * xn - xv[u][c];
-            const double sn = fmax(sv[u][c] + shalf * (xbar - cb[c]), 0.0);
-            gx[e] = xn; gs[e] = sn;
-            gxs[e] = xs[u][c] + xn; gys[e] = ysm[u][c] + sn;
-            xb[e] = xbar;
-            a1[c] += xbar; a4[c] += wfi[u] * xbar; aS[c] += sn;
-          }
-        }
-      }
-    }
-    __syncthreads();                                                     // stage read by everybody, xbar tile complete
-    if (mover && prod.su < total) { issue_load(prod, n_prod); ++n_prod; tma_next(G, T, ctl, total, prod); }
-    // row sums of xbar (complete over the column segment)
-    for (int ii = warp; ii < ((diag & 2) ? 0 : t.nr); ii += kMfWarps) {
-      double rs = 0.0;
-      for (int jl = lane; jl < t.jw; jl += 32) rs += xb[ii * t.jw + jl];
-      rs = warp_sum(rs);
-      if (lane == 0) st.P3i[((int64_t)b * G.C + (int64_t)f * N + t.i0 + ii) * G.cti + t.js] = rs;
-    }
-    if (cons.tk + 1 == t.ntiles) {                                       // super-tile complete: column sums out
-      const int64_t o = (((int64_t)b * G.F + f) * G.rt + t.it) * N + t.j0;
-      if (CPT == 1) {
-        red[tid] = a1[0]; red[kMfThreads + tid] = a4[0]; red[2 * kMfThreads + tid] = aS[0];
-        __syncthreads();
-        if (tid < t.jw) {
-          double s1 = 0.0, s4 = 0.0, sS = 0.0;
-          for (int g2 = 0; g2 < T.G; ++g2) {
-            const int k = g2 * T.JS + tid;
-            s1 += red[k]; s4 += red[kMfThreads + k]; sS += red[2 * kMfThreads + k];
-          }
-          const double rr = __ldg(in.r + ((int64_t)b * G.F + f) * N + t.j0 + tid);
-          st.P1[o + tid] = s1; st.P4[o + tid] = rr * s4; st.PS[o + tid] = sS;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-          if (act[c]) {
-            const int jl = jl0 + c * kMfThreads;
-            st.P1[o + jl] = a1[c]; st.P4[o + jl] = rj[c] * a4[c]; st.PS[o + jl] = aS[c];
-          }
-        }
-      }
-    }
-    __syncthreads();
-    tma_next(G, T, ctl, total, cons);
-  }
-}
-
-constexpr size_t kTmaSmemBytes = (size_t)(kTmaStages * 2 * kTmaChunk + kTmaChunk + 3 * kMfThreads + 2 * 64) * 8 +
-                                 kTmaStages * 8 + 64;
 
 // ---------------------------------------------------------------------------------------------------
 // KKT pieces of a candidate (which = 0: current iterate, 1: running average): the same partial sums from a
@@ -1661,62 +807,18 @@ template <class Kern> static int mf_grid(Kern kern) {
 struct MfPlan {
   int B; MfGeo G; MfIn in; MfSt st; Ctl* ctl; cudaStream_t s;
   int grid_iter, grid_eval, small_blocks, fused;
-  int use_tma; TmaGeo T;
-  int rows_in_flight;            // U of k_mf_iter<K, U>
-  int vec;                       // k_mf_iter_vec (16-byte accesses) instead of k_mf_iter
-  int async_copy;                // k_mf_iter_async (experimental)
-  int lean;                      // k_mf_iter_lean (experimental)
-  int pair;                      // k_mf_iter2 (pair version: 16-byte accesses, cheap reciprocal)
-  int diag;                      // tools only: bits of params->reserved >> 4 switch parts of the TMA pass off
+  int rows_in_flight;            // U of k_mf_iter<K, U> / k_mf_iter2<KP, U>
+  int pair;                      // k_mf_iter2 (pairs of adjacent columns, 16-byte accesses) instead of k_mf_iter
+  int diag;                      // tools only: bit 2 = time the small-vector kernel alone
 };
 
 static void mf_launch_iter(const MfPlan& P) {
   if (P.diag & 4) return;          // tools: time the small-vector kernel alone
-  if (P.use_tma) {
-    const int64_t supers = (int64_t)P.B * P.T.supers_inst;
-    const int g = (int)(supers < 2 * kNumSMs ? supers : 2 * kNumSMs);
-    switch (P.T.CPT) {
-      case 1: k_mf_iter_tma<1><<<g, kMfThreads, kTmaSmemBytes, P.s>>>(P.G, P.T, P.in, P.st, P.ctl, P.B, P.diag); break;
-      case 2: k_mf_iter_tma<2><<<g, kMfThreads, kTmaSmemBytes, P.s>>>(P.G, P.T, P.in, P.st, P.ctl, P.B, P.diag); break;
-      default: k_mf_iter_tma<4><<<g, kMfThreads, kTmaSmemBytes, P.s>>>(P.G, P.T, P.in, P.st, P.ctl, P.B, P.diag); break;
-    }
-    NEPTUNE_COUNT(1);
-    return;
-  }
   const int64_t total = (int64_t)P.B * P.G.tiles_inst;
   const int g = (int)(total < P.grid_iter ? total : P.grid_iter);
-  if (P.async_copy) {
-    if (P.G.K == 2) k_mf_iter_async<1><<<g, kMfThreads, async_smem_bytes<1>(), P.s>>>(P.G, P.in, P.st, P.ctl, P.B);
-    else k_mf_iter_async<2><<<g, kMfThreads, async_smem_bytes<2>(), P.s>>>(P.G, P.in, P.st, P.ctl, P.B);
-    NEPTUNE_COUNT(1);
-    return;
-  }
   if (P.pair) {
-    switch (P.G.K * 10 + P.rows_in_flight) {
-      case 21: k_mf_iter2<1, 1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
-      case 22: k_mf_iter2<1, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
-      case 41: k_mf_iter2<2, 1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
-      default: k_mf_iter2<2, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
-    }
-    NEPTUNE_COUNT(1);
-    return;
-  }
-  if (P.lean) {
-    switch (P.G.K) {
-      case 1: k_mf_iter_lean<1, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
-      case 2: k_mf_iter_lean<2, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
-      default: k_mf_iter_lean<4, 1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
-    }
-    NEPTUNE_COUNT(1);
-    return;
-  }
-  if (P.vec) {
-    switch (P.G.K * 10 + P.rows_in_flight) {
-      case 22: k_mf_iter_vec<1, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
-      case 24: k_mf_iter_vec<1, 4><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
-      case 41: k_mf_iter_vec<2, 1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
-      default: k_mf_iter_vec<2, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
-    }
+    if (P.rows_in_flight == 1) k_mf_iter2<1, 1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B);
+    else k_mf_iter2<1, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B);
     NEPTUNE_COUNT(1);
     return;
   }
@@ -1730,6 +832,34 @@ static void mf_launch_iter(const MfPlan& P) {
     default: k_mf_iter<4, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
   }
   NEPTUNE_COUNT(1);
+}
+
+// which pass runs and with how many rows in flight; `reserved`: bit 0 forces the 8-byte pass, bits 8..10 override U
+static void mf_choose_pass(MfPlan& P, int reserved, const void* x, const void* y, const void* d) {
+  const MfGeo& G = P.G;
+  switch (G.K) {
+    case 1: P.grid_eval = mf_grid(k_mf_eval<1>); break;
+    case 2: P.grid_eval = mf_grid(k_mf_eval<2>); break;
+    default: P.grid_eval = mf_grid(k_mf_eval<4>); break;
+  }
+  P.rows_in_flight = (reserved >> 8) & 7;
+  P.pair = !(reserved & 1) && !(G.N & 1) && G.K == 2 && G.N <= 64 && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)d) & 15) == 0;
+  if (P.pair) {
+    if (P.rows_in_flight != 1 && P.rows_in_flight != 2) P.rows_in_flight = 2;
+    P.grid_iter = P.rows_in_flight == 1 ? mf_grid(k_mf_iter2<1, 1>) : mf_grid(k_mf_iter2<1, 2>);
+    return;
+  }
+  if (P.rows_in_flight != 1 && P.rows_in_flight != 2 && !(P.rows_in_flight == 4 && G.K == 1))
+    P.rows_in_flight = G.K == 4 ? 1 : 2;
+  switch (G.K * 10 + P.rows_in_flight) {
+    case 11: P.grid_iter = mf_grid(k_mf_iter<1, 1>); break;
+    case 12: P.grid_iter = mf_grid(k_mf_iter<1, 2>); break;
+    case 14: P.grid_iter = mf_grid(k_mf_iter<1, 4>); break;
+    case 21: P.grid_iter = mf_grid(k_mf_iter<2, 1>); break;
+    case 22: P.grid_iter = mf_grid(k_mf_iter<2, 2>); break;
+    case 41: P.grid_iter = mf_grid(k_mf_iter<4, 1>); break;
+    default: P.grid_iter = mf_grid(k_mf_iter<4, 2>); break;
+  }
 }
 
 static void mf_launch_eval(const MfPlan& P, int which, int only_ps) {
@@ -1764,16 +894,13 @@ using namespace neptune;
 
 // host-only: the tile geometry the solver would use (tests, tools).  out[0..7] = {K columns per lane, JT columns per
 // tile, ct column tiles, RT rows per tile, rt row tiles, tiles per instance, F*N <= 4096 (single-block small
-// kernel), 0}; out[8..15] = bulk-copy pass {applicable, JS, cts, RS, G, CPT, super-tiles per instance, 0}
+// kernel), 0}; out[8..15] = 0 (reserved)
 extern "C" int neptune_pdhg_mf_geometry(int B, int N, int F, int32_t* out) {
   if (B <= 0 || N <= 0 || F <= 0 || !out) return NEPTUNE_E_ARG;
   const MfGeo G = make_geo(N, F, B);
   out[0] = G.K; out[1] = G.JT; out[2] = G.ct; out[3] = G.RT; out[4] = G.rt; out[5] = G.tiles_inst;
   out[6] = G.C <= 4096; out[7] = 0;
-  TmaGeo T{};
-  const bool ok = tma_geo(G, T);
-  out[8] = ok; out[9] = T.JS; out[10] = T.cts; out[11] = T.RS; out[12] = T.G; out[13] = T.CPT == 3 ? 4 : T.CPT;
-  out[14] = T.supers_inst; out[15] = 0;
+  for (int k = 8; k < 16; ++k) out[k] = 0;          // (bulk-copy pass geometry of round 1: removed)
   return 0;
 }
 
@@ -1785,204 +912,6 @@ extern "C" int neptune_pdhg_mf_workspace_bytes(int B, int N, int F, int64_t* byt
   *bytes = (int64_t)mf_layout(B, G).total;
   return 0;
 }
-
-// EXPERIMENTAL (reserved bit 13): the solve loop with k_mf_iter_fused -- a copy of neptune_pdhg_mf_solve whose chunk is
-// small(PREC, Y2) once, then check_every launches of the fused pass.  Kept separate so that the default loop
-// below stays exactly what ran on the GPU in round 1.
-static int mf_solve_fused(int B, int N, int F, int kind, const double* d, const double* w,
-                                     const double* r, const double* m, const double* Mj, const double* Kj,
-                                     const neptune_pdhg_params* prm, double* x, double* y,
-                                     neptune_pdhg_result* result_d, void* workspace, int64_t workspace_bytes,
-                                     void* stream) {
-  if (B <= 0 || N <= 0 || F <= 0) return NEPTUNE_E_ARG;
-  if (kind != NEPTUNE_KIND_MIN_DELAY) return NEPTUNE_E_ARG;      // the n columns / C5 / C6 rows are not stated here
-  if (!d || !w || !r || !m || !Mj || !Kj || !prm || !x || !y || !result_d || !workspace) return NEPTUNE_E_ARG;
-  int64_t need = 0;
-  { int rc = neptune_pdhg_mf_workspace_bytes(B, N, F, &need); if (rc) return rc; }
-  if (workspace_bytes < need) return NEPTUNE_E_NOMEM;
-  if ((int64_t)B * make_geo(N, F, B).tiles_inst >= (int64_t)INT32_MAX) return NEPTUNE_E_SIZE;
-
-  cudaStream_t caller = (cudaStream_t)stream;
-  cudaStream_t s = nullptr;
-  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-  NEPTUNE_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-  NEPTUNE_CUDA_OK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
-  NEPTUNE_CUDA_OK(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
-  NEPTUNE_CUDA_OK(cudaEventRecord(ev_in, caller));
-  NEPTUNE_CUDA_OK(cudaStreamWaitEvent(s, ev_in, 0));
-  const int check_every = prm->check_every > 0 ? prm->check_every : 64;
-  const int max_iters = prm->max_iters > 0 ? prm->max_iters : 20000;
-
-  MfPlan P{};
-  P.B = B; P.G = make_geo(N, F, B); P.s = s;
-  P.in = MfIn{d, w, r, m, Mj, Kj};
-  const MfGeo& G = P.G;
-  const MfWs W = mf_layout(B, G);
-  char* base = (char*)workspace;
-  double* xres = (double*)(base + W.xres); double* yres = (double*)(base + W.yres);
-  double* part = (double*)(base + W.part);
-  int* d_flag = (int*)(base + W.flag);          // [0] all done, [1] skip-POST flag of the graph's first node
-  Ctl* ctl = (Ctl*)(base + W.ctl);
-  P.ctl = ctl;
-  P.st = MfSt{x, y, (double*)(base + W.xsum), (double*)(base + W.ysum), (double*)(base + W.cbar),
-              (double*)(base + W.P1), (double*)(base + W.P4), (double*)(base + W.PS), (double*)(base + W.P3),
-              (double*)(base + W.P3i),
-              (double*)(base + W.S4), (double*)(base + W.S2), (double*)(base + W.wsum), (double*)(base + W.scal)};
-  // register pass variant: 16-byte accesses (k_mf_iter_vec) are opt-in (reserved bit 11; even N > 32, aligned
-  // vectors) -- measured equal or slower than the 8-byte pass on B200 (profiles/r01f_summary.md); rows in flight
-  // per warp: reserved bits 8..10 override (tools), default by K
-  P.vec = (prm->reserved & 0x800) && !(N & 1) && G.K >= 2 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
-  P.rows_in_flight = (prm->reserved >> 8) & 7;
-  P.async_copy = (prm->reserved & 0x1000) && !(N & 1) && G.K >= 2 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
-  if (P.async_copy) {
-    P.vec = 0;
-    int occ = 0;
-    if (G.K == 2) {
-      NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_mf_iter_async<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)async_smem_bytes<1>()));
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mf_iter_async<1>, kMfThreads, async_smem_bytes<1>());
-    } else {
-      NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_mf_iter_async<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)async_smem_bytes<2>()));
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mf_iter_async<2>, kMfThreads, async_smem_bytes<2>());
-    }
-    P.grid_iter = kNumSMs * (occ < 1 ? 1 : occ);
-  } else if (P.vec) {
-    if (G.K == 2 && P.rows_in_flight != 2 && P.rows_in_flight != 4) P.rows_in_flight = 2;
-    if (G.K == 4 && P.rows_in_flight != 1 && P.rows_in_flight != 2) P.rows_in_flight = 1;
-    switch (G.K * 10 + P.rows_in_flight) {
-      case 22: P.grid_iter = mf_grid(k_mf_iter_vec<1, 2>); break;
-      case 24: P.grid_iter = mf_grid(k_mf_iter_vec<1, 4>); break;
-      case 41: P.grid_iter = mf_grid(k_mf_iter_vec<2, 1>); break;
-      default: P.grid_iter = mf_grid(k_mf_iter_vec<2, 2>); break;
-    }
-  } else {
-    if (P.rows_in_flight != 1 && P.rows_in_flight != 2 && !(P.rows_in_flight == 4 && G.K == 1))
-      P.rows_in_flight = G.K == 4 ? 1 : 2;
-    switch (G.K * 10 + P.rows_in_flight) {
-      case 11: P.grid_iter = mf_grid(k_mf_iter<1, 1>); break;
-      case 12: P.grid_iter = mf_grid(k_mf_iter<1, 2>); break;
-      case 14: P.grid_iter = mf_grid(k_mf_iter<1, 4>); break;
-      case 21: P.grid_iter = mf_grid(k_mf_iter<2, 1>); break;
-      case 22: P.grid_iter = mf_grid(k_mf_iter<2, 2>); break;
-      case 41: P.grid_iter = mf_grid(k_mf_iter<4, 1>); break;
-      default: P.grid_iter = mf_grid(k_mf_iter<4, 2>); break;
-    }
-  }
-  switch (G.K) {
-    case 1: P.grid_eval = mf_grid(k_mf_eval<1>); break;
-    case 2: P.grid_eval = mf_grid(k_mf_eval<2>); break;
-    default: P.grid_eval = mf_grid(k_mf_eval<4>); break;
-  }
-  // bulk-copy-staged iteration pass: opt-in (bit 0 of params->reserved) where every tile is 16-byte aligned
-  // (even N, aligned vectors); measured slower than the register pass on B200 at every BASELINE shape
-  P.use_tma = 0;
-  P.diag = (prm->reserved >> 4) & 7;
-  if ((prm->reserved & 1) && tma_geo(G, P.T) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
-    if (P.T.CPT == 3) P.T.CPT = 4;
-    cudaError_t e;
-    switch (P.T.CPT) {
-      case 1: e = cudaFuncSetAttribute(k_mf_iter_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes); break;
-      case 2: e = cudaFuncSetAttribute(k_mf_iter_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes); break;
-      default: e = cudaFuncSetAttribute(k_mf_iter_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes); break;
-    }
-    NEPTUNE_CUDA_OK(e);
-    P.use_tma = 1;
-    P.G.cti = P.T.cts;
-  }
-  // fused pass: 8-byte register pass with the default rows in flight; counters zeroed once (the kernel resets them)
-  P.use_tma = 0; P.vec = 0; P.async_copy = 0; P.G.cti = P.G.ct;
-  P.rows_in_flight = G.K == 4 ? 1 : 2;
-  P.st.cnt = (int*)(base + W.cnt);
-  NEPTUNE_CUDA_OK(cudaMemsetAsync(P.st.cnt, 0, (size_t)B * 2 * sizeof(int), s));
-  switch (G.K) {
-    case 1: P.grid_iter = mf_grid(k_mf_iter_fused<1, 2>); break;
-    case 2: P.grid_iter = mf_grid(k_mf_iter_fused<2, 2>); break;
-    default: P.grid_iter = mf_grid(k_mf_iter_fused<4, 1>); break;
-  }
-  auto launch_fused = [&]() {
-    const int64_t total = (int64_t)B * G.tiles_inst;
-    const int g = (int)(total < P.grid_iter ? total : P.grid_iter);
-    switch (G.K) {
-      case 1: k_mf_iter_fused<1, 2><<<g, kMfThreads, 0, s>>>(P.G, P.in, P.st, ctl, B, check_every); break;
-      case 2: k_mf_iter_fused<2, 2><<<g, kMfThreads, 0, s>>>(P.G, P.in, P.st, ctl, B, check_every); break;
-      default: k_mf_iter_fused<4, 1><<<g, kMfThreads, 0, s>>>(P.G, P.in, P.st, ctl, B, check_every); break;
-    }
-    NEPTUNE_COUNT(1);
-  };
-  // small vectors: one block per instance does POST + PREC + Y2 in one launch while F*N is small; larger
-  // instances spread over several blocks and take the C2 dual in a second launch
-  P.fused = G.C <= 4096;
-  P.small_blocks = P.fused ? 1 : (int)((G.C + 255) / 256 < 8 * kNumSMs ? (G.C + 255) / 256 : 8 * kNumSMs);   // one item per thread: the sums are latency-bound
-
-  const size_t cb = (size_t)B * G.cols * 8, rb = (size_t)B * G.rows * 8;
-  NEPTUNE_CUDA_OK(cudaMemsetAsync(ctl, 0, (size_t)B * sizeof(Ctl), s));
-  NEPTUNE_CUDA_OK(cudaMemsetAsync(d_flag, 0, 8, s));
-  const int nblk = G.tiles_inst < kMfRestartBlocks ? G.tiles_inst : kMfRestartBlocks;
-  { k_mf_wsum<<<(int)(((int64_t)B * F * 32 + 255) / 256), 256, 0, s>>>(N, (int64_t)B * F, w, P.st.wsum); NEPTUNE_COUNT(1); }
-  { k_mf_setup<<<dim3(nblk, B), 256, 0, s>>>(G, P.in, P.st, nblk); NEPTUNE_COUNT(1); }
-  { k_mf_setup_norms<<<(B + 127) / 128, 128, 0, s>>>(G, P.in, P.st, ctl, B, nblk); NEPTUNE_COUNT(1); }
-  { k_ctl_init<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, 0.99); NEPTUNE_COUNT(1); }
-  NEPTUNE_CUDA_OK(cudaMemsetAsync(P.st.xsum, 0, cb, s));
-  NEPTUNE_CUDA_OK(cudaMemsetAsync(P.st.ysum, 0, rb, s));
-  NEPTUNE_CUDA_OK(cudaMemcpyAsync(xres, x, cb, cudaMemcpyDeviceToDevice, s));
-  NEPTUNE_CUDA_OK(cudaMemcpyAsync(yres, y, rb, cudaMemcpyDeviceToDevice, s));
-  mf_launch_eval(P, 0, 1);                      // PS <- column sums of the starting yS
-  NEPTUNE_LAUNCH_OK();
-
-  // `inner` iterations = {small(POST unless first of the chunk, PREC, Y2); pass} captured once and replayed;
-  // the chunk ends with small(POST).  Step sizes, restart flags and convergence live in device memory.
-  const int inner = check_every < 32 ? check_every : 32;
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t gexec = nullptr;
-  int64_t per_graph = 0;
-  {
-    int64_t c0 = 0, c1 = 0;
-    neptune_launch_count(&c0, 0);
-    NEPTUNE_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    for (int k = 0; k < inner; ++k) {
-      launch_fused();
-    }
-    NEPTUNE_CUDA_OK(cudaStreamEndCapture(s, &graph));
-    NEPTUNE_CUDA_OK(cudaGraphInstantiate(&gexec, graph, 0));
-    neptune_launch_count(&c1, 0);
-    per_graph = c1 - c0;
-    NEPTUNE_COUNT(-per_graph);
-  }
-  int h_flag = 0;
-  for (int it = 0; it < max_iters && !h_flag; it += check_every) {
-    int done = 0;
-    mf_launch_small(P, PH_PREC | PH_Y2, nullptr);          // c columns and C2 dual of the chunk's first iteration
-    for (; done + inner <= check_every; done += inner) {
-      NEPTUNE_CUDA_OK(cudaGraphLaunch(gexec, s));
-      NEPTUNE_COUNT(per_graph);
-    }
-    for (; done < check_every; ++done) launch_fused();      // the last block of each instance does POST (+ PREC, Y2)
-    { k_ctl_advance<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, check_every); NEPTUNE_COUNT(1); }
-    // KKT of the current iterate and of the running average
-    for (int wch = 0; wch < 2; ++wch) {
-      mf_launch_eval(P, wch, 0);
-      { k_mf_eval_small<<<B, 256, 0, s>>>(G, P.in, P.st, ctl, wch); NEPTUNE_COUNT(1); }
-    }
-    { k_ctl_decide<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, check_every, prm->eps_abs, prm->eps_rel, max_iters,
-                                                 result_d); NEPTUNE_COUNT(1); }
-    { k_mf_apply_restart<<<dim3(kMfRestartBlocks, B), 256, 0, s>>>(G, P.in, P.st, xres, yres, ctl, part); NEPTUNE_COUNT(1); }
-    { k_mf_restart_norms<<<(B + 127) / 128, 128, 0, s>>>(B, kMfRestartBlocks, part, ctl); NEPTUNE_COUNT(1); }
-    { k_ctl_after_restart<<<(B + 127) / 128, 128, 0, s>>>(B, ctl); NEPTUNE_COUNT(1); }
-    mf_launch_eval(P, 0, 1);                    // PS of the (possibly replaced) yS for the next PREC
-    { k_all_done<<<1, 1, 0, s>>>(B, ctl, d_flag); NEPTUNE_COUNT(1); }
-    NEPTUNE_CUDA_OK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, s));
-    NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
-  }
-  cudaGraphExecDestroy(gexec);
-  cudaGraphDestroy(graph);
-  NEPTUNE_LAUNCH_OK();
-  NEPTUNE_CUDA_OK(cudaEventRecord(ev_out, s));
-  NEPTUNE_CUDA_OK(cudaStreamWaitEvent(caller, ev_out, 0));
-  NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
-  cudaEventDestroy(ev_in); cudaEventDestroy(ev_out);
-  cudaStreamDestroy(s);
-  return 0;
-}
-
 
 extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double* d, const double* w,
                                      const double* r, const double* m, const double* Mj, const double* Kj,
@@ -1996,10 +925,6 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
   { int rc = neptune_pdhg_mf_workspace_bytes(B, N, F, &need); if (rc) return rc; }
   if (workspace_bytes < need) return NEPTUNE_E_NOMEM;
   if ((int64_t)B * make_geo(N, F, B).tiles_inst >= (int64_t)INT32_MAX) return NEPTUNE_E_SIZE;
-  if ((prm->reserved & 0x2000) && (int64_t)N * F <= 4096)   // experimental fused pass (not yet run on a GPU); larger
-                                                             // instances would serialise their small vectors in one block
-    return mf_solve_fused(B, N, F, kind, d, w, r, m, Mj, Kj, prm, x, y, result_d, workspace, workspace_bytes, stream);
-
   cudaStream_t caller = (cudaStream_t)stream;
   cudaStream_t s = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -2026,86 +951,8 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
               (double*)(base + W.P1), (double*)(base + W.P4), (double*)(base + W.PS), (double*)(base + W.P3),
               (double*)(base + W.P3i),
               (double*)(base + W.S4), (double*)(base + W.S2), (double*)(base + W.wsum), (double*)(base + W.scal)};
-  // register pass variant: 16-byte accesses (k_mf_iter_vec) are opt-in (reserved bit 11; even N > 32, aligned
-  // vectors) -- measured equal or slower than the 8-byte pass on B200 (profiles/r01f_summary.md); rows in flight
-  // per warp: reserved bits 8..10 override (tools), default by K
-  P.vec = (prm->reserved & 0x800) && !(N & 1) && G.K >= 2 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
-  P.rows_in_flight = (prm->reserved >> 8) & 7;
-  P.async_copy = (prm->reserved & 0x1000) && !(N & 1) && G.K >= 2 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
-  if (P.async_copy) {
-    P.vec = 0;
-    int occ = 0;
-    if (G.K == 2) {
-      NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_mf_iter_async<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)async_smem_bytes<1>()));
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mf_iter_async<1>, kMfThreads, async_smem_bytes<1>());
-    } else {
-      NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_mf_iter_async<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)async_smem_bytes<2>()));
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mf_iter_async<2>, kMfThreads, async_smem_bytes<2>());
-    }
-    P.grid_iter = kNumSMs * (occ < 1 ? 1 : occ);
-  } else if (P.vec) {
-    if (G.K == 2 && P.rows_in_flight != 2 && P.rows_in_flight != 4) P.rows_in_flight = 2;
-    if (G.K == 4 && P.rows_in_flight != 1 && P.rows_in_flight != 2) P.rows_in_flight = 1;
-    switch (G.K * 10 + P.rows_in_flight) {
-      case 22: P.grid_iter = mf_grid(k_mf_iter_vec<1, 2>); break;
-      case 24: P.grid_iter = mf_grid(k_mf_iter_vec<1, 4>); break;
-      case 41: P.grid_iter = mf_grid(k_mf_iter_vec<2, 1>); break;
-      default: P.grid_iter = mf_grid(k_mf_iter_vec<2, 2>); break;
-    }
-  } else {
-    if (P.rows_in_flight != 1 && P.rows_in_flight != 2 && !(P.rows_in_flight == 4 && G.K == 1))
-      P.rows_in_flight = G.K == 4 ? 1 : 2;
-    switch (G.K * 10 + P.rows_in_flight) {
-      case 11: P.grid_iter = mf_grid(k_mf_iter<1, 1>); break;
-      case 12: P.grid_iter = mf_grid(k_mf_iter<1, 2>); break;
-      case 14: P.grid_iter = mf_grid(k_mf_iter<1, 4>); break;
-      case 21: P.grid_iter = mf_grid(k_mf_iter<2, 1>); break;
-      case 22: P.grid_iter = mf_grid(k_mf_iter<2, 2>); break;
-      case 41: P.grid_iter = mf_grid(k_mf_iter<4, 1>); break;
-      default: P.grid_iter = mf_grid(k_mf_iter<4, 2>); break;
-    }
-  }
-  // pair version (reserved bit 15): even N > 32 and 16-byte aligned vectors
-  P.pair = (prm->reserved & 0x8000) && !(N & 1) && G.K >= 2 && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)d) & 15) == 0 &&
-           !P.async_copy && !P.vec;
-  if (P.pair) {
-    if (P.rows_in_flight != 1 && P.rows_in_flight != 2) P.rows_in_flight = G.K == 4 ? 1 : 2;
-    switch (G.K * 10 + P.rows_in_flight) {
-      case 21: P.grid_iter = mf_grid(k_mf_iter2<1, 1>); break;
-      case 22: P.grid_iter = mf_grid(k_mf_iter2<1, 2>); break;
-      case 41: P.grid_iter = mf_grid(k_mf_iter2<2, 1>); break;
-      default: P.grid_iter = mf_grid(k_mf_iter2<2, 2>); break;
-    }
-  }
-  P.lean = (prm->reserved & 0x4000) && !P.async_copy && !P.vec && !P.pair;        // experimental pointer-bumped register pass
-  if (P.lean) {
-    switch (G.K) {
-      case 1: P.grid_iter = mf_grid(k_mf_iter_lean<1, 2>); break;
-      case 2: P.grid_iter = mf_grid(k_mf_iter_lean<2, 2>); break;
-      default: P.grid_iter = mf_grid(k_mf_iter_lean<4, 1>); break;
-    }
-  }
-  switch (G.K) {
-    case 1: P.grid_eval = mf_grid(k_mf_eval<1>); break;
-    case 2: P.grid_eval = mf_grid(k_mf_eval<2>); break;
-    default: P.grid_eval = mf_grid(k_mf_eval<4>); break;
-  }
-  // bulk-copy-staged iteration pass: opt-in (bit 0 of params->reserved) where every tile is 16-byte aligned
-  // (even N, aligned vectors); measured slower than the register pass on B200 at every BASELINE shape
-  P.use_tma = 0;
   P.diag = (prm->reserved >> 4) & 7;
-  if ((prm->reserved & 1) && tma_geo(G, P.T) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
-    if (P.T.CPT == 3) P.T.CPT = 4;
-    cudaError_t e;
-    switch (P.T.CPT) {
-      case 1: e = cudaFuncSetAttribute(k_mf_iter_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes); break;
-      case 2: e = cudaFuncSetAttribute(k_mf_iter_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes); break;
-      default: e = cudaFuncSetAttribute(k_mf_iter_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes); break;
-    }
-    NEPTUNE_CUDA_OK(e);
-    P.use_tma = 1;
-    P.G.cti = P.T.cts;
-  }
+  mf_choose_pass(P, prm->reserved, x, y, d);
   // small vectors: one block per instance does POST + PREC + Y2 in one launch while F*N is small; larger
   // instances spread over several blocks and take the C2 dual in a second launch
   P.fused = G.C <= 4096;
@@ -2331,17 +1178,7 @@ static int mf_step_plan(MfPlan& P, int B, int N, int F, const double* d, const d
   P.st = MfSt{x, y, xsum, ysum, (double*)(base + W.cbar), (double*)(base + W.P1), (double*)(base + W.P4),
               (double*)(base + W.PS), nullptr, (double*)(base + W.P3i), const_cast<double*>(S4),
               const_cast<double*>(S2), nullptr, nullptr};
-  P.rows_in_flight = P.G.K == 4 ? 1 : 2;
-  switch (P.G.K * 10 + P.rows_in_flight) {
-    case 12: P.grid_iter = mf_grid(k_mf_iter<1, 2>); break;
-    case 22: P.grid_iter = mf_grid(k_mf_iter<2, 2>); break;
-    default: P.grid_iter = mf_grid(k_mf_iter<4, 1>); break;
-  }
-  switch (P.G.K) {
-    case 1: P.grid_eval = mf_grid(k_mf_eval<1>); break;
-    case 2: P.grid_eval = mf_grid(k_mf_eval<2>); break;
-    default: P.grid_eval = mf_grid(k_mf_eval<4>); break;
-  }
+  mf_choose_pass(P, 0, x, y, d);
   P.small_blocks = (int)((P.G.C + 255) / 256 < 4 * kNumSMs ? (P.G.C + 255) / 256 : 4 * kNumSMs);
   return 0;
 }

@@ -211,7 +211,7 @@ def pdhg_solve(mdl: Model, max_iters=20000, check_every=64, eps_rel=1e-6, eps_ab
 
 def pdhg_mf_solve(inst: InstanceBatch, max_iters=20000, check_every=64, eps_rel=1e-6, eps_abs=1e-8,
                   x0: Optional[torch.Tensor] = None, y0: Optional[torch.Tensor] = None, workspace=None,
-                  bulk_copy_kernel=False, rows_in_flight=0, vector_kernel=False, async_kernel=False, fused_kernel=False, lean_kernel=False, pair_kernel=False, _diag=0):
+                  scalar_kernel=False, rows_in_flight=0, _diag=0):
     """Matrix-free PDHG on the strengthened min-delay relaxation (`neptune_pdhg_mf_solve`): nothing is
     assembled, every coefficient is regenerated from the instance arrays.  Returns (x[B,cols], y[B,rows],
     results) in the canonical layout of `assemble(inst, "min_delay", flags=FLAG_STRENGTHEN)`."""
@@ -227,11 +227,9 @@ def pdhg_mf_solve(inst: InstanceBatch, max_iters=20000, check_every=64, eps_rel=
     if workspace is None or workspace.numel() < need.value:
         workspace = torch.empty(need.value, dtype=torch.uint8, device=dev)
     res = torch.zeros(inst.B * _PDHG_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    # reserved: bit 0 = bulk-copy-staged iteration pass (opt-in), bits 4..6 = tool diagnostics, bits 8..10 =
-    # rows in flight per warp of the register pass (0 = default), bit 11 = 16-byte accesses (opt-in, even N > 32), bit 12 =
-    # cp.async-prefetched pass, bit 13 = small vectors folded into the pass, bit 14 = pointer-bumped register pass (all three
-    # EXPERIMENTAL: not yet run on a GPU, see csrc/pdhg_mf.cu)
-    prm = PdhgParams(max_iters, check_every, 0, (1 if bulk_copy_kernel else 0) | (_diag << 4) | (rows_in_flight << 8) | (0x800 if vector_kernel else 0) | (0x1000 if async_kernel else 0) | (0x2000 if fused_kernel else 0) | (0x4000 if lean_kernel else 0) | (0x8000 if pair_kernel else 0),
+    # reserved (tools and tests): bit 0 = force the 8-byte iteration pass, bits 4..6 = tool diagnostics,
+    # bits 8..10 = rows of a warp in flight (0 = default)
+    prm = PdhgParams(max_iters, check_every, 0, (1 if scalar_kernel else 0) | (_diag << 4) | (rows_in_flight << 8),
                      eps_rel, eps_abs)
     check(lib.neptune_pdhg_mf_solve(inst.B, inst.N, inst.F, 0, _ptr(inst.d), _ptr(inst.w), _ptr(inst.r),
                                     _ptr(inst.m), _ptr(inst.Mj), _ptr(inst.Kj), C.byref(prm), _ptr(x), _ptr(y),

@@ -56,23 +56,20 @@ def test_no_cpu_fallback_without_gpu():
 
 
 def test_matrix_free_tile_geometry_covers_every_shape():
-    """host arithmetic only: the tiles of the matrix-free passes cover N x N exactly once, the bulk-copy pass is
-    offered only where every tile is 16-byte aligned and fits its shared-memory stage, workspaces hold the state"""
+    """host arithmetic only: the tiles of the matrix-free passes cover N x N exactly once (even N > 32: pairs of
+    adjacent columns, two columns per lane; odd wide N: four strided columns), workspaces hold the state"""
     lib = _lib.load()
     out = (ctypes.c_int32 * 16)()
     need = ctypes.c_int64()
     for (B, N, F) in [(1, 3, 2), (256, 50, 10), (4096, 20, 5), (1, 33, 3), (2, 64, 3), (1, 65, 1), (1, 500, 50), (1, 2000, 25),
-                      (1, 2000, 200), (3, 1026, 2), (1, 130, 2)]:
+                      (1, 2000, 200), (3, 1026, 2), (1, 130, 2), (1, 131, 2)]:
         assert lib.neptune_pdhg_mf_geometry(B, N, F, out) == 0
-        K, JT, ct, RT, rt, tiles, single, _, tma, JS, cts, RS, G, CPT, supers, _ = list(out)
+        K, JT, ct, RT, rt, tiles, single = list(out)[:7]
         assert JT == 32 * K and K in (1, 2, 4) and (K == 1) == (N <= 32)
+        assert K == (1 if N <= 32 else 2 if (N % 2 == 0 or N <= 64) else 4)
         assert (ct - 1) * JT < N <= ct * JT and (rt - 1) * RT < N <= rt * RT and 1 <= RT <= 64
         assert tiles == F * rt * ct and single == (F * N <= 4096)
-        assert tma == (N % 2 == 0)
-        if tma:
-            assert JS % 2 == 0 and (cts - 1) * JS < N <= cts * JS and RS >= 1 and RS * min(JS, N) <= 1024
-            assert (cts == 1 or RS == 1) and CPT in (1, 2, 4) and supers == F * rt * cts
-            assert G >= 1 and (G * JS <= 256 if JS <= 256 else (G == 1 and CPT * 256 >= JS))
+        assert list(out)[8:] == [0] * 8
         assert lib.neptune_pdhg_mf_workspace_bytes(B, N, F, ctypes.byref(need)) == 0
         X, C = F * N * N, F * N
         assert need.value >= 8 * B * (2 * (X + C) + 2 * (3 * C + 2 * N + X))        # xsum, xres, ysum, yres at least

@@ -2,7 +2,6 @@
 (tests/mf_reference.py, proven equal to the CSR iteration on the oracle's matrix in tests/test_mf_reference.py),
 agree with the CSR solver on the assembled matrix, and reach the HiGHS LP optimum."""
 import ctypes
-import os
 
 import numpy as np
 import pytest
@@ -34,7 +33,7 @@ def _close(got, want, tol):
 
 
 @pytest.mark.parametrize("name,make,iters", CASES, ids=[c[0] for c in CASES])
-@pytest.mark.parametrize("variant", ["register-pass", "bulk-copy-pass", "16-byte-pass"])
+@pytest.mark.parametrize("variant", ["default-pass", "8-byte-pass"])
 def test_iterates_equal_the_numpy_reference(name, make, iters, variant):
     """After `iters` iterations (no restart inside) the returned candidate -- current iterate or running
     average, whichever has the smaller KKT error -- equals the reference's.  Tolerance 1e-9 relative to the
@@ -43,8 +42,7 @@ def test_iterates_equal_the_numpy_reference(name, make, iters, variant):
     payloads = [make(s) for s in range(2)]
     inst = cuda_batch(payloads)
     x, y, res = device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-13, eps_abs=1e-15,
-                                     bulk_copy_kernel=variant == "bulk-copy-pass",
-                                     vector_kernel=variant == "16-byte-pass")
+                                     scalar_kernel=variant == "8-byte-pass")
     for b, p in enumerate(payloads):
         xr, yr, info = run_fixed(arrays_of(p), iters)
         assert _close(x[b].cpu().numpy(), xr, 1e-9), (name, b)
@@ -57,20 +55,19 @@ def test_iterates_equal_the_numpy_reference(name, make, iters, variant):
         assert np.all(y[b].cpu().numpy()[0:2 * inst.F * inst.N:2] == 0.0)      # free C1a rows
 
 
-@pytest.mark.parametrize("shape", [(130, 2), (300, 2), (64, 3)])
-def test_bulk_copy_and_16_byte_passes_equal_the_register_pass(shape):
-    """wider shapes (2 and 4 columns per thread of the bulk-copy pass; several row tiles): the iteration kernels
-    are the same arithmetic in a different order"""
+@pytest.mark.parametrize("shape", [(34, 3), (50, 4), (64, 3), (130, 2), (300, 2)])
+def test_pair_pass_equals_the_8_byte_pass(shape):
+    """even N in 33..64 runs the pair pass (16-byte accesses, reciprocal by Newton steps) by default: same
+    arithmetic as the 8-byte pass up to the last bits of 1/(3 + w r); wider shapes take the 8-byte pass either way;
+    one and two rows of a warp in flight"""
     from neptune_mip_b200 import device
-    inst = cuda_batch([synth.random_payload(shape[0], shape[1], 1, node_cores=60)])
-    xa, ya, ra = device.pdhg_mf_solve(inst, max_iters=33, check_every=33, eps_rel=1e-13, eps_abs=1e-15)
-    xb, yb, rb = device.pdhg_mf_solve(inst, max_iters=33, check_every=33, eps_rel=1e-13, eps_abs=1e-15, bulk_copy_kernel=True)
-    assert _close(xb.cpu().numpy(), xa.cpu().numpy(), 1e-11) and _close(yb.cpu().numpy(), ya.cpu().numpy(), 1e-11)
-    assert abs(ra[0]["primal_obj"] - rb[0]["primal_obj"]) <= 1e-11 * (1 + abs(ra[0]["primal_obj"]))
-    for u in (1, 2):
-        xc, yc, rc = device.pdhg_mf_solve(inst, max_iters=33, check_every=33, eps_rel=1e-13, eps_abs=1e-15, vector_kernel=True,
-                                          rows_in_flight=u)
-        assert _close(xc.cpu().numpy(), xa.cpu().numpy(), 1e-11) and _close(yc.cpu().numpy(), ya.cpu().numpy(), 1e-11)
+    inst = cuda_batch([synth.random_payload(shape[0], shape[1], s, node_cores=60) for s in range(2)])
+    kw = dict(max_iters=33, check_every=33, eps_rel=1e-13, eps_abs=1e-15)
+    xa, ya, ra = device.pdhg_mf_solve(inst, scalar_kernel=True, **kw)
+    for u in (0, 1, 2):
+        xb, yb, rb = device.pdhg_mf_solve(inst, rows_in_flight=u, **kw)
+        assert _close(xb.cpu().numpy(), xa.cpu().numpy(), 1e-11) and _close(yb.cpu().numpy(), ya.cpu().numpy(), 1e-11)
+        assert np.allclose(ra["primal_obj"], rb["primal_obj"], rtol=1e-11)
 
 
 def test_agrees_with_the_csr_solver_on_the_assembled_matrix():
@@ -143,47 +140,3 @@ def test_other_model_kinds_are_refused():
         assert lib.neptune_pdhg_mf_solve(1, 8, 4, kind, *args, ws.numel(), None) == -1
     assert lib.neptune_pdhg_mf_solve(1, 8, 4, 0, *args, 16, None) == -3          # workspace too small
     assert lib.neptune_pdhg_mf_solve(1, 8, 4, 0, *args, ws.numel(), None) == 0
-
-
-@pytest.mark.skipif(not os.environ.get("NEPTUNE_EXPERIMENTAL"), reason="cp.async-prefetched pass: written after the round's GPU budget "
-                    "was spent; run with NEPTUNE_EXPERIMENTAL=1 on a B200 before making it selectable by default")
-@pytest.mark.parametrize("shape,iters", [((50, 10), 64), ((64, 3), 40), ((70, 3), 64), ((130, 2), 33), ((300, 2), 33)])
-def test_experimental_async_pass_equals_register_pass(shape, iters):
-    from neptune_mip_b200 import device
-    inst = cuda_batch([synth.random_payload(shape[0], shape[1], s, node_cores=60) for s in range(2)])
-    kw = dict(max_iters=iters, check_every=iters, eps_rel=1e-13, eps_abs=1e-15)
-    xa, ya, ra = device.pdhg_mf_solve(inst, **kw)
-    xb, yb, rb = device.pdhg_mf_solve(inst, async_kernel=True, **kw)
-    assert _close(xb.cpu().numpy(), xa.cpu().numpy(), 1e-11) and _close(yb.cpu().numpy(), ya.cpu().numpy(), 1e-11)
-    assert np.allclose(ra["primal_obj"], rb["primal_obj"], rtol=1e-11)
-
-
-@pytest.mark.skipif(not os.environ.get("NEPTUNE_EXPERIMENTAL"), reason="fused pass (small vectors folded into the last-finishing block): "
-                    "written after the round's GPU budget was spent; run with NEPTUNE_EXPERIMENTAL=1 on a B200 first")
-@pytest.mark.parametrize("shape,iters", [((3, 2), 64), ((12, 5), 96), ((20, 5), 40), ((50, 10), 64), ((70, 3), 33), ((130, 2), 33)])
-def test_experimental_fused_pass_equals_two_kernel_iteration(shape, iters):
-    """same arithmetic and summation order as k_mf_iter + k_mf_small: bitwise equal results are expected"""
-    from neptune_mip_b200 import device
-    inst = cuda_batch([synth.random_payload(shape[0], shape[1], s, node_cores=60) for s in range(3)])
-    kw = dict(max_iters=iters, check_every=iters, eps_rel=1e-13, eps_abs=1e-15)
-    xa, ya, ra = device.pdhg_mf_solve(inst, **kw)
-    xb, yb, rb = device.pdhg_mf_solve(inst, fused_kernel=True, **kw)
-    assert _close(xb.cpu().numpy(), xa.cpu().numpy(), 1e-12) and _close(yb.cpu().numpy(), ya.cpu().numpy(), 1e-12)
-    # and a restarted solve takes the same decisions
-    kw = dict(max_iters=20000, check_every=128, eps_rel=1e-6, eps_abs=1e-9)
-    _, _, r1 = device.pdhg_mf_solve(inst, **kw)
-    _, _, r2 = device.pdhg_mf_solve(inst, fused_kernel=True, **kw)
-    assert r1["iters"].tolist() == r2["iters"].tolist() and np.allclose(r1["primal_obj"], r2["primal_obj"], rtol=1e-10)
-
-
-@pytest.mark.skipif(not os.environ.get("NEPTUNE_EXPERIMENTAL"), reason="pointer-bumped register pass: written after the round's GPU "
-                    "budget was spent; run with NEPTUNE_EXPERIMENTAL=1 on a B200 first")
-@pytest.mark.parametrize("shape,iters", [((3, 2), 64), ((20, 5), 40), ((33, 3), 33), ((50, 10), 64), ((70, 3), 64), ((130, 2), 33)])
-def test_experimental_lean_pass_equals_register_pass(shape, iters):
-    """same arithmetic and summation order as k_mf_iter<K, U> with U = default: bitwise equal results are expected"""
-    from neptune_mip_b200 import device
-    inst = cuda_batch([synth.random_payload(shape[0], shape[1], s, node_cores=60) for s in range(2)])
-    kw = dict(max_iters=iters, check_every=iters, eps_rel=1e-13, eps_abs=1e-15)
-    xa, ya, _ = device.pdhg_mf_solve(inst, **kw)
-    xb, yb, _ = device.pdhg_mf_solve(inst, lean_kernel=True, **kw)
-    assert _close(xb.cpu().numpy(), xa.cpu().numpy(), 1e-12) and _close(yb.cpu().numpy(), ya.cpu().numpy(), 1e-12)
