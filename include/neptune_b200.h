@@ -294,11 +294,13 @@ int neptune_route_lp_workspace_bytes(int B, int P, int N, int F, int64_t tableau
  * the priced nearest-pod cost, node prices on the CPU rows kept at their coordinate-wise dual optimum, annealed
  * cost perturbation of relative size `noise_coef` (csrc/lns.cu).  Chains start from randomised roundings of
  * guide[B][F][N] (c-bar of the LP relaxation) and lam0[B][N] (its CPU-row duals), and/or from
- * seeds[B][S][F][N]; any of the three may be NULL (no guide: every chain starts from a seed).  Returns every
- * chain's record: out_c[B][chains][F][N], out_g[B][chains] = objective of the record with every source routed
- * whole to its nearest priced pod (feasible, so an UPPER bound of the record's true objective; +inf = none),
- * out_lb[B][chains] (optional) = the priced objective at the record (a lower bound), out_round[B][chains].
- * Price the records exactly with neptune_route_lp. */
+ * seeds[B][S][F][N]; any of the three may be NULL (no guide: every chain starts from a seed).  Every chain returns
+ * two records (2*chains per instance): entries [0, chains) are the chains' best placements by the objective with
+ * every source routed WHOLE to its nearest priced pod (feasible, so an upper bound of the placement's true
+ * objective), entries [chains, 2*chains) the best by the priced objective (a lower bound; equal to the routing LP
+ * where the prices are optimal, i.e. where the optimum splits flows).  out_c[B][2*chains][F][N], out_g[B][2*chains]
+ * (the bound the record was chosen by; +inf = none), out_lb[B][2*chains] (optional: the other end of the bracket),
+ * out_round[B][2*chains].  Price the records exactly with neptune_route_lp. */
 int neptune_lns_search(int B, int N, int F, int kind, double alpha, int chains, int rounds, int k,
                        double noise_coef, uint64_t rng_seed,
                        const double* d, const double* w, const double* r, const double* m,

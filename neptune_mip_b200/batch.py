@@ -31,6 +31,7 @@ class BatchParams:
     lns_phases: int = 1           # > 1: population restarts from the best records between phases (lns_rounds is the total)
     lns_cooling: float = 0.6      # temperature factor from one phase to the next
     lns_restart_pool: int = 16    # records a restart phase draws its start placements from
+    lns_local_chains: int = 0     # > 0: the add/drop/swap search, restarted from the best records, adds one candidate
     elites: int = 16              # chain records priced exactly (routing LP) per instance
 
 
@@ -150,25 +151,42 @@ def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0,
     # far (population restarts: "go with the winners") at a lower temperature
     phases = max(1, prm.lns_phases)
     rounds = max(1, prm.lns_rounds // phases)
-    out_c = out_g = out_round = None
+    ub_c = ub_g = ub_r = lb_c = lb_g = lb_r = None            # records by upper bound / by lower bound, all phases
+    C_ = prm.lns_chains
     for ph in range(phases):
         noise = prm.lns_noise * (prm.lns_cooling ** ph)
         if ph == 0:
-            pc, pg, pr_ = device.lns_search(inst, kind, prm.alpha, prm.lns_chains, rounds, prm.lns_k, noise,
+            pc, pg, pr_ = device.lns_search(inst, kind, prm.alpha, C_, rounds, prm.lns_k, noise,
                                             prm.rng_seed, guide, lam0, seeds)
         else:
-            S = min(prm.lns_restart_pool, out_g.shape[1])
-            _, top = torch.topk(out_g, S, dim=1, largest=False)
-            pool = torch.gather(out_c, 1, top[:, :, None, None].expand(B, S, F, N)).contiguous()
-            pc, pg, pr_ = device.lns_search(inst, kind, prm.alpha, prm.lns_chains, rounds, prm.lns_k, noise,
+            S = min(prm.lns_restart_pool, ub_g.shape[1])
+            _, top = torch.topk(ub_g, S, dim=1, largest=False)
+            pool = torch.gather(ub_c, 1, top[:, :, None, None].expand(B, S, F, N)).contiguous()
+            pc, pg, pr_ = device.lns_search(inst, kind, prm.alpha, C_, rounds, prm.lns_k, noise,
                                             prm.rng_seed + 7919 * ph, None, lam0, pool)
             pr_ = pr_ + ph * rounds
-        out_c = pc if out_c is None else torch.cat([out_c, pc], dim=1)
-        out_g = pg if out_g is None else torch.cat([out_g, pg], dim=1)
-        out_round = pr_ if out_round is None else torch.cat([out_round, pr_], dim=1)
-    E = max(1, min(prm.elites, out_g.shape[1]))
-    _, idx = torch.topk(out_g, E, dim=1, largest=False)                       # lowest priced objective first
+        cat = lambda a_, b_: b_ if a_ is None else torch.cat([a_, b_], dim=1)          # noqa: E731
+        ub_c, ub_g, ub_r = cat(ub_c, pc[:, :C_]), cat(ub_g, pg[:, :C_]), cat(ub_r, pr_[:, :C_])
+        lb_c, lb_g, lb_r = cat(lb_c, pc[:, C_:]), cat(lb_g, pg[:, C_:]), cat(lb_r, pr_[:, C_:])
+    # elites: the best records of either kind, half each (a lower and an upper bound do not rank against each other)
+    Eh = max(1, min(prm.elites // 2, ub_g.shape[1]))
+    _, iu = torch.topk(ub_g, Eh, dim=1, largest=False)
+    _, il = torch.topk(lb_g, Eh, dim=1, largest=False)
+    out_c = torch.cat([ub_c, lb_c], dim=1)
+    out_g = torch.cat([ub_g, lb_g], dim=1)
+    out_round = torch.cat([ub_r, lb_r], dim=1)
+    idx = torch.cat([iu, il + ub_g.shape[1]], dim=1)
+    E = idx.shape[1]
     elite = torch.gather(out_c, 1, idx[:, :, None, None].expand(B, E, F, N)).contiguous()
+    if prm.lns_local_chains > 0:
+        # one more candidate from the add/drop/swap search (it prices overload by a penalty instead of node prices and
+        # does better where most CPU rows bind); restarted from the best records
+        pool = torch.cat([elite[:, :2], elite[:, Eh:Eh + 2], seeds], dim=1).contiguous()
+        lc, lobj, _ = device.local_search(inst, kind, pool, prm.alpha, prm.lns_local_chains, prm.sweeps, prm.rng_seed, None)
+        lc = torch.where(torch.isfinite(lobj)[:, None, None], lc, elite[:, 0])
+        elite = torch.cat([elite, lc[:, None]], dim=1).contiguous()
+        idx = torch.cat([idx, idx[:, :1]], dim=1)
+        E += 1
     pr = device.route_lp(inst, elite)
     a_d, a_u = objective_weights(inst, kind, prm.alpha)
     val = a_d[:, None] * pr["obj"] + a_u[:, None] * pr["n"].sum(dim=-1)
@@ -201,6 +219,6 @@ def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0,
         e1.record()
         e1.synchronize()
         ms = e0.elapsed_time(e1)
-    diag = dict(elite_g=torch.gather(out_g, 1, idx), elite_val=val, pivots=pr["info"][..., 0], status=pr["status"],
+    diag = dict(elite_g=torch.gather(out_g, 1, idx), elite_val=val, n_upper=Eh, pivots=pr["info"][..., 0], status=pr["status"],
                 fell_back=(flags != OK_ALL))
     return best_c, x, n, flags, scores, rnd, ms, diag

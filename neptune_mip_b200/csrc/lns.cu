@@ -35,10 +35,11 @@ struct LnsArgs {
   const double* guide;     // [B][F][N] c-bar of the relaxation, or null
   const double* lam0;      // [B][N] CPU-row duals of the relaxation (delay units), or null
   const uint8_t* seeds;    // [B][S][F][N] or null
-  uint8_t* out_c;          // [B][chains][F][N]
-  double* out_g;           // [B][chains] objective of the record's whole-flow routing: an upper bound of its true objective (+inf: none)
-  double* out_lb;          // [B][chains] priced (dual) objective at the record: a lower bound; may be null
-  int32_t* out_round;      // [B][chains] round of the record
+  uint8_t* out_c;          // [B][2*chains][F][N]: per chain one record by the upper bound, one by the lower bound
+  double* out_g;           // [B][2*chains] [0,chains): whole-flow objective of the record (upper bound of its true objective);
+                           //               [chains,2*chains): priced objective (lower bound); +inf: none
+  double* out_lb;          // [B][2*chains] the other end of each record's bracket; may be null
+  int32_t* out_round;      // [B][2*chains] round of the record
 };
 
 constexpr double kLnsBig = 1e9;                 // priced delay of "no pod"
@@ -269,7 +270,10 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
   __syncwarp();
 
   double bestu = INFINITY, bestg = -INFINITY; int best_round = -1;
-  uint8_t* outc = a.out_c + ((int64_t)b * a.chains + chain) * fn;
+  double bestg2 = INFINITY, bestu2 = INFINITY; int best_round2 = -1;
+  // records of an instance: [0, chains) by the whole-flow (upper-bound) objective, [chains, 2 chains) by the priced one
+  uint8_t* outc = a.out_c + ((int64_t)b * 2 * a.chains + chain) * fn;
+  uint8_t* outc2 = a.out_c + ((int64_t)b * 2 * a.chains + a.chains + chain) * fn;
   const int anneal_rounds = a.rounds - a.rounds / 8;
 
   for (int round = 0; round <= a.rounds; ++round) {
@@ -461,6 +465,13 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
         bestu = uval; bestg = g; best_round = round;
         for (int q = lane; q < fn; q += 32) outc[q] = c[q];
       }
+      // second record, by the lower bound: where the optimal routing splits flows, g is the LP value and the whole-flow
+      // value overstates it by sum_j lam_j (K_j - load_j).  Only with settled prices and a small bracket [g, U] (loose
+      // prices make g a mirage); both records are priced exactly by the caller.
+      if (!overloaded && !unserved && settled && uval - g <= 0.01 * fabs(uval) && g < bestg2 - 1e-9 * (1.0 + fabs(g))) {
+        bestg2 = g; bestu2 = uval; best_round2 = round;
+        for (int q = lane; q < fn; q += 32) outc2[q] = c[q];
+      }
     }
     if (round == a.rounds) break;
     if (kk == 0) continue;
@@ -611,11 +622,14 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
     __syncwarp();
   }
   if (lane == 0) {
-    a.out_g[(int64_t)b * a.chains + chain] = bestu < INFINITY ? a_d * bestu : INFINITY;
-    if (a.out_lb) a.out_lb[(int64_t)b * a.chains + chain] = bestu < INFINITY ? a_d * bestg : -INFINITY;
-    a.out_round[(int64_t)b * a.chains + chain] = best_round;
+    const int64_t o = (int64_t)b * 2 * a.chains + chain;
+    a.out_g[o] = bestu < INFINITY ? a_d * bestu : INFINITY;
+    a.out_g[o + a.chains] = bestg2 < INFINITY ? a_d * bestg2 : INFINITY;
+    if (a.out_lb) { a.out_lb[o] = bestu < INFINITY ? a_d * bestg : -INFINITY; a.out_lb[o + a.chains] = bestg2 < INFINITY ? a_d * bestu2 : INFINITY; }
+    a.out_round[o] = best_round; a.out_round[o + a.chains] = best_round2;
   }
   if (best_round < 0) for (int q = lane; q < fn; q += 32) outc[q] = c[q];
+  if (best_round2 < 0) for (int q = lane; q < fn; q += 32) outc2[q] = c[q];
 }
 
 }  // namespace neptune

@@ -398,16 +398,17 @@ def lns_search(inst: InstanceBatch, kind, alpha=0.5, chains=32, rounds=4000, k=3
                guide: Optional[torch.Tensor] = None, lam0: Optional[torch.Tensor] = None,
                seeds_u8: Optional[torch.Tensor] = None):
     """LP-guided k-node re-optimisation search (`neptune_lns_search`).  Returns every chain's record:
-    (c uint8[B,chains,F,N], g float64[B,chains] objective of the record's whole-flow routing (an upper bound of its
-    true objective; +inf: none), round int32[B,chains])."""
+    (c uint8[B,2*chains,F,N], g float64[B,2*chains], round int32[B,2*chains]): entries [:chains] are the chains' best
+    placements by the whole-flow objective (an upper bound of the true objective), entries [chains:] by the priced
+    objective (a lower bound); g is the bound the record was chosen by (+inf: none)."""
     lib = _lib.load()
     kind = KINDS.get(kind, kind)
     dev = inst.d.device
     S = 0 if seeds_u8 is None else seeds_u8.shape[1]
-    out_c = torch.empty((inst.B, chains, inst.F, inst.N), dtype=torch.uint8, device=dev)
-    out_g = torch.empty((inst.B, chains), dtype=torch.float64, device=dev)
-    out_round = torch.empty((inst.B, chains), dtype=torch.int32, device=dev)
-    out_lb = torch.empty((inst.B, chains), dtype=torch.float64, device=dev)
+    out_c = torch.empty((inst.B, 2 * chains, inst.F, inst.N), dtype=torch.uint8, device=dev)
+    out_g = torch.empty((inst.B, 2 * chains), dtype=torch.float64, device=dev)
+    out_round = torch.empty((inst.B, 2 * chains), dtype=torch.int32, device=dev)
+    out_lb = torch.empty((inst.B, 2 * chains), dtype=torch.float64, device=dev)
     check(lib.neptune_lns_search(inst.B, inst.N, inst.F, kind, C.c_double(alpha), chains, rounds, k,
                                  C.c_double(noise_coef), C.c_uint64(rng_seed), _ptr(inst.d), _ptr(inst.w), _ptr(inst.r),
                                  _ptr(inst.m), _ptr(inst.Mj), _ptr(inst.Kj), _ptr(inst.maxd), _ptr(guide), _ptr(lam0),

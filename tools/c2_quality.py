@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--phases", type=int, default=1)
     ap.add_argument("--cooling", type=float, default=0.6)
     ap.add_argument("--pool", type=int, default=16)
+    ap.add_argument("--local", type=int, default=0)
     ap.add_argument("--lp-iters", type=int, default=20000)
     ap.add_argument("--no-cut", action="store_true")
     ap.add_argument("--search", default="auto")
@@ -40,7 +41,7 @@ def main():
     datas = [data_to_solver_input(synth.config_payload(a.config, s), 1, with_db=False) for s in seeds]
     inst = device.InstanceBatch.from_datas(datas)
     prm = BatchParams(lp_iters=a.lp_iters, lp_check_every=256, lns_chains=a.chains, lns_rounds=a.rounds, lns_k=a.k,
-                      lns_noise=a.noise, elites=a.elites, lns_phases=a.phases, lns_cooling=a.cooling, lns_restart_pool=a.pool, lp_cut=not a.no_cut, search=a.search, rng_seed=a.rng,
+                      lns_noise=a.noise, elites=a.elites, lns_phases=a.phases, lns_cooling=a.cooling, lns_restart_pool=a.pool, lns_local_chains=a.local, lp_cut=not a.no_cut, search=a.search, rng_seed=a.rng,
                       chains=16, sweeps=400)
     for rep in range(a.repeat):
         prm.rng_seed = a.rng + rep
@@ -58,8 +59,8 @@ def main():
                           "lp_bound_gap": [float(f"{(gold[s]['objective'] - lp[k]['dual_obj']) / gold[s]['objective']:.2e}") for k, s in enumerate(seeds)] if lp is not None else None,
                           "lp_iters": [int(v) for v in lp["iters"]] if lp is not None else None,
                           "lp_converged": int(lp["converged"].sum()) if lp is not None else None,
-                          "elite_g_minus_opt": [[round(float(v) - gold[s]["objective"], 2) for v in res.lns_diag["elite_g"][k].cpu()[:4]] for k, s in enumerate(seeds)] if res.lns_diag else None,
-                          "elite_val_minus_opt": [[round(float(v) - gold[s]["objective"], 2) for v in res.lns_diag["elite_val"][k].cpu()[:4]] for k, s in enumerate(seeds)] if res.lns_diag else None,
+                          "elite_g_minus_opt": [[round(float(v) - gold[s]["objective"], 2) for v in res.lns_diag["elite_g"][k].cpu()[[0, 1, res.lns_diag["n_upper"], res.lns_diag["n_upper"] + 1]]] for k, s in enumerate(seeds)] if res.lns_diag else None,
+                          "elite_val_minus_opt": [[round(float(v) - gold[s]["objective"], 2) for v in res.lns_diag["elite_val"][k].cpu()] for k, s in enumerate(seeds)] if res.lns_diag else None,
                           "bad": {str(seeds[k]): {"gap": float(f"{gaps[k]:.3g}"), "status": res.lns_diag["status"][k].cpu().tolist()[:8], "fell_back": bool(res.lns_diag["fell_back"][k]),
                                                   "g": [round(float(v), 1) for v in res.lns_diag["elite_g"][k].cpu()[:4]], "opt": gold[seeds[k]]["objective"]}
                                   for k in range(len(seeds)) if gaps[k] > 1e-2} if res.lns_diag else None,
