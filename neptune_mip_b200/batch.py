@@ -166,6 +166,8 @@ def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0,
                                             prm.rng_seed + 7919 * ph, None, lam0, pool)
             pr_ = pr_ + ph * rounds
         cat = lambda a_, b_: b_ if a_ is None else torch.cat([a_, b_], dim=1)          # noqa: E731
+        ob = device.lns_search.last_other_bound
+        lb_u = ob[:, C_:] if ph == 0 else torch.cat([lb_u, ob[:, C_:]], dim=1)
         ub_c, ub_g, ub_r = cat(ub_c, pc[:, :C_]), cat(ub_g, pg[:, :C_]), cat(ub_r, pr_[:, :C_])
         lb_c, lb_g, lb_r = cat(lb_c, pc[:, C_:]), cat(lb_g, pg[:, C_:]), cat(lb_r, pr_[:, C_:])
     # elites: the best records of either kind, half each (a lower and an upper bound do not rank against each other)
@@ -219,6 +221,6 @@ def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0,
         e1.record()
         e1.synchronize()
         ms = e0.elapsed_time(e1)
-    diag = dict(elite_g=torch.gather(out_g, 1, idx), elite_val=val, n_upper=Eh, pivots=pr["info"][..., 0], status=pr["status"],
+    diag = dict(elite_g=torch.gather(out_g, 1, idx), elite_val=val, n_upper=Eh, lb_other=torch.gather(lb_u, 1, il), elite_c=elite, pivots=pr["info"][..., 0], status=pr["status"],
                 fell_back=(flags != OK_ALL))
     return best_c, x, n, flags, scores, rnd, ms, diag

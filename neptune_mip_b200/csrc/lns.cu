@@ -73,7 +73,6 @@ __host__ __device__ inline size_t lns_warp_shared(int N, int F, int k, int smax)
   size_t b = 0;
   b += (size_t)N * 8;               // lam
   b += (size_t)N * 8;               // loadfx
-  b += (size_t)N * 8;               // lastload
   b += fn * 8;                      // bestv
   b += lns_scratch_bytes(N, F, k, smax);
   b += ((size_t)F + 64 + (size_t)F) * 4;   // npods, misc (J, rad, mul, incT), fl
@@ -160,7 +159,6 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
   unsigned char* wp = smem + ((lns_block_shared(N, F) + 15) & ~(size_t)15) + (size_t)wid * lns_warp_shared(N, F, KK, smax);
   double* lam = (double*)wp; wp += (size_t)N * 8;
   unsigned long long* loadfx = (unsigned long long*)wp; wp += (size_t)N * 8;
-  unsigned long long* lastload = (unsigned long long*)wp; wp += (size_t)N * 8;   // load of a priced node when its price was last settled
   double* bestv = (double*)wp; wp += (size_t)fn * 8;
   unsigned char* scratch = wp; wp += lns_scratch_bytes(N, F, KK, smax);
   double* costT = (double*)scratch;                       // [F][NT]
@@ -186,7 +184,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
 
   // ---- start placement -----------------------------------------------------------------------------------
   for (int q = lane; q < fn; q += 32) c[q] = 0;
-  for (int j = lane; j < N; j += 32) { lam[j] = a.lam0 ? fmax(a.lam0[(int64_t)b * N + j], 0.0) : 0.0; lastload[j] = ~0ull; }
+  for (int j = lane; j < N; j += 32) lam[j] = a.lam0 ? fmax(a.lam0[(int64_t)b * N + j], 0.0) : 0.0;
   __syncwarp();
   const bool from_seed = a.seeds && (!a.guide || chain < a.S);
   if (from_seed) {
@@ -332,8 +330,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
     auto inJ = [&](int j) -> bool { return j < 64 ? (jm0 >> j) & 1 : (j < 128 ? (jm1 >> (j - 64)) & 1 : false); };
 
     // ---- CPU loads at the current prices; dual ascent on the prices of overloaded / priced nodes -----------------
-    // A node is (re)priced when it is overloaded, or when it carries a price and its load moved since that price
-    // was settled.  Price of node jj = the threshold at which enough of its flows leave:  a source (f,i) uses jj
+    // A node is (re)priced when it is overloaded or carries a price.  Price of node jj = the threshold at which enough of its flows leave:  a source (f,i) uses jj
     // while  lam_jj < th = (best priced alternative - d[i,jj]) / r[f,jj];  flows leave in ascending th until the
     // rest fits K_jj; ties with the alternative (th = 0) leave first, at a price of 1e-9.
     bool overloaded = false, settled = false;
@@ -360,7 +357,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
         if (j < N) {
           const double ld = (double)loadfx[j] * (1.0 / kFxScale);
           over = ld > s_K[j] + 1e-7;
-          need = over || (lam[j] > 0.0 && loadfx[j] != lastload[j]);
+          need = over || lam[j] > 0.0;      // a price goes stale without its node's load moving (a flow it pushed off found a better pod): re-derive it every round
         }
         unsigned todo = __ballot_sync(0xffffffffu, need);
         overloaded = overloaded || __any_sync(0xffffffffu, over);
@@ -439,8 +436,6 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
       }
       if (!changed) { settled = true; break; }
     }
-    for (int j = lane; j < N; j += 32) lastload[j] = settled && lam[j] > 0.0 ? loadfx[j] : ~0ull;
-    __syncwarp();
     // ---- record ---------------------------------------------------------------------------------------------------
     // With no node overloaded, routing every source WHOLE to its nearest priced pod is a feasible point of the MIP
     // (pods that end up unused are closed, the others serve at least one whole source: C1b holds), so its delay

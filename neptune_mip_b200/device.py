@@ -414,6 +414,7 @@ def lns_search(inst: InstanceBatch, kind, alpha=0.5, chains=32, rounds=4000, k=3
                                  _ptr(inst.m), _ptr(inst.Mj), _ptr(inst.Kj), _ptr(inst.maxd), _ptr(guide), _ptr(lam0),
                                  S, _ptr(seeds_u8), _ptr(out_c), _ptr(out_g), _ptr(out_lb), _ptr(out_round), _stream()),
           "neptune_lns_search")
+    lns_search.last_other_bound = out_lb          # diagnostics (tools): the other end of each record's bracket
     return out_c, out_g, out_round
 
 

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--cooling", type=float, default=0.6)
     ap.add_argument("--pool", type=int, default=16)
     ap.add_argument("--local", type=int, default=0)
+    ap.add_argument("--dump", default="")
     ap.add_argument("--lp-iters", type=int, default=20000)
     ap.add_argument("--no-cut", action="store_true")
     ap.add_argument("--search", default="auto")
@@ -64,8 +65,16 @@ def main():
                           "bad": {str(seeds[k]): {"gap": float(f"{gaps[k]:.3g}"), "status": res.lns_diag["status"][k].cpu().tolist()[:8], "fell_back": bool(res.lns_diag["fell_back"][k]),
                                                   "g": [round(float(v), 1) for v in res.lns_diag["elite_g"][k].cpu()[:4]], "opt": gold[seeds[k]]["objective"]}
                                   for k in range(len(seeds)) if gaps[k] > 1e-2} if res.lns_diag else None,
+                          "lb_records": [[(round(float(res.lns_diag["elite_g"][k, res.lns_diag["n_upper"] + q]) - gold[s]["objective"], 2),
+                                           round(float(res.lns_diag["lb_other"][k, q]) - gold[s]["objective"], 2),
+                                           round(float(res.lns_diag["elite_val"][k, res.lns_diag["n_upper"] + q]) - gold[s]["objective"], 2),
+                                           int(res.lns_diag["pivots"][k, res.lns_diag["n_upper"] + q])) for q in range(3)] for k, s in enumerate(seeds)] if res.lns_diag and len(seeds) <= 16 else None,
                           "rounds_of_best": res.lns_round.cpu().tolist() if res.lns_round is not None else None}))
         sys.stdout.flush()
+        if a.dump and res.lns_diag:
+            np.savez_compressed(os.path.join(ROOT, "gpurun_out", a.dump), elite_c=res.lns_diag["elite_c"].cpu().numpy(),
+                                elite_g=res.lns_diag["elite_g"].cpu().numpy(), elite_val=res.lns_diag["elite_val"].cpu().numpy(),
+                                n_upper=res.lns_diag["n_upper"], seeds=np.array(seeds))
 
 
 if __name__ == "__main__":
