@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
   for (int f = 0; f < F; ++f) scan_function(f);
   __syncwarp();
 
+  uint64_t dirtyF = ~0ull;             // functions whose routing changed since the node prices were last settled
   double bestu = INFINITY, bestg = -INFINITY; int best_round = -1;
   double bestg2 = INFINITY, bestu2 = INFINITY; int best_round2 = -1;
   // records of an instance: [0, chains) by the whole-flow (upper-bound) objective, [chains, 2 chains) by the priced one
@@ -335,6 +336,9 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
     // rest fits K_jj; ties with the alternative (th = 0) leave first, at a price of 1e-9.
     bool overloaded = false, settled = false;
     double ucost = 0.0;
+    // the state of a node depends only on the functions with a pod on it: a price is re-derived when the node is
+    // overloaded, or when one of its functions changed pods (last apply) or was re-routed by another node's new price
+    uint64_t dirty_now = dirtyF;
     for (int pass = 0; pass < 4; ++pass) {
       for (int j = lane; j < N; j += 32) loadfx[j] = 0ull;
       __syncwarp();
@@ -357,7 +361,9 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
         if (j < N) {
           const double ld = (double)loadfx[j] * (1.0 / kFxScale);
           over = ld > s_K[j] + 1e-7;
-          need = over || lam[j] > 0.0;      // a price goes stale without its node's load moving (a flow it pushed off found a better pod): re-derive it every round
+          uint64_t on = 0;
+          if (F <= 64) { for (int f = 0; f < F; ++f) if (c[f * N + j]) on |= 1ull << f; } else on = ~0ull;
+          need = over || (lam[j] > 0.0 && (on & dirty_now) != 0);
         }
         unsigned todo = __ballot_sync(0xffffffffu, need);
         overloaded = overloaded || __any_sync(0xffffffffu, over);
@@ -429,13 +435,14 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
             changed = true;
             if (lane == 0) lam[jj] = nl;
             __syncwarp();
-            for (int z = 0; z < nf; ++z) scan_function(fl[z]);      // their sources see a new price on jj
+            for (int z = 0; z < nf; ++z) { scan_function(fl[z]); dirty_now |= F <= 64 ? 1ull << fl[z] : ~0ull; }   // their sources see a new price on jj
             __syncwarp();
           }
         }
       }
       if (!changed) { settled = true; break; }
     }
+    dirtyF = settled ? 0ull : dirty_now;
     // ---- record ---------------------------------------------------------------------------------------------------
     // With no node overloaded, routing every source WHOLE to its nearest priced pod is a feasible point of the MIP
     // (pods that end up unused are closed, the others serve at least one whole source: C1b holds), so its delay
@@ -595,6 +602,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
     for (int f = 0; f < F; ++f) {
       const int nt_ = newT[f], ot_ = oldT[f];
       if (nt_ != ot_) {
+        dirtyF |= F <= 64 ? 1ull << f : ~0ull;
         if (lane < kk) c[f * N + Jn[lane]] = (nt_ >> lane) & 1;
         __syncwarp();
         rebuild_pods(f);
