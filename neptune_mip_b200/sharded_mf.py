@@ -236,3 +236,37 @@ class ShardedMF:
                 xr.copy_(self.x); yr.copy_(self.y)
                 self.xsum.zero_(); self.ysum.zero_(); since = 0
         return info
+
+
+def bench_record(rank, world_size, peak_gbs, n_nodes=2000, n_funcs=200, iters=64, seed=0):
+    """BASELINE config 4 inside bench.py (called by every rank of an initialised NCCL group): the sharded
+    matrix-free iteration on one n_nodes x n_funcs instance -- us per iteration (max over ranks), algorithmic GB/s
+    per GPU, the share of the all-reduce, and the drift of the sharded iterates from the single-GPU ones."""
+    from . import sharding, synth
+    from .core.utils import data_to_solver_input
+    data = data_to_solver_input(synth.random_payload(n_nodes, n_funcs, seed, node_cores=None), 1, with_db=False)
+    lp = ShardedMF(data)
+    N = n_nodes
+    lp.iterate(4)
+    torch.cuda.synchronize()
+    if world_size > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); lp.iterate(iters); e1.record(); e1.synchronize()
+    ms = sharding.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    # the exchange alone: the same number of all-reduces of 2N doubles, back to back
+    e0.record()
+    for _ in range(iters):
+        lp.allreduce(lp.coupling)
+    e1.record(); e1.synchronize()
+    ms_ar = sharding.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    by = 64 * lp.X + 112 * lp.Cn + 8 * N * N
+    kkt = lp._kkt(lp.x, lp.y)                                  # collective
+    rec = {"workload": f"C4: {n_nodes} nodes x {n_funcs} functions, one instance, functions sharded over {world_size} ranks "
+                       f"({lp.Fg} on rank 0), matrix-free PDHG", "iterations": iters,
+           "us_per_iteration": 1e3 * ms / iters, "gbs_per_gpu": by * iters / ms / 1e6,
+           "frac_of_measured_hbm": by * iters / ms / 1e6 / peak_gbs, "aggregate_gbs": world_size * by * iters / ms / 1e6,
+           "collective": "one NCCL all-reduce of 2N doubles per iteration (C4 activity | C2 activity), on the launch stream",
+           "allreduce_bytes_per_iteration": 16 * N, "allreduce_us": 1e3 * ms_ar / iters,
+           "allreduce_share_of_iteration": ms_ar / ms, "kkt_after": kkt}
+    return rec
