@@ -92,13 +92,23 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
         iters = int(lp_res["iters"].max())
         guide = xs[:, X:X + F * N].contiguous()
         del xs, ys
-    seeds = torch.stack([device.efttc(inst, k, prm.alpha)[0] for k in ("min_delay", "min_util", "min_delay_util")],
-                        dim=1).contiguous()
-    fallback = seeds[:, KINDS[kind]]
+    cache = {}
+
+    def get_seeds():
+        """EFTTC placements of the three objectives (one thread block per instance: seconds at 50x10, so the LP-guided
+        search only asks for them when it needs a fallback or feeds the add/drop/swap search)"""
+        if "s" not in cache:
+            cache["s"] = torch.stack([device.efttc(inst, k, prm.alpha)[0] for k in ("min_delay", "min_util", "min_delay_util")],
+                                     dim=1).contiguous()
+        return cache["s"]
+
     lns_round, lns_ms, lns_diag = None, 0.0, None
     if use_lns:
-        best_c, x, n, flags, scores, lns_round, lns_ms, lns_diag = lns_step1(inst, kind, prm, guide, lam0, seeds, time_it=time_pdhg)
+        lns_seeds = get_seeds() if (prm.lns_local_chains > 0 or guide is None) else None
+        best_c, x, n, flags, scores, lns_round, lns_ms, lns_diag = lns_step1(inst, kind, prm, guide, lam0, lns_seeds, time_it=time_pdhg)
     else:
+        seeds = get_seeds()
+        fallback = seeds[:, KINDS[kind]]
         best_c, best_obj, _ = device.local_search(inst, kind, seeds, prm.alpha, prm.chains, prm.sweeps,
                                                   prm.rng_seed, guide)
         bad = ~torch.isfinite(best_obj)
@@ -111,6 +121,7 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
     if bool(bad.any()):
         # rare (a pod starved by a split flow that no free source can top up): fall back, per instance, to the
         # first EFTTC seed that passes every check -- a worse objective, never an infeasible answer
+        seeds = get_seeds()
         for k in (KINDS[kind], 1, 2, 0):
             cf, xf, nf, _, _ = device.route_capacitated(inst, seeds[:, k].contiguous())
             ff, sf = device.check_solution(inst, xf, device.u8_to_f64(cf), nf, prm.alpha)
@@ -183,7 +194,7 @@ def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0,
     if prm.lns_local_chains > 0:
         # one more candidate from the add/drop/swap search (it prices overload by a penalty instead of node prices and
         # does better where most CPU rows bind); restarted from the best records
-        pool = torch.cat([elite[:, :2], elite[:, Eh:Eh + 2], seeds], dim=1).contiguous()
+        pool = torch.cat([elite[:, :2], elite[:, Eh:Eh + 2]] + ([seeds] if seeds is not None else []), dim=1).contiguous()
         lc, lobj, _ = device.local_search(inst, kind, pool, prm.alpha, prm.lns_local_chains, prm.sweeps, prm.rng_seed, None)
         lc = torch.where(torch.isfinite(lobj)[:, None, None], lc, elite[:, 0])
         elite = torch.cat([elite, lc[:, None]], dim=1).contiguous()
