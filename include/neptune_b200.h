@@ -306,6 +306,7 @@ int neptune_lns_search(int B, int N, int F, int kind, double alpha, int chains, 
                        const double* d, const double* w, const double* r, const double* m,
                        const double* Mj, const double* Kj, const double* maxd,
                        const double* guide, const double* lam0, int S, const uint8_t* seeds,
+                       int max_slots /* >= max_j floor(Mj / m), or 0 for F: sizes the shared-memory scratch */,
                        uint8_t* out_c, double* out_g, double* out_lb, int32_t* out_round, void* stream);
 
 /* ---- (d) EFTTC greedy -----------------------------------------------------------------------------

@@ -32,6 +32,7 @@ class BatchParams:
     lns_cooling: float = 0.6      # temperature factor from one phase to the next
     lns_restart_pool: int = 16    # records a restart phase draws its start placements from
     lns_local_chains: int = 0     # > 0: the add/drop/swap search, restarted from the best records, adds one candidate
+    lns_k4_chains: int = 0        # > 0: a second population of chains that re-optimise four nodes per round
     elites: int = 16              # chain records priced exactly (routing LP) per instance
 
 
@@ -153,34 +154,40 @@ def objective_weights(inst: device.InstanceBatch, kind, alpha):
 
 def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0, seeds, time_it=False):
     """Slot-count LNS -> exact pricing of the best chain records (routing LP) -> exact routing + checkers of the
-    winner.  Returns (c uint8[B,F,N], x, n, flags, scores, round[B], search ms)."""
+    winner.  Returns (c uint8[B,F,N], x, n, flags, scores, round[B], search ms, diagnostics)."""
     B, N, F = inst.B, inst.N, inst.F
     if time_it:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    # phase 0 starts from roundings of the relaxation; every later phase restarts ALL chains from the best records so
-    # far (population restarts: "go with the winners") at a lower temperature
     phases = max(1, prm.lns_phases)
     rounds = max(1, prm.lns_rounds // phases)
-    ub_c = ub_g = ub_r = lb_c = lb_g = lb_r = None            # records by upper bound / by lower bound, all phases
-    C_ = prm.lns_chains
+    pops = []                 # populations: dict(c, g, r, other, chains), records [0, chains) by upper bound, [chains, 2 chains) by lower
+
+    def population(chains, n_rounds, k, noise, rng, guide_, seeds_, round_scale=1, round_offset=0):
+        c_, g_, r_ = device.lns_search(inst, kind, prm.alpha, chains, n_rounds, k, noise, rng, guide_, lam0, seeds_)
+        pops.append(dict(c=c_, g=g_, r=r_ * round_scale + round_offset, other=device.lns_search.last_other_bound, chains=chains))
+
+    def records(upper):
+        part = lambda t, p: t[:, :p["chains"]] if upper else t[:, p["chains"]:]          # noqa: E731
+        return tuple(torch.cat([part(p[key], p) for p in pops], dim=1) for key in ("c", "g", "r", "other"))
+
     for ph in range(phases):
         noise = prm.lns_noise * (prm.lns_cooling ** ph)
         if ph == 0:
-            pc, pg, pr_ = device.lns_search(inst, kind, prm.alpha, C_, rounds, prm.lns_k, noise,
-                                            prm.rng_seed, guide, lam0, seeds)
+            # start from roundings of the relaxation; optionally a second population that re-optimises four nodes at a
+            # time (half as many, dearer rounds): it misses other instances than the three-node one does
+            population(prm.lns_chains, rounds, prm.lns_k, noise, prm.rng_seed, guide, seeds)
+            if prm.lns_k4_chains > 0:
+                population(prm.lns_k4_chains, max(1, rounds // 2), 4, noise, prm.rng_seed + 104729, guide, seeds, round_scale=2)
         else:
+            # population restart ("go with the winners"): every chain restarts from one of the best records so far
+            ub_c, ub_g, _, _ = records(True)
             S = min(prm.lns_restart_pool, ub_g.shape[1])
             _, top = torch.topk(ub_g, S, dim=1, largest=False)
             pool = torch.gather(ub_c, 1, top[:, :, None, None].expand(B, S, F, N)).contiguous()
-            pc, pg, pr_ = device.lns_search(inst, kind, prm.alpha, C_, rounds, prm.lns_k, noise,
-                                            prm.rng_seed + 7919 * ph, None, lam0, pool)
-            pr_ = pr_ + ph * rounds
-        cat = lambda a_, b_: b_ if a_ is None else torch.cat([a_, b_], dim=1)          # noqa: E731
-        ob = device.lns_search.last_other_bound
-        lb_u = ob[:, C_:] if ph == 0 else torch.cat([lb_u, ob[:, C_:]], dim=1)
-        ub_c, ub_g, ub_r = cat(ub_c, pc[:, :C_]), cat(ub_g, pg[:, :C_]), cat(ub_r, pr_[:, :C_])
-        lb_c, lb_g, lb_r = cat(lb_c, pc[:, C_:]), cat(lb_g, pg[:, C_:]), cat(lb_r, pr_[:, C_:])
+            population(prm.lns_chains, rounds, prm.lns_k, noise, prm.rng_seed + 7919 * ph, None, pool, round_offset=ph * rounds)
+    ub_c, ub_g, ub_r, _ = records(True)
+    lb_c, lb_g, lb_r, lb_u = records(False)
     # elites: the best records of either kind, half each (a lower and an upper bound do not rank against each other)
     Eh = max(1, min(prm.elites // 2, ub_g.shape[1]))
     _, iu = torch.topk(ub_g, Eh, dim=1, largest=False)

@@ -28,7 +28,7 @@
 namespace neptune {
 
 struct LnsArgs {
-  int B, N, F, kind, chains, rounds, k, smax, wpb, S;
+  int B, N, F, kind, chains, rounds, k, smax, wpb, S, maxslots;
   double alpha, noise_coef;
   uint64_t rng;
   const double *d, *w, *r, *m, *Mj, *Kj, *maxd;
@@ -45,6 +45,7 @@ struct LnsArgs {
 constexpr double kLnsBig = 1e9;                 // priced delay of "no pod"
 constexpr double kFxScale = 1073741824.0;       // 2^30: CPU loads are accumulated in fixed point (integer adds commute)
 constexpr int kLnsMaxK = 4;
+constexpr int kLnsMaxWarps = 12;                // chains per block: two blocks of 12 warps per SM (80 registers per thread)
 
 __device__ __forceinline__ uint64_t lns_mix(uint64_t z) {        // splitmix64 finaliser
   z += 0x9E3779B97F4A7C15ull;
@@ -62,19 +63,20 @@ __device__ __forceinline__ uint64_t lns_next(uint64_t& s) { s ^= s >> 12; s ^= s
 __host__ __device__ inline size_t lns_block_shared(int N, int F) {
   return ((size_t)N * N + 2 * (size_t)F * N + (size_t)N) * 8 + (size_t)N * 4 + 64;
 }
-__host__ __device__ inline size_t lns_scratch_bytes(int N, int F, int k, int smax) {
-  const size_t fn = (size_t)F * N, nT = (size_t)1 << k;
+__host__ __device__ inline size_t lns_scratch_bytes(int N, int F, int k, int smax, int maxslots) {
+  const size_t fn = (size_t)F * N, nT = (size_t)1 << k, tn = (size_t)(maxslots < F ? maxslots : F) * N;
   size_t dp = (size_t)F * nT * 8 + 2 * (size_t)smax * 8;      // costT, cur, nxt
-  size_t th = fn * 4 + fn * 2;                                // thresholds (float) + their scan list (u16) / exception list (u16)
+  size_t th = tn * 4 + tn * 2;                                // thresholds (float) + their scan list (u16) of one node's sources
+  if (th < fn * 2) th = fn * 2;                               // exception list (u16)
   return ((dp > th ? dp : th) + 15) & ~(size_t)15;
 }
-__host__ __device__ inline size_t lns_warp_shared(int N, int F, int k, int smax) {
+__host__ __device__ inline size_t lns_warp_shared(int N, int F, int k, int smax, int maxslots) {
   const size_t fn = (size_t)F * N;
   size_t b = 0;
   b += (size_t)N * 8;               // lam
   b += (size_t)N * 8;               // loadfx
-  b += fn * 8;                      // bestv
-  b += lns_scratch_bytes(N, F, k, smax);
+  b += fn * 4;                      // bestv (float: it ranks candidates, the records are priced exactly afterwards)
+  b += lns_scratch_bytes(N, F, k, smax, maxslots);
   b += ((size_t)F + 64 + (size_t)F) * 4;   // npods, misc (J, rad, mul, incT), fl
   b += 3 * fn;                      // asg, c, podlist
   b += (size_t)F * smax;            // choice
@@ -103,7 +105,7 @@ __device__ __forceinline__ double lns_multi_reduce(double (&acc)[NT], int lane) 
 }
 
 template <int KK>
-__global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
+__global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
   constexpr int NT = 1 << KK;
   const int N = a.N, F = a.F, b = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int chain = blockIdx.x * a.wpb + wid;
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
     for (int j = threadIdx.x; j < N; j += blockDim.x) {
       s_K[j] = a.Kj[(int64_t)b * N + j];
       int sl = m0 > 0.0 ? (int)floor(a.Mj[(int64_t)b * N + j] / m0 + 1e-9) : F;
-      s_slots[j] = sl > F ? F : (sl < 0 ? 0 : sl);
+      s_slots[j] = sl > a.maxslots ? a.maxslots : (sl < 0 ? 0 : sl);
     }
   }
   __syncthreads();
@@ -153,19 +155,21 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
   }
   __syncthreads();
   if (chain >= a.chains) return;                 // (no block-wide barrier below this line)
-  const double noise0 = s_scal[0], u = s_scal[1], a_d = s_scal[2];
+  // chains anneal from different start temperatures (x0.6, 0.9, 1.2, 1.5 by chain index): no single temperature
+  // suits every instance, and a mixed population finds the optimum of more of them than any uniform one
+  const double noise0 = s_scal[0] * (0.6 + 0.3 * (double)(chain & 3)), u = s_scal[1], a_d = s_scal[2];
 
   // ---- per-warp state ------------------------------------------------------------------------------------
-  unsigned char* wp = smem + ((lns_block_shared(N, F) + 15) & ~(size_t)15) + (size_t)wid * lns_warp_shared(N, F, KK, smax);
+  unsigned char* wp = smem + ((lns_block_shared(N, F) + 15) & ~(size_t)15) + (size_t)wid * lns_warp_shared(N, F, KK, smax, a.maxslots);
   double* lam = (double*)wp; wp += (size_t)N * 8;
   unsigned long long* loadfx = (unsigned long long*)wp; wp += (size_t)N * 8;
-  double* bestv = (double*)wp; wp += (size_t)fn * 8;
-  unsigned char* scratch = wp; wp += lns_scratch_bytes(N, F, KK, smax);
+  float* bestv = (float*)wp; wp += (size_t)fn * 4;
+  unsigned char* scratch = wp; wp += lns_scratch_bytes(N, F, KK, smax, a.maxslots);
   double* costT = (double*)scratch;                       // [F][NT]
   double* cur = costT + (size_t)F * NT;
   double* nxt = cur + smax;
   float* th = (float*)scratch;                            // aliases the DP arrays (never live together)
-  unsigned short* thl = (unsigned short*)(scratch + (size_t)fn * 4);   // sources whose threshold needs a pod scan
+  unsigned short* thl = (unsigned short*)(scratch + (size_t)(a.maxslots < F ? a.maxslots : F) * N * 4);   // sources whose threshold needs a pod scan
   unsigned short* exl = (unsigned short*)scratch;         // exception list, ditto
   int* npods = (int*)wp; wp += (size_t)F * 4;
   int* misc = (int*)wp; wp += 64 * 4;
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
           const double v = s_dT[j * N + i] + lam[j] * rf[j];
           if (v < best) { best = v; bj = j; }
         }
-        bestv[f * N + i] = best; asg[f * N + i] = (uint8_t)bj;
+        bestv[f * N + i] = (float)best; asg[f * N + i] = (uint8_t)bj;
       }
     }
   };
@@ -392,8 +396,8 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
               float tv = -1.0f;                              // never uses jj
               if (av > 0.0) {
                 if (asg[f * N + i] != jj) {
-                  const double tq = (bestv[f * N + i] - s_dT[jj * N + i]) / rfj;
-                  if (tq >= 0.0) { tv = bestv[f * N + i] >= 0.5 * kLnsBig ? INFINITY : (float)fmin(tq, 1e30); tot += av; }
+                  const double tq = ((double)bestv[f * N + i] - s_dT[jj * N + i]) / rfj;
+                  if (tq >= 0.0) { tv = bestv[f * N + i] >= 0.5f * (float)kLnsBig ? INFINITY : (float)fmin(tq, 1e30); tot += av; }
                 } else scan = true;
               }
               th[t] = tv;
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
     // LP afterwards (split flows), never be a mirage of loose prices.
     {
       double gp = 0.0;
-      for (int fi = lane; fi < fn; fi += 32) { const double wv = s_w[fi]; if (wv > 0.0) gp += wv * bestv[fi]; }
+      for (int fi = lane; fi < fn; fi += 32) { const double wv = s_w[fi]; if (wv > 0.0) gp += wv * (double)bestv[fi]; }
       for (int j = lane; j < N; j += 32) gp -= lam[j] * s_K[j];
       double g = warp_sum(gp), uval = ucost;
       if (u != 0.0) {
@@ -498,7 +502,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
         const double v = s_dT[j * N + i] + lam[j] * rf[j];
         if (v < best) { best = v; bj = j; }
       }
-      bestv[fi] = best; asg[fi] = (uint8_t)bj;             // (bestv, asg) now describe "the k nodes closed" for every source
+      bestv[fi] = (float)best; asg[fi] = (uint8_t)bj;      // (bestv, asg) now describe "the k nodes closed" for every source
     }
     __syncwarp();
 
@@ -529,7 +533,7 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
         const double wv = s_w[f * N + i];
         if (wv == 0.0) continue;
         double val[NT];
-        val[0] = bestv[f * N + i];
+        val[0] = (double)bestv[f * N + i];
         double vq[KK];
 #pragma unroll
         for (int q = 0; q < KK; ++q) vq[q] = s_dT[Jr[q] * N + i] + pj[q];
@@ -614,12 +618,12 @@ __global__ void __launch_bounds__(256, 2) k_lns(LnsArgs a) {
       for (int ib = 0; ib < N; ib += 32) {
         const int i = ib + lane;
         if (i >= N) continue;
-        double best = bestv[f * N + i]; int bj = asg[f * N + i];
+        double best = (double)bestv[f * N + i]; int bj = asg[f * N + i];
 #pragma unroll
         for (int q = 0; q < KK; ++q) {
           if (q < kk && ((nt_ >> q) & 1)) { const double v = s_dT[Jr[q] * N + i] + pj[q]; if (v < best || (v == best && Jr[q] < bj)) { best = v; bj = Jr[q]; } }
         }
-        bestv[f * N + i] = best; asg[f * N + i] = (uint8_t)bj;
+        bestv[f * N + i] = (float)best; asg[f * N + i] = (uint8_t)bj;
       }
     }
     __syncwarp();
@@ -643,7 +647,7 @@ extern "C" int neptune_lns_search(int B, int N, int F, int kind, double alpha, i
                                   double noise_coef, uint64_t rng_seed, const double* d, const double* w,
                                   const double* r, const double* m, const double* Mj, const double* Kj,
                                   const double* maxd, const double* guide, const double* lam0, int S,
-                                  const uint8_t* seeds, uint8_t* out_c, double* out_g, double* out_lb,
+                                  const uint8_t* seeds, int max_slots, uint8_t* out_c, double* out_g, double* out_lb,
                                   int32_t* out_round, void* stream) {
   if (B <= 0 || N <= 0 || F <= 0 || chains <= 0 || rounds < 0 || k < 2 || k > kLnsMaxK || !d || !w || !r || !m || !Mj ||
       !Kj || !out_c || !out_g || !out_round)
@@ -659,8 +663,9 @@ extern "C" int neptune_lns_search(int B, int N, int F, int kind, double alpha, i
   // states of the slot counters: (slots+1)^k for the common 3-slot nodes, capped by shared memory
   int smax = 1; for (int q = 0; q < k; ++q) smax *= 4;
   const size_t blk = (lns_block_shared(N, F) + 15) & ~(size_t)15;
-  int wpb = 8;
-  size_t per = lns_warp_shared(N, F, k, smax);
+  int wpb = kLnsMaxWarps;
+  a.maxslots = (max_slots > 0 && max_slots < F) ? max_slots : F;       // bound on floor(Mj / m) the caller vouches for (sizes the scratch)
+  size_t per = lns_warp_shared(N, F, k, smax, a.maxslots);
   while (wpb > 1 && blk + wpb * per > 112 * 1024) --wpb;              // two blocks per SM (227 KB, 1 KB reserved per block)
   if (blk + wpb * per > 200 * 1024) return NEPTUNE_E_SIZE;
   if (wpb > chains) wpb = chains;

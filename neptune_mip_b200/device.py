@@ -409,12 +409,13 @@ def lns_search(inst: InstanceBatch, kind, alpha=0.5, chains=32, rounds=4000, k=3
     out_g = torch.empty((inst.B, 2 * chains), dtype=torch.float64, device=dev)
     out_round = torch.empty((inst.B, 2 * chains), dtype=torch.int32, device=dev)
     out_lb = torch.empty((inst.B, 2 * chains), dtype=torch.float64, device=dev)
+    max_slots = int(torch.floor(inst.Mj / inst.m[:, :1] + 1e-9).max().clamp(min=0, max=inst.F).item())
     check(lib.neptune_lns_search(inst.B, inst.N, inst.F, kind, C.c_double(alpha), chains, rounds, k,
                                  C.c_double(noise_coef), C.c_uint64(rng_seed), _ptr(inst.d), _ptr(inst.w), _ptr(inst.r),
                                  _ptr(inst.m), _ptr(inst.Mj), _ptr(inst.Kj), _ptr(inst.maxd), _ptr(guide), _ptr(lam0),
-                                 S, _ptr(seeds_u8), _ptr(out_c), _ptr(out_g), _ptr(out_lb), _ptr(out_round), _stream()),
+                                 S, _ptr(seeds_u8), max_slots, _ptr(out_c), _ptr(out_g), _ptr(out_lb), _ptr(out_round), _stream()),
           "neptune_lns_search")
-    lns_search.last_other_bound = out_lb          # diagnostics (tools): the other end of each record's bracket
+    lns_search.last_other_bound = out_lb          # the other end of each record's bracket (diagnostics)
     return out_c, out_g, out_round
 
 
