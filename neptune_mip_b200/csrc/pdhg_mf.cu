@@ -1037,10 +1037,10 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
 }
 
 // ===================================================================================================
-// EXPERIMENTAL -- step-wise building blocks for the function-block-sharded matrix-free PDHG (SURVEY.md
-// section 8(e); one process per GPU, neptune_mip_b200/sharded_mf.py owns the loop and the all-reduce).
-// Written after the round's GPU budget was spent: NOT YET RUN on a GPU; the numpy statement it follows
-// (tests/mf_reference.ShardedMatrixFree) is proven equal to the unsharded iteration on 2 gloo ranks.
+// Step-wise building blocks for the function-block-sharded matrix-free PDHG (one
+// process per GPU, neptune_mip_b200/sharded_mf.py owns the loop and the all-reduce).  The numpy statement it
+// follows (tests/mf_reference.ShardedMatrixFree) is proven equal to the unsharded iteration on 2 gloo ranks;
+// two NCCL ranks on B200 reproduce the single-rank iterates to 3e-17 (tests/test_sharded_gpu.py).
 // A rank holds the functions of its block (F = functions of this rank); the 2N multipliers of the coupling
 // rows (y2: C2 memory, y4: C4 CPU) are replicated.  Per iteration:
 //   neptune_pdhg_mf_local_step : y1, y3 of the pass that just ran (local), c columns of the next iteration

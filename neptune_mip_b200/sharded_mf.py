@@ -1,14 +1,14 @@
-"""EXPERIMENTAL -- function-block-sharded MATRIX-FREE PDHG for one large instance (SURVEY.md section 8(e),
-BASELINE config 4).  Written after round 1's GPU budget was spent: not yet run on a GPU.  The iteration it drives
-is stated in numpy by `tests/mf_reference.ShardedMatrixFree`, which a world_size-2 gloo test proves equal to the
-unsharded iteration; `tools/sharded_run.py mf-parity` is the GPU check to run first.
+"""Function-block-sharded MATRIX-FREE PDHG for one large instance (BASELINE config 4).
+The iteration it drives is stated in numpy by `tests/mf_reference.ShardedMatrixFree`, which a world_size-2 gloo test
+proves equal to the unsharded iteration; on B200 (round 2) two NCCL ranks reproduce the single-rank iterates to
+3e-17 (`tools/sharded_run.py mf-parity`, profiles/r02_sharded_mf.md).
 
 One process per GPU.  Rank g owns the functions of its block: x[f,.,.], c[f,.], y1[f,.], y3[f,.], yS[f,.,.]
 are local; the 2N multipliers of the coupling rows (y2: C2 memory, y4: C4 CPU) are replicated.  ONE all-reduce of
 2N doubles per iteration -- [C4 activity of the pass that just ran | C2 activity of the c columns just updated] --
 and nothing of the matrix is stored: the per-GPU share of C4 (2000 nodes x 25 functions) is 4 x 0.8 GB of state
-instead of 9.6 GB of CSR, and its pass takes 1.75 ms against 4.08 ms for the sharded CSR pass (single-GPU
-measurement of the same kernel, profiles/r01g_ceiling.log).
+instead of 9.6 GB of CSR.  Measured on 2 x B200: 1.40 ms per iteration = 4.6 TB/s per GPU (0.70 of the measured
+copy bandwidth), the all-reduce 19 us of it (1.4 %).
 """
 from __future__ import annotations
 

@@ -29,13 +29,9 @@ def test_sharded_restarted_solve_reaches_the_single_gpu_lp_optimum():
     assert "SOLVE world=2" in out.stdout
 
 
-EXPERIMENTAL = pytest.mark.skipif(not os.environ.get("NEPTUNE_EXPERIMENTAL"),
-                                  reason="matrix-free sharded solver: written after the round's GPU budget was spent; "
-                                         "run with NEPTUNE_EXPERIMENTAL=1 on a B200 first")
 
 
-@EXPERIMENTAL
-def test_experimental_matrix_free_single_rank_equals_the_numpy_iteration():
+def test_matrix_free_single_rank_equals_the_numpy_iteration():
     """world size 1: the step-wise entry points (local step / pass / flush) reproduce tests/mf_reference.MatrixFree"""
     import numpy as np
     from helpers import arrays_of, data_of
@@ -45,8 +41,9 @@ def test_experimental_matrix_free_single_rank_equals_the_numpy_iteration():
     for (N, F, cores, iters) in ((12, 5, 25, 96), (50, 4, 200, 40), (70, 3, 60, 33)):
         p = synth.random_payload(N, F, 1, node_cores=cores)
         lp = ShardedMF(data_of(p))
-        lp.iterate(iters)
         ref = MatrixFree(arrays_of(p))
+        lp.tau, lp.sigma = ref.eta / ref.omega, ref.eta * ref.omega          # the reference's primal-weighted steps
+        lp.iterate(iters)
         for _ in range(iters):
             ref.step()
         xr, yr = ref.pack()
@@ -58,8 +55,7 @@ def test_experimental_matrix_free_single_rank_equals_the_numpy_iteration():
             assert abs(u - v) <= 1e-9 * (1 + abs(v))
 
 
-@EXPERIMENTAL
-def test_experimental_matrix_free_two_ranks_match_single_rank():
+def test_matrix_free_two_ranks_match_single_rank():
     env = dict(os.environ, NEPTUNE_DIST_BACKEND="gloo")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29535", os.path.join(ROOT, "tools", "sharded_run.py"), "mf-parity", "24", "6", "150"]
@@ -68,8 +64,7 @@ def test_experimental_matrix_free_two_ranks_match_single_rank():
     assert "MF-PARITY world=2" in out.stdout
 
 
-@EXPERIMENTAL
-def test_experimental_matrix_free_sharded_solve_reaches_the_single_gpu_optimum():
+def test_matrix_free_sharded_solve_reaches_the_single_gpu_optimum():
     env = dict(os.environ, NEPTUNE_DIST_BACKEND="gloo", NEPTUNE_NODE_CORES="12")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29536", os.path.join(ROOT, "tools", "sharded_run.py"), "mf-solve", "8", "4", "40000"]
