@@ -466,7 +466,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="instances per GPU per step")
-    ap.add_argument("--lp-iters", type=int, default=40000, help="cap on PDHG iterations (the solver stops at 1e-6 relative KKT error)")
+    ap.add_argument("--lp-iters", type=int, default=50000, help="cap on PDHG iterations (the solver stops at 1e-6 relative KKT error)")
     ap.add_argument("--search", default="auto", choices=["auto", "local"])
     ap.add_argument("--lns-chains", type=int, default=128)
     ap.add_argument("--lns-rounds", type=int, default=24000)

@@ -75,7 +75,7 @@ __host__ __device__ inline size_t lns_warp_shared(int N, int F, int k, int smax,
   size_t b = 0;
   b += (size_t)N * 8;               // lam
   b += (size_t)N * 8;               // loadfx
-  b += fn * 4;                      // bestv (float: it ranks candidates, the records are priced exactly afterwards)
+  b += (fn * 4 + 15) & ~(size_t)15; // bestv (float: it ranks candidates, the records are priced exactly afterwards)
   b += lns_scratch_bytes(N, F, k, smax, maxslots);
   b += ((size_t)F + 64 + (size_t)F) * 4;   // npods, misc (J, rad, mul, incT), fl
   b += 3 * fn;                      // asg, c, podlist
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
   unsigned char* wp = smem + ((lns_block_shared(N, F) + 15) & ~(size_t)15) + (size_t)wid * lns_warp_shared(N, F, KK, smax, a.maxslots);
   double* lam = (double*)wp; wp += (size_t)N * 8;
   unsigned long long* loadfx = (unsigned long long*)wp; wp += (size_t)N * 8;
-  float* bestv = (float*)wp; wp += (size_t)fn * 4;
+  float* bestv = (float*)wp; wp += ((size_t)fn * 4 + 15) & ~(size_t)15;
   unsigned char* scratch = wp; wp += lns_scratch_bytes(N, F, KK, smax, a.maxslots);
   double* costT = (double*)scratch;                       // [F][NT]
   double* cur = costT + (size_t)F * NT;

@@ -21,7 +21,7 @@ def _gold(cfg):
 def _solve(cfg, seeds, **kw):
     from neptune_mip_b200.batch import BatchParams, solve_batch
     inst = cuda_batch([synth.config_payload(cfg, s) for s in seeds])
-    prm = BatchParams(kind="min_delay", lp_iters=40000, lp_check_every=256, **kw)
+    prm = BatchParams(kind="min_delay", lp_iters=60000, lp_check_every=256, **kw)
     return inst, solve_batch(inst, prm)
 
 
