@@ -181,10 +181,14 @@ def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0,
                 population(prm.lns_k4_chains, max(1, rounds // 2), 4, noise, prm.rng_seed + 104729, guide, seeds, round_scale=2)
         else:
             # population restart ("go with the winners"): every chain restarts from one of the best records so far
-            ub_c, ub_g, _, _ = records(True)
-            S = min(prm.lns_restart_pool, ub_g.shape[1])
-            _, top = torch.topk(ub_g, S, dim=1, largest=False)
-            pool = torch.gather(ub_c, 1, top[:, :, None, None].expand(B, S, F, N)).contiguous()
+            # (drawn half from the records by upper bound, half from those by lower bound)
+            halves = []
+            for upper in (True, False):
+                rc, rg, _, _ = records(upper)
+                S = max(1, min(prm.lns_restart_pool // 2, rg.shape[1]))
+                _, top = torch.topk(rg, S, dim=1, largest=False)
+                halves.append(torch.gather(rc, 1, top[:, :, None, None].expand(B, S, F, N)))
+            pool = torch.cat(halves, dim=1).contiguous()
             population(prm.lns_chains, rounds, prm.lns_k, noise, prm.rng_seed + 7919 * ph, None, pool, round_offset=ph * rounds)
     ub_c, ub_g, ub_r, _ = records(True)
     lb_c, lb_g, lb_r, lb_u = records(False)

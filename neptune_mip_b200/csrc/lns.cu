@@ -472,9 +472,9 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
         for (int q = lane; q < fn; q += 32) outc[q] = c[q];
       }
       // second record, by the lower bound: where the optimal routing splits flows, g is the LP value and the whole-flow
-      // value overstates it by sum_j lam_j (K_j - load_j).  Only with settled prices and a small bracket [g, U] (loose
-      // prices make g a mirage); both records are priced exactly by the caller.
-      if (!overloaded && !unserved && settled && uval - g <= 0.01 * fabs(uval) && g < bestg2 - 1e-9 * (1.0 + fabs(g))) {
+      // value overstates it by sum_j lam_j (K_j - load_j) -- 15 % on a 20-node instance whose optimum splits a heavy flow.
+      // Only with settled prices; both records are priced exactly by the caller.
+      if (!overloaded && !unserved && settled && g < bestg2 - 1e-9 * (1.0 + fabs(g))) {
         bestg2 = g; bestu2 = uval; best_round2 = round;
         for (int q = lane; q < fn; q += 32) outc2[q] = c[q];
       }

@@ -42,7 +42,7 @@ constexpr double kRlpPivTol = 1e-11;    // smallest admissible pivot magnitude
 __host__ __device__ inline int64_t rlp_fixed_bytes(int N, int F) {
   const int64_t fn = (int64_t)F * N;
   // near, src, coloff (fn+1), podlist: 4 * fn ints (+1); colsrc / basis live after the tableau sizing below
-  int64_t b = (4 * fn + 8 + F + N) * 4 + ((fn + 7) & ~(int64_t)7);   // + working copy of the placement
+  int64_t b = (5 * fn + 8 + 2 * F + N) * 4 + ((fn + 7) & ~(int64_t)7);   // + C1b pod list, fully-active functions, working copy of the placement
   b = (b + 7) & ~(int64_t)7;
   b += ((int64_t)2 * N + fn + N) * 8;          // load, colq bound (rows <= fn + N), ...
   b += (int64_t)N * fn * 8;                    // dense x scratch
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) k_route_lp(RlpArgs a) {
   __shared__ double s_val[8];
   __shared__ int s_idx[8];
   __shared__ double red[32];
-  __shared__ int s_nS, s_nC, s_flag, s_grow, s_nA;
+  __shared__ int s_nS, s_nC, s_flag, s_grow, s_nA, s_nP;
   // ---- carve the slab --------------------------------------------------------------------------------
   char* p = a.ws + (int64_t)blockIdx.x * a.slab_bytes;
   int* near = (int*)p; p += fn * 4;
@@ -80,6 +80,8 @@ __global__ void __launch_bounds__(256) k_route_lp(RlpArgs a) {
   int* podlist = (int*)p; p += fn * 4;
   int* npods = (int*)p; p += (int64_t)F * 4;
   int* inA = (int*)p; p += (int64_t)N * 4;
+  int* c1b = (int*)p; p += fn * 4;          // pods (f*N + j) that get a C1b row: sum_i x[i,f,j] >= 1 - eps
+  int* fullF = (int*)p; p += (int64_t)F * 4; // functions whose every source is in the LP (they own a C1b row)
   uint8_t* cw = (uint8_t*)p; p += fn;       // working copy of the placement: starved pods are closed and the LP re-solved
   p = (char*)(((uintptr_t)p + 7) & ~(uintptr_t)7);
   double* load = (double*)p; p += (int64_t)N * 8;
@@ -98,7 +100,11 @@ __global__ void __launch_bounds__(256) k_route_lp(RlpArgs a) {
     const double* r = a.r + b * fn;
     const double* K = a.Kj + (int64_t)b * N;
     __syncthreads();
-    if (attempt == 0) for (int q = tid; q < (int)fn; q += nt) cw[q] = a.c[job * fn + q];
+    if (attempt == 0) {
+      for (int q = tid; q < (int)fn; q += nt) cw[q] = a.c[job * fn + q];
+      for (int f = tid; f < F; f += nt) fullF[f] = 0;
+      if (tid == 0) s_nP = 0;
+    }
     const uint8_t* c = cw;
     __syncthreads();
     if (tid == 0) s_flag = 1;
@@ -143,19 +149,20 @@ __global__ void __launch_bounds__(256) k_route_lp(RlpArgs a) {
     }
     int nS = 0, nC = 0, R = 0, C = 0;
     double* T = Treg; double* redc = nullptr; int* colsrc = nullptr; int* basis = nullptr;
-    bool solved_lp = false;
-    while (status == 1 && s_nA > 0) {
+    bool solved_lp = false, c1b_infeasible = false;
+    while (status == 1 && (s_nA > 0 || s_nP > 0)) {
       // ---- active sources and their columns (ordered: thread 0) ---------------------------------------
       if (tid == 0) {
         int ns = 0, nc = 0;
         for (int fi = 0; fi < (int)fn; ++fi) {
-          if (w[fi] > 0.0 && inA[near[fi]]) { src[ns] = fi; coloff[ns] = nc; nc += npods[fi / N]; ++ns; }
+          if ((w[fi] > 0.0 && inA[near[fi]]) || fullF[fi / N]) { src[ns] = fi; coloff[ns] = nc; nc += npods[fi / N]; ++ns; }
         }
         coloff[ns] = nc;
         s_nS = ns; s_nC = nc;
       }
       __syncthreads();
-      nS = s_nS; nC = s_nC; R = nS + N; C = nC + N + 1;
+      const int nP = s_nP;
+      nS = s_nS; nC = s_nC; R = nS + N + nP; C = nC + N + nP + 1;
       const int64_t need = (int64_t)R * C + C + (C + R + 2) / 2 + 2;
       if (need > a.tab_doubles) { status = 2; break; }
       redc = T + (int64_t)R * C;
@@ -179,11 +186,29 @@ __global__ void __launch_bounds__(256) k_route_lp(RlpArgs a) {
             T[(int64_t)(nS + j) * C + col] = wv * r[(int64_t)f * N + j];
             T[(int64_t)(nS + nj) * C + col] = -anj;
             redc[col] = wv * (d[(int64_t)i * N + j] - dnj);
+            // C1b rows of this function's starved pods, in canonical form: -sum_s x[s, jp] + surplus = -(1 - eps) with
+            // the basic x[s, near(s)] = 1 - (the other columns of s) substituted
+            for (int pp = 0; pp < nP; ++pp) {
+              const int fj = c1b[pp];
+              if (fj / N != f) continue;
+              const int jp = fj - f * N;
+              if (nj == jp) T[(int64_t)(nS + N + pp) * C + col] = 1.0;
+              else if (j == jp) T[(int64_t)(nS + N + pp) * C + col] = -1.0;
+            }
           } else {
             basis[s] = col;
           }
         }
         T[(int64_t)s * C + (C - 1)] = 1.0;
+      }
+      for (int pp = tid; pp < nP; pp += nt) {
+        const int fj = c1b[pp], f = fj / N, jp = fj - f * N;
+        int cnt = 0;
+        for (int i = 0; i < N; ++i) cnt += near[(int64_t)f * N + i] == jp;          // every source of f is active (fullF)
+        T[(int64_t)(nS + N + pp) * C + nC + N + pp] = 1.0;
+        T[(int64_t)(nS + N + pp) * C + (C - 1)] = (double)cnt - (1.0 - kEps);
+        basis[nS + N + pp] = nC + N + pp;
+        colsrc[nC + N + pp] = -1;
       }
       for (int j = tid; j < N; j += nt) {
         T[(int64_t)(nS + j) * C + nC + j] = 1.0;
@@ -232,11 +257,14 @@ __global__ void __launch_bounds__(256) k_route_lp(RlpArgs a) {
       pivots += it;
       if (it >= max_piv) { status = 2; break; }                 // did not converge (never seen): let the caller fall back
       if (infeasible) {
-        if (s_nA == N) { status = 0; break; }
-        for (int j = tid; j < N; j += nt) inA[j] = 1;
-        if (tid == 0) s_nA = N;
-        __syncthreads();
-        continue;
+        if (s_nA < N) {
+          for (int j = tid; j < N; j += nt) inA[j] = 1;
+          if (tid == 0) s_nA = N;
+          __syncthreads();
+          continue;
+        }
+        if (nP > 0) { c1b_infeasible = true; break; }          // the C1b rows cannot be met: those pods are closed below
+        status = 0; break;
       }
       // ---- nodes the optimum makes tight although their own sources are still pinned: widen A ----------
       if (tid == 0) s_grow = 0;
@@ -252,6 +280,18 @@ __global__ void __launch_bounds__(256) k_route_lp(RlpArgs a) {
       solved_lp = true;
       break;
     }
+    if (c1b_infeasible) {
+      // no routing gives the starved pods their share: close them and price the smaller placement
+      __syncthreads();
+      for (int pp = tid; pp < s_nP; pp += nt) cw[c1b[pp]] = 0;
+      for (int f = tid; f < F; f += nt) fullF[f] = 0;
+      __syncthreads();
+      if (tid == 0) s_nP = 0;
+      attempt = attempt < 2 ? 2 : attempt + 1;
+      __syncthreads();
+      if (attempt <= 5) continue;
+      status = 0;
+    }
     // ---- solution: dense x in the slab, cost, C1b repair, outputs ---------------------------------------
     int bad = 0;
     if (status == 1) {
@@ -259,7 +299,7 @@ __global__ void __launch_bounds__(256) k_route_lp(RlpArgs a) {
       __syncthreads();
       for (int fi = tid; fi < (int)fn; fi += nt) {
         const int f = fi / N, i = fi - f * N;
-        const bool active = solved_lp && w[fi] > 0.0 && inA[near[fi]];
+        const bool active = solved_lp && ((w[fi] > 0.0 && inA[near[fi]]) || fullF[f]);
         if (!active) xs[((int64_t)i * F + f) * N + near[fi]] = 1.0;
       }
       if (solved_lp) {
@@ -333,7 +373,32 @@ __global__ void __launch_bounds__(256) k_route_lp(RlpArgs a) {
       }
       __syncthreads();
       bad = s_flag;
-      if (bad && attempt < 4) {
+      if (bad && attempt < 2) {
+        // C1b is violated at the LP optimum of the capacity rows alone (constraints_step1.py:12-15): give every such
+        // pod its row  sum_i x[i,f,j] >= 1 - eps  (all sources of its function enter the LP, the zero-workload ones as
+        // free columns) and solve again -- the MIP's own treatment
+        if (tid == 0) {
+          int np_ = s_nP;
+          for (int fj = 0; fj < (int)fn; ++fj) {
+            if (!cw[fj]) continue;
+            const int f = fj / N, j = fj - f * N;
+            double rc = 0.0;
+            for (int i = 0; i < N; ++i) rc += xs[((int64_t)i * F + f) * N + j];
+            if (rc != 0.0 && rc + kEps < 1.0) {
+              bool have = false;
+              for (int pp = 0; pp < np_; ++pp) have = have || c1b[pp] == fj;
+              if (!have) { c1b[np_++] = fj; fullF[f] = 1; }
+            }
+          }
+          s_nP = np_;
+        }
+        ++attempt;
+        __syncthreads();
+        continue;
+      }
+      if (bad && attempt < 5) {
+        if (tid == 0) s_nP = 0;
+        for (int f = tid; f < F; f += nt) fullF[f] = 0;
         // C1b cannot be met for some pod at this routing (constraints_step1.py:12-15): close the starved pods and
         // solve the LP of the smaller placement -- still a feasible point of the MIP, at the LP value of that placement
         for (int fj = tid; fj < (int)fn; fj += nt) {

@@ -51,13 +51,14 @@ def test_route_lp_equals_highs_on_cpu_starved_placements(shape):
                 continue
             if st[b, q] == 0:
                 continue                                       # a function lost its last pod to C1b: no answer for this placement
-            # a pod the LP optimum leaves with a share in (0, 1 - eps) violates C1b (constraints_step1.py:12-15): the
-            # kernel closes it and prices the smaller placement c_out, so the value is the LP optimum OF c_out
+            # the value is the optimum of the LP WITH the C1b rows (every open pod keeps a share >= 1 - eps,
+            # constraints_step1.py:12-15) of the placement the kernel returns: c minus the pods nobody uses and, where
+            # no routing can give a pod its share, minus those pods
             closed = (cs[b, q] != c_out[b, q])
             xr = x[b, q]
             if np.any(xr[:, closed] != 0.0):
                 raise AssertionError("flow on a closed pod")
-            lp2 = routing.lp_routing(a, c_out[b, q]) if closed.any() else lp
+            lp2 = routing.lp_routing(a, c_out[b, q], c1b=True)
             assert lp2 is not None and obj[b, q] >= lp[0] - 1e-9 * (1 + abs(lp[0]))
             assert abs(obj[b, q] - lp2[0]) <= 1e-9 * (1 + abs(lp2[0])), (b, q, obj[b, q], lp2[0], lp[0], info[b, q])
             assert np.all(np.abs(xr.sum(axis=2) - 1.0) < 1e-9)
