@@ -60,6 +60,8 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
     lp_res, guide, lam0, pdhg_ms, iters, dims = None, None, None, 0.0, 0, (0, 0, 0)
     bytes_iter, path = 0, ""
     use_lns = prm.search == "auto" and device.lns_supported(inst, kind)
+    if use_lns and KINDS.get(kind, kind) == 2 and not bool((objective_weights(inst, kind, prm.alpha)[0] > 0).all()):
+        use_lns = False         # no workload: the combined objective has no delay term (objectives.py:34-35), nothing to price
     inst_lp = device.slot_relaxation(inst) if (use_lns and prm.lp_cut) else inst
     if prm.lp_iters > 0:
         N, F, B = inst.N, inst.F, inst.B

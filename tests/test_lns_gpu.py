@@ -106,12 +106,13 @@ def test_a_proven_optimum_is_a_fixed_point_with_a_tight_bracket():
 
 
 def test_c5_sweep_subsample_against_the_proven_optima():
-    """BASELINE config 5 (20 x 5, most CPU rows bind): the 64 instances with a proven optimum."""
+    """BASELINE config 5 (20 x 5): the 64 instances with a proven optimum, all within 1e-4 -- several optima split a
+    heavy flow (whole-flow value 15 % above the LP value) or need a C1b row in the routing LP."""
     gold = _gold("C5")
     seeds = sorted(gold)[:64]
-    inst, res = _solve("C5", seeds, lns_chains=32, lns_rounds=3000, lns_noise=0.1, elites=16, lns_local_chains=16, sweeps=300)
+    inst, res = _solve("C5", seeds, lns_chains=32, lns_rounds=2000, lns_noise=0.1, elites=16)
     delay = res.scores[:, 0].cpu().numpy()
     assert (res.flags.cpu().numpy() == 63).all()
     gaps = np.array([(delay[k] - gold[s]["objective"]) / gold[s]["objective"] for k, s in enumerate(seeds)])
     assert gaps.min() >= -1e-9
-    assert (gaps <= 1e-4).sum() >= 58 and gaps.max() <= 0.02, (int((gaps <= 1e-4).sum()), gaps.max())
+    assert gaps.max() <= 1e-4, (int((gaps <= 1e-4).sum()), gaps.max())           # 64 of 64 (measured: worst 1e-15)
