@@ -2,6 +2,7 @@
 model, assembly + CSR otherwise) -> EFTTC -> local search -> exact check in one go (what bench.py times, and what a sweep like BASELINE.json's config 5 calls)."""
 from __future__ import annotations
 
+import dataclasses
 from dataclasses import dataclass
 from typing import Optional
 
@@ -31,8 +32,10 @@ class BatchParams:
     lns_phases: int = 1           # > 1: population restarts from the best records between phases (lns_rounds is the total)
     lns_cooling: float = 0.6      # temperature factor from one phase to the next
     lns_restart_pool: int = 16    # records a restart phase draws its start placements from
-    lns_local_chains: int = 0     # > 0: the add/drop/swap search, restarted from the best records, adds one candidate
+    lns_local_chains: int = -1    # > 0: the add/drop/swap search, restarted from the best records, adds one candidate; -1: 16 chains when F*N <= 256
     lns_k4_chains: int = 0        # > 0: a second population of chains that re-optimise four nodes per round
+    lns_polish: int = -12         # > 0: iterations of exact steepest descent (every single-pod change priced by the routing LP) from the best
+                                  # record; < 0: that many, but only for tiny instances (F*N <= 64); 0: never
     elites: int = 16              # chain records priced exactly (routing LP) per instance
 
 
@@ -107,6 +110,8 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
 
     lns_round, lns_ms, lns_diag = None, 0.0, None
     if use_lns:
+        if prm.lns_local_chains < 0:
+            prm = dataclasses.replace(prm, lns_local_chains=16 if inst.F * inst.N <= 256 else 0)
         lns_seeds = get_seeds() if (prm.lns_local_chains > 0 or guide is None) else None
         best_c, x, n, flags, scores, lns_round, lns_ms, lns_diag = lns_step1(inst, kind, prm, guide, lam0, lns_seeds, time_it=time_pdhg)
     else:
@@ -136,6 +141,53 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
                 break
     return BatchResult(best_c, x, n, flags, scores, lp_res, pdhg_ms, iters, dims, bytes_iter, path,
                        "lns" if use_lns else "local", lns_round, lns_ms, lns_diag)
+
+
+def polish_exact(inst: device.InstanceBatch, kind, alpha, c: torch.Tensor, max_iters: int = 12):
+    """Steepest descent over single-pod changes with EVERY neighbour priced exactly: all F*N flips (add / drop) and all
+    F*N*N moves of a pod to another node, `neptune_route_lp` on the whole batch of candidates per iteration (the
+    "thousands of candidate placements per launch" of the north star, with the routing LP as the evaluator).  For small
+    instances where most CPU rows bind: there the node prices of the search stall below the LP value and its records
+    are loose.  c uint8[B,F,N] -> improved c (same shape); memory is a slot count (lns_supported)."""
+    B, N, F = inst.B, inst.N, inst.F
+    dev = c.device
+    a_d, a_u = objective_weights(inst, kind, alpha)
+    slots = torch.floor(inst.Mj / inst.m[:, :1] + 1e-9).clamp_(max=float(F))                      # [B,N]
+    eye_fn = torch.eye(F * N, dtype=torch.uint8, device=dev).reshape(F * N, F, N)
+    # moves (f, j -> j2): index m = (f*N + j)*N + j2
+    fi, ji, j2i = torch.meshgrid(torch.arange(F, device=dev), torch.arange(N, device=dev), torch.arange(N, device=dev), indexing="ij")
+    fi, ji, j2i = fi.reshape(-1), ji.reshape(-1), j2i.reshape(-1)
+
+    def value(cands):
+        pr = device.route_lp(inst, cands.contiguous())
+        v = a_d[:, None] * pr["obj"] + a_u[:, None] * pr["n"].sum(dim=-1)
+        return torch.where(pr["status"] == 1, v, torch.full_like(v, float("inf")))
+
+    cur = c.clone()
+    cur_val = value(cur[:, None])[:, 0]
+    for _ in range(max_iters):
+        flips = cur[:, None] ^ eye_fn[None]                                                      # [B,FN,F,N]
+        moved = cur[:, None].expand(B, F * N * N, F, N).clone()
+        src_on = cur[:, fi, ji] > 0                                                              # [B,M]
+        dst_off = cur[:, fi, j2i] == 0
+        ok = src_on & dst_off & (ji != j2i)[None]
+        bidx = torch.arange(B, device=dev)[:, None].expand(B, F * N * N)
+        midx = torch.arange(F * N * N, device=dev)[None].expand(B, F * N * N)
+        moved[bidx[ok], midx[ok], fi[None].expand(B, -1)[ok], ji[None].expand(B, -1)[ok]] = 0
+        moved[bidx[ok], midx[ok], fi[None].expand(B, -1)[ok], j2i[None].expand(B, -1)[ok]] = 1
+        cands = torch.cat([flips, moved], dim=1)
+        # slot limits and coverage: an invalid candidate is replaced by the current placement (it cannot win)
+        bad = (cands.sum(dim=2).to(torch.float64) > slots[:, None, :]).any(dim=2) | (cands.sum(dim=3) == 0).any(dim=2)
+        cands = torch.where(bad[:, :, None, None], cur[:, None].expand_as(cands), cands)
+        vals = value(cands)
+        best, arg = vals.min(dim=1)
+        better = best < cur_val - 1e-9 * (1.0 + cur_val.abs())
+        if not bool(better.any()):
+            break
+        pick = cands[torch.arange(B, device=dev), arg]
+        cur = torch.where(better[:, None, None], pick, cur)
+        cur_val = torch.where(better, best, cur_val)
+    return cur, cur_val
 
 
 def objective_weights(inst: device.InstanceBatch, kind, alpha):
@@ -220,9 +272,14 @@ def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0,
     order = torch.argsort(val, dim=1, stable=True)
     ar = torch.arange(B, device=val.device)
     best_c = x = n = flags = scores = rnd = None
+    polished = None
+    if prm.lns_polish > 0 or (prm.lns_polish < 0 and F * N <= 64 and B * (F * N + F * N * N) <= 200000):
+        # tiny instances: exact steepest descent from the best priced record
+        start = elite[ar, order[:, 0]].contiguous()
+        polished, pval = polish_exact(inst, kind, prm.alpha, start, max_iters=abs(prm.lns_polish) if prm.lns_polish else 12)
     for rank in range(E):
         pick = order[:, rank]
-        cand = elite[ar, pick].contiguous()
+        cand = elite[ar, pick].contiguous() if not (rank == 0 and polished is not None) else polished
         fin = device.route_lp(inst, cand[:, None].contiguous(), want_x=True)
         cx, cc, cn = fin["x"][:, 0].contiguous(), fin["c_out"][:, 0].contiguous(), fin["n"][:, 0].contiguous()
         st = fin["status"][:, 0]

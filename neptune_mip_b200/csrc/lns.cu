@@ -343,7 +343,8 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
     // the state of a node depends only on the functions with a pod on it: a price is re-derived when the node is
     // overloaded, or when one of its functions changed pods (last apply) or was re-routed by another node's new price
     uint64_t dirty_now = dirtyF;
-    for (int pass = 0; pass < 4; ++pass) {
+    const int max_pass = N <= 32 ? 12 : 4;              // small instances with most CPU rows binding need more sweeps of the ascent
+    for (int pass = 0; pass < max_pass; ++pass) {
       for (int j = lane; j < N; j += 32) loadfx[j] = 0ull;
       __syncwarp();
       double up = 0.0;
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
         }
         unsigned todo = __ballot_sync(0xffffffffu, need);
         overloaded = overloaded || __any_sync(0xffffffffu, over);
-        if (pass == 3) continue;                           // last pass only evaluates
+        if (pass == max_pass - 1) continue;                // last pass only evaluates
         while (todo) {
           const int jj = jb + (__ffs(todo) - 1); todo &= todo - 1;
           int nf = 0;
