@@ -34,6 +34,8 @@ class BatchParams:
     lns_restart_pool: int = 16    # records a restart phase draws its start placements from
     lns_local_chains: int = -1    # > 0: the add/drop/swap search, restarted from the best records, adds one candidate; -1: 16 chains when F*N <= 256
     lns_k4_chains: int = 0        # > 0: a second population of chains that re-optimise four nodes per round
+    lns_final_k4: int = 0         # > 0: rounds of a final phase that restarts one 4-node chain from every record
+    lns_final_noise: float = 0.15 # its temperature, as a fraction of lns_noise
     lns_polish: int = -12         # > 0: iterations of exact steepest descent (every single-pod change priced by the routing LP) from the best
                                   # record; < 0: that many, but only for tiny instances (F*N <= 64); 0: never
     elites: int = 16              # chain records priced exactly (routing LP) per instance
@@ -244,6 +246,12 @@ def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0,
                 halves.append(torch.gather(rc, 1, top[:, :, None, None].expand(B, S, F, N)))
             pool = torch.cat(halves, dim=1).contiguous()
             population(prm.lns_chains, rounds, prm.lns_k, noise, prm.rng_seed + 7919 * ph, None, pool, round_offset=ph * rounds)
+    if prm.lns_final_k4 > 0:
+        # intensification: every record so far is the start of one chain that re-optimises FOUR nodes at a time, almost
+        # cold -- moves no three-node step can make
+        allc = torch.cat([records(True)[0], records(False)[0]], dim=1).contiguous()
+        population(allc.shape[1], prm.lns_final_k4, 4, prm.lns_noise * prm.lns_final_noise, prm.rng_seed + 15485863, None, allc,
+                   round_offset=prm.lns_rounds)
     ub_c, ub_g, ub_r, _ = records(True)
     lb_c, lb_g, lb_r, lb_u = records(False)
     # elites: the best records of either kind, half each (a lower and an upper bound do not rank against each other)

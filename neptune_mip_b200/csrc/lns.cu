@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
       const int i = ib + lane;
       double best = kLnsBig; int bj = 255;
       if (i < N) {
+#pragma unroll 2
         for (int q = 0; q < np; ++q) {
           const int j = pl[q];
           const double v = s_dT[j * N + i] + lam[j] * rf[j];
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
   uint8_t* outc2 = a.out_c + ((int64_t)b * 2 * a.chains + a.chains + chain) * fn;
   const int anneal_rounds = a.rounds - a.rounds / 8;
 
+  #pragma unroll 1
   for (int round = 0; round <= a.rounds; ++round) {
     // ---- neighbourhood: a random node and k-1 nodes near it (tournaments on d), or k random nodes ----------
     int kk = KK;
@@ -289,11 +291,13 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
       J[0] = (int)(((h0 & 0xffffffffull) * (uint64_t)N) >> 32);
       const bool local = ((h0 >> 40) & 3) != 0;
       int have = 1;
+      #pragma unroll 1
       for (int tries = 0; have < KK && tries < 16 * KK; ++tries) {
         int bj = -1; double bd = INFINITY;
         const uint64_t h = lns_next(rs);
         const int tsize = local ? 1 + (int)((h >> 50) & 3) : 1;
         uint64_t hh = h;
+        #pragma unroll 1
         for (int t = 0; t < tsize; ++t) {
           hh = lns_mix(hh + t);
           const int j = (int)(((hh & 0xffffffffull) * (uint64_t)N) >> 32);
@@ -344,10 +348,13 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
     // overloaded, or when one of its functions changed pods (last apply) or was re-routed by another node's new price
     uint64_t dirty_now = dirtyF;
     const int max_pass = N <= 32 ? 12 : 4;              // small instances with most CPU rows binding need more sweeps of the ascent
+    #pragma unroll 1
     for (int pass = 0; pass < max_pass; ++pass) {
+      #pragma unroll 1
       for (int j = lane; j < N; j += 32) loadfx[j] = 0ull;
       __syncwarp();
       double up = 0.0;
+      #pragma unroll 1
       for (int fi = lane; fi < fn; fi += 32) {
         const int bj = asg[fi];
         if (bj == 255) continue;
@@ -360,6 +367,7 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
       ucost = warp_sum(up);                              // delay of the whole-flow routing at the current prices
       __syncwarp();
       bool changed = false; overloaded = false;
+      #pragma unroll 1
       for (int jb = 0; jb < N; jb += 32) {
         const int j = jb + lane;
         bool need = false, over = false;
@@ -373,9 +381,11 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
         unsigned todo = __ballot_sync(0xffffffffu, need);
         overloaded = overloaded || __any_sync(0xffffffffu, over);
         if (pass == max_pass - 1) continue;                // last pass only evaluates
+        #pragma unroll 1
         while (todo) {
           const int jj = jb + (__ffs(todo) - 1); todo &= todo - 1;
           int nf = 0;
+          #pragma unroll 1
           for (int fb = 0; fb < F; fb += 32) {
             const int f = fb + lane;
             const bool on = f < F && c[f * N + jj];
@@ -388,6 +398,7 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
           // thresholds: a source whose nearest priced pod is not jj has that pod as its alternative; the sources
           // currently ON jj need their second-best pod -- a pod scan, done for the compacted list of them only
           double tot = 0.0; int nscan = 0;
+          #pragma unroll 1
           for (int tb = 0; tb < M; tb += 32) {
             const int t = tb + lane;
             bool scan = false;
@@ -408,11 +419,13 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
             nscan += __popc(bal);
           }
           __syncwarp();
+          #pragma unroll 1
           for (int e = lane; e < nscan; e += 32) {
             const int t = thl[e], z = t / N, i = t - z * N, f = fl[z];
             const double* rf = s_r + f * N; const uint8_t* pl = podlist + f * N; const int np = npods[f];
             const double rfj = rf[jj];
             double alt = kLnsBig;
+            #pragma unroll 1
             for (int q = 0; q < np; ++q) { const int j2 = pl[q]; if (j2 == jj) continue; const double v = s_dT[j2 * N + i] + lam[j2] * rf[j2]; if (v < alt) alt = v; }
             const double tq = (alt - s_dT[jj * N + i]) / rfj;
             if (tq >= 0.0) { th[t] = alt >= 0.5 * kLnsBig ? INFINITY : (float)fmin(tq, 1e30); tot += s_w[f * N + i] * rfj; }   // no other pod: cannot leave
@@ -422,13 +435,16 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
           double nl = 0.0;
           if (tot > s_K[jj] + 1e-9) {
             float last = -1.0f;
+            #pragma unroll 1
             for (int it = 0; it < M && tot > s_K[jj] + 1e-9; ++it) {
               unsigned mn = 0xffffffffu;
+              #pragma unroll 1
               for (int t = lane; t < M; t += 32) { const float tv = th[t]; if (tv > last) mn = min(mn, __float_as_uint(tv)); }
               mn = __reduce_min_sync(0xffffffffu, mn);
               if (mn >= 0x7f800000u) break;                 // nothing movable left: the node stays overloaded (never recorded)
               last = __uint_as_float(mn);
               double rem = 0.0;
+              #pragma unroll 1
               for (int t = lane; t < M; t += 32) if (th[t] == last) { const int z = t / N; rem += s_w[fl[z] * N + (t - z * N)] * s_r[fl[z] * N + jj]; }
               tot -= warp_sum(rem);
             }
@@ -440,6 +456,7 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
             changed = true;
             if (lane == 0) lam[jj] = nl;
             __syncwarp();
+            #pragma unroll 1
             for (int z = 0; z < nf; ++z) { scan_function(fl[z]); dirty_now |= F <= 64 ? 1ull << fl[z] : ~0ull; }   // their sources see a new price on jj
             __syncwarp();
           }
@@ -456,20 +473,25 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
     // LP afterwards (split flows), never be a mirage of loose prices.
     {
       double gp = 0.0;
+      #pragma unroll 1
       for (int fi = lane; fi < fn; fi += 32) { const double wv = s_w[fi]; if (wv > 0.0) gp += wv * (double)bestv[fi]; }
+      #pragma unroll 1
       for (int j = lane; j < N; j += 32) gp -= lam[j] * s_K[j];
       double g = warp_sum(gp), uval = ucost;
       if (u != 0.0) {
         int act = 0;
+        #pragma unroll 1
         for (int j = lane; j < N; j += 32) { int any = 0; for (int f = 0; f < F; ++f) any |= c[f * N + j]; act += any; }
         act = __reduce_add_sync(0xffffffffu, act);
         g += u * (double)act; uval += u * (double)act;
       }
       bool unserved = false;
+      #pragma unroll 1
       for (int fi = lane; fi < fn; fi += 32) unserved = unserved || asg[fi] == 255;
       unserved = __any_sync(0xffffffffu, unserved);
       if (!overloaded && !unserved && uval < bestu - 1e-9 * (1.0 + fabs(uval))) {
         bestu = uval; bestg = g; best_round = round;
+        #pragma unroll 1
         for (int q = lane; q < fn; q += 32) outc[q] = c[q];
       }
       // second record, by the lower bound: where the optimal routing splits flows, g is the LP value and the whole-flow
@@ -477,6 +499,7 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
       // Only with settled prices; both records are priced exactly by the caller.
       if (!overloaded && !unserved && settled && g < bestg2 - 1e-9 * (1.0 + fabs(g))) {
         bestg2 = g; bestu2 = uval; best_round2 = round;
+        #pragma unroll 1
         for (int q = lane; q < fn; q += 32) outc2[q] = c[q];
       }
     }
@@ -485,6 +508,7 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
 
     // ---- sources served from the k nodes: their nearest pod OUTSIDE the k nodes (compacted list, then a scan) ------
     int nex = 0;
+    #pragma unroll 1
     for (int fb = 0; fb < fn; fb += 32) {
       const int fi = fb + lane;
       const bool ex = fi < fn && asg[fi] != 255 && inJ(asg[fi]);
@@ -493,10 +517,12 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
       nex += __popc(bal);
     }
     __syncwarp();
+    #pragma unroll 1
     for (int e = lane; e < nex; e += 32) {
       const int fi = exl[e], f = fi / N, i = fi - f * N;
       const uint8_t* pl = podlist + f * N; const double* rf = s_r + f * N; const int np = npods[f];
       double best = kLnsBig; int bj = 255;
+      #pragma unroll 1
       for (int q = 0; q < np; ++q) {
         const int j = pl[q];
         if (inJ(j)) continue;
@@ -514,6 +540,7 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
     int Jr[KK];
 #pragma unroll
     for (int q = 0; q < KK; ++q) Jr[q] = q < kk ? Jn[q] : 0;
+    #pragma unroll 1
     for (int f = lane; f < F; f += 32) {
       int ot = 0;
 #pragma unroll
@@ -521,6 +548,7 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
       oldT[f] = (uint8_t)ot;
     }
     __syncwarp();
+    #pragma unroll 1
     for (int f = 0; f < F; ++f) {
       double pj[KK];
 #pragma unroll
@@ -528,6 +556,7 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
       double acc[NT];
 #pragma unroll
       for (int t = 0; t < NT; ++t) acc[t] = 0.0;
+      #pragma unroll 1
       for (int ib = 0; ib < N; ib += 32) {
         const int i = ib + lane;
         if (i >= N) continue;
@@ -557,21 +586,27 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
 
     // ---- DP over functions, state = slot counters of the k nodes -----------------------------------------------
     const int S_ = misc[32];
+    #pragma unroll 1
     for (int T = lane; T < NT; T += 32) { int s = 0; for (int q = 0; q < kk; ++q) if ((T >> q) & 1) s += mul[q]; incT[T] = s; }
+    #pragma unroll 1
     for (int s = lane; s < S_; s += 32) {
       int supp = 0;
+      #pragma unroll 1
       for (int q = 0; q < kk; ++q) if ((s / mul[q]) % rad[q] > 0) supp |= 1 << q;
       suppT[s] = (uint8_t)supp;
       cur[s] = s == 0 ? 0.0 : INFINITY;
     }
     __syncwarp();
     double* pc = cur; double* pn = nxt;
+    #pragma unroll 1
     for (int f = 0; f < F; ++f) {
       const double* ct = costT + f * NT;
+      #pragma unroll 1
       for (int s2 = lane; s2 < S_; s2 += 32) {
         const int supp = suppT[s2];
         double best = INFINITY; int bt = 0;
         int Ts = supp;
+        #pragma unroll 1
         while (true) {
           const double v = pc[s2 - incT[Ts]] + ct[Ts];
           if (v < best) { best = v; bt = Ts; }
@@ -585,11 +620,13 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
     }
     // best final state (utilisation: an empty node costs nothing, a used one u)
     double bv = INFINITY; int bs = 0x7fffffff;
+    #pragma unroll 1
     for (int s = lane; s < S_; s += 32) {
       double v = pc[s];
       if (u != 0.0) v += u * (double)__popc((unsigned)suppT[s]);
       if (v < bv) { bv = v; bs = s; }
     }
+    #pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) {
       const double v2 = __shfl_xor_sync(0xffffffffu, bv, o); const int s2 = __shfl_xor_sync(0xffffffffu, bs, o);
       if (v2 < bv || (v2 == bv && s2 < bs)) { bv = v2; bs = s2; }
@@ -597,13 +634,16 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
     if (lane == 0) {
       if (bv < INFINITY) {
         int s = bs;
+        #pragma unroll 1
         for (int f = F - 1; f >= 0; --f) { const int Tc = choice[f * smax + s]; newT[f] = (uint8_t)Tc; s -= incT[Tc]; }
       } else {
+        #pragma unroll 1
         for (int f = 0; f < F; ++f) newT[f] = oldT[f];
       }
     }
     __syncwarp();
     // ---- apply: pods of the k nodes, then the nearest pod of every source of the functions that use them ---------
+    #pragma unroll 1
     for (int f = 0; f < F; ++f) {
       const int nt_ = newT[f], ot_ = oldT[f];
       if (nt_ != ot_) {
@@ -616,6 +656,7 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
       double pj[KK];
 #pragma unroll
       for (int q = 0; q < KK; ++q) pj[q] = q < kk ? lam[Jr[q]] * s_r[f * N + Jr[q]] : kLnsBig;
+      #pragma unroll 1
       for (int ib = 0; ib < N; ib += 32) {
         const int i = ib + lane;
         if (i >= N) continue;

@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--local", type=int, default=0)
     ap.add_argument("--dump", default="")
     ap.add_argument("--k4", type=int, default=0)
+    ap.add_argument("--final-k4", type=int, default=0)
+    ap.add_argument("--final-noise", type=float, default=0.15)
     ap.add_argument("--lp-iters", type=int, default=20000)
     ap.add_argument("--no-cut", action="store_true")
     ap.add_argument("--search", default="auto")
@@ -43,7 +45,7 @@ def main():
     datas = [data_to_solver_input(synth.config_payload(a.config, s), 1, with_db=False) for s in seeds]
     inst = device.InstanceBatch.from_datas(datas)
     prm = BatchParams(lp_iters=a.lp_iters, lp_check_every=256, lns_chains=a.chains, lns_rounds=a.rounds, lns_k=a.k,
-                      lns_noise=a.noise, elites=a.elites, lns_phases=a.phases, lns_cooling=a.cooling, lns_restart_pool=a.pool, lns_local_chains=a.local, lns_k4_chains=a.k4, lp_cut=not a.no_cut, search=a.search, rng_seed=a.rng,
+                      lns_noise=a.noise, elites=a.elites, lns_phases=a.phases, lns_cooling=a.cooling, lns_restart_pool=a.pool, lns_local_chains=a.local, lns_k4_chains=a.k4, lns_final_k4=a.final_k4, lns_final_noise=a.final_noise, lp_cut=not a.no_cut, search=a.search, rng_seed=a.rng,
                       chains=16, sweeps=400)
     for rep in range(a.repeat):
         prm.rng_seed = a.rng + rep
