@@ -25,8 +25,8 @@ class BatchParams:
     rng_seed: int = 1
     search: str = "auto"          # "auto": slot-count LNS (csrc/lns.cu) where it applies, else the add/drop/swap search; "local": always the latter
     lp_cut: bool = True           # relax with the Chvatal-Gomory rounding of the memory rows (one memory size per instance)
-    lns_chains: int = 32          # warp-sized chains per instance
-    lns_rounds: int = 6000        # k-node re-optimisations per chain
+    lns_chains: int = 96          # warp-sized chains per instance
+    lns_rounds: int = 20000       # k-node re-optimisations per chain
     lns_k: int = 3
     lns_noise: float = 0.1
     lns_phases: int = 1           # > 1: population restarts from the best records between phases (lns_rounds is the total)
@@ -34,11 +34,11 @@ class BatchParams:
     lns_restart_pool: int = 16    # records a restart phase draws its start placements from
     lns_local_chains: int = -1    # > 0: the add/drop/swap search, restarted from the best records, adds one candidate; -1: 16 chains when F*N <= 256
     lns_k4_chains: int = 0        # > 0: a second population of chains that re-optimise four nodes per round
-    lns_final_k4: int = 0         # > 0: rounds of a final phase that restarts one 4-node chain from every record
-    lns_final_noise: float = 0.15 # its temperature, as a fraction of lns_noise
+    lns_final_k4: int = 3000      # > 0: rounds of a final phase that restarts one 4-node chain from every record
+    lns_final_noise: float = 0.3  # its temperature, as a fraction of lns_noise
     lns_polish: int = -12         # > 0: iterations of exact steepest descent (every single-pod change priced by the routing LP) from the best
                                   # record; < 0: that many, but only for tiny instances (F*N <= 64); 0: never
-    elites: int = 16              # chain records priced exactly (routing LP) per instance
+    elites: int = 32              # chain records priced exactly (routing LP) per instance
 
 
 @dataclass

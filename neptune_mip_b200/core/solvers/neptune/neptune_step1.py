@@ -21,12 +21,12 @@ class NeptuneStepBase(GpuStepMixin, Solver):
     it, so it is off by default (C4 would need 2 x 38 GB for it)."""
 
     def __init__(self, chains: int = 64, sweeps: int = 300, lp_iters: int = 20000, rng_seed: int = 1,
-                 keep_model: bool = False, lns_chains: int = 256, lns_rounds: int = 6000, lns_k: int = 3,
-                 lns_noise: float = 0.06, elites: int = 16, search: str = "auto", **kwargs):
+                 keep_model: bool = False, lns_chains: int = 384, lns_rounds: int = 8000, lns_k: int = 3,
+                 lns_noise: float = 0.1, lns_final_k4: int = 1500, elites: int = 32, search: str = "auto", **kwargs):
         super().__init__(**kwargs)
         self.chains, self.sweeps, self.lp_iters, self.rng_seed = chains, sweeps, lp_iters, rng_seed
         self.lns_chains, self.lns_rounds, self.lns_k, self.lns_noise = lns_chains, lns_rounds, lns_k, lns_noise
-        self.elites, self.search = elites, search
+        self.elites, self.search, self.lns_final_k4 = elites, search, lns_final_k4
         self.keep_model = keep_model
         self.model = None
         self.lp_bound = None
@@ -60,7 +60,7 @@ class NeptuneStep1CPUBase(NeptuneStepBase):
         prm = BatchParams(kind=self.kind, alpha=self._alpha(), lp_iters=self.lp_iters, lp_check_every=256,
                           chains=self.chains, sweeps=self.sweeps, rng_seed=self.rng_seed, search=self.search,
                           lns_chains=self.lns_chains, lns_rounds=self.lns_rounds, lns_k=self.lns_k,
-                          lns_noise=self.lns_noise, elites=self.elites)
+                          lns_noise=self.lns_noise, elites=self.elites, lns_final_k4=self.lns_final_k4)
         res = solve_batch(self.inst, prm)
         self._take(res.c, res.x, res.n, res.flags, res.scores)
         if res.lp is not None:

@@ -32,7 +32,7 @@ def test_c2_objectives_against_the_proven_optima():
     larger budget)."""
     gold = _gold("C2")
     seeds = sorted(gold)
-    inst, res = _solve("C2", seeds, lns_chains=128, lns_rounds=12000, lns_noise=0.1, elites=32)
+    inst, res = _solve("C2", seeds, lns_chains=96, lns_rounds=12000, lns_noise=0.1, elites=32, lns_final_k4=2000)
     assert res.search_path == "lns"
     flags = res.flags.cpu().numpy()
     delay = res.scores[:, 0].cpu().numpy()
@@ -110,7 +110,7 @@ def test_c5_sweep_subsample_against_the_proven_optima():
     heavy flow (whole-flow value 15 % above the LP value) or need a C1b row in the routing LP."""
     gold = _gold("C5")
     seeds = sorted(gold)[:64]
-    inst, res = _solve("C5", seeds, lns_chains=32, lns_rounds=2000, lns_noise=0.1, elites=16)
+    inst, res = _solve("C5", seeds, lns_chains=32, lns_rounds=2000, lns_noise=0.1, elites=16, lns_final_k4=0, lns_local_chains=0)
     delay = res.scores[:, 0].cpu().numpy()
     assert (res.flags.cpu().numpy() == 63).all()
     gaps = np.array([(delay[k] - gold[s]["objective"]) / gold[s]["objective"] for k, s in enumerate(seeds)])
