@@ -926,8 +926,22 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
   if (workspace_bytes < need) return NEPTUNE_E_NOMEM;
   if ((int64_t)B * make_geo(N, F, B).tiles_inst >= (int64_t)INT32_MAX) return NEPTUNE_E_SIZE;
   cudaStream_t caller = (cudaStream_t)stream;
-  cudaStream_t s = nullptr;
-  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // side stream, events, graph: released on EVERY return path (an error between BeginCapture and EndCapture also
+  // ends the capture, so the side stream is never left capturing)
+  struct Guard {
+    cudaStream_t s = nullptr; cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr; bool capturing = false;
+    ~Guard() {
+      if (capturing && s) { cudaGraph_t g = nullptr; cudaStreamEndCapture(s, &g); if (g) cudaGraphDestroy(g); }
+      if (gexec) cudaGraphExecDestroy(gexec);
+      if (graph) cudaGraphDestroy(graph);
+      if (ev_in) cudaEventDestroy(ev_in);
+      if (ev_out) cudaEventDestroy(ev_out);
+      if (s) cudaStreamDestroy(s);
+    }
+  } guard;
+  cudaStream_t& s = guard.s;
+  cudaEvent_t& ev_in = guard.ev_in; cudaEvent_t& ev_out = guard.ev_out;
   NEPTUNE_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   NEPTUNE_CUDA_OK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
   NEPTUNE_CUDA_OK(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
@@ -976,17 +990,19 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
   // `inner` iterations = {small(POST unless first of the chunk, PREC, Y2); pass} captured once and replayed;
   // the chunk ends with small(POST).  Step sizes, restart flags and convergence live in device memory.
   const int inner = check_every < 32 ? check_every : 32;
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t gexec = nullptr;
+  cudaGraph_t& graph = guard.graph;
+  cudaGraphExec_t& gexec = guard.gexec;
   int64_t per_graph = 0;
   {
     int64_t c0 = 0, c1 = 0;
     neptune_launch_count(&c0, 0);
     NEPTUNE_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    guard.capturing = true;
     for (int k = 0; k < inner; ++k) {
       mf_launch_small(P, PH_POST | PH_PREC | PH_Y2, k == 0 ? d_flag + 1 : nullptr);
       mf_launch_iter(P);
     }
+    guard.capturing = false;
     NEPTUNE_CUDA_OK(cudaStreamEndCapture(s, &graph));
     NEPTUNE_CUDA_OK(cudaGraphInstantiate(&gexec, graph, 0));
     neptune_launch_count(&c1, 0);
@@ -995,27 +1011,28 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
   }
   int h_flag = 0;
   for (int it = 0; it < max_iters && !h_flag; it += check_every) {
+    const int chunk = check_every < max_iters - it ? check_every : max_iters - it;      // the last chunk stops at max_iters
     int done = 0;
     bool first = true;
-    for (; done + inner <= check_every; done += inner) {
+    for (; done + inner <= chunk; done += inner) {
       NEPTUNE_CUDA_OK(cudaMemsetAsync(d_flag + 1, first ? 1 : 0, 1, s));     // int 1 / 0 (little endian)
       NEPTUNE_CUDA_OK(cudaGraphLaunch(gexec, s));
       NEPTUNE_COUNT(per_graph);
       first = false;
     }
-    for (; done < check_every; ++done) {
+    for (; done < chunk; ++done) {
       mf_launch_small(P, (first ? 0 : PH_POST) | PH_PREC | PH_Y2, nullptr);
       mf_launch_iter(P);
       first = false;
     }
     mf_launch_small(P, PH_POST, nullptr);
-    { k_ctl_advance<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, check_every); NEPTUNE_COUNT(1); }
+    { k_ctl_advance<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, chunk); NEPTUNE_COUNT(1); }
     // KKT of the current iterate and of the running average
     for (int wch = 0; wch < 2; ++wch) {
       mf_launch_eval(P, wch, 0);
       { k_mf_eval_small<<<B, 256, 0, s>>>(G, P.in, P.st, ctl, wch); NEPTUNE_COUNT(1); }
     }
-    { k_ctl_decide<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, check_every, prm->eps_abs, prm->eps_rel, max_iters,
+    { k_ctl_decide<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, chunk, prm->eps_abs, prm->eps_rel, max_iters,
                                                  result_d); NEPTUNE_COUNT(1); }
     { k_mf_apply_restart<<<dim3(kMfRestartBlocks, B), 256, 0, s>>>(G, P.in, P.st, xres, yres, ctl, part); NEPTUNE_COUNT(1); }
     { k_mf_restart_norms<<<(B + 127) / 128, 128, 0, s>>>(B, kMfRestartBlocks, part, ctl); NEPTUNE_COUNT(1); }
@@ -1025,15 +1042,11 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
     NEPTUNE_CUDA_OK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, s));
     NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
   }
-  cudaGraphExecDestroy(gexec);
-  cudaGraphDestroy(graph);
   NEPTUNE_LAUNCH_OK();
   NEPTUNE_CUDA_OK(cudaEventRecord(ev_out, s));
   NEPTUNE_CUDA_OK(cudaStreamWaitEvent(caller, ev_out, 0));
   NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
-  cudaEventDestroy(ev_in); cudaEventDestroy(ev_out);
-  cudaStreamDestroy(s);
-  return 0;
+  return 0;          // `guard` releases the graph, its exec, the events and the side stream
 }
 
 // ===================================================================================================
