@@ -212,6 +212,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
+    device.lns_block_mode(args.lns_block_mode)
 
     B = args.batch
     prm = BatchParams(kind="min_delay", lp_iters=args.lp_iters, lp_check_every=256, chains=args.chains, sweeps=args.sweeps,
@@ -476,6 +477,8 @@ def main():
     ap.add_argument("--lns-phases", type=int, default=1)
     ap.add_argument("--lns-final-k4", type=int, default=3000, help="rounds of the final phase: one 4-node chain restarted from every record")
     ap.add_argument("--elites", type=int, default=32)
+    ap.add_argument("--lns-block-mode", type=int, default=0, choices=[0, 1, 2],
+                    help="chains per block of the search kernel: 0 automatic, 1 = 8, 2 = 12 (same results)")
     ap.add_argument("--chains", type=int, default=8, help="add/drop/swap search (--search local)")
     ap.add_argument("--sweeps", type=int, default=400)
     ap.add_argument("--e2e-steps", type=int, default=2, help="steps of the end-to-end leg (at most --steps)")

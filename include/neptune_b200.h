@@ -308,6 +308,10 @@ int neptune_lns_search(int B, int N, int F, int kind, double alpha, int chains, 
                        const double* guide, const double* lam0, int S, const uint8_t* seeds,
                        int max_slots /* >= max_j floor(Mj / m), or 0 for F: sizes the shared-memory scratch */,
                        uint8_t* out_c, double* out_g, double* out_lb, int32_t* out_round, void* stream);
+/* chains per thread block of neptune_lns_search: 0 (default) = 8 while all blocks are resident at once, 12 (at 80
+ * registers) beyond; 1 = always 8; 2 = always 12.  The results do not depend on it (a chain's random stream is a
+ * function of its index only); it is a tuning and measurement switch. */
+int neptune_lns_block_mode(int mode);
 
 /* ---- (d) EFTTC greedy -----------------------------------------------------------------------------
  * Replaces `EfttcStepBase.solve()` (`core/solvers/efttc/efttc_step1.py:39-90` and helpers

@@ -45,7 +45,10 @@ struct LnsArgs {
 constexpr double kLnsBig = 1e9;                 // priced delay of "no pod"
 constexpr double kFxScale = 1073741824.0;       // 2^30: CPU loads are accumulated in fixed point (integer adds commute)
 constexpr int kLnsMaxK = 4;
-constexpr int kLnsMaxWarps = 8;                 // chains per block: two blocks of 8 warps per SM at 128 registers (12 warps at 80 registers measured 10 % slower)
+// chains per block: two blocks per SM, either 8 warps at 128 registers or 12 warps at 80 registers.  A chain-round is
+// 3-10 % slower at 80 registers, so 8 is used while all blocks are resident at once (2 * 148); beyond that the 24
+// resident warps per SM of the 12-warp build win (the kernel is latency-bound: 30 % issue-active at 16 warps per SM).
+constexpr int kLnsWarps = 8, kLnsWarpsWide = 12;
 
 __device__ __forceinline__ uint64_t lns_mix(uint64_t z) {        // splitmix64 finaliser
   z += 0x9E3779B97F4A7C15ull;
@@ -104,8 +107,8 @@ __device__ __forceinline__ double lns_multi_reduce(double (&acc)[NT], int lane) 
   return v;
 }
 
-template <int KK>
-__global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
+template <int KK, int WPB>
+__global__ void __launch_bounds__(WPB * 32, 2) k_lns(LnsArgs a) {
   constexpr int NT = 1 << KK;
   const int N = a.N, F = a.F, b = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int chain = blockIdx.x * a.wpb + wid;
@@ -685,6 +688,13 @@ __global__ void __launch_bounds__(kLnsMaxWarps * 32, 2) k_lns(LnsArgs a) {
 
 using namespace neptune;
 
+static int g_lns_block_mode = 0;      // 0: by the number of blocks, 1: always 8 chains per block, 2: always 12
+extern "C" int neptune_lns_block_mode(int mode) {
+  if (mode < 0 || mode > 2) return NEPTUNE_E_ARG;
+  g_lns_block_mode = mode;
+  return 0;
+}
+
 extern "C" int neptune_lns_search(int B, int N, int F, int kind, double alpha, int chains, int rounds, int k,
                                   double noise_coef, uint64_t rng_seed, const double* d, const double* w,
                                   const double* r, const double* m, const double* Mj, const double* Kj,
@@ -705,25 +715,32 @@ extern "C" int neptune_lns_search(int B, int N, int F, int kind, double alpha, i
   // states of the slot counters: (slots+1)^k for the common 3-slot nodes, capped by shared memory
   int smax = 1; for (int q = 0; q < k; ++q) smax *= 4;
   const size_t blk = (lns_block_shared(N, F) + 15) & ~(size_t)15;
-  int wpb = kLnsMaxWarps;
   a.maxslots = (max_slots > 0 && max_slots < F) ? max_slots : F;       // bound on floor(Mj / m) the caller vouches for (sizes the scratch)
-  size_t per = lns_warp_shared(N, F, k, smax, a.maxslots);
-  while (wpb > 1 && blk + wpb * per > 112 * 1024) --wpb;              // two blocks per SM (227 KB, 1 KB reserved per block)
+  const size_t per = lns_warp_shared(N, F, k, smax, a.maxslots);
+  const int wide_mode = g_lns_block_mode;
+  const size_t budget = 112 * 1024;                                     // two blocks per SM (228 KB, 1 KB reserved per block)
+  int wpb = kLnsWarps;
+  const int64_t blocks8 = (int64_t)B * ((chains + kLnsWarps - 1) / kLnsWarps);
+  const bool wide = blocks8 > 2 * kNumSMs && blk + kLnsWarpsWide * per <= budget && !(wide_mode & 1);
+  if (wide || (wide_mode & 2)) wpb = kLnsWarpsWide;
+  const int cap = wpb;
+  while (wpb > 1 && blk + wpb * per > budget) --wpb;
   if (blk + wpb * per > 200 * 1024) return NEPTUNE_E_SIZE;
   if (wpb > chains) wpb = chains;
   a.smax = smax; a.wpb = wpb;
   const size_t sm = blk + wpb * per;
   const dim3 grid((chains + wpb - 1) / wpb, B);
-  if (k == 3) {
-    NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_lns<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_lns<3><<<grid, wpb * 32, sm, (cudaStream_t)stream>>>(a);
-  } else if (k == 4) {
-    NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_lns<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_lns<4><<<grid, wpb * 32, sm, (cudaStream_t)stream>>>(a);
+#define NEPTUNE_LNS_LAUNCH(KK_, W_)                                                                                   \
+  do {                                                                                                                \
+    NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_lns<KK_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));     \
+    k_lns<KK_, W_><<<grid, wpb * 32, sm, (cudaStream_t)stream>>>(a);                                                  \
+  } while (0)
+  if (cap == kLnsWarpsWide) {
+    if (k == 3) NEPTUNE_LNS_LAUNCH(3, kLnsWarpsWide); else if (k == 4) NEPTUNE_LNS_LAUNCH(4, kLnsWarpsWide); else NEPTUNE_LNS_LAUNCH(2, kLnsWarpsWide);
   } else {
-    NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_lns<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_lns<2><<<grid, wpb * 32, sm, (cudaStream_t)stream>>>(a);
+    if (k == 3) NEPTUNE_LNS_LAUNCH(3, kLnsWarps); else if (k == 4) NEPTUNE_LNS_LAUNCH(4, kLnsWarps); else NEPTUNE_LNS_LAUNCH(2, kLnsWarps);
   }
+#undef NEPTUNE_LNS_LAUNCH
   NEPTUNE_COUNT(1);
   NEPTUNE_LAUNCH_OK();
   return 0;

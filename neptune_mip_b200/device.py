@@ -394,6 +394,12 @@ def lns_supported(inst: InstanceBatch, kind) -> bool:
     return bool((inst.m == inst.m[:, :1]).all()) and bool((inst.m > 0).all())
 
 
+def lns_block_mode(mode: int) -> None:
+    """Chains per block of `lns_search`: 0 automatic (8, or 12 when the blocks of 8 would not all be resident), 1 = 8,
+    2 = 12.  Same results either way."""
+    check(_lib.load().neptune_lns_block_mode(int(mode)), "neptune_lns_block_mode")
+
+
 def lns_search(inst: InstanceBatch, kind, alpha=0.5, chains=32, rounds=4000, k=3, noise_coef=0.06, rng_seed=1,
                guide: Optional[torch.Tensor] = None, lam0: Optional[torch.Tensor] = None,
                seeds_u8: Optional[torch.Tensor] = None):
