@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(256) k_route_cap(int N, int F, const double* _
   const CapResult cr = cap_route(q, 4 * N + 16, red, sh);
   uint8_t* cout = cout0 + b * fn;
   double* x = x0 + (int64_t)b * N * fn;
-  for (int64_t k = tid; k < (int64_t)N * fn; k += blockDim.x) x[k] = 0.0;
+  // x arrives zero-filled (cudaMemsetAsync in the launcher: one block per instance cannot fill 6.4 GB at C4)
   for (int64_t k = tid; k < fn; k += blockDim.x) cout[k] = q.c[k];
   __syncthreads();
   if (cr.feasible) {
@@ -372,6 +372,7 @@ extern "C" int neptune_route_capacitated(int B, int N, int F, const double* d, c
   stride = (stride + 255) & ~(int64_t)255;
   char* ws = nullptr;
   NEPTUNE_CUDA_OK(cudaMallocAsync(&ws, (size_t)stride * B, s));
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(x, 0, (size_t)B * N * fn * 8, s));
   { k_route_cap<<<B, 256, 0, s>>>(N, F, d, w, r, Kj, c, c_out, x, n, obj_out, feas_out, ws, stride); NEPTUNE_COUNT(1); }
   NEPTUNE_LAUNCH_OK();
   NEPTUNE_CUDA_OK(cudaFreeAsync(ws, s));
