@@ -145,50 +145,69 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
                        "lns" if use_lns else "local", lns_round, lns_ms, lns_diag)
 
 
-def polish_exact(inst: device.InstanceBatch, kind, alpha, c: torch.Tensor, max_iters: int = 12):
-    """Steepest descent over single-pod changes with EVERY neighbour priced exactly: all F*N flips (add / drop) and all
-    F*N*N moves of a pod to another node, `neptune_route_lp` on the whole batch of candidates per iteration (the
-    "thousands of candidate placements per launch" of the north star, with the routing LP as the evaluator).  For small
-    instances where most CPU rows bind: there the node prices of the search stall below the LP value and its records
-    are loose.  c uint8[B,F,N] -> improved c (same shape); memory is a slot count (lns_supported)."""
+def polish_exact(inst: device.InstanceBatch, kind, alpha, c: torch.Tensor, max_iters: int = 12, depth: int = 3,
+                 chunk: int = 4096):
+    """Steepest descent with EVERY neighbour priced exactly by the routing LP (`neptune_route_lp` on the whole batch
+    of candidates: the "thousands of candidate placements per launch" of the north star).  Neighbourhoods by size,
+    the next one only when the smaller ones hold no improvement: all single pod flips (add / drop), all PAIRS of flips
+    (moves of a pod, swaps of two functions on a node, two adds, ...), all TRIPLES.  For small instances where most
+    CPU rows bind: there the node prices of the search stall below the LP value, its records are loose, and the
+    optimum is one or two coupled changes away (a pod swap on a full node plus the re-routing it allows).
+    c uint8[B,F,N] -> (improved c, its exact value [B]); memory is a slot count (lns_supported)."""
     B, N, F = inst.B, inst.N, inst.F
+    FN = F * N
     dev = c.device
     a_d, a_u = objective_weights(inst, kind, alpha)
     slots = torch.floor(inst.Mj / inst.m[:, :1] + 1e-9).clamp_(max=float(F))                      # [B,N]
-    eye_fn = torch.eye(F * N, dtype=torch.uint8, device=dev).reshape(F * N, F, N)
-    # moves (f, j -> j2): index m = (f*N + j)*N + j2
-    fi, ji, j2i = torch.meshgrid(torch.arange(F, device=dev), torch.arange(N, device=dev), torch.arange(N, device=dev), indexing="ij")
-    fi, ji, j2i = fi.reshape(-1), ji.reshape(-1), j2i.reshape(-1)
+    # the tableau of such an instance is small: rows <= N + F*N + pods, a slab of 2^17 doubles per candidate is ample
+    slab = 1 << 17 if FN <= 64 else 1 << 19
+    ar = torch.arange(FN, device=dev)
+    masks = {}
+
+    def flip_masks(size):
+        if size not in masks:
+            comb = torch.combinations(ar, r=size) if size > 1 else ar[:, None]                    # [M,size]
+            mk = torch.zeros((comb.shape[0], FN), dtype=torch.uint8, device=dev)
+            mk.scatter_(1, comb, 1)
+            masks[size] = mk.reshape(-1, F, N)
+        return masks[size]
 
     def value(cands):
-        pr = device.route_lp(inst, cands.contiguous())
+        pr = device.route_lp(inst, cands.contiguous(), tableau_doubles=slab)
         v = a_d[:, None] * pr["obj"] + a_u[:, None] * pr["n"].sum(dim=-1)
         return torch.where(pr["status"] == 1, v, torch.full_like(v, float("inf")))
 
+    def best_of(cur, size):
+        mk = flip_masks(size)
+        best = torch.full((B,), float("inf"), dtype=torch.float64, device=dev)
+        pick = cur.clone()
+        for lo in range(0, mk.shape[0], chunk):
+            cands = cur[:, None] ^ mk[None, lo:lo + chunk]                                        # [B,M,F,N]
+            # slot limits and coverage: an invalid candidate is replaced by the current placement (it cannot win)
+            bad = (cands.sum(dim=2).to(torch.float64) > slots[:, None, :]).any(dim=2) | (cands.sum(dim=3) == 0).any(dim=2)
+            cands = torch.where(bad[:, :, None, None], cur[:, None].expand_as(cands), cands)
+            vals = value(cands)
+            v, arg = vals.min(dim=1)                                                              # first minimum: deterministic
+            take = v < best
+            pick = torch.where(take[:, None, None], cands[torch.arange(B, device=dev), arg], pick)
+            best = torch.where(take, v, best)
+        return best, pick
+
     cur = c.clone()
     cur_val = value(cur[:, None])[:, 0]
-    for _ in range(max_iters):
-        flips = cur[:, None] ^ eye_fn[None]                                                      # [B,FN,F,N]
-        moved = cur[:, None].expand(B, F * N * N, F, N).clone()
-        src_on = cur[:, fi, ji] > 0                                                              # [B,M]
-        dst_off = cur[:, fi, j2i] == 0
-        ok = src_on & dst_off & (ji != j2i)[None]
-        bidx = torch.arange(B, device=dev)[:, None].expand(B, F * N * N)
-        midx = torch.arange(F * N * N, device=dev)[None].expand(B, F * N * N)
-        moved[bidx[ok], midx[ok], fi[None].expand(B, -1)[ok], ji[None].expand(B, -1)[ok]] = 0
-        moved[bidx[ok], midx[ok], fi[None].expand(B, -1)[ok], j2i[None].expand(B, -1)[ok]] = 1
-        cands = torch.cat([flips, moved], dim=1)
-        # slot limits and coverage: an invalid candidate is replaced by the current placement (it cannot win)
-        bad = (cands.sum(dim=2).to(torch.float64) > slots[:, None, :]).any(dim=2) | (cands.sum(dim=3) == 0).any(dim=2)
-        cands = torch.where(bad[:, :, None, None], cur[:, None].expand_as(cands), cands)
-        vals = value(cands)
-        best, arg = vals.min(dim=1)
-        better = best < cur_val - 1e-9 * (1.0 + cur_val.abs())
-        if not bool(better.any()):
+    size, it = 1, 0
+    while it < max_iters and size <= depth:
+        if size == 3 and B * (FN ** 3) // 6 > 4_000_000:      # bounded work: triples only where they are cheap
             break
-        pick = cands[torch.arange(B, device=dev), arg]
-        cur = torch.where(better[:, None, None], pick, cur)
-        cur_val = torch.where(better, best, cur_val)
+        best, pick = best_of(cur, size)
+        better = best < cur_val - 1e-9 * (1.0 + cur_val.abs())
+        if bool(better.any()):
+            cur = torch.where(better[:, None, None], pick, cur)
+            cur_val = torch.where(better, best, cur_val)
+            size = 1
+            it += 1
+        else:
+            size += 1
     return cur, cur_val
 
 
@@ -281,7 +300,7 @@ def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0,
     ar = torch.arange(B, device=val.device)
     best_c = x = n = flags = scores = rnd = None
     polished = None
-    if prm.lns_polish > 0 or (prm.lns_polish < 0 and F * N <= 64 and B * (F * N + F * N * N) <= 200000):
+    if prm.lns_polish > 0 or (prm.lns_polish < 0 and F * N <= 64 and B * (F * N) ** 2 <= 400000):
         # tiny instances: exact steepest descent from the best priced record
         start = elite[ar, order[:, 0]].contiguous()
         polished, pval = polish_exact(inst, kind, prm.alpha, start, max_iters=abs(prm.lns_polish) if prm.lns_polish else 12)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE config 4 (2000 nodes x 200 functions) on ONE GPU: a checked placement and the bracket around it.
 
-  EFTTC placement (k_efttc) -> CPU-capacity-aware routing (k_route_cap) -> the reference's checkers (k_check)
+  EFTTC placement (k_efttc) -> nearest-pod routing (k_route) -> the reference's checkers (k_check)
   -> lower bound of the slot-cut LP relaxation after a bounded number of matrix-free PDHG iterations (the dual
      objective with the box terms is a valid bound at every iterate).
 
@@ -37,13 +37,18 @@ def record(n_nodes=2000, n_funcs=200, lp_iters=512, seed=0):
         return e0.elapsed_time(e1), out
 
     ms_e, (c, n_e, info) = timed(lambda: device.efttc(inst, "min_delay"))
-    ms_r, (c2, x, n, obj, feas) = timed(lambda: device.route_capacitated(inst, c))
+    # EFTTC's own routing is "every source to its nearest pod" with a global CPU check after every cycle
+    # (efttc_step1.py:196-212, utils/constraints_step1.py:70-80), so the nearest routing of its placement is CPU-feasible
+    ms_r, (x, n) = timed(lambda: device.route_placements(inst, c))
+    c2 = c
     ms_c, (flags, scores) = timed(lambda: device.check_solution(inst, x, device.u8_to_f64(c2), n))
     fl = int(flags.cpu()[0])
+    obj = scores[:, 0]
+    feas = torch.tensor([1 if (fl & (OK_HANDLE | OK_MEMORY | OK_CPU | OK_C_X | OK_N_C)) == (OK_HANDLE | OK_MEMORY | OK_CPU | OK_C_X | OK_N_C) else 0])
     names = {"handle_all_requests": OK_HANDLE, "memory": OK_MEMORY, "cpu": OK_CPU, "c_according_to_x": OK_C_X,
              "n_according_to_c": OK_N_C}
     rec = {"workload": f"C4: {n_nodes} nodes x {n_funcs} functions, one instance, one GPU",
-           "placement": "EFTTC (k_efttc) + CPU-capacity-aware routing (k_route_cap); the searches stop at N = 768 / 128",
+           "placement": "EFTTC (k_efttc) + nearest-pod routing (k_route), as EFTTC routes; the searches stop at N = 768 / 128",
            "pods": int(c2.sum().item()), "objective_min_delay": float(obj.cpu()[0]),
            "feasible": bool(int(feas.cpu()[0])), "checkers": {k: bool(fl & v) for k, v in names.items()},
            "ms": {"host_instance_build": 1e3 * t_build, "efttc": ms_e, "routing": ms_r, "checkers": ms_c},

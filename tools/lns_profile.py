@@ -22,3 +22,13 @@ for rep in range(2):
     e1.record(); e1.synchronize()
     print(f"B {B} chains {chains} rounds {rounds} k {k} mode {mode}: {e0.elapsed_time(e1):.1f} ms  "
           f"({1e3 * e0.elapsed_time(e1) / (B * chains * max(rounds, 1)):.3f} us per chain-round)  best {float(g[0].min()):.3f}")
+if os.environ.get("LNS_PER_INSTANCE"):
+    # the same chains, one instance per launch (12 blocks on 12 SMs): how much do the instances differ?
+    ts = []
+    for b in range(B):
+        one = device.InstanceBatch(B=1, N=N, F=F, budget=inst.budget, **{kk: getattr(inst, kk)[b:b + 1].contiguous() for kk in device.InstanceBatch.FIELDS})
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        device.lns_search(one, "min_delay", chains=chains, rounds=rounds, k=k, noise_coef=0.1, rng_seed=1, guide=guide[b:b + 1].contiguous(), lam0=lam0[b:b + 1].contiguous())
+        e1.record(); e1.synchronize(); ts.append(e0.elapsed_time(e1))
+    print("per-instance ms (one launch each):", [round(t, 1) for t in ts], "max/mean", round(max(ts) / (sum(ts) / len(ts)), 2))
