@@ -156,6 +156,20 @@ int neptune_pdhg_mf_solve(int B, int N, int F, int kind,
                           const neptune_pdhg_params* params_h,
                           double* x, double* y, neptune_pdhg_result* result_d,
                           void* workspace, int64_t workspace_bytes, void* stream);
+/* The same solver for the models with node columns n[j] (`NeptuneStep1CPUMinUtilization`,
+ * `NeptuneStep1CPUMinDelayAndUtilization`: reference core/solvers/neptune/neptune_step1.py:38-77): columns x, c, n;
+ * the rows above plus C5a (sum_f c[f,j] - M n[j] <= 0), C5b (sum_f c[f,j] - n[j] >= -eps) and C6
+ * (cost[j] n[j] <= budget) of utils/constraints_step1.py:69-80, 101-103 -- the canonical layout of
+ * neptune_assemble(kind, NEPTUNE_FLAG_STRENGTHEN).  The new rows and columns are O(N): they live in the small-vector
+ * kernel, the streaming pass is unchanged.  d_obj[B][N][N] is the delay matrix AS IT ENTERS THE OBJECTIVE
+ * (objectives.py:24-52): zeros for kind 1, d * (1 - alpha) / (largest workload-weighted delay) for kind 2; obj_n is
+ * the coefficient of every n[j] (1, or alpha / N).  Workspace: neptune_pdhg_mf_workspace_bytes. */
+int neptune_pdhg_mf_solve_util(int B, int N, int F, int kind, const double* d_obj, const double* w,
+                               const double* r, const double* m, const double* Mj, const double* Kj,
+                               const double* cost, double budget, double obj_n,
+                               const neptune_pdhg_params* prm, double* x, double* y,
+                               neptune_pdhg_result* result_d, void* workspace, int64_t workspace_bytes,
+                               void* stream);
 
 /* ---- (b, matrix-free, sharded) EXPERIMENTAL: step-wise building blocks of the matrix-free iteration for the
  * function-block-sharded solver (neptune_mip_b200/sharded_mf.py, one process per GPU).  Not yet

@@ -2,6 +2,8 @@
 model, assembly + CSR otherwise) -> EFTTC -> local search -> exact check in one go (what bench.py times, and what a sweep like BASELINE.json's config 5 calls)."""
 from __future__ import annotations
 
+import os
+
 import dataclasses
 from dataclasses import dataclass
 from typing import Optional
@@ -19,13 +21,14 @@ class BatchParams:
     alpha: float = 0.5
     lp_iters: int = 2048          # PDHG iterations on the strengthened relaxation (bound + rounding guide)
     lp_check_every: int = 256
-    lp_path: str = "auto"         # "auto": matrix-free PDHG for the min-delay model, assembled CSR otherwise; "csr": always CSR
+    lp_path: str = "auto"         # "auto": matrix-free PDHG (all three objectives); "csr": the assembled model through the CSR solver
     chains: int = 16              # local-search chains per instance (add/drop/swap search)
     sweeps: int = 200
     rng_seed: int = 1
     search: str = "auto"          # "auto": slot-count LNS (csrc/lns.cu) where it applies, else the add/drop/swap search; "local": always the latter
     lp_cut: bool = True           # relax with the Chvatal-Gomory rounding of the memory rows (one memory size per instance)
     lns_chains: int = 96          # warp-sized chains per instance
+    lns_fill_waves: bool = True   # raise the chain count (at most 1.5x) until the blocks of the search fill whole waves of the GPU
     lns_rounds: int = 20000       # k-node re-optimisations per chain
     lns_k: int = 3
     lns_noise: float = 0.1
@@ -73,15 +76,20 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
         X = F * N * N
         if time_pdhg:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if KINDS.get(kind, kind) == 0 and prm.lp_path != "csr":
-            # min-delay: the relaxation is solved matrix-free (nothing is assembled; every coefficient of the
-            # strengthened model is regenerated from d, w, r, m inside the iteration kernels)
-            rows, cols, nnz = device.model_sizes(N, F, 0, FLAG_STRENGTHEN)
+        if prm.lp_path != "csr":
+            # the relaxation is solved matrix-free (nothing is assembled; every coefficient of the strengthened model is
+            # regenerated from d, w, r, m inside the iteration kernels); the models with node columns n[j] add O(N) rows
+            # and columns that live in the small-vector kernel (neptune_pdhg_mf_solve_util)
+            kk = KINDS.get(kind, kind)
+            rows, cols, nnz = device.model_sizes(N, F, kk, FLAG_STRENGTHEN)
             if time_pdhg:
                 e0.record()
             xs, ys, lp_res = device.pdhg_mf_solve(inst_lp, max_iters=prm.lp_iters, check_every=prm.lp_check_every,
-                                                  eps_rel=1e-6, eps_abs=1e-9)
+                                                  eps_rel=1e-6, eps_abs=1e-9, kind=kk, alpha=prm.alpha)
             lam0 = ys[:, 3 * F * N + N:3 * F * N + 2 * N].contiguous()       # duals of the CPU rows C4
+            if kk == 2:      # the combined objective scales the delays: prices back in delay units for the search
+                a_d = objective_weights(inst, kind, prm.alpha)[0]
+                lam0 = lam0 / torch.where(a_d > 0, a_d, torch.ones_like(a_d))[:, None]
             bytes_iter, path = B * (64 * X + 112 * F * N + 8 * N * N), "matrix-free"
         else:
             lp = device.assemble(inst, kind, prm.alpha, flags=FLAG_STRENGTHEN)
@@ -145,6 +153,9 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
                        "lns" if use_lns else "local", lns_round, lns_ms, lns_diag)
 
 
+_DEBUG_SYNC = int(os.environ.get("NEPTUNE_DEBUG_SYNC", "0"))
+
+
 def polish_exact(inst: device.InstanceBatch, kind, alpha, c: torch.Tensor, max_iters: int = 12, depth: int = 3,
                  chunk: int = 4096):
     """Steepest descent with EVERY neighbour priced exactly by the routing LP (`neptune_route_lp` on the whole batch
@@ -173,7 +184,11 @@ def polish_exact(inst: device.InstanceBatch, kind, alpha, c: torch.Tensor, max_i
         return masks[size]
 
     def value(cands):
+        if _DEBUG_SYNC == 1:
+            torch.cuda.synchronize(); print("polish: before route_lp", tuple(cands.shape), flush=True)
         pr = device.route_lp(inst, cands.contiguous(), tableau_doubles=slab)
+        if _DEBUG_SYNC in (1, 2):
+            torch.cuda.synchronize(); print("polish: after route_lp", tuple(cands.shape), "status counts", torch.bincount(pr["status"].reshape(-1), minlength=3).tolist(), flush=True)
         v = a_d[:, None] * pr["obj"] + a_u[:, None] * pr["n"].sum(dim=-1)
         return torch.where(pr["status"] == 1, v, torch.full_like(v, float("inf")))
 
@@ -211,20 +226,18 @@ def polish_exact(inst: device.InstanceBatch, kind, alpha, c: torch.Tensor, max_i
     return cur, cur_val
 
 
-def objective_weights(inst: device.InstanceBatch, kind, alpha):
-    """(a_d[B], a_u[B]): objective = a_d * delay + a_u * active nodes (reference objectives.py:4-52)."""
-    k = KINDS.get(kind, kind)
-    one = torch.ones(inst.B, dtype=torch.float64, device=inst.d.device)
-    if k == 0:
-        return one, 0 * one
-    if k == 1:
-        return 0 * one, one
-    far = torch.where(inst.d[:, None, :, :] <= inst.maxd[:, :, None, None], inst.d[:, None, :, :],
-                      torch.full_like(inst.d[:, None, :, :], -float("inf"))).amax(dim=-1)          # [B,F,N]
-    wmax = (inst.w * far).sum(dim=(1, 2))
-    wsum = inst.w.sum(dim=(1, 2))
-    a_d = torch.where((wsum != 0) & (wmax != 0), (1.0 - alpha) / wmax, 0 * one)
-    return a_d, one * (alpha / inst.N)
+objective_weights = device.objective_weights      # (a_d[B], a_u[B]) of the three objectives
+
+
+def fill_waves(B: int, chains: int, chains_per_block: int = 8, resident_blocks: int = 2 * 148, cap: float = 1.5) -> int:
+    """Chains per instance that cost no extra time: the search kernel runs `chains_per_block` chains per block, two
+    blocks per SM, and every block of a launch takes about as long (measured: 32 instances x 96 chains = 384 blocks =
+    1.3 waves take as long as 48 x 96 = 576 blocks = 1.95 waves).  The count is raised to the largest one with the same
+    number of waves, at most `cap` times what was asked (a lone instance should not light up the whole GPU)."""
+    per_inst = -(-chains // chains_per_block)
+    waves = -(-(B * per_inst) // resident_blocks)
+    fit = (waves * resident_blocks) // B
+    return max(chains, min(fit * chains_per_block, int(cap * chains) // chains_per_block * chains_per_block))
 
 
 def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0, seeds, time_it=False):
@@ -236,6 +249,7 @@ def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0,
         e0.record()
     phases = max(1, prm.lns_phases)
     rounds = max(1, prm.lns_rounds // phases)
+    main_chains = fill_waves(B, prm.lns_chains) if prm.lns_fill_waves else prm.lns_chains
     pops = []                 # populations: dict(c, g, r, other, chains), records [0, chains) by upper bound, [chains, 2 chains) by lower
 
     def population(chains, n_rounds, k, noise, rng, guide_, seeds_, round_scale=1, round_offset=0):
@@ -251,7 +265,7 @@ def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0,
         if ph == 0:
             # start from roundings of the relaxation; optionally a second population that re-optimises four nodes at a
             # time (half as many, dearer rounds): it misses other instances than the three-node one does
-            population(prm.lns_chains, rounds, prm.lns_k, noise, prm.rng_seed, guide, seeds)
+            population(main_chains, rounds, prm.lns_k, noise, prm.rng_seed, guide, seeds)
             if prm.lns_k4_chains > 0:
                 population(prm.lns_k4_chains, max(1, rounds // 2), 4, noise, prm.rng_seed + 104729, guide, seeds, round_scale=2)
         else:
@@ -264,7 +278,7 @@ def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0,
                 _, top = torch.topk(rg, S, dim=1, largest=False)
                 halves.append(torch.gather(rc, 1, top[:, :, None, None].expand(B, S, F, N)))
             pool = torch.cat(halves, dim=1).contiguous()
-            population(prm.lns_chains, rounds, prm.lns_k, noise, prm.rng_seed + 7919 * ph, None, pool, round_offset=ph * rounds)
+            population(main_chains, rounds, prm.lns_k, noise, prm.rng_seed + 7919 * ph, None, pool, round_offset=ph * rounds)
     if prm.lns_final_k4 > 0:
         # intensification: every record so far is the start of one chain that re-optimises FOUR nodes at a time, almost
         # cold -- moves no three-node step can make
@@ -303,7 +317,11 @@ def lns_step1(inst: device.InstanceBatch, kind, prm: "BatchParams", guide, lam0,
     if prm.lns_polish > 0 or (prm.lns_polish < 0 and F * N <= 64 and B * (F * N) ** 2 <= 400000):
         # tiny instances: exact steepest descent from the best priced record
         start = elite[ar, order[:, 0]].contiguous()
+        if _DEBUG_SYNC in (1, 2, 3):
+            torch.cuda.synchronize(); print('before polish', flush=True)
         polished, pval = polish_exact(inst, kind, prm.alpha, start, max_iters=abs(prm.lns_polish) if prm.lns_polish else 12)
+        if _DEBUG_SYNC:
+            torch.cuda.synchronize(); print('polish done', flush=True)
     for rank in range(E):
         pick = order[:, rank]
         cand = elite[ar, pick].contiguous() if not (rank == 0 and polished is not None) else polished

@@ -39,10 +39,11 @@ constexpr int kGeoSeg = 1024;          // column segment used when balancing the
 struct MfGeo {
   int N, F, K, JT, ct, RT, rt, tiles_inst;
   int cti;                       // column segments of the iteration kernel in use (layout of P3i)
-  int64_t X, C, cols, rows, r2, r3, r4, rs;
+  int with_n;                    // node columns n[j] and rows C5a / C5b / C6 present (min-utilisation, combined objective)
+  int64_t X, C, cols, rows, r2, r3, r4, r5, r6, rs;
 };
 
-static MfGeo make_geo(int N, int F, int B) {
+static MfGeo make_geo(int N, int F, int B, int kind = NEPTUNE_KIND_MIN_DELAY) {
   MfGeo G;
   G.N = N; G.F = F;
   G.K = N <= 32 ? 1 : ((N & 1) == 0 || N <= 64 ? 2 : 4);        // columns per lane (even N: one pair of adjacent columns, 16-byte accesses)
@@ -64,13 +65,19 @@ static MfGeo make_geo(int N, int F, int B) {
   G.rt = (N + G.RT - 1) / G.RT;
   G.tiles_inst = F * G.rt * G.ct;
   G.cti = G.ct;
-  Layout L(N, F, NEPTUNE_KIND_MIN_DELAY, NEPTUNE_FLAG_STRENGTHEN);
+  Layout L(N, F, kind, NEPTUNE_FLAG_STRENGTHEN);
+  G.with_n = L.with_n;
   G.X = L.X; G.C = L.C; G.cols = L.cols; G.rows = L.rows;
-  G.r2 = L.r2; G.r3 = L.r3; G.r4 = L.r4; G.rs = L.rs;
+  G.r2 = L.r2; G.r3 = L.r3; G.r4 = L.r4; G.r5 = L.r5; G.r6 = L.r6; G.rs = L.rs;
   return G;
 }
 
-struct MfIn { const double *d, *w, *r, *m, *Mj, *Kj; };
+// d is the delay matrix AS IT ENTERS THE OBJECTIVE: the caller scales it for the combined objective ((1 - alpha) / the
+// largest workload-weighted delay, objectives.py:36-52) and passes zeros for min-utilisation; nothing else reads it.
+// cost / budget / objn (objective coefficient of every n[j]) are read only when the model has node columns.
+struct MfIn { const double *d, *w, *r, *m, *Mj, *Kj; const double* cost; double budget, objn; };
+
+constexpr double kMfBigM = 1e6;        // constraints_step1.py:1
 
 struct MfSt {
   double *x, *y, *xsum, *ysum;   // canonical vectors [B][cols] / [B][rows]
@@ -539,9 +546,10 @@ k_mf_small(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int mask, con
       if (prec) {
         const double sS = strided_sum(PS + po, rt, N);
         const double mf = m[f];
-        const double gc = -y1 + mf * y[G.r2 + j] - sS;
+        double gc = -y1 + mf * y[G.r2 + j] - sS;
+        if (G.with_n) gc += y[G.r5 + 2 * j] + y[G.r5 + 2 * j + 1];      // C5a, C5b carry every c[., j]
         const double co = c[q];
-        double cn = co - tau * gc / (1.0 + mf + (double)N);
+        double cn = co - tau * gc / ((G.with_n ? 3.0 : 1.0) + mf + (double)N);
         cn = fmin(fmax(cn, 0.0), 1.0);
         cbar[q] = 2.0 * cn - co;
         c[q] = cn; cs[q] += cn;
@@ -564,6 +572,39 @@ k_mf_small(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int mask, con
       const double vv = y[G.r2 + j] + s * a;
       const double yn = vv - s * fmin(vv / s, Mj[j]);             // C2: (-inf, Mj]
       y[G.r2 + j] = yn; ys[G.r2 + j] += yn;
+      if (G.with_n) {
+        // node column n[j] from the duals of the previous iteration, then the three rows that see only (c, n)
+        double a5 = 0.0;
+        for (int f0 = 0; f0 < F; f0 += 8) {
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = (f0 + u < F) ? cbar[(int64_t)(f0 + u) * N + j] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) a5 += v[u];
+        }
+        double* __restrict__ nv = st.x + (int64_t)b * G.cols + G.X + C;
+        double* __restrict__ ns = st.xsum + (int64_t)b * G.cols + G.X + C;
+        const double cj = in.cost[(int64_t)b * N + j];
+        const double y5a = y[G.r5 + 2 * j], y5b = y[G.r5 + 2 * j + 1], y6 = y[G.r6 + j];
+        const double gn = in.objn - kMfBigM * y5a - y5b + cj * y6;
+        const double no = nv[j];
+        double nn = no - tau * gn / (kMfBigM + 1.0 + fabs(cj));
+        nn = fmin(fmax(nn, 0.0), 1.0);
+        const double nbar = 2.0 * nn - no;
+        nv[j] = nn; ns[j] += nn;
+        double sr = sigma / ((double)F + kMfBigM);
+        double v5 = y5a + sr * (a5 - kMfBigM * nbar);
+        v5 = v5 - sr * fmin(v5 / sr, 0.0);                          // C5a: (-inf, 0]
+        y[G.r5 + 2 * j] = v5; ys[G.r5 + 2 * j] += v5;
+        sr = sigma / ((double)F + 1.0);
+        v5 = y5b + sr * (a5 - nbar);
+        v5 = v5 - sr * fmax(v5 / sr, -kEps);                        // C5b: [-eps, +inf)
+        y[G.r5 + 2 * j + 1] = v5; ys[G.r5 + 2 * j + 1] += v5;
+        sr = cj != 0.0 ? sigma / fabs(cj) : sigma;
+        v5 = y6 + sr * (cj * nbar);
+        v5 = v5 - sr * fmin(v5 / sr, in.budget);                    // C6: (-inf, budget]
+        y[G.r6 + j] = v5; ys[G.r6 + j] += v5;
+      }
     }
   }
 }
@@ -601,7 +642,8 @@ k_mf_eval_small(MfGeo G, MfIn in, MfSt st, Ctl* __restrict__ ctl, int which) {
     viol = a - 1.0;
     pres2 += viol * viol;
     dobj -= yv[G.r3 + q] * sc;
-    const double rcc = -y1 + m[f] * yv[G.r2 + j] * sc - sS;
+    double rcc = -y1 + m[f] * yv[G.r2 + j] * sc - sS;
+    if (G.with_n) rcc += (yv[G.r5 + 2 * j] + yv[G.r5 + 2 * j + 1]) * sc;
     dobj += fmin(rcc, 0.0);                                       // c in [0, 1]
   }
   for (int64_t j = threadIdx.x; j < N; j += blockDim.x) {
@@ -615,6 +657,21 @@ k_mf_eval_small(MfGeo G, MfIn in, MfSt st, Ctl* __restrict__ ctl, int which) {
     const double y2 = yv[G.r2 + j] * sc, y4 = yv[G.r4 + j] * sc;
     if (y2 > 0.0) dobj -= Mj[j] * y2; else dres2 += y2 * y2;
     if (y4 > 0.0) dobj -= Kj[j] * y4; else dres2 += y4 * y4;
+    if (G.with_n) {
+      double a5 = 0.0;
+      for (int f = 0; f < F; ++f) a5 += cv[(int64_t)f * N + j] * sc;
+      const double nj = xvec[G.X + C + j] * sc, cj = in.cost[(int64_t)b * N + j];
+      const double y5a = yv[G.r5 + 2 * j] * sc, y5b = yv[G.r5 + 2 * j + 1] * sc, y6 = yv[G.r6 + j] * sc;
+      viol = fmax(a5 - kMfBigM * nj, 0.0); pres2 += viol * viol;
+      viol = fmin(a5 - nj + kEps, 0.0); pres2 += viol * viol;
+      viol = fmax(cj * nj - in.budget, 0.0); pres2 += viol * viol;
+      if (y5a < 0.0) dres2 += y5a * y5a;                           // hi = 0: nothing for the dual objective
+      if (y5b > 0.0) dres2 += y5b * y5b; else dobj += kEps * y5b;
+      if (y6 > 0.0) dobj -= in.budget * y6; else dres2 += y6 * y6;
+      const double rcn = in.objn - kMfBigM * y5a - y5b + cj * y6;
+      dobj += fmin(rcn, 0.0);                                     // n in [0, 1]
+      pobj += in.objn * nj;
+    }
   }
   const double* __restrict__ sq = st.scal + (int64_t)b * G.tiles_inst * 4;
   for (int t = threadIdx.x; t < G.tiles_inst; t += blockDim.x) {
@@ -698,11 +755,23 @@ __global__ void k_mf_setup_norms(MfGeo G, MfIn in, MfSt st, Ctl* __restrict__ ct
     if (isfinite(mj)) m2 += mj * mj;
     if (isfinite(kj)) { k2 += kj * kj; k2s += kj * kj * st.S4[(int64_t)b * N + j]; }
   }
+  double nb2n = 0.0, nbs2n = 0.0, nc2n = 0.0, ncs2n = 0.0;
+  if (G.with_n) {
+    const double bud2 = isfinite(in.budget) ? in.budget * in.budget : 0.0;
+    nb2n = kEps * kEps * N + bud2 * N;
+    nbs2n = kEps * kEps * N / ((double)G.F + 1.0);
+    nc2n = in.objn * in.objn * N;
+    for (int j = 0; j < N; ++j) {
+      const double cj = fabs(in.cost[(int64_t)b * N + j]);
+      nbs2n += bud2 * (cj != 0.0 ? 1.0 / cj : 1.0);
+      ncs2n += in.objn * in.objn / (kMfBigM + 1.0 + cj);
+    }
+  }
   double* acc = ctl[b].acc;
-  acc[ACC_NB2] = kEps * kEps * C + m2 + C + k2;
-  acc[ACC_NC2] = nc2;
-  acc[ACC_NBS2] = kEps * kEps * C / (double)(N + 1) + m2 * st.S2[b] + C / (double)N + k2s;
-  acc[ACC_NCS2] = ncs2;
+  acc[ACC_NB2] = kEps * kEps * C + m2 + C + k2 + nb2n;
+  acc[ACC_NC2] = nc2 + nc2n;
+  acc[ACC_NBS2] = kEps * kEps * C / (double)(N + 1) + m2 * st.S2[b] + C / (double)N + k2s + nbs2n;
+  acc[ACC_NCS2] = ncs2 + ncs2n;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -733,9 +802,11 @@ k_mf_apply_restart(MfGeo G, MfIn in, MfSt st, double* __restrict__ xres, double*
         const int64_t rem = k - (int64_t)f * NN;
         const int i = (int)(rem / N), j = (int)(rem - (int64_t)i * N);
         diag = 1.0 / (3.0 + fabs(w[(int64_t)f * N + i] * r[(int64_t)f * N + j]));
-      } else {
+      } else if (k < G.X + G.C) {
         const int f = (int)((k - G.X) / N);
-        diag = 1.0 / (1.0 + fabs(m[f]) + (double)N);
+        diag = 1.0 / ((G.with_n ? 3.0 : 1.0) + fabs(m[f]) + (double)N);
+      } else {
+        diag = 1.0 / (kMfBigM + 1.0 + fabs(in.cost[(int64_t)b * N + (k - G.X - G.C)]));
       }
       const int64_t q = (int64_t)b * G.cols + k;
       const double nv = (action == 1) ? st.xsum[q] * inv : st.x[q];
@@ -748,7 +819,9 @@ k_mf_apply_restart(MfGeo G, MfIn in, MfSt st, double* __restrict__ xres, double*
       if (row < G.r2) diag = (row & 1) ? 1.0 / (double)(N + 1) : 1.0;
       else if (row < G.r3) diag = st.S2[b];
       else if (row < G.r4) diag = 1.0 / (double)N;
-      else if (row < G.rs) diag = st.S4[(int64_t)b * N + (row - G.r4)];
+      else if (row < G.r5) diag = st.S4[(int64_t)b * N + (row - G.r4)];
+      else if (row < G.r6) diag = ((row - G.r5) & 1) ? 1.0 / ((double)F + 1.0) : 1.0 / ((double)F + kMfBigM);
+      else if (row < G.rs) { const double cj = fabs(in.cost[(int64_t)b * N + (row - G.r6)]); diag = cj != 0.0 ? 1.0 / cj : 1.0; }
       else diag = 0.5;
       const int64_t q = (int64_t)b * G.rows + row;
       const double nv = (action == 1) ? st.ysum[q] * inv : st.y[q];
@@ -906,21 +979,22 @@ extern "C" int neptune_pdhg_mf_geometry(int B, int N, int F, int32_t* out) {
 
 extern "C" int neptune_pdhg_mf_workspace_bytes(int B, int N, int F, int64_t* bytes) {
   if (B <= 0 || N <= 0 || F <= 0 || !bytes) return NEPTUNE_E_ARG;
-  Layout L(N, F, NEPTUNE_KIND_MIN_DELAY, NEPTUNE_FLAG_STRENGTHEN);
+  // sized for the layout WITH node columns (N more columns, 3N more rows): valid for every kind
+  Layout L(N, F, NEPTUNE_KIND_MIN_DELAY_UTIL, NEPTUNE_FLAG_STRENGTHEN);
   if (L.cols >= (int64_t)INT32_MAX || L.rows >= (int64_t)INT32_MAX) return NEPTUNE_E_SIZE;
-  const MfGeo G = make_geo(N, F, B);
+  const MfGeo G = make_geo(N, F, B, NEPTUNE_KIND_MIN_DELAY_UTIL);
   *bytes = (int64_t)mf_layout(B, G).total;
   return 0;
 }
 
-extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double* d, const double* w,
-                                     const double* r, const double* m, const double* Mj, const double* Kj,
-                                     const neptune_pdhg_params* prm, double* x, double* y,
-                                     neptune_pdhg_result* result_d, void* workspace, int64_t workspace_bytes,
-                                     void* stream) {
+static int mf_solve_impl(int B, int N, int F, int kind, const double* d, const double* w, const double* r,
+                         const double* m, const double* Mj, const double* Kj, const double* cost, double budget,
+                         double objn, const neptune_pdhg_params* prm, double* x, double* y,
+                         neptune_pdhg_result* result_d, void* workspace, int64_t workspace_bytes, void* stream) {
   if (B <= 0 || N <= 0 || F <= 0) return NEPTUNE_E_ARG;
-  if (kind != NEPTUNE_KIND_MIN_DELAY) return NEPTUNE_E_ARG;      // the n columns / C5 / C6 rows are not stated here
+  if (kind < 0 || kind > 2) return NEPTUNE_E_ARG;
   if (!d || !w || !r || !m || !Mj || !Kj || !prm || !x || !y || !result_d || !workspace) return NEPTUNE_E_ARG;
+  if (kind != NEPTUNE_KIND_MIN_DELAY && !cost) return NEPTUNE_E_ARG;
   int64_t need = 0;
   { int rc = neptune_pdhg_mf_workspace_bytes(B, N, F, &need); if (rc) return rc; }
   if (workspace_bytes < need) return NEPTUNE_E_NOMEM;
@@ -951,8 +1025,8 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
   const int max_iters = prm->max_iters > 0 ? prm->max_iters : 20000;
 
   MfPlan P{};
-  P.B = B; P.G = make_geo(N, F, B); P.s = s;
-  P.in = MfIn{d, w, r, m, Mj, Kj};
+  P.B = B; P.G = make_geo(N, F, B, kind); P.s = s;
+  P.in = MfIn{d, w, r, m, Mj, Kj, cost, budget, objn};
   const MfGeo& G = P.G;
   const MfWs W = mf_layout(B, G);
   char* base = (char*)workspace;
@@ -1047,6 +1121,27 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
   NEPTUNE_CUDA_OK(cudaStreamWaitEvent(caller, ev_out, 0));
   NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
   return 0;          // `guard` releases the graph, its exec, the events and the side stream
+}
+
+extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double* d, const double* w,
+                                     const double* r, const double* m, const double* Mj, const double* Kj,
+                                     const neptune_pdhg_params* prm, double* x, double* y,
+                                     neptune_pdhg_result* result_d, void* workspace, int64_t workspace_bytes,
+                                     void* stream) {
+  if (kind != NEPTUNE_KIND_MIN_DELAY) return NEPTUNE_E_ARG;      // node columns: neptune_pdhg_mf_solve_util
+  return mf_solve_impl(B, N, F, kind, d, w, r, m, Mj, Kj, nullptr, 0.0, 0.0, prm, x, y, result_d, workspace,
+                       workspace_bytes, stream);
+}
+
+extern "C" int neptune_pdhg_mf_solve_util(int B, int N, int F, int kind, const double* d_obj, const double* w,
+                                          const double* r, const double* m, const double* Mj, const double* Kj,
+                                          const double* cost, double budget, double obj_n,
+                                          const neptune_pdhg_params* prm, double* x, double* y,
+                                          neptune_pdhg_result* result_d, void* workspace, int64_t workspace_bytes,
+                                          void* stream) {
+  if (kind != NEPTUNE_KIND_MIN_UTIL && kind != NEPTUNE_KIND_MIN_DELAY_UTIL) return NEPTUNE_E_ARG;
+  return mf_solve_impl(B, N, F, kind, d_obj, w, r, m, Mj, Kj, cost, budget, obj_n, prm, x, y, result_d, workspace,
+                       workspace_bytes, stream);
 }
 
 // ===================================================================================================
@@ -1186,7 +1281,7 @@ static int mf_step_plan(MfPlan& P, int B, int N, int F, const double* d, const d
   const MfStepWs W = mf_step_layout(B, P.G);
   if (ws_bytes < (int64_t)W.total) return NEPTUNE_E_NOMEM;
   char* base = (char*)ws;
-  P.in = MfIn{d, w, r, m, Mj, Kj};
+  P.in = MfIn{d, w, r, m, Mj, Kj, nullptr, 0.0, 0.0};
   P.ctl = (Ctl*)(base + W.ctl);
   P.st = MfSt{x, y, xsum, ysum, (double*)(base + W.cbar), (double*)(base + W.P1), (double*)(base + W.P4),
               (double*)(base + W.PS), nullptr, (double*)(base + W.P3i), const_cast<double*>(S4),

@@ -209,16 +209,36 @@ def pdhg_solve(mdl: Model, max_iters=20000, check_every=64, eps_rel=1e-6, eps_ab
     return x, y, out
 
 
+def objective_weights(inst: InstanceBatch, kind, alpha=0.5):
+    """(a_d[B], a_u[B]): objective = a_d * (workload-weighted delay) + a_u * (active nodes), reference
+    objectives.py:4-52 -- (1, 0) for min-delay, (0, 1) for min-utilisation, ((1 - alpha) / the largest
+    workload-weighted delay, alpha / N) for the combined objective."""
+    k = KINDS.get(kind, kind)
+    one = torch.ones(inst.B, dtype=torch.float64, device=inst.d.device)
+    if k == 0:
+        return one, 0 * one
+    if k == 1:
+        return 0 * one, one
+    far = torch.where(inst.d[:, None, :, :] <= inst.maxd[:, :, None, None], inst.d[:, None, :, :],
+                      torch.full_like(inst.d[:, None, :, :], -float("inf"))).amax(dim=-1)          # [B,F,N]
+    wmax = (inst.w * far).sum(dim=(1, 2))
+    wsum = inst.w.sum(dim=(1, 2))
+    a_d = torch.where((wsum != 0) & (wmax != 0), (1.0 - alpha) / wmax, 0 * one)
+    return a_d, one * (alpha / inst.N)
+
+
 def pdhg_mf_solve(inst: InstanceBatch, max_iters=20000, check_every=64, eps_rel=1e-6, eps_abs=1e-8,
                   x0: Optional[torch.Tensor] = None, y0: Optional[torch.Tensor] = None, workspace=None,
-                  scalar_kernel=False, rows_in_flight=0, _diag=0):
-    """Matrix-free PDHG on the strengthened min-delay relaxation (`neptune_pdhg_mf_solve`): nothing is
-    assembled, every coefficient is regenerated from the instance arrays.  Returns (x[B,cols], y[B,rows],
-    results) in the canonical layout of `assemble(inst, "min_delay", flags=FLAG_STRENGTHEN)`."""
+                  scalar_kernel=False, rows_in_flight=0, _diag=0, kind="min_delay", alpha=0.5):
+    """Matrix-free PDHG on the strengthened relaxation (`neptune_pdhg_mf_solve`, and `neptune_pdhg_mf_solve_util`
+    for the models with node columns): nothing is assembled, every coefficient is regenerated from the instance
+    arrays.  Returns (x[B,cols], y[B,rows], results) in the canonical layout of
+    `assemble(inst, kind, flags=FLAG_STRENGTHEN)`."""
     _require_cuda()
     lib = _lib.load()
     from ._lib import FLAG_STRENGTHEN
-    rows, cols, _ = model_sizes(inst.N, inst.F, 0, FLAG_STRENGTHEN)
+    k = KINDS.get(kind, kind)
+    rows, cols, _ = model_sizes(inst.N, inst.F, k, FLAG_STRENGTHEN)
     dev = inst.d.device
     x = torch.zeros((inst.B, cols), dtype=torch.float64, device=dev) if x0 is None else x0
     y = torch.zeros((inst.B, rows), dtype=torch.float64, device=dev) if y0 is None else y0
@@ -231,10 +251,20 @@ def pdhg_mf_solve(inst: InstanceBatch, max_iters=20000, check_every=64, eps_rel=
     # bits 8..10 = rows of a warp in flight (0 = default)
     prm = PdhgParams(max_iters, check_every, 0, (1 if scalar_kernel else 0) | (_diag << 4) | (rows_in_flight << 8),
                      eps_rel, eps_abs)
-    check(lib.neptune_pdhg_mf_solve(inst.B, inst.N, inst.F, 0, _ptr(inst.d), _ptr(inst.w), _ptr(inst.r),
-                                    _ptr(inst.m), _ptr(inst.Mj), _ptr(inst.Kj), C.byref(prm), _ptr(x), _ptr(y),
-                                    _ptr(res), _ptr(workspace), workspace.numel(), _stream()),
-          "neptune_pdhg_mf_solve")
+    if k == 0:
+        check(lib.neptune_pdhg_mf_solve(inst.B, inst.N, inst.F, 0, _ptr(inst.d), _ptr(inst.w), _ptr(inst.r),
+                                        _ptr(inst.m), _ptr(inst.Mj), _ptr(inst.Kj), C.byref(prm), _ptr(x), _ptr(y),
+                                        _ptr(res), _ptr(workspace), workspace.numel(), _stream()),
+              "neptune_pdhg_mf_solve")
+    else:
+        # the delay matrix as it enters the objective (objectives.py:24-52): zeros, or d scaled per instance
+        a_d, a_u = objective_weights(inst, k, alpha)
+        d_obj = (inst.d * a_d[:, None, None]).contiguous()
+        check(lib.neptune_pdhg_mf_solve_util(inst.B, inst.N, inst.F, k, _ptr(d_obj), _ptr(inst.w), _ptr(inst.r),
+                                             _ptr(inst.m), _ptr(inst.Mj), _ptr(inst.Kj), _ptr(inst.cost),
+                                             C.c_double(float(inst.budget)), C.c_double(float(a_u[0])), C.byref(prm),
+                                             _ptr(x), _ptr(y), _ptr(res), _ptr(workspace), workspace.numel(), _stream()),
+              "neptune_pdhg_mf_solve_util")
     out = np.frombuffer(res.cpu().numpy().tobytes(), dtype=_PDHG_DTYPE)
     return x, y, out
 

@@ -171,6 +171,133 @@ class MatrixFree:
         self.x, self.c, self.y1, self.y2, self.y3, self.y4, self.yS = [np.array(t, dtype=float) for t in st]
         self.sS = self.yS.sum(axis=1)
 
+    def movement(self, st, rst):
+        """distance from the last restart point in the preconditioned norms (primal, dual)"""
+        Td = (self.Tx, self.Tc); Sd = (self.S1, self.S2, self.S3, self.S4, self.SS)
+        dx2 = sum(np.sum((st[k] - rst[k]) ** 2 / Td[k]) for k in range(2))
+        dy2 = sum(np.sum((st[2 + k] - rst[2 + k]) ** 2 / Sd[k]) for k in range(5))
+        return np.sqrt(dx2), np.sqrt(dy2)
+
+
+BIG_M = 1e6
+
+
+def util_objective(a, kind, alpha):
+    """(x-objective [F,N,N], n-objective scalar) of the models with node variables, reference `objectives.py:24-52`
+    as oracle/model.py states them."""
+    from oracle import model as omodel
+    full = omodel.objective_step1(a, kind, alpha)
+    N, F = a["N"], a["F"]; X = F * N * N
+    return full[:X].reshape(F, N, N), float(full[X + F * N]) if N else 0.0
+
+
+class MatrixFreeN(MatrixFree):
+    """The iteration for the models with node variables n[j] (min-utilisation and the combined objective, reference
+    `neptune_step1.py:38-77`): columns x, c, n; the rows of `MatrixFree` plus C5a (sum_f c[f,j] - M n[j] <= 0), C5b
+    (sum_f c[f,j] - n[j] >= -eps) and C6 (cost_j n[j] <= budget), `constraints_step1.py:69-80, 101-103`.  Everything
+    new is O(N) or O(F*N): it lives in the small-vector kernel; the pass over x only sees another objective."""
+
+    def __init__(self, a, kind, alpha=0.5):
+        super().__init__(a)
+        N, F = self.N, self.F
+        self.obj, self.objn = util_objective(a, kind, alpha)
+        self.cost, self.budget = a["cost"].astype(float), float(a["budget"])
+        self.Tc = np.repeat((1.0 / (3.0 + a["m"] + N))[:, None], N, 1)
+        self.Tn = 1.0 / (BIG_M + 1.0 + np.abs(self.cost))
+        self.S5a, self.S5b = 1.0 / (F + BIG_M), 1.0 / (F + 1.0)
+        self.S6 = np.where(self.cost != 0, 1.0 / np.where(self.cost != 0, np.abs(self.cost), 1.0), 1.0)
+        Mj, Kj = a["Mj"], a["Kj"]
+        bud2 = self.budget ** 2 if np.isfinite(self.budget) else 0.0
+        self.nb = np.sqrt(EPS ** 2 * F * N + np.sum(Mj ** 2) + F * N + np.sum(Kj ** 2) + EPS ** 2 * N + bud2 * N)
+        self.nc = np.sqrt(np.sum(self.obj ** 2) + self.objn ** 2 * N)
+        nbs = np.sqrt(EPS ** 2 * self.S1 * F * N + np.sum(Mj ** 2) * self.S2 + self.S3 * F * N + np.sum(Kj ** 2 * self.S4)
+                      + EPS ** 2 * self.S5b * N + bud2 * np.sum(self.S6))
+        ncs = np.sqrt(np.sum(self.obj ** 2 * self.Tx) + self.objn ** 2 * np.sum(self.Tn))
+        self.omega = ncs / nbs if nbs > 1e-10 and ncs > 1e-10 else 1.0
+        z = np.zeros
+        self.n, self.y5a, self.y5b, self.y6 = z(N), z(N), z(N), z(N)
+
+    def step(self):
+        a, N = self.a, self.N
+        tau, sig = self.eta / self.omega, self.eta * self.omega
+        # ---- small kernel, part 1: c and n columns from the duals of the previous iteration ----
+        gc = -self.y1 + a["m"][:, None] * self.y2[None, :] - self.sS + (self.y5a + self.y5b)[None, :]
+        cn = np.clip(self.c - tau * self.Tc * gc, 0.0, 1.0)
+        cb = 2 * cn - self.c
+        self.c = cn
+        gn = self.objn - BIG_M * self.y5a - self.y5b + self.cost * self.y6
+        nn = np.clip(self.n - tau * self.Tn * gn, 0.0, 1.0)
+        nbar = 2 * nn - self.n
+        self.n = nn
+        # duals of the rows over (c, n) only
+        s = sig * self.S2
+        v = self.y2 + s * (a["m"] @ cb)
+        y2n = v - s * np.minimum(v / s, a["Mj"])
+        a5 = cb.sum(axis=0)
+        s = sig * self.S5a
+        v = self.y5a + s * (a5 - BIG_M * nbar)
+        y5an = v - s * np.minimum(v / s, 0.0)
+        s = sig * self.S5b
+        v = self.y5b + s * (a5 - nbar)
+        y5bn = v - s * np.maximum(v / s, -EPS)
+        s = sig * self.S6
+        v = self.y6 + s * (self.cost * nbar)
+        y6n = v - s * np.minimum(v / s, self.budget)
+        # ---- the pass over (f,i,j) and the remaining duals: as in the base class ----
+        g = self.obj + self.y1[:, None, :] + self.y3[:, :, None] + self.wr * self.y4[None, None, :] + self.yS
+        xn = np.clip(self.x - tau * self.Tx * g, 0.0, 1.0)
+        xb = 2 * xn - self.x
+        self.yS = np.maximum(self.yS + sig * self.SS * (xb - cb[:, None, :]), 0.0)
+        self.x = xn
+        A1, A3, A4 = xb.sum(axis=1), xb.sum(axis=2), (self.wr * xb).sum(axis=(0, 1))
+        self.sS = self.yS.sum(axis=1)
+        s = sig * self.S1
+        v = self.y1 + s * (A1 - cb)
+        self.y1 = v - s * np.maximum(v / s, -EPS)
+        s = sig * self.S3
+        self.y3 = self.y3 + s * A3 - s
+        s = sig * self.S4
+        v = self.y4 + s * A4
+        self.y4 = v - s * np.minimum(v / s, a["Kj"])
+        self.y2, self.y5a, self.y5b, self.y6 = y2n, y5an, y5bn, y6n
+
+    def pack(self):
+        F, N = self.F, self.N
+        y1 = np.zeros((F * N, 2)); y1[:, 1] = self.y1.reshape(-1)
+        y5 = np.stack([self.y5a, self.y5b], 1).reshape(-1)
+        return (np.concatenate([self.x.reshape(-1), self.c.reshape(-1), self.n]),
+                np.concatenate([y1.reshape(-1), self.y2, self.y3.reshape(-1), self.y4, y5, self.y6, self.yS.reshape(-1)]))
+
+    def kkt(self, st):
+        a = self.a
+        x, c, y1, y2, y3, y4, yS, n, y5a, y5b, y6 = st
+        p2, d2, _, dobj = super().kkt((x, c, y1, y2, y3, y4, yS))
+        # super() priced the c columns without the C5 duals: redo that term
+        rcc0 = -y1 + a["m"][:, None] * y2[None, :] - yS.sum(axis=1)
+        rcc = rcc0 + (y5a + y5b)[None, :]
+        dobj += np.sum(np.minimum(rcc, 0)) - np.sum(np.minimum(rcc0, 0))
+        a5 = c.sum(axis=0)
+        p2 += np.sum(np.maximum(a5 - BIG_M * n, 0) ** 2) + np.sum(np.minimum(a5 - n + EPS, 0) ** 2)
+        p2 += np.sum(np.maximum(self.cost * n - self.budget, 0) ** 2)
+        d2 += np.sum(np.minimum(y5a, 0) ** 2) + np.sum(np.maximum(y5b, 0) ** 2) + np.sum(np.minimum(y6, 0) ** 2)
+        dobj += EPS * np.sum(np.minimum(y5b, 0)) - self.budget * np.sum(np.maximum(y6, 0))
+        rcn = self.objn - BIG_M * y5a - y5b + self.cost * y6
+        dobj += np.sum(np.minimum(rcn, 0))
+        return p2, d2, float(np.sum(self.obj * x) + self.objn * np.sum(n)), dobj
+
+    def state(self):
+        return (self.x, self.c, self.y1, self.y2, self.y3, self.y4, self.yS, self.n, self.y5a, self.y5b, self.y6)
+
+    def set_state(self, st):
+        super().set_state(st[:7])
+        self.n, self.y5a, self.y5b, self.y6 = [np.array(t, dtype=float) for t in st[7:]]
+
+    def movement(self, st, rst):
+        dx, dy = super().movement(st[:7], rst[:7])
+        dx2 = dx ** 2 + np.sum((st[7] - rst[7]) ** 2 / self.Tn)
+        dy2 = dy ** 2 + np.sum((st[8] - rst[8]) ** 2 / self.S5a) + np.sum((st[9] - rst[9]) ** 2 / self.S5b) + np.sum((st[10] - rst[10]) ** 2 / self.S6)
+        return np.sqrt(dx2), np.sqrt(dy2)
+
 
 def solve(mf: MatrixFree, max_iters=20000, check=64, eps=1e-6, verbose=False):
     """restart logic of pdhg.cu on the matrix-free state"""
@@ -213,9 +340,7 @@ def solve(mf: MatrixFree, max_iters=20000, check=64, eps=1e-6, verbose=False):
             if pick == 1:
                 mf.set_state(tuple(s_ / cnt for s_ in sums))
             st = mf.state()
-            Td = (mf.Tx, mf.Tc); Sd = (mf.S1, mf.S2, mf.S3, mf.S4, mf.SS)
-            dx = np.sqrt(sum(np.sum((st[k] - rst[k]) ** 2 / Td[k]) for k in range(2)))
-            dy = np.sqrt(sum(np.sum((st[2 + k] - rst[2 + k]) ** 2 / Sd[k]) for k in range(5)))
+            dx, dy = mf.movement(st, rst)
             if dx > 1e-10 and dy > 1e-10:
                 nw = np.exp(0.5 * np.log(dy / dx) + 0.5 * np.log(mf.omega))
                 mf.omega = min(max(nw, 0.5 * mf.omega), 2.0 * mf.omega)
@@ -227,11 +352,11 @@ def solve(mf: MatrixFree, max_iters=20000, check=64, eps=1e-6, verbose=False):
 
 
 
-def run_fixed(a, iters):
+def run_fixed(a, iters, kind="min_delay", alpha=0.5):
     """What `neptune_pdhg_mf_solve(max_iters = check_every = iters)` returns with unreachable tolerances:
     `iters` iterations, then the better (smaller KKT error) of the current iterate and the running average.
     Returns (x, y, info) with x / y in the canonical layout of the strengthened model."""
-    mf = MatrixFree(a)
+    mf = MatrixFree(a) if kind == "min_delay" else MatrixFreeN(a, kind, alpha)
     sums = [np.zeros_like(t) for t in mf.state()]
     for _ in range(iters):
         mf.step()

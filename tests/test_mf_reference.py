@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from helpers import arrays_of, float_payload
-from mf_reference import Generic, MatrixFree, pc_diag, run_fixed, solve, strengthened
+from mf_reference import Generic, MatrixFree, MatrixFreeN, pc_diag, run_fixed, solve, strengthened
 from neptune_mip_b200 import synth
 from oracle import mip as omip
 
@@ -75,3 +75,22 @@ def test_lp_value_sweep_against_highs(seed):
     assert out["converged"], (N, F, cores, out)
     tol = 1e-4 * (1 + abs(lp["objective"]))
     assert abs(out["primal"] - lp["objective"]) <= tol and abs(out["dual"] - lp["objective"]) <= tol, (N, F, cores, out, lp["objective"])
+
+
+@pytest.mark.parametrize("kind", ["min_util", "min_delay_util"])
+@pytest.mark.parametrize("name,make", CASES[:3], ids=[c[0] for c in CASES[:3]])
+def test_matrix_free_iteration_with_node_variables_equals_csr_iteration(name, make, kind):
+    """the models with n[j] columns and C5a / C5b / C6 rows (reference neptune_step1.py:38-77): closed form == CSR"""
+    a = arrays_of(make())
+    m = strengthened(a, kind, 0.5)
+    T, S = pc_diag(m)
+    g, mf = Generic(m, T, S), MatrixFreeN(a, kind, 0.5)
+    assert abs(g.omega - mf.omega) <= 1e-12 * g.omega
+    assert abs(g.nb - mf.nb) <= 1e-12 * (1 + g.nb) and abs(g.nc - mf.nc) <= 1e-12 * (1 + g.nc)
+    for _ in range(150):
+        g.step(); mf.step()
+    x, y = mf.pack()
+    assert np.abs(x - g.x).max() <= 1e-10 * (1 + np.abs(g.x).max())
+    assert np.abs(y - g.y).max() <= 1e-10 * (1 + np.abs(g.y).max())
+    for u, v in zip(g.kkt(g.x, g.y), mf.kkt(mf.state())):
+        assert abs(u - v) <= 1e-9 * (1 + abs(u))

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from helpers import arrays_of, cuda_batch, float_payload
-from mf_reference import MatrixFree, run_fixed, solve, strengthened
+from mf_reference import MatrixFree, MatrixFreeN, run_fixed, solve, strengthened
 from neptune_mip_b200 import synth
 from oracle import mip as omip
 
@@ -120,8 +120,55 @@ def test_instances_of_a_batch_converge_independently():
         assert np.array_equal(y[b].cpu().numpy(), ys[0].cpu().numpy())
 
 
+UTIL_CASES = [c for c in CASES if c[0] in ("C1-3x2", "8x4", "12x5", "33x3", "50x10", "70x3")]
+
+
+@pytest.mark.parametrize("name,make,iters", UTIL_CASES, ids=[c[0] for c in UTIL_CASES])
+@pytest.mark.parametrize("kind", ["min_util", "min_delay_util"])
+def test_node_variable_models_iterates_equal_the_numpy_reference(name, make, iters, kind):
+    """`neptune_pdhg_mf_solve_util` (columns x, c, n; rows + C5a / C5b / C6, reference neptune_step1.py:38-77): the
+    candidate after `iters` iterations equals the numpy statement, which tests/test_mf_reference.py proves equal to
+    the CSR iteration on the oracle's matrix of that model.  1e-9 relative to the largest entry."""
+    from neptune_mip_b200 import device
+    payloads = [make(s) for s in range(2)]
+    inst = cuda_batch(payloads)
+    x, y, res = device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-13, eps_abs=1e-15, kind=kind, alpha=0.5)
+    N, F = inst.N, inst.F
+    assert x.shape[1] == F * N * N + F * N + N and y.shape[1] == 3 * F * N + 2 * N + 3 * N + F * N * N
+    for b, p in enumerate(payloads):
+        xr, yr, info = run_fixed(arrays_of(p), iters, kind, 0.5)
+        assert _close(x[b].cpu().numpy(), xr, 1e-9), (name, b)
+        assert _close(y[b].cpu().numpy(), yr, 1e-9), (name, b)
+        assert abs(res[b]["primal_obj"] - info["primal_obj"]) <= 1e-9 * (1 + abs(info["primal_obj"]))
+        assert abs(res[b]["dual_obj"] - info["dual_obj"]) <= 1e-9 * (1 + abs(info["dual_obj"]))
+        assert abs(res[b]["primal_res"] - info["primal_res"]) <= 1e-9 * (1 + info["primal_res"])
+        assert abs(res[b]["primal_weight"] - info["omega"]) <= 1e-12 * info["omega"]
+        assert res[b]["iters"] == iters and res[b]["converged"] == 0
+
+
+@pytest.mark.parametrize("kind", ["min_util", "min_delay_util"])
+def test_node_variable_models_reach_the_highs_lp_optimum_and_the_csr_solver(kind):
+    """LP value of the reference's relaxation with node columns: HiGHS on the oracle's matrix, the CSR solver on the
+    assembled matrix, and the matrix-free solver agree to 1e-4 relative."""
+    from neptune_mip_b200 import device
+    from neptune_mip_b200._lib import FLAG_STRENGTHEN
+    p = synth.random_payload(12, 5, 1, node_cores=25)
+    lp = omip.solve_model(strengthened(arrays_of(p), kind, 0.5), relax=True)
+    inst = cuda_batch([p])
+    x, y, res = device.pdhg_mf_solve(inst, max_iters=60000, check_every=128, eps_rel=1e-6, eps_abs=1e-9, kind=kind, alpha=0.5)
+    assert res[0]["converged"] == 1
+    tol = 1e-4 * (1 + abs(lp["objective"]))
+    assert abs(res[0]["primal_obj"] - lp["objective"]) <= tol and abs(res[0]["dual_obj"] - lp["objective"]) <= tol
+    mdl = device.assemble(inst, kind, 0.5, flags=FLAG_STRENGTHEN)
+    xa, ya, ra = device.pdhg_solve(mdl, max_iters=60000, check_every=128, eps_rel=1e-6, eps_abs=1e-9)
+    assert abs(ra[0]["primal_obj"] - res[0]["primal_obj"]) <= 2 * tol
+    n = x[0, -inst.N:].cpu().numpy()
+    assert n.min() >= 0.0 and n.max() <= 1.0
+
+
 def test_other_model_kinds_are_refused():
-    """only the min-delay model is stated in closed form; the n-column models go through the CSR solver"""
+    """`neptune_pdhg_mf_solve` is the min-delay entry point; the n-column models have their own
+    (`neptune_pdhg_mf_solve_util`)"""
     import torch
     from neptune_mip_b200 import _lib, device
     lib = _lib.load()

@@ -39,6 +39,9 @@ def record(n_nodes=2000, n_funcs=200, lp_iters=512, seed=0):
     ms_e, (c, n_e, info) = timed(lambda: device.efttc(inst, "min_delay"))
     # EFTTC's own routing is "every source to its nearest pod" with a global CPU check after every cycle
     # (efttc_step1.py:196-212, utils/constraints_step1.py:70-80), so the nearest routing of its placement is CPU-feasible
+    import numpy as np
+    os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
+    np.save(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", f"c4_efttc_c_{n_nodes}x{n_funcs}.npy"), c[0].cpu().numpy())
     ms_r, (x, n) = timed(lambda: device.route_placements(inst, c))
     c2 = c
     ms_c, (flags, scores) = timed(lambda: device.check_solution(inst, x, device.u8_to_f64(c2), n))
@@ -49,7 +52,7 @@ def record(n_nodes=2000, n_funcs=200, lp_iters=512, seed=0):
              "n_according_to_c": OK_N_C}
     rec = {"workload": f"C4: {n_nodes} nodes x {n_funcs} functions, one instance, one GPU",
            "placement": "EFTTC (k_efttc) + nearest-pod routing (k_route), as EFTTC routes; the searches stop at N = 768 / 128",
-           "pods": int(c2.sum().item()), "objective_min_delay": float(obj.cpu()[0]),
+           "pods": int(c2.sum().item()), "functions_without_pod": int((c2[0].sum(dim=1) == 0).sum().item()), "objective_min_delay": float(obj.cpu()[0]),
            "feasible": bool(int(feas.cpu()[0])), "checkers": {k: bool(fl & v) for k, v in names.items()},
            "ms": {"host_instance_build": 1e3 * t_build, "efttc": ms_e, "routing": ms_r, "checkers": ms_c},
            "x_bytes": int(x.numel() * 8)}
