@@ -467,7 +467,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="instances per GPU per step")
+    ap.add_argument("--batch", type=int, default=48,
+                    help="instances per GPU per step (48 x 96 chains = 576 search blocks = two full waves of 2 x 148 resident blocks)")
     ap.add_argument("--lp-iters", type=int, default=50000, help="cap on PDHG iterations (the solver stops at 1e-6 relative KKT error)")
     ap.add_argument("--search", default="auto", choices=["auto", "local"])
     ap.add_argument("--lns-chains", type=int, default=96)

@@ -327,6 +327,18 @@ int neptune_lns_search(int B, int N, int F, int kind, double alpha, int chains, 
  * function of its index only); it is a tuning and measurement switch. */
 int neptune_lns_block_mode(int mode);
 
+/* ---- (d2) round-robin delay-improvement greedy (csrc/site.cu) ---------------------------------------
+ * A placement for instances too large for the one-block-per-instance EFTTC kernel and the shared-memory searches
+ * (BASELINE config 4).  The move is EFTTC's `find_best_node_by_delay_improvement`
+ * (`core/solvers/efttc/efttc_step1.py:214-288`): gain(f, j) = sum_i w[f,i] max(0, cur[f,i] - d[i,j]); every function
+ * proposes its best node in every round, a node accepts in order of gain while its memory lasts (`:290-312`).
+ * c_out[B][F][N] uint8, info_out[B][2] = {rounds that placed a pod, pods}.  `unserved_delay` (> every d) is the delay
+ * of a source whose function has no pod yet.  CPU capacity is left to neptune_route_capacitated + the checkers. */
+int neptune_site_greedy_workspace_bytes(int B, int N, int F, int64_t* bytes);
+int neptune_site_greedy(int B, int N, int F, const double* d, const double* w, const double* m, const double* Mj,
+                        double unserved_delay, int max_rounds, uint8_t* c_out, int32_t* info_out,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- (d) EFTTC greedy -----------------------------------------------------------------------------
  * Replaces `EfttcStepBase.solve()` (`core/solvers/efttc/efttc_step1.py:39-90` and helpers
  * :92-312, score_local :356-439).  One thread block per instance; deterministic, same

@@ -28,7 +28,8 @@ class BatchParams:
     search: str = "auto"          # "auto": slot-count LNS (csrc/lns.cu) where it applies, else the add/drop/swap search; "local": always the latter
     lp_cut: bool = True           # relax with the Chvatal-Gomory rounding of the memory rows (one memory size per instance)
     lns_chains: int = 96          # warp-sized chains per instance
-    lns_fill_waves: bool = True   # raise the chain count (at most 1.5x) until the blocks of the search fill whole waves of the GPU
+    lns_fill_waves: bool = False  # raise the chain count (at most 1.5x) until the blocks of the search fill whole waves of the GPU
+                                  # (measured: NOT free -- 32 x 144 chains take 9.1 s where 32 x 96 take 7.1 s; fill the waves with instances instead)
     lns_rounds: int = 20000       # k-node re-optimisations per chain
     lns_k: int = 3
     lns_noise: float = 0.1
@@ -156,7 +157,7 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
 _DEBUG_SYNC = int(os.environ.get("NEPTUNE_DEBUG_SYNC", "0"))
 
 
-def polish_exact(inst: device.InstanceBatch, kind, alpha, c: torch.Tensor, max_iters: int = 12, depth: int = 3,
+def polish_exact(inst: device.InstanceBatch, kind, alpha, c: torch.Tensor, max_iters: int = 12, depth: int = 2,
                  chunk: int = 4096):
     """Steepest descent with EVERY neighbour priced exactly by the routing LP (`neptune_route_lp` on the whole batch
     of candidates: the "thousands of candidate placements per launch" of the north star).  Neighbourhoods by size,
@@ -183,10 +184,16 @@ def polish_exact(inst: device.InstanceBatch, kind, alpha, c: torch.Tensor, max_i
             masks[size] = mk.reshape(-1, F, N)
         return masks[size]
 
+    depth = int(os.environ.get("NEPTUNE_POLISH_DEPTH", depth))
+    zero_ws = bool(os.environ.get("NEPTUNE_RLP_ZERO"))
+
     def value(cands):
         if _DEBUG_SYNC == 1:
             torch.cuda.synchronize(); print("polish: before route_lp", tuple(cands.shape), flush=True)
-        pr = device.route_lp(inst, cands.contiguous(), tableau_doubles=slab)
+        ws = None
+        if zero_ws:
+            ws = torch.zeros(296 * ((1 << 20) + (slab << 3)), dtype=torch.uint8, device=dev)
+        pr = device.route_lp(inst, cands.contiguous(), tableau_doubles=slab, workspace=ws)
         if _DEBUG_SYNC in (1, 2):
             torch.cuda.synchronize(); print("polish: after route_lp", tuple(cands.shape), "status counts", torch.bincount(pr["status"].reshape(-1), minlength=3).tolist(), flush=True)
         v = a_d[:, None] * pr["obj"] + a_u[:, None] * pr["n"].sum(dim=-1)
@@ -230,10 +237,11 @@ objective_weights = device.objective_weights      # (a_d[B], a_u[B]) of the thre
 
 
 def fill_waves(B: int, chains: int, chains_per_block: int = 8, resident_blocks: int = 2 * 148, cap: float = 1.5) -> int:
-    """Chains per instance that cost no extra time: the search kernel runs `chains_per_block` chains per block, two
-    blocks per SM, and every block of a launch takes about as long (measured: 32 instances x 96 chains = 384 blocks =
-    1.3 waves take as long as 48 x 96 = 576 blocks = 1.95 waves).  The count is raised to the largest one with the same
-    number of waves, at most `cap` times what was asked (a lone instance should not light up the whole GPU)."""
+    """Largest chain count with the same number of waves of search blocks (`chains_per_block` chains per block, two
+    blocks per SM), at most `cap` times what was asked.  32 instances x 96 chains (384 blocks = 1.3 waves) take as long
+    as 48 x 96 (576 blocks = 1.95 waves), so idle block slots exist -- but filling them with more chains of the SAME
+    instances also grows the record pricing and the final phase (9.1 s against 7.1 s at 32 x 144): off by default, the
+    bench fills the waves with instances (batch 48)."""
     per_inst = -(-chains // chains_per_block)
     waves = -(-(B * per_inst) // resident_blocks)
     fit = (waves * resident_blocks) // B

@@ -44,7 +44,7 @@ __host__ __device__ inline int64_t rlp_fixed_bytes(int N, int F) {
   // near, src, coloff (fn+1), podlist: 4 * fn ints (+1); colsrc / basis live after the tableau sizing below
   int64_t b = (5 * fn + 8 + 2 * F + N) * 4 + ((fn + 7) & ~(int64_t)7);   // + C1b pod list, fully-active functions, working copy of the placement
   b = (b + 7) & ~(int64_t)7;
-  b += ((int64_t)2 * N + fn + N) * 8;          // load, colq bound (rows <= fn + N), ...
+  b += ((int64_t)2 * N + 2 * fn + N) * 8;      // load, colq (rows <= fn sources + N nodes + fn C1b rows), ...
   b += (int64_t)N * fn * 8;                    // dense x scratch
   return (b + 255) & ~(int64_t)255;
 }
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) k_route_lp(RlpArgs a) {
   p = (char*)(((uintptr_t)p + 7) & ~(uintptr_t)7);
   double* load = (double*)p; p += (int64_t)N * 8;
   p += (int64_t)N * 8;
-  double* colq = (double*)p; p += (fn + N) * 8;
+  double* colq = (double*)p; p += (2 * fn + N) * 8;       // one entry per tableau row: sources + nodes + C1b rows
   double* xs = (double*)p; p += (int64_t)N * fn * 8;
   p = (char*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
   // tableau region: T[R][C] | red[C] | colsrc[C] (int) | basis[R] (int)
@@ -305,11 +305,14 @@ __global__ void __launch_bounds__(256) k_route_lp(RlpArgs a) {
       if (solved_lp) {
         for (int row = tid; row < R; row += nt) {
           const int col = basis[row];
-          if (col >= nC) continue;
+          if (col < 0 || col >= nC) continue;
           const double v = T[(int64_t)row * C + (C - 1)];
           if (!(v > 0.0)) continue;
-          const int s = colsrc[col], fi = src[s], f = fi / N, i = fi - f * N;
-          const int j = podlist[(int64_t)f * N + (col - coloff[s])];
+          const int s = colsrc[col];
+          if (s < 0 || s >= nS) continue;                        // (defensive: indices read back from the slab)
+          const int fi = src[s], f = fi / N, i = fi - f * N, qq = col - coloff[s];
+          if (fi < 0 || fi >= (int)fn || qq < 0 || qq >= npods[f]) continue;
+          const int j = podlist[(int64_t)f * N + qq];
           xs[((int64_t)i * F + f) * N + j] = v > 1.0 ? 1.0 : v;
         }
       }

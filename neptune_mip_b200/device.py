@@ -326,6 +326,25 @@ def efttc(inst: InstanceBatch, kind, alpha=0.5, workspace=None):
     return c, n, info
 
 
+def site_greedy(inst: InstanceBatch, max_rounds: int = 0):
+    """Round-robin delay-improvement greedy (`neptune_site_greedy`): c uint8[B,F,N], info int32[B,2] = (rounds, pods).
+    For the sizes the EFTTC block and the shared-memory searches do not reach (C4)."""
+    _require_cuda()
+    lib = _lib.load()
+    dev = inst.d.device
+    need = C.c_int64()
+    check(lib.neptune_site_greedy_workspace_bytes(inst.B, inst.N, inst.F, C.byref(need)), "neptune_site_greedy_workspace_bytes")
+    ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    c = torch.empty((inst.B, inst.F, inst.N), dtype=torch.uint8, device=dev)
+    info = torch.empty((inst.B, 2), dtype=torch.int32, device=dev)
+    unserved = 2.0 * float(inst.d.max()) + 1.0
+    rounds = max_rounds if max_rounds > 0 else inst.N * inst.F
+    check(lib.neptune_site_greedy(inst.B, inst.N, inst.F, _ptr(inst.d), _ptr(inst.w), _ptr(inst.m), _ptr(inst.Mj),
+                                  C.c_double(unserved), rounds, _ptr(c), _ptr(info), _ptr(ws), ws.numel(), _stream()),
+          "neptune_site_greedy")
+    return c, info
+
+
 def u8_to_f64(t: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty(t.shape, dtype=torch.float64, device=t.device)

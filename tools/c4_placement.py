@@ -1,12 +1,12 @@
 #!/usr/bin/env python
 """BASELINE config 4 (2000 nodes x 200 functions) on ONE GPU: a checked placement and the bracket around it.
 
-  EFTTC placement (k_efttc) -> nearest-pod routing (k_route) -> the reference's checkers (k_check)
+  greedy placement (k_site_*, csrc/site.cu) -> CPU-capacity-aware routing (k_route_cap) -> the reference's checkers (k_check)
   -> lower bound of the slot-cut LP relaxation after a bounded number of matrix-free PDHG iterations (the dual
      objective with the box terms is a valid bound at every iterate).
 
 The add/drop/swap search and k_lns keep a chain's state in shared memory and stop at N = 768 / N = 128, so at this
-size the placement is EFTTC's; the record says so.  Prints one JSON object (also used by bench.py's `c4_placement`).
+size the placement is the greedy one; the record says so.  Prints one JSON object.
 """
 from __future__ import annotations
 
@@ -19,7 +19,7 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def record(n_nodes=2000, n_funcs=200, lp_iters=512, seed=0):
+def record(n_nodes=2000, n_funcs=200, lp_iters=512, seed=0, efttc=False):
     import torch
     from neptune_mip_b200 import device, synth
     from neptune_mip_b200._lib import OK_C_X, OK_CPU, OK_HANDLE, OK_MEMORY, OK_N_C
@@ -36,26 +36,29 @@ def record(n_nodes=2000, n_funcs=200, lp_iters=512, seed=0):
         e0.record(); out = fn(); e1.record(); e1.synchronize()
         return e0.elapsed_time(e1), out
 
-    ms_e, (c, n_e, info) = timed(lambda: device.efttc(inst, "min_delay"))
-    # EFTTC's own routing is "every source to its nearest pod" with a global CPU check after every cycle
-    # (efttc_step1.py:196-212, utils/constraints_step1.py:70-80), so the nearest routing of its placement is CPU-feasible
-    import numpy as np
-    os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
-    np.save(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", f"c4_efttc_c_{n_nodes}x{n_funcs}.npy"), c[0].cpu().numpy())
-    ms_r, (x, n) = timed(lambda: device.route_placements(inst, c))
-    c2 = c
+    ms_e, (c, info) = timed(lambda: device.site_greedy(inst))
+    ms_r, (c2, x, n, obj, feas) = timed(lambda: device.route_capacitated(inst, c))
     ms_c, (flags, scores) = timed(lambda: device.check_solution(inst, x, device.u8_to_f64(c2), n))
     fl = int(flags.cpu()[0])
-    obj = scores[:, 0]
-    feas = torch.tensor([1 if (fl & (OK_HANDLE | OK_MEMORY | OK_CPU | OK_C_X | OK_N_C)) == (OK_HANDLE | OK_MEMORY | OK_CPU | OK_C_X | OK_N_C) else 0])
     names = {"handle_all_requests": OK_HANDLE, "memory": OK_MEMORY, "cpu": OK_CPU, "c_according_to_x": OK_C_X,
              "n_according_to_c": OK_N_C}
+    near_x, _ = device.route_placements(inst, c)
+    near_obj = float(device.check_solution(inst, near_x, device.u8_to_f64(c), n)[1].cpu()[0, 0])
+    del near_x
     rec = {"workload": f"C4: {n_nodes} nodes x {n_funcs} functions, one instance, one GPU",
-           "placement": "EFTTC (k_efttc) + nearest-pod routing (k_route), as EFTTC routes; the searches stop at N = 768 / 128",
-           "pods": int(c2.sum().item()), "functions_without_pod": int((c2[0].sum(dim=1) == 0).sum().item()), "objective_min_delay": float(obj.cpu()[0]),
-           "feasible": bool(int(feas.cpu()[0])), "checkers": {k: bool(fl & v) for k, v in names.items()},
-           "ms": {"host_instance_build": 1e3 * t_build, "efttc": ms_e, "routing": ms_r, "checkers": ms_c},
+           "placement": "round-robin delay-improvement greedy (k_site_*: EFTTC's move, every function proposes per round) + "
+                        "CPU-capacity-aware routing (k_route_cap); the searches stop at N = 768 / 128",
+           "greedy_rounds": int(info.cpu()[0, 0]), "pods": int(c2.sum().item()),
+           "functions_without_pod": int((c2[0].sum(dim=1) == 0).sum().item()),
+           "objective_min_delay": float(obj.cpu()[0]), "objective_if_every_source_took_its_nearest_pod": near_obj,
+           "feasible": bool(int(feas.cpu()[0])) and all(bool(fl & v) for v in names.values()),
+           "checkers": {k: bool(fl & v) for k, v in names.items()},
+           "ms": {"host_instance_build": 1e3 * t_build, "greedy": ms_e, "routing": ms_r, "checkers": ms_c},
            "x_bytes": int(x.numel() * 8)}
+    if efttc:
+        ms_ef, (ce, _, _) = timed(lambda: device.efttc(inst, "min_delay"))
+        rec["efttc_for_comparison"] = {"ms": ms_ef, "pods": int(ce.sum().item()), "functions_without_pod": int((ce[0].sum(dim=1) == 0).sum().item()),
+                                       "note": "one block per instance; its trading cycles leave most functions without a pod at this size"}
     del x
     if lp_iters > 0:
         lp = device.slot_relaxation(inst)
@@ -74,5 +77,6 @@ if __name__ == "__main__":
     ap.add_argument("--nodes", type=int, default=2000)
     ap.add_argument("--funcs", type=int, default=200)
     ap.add_argument("--lp-iters", type=int, default=512)
+    ap.add_argument("--efttc", action="store_true", help="also time the EFTTC kernel at this size (minutes)")
     a = ap.parse_args()
-    print(json.dumps(record(a.nodes, a.funcs, a.lp_iters)))
+    print(json.dumps(record(a.nodes, a.funcs, a.lp_iters, efttc=a.efttc)))

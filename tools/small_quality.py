@@ -18,7 +18,8 @@ def serve(payload):
 
 
 gold = json.load(open(os.path.join(ROOT, "tests", "golden", "random_small.json")))
-for rec in gold[:int(os.environ.get('SMALL_MAX', '99'))]:
+only = os.environ.get('SMALL_ONLY')
+for rec in ([gold[int(only)]] if only else gold[:int(os.environ.get('SMALL_MAX', '99'))]):
     want = rec["neptune"]["NeptuneMinDelay"]["score"]["step1"]
     payload = synth.random_payload(rec["N"], rec["F"], rec["seed"], node_cores=rec["node_cores"], solver_type="NeptuneMinDelay",
                                    args={"verbose": False, "chains": 64, "sweeps": 300})
