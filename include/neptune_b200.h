@@ -339,6 +339,18 @@ int neptune_site_greedy(int B, int N, int F, const double* d, const double* w, c
                         double unserved_delay, int max_rounds, uint8_t* c_out, int32_t* info_out,
                         void* workspace, int64_t workspace_bytes, void* stream);
 
+/* neptune_route_two_choice: routing of ONE placement per instance at sizes where the per-instance routers do not
+ * finish (C4: 400 000 sources).  Every source sends the share theta[j1] to its nearest pod and the rest to its
+ * second-nearest one; theta[j] starts at 1 and is lowered until node j's CPU row holds (`constrain_CPU_usage`,
+ * constraints_step1.py:57-65; `constrain_handle_all_requests` :27-33 holds by construction).  Pods that are nobody's
+ * nearest are closed.  c[B][F][N] -> c_out, x[B][N][F][N] (may be NULL), n_out[B][N], obj_out[B] (objectives.py:4-11
+ * on that x), feas_out[B] (1 = every CPU row holds), *iters_out (host int). */
+int neptune_route_two_choice_workspace_bytes(int B, int N, int F, int64_t* bytes);
+int neptune_route_two_choice(int B, int N, int F, const double* d, const double* w, const double* r, const double* Kj,
+                             const uint8_t* c, uint8_t* c_out, double* x, double* n_out, double* obj_out,
+                             int32_t* feas_out, int32_t* iters_out, int max_iters,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- (d) EFTTC greedy -----------------------------------------------------------------------------
  * Replaces `EfttcStepBase.solve()` (`core/solvers/efttc/efttc_step1.py:39-90` and helpers
  * :92-312, score_local :356-439).  One thread block per instance; deterministic, same

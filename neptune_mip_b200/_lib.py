@@ -67,6 +67,8 @@ _SIGNATURES = {
     "neptune_route_lp_workspace_bytes": [_i, _i, _i, _i, _i64, C.POINTER(_i64)],
     "neptune_site_greedy_workspace_bytes": [_i, _i, _i, C.POINTER(_i64)],
     "neptune_site_greedy": [_i, _i, _i, _p, _p, _p, _p, _d, _i, _p, _p, _p, _i64, _p],
+    "neptune_route_two_choice_workspace_bytes": [_i, _i, _i, C.POINTER(_i64)],
+    "neptune_route_two_choice": [_i, _i, _i] + [_p] * 4 + [_p] * 6 + [C.POINTER(C.c_int32), _i, _p, _i64, _p],
     "neptune_lns_block_mode": [_i],
     "neptune_lns_search": [_i, _i, _i, _i, _d, _i, _i, _i, _d, C.c_uint64] + [_p] * 9 + [_i, _p, _i, _p, _p, _p, _p, _p],
     "neptune_eval_placements": [_i, _i, _i, _i, _d] + _INST + [_p] * 4 + [_p],

@@ -125,6 +125,127 @@ __global__ void k_site_init(int64_t n_cur, double* __restrict__ cur, double big,
   for (int64_t k = t; k < n_mem; k += nt) memfree[k] = Mj[k];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Two-choice routing of a placement at sizes where the per-instance routers (one block, serial marginal-flow loop)
+// do not finish (C4: 400 000 sources): every source (f, i) sends the share theta[j1] to its nearest pod j1 and the rest
+// to its second-nearest pod j2; theta[j] <= 1 is lowered until node j's CPU row holds:
+//     P[j] theta[j] + Pfix[j] + S[j] <= K[j],   P = splittable primary load, Pfix = primaries without a second pod,
+//     S[j] = spill that arrives from other nodes' sources = sum w r[f,j] (1 - theta[j1]).
+// theta starts at 1 and only decreases (S only grows), so the iteration converges to the largest feasible theta.  Loads
+// are accumulated in fixed point (integer adds commute): deterministic.  A pod that is nobody's nearest is closed
+// first.  Rows of the model it answers: constrain_handle_all_requests + constrain_CPU_usage
+// (constraints_step1.py:27-33, 57-65) with the objective of objectives.py:4-11 evaluated on the x it writes.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr double kTcFx = 1073741824.0;           // 2^30
+
+__global__ void __launch_bounds__(kSiteThreads)
+k_tc_nearest(int N, int F, const double* __restrict__ d0, const uint8_t* __restrict__ c0, int* __restrict__ j1o,
+             int* __restrict__ j2o, int* __restrict__ prim) {
+  const int b = blockIdx.z, f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ int s_list[];                // pods of f (any order: the choice below breaks ties by node index)
+  __shared__ int s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const uint8_t* __restrict__ c = c0 + ((int64_t)b * F + f) * N;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) if (c[j]) s_list[atomicAdd(&s_n, 1)] = j;
+  __syncthreads();
+  if (i >= N) return;
+  const double* __restrict__ di = d0 + (int64_t)b * N * N + (int64_t)i * N;
+  double v1 = INFINITY, v2 = INFINITY; int a1 = -1, a2 = -1;
+  const int n = s_n;
+  for (int q = 0; q < n; ++q) {
+    const int j = s_list[q];
+    const double v = di[j];
+    if (v < v1 || (v == v1 && j < a1)) { v2 = v1; a2 = a1; v1 = v; a1 = j; }
+    else if (v < v2 || (v == v2 && j < a2)) { v2 = v; a2 = j; }
+  }
+  const int64_t o = ((int64_t)b * F + f) * N + i;
+  j1o[o] = a1; j2o[o] = a2;
+  if (a1 >= 0) atomicAdd(&prim[((int64_t)b * F + f) * N + a1], 1);
+}
+
+__global__ void k_tc_close(int64_t n, uint8_t* __restrict__ c, const int* __restrict__ prim) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n && c[t] && prim[t] == 0) c[t] = 0;
+}
+
+// which = 0: P and Pfix (once); which = 1: the spill S at the current theta
+__global__ void __launch_bounds__(kSiteThreads)
+k_tc_loads(int N, int F, const double* __restrict__ w0, const double* __restrict__ r0, const int* __restrict__ j1o,
+           const int* __restrict__ j2o, const double* __restrict__ theta0, unsigned long long* __restrict__ P,
+           unsigned long long* __restrict__ Pfix, unsigned long long* __restrict__ S, int which) {
+  const int b = blockIdx.z, f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int64_t o = ((int64_t)b * F + f) * N + i;
+  const double wv = w0[o];
+  const int a1 = j1o[o], a2 = j2o[o];
+  if (wv <= 0.0 || a1 < 0) return;
+  const double* __restrict__ r = r0 + ((int64_t)b * F + f) * N;
+  if (which == 0) {
+    const unsigned long long q = (unsigned long long)(fmin(wv * r[a1], 1e9) * kTcFx + 0.5);
+    atomicAdd((a2 >= 0 ? P : Pfix) + (int64_t)b * N + a1, q);
+  } else if (a2 >= 0) {
+    const double sp = wv * r[a2] * (1.0 - theta0[(int64_t)b * N + a1]);
+    if (sp > 0.0) atomicAdd(S + (int64_t)b * N + a2, (unsigned long long)(fmin(sp, 1e9) * kTcFx + 0.5));
+  }
+}
+
+__global__ void k_tc_theta(int64_t n, int N, const double* __restrict__ K, const unsigned long long* __restrict__ P,
+                           const unsigned long long* __restrict__ Pfix, const unsigned long long* __restrict__ S,
+                           double* __restrict__ theta, int* __restrict__ changed, int* __restrict__ over) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const double p = (double)P[t] / kTcFx, pf = (double)Pfix[t] / kTcFx, sp = (double)S[t] / kTcFx;
+  const double cap = K[t] * (1.0 - 1e-9);
+  const double th = theta[t];
+  double want = p > 0.0 ? (cap - sp - pf) / p : 1.0;
+  want = fmin(fmax(want, 0.0), th);                            // only ever lowered
+  if (want < th - 1e-12) { theta[t] = want; atomicAdd(changed, 1); }
+  if (p * want + pf + sp > K[t] * (1.0 + 1e-9) + 1e-9) atomicAdd(over + t / N, 1);      // still above capacity at this theta (per instance)
+}
+
+__global__ void __launch_bounds__(kSiteThreads)
+k_tc_write(int N, int F, const double* __restrict__ d0, const double* __restrict__ w0, const int* __restrict__ j1o,
+           const int* __restrict__ j2o, const double* __restrict__ theta0, double* __restrict__ x0,
+           double* __restrict__ part) {
+  const int b = blockIdx.z, f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double red[32];
+  double cost = 0.0;
+  if (i < N) {
+    const int64_t o = ((int64_t)b * F + f) * N + i;
+    const int a1 = j1o[o], a2 = j2o[o];
+    if (a1 >= 0) {
+      const double th = a2 >= 0 ? theta0[(int64_t)b * N + a1] : 1.0;
+      const double* __restrict__ di = d0 + (int64_t)b * N * N + (int64_t)i * N;
+      if (x0) {
+        double* __restrict__ xr = x0 + (((int64_t)b * N + i) * F + f) * N;
+        xr[a1] = th;
+        if (a2 >= 0 && th < 1.0) xr[a2] = 1.0 - th;
+      }
+      cost = w0[o] * (th * di[a1] + (a2 >= 0 ? (1.0 - th) * di[a2] : 0.0));
+    }
+  }
+  const double s = block_sum(cost, red);
+  if (threadIdx.x == 0) part[((int64_t)b * F + f) * gridDim.x + blockIdx.x] = s;
+}
+
+__global__ void k_tc_finish(int N, int F, int nblk, const double* __restrict__ part, const uint8_t* __restrict__ c0,
+                            const int* __restrict__ over, double* __restrict__ n_out, double* __restrict__ obj,
+                            int32_t* __restrict__ feas) {
+  const int b = blockIdx.x;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    int any = 0;
+    for (int f = 0; f < F; ++f) any |= c0[((int64_t)b * F + f) * N + j];
+    n_out[(int64_t)b * N + j] = any ? 1.0 : 0.0;
+  }
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int64_t k = 0; k < (int64_t)F * nblk; ++k) s += part[(int64_t)b * F * nblk + k];      // fixed order
+    obj[b] = s;
+    feas[b] = over[b] == 0 ? 1 : 0;
+  }
+}
+
 static inline int64_t site_align(int64_t v) { return (v + 255) & ~(int64_t)255; }
 
 }  // namespace neptune
@@ -183,6 +304,69 @@ extern "C" int neptune_site_greedy(int B, int N, int F, const double* d, const d
       h_prev = h;
     }
   }
+  NEPTUNE_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int neptune_route_two_choice_workspace_bytes(int B, int N, int F, int64_t* bytes) {
+  if (B <= 0 || N <= 0 || F <= 0 || !bytes) return NEPTUNE_E_ARG;
+  const int64_t fn = (int64_t)B * F * N, nblk = (N + kSiteThreads - 1) / kSiteThreads;
+  *bytes = 3 * site_align(fn * 4) + 4 * site_align((int64_t)B * N * 8) + site_align((int64_t)B * F * nblk * 8) + site_align(4 * ((int64_t)B + 1)) + 256;
+  return 0;
+}
+
+extern "C" int neptune_route_two_choice(int B, int N, int F, const double* d, const double* w, const double* r,
+                                        const double* Kj, const uint8_t* c, uint8_t* c_out, double* x, double* n_out,
+                                        double* obj_out, int32_t* feas_out, int32_t* iters_out, int max_iters,
+                                        void* workspace, int64_t workspace_bytes, void* stream) {
+  if (B <= 0 || N <= 0 || F <= 0 || !d || !w || !r || !Kj || !c || !c_out || !n_out || !obj_out || !feas_out ||
+      !workspace || max_iters <= 0)
+    return NEPTUNE_E_ARG;
+  int64_t need = 0;
+  neptune_route_two_choice_workspace_bytes(B, N, F, &need);
+  if (workspace_bytes < need) return NEPTUNE_E_NOMEM;
+  if (F > 65535 || B > 65535) return NEPTUNE_E_SIZE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t fn = (int64_t)B * F * N, bn = (int64_t)B * N;
+  const int nblk = (N + kSiteThreads - 1) / kSiteThreads;
+  char* p = (char*)workspace;
+  int* j1 = (int*)p; p += site_align(fn * 4);
+  int* j2 = (int*)p; p += site_align(fn * 4);
+  int* prim = (int*)p; p += site_align(fn * 4);
+  double* theta = (double*)p; p += site_align(bn * 8);
+  unsigned long long* P = (unsigned long long*)p; p += site_align(bn * 8);
+  unsigned long long* Pfix = (unsigned long long*)p; p += site_align(bn * 8);
+  unsigned long long* S = (unsigned long long*)p; p += site_align(bn * 8);
+  double* part = (double*)p; p += site_align((int64_t)B * F * nblk * 8);
+  int* d_flags = (int*)p;                        // [0] changed, [1 + b] nodes of instance b still above capacity
+  const dim3 gfn(nblk, F, B);
+  const size_t sm = (size_t)N * sizeof(int);
+  if (sm > 200 * 1024) return NEPTUNE_E_SIZE;
+  NEPTUNE_CUDA_OK(cudaFuncSetAttribute(k_tc_nearest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  NEPTUNE_CUDA_OK(cudaMemcpyAsync(c_out, c, (size_t)fn, cudaMemcpyDeviceToDevice, s));
+  // nearest and second-nearest pod of every source; pods that are nobody's nearest are closed, then once more
+  for (int pass = 0; pass < 2; ++pass) {
+    NEPTUNE_CUDA_OK(cudaMemsetAsync(prim, 0, (size_t)fn * 4, s));
+    { k_tc_nearest<<<gfn, kSiteThreads, sm, s>>>(N, F, d, c_out, j1, j2, prim); NEPTUNE_COUNT(1); }
+    if (pass == 0) { k_tc_close<<<(int)((fn + 255) / 256), 256, 0, s>>>(fn, c_out, prim); NEPTUNE_COUNT(1); }
+  }
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(P, 0, (size_t)bn * 8, s));
+  NEPTUNE_CUDA_OK(cudaMemsetAsync(Pfix, 0, (size_t)bn * 8, s));
+  { k_site_init<<<4 * kNumSMs, 256, 0, s>>>(bn, theta, 1.0, 0, nullptr, nullptr); NEPTUNE_COUNT(1); }
+  { k_tc_loads<<<gfn, kSiteThreads, 0, s>>>(N, F, w, r, j1, j2, theta, P, Pfix, S, 0); NEPTUNE_COUNT(1); }
+  int it = 0, h[1] = {1};
+  for (; it < max_iters && h[0]; ++it) {
+    NEPTUNE_CUDA_OK(cudaMemsetAsync(S, 0, (size_t)bn * 8, s));
+    NEPTUNE_CUDA_OK(cudaMemsetAsync(d_flags, 0, 4 * ((size_t)B + 1), s));
+    { k_tc_loads<<<gfn, kSiteThreads, 0, s>>>(N, F, w, r, j1, j2, theta, P, Pfix, S, 1); NEPTUNE_COUNT(1); }
+    { k_tc_theta<<<(int)((bn + 255) / 256), 256, 0, s>>>(bn, N, Kj, P, Pfix, S, theta, d_flags, d_flags + 1); NEPTUNE_COUNT(1); }
+    NEPTUNE_CUDA_OK(cudaMemcpyAsync(h, d_flags, 4, cudaMemcpyDeviceToHost, s));
+    NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
+  }
+  if (iters_out) *iters_out = it;
+  if (x) NEPTUNE_CUDA_OK(cudaMemsetAsync(x, 0, (size_t)B * N * F * N * 8, s));
+  { k_tc_write<<<gfn, kSiteThreads, 0, s>>>(N, F, d, w, j1, j2, theta, x, part); NEPTUNE_COUNT(1); }
+  { k_tc_finish<<<B, 256, 0, s>>>(N, F, nblk, part, c_out, d_flags + 1, n_out, obj_out, feas_out); NEPTUNE_COUNT(1); }
   NEPTUNE_LAUNCH_OK();
   return 0;
 }

@@ -345,6 +345,29 @@ def site_greedy(inst: InstanceBatch, max_rounds: int = 0):
     return c, info
 
 
+def route_two_choice(inst: InstanceBatch, c_u8: torch.Tensor, want_x=True, max_iters=500):
+    """Nearest / second-nearest routing with per-node shares lowered until the CPU rows hold (`neptune_route_two_choice`):
+    the router for sizes the per-instance ones do not reach.  c_u8[B,F,N] ->
+    (c_out uint8[B,F,N], x[B,N,F,N] or None, n[B,N], obj[B], feasible int32[B], iterations)."""
+    _require_cuda()
+    lib = _lib.load()
+    dev = inst.d.device
+    assert c_u8.shape == (inst.B, inst.F, inst.N) and c_u8.is_contiguous()
+    need = C.c_int64()
+    check(lib.neptune_route_two_choice_workspace_bytes(inst.B, inst.N, inst.F, C.byref(need)), "neptune_route_two_choice_workspace_bytes")
+    ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    c_out = torch.empty_like(c_u8)
+    x = torch.empty((inst.B, inst.N, inst.F, inst.N), dtype=torch.float64, device=dev) if want_x else None
+    n = torch.empty((inst.B, inst.N), dtype=torch.float64, device=dev)
+    obj = torch.empty(inst.B, dtype=torch.float64, device=dev)
+    feas = torch.empty(inst.B, dtype=torch.int32, device=dev)
+    iters = C.c_int32(0)
+    check(lib.neptune_route_two_choice(inst.B, inst.N, inst.F, _ptr(inst.d), _ptr(inst.w), _ptr(inst.r), _ptr(inst.Kj),
+                                       _ptr(c_u8), _ptr(c_out), _ptr(x), _ptr(n), _ptr(obj), _ptr(feas), C.byref(iters),
+                                       max_iters, _ptr(ws), ws.numel(), _stream()), "neptune_route_two_choice")
+    return c_out, x, n, obj, feas, int(iters.value)
+
+
 def u8_to_f64(t: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty(t.shape, dtype=torch.float64, device=t.device)

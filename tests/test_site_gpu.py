@@ -45,9 +45,45 @@ def test_device_greedy_equals_the_oracle(name, make):
         assert info[b].cpu().tolist() == [rounds, pods]
 
 
+def test_oracle_two_choice_routing_keeps_the_rows():
+    """numpy statement of the router: every source routed (rows of x sum to 1), CPU rows hold when it reports feasible"""
+    for (N, F, s, k) in [(12, 5, 1, 25), (20, 5, 1, 100), (50, 10, 2, 200)]:
+        a = arrays_of(synth.random_payload(N, F, s, node_cores=k))
+        c, _, _ = osite.solve(a)
+        c2, x, obj, feas, it = osite.route_two_choice(a, c)
+        assert feas and np.abs(x.sum(axis=2) - 1.0).max() <= 1e-12
+        load = np.einsum("ifj,fi,fj->j", x, a["w"], a["r"])
+        assert (load <= a["Kj"] * (1 + 1e-9)).all()
+        assert abs(obj - float(np.einsum("ifj,ij,fi->", x, a["d"], a["w"]))) <= 1e-9 * obj
+        assert ((x.sum(axis=0) > 0) <= (c2 > 0)).all()                      # flows only to open pods
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(12, 5, 1, 25), (20, 5, 1, 100), (50, 10, 2, 200), (50, 10, 3, 60), (300, 7, 0, None)])
+def test_device_two_choice_routing_equals_the_oracle(shape):
+    """same nearest / second-nearest pods, same shares (the device accumulates loads in 2^-30 fixed point: 1e-7)"""
+    from neptune_mip_b200 import device
+    N, F, s, k = shape
+    p = synth.random_payload(N, F, s, node_cores=k)
+    a = arrays_of(p)
+    inst = cuda_batch([p])
+    c, _ = device.site_greedy(inst)
+    c2, x, n, obj, feas, it = device.route_two_choice(inst, c)
+    wc, wx, wobj, wfeas, wit = osite.route_two_choice(a, c[0].cpu().numpy())
+    assert np.array_equal(c2[0].cpu().numpy(), wc)
+    assert bool(int(feas.cpu()[0])) == wfeas
+    if wfeas:
+        assert np.abs(x[0].cpu().numpy() - wx).max() <= 1e-6
+        assert abs(float(obj.cpu()[0]) - wobj) <= 1e-7 * (1 + abs(wobj))
+        load = np.einsum("ifj,fi,fj->j", x[0].cpu().numpy(), a["w"], a["r"])
+        assert (load <= a["Kj"] * (1 + 1e-9) + 1e-9).all()
+    c3, x3, _, obj3, _, _ = device.route_two_choice(inst, c)
+    assert np.array_equal(x3.cpu().numpy(), x.cpu().numpy()) and float(obj3.cpu()[0]) == float(obj.cpu()[0])      # deterministic
+
+
 @pytest.mark.gpu
 def test_c4_feasible_placement():
-    """BASELINE config 4: 2000 nodes x 200 functions.  Greedy placement -> capacity-aware routing -> the reference's
+    """BASELINE config 4: 2000 nodes x 200 functions.  Greedy placement -> two-choice routing -> the reference's
     checkers: every flag set (handle_all_requests, memory, CPU, c<->x, n<->c)."""
     import torch
     from neptune_mip_b200 import device
@@ -56,7 +92,7 @@ def test_c4_feasible_placement():
     inst = device.InstanceBatch.from_datas([data_to_solver_input(synth.random_payload(2000, 200, 0, node_cores=None), 1, with_db=False)])
     c, info = device.site_greedy(inst)
     assert int((c[0].sum(dim=1) == 0).sum()) == 0
-    c2, x, n, obj, feas = device.route_capacitated(inst, c)
+    c2, x, n, obj, feas, iters = device.route_two_choice(inst, c)
     assert int(feas.cpu()[0]) == 1
     flags, scores = device.check_solution(inst, x, device.u8_to_f64(c2), n)
     fl = int(flags.cpu()[0])

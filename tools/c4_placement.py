@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE config 4 (2000 nodes x 200 functions) on ONE GPU: a checked placement and the bracket around it.
 
-  greedy placement (k_site_*, csrc/site.cu) -> CPU-capacity-aware routing (k_route_cap) -> the reference's checkers (k_check)
+  greedy placement (k_site_*, csrc/site.cu) -> two-choice routing (k_tc_*) -> the reference's checkers (k_check)
   -> lower bound of the slot-cut LP relaxation after a bounded number of matrix-free PDHG iterations (the dual
      objective with the box terms is a valid bound at every iterate).
 
@@ -37,7 +37,7 @@ def record(n_nodes=2000, n_funcs=200, lp_iters=512, seed=0, efttc=False):
         return e0.elapsed_time(e1), out
 
     ms_e, (c, info) = timed(lambda: device.site_greedy(inst))
-    ms_r, (c2, x, n, obj, feas) = timed(lambda: device.route_capacitated(inst, c))
+    ms_r, (c2, x, n, obj, feas, route_iters) = timed(lambda: device.route_two_choice(inst, c))
     ms_c, (flags, scores) = timed(lambda: device.check_solution(inst, x, device.u8_to_f64(c2), n))
     fl = int(flags.cpu()[0])
     names = {"handle_all_requests": OK_HANDLE, "memory": OK_MEMORY, "cpu": OK_CPU, "c_according_to_x": OK_C_X,
@@ -47,8 +47,8 @@ def record(n_nodes=2000, n_funcs=200, lp_iters=512, seed=0, efttc=False):
     del near_x
     rec = {"workload": f"C4: {n_nodes} nodes x {n_funcs} functions, one instance, one GPU",
            "placement": "round-robin delay-improvement greedy (k_site_*: EFTTC's move, every function proposes per round) + "
-                        "CPU-capacity-aware routing (k_route_cap); the searches stop at N = 768 / 128",
-           "greedy_rounds": int(info.cpu()[0, 0]), "pods": int(c2.sum().item()),
+                        "two-choice routing (k_tc_*: nearest / second-nearest pod, shares lowered until the CPU rows hold); the searches stop at N = 768 / 128",
+           "greedy_rounds": int(info.cpu()[0, 0]), "routing_iterations": route_iters, "pods": int(c2.sum().item()),
            "functions_without_pod": int((c2[0].sum(dim=1) == 0).sum().item()),
            "objective_min_delay": float(obj.cpu()[0]), "objective_if_every_source_took_its_nearest_pod": near_obj,
            "feasible": bool(int(feas.cpu()[0])) and all(bool(fl & v) for v in names.values()),
