@@ -371,6 +371,13 @@ def run_ours(args):
                 extra["c3_pdhg"] = c3_pdhg(peak)
             except Exception as e:  # pragma: no cover
                 extra["c3_pdhg"] = {"error": f"{type(e).__name__}: {e}"}
+        if rank == 0 and world == 1:
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import c4_placement
+                extra["c4_placement"] = c4_placement.record(args.c4_nodes, args.c4_funcs, lp_iters=64)
+            except Exception as e:  # pragma: no cover
+                extra["c4_placement"] = {"error": f"{type(e).__name__}: {e}"}
         if world > 1:
             try:
                 extra["c4_sharded"] = c4_sharded(args, rank, world, peak)
