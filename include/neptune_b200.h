@@ -163,10 +163,13 @@ int neptune_pdhg_mf_solve(int B, int N, int F, int kind,
  * neptune_assemble(kind, NEPTUNE_FLAG_STRENGTHEN).  The new rows and columns are O(N): they live in the small-vector
  * kernel, the streaming pass is unchanged.  d_obj[B][N][N] is the delay matrix AS IT ENTERS THE OBJECTIVE
  * (objectives.py:24-52): zeros for kind 1, d * (1 - alpha) / (largest workload-weighted delay) for kind 2; obj_n is
- * the coefficient of every n[j] (1, or alpha / N).  Workspace: neptune_pdhg_mf_workspace_bytes. */
+ * the coefficient of every n[j] (1, or alpha / N).  big_m[B][N] (or NULL for the reference's 10^6) is the M of row C5a per
+ * node: any valid bound on the pods node j can hold keeps the MIP unchanged and tightens the relaxation ("node cut":
+ * with floor(Mj / m) the LP bound of the combined objective goes from 5 % to 81-90 % of the MIP optimum on the small
+ * goldens).  Workspace: neptune_pdhg_mf_workspace_bytes. */
 int neptune_pdhg_mf_solve_util(int B, int N, int F, int kind, const double* d_obj, const double* w,
                                const double* r, const double* m, const double* Mj, const double* Kj,
-                               const double* cost, double budget, double obj_n,
+                               const double* cost, double budget, double obj_n, const double* big_m,
                                const neptune_pdhg_params* prm, double* x, double* y,
                                neptune_pdhg_result* result_d, void* workspace, int64_t workspace_bytes,
                                void* stream);

@@ -44,7 +44,7 @@ _SIGNATURES = {
     "neptune_pdhg_solve": [_i, _i64, _i64, _i64] + [_p] * 11 + [C.POINTER(PdhgParams)] + [_p] * 3 + [_p, _i64, _p],
     "neptune_pdhg_mf_workspace_bytes": [_i, _i, _i, C.POINTER(_i64)],
     "neptune_pdhg_mf_geometry": [_i, _i, _i, C.POINTER(C.c_int32)],
-    "neptune_pdhg_mf_solve_util": [_i, _i, _i, _i] + [_p] * 7 + [_d, _d] + [C.POINTER(PdhgParams)] + [_p] * 3 + [_p, _i64, _p],
+    "neptune_pdhg_mf_solve_util": [_i, _i, _i, _i] + [_p] * 7 + [_d, _d, _p] + [C.POINTER(PdhgParams)] + [_p] * 3 + [_p, _i64, _p],
     "neptune_pdhg_mf_solve": [_i, _i, _i, _i] + [_p] * 6 + [C.POINTER(PdhgParams)] + [_p] * 3 + [_p, _i64, _p],
     "neptune_pdhg_mf_step_bytes": [_i, _i, _i, C.POINTER(_i64)],
     "neptune_pdhg_mf_column_sums": [_i, _i, _i] + [_p] * 9 + [_p, _i64, _p],

@@ -86,7 +86,7 @@ def solve_batch(inst: device.InstanceBatch, prm: BatchParams, time_pdhg: bool = 
             if time_pdhg:
                 e0.record()
             xs, ys, lp_res = device.pdhg_mf_solve(inst_lp, max_iters=prm.lp_iters, check_every=prm.lp_check_every,
-                                                  eps_rel=1e-6, eps_abs=1e-9, kind=kk, alpha=prm.alpha)
+                                                  eps_rel=1e-6, eps_abs=1e-9, kind=kk, alpha=prm.alpha, node_cut=prm.lp_cut)
             lam0 = ys[:, 3 * F * N + N:3 * F * N + 2 * N].contiguous()       # duals of the CPU rows C4
             if kk == 2:      # the combined objective scales the delays: prices back in delay units for the search
                 a_d = objective_weights(inst, kind, prm.alpha)[0]

@@ -75,9 +75,11 @@ static MfGeo make_geo(int N, int F, int B, int kind = NEPTUNE_KIND_MIN_DELAY) {
 // d is the delay matrix AS IT ENTERS THE OBJECTIVE: the caller scales it for the combined objective ((1 - alpha) / the
 // largest workload-weighted delay, objectives.py:36-52) and passes zeros for min-utilisation; nothing else reads it.
 // cost / budget / objn (objective coefficient of every n[j]) are read only when the model has node columns.
-struct MfIn { const double *d, *w, *r, *m, *Mj, *Kj; const double* cost; double budget, objn; };
+struct MfIn { const double *d, *w, *r, *m, *Mj, *Kj; const double* cost; double budget, objn; const double* bigm; };
 
 constexpr double kMfBigM = 1e6;        // constraints_step1.py:1
+// the big M of row C5a for node j: the reference's 10^6, or the caller's (valid) bound on the pods node j can hold
+__device__ __forceinline__ double mf_bigm(const MfIn& in, int64_t bj) { return in.bigm ? in.bigm[bj] : kMfBigM; }
 
 struct MfSt {
   double *x, *y, *xsum, *ysum;   // canonical vectors [B][cols] / [B][rows]
@@ -584,16 +586,16 @@ k_mf_small(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int mask, con
         }
         double* __restrict__ nv = st.x + (int64_t)b * G.cols + G.X + C;
         double* __restrict__ ns = st.xsum + (int64_t)b * G.cols + G.X + C;
-        const double cj = in.cost[(int64_t)b * N + j];
+        const double cj = in.cost[(int64_t)b * N + j], Mb = mf_bigm(in, (int64_t)b * N + j);
         const double y5a = y[G.r5 + 2 * j], y5b = y[G.r5 + 2 * j + 1], y6 = y[G.r6 + j];
-        const double gn = in.objn - kMfBigM * y5a - y5b + cj * y6;
+        const double gn = in.objn - Mb * y5a - y5b + cj * y6;
         const double no = nv[j];
-        double nn = no - tau * gn / (kMfBigM + 1.0 + fabs(cj));
+        double nn = no - tau * gn / (Mb + 1.0 + fabs(cj));
         nn = fmin(fmax(nn, 0.0), 1.0);
         const double nbar = 2.0 * nn - no;
         nv[j] = nn; ns[j] += nn;
-        double sr = sigma / ((double)F + kMfBigM);
-        double v5 = y5a + sr * (a5 - kMfBigM * nbar);
+        double sr = sigma / ((double)F + Mb);
+        double v5 = y5a + sr * (a5 - Mb * nbar);
         v5 = v5 - sr * fmin(v5 / sr, 0.0);                          // C5a: (-inf, 0]
         y[G.r5 + 2 * j] = v5; ys[G.r5 + 2 * j] += v5;
         sr = sigma / ((double)F + 1.0);
@@ -660,15 +662,15 @@ k_mf_eval_small(MfGeo G, MfIn in, MfSt st, Ctl* __restrict__ ctl, int which) {
     if (G.with_n) {
       double a5 = 0.0;
       for (int f = 0; f < F; ++f) a5 += cv[(int64_t)f * N + j] * sc;
-      const double nj = xvec[G.X + C + j] * sc, cj = in.cost[(int64_t)b * N + j];
+      const double nj = xvec[G.X + C + j] * sc, cj = in.cost[(int64_t)b * N + j], Mb = mf_bigm(in, (int64_t)b * N + j);
       const double y5a = yv[G.r5 + 2 * j] * sc, y5b = yv[G.r5 + 2 * j + 1] * sc, y6 = yv[G.r6 + j] * sc;
-      viol = fmax(a5 - kMfBigM * nj, 0.0); pres2 += viol * viol;
+      viol = fmax(a5 - Mb * nj, 0.0); pres2 += viol * viol;
       viol = fmin(a5 - nj + kEps, 0.0); pres2 += viol * viol;
       viol = fmax(cj * nj - in.budget, 0.0); pres2 += viol * viol;
       if (y5a < 0.0) dres2 += y5a * y5a;                           // hi = 0: nothing for the dual objective
       if (y5b > 0.0) dres2 += y5b * y5b; else dobj += kEps * y5b;
       if (y6 > 0.0) dobj -= in.budget * y6; else dres2 += y6 * y6;
-      const double rcn = in.objn - kMfBigM * y5a - y5b + cj * y6;
+      const double rcn = in.objn - Mb * y5a - y5b + cj * y6;
       dobj += fmin(rcn, 0.0);                                     // n in [0, 1]
       pobj += in.objn * nj;
     }
@@ -764,7 +766,7 @@ __global__ void k_mf_setup_norms(MfGeo G, MfIn in, MfSt st, Ctl* __restrict__ ct
     for (int j = 0; j < N; ++j) {
       const double cj = fabs(in.cost[(int64_t)b * N + j]);
       nbs2n += bud2 * (cj != 0.0 ? 1.0 / cj : 1.0);
-      ncs2n += in.objn * in.objn / (kMfBigM + 1.0 + cj);
+      ncs2n += in.objn * in.objn / (mf_bigm(in, (int64_t)b * N + j) + 1.0 + cj);
     }
   }
   double* acc = ctl[b].acc;
@@ -806,7 +808,7 @@ k_mf_apply_restart(MfGeo G, MfIn in, MfSt st, double* __restrict__ xres, double*
         const int f = (int)((k - G.X) / N);
         diag = 1.0 / ((G.with_n ? 3.0 : 1.0) + fabs(m[f]) + (double)N);
       } else {
-        diag = 1.0 / (kMfBigM + 1.0 + fabs(in.cost[(int64_t)b * N + (k - G.X - G.C)]));
+        diag = 1.0 / (mf_bigm(in, (int64_t)b * N + (k - G.X - G.C)) + 1.0 + fabs(in.cost[(int64_t)b * N + (k - G.X - G.C)]));
       }
       const int64_t q = (int64_t)b * G.cols + k;
       const double nv = (action == 1) ? st.xsum[q] * inv : st.x[q];
@@ -820,7 +822,7 @@ k_mf_apply_restart(MfGeo G, MfIn in, MfSt st, double* __restrict__ xres, double*
       else if (row < G.r3) diag = st.S2[b];
       else if (row < G.r4) diag = 1.0 / (double)N;
       else if (row < G.r5) diag = st.S4[(int64_t)b * N + (row - G.r4)];
-      else if (row < G.r6) diag = ((row - G.r5) & 1) ? 1.0 / ((double)F + 1.0) : 1.0 / ((double)F + kMfBigM);
+      else if (row < G.r6) diag = ((row - G.r5) & 1) ? 1.0 / ((double)F + 1.0) : 1.0 / ((double)F + mf_bigm(in, (int64_t)b * N + ((row - G.r5) >> 1)));
       else if (row < G.rs) { const double cj = fabs(in.cost[(int64_t)b * N + (row - G.r6)]); diag = cj != 0.0 ? 1.0 / cj : 1.0; }
       else diag = 0.5;
       const int64_t q = (int64_t)b * G.rows + row;
@@ -989,7 +991,7 @@ extern "C" int neptune_pdhg_mf_workspace_bytes(int B, int N, int F, int64_t* byt
 
 static int mf_solve_impl(int B, int N, int F, int kind, const double* d, const double* w, const double* r,
                          const double* m, const double* Mj, const double* Kj, const double* cost, double budget,
-                         double objn, const neptune_pdhg_params* prm, double* x, double* y,
+                         double objn, const double* bigm, const neptune_pdhg_params* prm, double* x, double* y,
                          neptune_pdhg_result* result_d, void* workspace, int64_t workspace_bytes, void* stream) {
   if (B <= 0 || N <= 0 || F <= 0) return NEPTUNE_E_ARG;
   if (kind < 0 || kind > 2) return NEPTUNE_E_ARG;
@@ -1026,7 +1028,7 @@ static int mf_solve_impl(int B, int N, int F, int kind, const double* d, const d
 
   MfPlan P{};
   P.B = B; P.G = make_geo(N, F, B, kind); P.s = s;
-  P.in = MfIn{d, w, r, m, Mj, Kj, cost, budget, objn};
+  P.in = MfIn{d, w, r, m, Mj, Kj, cost, budget, objn, bigm};
   const MfGeo& G = P.G;
   const MfWs W = mf_layout(B, G);
   char* base = (char*)workspace;
@@ -1129,18 +1131,18 @@ extern "C" int neptune_pdhg_mf_solve(int B, int N, int F, int kind, const double
                                      neptune_pdhg_result* result_d, void* workspace, int64_t workspace_bytes,
                                      void* stream) {
   if (kind != NEPTUNE_KIND_MIN_DELAY) return NEPTUNE_E_ARG;      // node columns: neptune_pdhg_mf_solve_util
-  return mf_solve_impl(B, N, F, kind, d, w, r, m, Mj, Kj, nullptr, 0.0, 0.0, prm, x, y, result_d, workspace,
+  return mf_solve_impl(B, N, F, kind, d, w, r, m, Mj, Kj, nullptr, 0.0, 0.0, nullptr, prm, x, y, result_d, workspace,
                        workspace_bytes, stream);
 }
 
 extern "C" int neptune_pdhg_mf_solve_util(int B, int N, int F, int kind, const double* d_obj, const double* w,
                                           const double* r, const double* m, const double* Mj, const double* Kj,
-                                          const double* cost, double budget, double obj_n,
+                                          const double* cost, double budget, double obj_n, const double* big_m,
                                           const neptune_pdhg_params* prm, double* x, double* y,
                                           neptune_pdhg_result* result_d, void* workspace, int64_t workspace_bytes,
                                           void* stream) {
   if (kind != NEPTUNE_KIND_MIN_UTIL && kind != NEPTUNE_KIND_MIN_DELAY_UTIL) return NEPTUNE_E_ARG;
-  return mf_solve_impl(B, N, F, kind, d_obj, w, r, m, Mj, Kj, cost, budget, obj_n, prm, x, y, result_d, workspace,
+  return mf_solve_impl(B, N, F, kind, d_obj, w, r, m, Mj, Kj, cost, budget, obj_n, big_m, prm, x, y, result_d, workspace,
                        workspace_bytes, stream);
 }
 
@@ -1281,7 +1283,7 @@ static int mf_step_plan(MfPlan& P, int B, int N, int F, const double* d, const d
   const MfStepWs W = mf_step_layout(B, P.G);
   if (ws_bytes < (int64_t)W.total) return NEPTUNE_E_NOMEM;
   char* base = (char*)ws;
-  P.in = MfIn{d, w, r, m, Mj, Kj, nullptr, 0.0, 0.0};
+  P.in = MfIn{d, w, r, m, Mj, Kj, nullptr, 0.0, 0.0, nullptr};
   P.ctl = (Ctl*)(base + W.ctl);
   P.st = MfSt{x, y, xsum, ysum, (double*)(base + W.cbar), (double*)(base + W.P1), (double*)(base + W.P4),
               (double*)(base + W.PS), nullptr, (double*)(base + W.P3i), const_cast<double*>(S4),

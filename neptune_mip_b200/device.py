@@ -229,11 +229,13 @@ def objective_weights(inst: InstanceBatch, kind, alpha=0.5):
 
 def pdhg_mf_solve(inst: InstanceBatch, max_iters=20000, check_every=64, eps_rel=1e-6, eps_abs=1e-8,
                   x0: Optional[torch.Tensor] = None, y0: Optional[torch.Tensor] = None, workspace=None,
-                  scalar_kernel=False, rows_in_flight=0, _diag=0, kind="min_delay", alpha=0.5):
+                  scalar_kernel=False, rows_in_flight=0, _diag=0, kind="min_delay", alpha=0.5, node_cut=False):
     """Matrix-free PDHG on the strengthened relaxation (`neptune_pdhg_mf_solve`, and `neptune_pdhg_mf_solve_util`
     for the models with node columns): nothing is assembled, every coefficient is regenerated from the instance
     arrays.  Returns (x[B,cols], y[B,rows], results) in the canonical layout of
-    `assemble(inst, kind, flags=FLAG_STRENGTHEN)`."""
+    `assemble(inst, kind, flags=FLAG_STRENGTHEN)`.  `node_cut` (models with node columns): the big M of row C5a becomes
+    the number of pods node j can hold, floor(Mj / min_f m) capped by F -- valid for the MIP, and the relaxation then says
+    something about the node term."""
     _require_cuda()
     lib = _lib.load()
     from ._lib import FLAG_STRENGTHEN
@@ -260,9 +262,14 @@ def pdhg_mf_solve(inst: InstanceBatch, max_iters=20000, check_every=64, eps_rel=
         # the delay matrix as it enters the objective (objectives.py:24-52): zeros, or d scaled per instance
         a_d, a_u = objective_weights(inst, k, alpha)
         d_obj = (inst.d * a_d[:, None, None]).contiguous()
+        big_m = None
+        if node_cut:
+            m_min = inst.m.amin(dim=1, keepdim=True)
+            big_m = torch.where(m_min > 0, torch.floor(inst.Mj / torch.where(m_min > 0, m_min, torch.ones_like(m_min)) + 1e-9),
+                                torch.full_like(inst.Mj, float(inst.F))).clamp_(min=0.0, max=float(inst.F)).contiguous()
         check(lib.neptune_pdhg_mf_solve_util(inst.B, inst.N, inst.F, k, _ptr(d_obj), _ptr(inst.w), _ptr(inst.r),
                                              _ptr(inst.m), _ptr(inst.Mj), _ptr(inst.Kj), _ptr(inst.cost),
-                                             C.c_double(float(inst.budget)), C.c_double(float(a_u[0])), C.byref(prm),
+                                             C.c_double(float(inst.budget)), C.c_double(float(a_u[0])), _ptr(big_m), C.byref(prm),
                                              _ptr(x), _ptr(y), _ptr(res), _ptr(workspace), workspace.numel(), _stream()),
               "neptune_pdhg_mf_solve_util")
     out = np.frombuffer(res.cpu().numpy().tobytes(), dtype=_PDHG_DTYPE)

@@ -16,10 +16,22 @@ import scipy.sparse as sp
 EPS = 1e-6
 
 
-def strengthened(a, kind="min_delay", alpha=0.5):
+def node_cut_bigm(a):
+    """M of row C5a per node for the "node cut": the pods node j can hold, floor(Mj / min m) capped by F"""
+    mm = a["m"].min()
+    return np.clip(np.floor(a["Mj"] / mm + 1e-9), 0.0, float(a["F"])) if mm > 0 else np.full(a["N"], float(a["F"]))
+
+
+def strengthened(a, kind="min_delay", alpha=0.5, bigm=None):
     from oracle import model as omodel
     m = omodel.build_step1(a, kind, alpha)
     N, F = a["N"], a["F"]; X = F * N * N
+    if bigm is not None:                                      # C5a rows: sum_f c[f,j] - M_j n[j] <= 0 with the caller's M_j
+        A = m["A"].tolil()
+        r5 = 3 * F * N + 2 * N
+        for jj in range(N):
+            A[r5 + 2 * jj, X + F * N + jj] = -float(bigm[jj])
+        m = dict(m); m["A"] = A.tocsr()
     q = np.arange(X); f = q // (N * N); j = q % N
     S = sp.csr_matrix((np.tile([1.0, -1.0], X), np.stack([q, X + f * N + j], 1).reshape(-1),
                        np.arange(0, 2 * X + 1, 2)), shape=(X, m["A"].shape[1]))
@@ -197,14 +209,15 @@ class MatrixFreeN(MatrixFree):
     (sum_f c[f,j] - n[j] >= -eps) and C6 (cost_j n[j] <= budget), `constraints_step1.py:69-80, 101-103`.  Everything
     new is O(N) or O(F*N): it lives in the small-vector kernel; the pass over x only sees another objective."""
 
-    def __init__(self, a, kind, alpha=0.5):
+    def __init__(self, a, kind, alpha=0.5, bigm=None):
         super().__init__(a)
         N, F = self.N, self.F
+        self.M = np.full(N, BIG_M) if bigm is None else np.asarray(bigm, dtype=float)
         self.obj, self.objn = util_objective(a, kind, alpha)
         self.cost, self.budget = a["cost"].astype(float), float(a["budget"])
         self.Tc = np.repeat((1.0 / (3.0 + a["m"] + N))[:, None], N, 1)
-        self.Tn = 1.0 / (BIG_M + 1.0 + np.abs(self.cost))
-        self.S5a, self.S5b = 1.0 / (F + BIG_M), 1.0 / (F + 1.0)
+        self.Tn = 1.0 / (self.M + 1.0 + np.abs(self.cost))
+        self.S5a, self.S5b = 1.0 / (F + self.M), 1.0 / (F + 1.0)
         self.S6 = np.where(self.cost != 0, 1.0 / np.where(self.cost != 0, np.abs(self.cost), 1.0), 1.0)
         Mj, Kj = a["Mj"], a["Kj"]
         bud2 = self.budget ** 2 if np.isfinite(self.budget) else 0.0
@@ -225,7 +238,7 @@ class MatrixFreeN(MatrixFree):
         cn = np.clip(self.c - tau * self.Tc * gc, 0.0, 1.0)
         cb = 2 * cn - self.c
         self.c = cn
-        gn = self.objn - BIG_M * self.y5a - self.y5b + self.cost * self.y6
+        gn = self.objn - self.M * self.y5a - self.y5b + self.cost * self.y6
         nn = np.clip(self.n - tau * self.Tn * gn, 0.0, 1.0)
         nbar = 2 * nn - self.n
         self.n = nn
@@ -235,7 +248,7 @@ class MatrixFreeN(MatrixFree):
         y2n = v - s * np.minimum(v / s, a["Mj"])
         a5 = cb.sum(axis=0)
         s = sig * self.S5a
-        v = self.y5a + s * (a5 - BIG_M * nbar)
+        v = self.y5a + s * (a5 - self.M * nbar)
         y5an = v - s * np.minimum(v / s, 0.0)
         s = sig * self.S5b
         v = self.y5b + s * (a5 - nbar)
@@ -277,11 +290,11 @@ class MatrixFreeN(MatrixFree):
         rcc = rcc0 + (y5a + y5b)[None, :]
         dobj += np.sum(np.minimum(rcc, 0)) - np.sum(np.minimum(rcc0, 0))
         a5 = c.sum(axis=0)
-        p2 += np.sum(np.maximum(a5 - BIG_M * n, 0) ** 2) + np.sum(np.minimum(a5 - n + EPS, 0) ** 2)
+        p2 += np.sum(np.maximum(a5 - self.M * n, 0) ** 2) + np.sum(np.minimum(a5 - n + EPS, 0) ** 2)
         p2 += np.sum(np.maximum(self.cost * n - self.budget, 0) ** 2)
         d2 += np.sum(np.minimum(y5a, 0) ** 2) + np.sum(np.maximum(y5b, 0) ** 2) + np.sum(np.minimum(y6, 0) ** 2)
         dobj += EPS * np.sum(np.minimum(y5b, 0)) - self.budget * np.sum(np.maximum(y6, 0))
-        rcn = self.objn - BIG_M * y5a - y5b + self.cost * y6
+        rcn = self.objn - self.M * y5a - y5b + self.cost * y6
         dobj += np.sum(np.minimum(rcn, 0))
         return p2, d2, float(np.sum(self.obj * x) + self.objn * np.sum(n)), dobj
 
@@ -352,11 +365,11 @@ def solve(mf: MatrixFree, max_iters=20000, check=64, eps=1e-6, verbose=False):
 
 
 
-def run_fixed(a, iters, kind="min_delay", alpha=0.5):
+def run_fixed(a, iters, kind="min_delay", alpha=0.5, bigm=None):
     """What `neptune_pdhg_mf_solve(max_iters = check_every = iters)` returns with unreachable tolerances:
     `iters` iterations, then the better (smaller KKT error) of the current iterate and the running average.
     Returns (x, y, info) with x / y in the canonical layout of the strengthened model."""
-    mf = MatrixFree(a) if kind == "min_delay" else MatrixFreeN(a, kind, alpha)
+    mf = MatrixFree(a) if kind == "min_delay" else MatrixFreeN(a, kind, alpha, bigm)
     sums = [np.zeros_like(t) for t in mf.state()]
     for _ in range(iters):
         mf.step()

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from helpers import arrays_of, float_payload
-from mf_reference import Generic, MatrixFree, MatrixFreeN, pc_diag, run_fixed, solve, strengthened
+from mf_reference import Generic, MatrixFree, MatrixFreeN, node_cut_bigm, pc_diag, run_fixed, solve, strengthened
 from neptune_mip_b200 import synth
 from oracle import mip as omip
 
@@ -77,14 +77,17 @@ def test_lp_value_sweep_against_highs(seed):
     assert abs(out["primal"] - lp["objective"]) <= tol and abs(out["dual"] - lp["objective"]) <= tol, (N, F, cores, out, lp["objective"])
 
 
+@pytest.mark.parametrize("cut", [False, True], ids=["M=1e6", "node-cut"])
 @pytest.mark.parametrize("kind", ["min_util", "min_delay_util"])
 @pytest.mark.parametrize("name,make", CASES[:3], ids=[c[0] for c in CASES[:3]])
-def test_matrix_free_iteration_with_node_variables_equals_csr_iteration(name, make, kind):
-    """the models with n[j] columns and C5a / C5b / C6 rows (reference neptune_step1.py:38-77): closed form == CSR"""
+def test_matrix_free_iteration_with_node_variables_equals_csr_iteration(name, make, kind, cut):
+    """the models with n[j] columns and C5a / C5b / C6 rows (reference neptune_step1.py:38-77): closed form == CSR,
+    with the reference's M = 10^6 and with the per-node M of the node cut"""
     a = arrays_of(make())
-    m = strengthened(a, kind, 0.5)
+    bigm = node_cut_bigm(a) if cut else None
+    m = strengthened(a, kind, 0.5, bigm)
     T, S = pc_diag(m)
-    g, mf = Generic(m, T, S), MatrixFreeN(a, kind, 0.5)
+    g, mf = Generic(m, T, S), MatrixFreeN(a, kind, 0.5, bigm)
     assert abs(g.omega - mf.omega) <= 1e-12 * g.omega
     assert abs(g.nb - mf.nb) <= 1e-12 * (1 + g.nb) and abs(g.nc - mf.nc) <= 1e-12 * (1 + g.nc)
     for _ in range(150):
@@ -94,3 +97,15 @@ def test_matrix_free_iteration_with_node_variables_equals_csr_iteration(name, ma
     assert np.abs(y - g.y).max() <= 1e-10 * (1 + np.abs(g.y).max())
     for u, v in zip(g.kkt(g.x, g.y), mf.kkt(mf.state())):
         assert abs(u - v) <= 1e-9 * (1 + abs(u))
+
+
+def test_node_cut_is_valid_and_tightens_the_relaxation():
+    """M_j = pods node j can hold: the MIP optimum is unchanged (every integer point satisfies the tighter row), the LP
+    bound moves from ~0 towards it"""
+    a = arrays_of(synth.random_payload(12, 5, 1, node_cores=25))
+    for kind in ("min_util", "min_delay_util"):
+        lp_ref = omip.solve_model(strengthened(a, kind, 0.5), relax=True)["objective"]
+        lp_cut = omip.solve_model(strengthened(a, kind, 0.5, node_cut_bigm(a)), relax=True)["objective"]
+        mip = omip.solve_step1(a, kind, 0.5, time_limit=60)
+        assert lp_ref <= lp_cut + 1e-9 <= mip["objective"] + 1e-6
+        assert lp_cut >= 0.4 * mip["objective"] and lp_ref <= 0.1 * mip["objective"]

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from helpers import arrays_of, cuda_batch, float_payload
-from mf_reference import MatrixFree, MatrixFreeN, run_fixed, solve, strengthened
+from mf_reference import MatrixFree, MatrixFreeN, node_cut_bigm, run_fixed, solve, strengthened
 from neptune_mip_b200 import synth
 from oracle import mip as omip
 
@@ -164,6 +164,26 @@ def test_node_variable_models_reach_the_highs_lp_optimum_and_the_csr_solver(kind
     assert abs(ra[0]["primal_obj"] - res[0]["primal_obj"]) <= 2 * tol
     n = x[0, -inst.N:].cpu().numpy()
     assert n.min() >= 0.0 and n.max() <= 1.0
+
+
+@pytest.mark.parametrize("kind", ["min_util", "min_delay_util"])
+def test_node_cut_iterates_and_lp_value(kind):
+    """per-node M of row C5a (`node_cut=True`): iterates equal the numpy statement with that M, and the converged value is
+    the HiGHS optimum of the oracle's matrix with the same coefficient -- far above the vacuous bound of M = 10^6"""
+    from neptune_mip_b200 import device
+    p = synth.random_payload(12, 5, 1, node_cores=25)
+    a = arrays_of(p)
+    inst = cuda_batch([p])
+    x, y, res = device.pdhg_mf_solve(inst, max_iters=96, check_every=96, eps_rel=1e-13, eps_abs=1e-15, kind=kind, node_cut=True)
+    xr, yr, info = run_fixed(a, 96, kind, 0.5, node_cut_bigm(a))
+    assert _close(x[0].cpu().numpy(), xr, 1e-9) and _close(y[0].cpu().numpy(), yr, 1e-9)
+    lp_cut = omip.solve_model(strengthened(a, kind, 0.5, node_cut_bigm(a)), relax=True)["objective"]
+    lp_ref = omip.solve_model(strengthened(a, kind, 0.5), relax=True)["objective"]
+    x, y, res = device.pdhg_mf_solve(inst, max_iters=60000, check_every=128, eps_rel=1e-6, eps_abs=1e-9, kind=kind, node_cut=True)
+    assert res[0]["converged"] == 1
+    tol = 1e-4 * (1 + abs(lp_cut))
+    assert abs(res[0]["primal_obj"] - lp_cut) <= tol and abs(res[0]["dual_obj"] - lp_cut) <= tol
+    assert res[0]["dual_obj"] > 5 * lp_ref
 
 
 def test_other_model_kinds_are_refused():
