@@ -99,7 +99,10 @@ typedef struct neptune_pdhg_params {
   int     ruiz_iters;       /* Ruiz equilibration passes (then one Pock-Chambolle pass) */
   int     reserved;         /* 0.  neptune_pdhg_mf_solve reads it as switches for measurements and tests:
                              * bit 0 = force the 8-byte iteration pass, bits 4..6 = tool diagnostics,
-                             * bits 8..10 = rows of a warp in flight (0 = default) */
+                             * bits 8..10 = rows of a warp in flight (0 = default), bit 11 = register passes whatever the
+                             * default, bit 12 = bulk-copy (cp.async.bulk) staged pass, bit 13 = the same with the running
+                             * sums by bulk reduction (even N <= 64; other shapes ignore both), bits 14..18 = its consumer
+                             * warps, bits 19..22 = cap on its stages */
   double  eps_rel;          /* termination: relative KKT tolerance */
   double  eps_abs;
 } neptune_pdhg_params;

@@ -31,6 +31,8 @@
 // pointer bumping: profiles/r02_pdhg_variants.md) -- none beat these two and they were removed.
 #include "common.cuh"
 #include "pdhg_ctl.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace neptune {
 
@@ -356,6 +358,10 @@ k_mf_iter2(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
     __syncthreads();
   }
 }
+
+}  // namespace neptune
+#include "pdhg_mf_bulk.cuh"      // k_mf_iter_bulk<RED>: the same pass with the streams staged by the bulk-copy engine
+namespace neptune {
 
 // ---------------------------------------------------------------------------------------------------
 // KKT pieces of a candidate (which = 0: current iterate, 1: running average): the same partial sums from a
@@ -884,6 +890,9 @@ struct MfPlan {
   int grid_iter, grid_eval, small_blocks, fused;
   int rows_in_flight;            // U of k_mf_iter<K, U> / k_mf_iter2<KP, U>
   int pair;                      // k_mf_iter2 (pairs of adjacent columns, 16-byte accesses) instead of k_mf_iter
+  int bulk;                      // k_mf_iter_bulk (streams staged through shared memory by the bulk-copy engine): 1 = four
+                                 // streams per stage, 2 = running sums by bulk reduction (two streams per stage)
+  BulkCfg bcfg;
   int diag;                      // tools only: bit 2 = time the small-vector kernel alone
 };
 
@@ -891,6 +900,13 @@ static void mf_launch_iter(const MfPlan& P) {
   if (P.diag & 4) return;          // tools: time the small-vector kernel alone
   const int64_t total = (int64_t)P.B * P.G.tiles_inst;
   const int g = (int)(total < P.grid_iter ? total : P.grid_iter);
+  if (P.bulk) {
+    const int threads = (P.bcfg.nw + 1) * 32;
+    if (P.bulk == 2) k_mf_iter_bulk<true><<<g, threads, P.bcfg.smem, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, P.bcfg);
+    else k_mf_iter_bulk<false><<<g, threads, P.bcfg.smem, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, P.bcfg);
+    NEPTUNE_COUNT(1);
+    return;
+  }
   if (P.pair) {
     if (P.rows_in_flight == 1) k_mf_iter2<1, 1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B);
     else k_mf_iter2<1, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B);
@@ -909,13 +925,45 @@ static void mf_launch_iter(const MfPlan& P) {
   NEPTUNE_COUNT(1);
 }
 
-// which pass runs and with how many rows in flight; `reserved`: bit 0 forces the 8-byte pass, bits 8..10 override U
+// the pass a solve takes when `reserved` does not say: NEPTUNE_MF_PASS = pair | bulk | bulkred (measurements), else the
+// compiled default
+constexpr int kMfDefaultBulk = 0;        // 0: register passes; 1: bulk-copy staging; 2: bulk-copy staging + bulk reduction
+static int mf_default_bulk() {
+  const char* e = getenv("NEPTUNE_MF_PASS");
+  if (!e || !*e) return kMfDefaultBulk;
+  if (!strcmp(e, "bulk")) return 1;
+  if (!strcmp(e, "bulkred")) return 2;
+  if (!strcmp(e, "pair") || !strcmp(e, "register")) return 0;
+  return kMfDefaultBulk;
+}
+
+// which pass runs and with how many rows in flight; `reserved`: bit 0 forces the 8-byte pass, bits 8..10 override U,
+// bit 12 = bulk-copy staging, bit 13 = bulk-copy staging with the running sums by bulk reduction, bit 11 = register
+// passes whatever the default, bits 14..18 = consumer warps of the bulk pass (0 = chosen by shape), bits 19..22 = cap on
+// its stages (0 = as many as fit)
 static void mf_choose_pass(MfPlan& P, int reserved, const void* x, const void* y, const void* d) {
   const MfGeo& G = P.G;
   switch (G.K) {
     case 1: P.grid_eval = mf_grid(k_mf_eval<1>); break;
     case 2: P.grid_eval = mf_grid(k_mf_eval<2>); break;
     default: P.grid_eval = mf_grid(k_mf_eval<4>); break;
+  }
+  P.bulk = 0;
+  {
+    int want = (reserved & (1 << 13)) ? 2 : ((reserved & (1 << 12)) ? 1 : 0);
+    const bool forced = want != 0;
+    if (!forced && !(reserved & ((1 << 11) | 1))) want = (G.N > 32) ? mf_default_bulk() : 0;    // default: the pair pass's shapes
+    const uintptr_t al = (uintptr_t)x | (uintptr_t)y | (uintptr_t)d | (uintptr_t)P.st.xsum | (uintptr_t)P.st.ysum;
+    if (want && !(G.N & 1) && G.N <= 64 && G.rt == 1 && G.ct == 1 && (al & 15) == 0) {
+      P.bcfg = bulk_config(G.N, want == 2, (reserved >> 14) & 31, (reserved >> 19) & 15);
+      if (P.bcfg.ok) {
+        cudaError_t e = want == 2
+            ? cudaFuncSetAttribute(k_mf_iter_bulk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.bcfg.smem)
+            : cudaFuncSetAttribute(k_mf_iter_bulk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.bcfg.smem);
+        if (e == cudaSuccess) { P.bulk = want; P.grid_iter = kNumSMs; P.pair = 0; P.rows_in_flight = 0; return; }
+        (void)cudaGetLastError();
+      }
+    }
   }
   P.rows_in_flight = (reserved >> 8) & 7;
   P.pair = !(reserved & 1) && !(G.N & 1) && G.K == 2 && G.N <= 64 && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)d) & 15) == 0;
@@ -969,13 +1017,23 @@ using namespace neptune;
 
 // host-only: the tile geometry the solver would use (tests, tools).  out[0..7] = {K columns per lane, JT columns per
 // tile, ct column tiles, RT rows per tile, rt row tiles, tiles per instance, F*N <= 4096 (single-block small
-// kernel), 0}; out[8..15] = 0 (reserved)
+// kernel), 0}; out[8..15] = geometry of the bulk-copy pass (below)
 extern "C" int neptune_pdhg_mf_geometry(int B, int N, int F, int32_t* out) {
   if (B <= 0 || N <= 0 || F <= 0 || !out) return NEPTUNE_E_ARG;
   const MfGeo G = make_geo(N, F, B);
   out[0] = G.K; out[1] = G.JT; out[2] = G.ct; out[3] = G.RT; out[4] = G.rt; out[5] = G.tiles_inst;
   out[6] = G.C <= 4096; out[7] = 0;
-  for (int k = 8; k < 16; ++k) out[k] = 0;          // (bulk-copy pass geometry of round 1: removed)
+  for (int k = 8; k < 16; ++k) out[k] = 0;
+  // the bulk-copy pass (pdhg_mf_bulk.cuh): out[8..10] = {applicable, stages, consumer warps} with four streams per stage,
+  // out[11..13] = the same with the running sums by bulk reduction, out[14] = the pass a default solve takes for this
+  // shape (0 register passes, 1 / 2 bulk), out[15] = dynamic shared memory of the reduction version in bytes
+  if (G.rt == 1 && G.ct == 1) {
+    const BulkCfg c4 = bulk_config(N, 0, 0, 0), c2 = bulk_config(N, 1, 0, 0);
+    out[8] = c4.ok; out[9] = c4.stages; out[10] = c4.nw;
+    out[11] = c2.ok; out[12] = c2.stages; out[13] = c2.nw; out[15] = (int32_t)c2.smem;
+    const int dflt = N > 32 ? mf_default_bulk() : 0;
+    out[14] = (dflt == 1 && c4.ok) ? 1 : ((dflt == 2 && c2.ok) ? 2 : 0);
+  }
   return 0;
 }
 

@@ -61,7 +61,7 @@ def test_matrix_free_tile_geometry_covers_every_shape():
     lib = _lib.load()
     out = (ctypes.c_int32 * 16)()
     need = ctypes.c_int64()
-    for (B, N, F) in [(1, 3, 2), (256, 50, 10), (4096, 20, 5), (1, 33, 3), (2, 64, 3), (1, 65, 1), (1, 500, 50), (1, 2000, 25),
+    for (B, N, F) in [(1, 3, 2), (256, 50, 10), (4096, 20, 5), (1, 33, 3), (2, 64, 3), (2, 34, 3), (1, 56, 2), (1, 8, 4), (1, 65, 1), (1, 500, 50), (1, 2000, 25),
                       (1, 2000, 200), (3, 1026, 2), (1, 130, 2), (1, 131, 2)]:
         assert lib.neptune_pdhg_mf_geometry(B, N, F, out) == 0
         K, JT, ct, RT, rt, tiles, single = list(out)[:7]
@@ -69,7 +69,17 @@ def test_matrix_free_tile_geometry_covers_every_shape():
         assert K == (1 if N <= 32 else 2 if (N % 2 == 0 or N <= 64) else 4)
         assert (ct - 1) * JT < N <= ct * JT and (rt - 1) * RT < N <= rt * RT and 1 <= RT <= 64
         assert tiles == F * rt * ct and single == (F * N <= 4096)
-        assert list(out)[8:] == [0] * 8
+        # bulk-copy pass: even N <= 64 only; a stage is 4 (2 with bulk reduction) slabs of N*N doubles, at least two stages
+        ok4, st4, nw4, ok2, st2, nw2, dflt, smem2 = list(out)[8:]
+        if N % 2 or N > 64:
+            assert (ok4, ok2, dflt) == (0, 0, 0)
+        else:
+            slab = (8 * N * N + 127) // 128 * 128
+            assert ok2 == 1 and 2 <= st2 <= 8 and 4 <= nw2 <= 15 and smem2 <= 227 * 1024 and smem2 >= st2 * 2 * slab
+            assert (nw2 * ((N + nw2 - 1) // nw2) >= N) and ok4 == (1 if 2 * 4 * slab + 3 * nw4 * N * 8 + 384 <= 227 * 1024 else 0)
+            if ok4:
+                assert st4 >= 2 and st4 * 4 * slab <= 227 * 1024
+        assert dflt in (0, 1, 2) and (N > 32 or dflt == 0)
         assert lib.neptune_pdhg_mf_workspace_bytes(B, N, F, ctypes.byref(need)) == 0
         X, C = F * N * N, F * N
         assert need.value >= 8 * B * (2 * (X + C) + 2 * (3 * C + 2 * N + X))        # xsum, xres, ysum, yres at least

@@ -70,6 +70,68 @@ def test_pair_pass_equals_the_8_byte_pass(shape):
         assert np.allclose(ra["primal_obj"], rb["primal_obj"], rtol=1e-11)
 
 
+def _bulk_geometry(N, F, B=2):
+    from neptune_mip_b200 import _lib
+    out = (ctypes.c_int32 * 16)()
+    assert _lib.load().neptune_pdhg_mf_geometry(B, N, F, out) == 0
+    return list(out)[8:]
+
+
+@pytest.mark.parametrize("shape", [(50, 4), (34, 3), (64, 3), (20, 5), (8, 4), (2, 2)])
+@pytest.mark.parametrize("mode", [1, 2], ids=["staged-sums", "bulk-reduction"])
+def test_bulk_copy_pass_equals_the_register_passes(shape, mode):
+    """even N <= 64: the pass with its streams staged through shared memory by cp.async.bulk (mode 1: x, yS and both
+    running sums; mode 2: the running sums added by cp.reduce.async.bulk) does the arithmetic of the pair pass; the
+    column sums are taken over another grouping of the rows, so the comparison is 1e-11, not bitwise.  Shapes whose
+    stage does not fit twice (N = 64 with four streams) fall back to the register pass -- the geometry says which."""
+    from neptune_mip_b200 import device
+    ok4, st4, nw4, ok2, st2, nw2, dflt, smem2 = _bulk_geometry(*shape)
+    assert ok2 == 1 and ok4 == (0 if shape[0] > 56 else 1)
+    inst = cuda_batch([synth.random_payload(shape[0], shape[1], s, node_cores=60) for s in range(3)])
+    kw = dict(max_iters=70, check_every=70, eps_rel=1e-13, eps_abs=1e-15)
+    xa, ya, ra = device.pdhg_mf_solve(inst, scalar_kernel=True, **kw)
+    xb, yb, rb = device.pdhg_mf_solve(inst, bulk=mode, **kw)
+    assert _close(xb.cpu().numpy(), xa.cpu().numpy(), 1e-11) and _close(yb.cpu().numpy(), ya.cpu().numpy(), 1e-11)
+    assert np.allclose(ra["primal_obj"], rb["primal_obj"], rtol=1e-11) and np.allclose(ra["dual_obj"], rb["dual_obj"], rtol=1e-9)
+    # bit-reproducible: fixed summation orders, one addition per element in the reduction
+    xc, yc, rc = device.pdhg_mf_solve(inst, bulk=mode, **kw)
+    assert np.array_equal(xb.cpu().numpy(), xc.cpu().numpy()) and np.array_equal(yb.cpu().numpy(), yc.cpu().numpy())
+
+
+@pytest.mark.parametrize("mode,warps,stages", [(1, 0, 0), (2, 0, 0), (2, 8, 2), (2, 15, 3), (2, 5, 4), (1, 10, 2)])
+def test_bulk_copy_pass_many_tiles_per_block(mode, warps, stages):
+    """more tiles per block than stages (every stage and both barrier phases are reused many times), every geometry the
+    tools can ask for; against the numpy statement of the iteration on two instances and the pair pass on all"""
+    from neptune_mip_b200 import device
+    B = 96                                                   # 960 slabs over 148 blocks: 6-7 tiles per block
+    payloads = [synth.random_payload(50, 10, s, node_cores=200) for s in range(B)]
+    inst = cuda_batch(payloads)
+    kw = dict(max_iters=40, check_every=40, eps_rel=1e-13, eps_abs=1e-15)
+    xa, ya, ra = device.pdhg_mf_solve(inst, register_pass=True, **kw)
+    xb, yb, rb = device.pdhg_mf_solve(inst, bulk=mode, bulk_warps=warps, bulk_stages=stages, **kw)
+    assert _close(xb.cpu().numpy(), xa.cpu().numpy(), 1e-11) and _close(yb.cpu().numpy(), ya.cpu().numpy(), 1e-11)
+    for b in (0, B - 1):
+        xr, yr, info = run_fixed(arrays_of(payloads[b]), 40)
+        assert _close(xb[b].cpu().numpy(), xr, 1e-9) and _close(yb[b].cpu().numpy(), yr, 1e-9)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_bulk_copy_pass_frozen_instances_and_solo_runs(mode):
+    """converged instances go through the barrier protocol without copies: their state stays frozen, the others take
+    exactly the trajectory of their solo runs (restarts included)"""
+    from neptune_mip_b200 import device
+    ps = [synth.random_payload(8, 4, 1, node_cores=200), synth.random_payload(8, 4, 1, node_cores=12),
+          synth.random_payload(8, 4, 2, node_cores=30)]
+    kw = dict(max_iters=20000, check_every=128, eps_rel=1e-6, eps_abs=1e-9, bulk=mode)
+    x, y, res = device.pdhg_mf_solve(cuda_batch(ps), **kw)
+    assert len(set(res["iters"].tolist())) > 1
+    for b, p in enumerate(ps):
+        xs, ys, rs = device.pdhg_mf_solve(cuda_batch([p]), **kw)
+        assert res[b]["converged"] == 1 and res[b]["iters"] == rs[0]["iters"] and res[b]["restarts"] == rs[0]["restarts"]
+        assert np.array_equal(x[b].cpu().numpy(), xs[0].cpu().numpy())
+        assert np.array_equal(y[b].cpu().numpy(), ys[0].cpu().numpy())
+
+
 def test_agrees_with_the_csr_solver_on_the_assembled_matrix():
     """same algorithm on the assembled (reference-identical + strengthening rows) CSR matrix with the same step
     sizes (ruiz_iters = 0).  Bound 5e-5 relative (BASELINE.json's 1e-4 with margin): the CSR kernels square a

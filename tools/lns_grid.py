@@ -1,0 +1,79 @@
+"""GPU experiment: search settings against the proven C2 optima (tests/golden/mip_optima.json).  One batch per setting =
+the 15 C2 seeds with a proven optimum + extra copies of the seeds that miss most often (seed 6: its chains are keyed by
+the batch position, so copies are independent trials).  Prints, per setting: how many of the 15 seeds end within 1e-4, the
+success rate over the copies, the search time.   python tools/lns_grid.py [--copies 9] [--only name,name]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from neptune_mip_b200 import device, synth  # noqa: E402
+from neptune_mip_b200.batch import BatchParams, solve_batch  # noqa: E402
+from neptune_mip_b200.core.utils import data_to_solver_input  # noqa: E402
+
+BASE = dict(lp_iters=50000, lp_check_every=256, lns_chains=96, lns_rounds=20000, lns_k=3, lns_noise=0.1, lns_final_k4=3000,
+            lns_final_noise=0.3, elites=32)
+GRID = [
+    ("bench-default", {}),
+    ("noise-0.2", dict(lns_noise=0.2)),
+    ("noise-0.05", dict(lns_noise=0.05)),
+    ("k4-main", dict(lns_k=4, lns_rounds=10000)),
+    ("chains-192x10000", dict(lns_chains=192, lns_rounds=10000)),
+    ("chains-48x40000", dict(lns_chains=48, lns_rounds=40000)),
+    ("phases-2", dict(lns_phases=2)),
+    ("phases-4-cool-0.8", dict(lns_phases=4, lns_cooling=0.8)),
+    ("final-k4-6000-hot", dict(lns_final_k4=6000, lns_final_noise=0.6)),
+    ("no-cut-guide", dict(lp_cut=False)),
+    ("rng-2", dict(rng_seed=2)),
+    ("rng-3", dict(rng_seed=3)),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--copies", type=int, default=9)
+    ap.add_argument("--hard", default="6")
+    ap.add_argument("--only", default="")
+    ap.add_argument("--out", default="lns_grid.json")
+    a = ap.parse_args()
+    gold = {r["seed"]: r for r in json.load(open(os.path.join(ROOT, "tests", "golden", "mip_optima.json")))
+            if r["config"] == "C2" and r["optimal"]}
+    base_seeds = [s for s in range(16) if s in gold]
+    hard = [int(v) for v in a.hard.split(",") if v]
+    seeds = base_seeds + [h for h in hard for _ in range(a.copies)]
+    datas = [data_to_solver_input(synth.config_payload("C2", s), 1, with_db=False) for s in seeds]
+    inst = device.InstanceBatch.from_datas(datas)
+    opt = np.array([gold[s]["objective"] for s in seeds])
+    only = set(v for v in a.only.split(",") if v)
+    rows = []
+    for name, over in GRID:
+        if only and name not in only:
+            continue
+        prm = BatchParams(**{**BASE, **over})
+        torch.cuda.synchronize(); t0 = time.time()
+        res = solve_batch(inst, prm, time_pdhg=True)
+        torch.cuda.synchronize(); dt = time.time() - t0
+        sc = res.scores[:, 0].cpu().numpy(); fl = res.flags.cpu().numpy()
+        gaps = (sc - opt) / opt
+        nb = len(base_seeds)
+        row = {"setting": name, "override": over, "wall_s": round(dt, 2), "pdhg_ms": round(res.pdhg_ms, 1), "lns_ms": round(res.lns_ms, 1),
+               "feasible": int((fl == 63).sum()), "instances": len(seeds),
+               "within_1e4_of_15": int((gaps[:nb] <= 1e-4).sum()),
+               "missed_seeds": {str(base_seeds[k]): float(f"{gaps[k]:.2e}") for k in range(nb) if gaps[k] > 1e-4},
+               "hard_copies": {str(h): {"within_1e4": int(sum(gaps[k] <= 1e-4 for k in range(len(seeds)) if seeds[k] == h)),
+                                        "of": int(sum(1 for s in seeds if s == h)),
+                                        "gaps": [float(f"{gaps[k]:.2e}") for k in range(len(seeds)) if seeds[k] == h]} for h in hard}}
+        rows.append(row)
+        print("GRID", json.dumps(row), flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", a.out), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

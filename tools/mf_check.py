@@ -79,6 +79,41 @@ def variants():
         print("VAR", name, "small-vector kernel alone us/iter %.1f" % (1e3 * ms / iters), flush=True)
 
 
+def bulk():
+    """the bulk-copy staged pass (csrc/pdhg_mf_bulk.cuh) against the pair pass: time per iteration and iterate difference,
+    over consumer-warp counts and stage caps"""
+    rows = []
+    for name, inst, iters in (("C2 batch 256", synth_batch(50, 10, 256), 512), ("64x10 batch 128", synth_batch(64, 10, 128), 256),
+                              ("34x10 batch 512", synth_batch(34, 10, 512), 256), ("C2 batch 48 (L2-resident)", synth_batch(50, 10, 48), 512)):
+        kwt = dict(max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14)
+        device.pdhg_mf_solve(inst, max_iters=32, check_every=32, register_pass=True)
+        (xr, yr, _), ms = timed(lambda: device.pdhg_mf_solve(inst, register_pass=True, **kwt))
+        (_, _, _), ms2 = timed(lambda: device.pdhg_mf_solve(inst, register_pass=True, **kwt))
+        ms = min(ms, ms2)
+        print("BULK", name, "pair pass (registers) us/iter %.1f GB/s %.0f" % (1e3 * ms / iters, bytes_iter(inst) * iters / ms / 1e6), flush=True)
+        rows.append({"shape": name, "pass": "pair", "us_per_iter": 1e3 * ms / iters, "gbs": bytes_iter(inst) * iters / ms / 1e6})
+        full = name.startswith("C2 batch 256")
+        for mode in (2, 1):
+            for warps in ((0, 8, 10, 15) if full else (0,)):
+                for cap in ((0, 3, 2) if (full and warps == 0) else (0,)):
+                    kw = dict(bulk=mode, bulk_warps=warps, bulk_stages=cap)
+                    try:
+                        device.pdhg_mf_solve(inst, max_iters=32, check_every=32, **kw)
+                        (xb, yb, _), ms = timed(lambda: device.pdhg_mf_solve(inst, **kw, **kwt))
+                        (_, _, _), ms2 = timed(lambda: device.pdhg_mf_solve(inst, **kw, **kwt))
+                    except Exception as e:          # a trap inside the kernel poisons the context: stop here
+                        print("BULK", name, kw, "FAILED", repr(e), flush=True)
+                        raise
+                    ms = min(ms, ms2)
+                    dx, dy = float((xb - xr).abs().max()), float((yb - yr).abs().max())
+                    print("BULK", name, "bulk mode %d (%s) warps %d stage cap %d" % (mode, "sums by bulk reduction" if mode == 2 else "four streams staged", warps, cap),
+                          "us/iter %.1f GB/s %.0f" % (1e3 * ms / iters, bytes_iter(inst) * iters / ms / 1e6), "max |dx| %.1e |dy| %.1e vs pair" % (dx, dy), flush=True)
+                    rows.append({"shape": name, "pass": "bulk%d" % mode, "warps": warps, "stage_cap": cap, "us_per_iter": 1e3 * ms / iters,
+                                 "gbs": bytes_iter(inst) * iters / ms / 1e6, "max_dx": dx, "max_dy": dy})
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "mf_bulk.json"), "w"), indent=1)
+
+
 def ceiling():
     """what plain torch kernels reach on this box for copy / read-modify-write streams"""
     n = 1 << 27
@@ -111,6 +146,8 @@ if __name__ == "__main__":
     t0 = time.time()
     if "--variants" in sys.argv:
         variants()
+    if "--bulk" in sys.argv:
+        bulk()
     if "--ceiling" in sys.argv:
         ceiling()
     if "--converge" in sys.argv:
