@@ -38,8 +38,12 @@ struct BulkCfg {
   int stages;
   unsigned slab_bytes;    // N * N * 8
   unsigned slab_stride;   // slab_bytes rounded up to 128
-  unsigned streams;       // 2 (red) or 4
+  unsigned streams;       // read-write slabs of a stage: 2 (red) or 4; the d slab follows them
+  unsigned vec_off;       // offset of the small vectors inside a stage: w[N] r[N] y3[N] y4[N] cbar[N] y1[2N] hdr[4]
+  unsigned stage_bytes;
   size_t smem;            // dynamic shared memory of the launch
+  int diag;               // measurements only (tools/mf_check.py): 1 = no copies (arithmetic on whatever the stage holds),
+                          // 2 = no arithmetic (copy through), 3 = loads only; results are meaningless then
 };
 
 // consumer warps: rows go round robin over the warps, so take the fewest rounds a block of at most 512 threads (128
@@ -58,14 +62,15 @@ static BulkCfg bulk_config(int N, int red, int nw_override, int stage_cap) {
   c.slab_bytes = (unsigned)N * (unsigned)N * 8u;
   c.slab_stride = (c.slab_bytes + 127u) & ~127u;
   c.streams = red ? 2u : 4u;
+  c.vec_off = (c.streams + 1u) * c.slab_stride;
+  c.stage_bytes = c.vec_off + (((unsigned)(7 * N + 4) * 8u + 127u) & ~127u);
   const size_t fixed = 256 /* barriers */ + (size_t)3 * c.nw * N * 8 /* column partials */ + 128 /* alignment slack */;
-  const size_t stage = (size_t)c.streams * c.slab_stride;
-  int s = (int)((kBulkSmemMax - fixed) / stage);
+  int s = (int)((kBulkSmemMax - fixed) / c.stage_bytes);
   if (s > kBulkMaxStages) s = kBulkMaxStages;
   if (stage_cap >= 2 && s > stage_cap) s = stage_cap;
   if (s < 2) return c;
   c.stages = s;
-  c.smem = fixed + (size_t)s * stage;
+  c.smem = fixed + (size_t)s * c.stage_bytes;
   c.ok = 1;
   return c;
 }
@@ -124,6 +129,10 @@ __device__ __forceinline__ void consumer_sync(int threads) { asm volatile("bar.s
 // grid: one block per SM (at most one block per tile); block: (cfg.nw + 1) warps, the LAST warp is the producer.
 // tile n of block k is slab  k + n * gridDim.x  (slab = b * F + f); slabs of converged instances go through the barrier
 // protocol without copies or arithmetic, so stage and phase are closed formulas of n for both roles.
+// EVERYTHING a consumer reads arrives through the stage: the slabs of x, yS (xsum, ysum), the delay matrix, the vectors
+// w[f,:], r[f,:], y3[f,:], y4, cbar[f,:], the (C1a, C1b) multiplier pairs of the function, and a header {tau, sigma / 2,
+// live} written by the producer -- a consumer's only global accesses are the stores of the partial sums (measured: with
+// the vectors read from global memory a tile cost 4.5 us of dependent L2 round trips, all warps in lockstep).
 template <bool RED>
 __global__ void __launch_bounds__((kBulkMaxWarps + 1) * 32, 1)
 k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, BulkCfg cfg) {
@@ -134,11 +143,10 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
   const int64_t total = (int64_t)B * F;
   // shared-memory carve: [barriers 256 B][column partials 3 * NW * N doubles][stages], stages 128-byte aligned
   unsigned char* base = bulk_smem_raw;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base);                      // full[0..S), done[S..2S)
   double* colbuf = reinterpret_cast<double*>(base + 256);
   const uint32_t base_addr = smem_addr(base);
   const uint32_t stage0 = (base_addr + 256u + (uint32_t)(3 * NW * N * 8) + 127u) & ~127u;
-  const uint32_t stage_bytes = cfg.streams * cfg.slab_stride;
+  const uint32_t stage_bytes = cfg.stage_bytes;
   const uint32_t bar_full = base_addr, bar_done = base_addr + 8u * (uint32_t)S;
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8u * s, 1u); mbar_init(bar_done + 8u * s, (uint32_t)NW); }
@@ -149,37 +157,53 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
   // number of tiles of this block
   const int64_t first = blockIdx.x;
   const int T = first < total ? (int)((total - first + gridDim.x - 1) / gridDim.x) : 0;
+  const uint32_t vecb = (uint32_t)N * 8u;          // bytes of one N-vector (a multiple of 16: N is even)
 
   if (warp == NW) {
     // ------------------------------------------------------------ producer: one lane moves every byte
     if (lane == 0) {
-      auto slab_ptrs = [&](int n, double*& xg, double*& sg, double*& xsg, double*& ssg, bool& live) {
+      struct Prep { double tau, shalf; int conv; };
+      auto prep_tile = [&](int n) {          // the control block of the tile's instance (requested ahead of the waits)
+        const int64_t slab = first + (int64_t)n * gridDim.x;
+        const int b = (int)(slab / F);
+        Prep p; p.tau = ctl[b].tau; p.shalf = 0.5 * ctl[b].sigma; p.conv = ctl[b].converged;
+        return p;
+      };
+      auto load_tile = [&](int n, const Prep& pr) {
         const int64_t slab = first + (int64_t)n * gridDim.x;
         const int b = (int)(slab / F), f = (int)(slab - (int64_t)b * F);
-        live = !ctl[b].converged;
-        xg = st.x + (int64_t)b * G.cols + (int64_t)f * NN;
-        sg = st.y + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
-        xsg = st.xsum + (int64_t)b * G.cols + (int64_t)f * NN;
-        ssg = st.ysum + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
-      };
-      auto load_tile = [&](int n) {
-        double *xg, *sg, *xsg, *ssg; bool live;
-        slab_ptrs(n, xg, sg, xsg, ssg, live);
         const int s = n % S;
         const uint32_t bar = bar_full + 8u * s, dst = stage0 + (uint32_t)s * stage_bytes;
-        if (!live) { mbar_arrive(bar); return; }
-        mbar_arrive_expect_tx(bar, cfg.streams * cfg.slab_bytes);
+        double* hdr = reinterpret_cast<double*>(base + (dst - base_addr) + cfg.vec_off) + 7 * N;
+        hdr[0] = pr.tau; hdr[1] = pr.shalf; hdr[2] = (!pr.conv && cfg.diag < 2) ? 1.0 : 0.0;
+        if (pr.conv || cfg.diag == 1) { mbar_arrive(bar); return; }
+        const double* xg = st.x + (int64_t)b * G.cols + (int64_t)f * NN;
+        const double* yb = st.y + (int64_t)b * G.rows;
+        const double* sg = yb + G.rs + (int64_t)f * NN;
+        mbar_arrive_expect_tx(bar, (cfg.streams + 1u) * cfg.slab_bytes + 7u * vecb);
         bulk_load(dst, xg, cfg.slab_bytes, bar);
         bulk_load(dst + cfg.slab_stride, sg, cfg.slab_bytes, bar);
         if (!RED) {
-          bulk_load(dst + 2u * cfg.slab_stride, xsg, cfg.slab_bytes, bar);
-          bulk_load(dst + 3u * cfg.slab_stride, ssg, cfg.slab_bytes, bar);
+          bulk_load(dst + 2u * cfg.slab_stride, st.xsum + (int64_t)b * G.cols + (int64_t)f * NN, cfg.slab_bytes, bar);
+          bulk_load(dst + 3u * cfg.slab_stride, st.ysum + (int64_t)b * G.rows + G.rs + (int64_t)f * NN, cfg.slab_bytes, bar);
         }
+        bulk_load(dst + cfg.streams * cfg.slab_stride, in.d + (int64_t)b * NN, cfg.slab_bytes, bar);
+        const uint32_t v = dst + cfg.vec_off;
+        bulk_load(v, in.w + ((int64_t)b * F + f) * N, vecb, bar);
+        bulk_load(v + vecb, in.r + ((int64_t)b * F + f) * N, vecb, bar);
+        bulk_load(v + 2u * vecb, yb + G.r3 + (int64_t)f * N, vecb, bar);
+        bulk_load(v + 3u * vecb, yb + G.r4, vecb, bar);
+        bulk_load(v + 4u * vecb, st.cbar + (int64_t)b * G.C + (int64_t)f * N, vecb, bar);
+        bulk_load(v + 5u * vecb, yb + 2 * (int64_t)f * N, 2u * vecb, bar);
       };
       auto store_tile = [&](int n) {
-        double *xg, *sg, *xsg, *ssg; bool live;
-        slab_ptrs(n, xg, sg, xsg, ssg, live);
-        if (live) {
+        const int64_t slab = first + (int64_t)n * gridDim.x;
+        const int b = (int)(slab / F), f = (int)(slab - (int64_t)b * F);
+        if (!ctl[b].converged && cfg.diag != 1 && cfg.diag != 3) {
+          double* xg = st.x + (int64_t)b * G.cols + (int64_t)f * NN;
+          double* sg = st.y + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
+          double* xsg = st.xsum + (int64_t)b * G.cols + (int64_t)f * NN;
+          double* ssg = st.ysum + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
           const uint32_t src = stage0 + (uint32_t)(n % S) * stage_bytes;
           bulk_store(xg, src, cfg.slab_bytes);
           bulk_store(sg, src + cfg.slab_stride, cfg.slab_bytes);
@@ -193,20 +217,19 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
         }
         bulk_commit();          // an empty group for a converged slab keeps the group count equal to the tile count
       };
-      int next_load = 0;
-      for (; next_load < S && next_load < T; ++next_load) load_tile(next_load);
+      for (int n = 0; n < S && n < T; ++n) load_tile(n, prep_tile(n));
       // with three or more stages the refill of a stage waits for the stores of the PREVIOUS tile only, so the stores of
       // the tile just finished drain while the next loads are issued
       const bool lag = S >= 3;
       for (int k = 0; k < T; ++k) {
+        const int freed = lag ? k - 1 : k, nl = freed + S;
+        const bool refill = freed >= 0 && nl < T;                     // loads go in tile order
+        Prep pr{0.0, 0.0, 1};
+        if (refill) pr = prep_tile(nl);
         mbar_wait(bar_done + 8u * (k % S), (uint32_t)((k / S) & 1));
         store_tile(k);
-        int freed;
-        if (lag) { bulk_wait_read<1>(); freed = k - 1; } else { bulk_wait_read<0>(); freed = k; }
-        if (freed >= 0 && freed + S < T) {          // tile freed + S is the next one to load (loads go in order)
-          load_tile(freed + S);
-          next_load = freed + S + 1;
-        }
+        if (lag) bulk_wait_read<1>(); else bulk_wait_read<0>();
+        if (refill) load_tile(nl, pr);
       }
       bulk_wait_all();
     }
@@ -224,56 +247,41 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
     const int b = (int)(slab / F), f = (int)(slab - (int64_t)b * F);
     const int s = n % S;
     const uint32_t ph = (uint32_t)((n / S) & 1);
-    const bool live = !ctl[b].converged;
-    if (!live) {
-      mbar_wait(bar_full + 8u * s, ph);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_done + 8u * s);
-      continue;
-    }
-    const double tau = ctl[b].tau, shalf = 0.5 * ctl[b].sigma;
-    const double* __restrict__ d = in.d + (int64_t)b * NN;
-    const double* __restrict__ w = in.w + ((int64_t)b * F + f) * N;
-    const double* __restrict__ r = in.r + ((int64_t)b * F + f) * N;
-    const double* __restrict__ y = st.y + (int64_t)b * G.rows;
-    const double* __restrict__ y3 = y + G.r3 + (int64_t)f * N;
-    const double* __restrict__ cbar = st.cbar + (int64_t)b * G.C + (int64_t)f * N;
-    double* __restrict__ P3 = st.P3i + ((int64_t)b * G.C + (int64_t)f * N) * G.cti;
-    // column constants of this lane's pair and the first row's constants: requested before the wait on the stage
-    double y1j[2], rj[2], rr4[2], cb[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const unsigned je = jl + e;
-      y1j[e] = y[2 * ((int64_t)f * N + je) + 1];
-      rj[e] = __ldg(r + je);
-      rr4[e] = rj[e] * y[G.r4 + je];
-      cb[e] = cbar[je];
-    }
-    int i = warp;
-    double wn = 0.0, y3n = 0.0; double2 dn = make_double2(0.0, 0.0);
-    if (i < N) { wn = __ldg(w + i); y3n = y3[i]; dn = __ldg(reinterpret_cast<const double2*>(d + (unsigned)i * (unsigned)N + jl)); }
-    double a1[2] = {0.0, 0.0}, a4[2] = {0.0, 0.0}, aS[2] = {0.0, 0.0};
-
     mbar_wait(bar_full + 8u * s, ph);
-    const uint32_t sx = stage0 + (uint32_t)s * stage_bytes;
-    unsigned char* stage_ptr = base + (sx - base_addr);
+    unsigned char* stage_ptr = base + (stage0 - base_addr) + (size_t)s * stage_bytes;
     double* xs_ = reinterpret_cast<double*>(stage_ptr);
     double* ss_ = reinterpret_cast<double*>(stage_ptr + cfg.slab_stride);
     double* xsum_ = reinterpret_cast<double*>(stage_ptr + 2u * cfg.slab_stride);     // only when !RED
     double* ysum_ = reinterpret_cast<double*>(stage_ptr + 3u * cfg.slab_stride);
-
-    for (; i < N; i += NW) {
-      const double wfi = wn, ty = y3n; const double2 dv = dn;
-      const int inext = i + NW;
-      if (inext < N) {          // the next row's constants travel while this row is computed
-        wn = __ldg(w + inext); y3n = y3[inext];
-        dn = __ldg(reinterpret_cast<const double2*>(d + (unsigned)inext * (unsigned)N + jl));
-      }
+    const double* d_ = reinterpret_cast<const double*>(stage_ptr + cfg.streams * cfg.slab_stride);
+    const double* vw = reinterpret_cast<const double*>(stage_ptr + cfg.vec_off);
+    const double *vr = vw + N, *vy3 = vw + 2 * N, *vy4 = vw + 3 * N, *vcb = vw + 4 * N, *vy1 = vw + 5 * N, *hdr = vw + 7 * N;
+    if (hdr[2] == 0.0) {          // converged instance (or a copy-only measurement): release the stage untouched
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_done + 8u * s);
+      continue;
+    }
+    const double tau = hdr[0], shalf = hdr[1];
+    double* __restrict__ P3 = st.P3i + ((int64_t)b * G.C + (int64_t)f * N) * G.cti;
+    double y1j[2], rj[2], rr4[2], cb[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const unsigned je = jl + e;
+      y1j[e] = vy1[2 * je + 1];
+      rj[e] = vr[je];
+      rr4[e] = rj[e] * vy4[je];
+      cb[e] = vcb[je];
+    }
+    const double r_tot = (int)threadIdx.x < N ? vr[threadIdx.x] : 0.0;      // for the totals below: read before the stage is released
+    double a1[2] = {0.0, 0.0}, a4[2] = {0.0, 0.0}, aS[2] = {0.0, 0.0};
+    for (int i = warp; i < N; i += NW) {
+      const double wfi = vw[i], ty = vy3[i];
       double rsum = 0.0;
       if (vj) {
         const unsigned o = (unsigned)i * (unsigned)N + jc;
         const double2 xv = *reinterpret_cast<const double2*>(xs_ + o);
         const double2 sv = *reinterpret_cast<const double2*>(ss_ + o);
+        const double2 dv = *reinterpret_cast<const double2*>(d_ + o);
         double xn[2], sn[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -321,7 +329,7 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
       }
       const int64_t o = ((int64_t)b * F + f) * (int64_t)G.rt * N + j;      // rt = 1: one row tile per slab
       st.P1[o] = t1;
-      st.P4[o] = __ldg(r + j) * t4;
+      st.P4[o] = r_tot * t4;
       st.PS[o] = tS;
     }
     consumer_sync(nthr);

@@ -83,10 +83,10 @@ def test_bulk_copy_pass_equals_the_register_passes(shape, mode):
     """even N <= 64: the pass with its streams staged through shared memory by cp.async.bulk (mode 1: x, yS and both
     running sums; mode 2: the running sums added by cp.reduce.async.bulk) does the arithmetic of the pair pass; the
     column sums are taken over another grouping of the rows, so the comparison is 1e-11, not bitwise.  Shapes whose
-    stage does not fit twice (N = 64 with four streams) fall back to the register pass -- the geometry says which."""
+    stage does not fit twice (N > 50 with four streams) fall back to the register pass -- the geometry says which."""
     from neptune_mip_b200 import device
     ok4, st4, nw4, ok2, st2, nw2, dflt, smem2 = _bulk_geometry(*shape)
-    assert ok2 == 1 and ok4 == (0 if shape[0] > 56 else 1)
+    assert ok2 == 1 and ok4 == (0 if shape[0] > 50 else 1)
     inst = cuda_batch([synth.random_payload(shape[0], shape[1], s, node_cores=60) for s in range(3)])
     kw = dict(max_iters=70, check_every=70, eps_rel=1e-13, eps_abs=1e-15)
     xa, ya, ra = device.pdhg_mf_solve(inst, scalar_kernel=True, **kw)

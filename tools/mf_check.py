@@ -114,6 +114,23 @@ def bulk():
     json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "mf_bulk.json"), "w"), indent=1)
 
 
+def bulk_diag():
+    """where the bulk-copy pass spends its time: arithmetic only (no copies), copy-through (no arithmetic), loads only"""
+    inst, iters = synth_batch(50, 10, 256), 512
+    kwt = dict(max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14)
+    for mode in (1, 2):
+        for diag, what in ((0, "full"), (1, "arithmetic only (no copies)"), (2, "copy through (no arithmetic)"), (3, "loads only")):
+            for cap in (0, 2):
+                for warps in ((0, 8) if diag == 1 else (0,)):
+                    kw = dict(bulk=mode, bulk_stages=cap, bulk_warps=warps, _diag=diag)
+                    device.pdhg_mf_solve(inst, max_iters=32, check_every=32, **kw)
+                    _, ms = timed(lambda: device.pdhg_mf_solve(inst, **kw, **kwt))
+                    print("BDIAG C2 batch 256 mode %d stage cap %d warps %d %s us/iter %.1f" % (mode, cap, warps, what, 1e3 * ms / iters), flush=True)
+    device.pdhg_mf_solve(inst, max_iters=32, check_every=32, _diag=4)
+    _, ms = timed(lambda: device.pdhg_mf_solve(inst, _diag=4, **kwt))
+    print("BDIAG small-vector kernel alone us/iter %.1f" % (1e3 * ms / iters), flush=True)
+
+
 def ceiling():
     """what plain torch kernels reach on this box for copy / read-modify-write streams"""
     n = 1 << 27
@@ -146,6 +163,8 @@ if __name__ == "__main__":
     t0 = time.time()
     if "--variants" in sys.argv:
         variants()
+    if "--bulk-diag" in sys.argv:
+        bulk_diag()
     if "--bulk" in sys.argv:
         bulk()
     if "--ceiling" in sys.argv:
