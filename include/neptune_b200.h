@@ -102,7 +102,8 @@ typedef struct neptune_pdhg_params {
                              * bits 8..10 = rows of a warp in flight (0 = default), bit 11 = register passes whatever the
                              * default, bit 12 = bulk-copy (cp.async.bulk) staged pass, bit 13 = the same with the running
                              * sums by bulk reduction (even N <= 64; other shapes ignore both), bits 14..18 = its consumer
-                             * warps, bits 19..22 = cap on its stages */
+                             * warps, bits 19..22 = cap on its stages, bit 23 = keep the small-vector update of the
+                             * bulk pass in its own launches */
   double  eps_rel;          /* termination: relative KKT tolerance */
   double  eps_abs;
 } neptune_pdhg_params;

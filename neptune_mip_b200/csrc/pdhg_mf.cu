@@ -359,10 +359,6 @@ k_mf_iter2(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B) {
   }
 }
 
-}  // namespace neptune
-#include "pdhg_mf_bulk.cuh"      // k_mf_iter_bulk<RED>: the same pass with the streams staged by the bulk-copy engine
-namespace neptune {
-
 // ---------------------------------------------------------------------------------------------------
 // KKT pieces of a candidate (which = 0: current iterate, 1: running average): the same partial sums from a
 // read-only pass, plus per tile {obj.x, sum min(rc_x, 0), sum max(x - c, 0)^2}.  mode 1: only the column
@@ -617,6 +613,10 @@ k_mf_small(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int mask, con
   }
 }
 
+}  // namespace neptune
+#include "pdhg_mf_bulk.cuh"      // k_mf_iter_bulk<RED, FUSE>: the iteration pass with the streams staged by the bulk-copy engine
+namespace neptune {
+
 // rows / c-columns part of the KKT evaluation from the partial sums of k_mf_eval; one block per instance,
 // fixed summation order.  Writes ctl[b].acc[ACC_CUR / ACC_AVG + {PRES2, DRES2, POBJ, DOBJ}].
 __global__ void __launch_bounds__(256)
@@ -854,7 +854,7 @@ static inline size_t mf_align(size_t v) { return (v + 255) & ~(size_t)255; }
 constexpr int kMfRestartBlocks = 64;       // blocks per instance of k_mf_apply_restart / k_mf_setup (upper bound)
 
 struct MfWs {
-  size_t xsum, xres, ysum, yres, cbar, P1, P4, PS, P3, P3i, S4, S2, wsum, scal, part, ctl, flag, cnt, total;
+  size_t xsum, xres, ysum, yres, cbar, P1, P4, PS, P3, P3i, S4, S2, wsum, scal, part, ctl, flag, cnt, q0, q1, aP1, aP4, aPS, aP3i, total;
 };
 
 static MfWs mf_layout(int B, const MfGeo& G) {
@@ -874,6 +874,10 @@ static MfWs mf_layout(int B, const MfGeo& G) {
   W.ctl = take((size_t)B * sizeof(Ctl));
   W.flag = take(256);
   W.cnt = take((size_t)B * 2 * sizeof(int));
+  // the two small-state buffers the fused launches of a chunk alternate between: y rows [0, rs) | c | cbar per instance
+  W.q0 = take((size_t)B * (G.rs + 2 * G.C) * 8); W.q1 = take((size_t)B * (G.rs + 2 * G.C) * 8);
+  // ... and the second set of partial sums (a fused launch reads the set the launch before wrote, writes the other)
+  W.aP1 = take(pb); W.aP4 = take(pb); W.aPS = take(pb); W.aP3i = take((size_t)B * G.C * G.ct * 8);
   W.total = t + 256;
   return W;
 }
@@ -893,6 +897,10 @@ struct MfPlan {
   int bulk;                      // k_mf_iter_bulk (streams staged through shared memory by the bulk-copy engine): 1 = four
                                  // streams per stage, 2 = running sums by bulk reduction (two streams per stage)
   BulkCfg bcfg;
+  int allow_fuse;                // the caller runs whole chunks (mf_solve_impl): the small-vector update may run inside the pass
+  int fuse;                      // ... and does: no k_mf_small launch between the passes of a chunk
+  double* q[2];                  // the two small-state buffers of the fused launches
+  double *aP1, *aP4, *aPS, *aP3i; // the second set of partial sums (launch k writes set k & 1; set 1 = st.P1, st.P4, st.PS, st.P3i)
   int diag;                      // tools only: bit 2 = time the small-vector kernel alone
 };
 
@@ -902,8 +910,8 @@ static void mf_launch_iter(const MfPlan& P) {
   const int g = (int)(total < P.grid_iter ? total : P.grid_iter);
   if (P.bulk) {
     const int threads = (P.bcfg.nw + 1) * 32;
-    if (P.bulk == 2) k_mf_iter_bulk<true><<<g, threads, P.bcfg.smem, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, P.bcfg);
-    else k_mf_iter_bulk<false><<<g, threads, P.bcfg.smem, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, P.bcfg);
+    if (P.bulk == 2) k_mf_iter_bulk<true, false><<<g, threads, P.bcfg.smem, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, P.bcfg, BulkFuse{});
+    else k_mf_iter_bulk<false, false><<<g, threads, P.bcfg.smem, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, P.bcfg, BulkFuse{});
     NEPTUNE_COUNT(1);
     return;
   }
@@ -922,6 +930,26 @@ static void mf_launch_iter(const MfPlan& P) {
     case 41: k_mf_iter<4, 1><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
     default: k_mf_iter<4, 2><<<g, kMfThreads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, P.B); break;
   }
+  NEPTUNE_COUNT(1);
+}
+
+// launch k of a chunk with the small-vector update inside the pass: reads the small state the launch before wrote (the
+// canonical arrays when it is the first of the chunk -- known on the host, or told by the device flag of graph node 0)
+static void mf_launch_fused(const MfPlan& P, int k, const int* first_flag, int force_first) {
+  const int64_t total = (int64_t)P.B * P.G.tiles_inst;
+  const int g = (int)(total < P.grid_iter ? total : P.grid_iter);
+  const int threads = (P.bcfg.nw + 1 + kBulkSmallWarps) * 32;
+  BulkFuse fz{P.q[(k + 1) & 1], P.q[k & 1], first_flag, force_first, (int64_t)(P.G.rs + 2 * P.G.C),
+              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (k & 1) {          // odd launch: reads the second set, writes the canonical one
+    fz.rP1 = P.aP1; fz.rP4 = P.aP4; fz.rPS = P.aPS; fz.rP3 = P.aP3i;
+    fz.wP1 = P.st.P1; fz.wP4 = P.st.P4; fz.wPS = P.st.PS; fz.wP3 = P.st.P3i;
+  } else {
+    fz.rP1 = P.st.P1; fz.rP4 = P.st.P4; fz.rPS = P.st.PS; fz.rP3 = P.st.P3i;
+    fz.wP1 = P.aP1; fz.wP4 = P.aP4; fz.wPS = P.aPS; fz.wP3 = P.aP3i;
+  }
+  if (P.bulk == 2) k_mf_iter_bulk<true, true><<<g, threads, P.bcfg.smem, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, P.bcfg, fz);
+  else k_mf_iter_bulk<false, true><<<g, threads, P.bcfg.smem, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, P.bcfg, fz);
   NEPTUNE_COUNT(1);
 }
 
@@ -948,7 +976,7 @@ static void mf_choose_pass(MfPlan& P, int reserved, const void* x, const void* y
     case 2: P.grid_eval = mf_grid(k_mf_eval<2>); break;
     default: P.grid_eval = mf_grid(k_mf_eval<4>); break;
   }
-  P.bulk = 0;
+  P.bulk = 0; P.fuse = 0;
   {
     int want = (reserved & (1 << 13)) ? 2 : ((reserved & (1 << 12)) ? 1 : 0);
     const bool forced = want != 0;
@@ -956,13 +984,20 @@ static void mf_choose_pass(MfPlan& P, int reserved, const void* x, const void* y
     const uintptr_t al = (uintptr_t)x | (uintptr_t)y | (uintptr_t)d | (uintptr_t)P.st.xsum | (uintptr_t)P.st.ysum |
                          (uintptr_t)P.in.w | (uintptr_t)P.in.r | (uintptr_t)P.st.cbar;
     if (want && !(G.N & 1) && G.N <= 64 && G.rt == 1 && G.ct == 1 && (al & 15) == 0) {
-      P.bcfg = bulk_config(G.N, want == 2, (reserved >> 14) & 31, (reserved >> 19) & 15);
+      // bit 23: keep the small-vector update in its own launches (k_mf_small) even where it could run inside the pass
+      const int try_fuse = P.allow_fuse && !(reserved & (1 << 23)) && !G.with_n;
+      P.bcfg = bulk_config(G.N, want == 2, (reserved >> 14) & 31, (reserved >> 19) & 15, G.F, try_fuse);
+      if (!P.bcfg.ok && try_fuse) P.bcfg = bulk_config(G.N, want == 2, (reserved >> 14) & 31, (reserved >> 19) & 15);
       P.bcfg.diag = (reserved >> 4) & 3;
       if (P.bcfg.ok) {
-        cudaError_t e = want == 2
-            ? cudaFuncSetAttribute(k_mf_iter_bulk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.bcfg.smem)
-            : cudaFuncSetAttribute(k_mf_iter_bulk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.bcfg.smem);
-        if (e == cudaSuccess) { P.bulk = want; P.grid_iter = kNumSMs; P.pair = 0; P.rows_in_flight = 0; return; }
+        cudaError_t e;
+        if (P.bcfg.fuse)
+          e = want == 2 ? cudaFuncSetAttribute(k_mf_iter_bulk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.bcfg.smem)
+                        : cudaFuncSetAttribute(k_mf_iter_bulk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.bcfg.smem);
+        else
+          e = want == 2 ? cudaFuncSetAttribute(k_mf_iter_bulk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.bcfg.smem)
+                        : cudaFuncSetAttribute(k_mf_iter_bulk<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.bcfg.smem);
+        if (e == cudaSuccess) { P.bulk = want; P.fuse = P.bcfg.fuse; P.grid_iter = kNumSMs; P.pair = 0; P.rows_in_flight = 0; return; }
         (void)cudaGetLastError();
       }
     }
@@ -1102,6 +1137,11 @@ static int mf_solve_impl(int B, int N, int F, int kind, const double* d, const d
               (double*)(base + W.P3i),
               (double*)(base + W.S4), (double*)(base + W.S2), (double*)(base + W.wsum), (double*)(base + W.scal)};
   P.diag = (prm->reserved >> 4) & 7;
+  P.q[0] = (double*)(base + W.q0); P.q[1] = (double*)(base + W.q1);
+  P.aP1 = (double*)(base + W.aP1); P.aP4 = (double*)(base + W.aP4); P.aPS = (double*)(base + W.aPS); P.aP3i = (double*)(base + W.aP3i);
+  // the fused launches of a graph replay alternate between the two small-state buffers: a replay must be an even number
+  // of launches
+  P.allow_fuse = ((check_every < 32 ? check_every : 32) & 1) == 0;
   mf_choose_pass(P, prm->reserved, x, y, d);
   // small vectors: one block per instance does POST + PREC + Y2 in one launch while F*N is small; larger
   // instances spread over several blocks and take the C2 dual in a second launch
@@ -1135,6 +1175,7 @@ static int mf_solve_impl(int B, int N, int F, int kind, const double* d, const d
     NEPTUNE_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     guard.capturing = true;
     for (int k = 0; k < inner; ++k) {
+      if (P.fuse) { mf_launch_fused(P, k, k == 0 ? d_flag + 1 : nullptr, 0); continue; }
       mf_launch_small(P, PH_POST | PH_PREC | PH_Y2, k == 0 ? d_flag + 1 : nullptr);
       mf_launch_iter(P);
     }
@@ -1157,11 +1198,18 @@ static int mf_solve_impl(int B, int N, int F, int kind, const double* d, const d
       first = false;
     }
     for (; done < chunk; ++done) {
+      if (P.fuse) { mf_launch_fused(P, done, nullptr, first ? 1 : 0); first = false; continue; }
       mf_launch_small(P, (first ? 0 : PH_POST) | PH_PREC | PH_Y2, nullptr);
       mf_launch_iter(P);
       first = false;
     }
-    mf_launch_small(P, PH_POST, nullptr);
+    if (P.fuse) {
+      const bool odd = (chunk - 1) & 1;       // the last launch of the chunk wrote set (chunk - 1) & 1
+      k_mf_small_from<<<B, 256, 0, s>>>(G, P.in, P.st, ctl, P.q[(chunk - 1) & 1], (int64_t)(G.rs + 2 * G.C),
+                                        odd ? P.st.P1 : P.aP1, odd ? P.st.P4 : P.aP4, odd ? P.st.P3i : P.aP3i); NEPTUNE_COUNT(1);
+    } else {
+      mf_launch_small(P, PH_POST, nullptr);
+    }
     { k_ctl_advance<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, chunk); NEPTUNE_COUNT(1); }
     // KKT of the current iterate and of the running average
     for (int wch = 0; wch < 2; ++wch) {

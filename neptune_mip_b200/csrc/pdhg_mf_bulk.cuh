@@ -28,6 +28,7 @@
 namespace neptune {
 
 constexpr int kBulkMaxStages = 8;
+constexpr int kBulkSmallWarps = 2;                // warps of the in-pass small-vector update (FUSE)
 constexpr int kBulkMaxWarps = 15;                 // consumer warps
 constexpr size_t kBulkSmemMax = 227 * 1024;       // dynamic shared memory a block may opt in to on sm_100a
 
@@ -42,6 +43,8 @@ struct BulkCfg {
   unsigned vec_off;       // offset of the small vectors inside a stage: w[N] r[N] y3[N] y4[N] cbar[N] y1[2N] hdr[4]
   unsigned stage_bytes;
   size_t smem;            // dynamic shared memory of the launch
+  int fuse;               // the small-vector update of an instance runs inside the pass (bulk_small_pre), see k_mf_iter_bulk
+  unsigned inst_bytes;    // shared memory of the per-instance vectors y1[C] y3[C] cbar[C] y4[N] (fuse), rounded to 128
   int diag;               // measurements only (tools/mf_check.py): 1 = no copies (arithmetic on whatever the stage holds),
                           // 2 = no arithmetic (copy through), 3 = loads only; results are meaningless then
 };
@@ -54,17 +57,25 @@ static int bulk_pick_warps(int N) {
   return nw < 4 ? 4 : nw;
 }
 
-static BulkCfg bulk_config(int N, int red, int nw_override, int stage_cap) {
+static BulkCfg bulk_config(int N, int red, int nw_override, int stage_cap, int F = 0, int fuse = 0) {
   BulkCfg c{};
   c.red = red ? 1 : 0;
   if ((N & 1) || N > 64 || N < 2) return c;
+  c.fuse = (fuse && F > 0) ? 1 : 0;
+  c.inst_bytes = c.fuse ? (((unsigned)(3 * F * N + N) * 8u + 127u) & ~127u) : 0u;      // ONE of the two buffers
   c.nw = (nw_override >= 1 && nw_override <= kBulkMaxWarps) ? nw_override : bulk_pick_warps(N);
+  if (c.fuse && c.nw > kBulkMaxWarps - kBulkSmallWarps) {        // the block also holds the small-vector warps
+    const int cap = kBulkMaxWarps - kBulkSmallWarps, rounds = (N + cap - 1) / cap;
+    c.nw = (N + rounds - 1) / rounds;
+    if (c.nw < 4) c.nw = 4;
+  }
   c.slab_bytes = (unsigned)N * (unsigned)N * 8u;
   c.slab_stride = (c.slab_bytes + 127u) & ~127u;
   c.streams = red ? 2u : 4u;
   c.vec_off = (c.streams + 1u) * c.slab_stride;
   c.stage_bytes = c.vec_off + (((unsigned)(7 * N + 4) * 8u + 127u) & ~127u);
-  const size_t fixed = 256 /* barriers */ + (size_t)3 * c.nw * N * 8 /* column partials */ + 128 /* alignment slack */;
+  const size_t fixed = 256 /* barriers */ + (size_t)3 * c.nw * N * 8 /* column partials */ + 256 /* alignment slack */ + 2 * (size_t)c.inst_bytes;
+  if (fixed + 2 * (size_t)c.stage_bytes > kBulkSmemMax) return c;
   int s = (int)((kBulkSmemMax - fixed) / c.stage_bytes);
   if (s > kBulkMaxStages) s = kBulkMaxStages;
   if (stage_cap >= 2 && s > stage_cap) s = stage_cap;
@@ -125,38 +136,176 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void consumer_sync(int threads) { asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); }
 
+// ---- the small-vector update of ONE instance, inside the pass (FUSE) ---------------------------------------------
+// Same arithmetic, term for term, as k_mf_small (POST of the pass that ran before, PREC and Y2 of the iteration that starts)
+// for the min-delay model, run by the consumer threads of a block before its first tile of an instance.  Every block that
+// holds tiles of the instance computes it (it only reads what the PREVIOUS launch left: the partial sums and the small
+// state `src`), keeps y1, y3, y4, cbar in shared memory for its tiles, and the block that owns tile f = 0 (`writer`)
+// also writes the new small state to `dst` and advances the running sums.  `src` and `dst` are different buffers (the
+// launches of a chunk alternate between two), so a block that is still reading never sees a half-written state.
+struct BulkFuse {
+  const double* src_q;    // [B][qstride] small state read by this launch unless it is the first of a chunk
+  double* dst_q;          // [B][qstride] small state written by this launch: y rows [0, rs) | c [C] | cbar [C]
+  const int* first;       // device flag (graph node 0): non-zero -> first launch of a chunk
+  int force_first;        // host-known: first launch of a chunk (read the canonical arrays, no POST)
+  int64_t qstride;        // rs + 2 C
+  // partial sums: a launch reads the set the launch before wrote and writes the other one (a block may still be reading
+  // the sums of an instance while another block, further into the same launch, writes that instance's new ones)
+  const double *rP1, *rP4, *rPS, *rP3;
+  double *wP1, *wP4, *wPS, *wP3;
+};
+
+// The update is a chain of dependent global round trips (microseconds each while the copies saturate the memory system), so
+// every load of a batch of items is issued before the first use (kItems items of a thread in flight), and the running sums
+// advance by fire-and-forget reductions (one addition per element and launch: the value of a load-add-store, bit for bit).
+// Row and column tiles: rt = ct = 1 on this path, so a "sum of partials" is one value (0.0 + v, as strided_sum returns it).
+constexpr int kSmallItems = 4;
+__device__ __forceinline__ void bulk_small_pre(const MfGeo& G, const MfIn& in, const MfSt& st, const BulkFuse& fz, int b, bool post, bool writer,
+                                               double tau, double sigma, const double* __restrict__ sy, const double* __restrict__ sc,
+                                               const double* __restrict__ scbar, double* __restrict__ dy, double* __restrict__ dc,
+                                               double* __restrict__ dcbar, double* iy1, double* iy3, double* icb, double* iy4,
+                                               int tid, int nth) {
+  const int N = G.N, F = G.F;
+  const int C = (int)G.C;
+  double* __restrict__ ys = st.ysum + (int64_t)b * G.rows;
+  double* __restrict__ cs = st.xsum + (int64_t)b * G.cols + G.X;
+  const double* __restrict__ P1 = fz.rP1 + (int64_t)b * C;
+  const double* __restrict__ P4 = fz.rP4 + (int64_t)b * C;
+  const double* __restrict__ PS = fz.rPS + (int64_t)b * C;
+  const double* __restrict__ P3 = fz.rP3 + (int64_t)b * C;
+  const double* __restrict__ m = in.m + (int64_t)b * F;
+  const double s1 = sigma / (double)(N + 1), s3 = sigma / (double)N;
+  for (int q0 = tid; q0 < C; q0 += kSmallItems * nth) {
+    double l_y1[kSmallItems], l_y3[kSmallItems], l_p1[kSmallItems], l_cb[kSmallItems], l_p3[kSmallItems], l_ps[kSmallItems],
+        l_y2[kSmallItems], l_c[kSmallItems], l_m[kSmallItems];
+#pragma unroll
+    for (int u = 0; u < kSmallItems; ++u) {
+      const int q = q0 + u * nth;
+      const int qq = q < C ? q : 0;
+      const int f = qq / N, j = qq - f * N;
+      l_y1[u] = sy[2 * qq + 1]; l_y3[u] = sy[G.r3 + qq]; l_ps[u] = PS[qq]; l_y2[u] = sy[G.r2 + j]; l_c[u] = sc[qq]; l_m[u] = m[f];
+      l_p1[u] = post ? P1[qq] : 0.0; l_cb[u] = post ? scbar[qq] : 0.0; l_p3[u] = post ? P3[qq] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < kSmallItems; ++u) {
+      const int q = q0 + u * nth;
+      if (q < C) {
+        double y1 = l_y1[u], y3n = l_y3[u];
+        if (post) {
+          const double a1 = (0.0 + l_p1[u]) - l_cb[u];
+          const double a3 = 0.0 + l_p3[u];
+          const double v1 = y1 + s1 * a1;
+          y1 = v1 - s1 * fmax(v1 / s1, -kEps);
+          y3n = y3n + s3 * a3 - s3;
+          if (writer) { atomicAdd(ys + 2 * q + 1, y1); atomicAdd(ys + G.r3 + q, y3n); }
+        }
+        const double sS = 0.0 + l_ps[u];
+        const double mf = l_m[u];
+        const double gc = -y1 + mf * l_y2[u] - sS;
+        const double co = l_c[u];
+        double cn = co - tau * gc / (1.0 + mf + (double)N);
+        cn = fmin(fmax(cn, 0.0), 1.0);
+        const double cb = 2.0 * cn - co;
+        iy1[q] = y1; iy3[q] = y3n; icb[q] = cb;
+        if (writer) { dy[2 * q + 1] = y1; dy[G.r3 + q] = y3n; dcbar[q] = cb; dc[q] = cn; atomicAdd(cs + q, cn); }
+      }
+    }
+  }
+  {
+    // C4 dual: the F partials of a column, all requested at once, added in function order (strided_sum's order)
+    const double* __restrict__ Kj = in.Kj + (int64_t)b * N;
+    for (int j = tid; j < N; j += nth) {
+      double yn = sy[G.r4 + j];
+      if (post) {
+        double a = 0.0;
+        if (F <= 16) {
+          double v[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = k < F ? P4[(int64_t)k * N + j] : 0.0;
+          const double s4 = st.S4[(int64_t)b * N + j], kj = Kj[j];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) if (k < F) a += v[k];
+          const double s = sigma * s4;
+          const double vv = yn + s * a;
+          yn = vv - s * fmin(vv / s, kj);
+        } else {
+          a = strided_sum(P4 + j, F, N);
+          const double s = sigma * st.S4[(int64_t)b * N + j];
+          const double vv = yn + s * a;
+          yn = vv - s * fmin(vv / s, Kj[j]);
+        }
+        if (writer) atomicAdd(ys + G.r4 + j, yn);
+      }
+      iy4[j] = yn;
+      if (writer) dy[G.r4 + j] = yn;
+    }
+  }
+}
+
+// C2 dual of the instance from the cbar just computed (shared memory); only the writer needs it (the pass does not read y2)
+__device__ __forceinline__ void bulk_small_y2(const MfGeo& G, const MfIn& in, const MfSt& st, int b, double sigma,
+                                              const double* __restrict__ sy, double* __restrict__ dy, const double* icb, int tid, int nth) {
+  const int N = G.N, F = G.F;
+  const double* __restrict__ m = in.m + (int64_t)b * F;
+  const double* __restrict__ Mj = in.Mj + (int64_t)b * N;
+  double* __restrict__ ys = st.ysum + (int64_t)b * G.rows;
+  const double s = sigma * st.S2[b];
+  for (int j = tid; j < N; j += nth) {
+    const double y2 = sy[G.r2 + j], mj = Mj[j];
+    double a = 0.0;
+    for (int f = 0; f < F; ++f) a += m[f] * icb[f * N + j];
+    const double vv = y2 + s * a;
+    const double yn = vv - s * fmin(vv / s, mj);
+    dy[G.r2 + j] = yn; atomicAdd(ys + G.r2 + j, yn);
+  }
+}
+
 // ---- the pass -------------------------------------------------------------------------------------------------
 // grid: one block per SM (at most one block per tile); block: (cfg.nw + 1) warps, the LAST warp is the producer.
-// tile n of block k is slab  k + n * gridDim.x  (slab = b * F + f); slabs of converged instances go through the barrier
-// protocol without copies or arithmetic, so stage and phase are closed formulas of n for both roles.
-// EVERYTHING a consumer reads arrives through the stage: the slabs of x, yS (xsum, ysum), the delay matrix, the vectors
-// w[f,:], r[f,:], y3[f,:], y4, cbar[f,:], the (C1a, C1b) multiplier pairs of the function, and a header {tau, sigma / 2,
-// live} written by the producer -- a consumer's only global accesses are the stores of the partial sums (measured: with
-// the vectors read from global memory a tile cost 4.5 us of dependent L2 round trips, all warps in lockstep).
-template <bool RED>
+// Tiles: slab = b * F + f.  !FUSE: tile n of block k is slab k + n * gridDim.x.  FUSE: a block owns a CONTIGUOUS run of
+// slabs (so it meets few instances, and the small-vector update of an instance runs once per block that holds tiles of
+// it).  Slabs of converged instances go through the barrier protocol without copies or arithmetic, so stage and phase are
+// closed formulas of n for both roles.
+// EVERYTHING a consumer reads arrives through shared memory: the slabs of x, yS (xsum, ysum), the delay matrix, the vectors
+// w[f,:], r[f,:] and a header {tau, sigma / 2, live} written by the producer; y3[f,:], y4, cbar[f,:] and the (C1a, C1b)
+// multiplier pairs come through the stage (!FUSE) or from the block's own small-vector update (FUSE) -- a consumer's only
+// global accesses on the tile path are the stores of the partial sums (measured: with the vectors read from global memory a
+// tile cost 4.5 us of dependent L2 round trips, all warps in lockstep).
+template <bool RED, bool FUSE>
 __global__ void __launch_bounds__((kBulkMaxWarps + 1) * 32, 1)
-k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, BulkCfg cfg) {
+k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, BulkCfg cfg, BulkFuse fz) {
   extern __shared__ __align__(128) unsigned char bulk_smem_raw[];
   const int N = G.N, F = G.F, NW = cfg.nw, S = cfg.stages;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t NN = (int64_t)N * N;
   const int64_t total = (int64_t)B * F;
-  // shared-memory carve: [barriers 256 B][column partials 3 * NW * N doubles][stages], stages 128-byte aligned
+  // shared-memory carve: [barriers 256 B][column partials 3 * NW * N doubles][per-instance vectors (FUSE)][stages]
   unsigned char* base = bulk_smem_raw;
   double* colbuf = reinterpret_cast<double*>(base + 256);
   const uint32_t base_addr = smem_addr(base);
-  const uint32_t stage0 = (base_addr + 256u + (uint32_t)(3 * NW * N * 8) + 127u) & ~127u;
+  const uint32_t inst0 = (base_addr + 256u + (uint32_t)(3 * NW * N * 8) + 127u) & ~127u;
+  const uint32_t stage0 = inst0 + 2u * cfg.inst_bytes;
   const uint32_t stage_bytes = cfg.stage_bytes;
   const uint32_t bar_full = base_addr, bar_done = base_addr + 8u * (uint32_t)S;
+  const uint32_t bar_ifull = base_addr + 16u * (uint32_t)S, bar_ifree = bar_ifull + 16u;      // two instance-vector buffers (FUSE)
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8u * s, 1u); mbar_init(bar_done + 8u * s, (uint32_t)NW); }
+    for (int q = 0; q < 2; ++q) { mbar_init(bar_ifull + 8u * q, (uint32_t)kBulkSmallWarps); mbar_init(bar_ifree + 8u * q, (uint32_t)NW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
   __syncthreads();
-  // number of tiles of this block
-  const int64_t first = blockIdx.x;
-  const int T = first < total ? (int)((total - first + gridDim.x - 1) / gridDim.x) : 0;
+  // tiles of this block
+  int64_t first, step; int T;
+  if (FUSE) {
+    const int64_t q = total / gridDim.x, rem = total - q * gridDim.x;
+    first = (int64_t)blockIdx.x * q + (blockIdx.x < rem ? blockIdx.x : rem);
+    T = (int)(q + (blockIdx.x < rem ? 1 : 0));
+    step = 1;
+  } else {
+    first = blockIdx.x; step = gridDim.x;
+    T = first < total ? (int)((total - first + gridDim.x - 1) / gridDim.x) : 0;
+  }
   const uint32_t vecb = (uint32_t)N * 8u;          // bytes of one N-vector (a multiple of 16: N is even)
 
   if (warp == NW) {
@@ -164,13 +313,13 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
     if (lane == 0) {
       struct Prep { double tau, shalf; int conv; };
       auto prep_tile = [&](int n) {          // the control block of the tile's instance (requested ahead of the waits)
-        const int64_t slab = first + (int64_t)n * gridDim.x;
+        const int64_t slab = first + (int64_t)n * step;
         const int b = (int)(slab / F);
         Prep p; p.tau = ctl[b].tau; p.shalf = 0.5 * ctl[b].sigma; p.conv = ctl[b].converged;
         return p;
       };
       auto load_tile = [&](int n, const Prep& pr) {
-        const int64_t slab = first + (int64_t)n * gridDim.x;
+        const int64_t slab = first + (int64_t)n * step;
         const int b = (int)(slab / F), f = (int)(slab - (int64_t)b * F);
         const int s = n % S;
         const uint32_t bar = bar_full + 8u * s, dst = stage0 + (uint32_t)s * stage_bytes;
@@ -180,7 +329,7 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
         const double* xg = st.x + (int64_t)b * G.cols + (int64_t)f * NN;
         const double* yb = st.y + (int64_t)b * G.rows;
         const double* sg = yb + G.rs + (int64_t)f * NN;
-        mbar_arrive_expect_tx(bar, (cfg.streams + 1u) * cfg.slab_bytes + 7u * vecb);
+        mbar_arrive_expect_tx(bar, (cfg.streams + 1u) * cfg.slab_bytes + (FUSE ? 2u : 7u) * vecb);
         bulk_load(dst, xg, cfg.slab_bytes, bar);
         bulk_load(dst + cfg.slab_stride, sg, cfg.slab_bytes, bar);
         if (!RED) {
@@ -191,13 +340,15 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
         const uint32_t v = dst + cfg.vec_off;
         bulk_load(v, in.w + ((int64_t)b * F + f) * N, vecb, bar);
         bulk_load(v + vecb, in.r + ((int64_t)b * F + f) * N, vecb, bar);
-        bulk_load(v + 2u * vecb, yb + G.r3 + (int64_t)f * N, vecb, bar);
-        bulk_load(v + 3u * vecb, yb + G.r4, vecb, bar);
-        bulk_load(v + 4u * vecb, st.cbar + (int64_t)b * G.C + (int64_t)f * N, vecb, bar);
-        bulk_load(v + 5u * vecb, yb + 2 * (int64_t)f * N, 2u * vecb, bar);
+        if (!FUSE) {
+          bulk_load(v + 2u * vecb, yb + G.r3 + (int64_t)f * N, vecb, bar);
+          bulk_load(v + 3u * vecb, yb + G.r4, vecb, bar);
+          bulk_load(v + 4u * vecb, st.cbar + (int64_t)b * G.C + (int64_t)f * N, vecb, bar);
+          bulk_load(v + 5u * vecb, yb + 2 * (int64_t)f * N, 2u * vecb, bar);
+        }
       };
       auto store_tile = [&](int n) {
-        const int64_t slab = first + (int64_t)n * gridDim.x;
+        const int64_t slab = first + (int64_t)n * step;
         const int b = (int)(slab / F), f = (int)(slab - (int64_t)b * F);
         if (!ctl[b].converged && cfg.diag != 1 && cfg.diag != 3) {
           double* xg = st.x + (int64_t)b * G.cols + (int64_t)f * NN;
@@ -237,16 +388,66 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
     return;
   }
 
+  // -------------------------------------------------------------- small-vector warps (FUSE): one update per instance
+  // of the block's run, into one of two shared buffers, AHEAD of the consumers (the update is a chain of dependent L2
+  // round trips -- 7 us under load -- that must not sit on the consumers' path)
+  if (FUSE && warp > NW) {
+    const int tid = (warp - NW - 1) * 32 + lane, nth = kBulkSmallWarps * 32;
+    const bool chunk_first = fz.force_first || (fz.first && *fz.first);
+    int m = 0;
+    for (int n = 0; n < T; ++n) {
+      const int64_t slab = first + n;
+      const int b = (int)(slab / F), f = (int)(slab - (int64_t)b * F);
+      if (!(n == 0 || f == 0)) continue;
+      const uint32_t ib = (uint32_t)(m & 1);
+      if (m >= 2) mbar_wait(bar_ifree + 8u * ib, (uint32_t)(((m - 2) >> 1) & 1));
+      if (!ctl[b].converged && cfg.diag == 0) {
+        double* iy1 = reinterpret_cast<double*>(base + (inst0 - base_addr) + ib * cfg.inst_bytes);
+        double* iy3 = iy1 + G.C; double* icb = iy3 + G.C; double* iy4 = icb + G.C;
+        const double tau_b = ctl[b].tau, sigma_b = ctl[b].sigma;
+        const bool writer = f == 0;          // the block that owns the instance's first slab
+        const double* sy = chunk_first ? st.y + (int64_t)b * G.rows : fz.src_q + (int64_t)b * fz.qstride;
+        const double* sc = chunk_first ? st.x + (int64_t)b * G.cols + G.X : sy + G.rs;
+        const double* scb = chunk_first ? st.cbar + (int64_t)b * G.C : sc + G.C;
+        double* dy = fz.dst_q + (int64_t)b * fz.qstride;
+        bulk_small_pre(G, in, st, fz, b, !chunk_first, writer, tau_b, sigma_b, sy, sc, scb, dy, dy + G.rs, dy + G.rs + G.C,
+                       iy1, iy3, icb, iy4, tid, nth);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ifull + 8u * ib);          // the consumers need nothing of the C2 dual
+        if (writer) {
+          asm volatile("bar.sync 2, %0;" ::"r"(nth) : "memory");  // every cbar of the instance is in the buffer
+          bulk_small_y2(G, in, st, b, sigma_b, sy, dy, icb, tid, nth);
+        }
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ifull + 8u * ib);
+      }
+      ++m;
+    }
+    return;
+  }
+
   // -------------------------------------------------------------- consumers
   const int nthr = NW * 32;
   const unsigned jc = (unsigned)(2 * lane);
   const bool vj = (int)jc < N;
   const unsigned jl = vj ? jc : 0u;
+  // per-instance vectors of the fused small-vector update (written by the small-vector warps)
+  double *iy1 = nullptr, *iy3 = nullptr, *icb = nullptr, *iy4 = nullptr;
+  int m_inst = 0; uint32_t cur_ib = 0;
   for (int n = 0; n < T; ++n) {
-    const int64_t slab = first + (int64_t)n * gridDim.x;
+    const int64_t slab = first + (int64_t)n * step;
     const int b = (int)(slab / F), f = (int)(slab - (int64_t)b * F);
     const int s = n % S;
     const uint32_t ph = (uint32_t)((n / S) & 1);
+    const bool inst_last = FUSE && (f == F - 1 || n == T - 1);
+    if (FUSE && (n == 0 || f == 0)) {          // first tile of an instance in this block: its vectors
+      cur_ib = (uint32_t)(m_inst & 1);
+      mbar_wait(bar_ifull + 8u * cur_ib, (uint32_t)((m_inst >> 1) & 1));
+      iy1 = reinterpret_cast<double*>(base + (inst0 - base_addr) + cur_ib * cfg.inst_bytes);
+      iy3 = iy1 + G.C; icb = iy3 + G.C; iy4 = icb + G.C;
+      ++m_inst;
+    }
     mbar_wait(bar_full + 8u * s, ph);
     unsigned char* stage_ptr = base + (stage0 - base_addr) + (size_t)s * stage_bytes;
     double* xs_ = reinterpret_cast<double*>(stage_ptr);
@@ -255,19 +456,21 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
     double* ysum_ = reinterpret_cast<double*>(stage_ptr + 3u * cfg.slab_stride);
     const double* d_ = reinterpret_cast<const double*>(stage_ptr + cfg.streams * cfg.slab_stride);
     const double* vw = reinterpret_cast<const double*>(stage_ptr + cfg.vec_off);
-    const double *vr = vw + N, *vy3 = vw + 2 * N, *vy4 = vw + 3 * N, *vcb = vw + 4 * N, *vy1 = vw + 5 * N, *hdr = vw + 7 * N;
+    const double *vr = vw + N, *hdr = vw + 7 * N;
+    const double *vy3 = FUSE ? iy3 + f * N : vw + 2 * N, *vy4 = FUSE ? iy4 : vw + 3 * N, *vcb = FUSE ? icb + f * N : vw + 4 * N;
+    const double* vy1 = FUSE ? iy1 + f * N : vw + 5 * N;
     if (hdr[2] == 0.0) {          // converged instance (or a copy-only measurement): release the stage untouched
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_done + 8u * s);
+      if (lane == 0) { mbar_arrive(bar_done + 8u * s); if (inst_last) mbar_arrive(bar_ifree + 8u * cur_ib); }
       continue;
     }
     const double tau = hdr[0], shalf = hdr[1];
-    double* __restrict__ P3 = st.P3i + ((int64_t)b * G.C + (int64_t)f * N) * G.cti;
+    double* __restrict__ P3 = (FUSE ? fz.wP3 : st.P3i) + ((int64_t)b * G.C + (int64_t)f * N) * G.cti;
     double y1j[2], rj[2], rr4[2], cb[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const unsigned je = jl + e;
-      y1j[e] = vy1[2 * je + 1];
+      y1j[e] = FUSE ? vy1[je] : vy1[2 * je + 1];
       rj[e] = vr[je];
       rr4[e] = rj[e] * vy4[je];
       cb[e] = vcb[je];
@@ -310,7 +513,7 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
     // this warp's writes to the stage are done: make them visible to the async proxy, then release the stage
     fence_async_smem();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_done + 8u * s);
+    if (lane == 0) { mbar_arrive(bar_done + 8u * s); if (inst_last) mbar_arrive(bar_ifree + 8u * cur_ib); }
     // column sums: per-warp partials -> totals in warp order
     if (vj) {
 #pragma unroll
@@ -328,11 +531,56 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
         t1 += colbuf[(0 * NW + q) * N + j]; t4 += colbuf[(1 * NW + q) * N + j]; tS += colbuf[(2 * NW + q) * N + j];
       }
       const int64_t o = ((int64_t)b * F + f) * (int64_t)G.rt * N + j;      // rt = 1: one row tile per slab
-      st.P1[o] = t1;
-      st.P4[o] = r_tot * t4;
-      st.PS[o] = tS;
+      (FUSE ? fz.wP1 : st.P1)[o] = t1;
+      (FUSE ? fz.wP4 : st.P4)[o] = r_tot * t4;
+      (FUSE ? fz.wPS : st.PS)[o] = tS;
     }
     consumer_sync(nthr);
+  }
+}
+
+// end of a chunk of fused launches: POST of the last pass from the small state `q` (same arithmetic as k_mf_small), and the
+// whole small state back into the canonical arrays (y rows [0, rs), the c columns, cbar).  One block per instance.
+__global__ void __launch_bounds__(256)
+k_mf_small_from(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, const double* __restrict__ qbuf, int64_t qstride,
+                const double* __restrict__ rP1, const double* __restrict__ rP4, const double* __restrict__ rP3) {
+  const int b = blockIdx.x;
+  if (ctl[b].converged) return;
+  const int N = G.N, F = G.F, rt = G.rt, ct = G.cti;
+  const int C = (int)G.C;
+  const double sigma = ctl[b].sigma;
+  const double* __restrict__ sy = qbuf + (int64_t)b * qstride;
+  const double* __restrict__ sc = sy + G.rs;
+  const double* __restrict__ scbar = sc + C;
+  double* __restrict__ y = st.y + (int64_t)b * G.rows;
+  double* __restrict__ ys = st.ysum + (int64_t)b * G.rows;
+  double* __restrict__ c = st.x + (int64_t)b * G.cols + G.X;
+  double* __restrict__ cbar = st.cbar + (int64_t)b * C;
+  const double* __restrict__ P1 = rP1 + (int64_t)b * F * rt * N;
+  const double* __restrict__ P4 = rP4 + (int64_t)b * F * rt * N;
+  const double* __restrict__ P3 = rP3 + (int64_t)b * C * ct;
+  const double* __restrict__ Kj = in.Kj + (int64_t)b * N;
+  const int K4 = F * rt;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const double a = strided_sum(P4 + j, K4, N);
+    const double s = sigma * st.S4[(int64_t)b * N + j];
+    const double v = sy[G.r4 + j] + s * a;
+    const double yn = v - s * fmin(v / s, Kj[j]);
+    y[G.r4 + j] = yn; ys[G.r4 + j] += yn;
+    y[G.r2 + j] = sy[G.r2 + j];
+  }
+  const double s1 = sigma / (double)(N + 1), s3 = sigma / (double)N;
+  for (int q = threadIdx.x; q < C; q += blockDim.x) {
+    const int f = q / N, j = q - f * N;
+    const int64_t po = (int64_t)f * rt * N + j;
+    const double a1 = strided_sum(P1 + po, rt, N) - scbar[q];
+    const double a3 = strided_sum(P3 + (int64_t)q * ct, ct, 1);
+    const double v1 = sy[2 * q + 1] + s1 * a1;
+    const double y1 = v1 - s1 * fmax(v1 / s1, -kEps);
+    const double y3n = sy[G.r3 + q] + s3 * a3 - s3;
+    y[2 * q + 1] = y1; ys[2 * q + 1] += y1;
+    y[G.r3 + q] = y3n; ys[G.r3 + q] += y3n;
+    c[q] = sc[q]; cbar[q] = scbar[q];
   }
 }
 

@@ -230,7 +230,7 @@ def objective_weights(inst: InstanceBatch, kind, alpha=0.5):
 def pdhg_mf_solve(inst: InstanceBatch, max_iters=20000, check_every=64, eps_rel=1e-6, eps_abs=1e-8,
                   x0: Optional[torch.Tensor] = None, y0: Optional[torch.Tensor] = None, workspace=None,
                   scalar_kernel=False, rows_in_flight=0, _diag=0, kind="min_delay", alpha=0.5, node_cut=False,
-                  bulk=0, bulk_warps=0, bulk_stages=0, register_pass=False):
+                  bulk=0, bulk_warps=0, bulk_stages=0, register_pass=False, unfused_small=False):
     """Matrix-free PDHG on the strengthened relaxation (`neptune_pdhg_mf_solve`, and `neptune_pdhg_mf_solve_util`
     for the models with node columns): nothing is assembled, every coefficient is regenerated from the instance
     arrays.  Returns (x[B,cols], y[B,rows], results) in the canonical layout of
@@ -239,7 +239,7 @@ def pdhg_mf_solve(inst: InstanceBatch, max_iters=20000, check_every=64, eps_rel=
     something about the node term.  `bulk` (even N <= 64): 1 = the iteration pass with its streams staged through shared
     memory by the bulk-copy engine, 2 = the same with the running sums added by bulk reduction; `register_pass` forces
     the register passes whatever the library's default; `bulk_warps` / `bulk_stages` override the bulk pass's geometry
-    (measurements)."""
+    (measurements); `unfused_small` keeps the small-vector update of the bulk pass in its own launches."""
     _require_cuda()
     lib = _lib.load()
     from ._lib import FLAG_STRENGTHEN
@@ -255,10 +255,11 @@ def pdhg_mf_solve(inst: InstanceBatch, max_iters=20000, check_every=64, eps_rel=
     res = torch.zeros(inst.B * _PDHG_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     # reserved (tools and tests): bit 0 = force the 8-byte iteration pass, bits 4..6 = tool diagnostics,
     # bits 8..10 = rows of a warp in flight (0 = default), bit 11 = register passes, bit 12 / 13 = bulk-copy pass
-    # (staged sums / sums by bulk reduction), bits 14..18 = its consumer warps, bits 19..22 = cap on its stages
+    # (staged sums / sums by bulk reduction), bits 14..18 = its consumer warps, bits 19..22 = cap on its stages,
+    # bit 23 = small-vector update in its own launches (not inside the bulk pass)
     reserved = ((1 if scalar_kernel else 0) | (_diag << 4) | (rows_in_flight << 8) | ((1 << 11) if register_pass else 0)
                 | ((1 << 12) if bulk == 1 else 0) | ((1 << 13) if bulk == 2 else 0) | ((bulk_warps & 31) << 14)
-                | ((bulk_stages & 15) << 19))
+                | ((bulk_stages & 15) << 19) | ((1 << 23) if unfused_small else 0))
     prm = PdhgParams(max_iters, check_every, 0, reserved, eps_rel, eps_abs)
     if k == 0:
         check(lib.neptune_pdhg_mf_solve(inst.B, inst.N, inst.F, 0, _ptr(inst.d), _ptr(inst.w), _ptr(inst.r),

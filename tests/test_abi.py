@@ -77,7 +77,7 @@ def test_matrix_free_tile_geometry_covers_every_shape():
             slab = (8 * N * N + 127) // 128 * 128
             vec = ((7 * N + 4) * 8 + 127) // 128 * 128          # a stage: 2 or 4 read-write slabs + the delay matrix + the small vectors
             assert ok2 == 1 and 2 <= st2 <= 8 and 4 <= nw2 <= 15 and smem2 <= 227 * 1024 and smem2 >= st2 * (3 * slab + vec)
-            assert (nw2 * ((N + nw2 - 1) // nw2) >= N) and ok4 == (1 if 2 * (5 * slab + vec) + 3 * nw4 * N * 8 + 384 <= 227 * 1024 else 0)
+            assert (nw2 * ((N + nw2 - 1) // nw2) >= N) and ok4 == (1 if 2 * (5 * slab + vec) + 3 * nw4 * N * 8 + 512 <= 227 * 1024 else 0)
             if ok4:
                 assert st4 >= 2 and st4 * (5 * slab + vec) <= 227 * 1024
         assert dflt in (0, 1, 2) and (N > 32 or dflt == 0)

@@ -79,50 +79,55 @@ def _bulk_geometry(N, F, B=2):
 
 @pytest.mark.parametrize("shape", [(50, 4), (34, 3), (64, 3), (20, 5), (8, 4), (2, 2)])
 @pytest.mark.parametrize("mode", [1, 2], ids=["staged-sums", "bulk-reduction"])
-def test_bulk_copy_pass_equals_the_register_passes(shape, mode):
+@pytest.mark.parametrize("unfused", [False, True], ids=["small-vectors-in-pass", "small-vectors-own-launch"])
+def test_bulk_copy_pass_equals_the_register_passes(shape, mode, unfused):
     """even N <= 64: the pass with its streams staged through shared memory by cp.async.bulk (mode 1: x, yS and both
     running sums; mode 2: the running sums added by cp.reduce.async.bulk) does the arithmetic of the pair pass; the
     column sums are taken over another grouping of the rows, so the comparison is 1e-11, not bitwise.  Shapes whose
-    stage does not fit twice (N > 50 with four streams) fall back to the register pass -- the geometry says which."""
+    stage does not fit twice (N > 50 with four streams) fall back to the register pass -- the geometry says which.
+    By default the small-vector update (k_mf_small's arithmetic) runs inside the pass, per block and instance, on two
+    alternating small-state buffers; `unfused_small` keeps it in its own launches."""
     from neptune_mip_b200 import device
     ok4, st4, nw4, ok2, st2, nw2, dflt, smem2 = _bulk_geometry(*shape)
     assert ok2 == 1 and ok4 == (0 if shape[0] > 50 else 1)
     inst = cuda_batch([synth.random_payload(shape[0], shape[1], s, node_cores=60) for s in range(3)])
     kw = dict(max_iters=70, check_every=70, eps_rel=1e-13, eps_abs=1e-15)
     xa, ya, ra = device.pdhg_mf_solve(inst, scalar_kernel=True, **kw)
-    xb, yb, rb = device.pdhg_mf_solve(inst, bulk=mode, **kw)
+    xb, yb, rb = device.pdhg_mf_solve(inst, bulk=mode, unfused_small=unfused, **kw)
     assert _close(xb.cpu().numpy(), xa.cpu().numpy(), 1e-11) and _close(yb.cpu().numpy(), ya.cpu().numpy(), 1e-11)
     assert np.allclose(ra["primal_obj"], rb["primal_obj"], rtol=1e-11) and np.allclose(ra["dual_obj"], rb["dual_obj"], rtol=1e-9)
     # bit-reproducible: fixed summation orders, one addition per element in the reduction
-    xc, yc, rc = device.pdhg_mf_solve(inst, bulk=mode, **kw)
+    xc, yc, rc = device.pdhg_mf_solve(inst, bulk=mode, unfused_small=unfused, **kw)
     assert np.array_equal(xb.cpu().numpy(), xc.cpu().numpy()) and np.array_equal(yb.cpu().numpy(), yc.cpu().numpy())
 
 
-@pytest.mark.parametrize("mode,warps,stages", [(1, 0, 0), (2, 0, 0), (2, 8, 2), (2, 15, 3), (2, 5, 4), (1, 10, 2)])
-def test_bulk_copy_pass_many_tiles_per_block(mode, warps, stages):
+@pytest.mark.parametrize("mode,warps,stages,unfused", [(1, 0, 0, False), (2, 0, 0, False), (2, 0, 0, True), (2, 8, 2, False), (2, 15, 3, True),
+                                                       (2, 5, 4, False), (1, 10, 2, True), (2, 13, 2, False)])
+def test_bulk_copy_pass_many_tiles_per_block(mode, warps, stages, unfused):
     """more tiles per block than stages (every stage and both barrier phases are reused many times), every geometry the
     tools can ask for; against the numpy statement of the iteration on two instances and the pair pass on all"""
     from neptune_mip_b200 import device
     B = 96                                                   # 960 slabs over 148 blocks: 6-7 tiles per block
     payloads = [synth.random_payload(50, 10, s, node_cores=200) for s in range(B)]
     inst = cuda_batch(payloads)
-    kw = dict(max_iters=40, check_every=40, eps_rel=1e-13, eps_abs=1e-15)
+    kw = dict(max_iters=70, check_every=70, eps_rel=1e-13, eps_abs=1e-15)      # two graph replays of 32 + a remainder of 6
     xa, ya, ra = device.pdhg_mf_solve(inst, register_pass=True, **kw)
-    xb, yb, rb = device.pdhg_mf_solve(inst, bulk=mode, bulk_warps=warps, bulk_stages=stages, **kw)
+    xb, yb, rb = device.pdhg_mf_solve(inst, bulk=mode, bulk_warps=warps, bulk_stages=stages, unfused_small=unfused, **kw)
     assert _close(xb.cpu().numpy(), xa.cpu().numpy(), 1e-11) and _close(yb.cpu().numpy(), ya.cpu().numpy(), 1e-11)
     for b in (0, B - 1):
-        xr, yr, info = run_fixed(arrays_of(payloads[b]), 40)
+        xr, yr, info = run_fixed(arrays_of(payloads[b]), 70)
         assert _close(xb[b].cpu().numpy(), xr, 1e-9) and _close(yb[b].cpu().numpy(), yr, 1e-9)
 
 
 @pytest.mark.parametrize("mode", [1, 2])
-def test_bulk_copy_pass_frozen_instances_and_solo_runs(mode):
+@pytest.mark.parametrize("unfused", [False, True])
+def test_bulk_copy_pass_frozen_instances_and_solo_runs(mode, unfused):
     """converged instances go through the barrier protocol without copies: their state stays frozen, the others take
     exactly the trajectory of their solo runs (restarts included)"""
     from neptune_mip_b200 import device
     ps = [synth.random_payload(8, 4, 1, node_cores=200), synth.random_payload(8, 4, 1, node_cores=12),
           synth.random_payload(8, 4, 2, node_cores=30)]
-    kw = dict(max_iters=20000, check_every=128, eps_rel=1e-6, eps_abs=1e-9, bulk=mode)
+    kw = dict(max_iters=20000, check_every=128, eps_rel=1e-6, eps_abs=1e-9, bulk=mode, unfused_small=unfused)
     x, y, res = device.pdhg_mf_solve(cuda_batch(ps), **kw)
     assert len(set(res["iters"].tolist())) > 1
     for b, p in enumerate(ps):

@@ -122,10 +122,11 @@ def bulk_diag():
         for diag, what in ((0, "full"), (1, "arithmetic only (no copies)"), (2, "copy through (no arithmetic)"), (3, "loads only")):
             for cap in (0, 2):
                 for warps in ((0, 8) if diag == 1 else (0,)):
-                    kw = dict(bulk=mode, bulk_stages=cap, bulk_warps=warps, _diag=diag)
-                    device.pdhg_mf_solve(inst, max_iters=32, check_every=32, **kw)
-                    _, ms = timed(lambda: device.pdhg_mf_solve(inst, **kw, **kwt))
-                    print("BDIAG C2 batch 256 mode %d stage cap %d warps %d %s us/iter %.1f" % (mode, cap, warps, what, 1e3 * ms / iters), flush=True)
+                    for unfused in (False, True):
+                        kw = dict(bulk=mode, bulk_stages=cap, bulk_warps=warps, _diag=diag, unfused_small=unfused)
+                        device.pdhg_mf_solve(inst, max_iters=32, check_every=32, **kw)
+                        _, ms = timed(lambda: device.pdhg_mf_solve(inst, **kw, **kwt))
+                        print("BDIAG C2 batch 256 mode %d stage cap %d warps %d %s %s us/iter %.1f" % (mode, cap, warps, "small vectors in their own launch" if unfused else "small vectors inside the pass", what, 1e3 * ms / iters), flush=True)
     device.pdhg_mf_solve(inst, max_iters=32, check_every=32, _diag=4)
     _, ms = timed(lambda: device.pdhg_mf_solve(inst, _diag=4, **kwt))
     print("BDIAG small-vector kernel alone us/iter %.1f" % (1e3 * ms / iters), flush=True)
