@@ -161,8 +161,9 @@ def run_reference(args):
 # our arm
 # ---------------------------------------------------------------------------------------------------
 def pdhg_roofline(device, host_fn, B, iters, peak, peak_src, in_step=None):
-    """Achieved HBM GB/s of the PDHG iteration (k_mf_iter2 / k_mf_iter + k_mf_small): algorithmic bytes (DESIGN.md
-    section 3b: 64 B per x column + the F*N-sized vectors + d) over the CUDA-event time of the solver call."""
+    """Achieved HBM GB/s of the PDHG iteration (C2: k_mf_iter_bulk, the bulk-copy staged pass with the small-vector update
+    inside the launch): algorithmic bytes (64 B per x column + the F*N-sized vectors + d) over the
+    CUDA-event time of the solver call."""
     import torch
     X = N_FUNCS * N_NODES * N_NODES
     if in_step is not None:
@@ -182,15 +183,18 @@ def pdhg_roofline(device, host_fn, B, iters, peak, peak_src, in_step=None):
         note = (f"probe outside the timed steps: the same kernels on {B} C2 instances (working set {B * 32 * X // 1000000} MB "
                 f"> L2), {iters} iterations, one solver call timed with CUDA events -- the step's own batch is L2-resident")
     ach = bytes_iter * it / (ms / 1e3) / 1e9
-    tpath = os.path.join(ROOT, "profiles", "r02_pdhg_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02c_pdhg_traffic.json")
     traffic = None
     if os.path.exists(tpath):
         t = json.load(open(tpath))
         traffic = {"dram_bytes_per_iteration": t["per_instance_dram_bytes"] * B, "captured_on": t.get("kernel_build")}
     return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "traffic": traffic["dram_bytes_per_iteration"] if traffic else None, "traffic_source": traffic["captured_on"] if traffic else None,
-            "kernel": "PDHG iteration (matrix-free) = k_mf_iter2<1,2> (one streaming pass over x, yS and their running sums, "
-                      "16-byte accesses) + k_mf_small (F*N-sized vectors)",
+            "kernel": "PDHG iteration (matrix-free) = k_mf_iter_bulk<RED, FUSE>: one launch per iteration -- x, yS, d and the "
+                      "function's vectors staged through shared memory by cp.async.bulk + mbarrier (one producer lane), updated "
+                      "in place by the consumer warps, written back by bulk stores, running sums by cp.reduce.async.bulk "
+                      "add.f64, the F*N-sized vectors (k_mf_small's arithmetic) updated by two small-vector warps of the same "
+                      "launch; tools and tests can still ask for the register passes k_mf_iter2 / k_mf_iter + k_mf_small",
             "bytes_per_iteration": bytes_iter, "iterations_timed": it, "pdhg_ms": ms, "us_per_iteration": 1e3 * ms / it,
             "peak_source": peak_src, "measured": note}
 
@@ -337,7 +341,7 @@ def run_ours(args):
             roof = pdhg_roofline(device, None, B, 0, peak, peak_src,
                                  in_step=(acc["pdhg_ms"], acc["iters"], acc["bytes"], "inside the timed steps (CUDA events around the solver call)"))
         elif rank == 0:
-            roof = pdhg_roofline(device, lambda b: make_hosts("C2", b, 0), 256, 2048, peak, peak_src)
+            roof = pdhg_roofline(device, lambda b: make_hosts("C2", b, 0), args.probe_batch, 2048, peak, peak_src)
         if roof:
             roof["pdhg_share_of_step"] = acc["pdhg_ms"] / ms_total
             roof["search_share_of_step"] = acc["lns_ms"] / ms_total
@@ -351,7 +355,7 @@ def run_ours(args):
                        "lns_chains": args.lns_chains, "lns_rounds": args.lns_rounds, "lns_k": args.lns_k, "lns_noise": args.lns_noise, "lns_final_k4_rounds": args.lns_final_k4,
                        "elites": args.elites, "lp_path": acc["path"],
                        "l2": ("PDHG working set of the batch (%d MB) exceeds the 126 MB L2" % (B * 32 * X // 1000000)) if B * 32 * X > L2_BYTES else
-                             "the step's PDHG working set is L2-resident (the search sets the batch size); the HBM roofline is probed on 256 instances, see roofline.measured"},
+                             "the step's PDHG working set is L2-resident (the search sets the batch size); the HBM roofline is probed on " + str(args.probe_batch) + " instances, see roofline.measured"},
             "e2e": {"value": e2e_value, "unit": "instances/s", "h2d_bytes_per_step": inst.h2d_bytes(),
                     "d2h_bytes_per_step": d2h.get("bytes", 0), "ms_per_step": ms_e2e, "steps": e2e_steps},
             "gpu_launches": launches, "clocks": clocks, "quality": quality,
@@ -490,6 +494,7 @@ def main():
     ap.add_argument("--chains", type=int, default=8, help="add/drop/swap search (--search local)")
     ap.add_argument("--sweeps", type=int, default=400)
     ap.add_argument("--e2e-steps", type=int, default=2, help="steps of the end-to-end leg (at most --steps)")
+    ap.add_argument("--probe-batch", type=int, default=296, help="instances of the PDHG roofline probe: two per SM (working set 0.8 MB each, 237 MB > L2); 256 instances measure 4.90 TB/s where 296 measure 5.12")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the C5 / C3 / C4 sub-records")
     ap.add_argument("--c5-instances", type=int, default=4096)

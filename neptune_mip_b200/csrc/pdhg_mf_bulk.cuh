@@ -28,6 +28,7 @@
 namespace neptune {
 
 constexpr int kBulkMaxStages = 8;
+constexpr int kRows = 1;                          // rows of a consumer warp in flight together
 constexpr int kBulkSmallWarps = 2;                // warps of the in-pass small-vector update (FUSE)
 constexpr int kBulkMaxWarps = 15;                 // consumer warps
 constexpr size_t kBulkSmemMax = 227 * 1024;       // dynamic shared memory a block may opt in to on sm_100a
@@ -477,38 +478,55 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
     }
     const double r_tot = (int)threadIdx.x < N ? vr[threadIdx.x] : 0.0;      // for the totals below: read before the stage is released
     double a1[2] = {0.0, 0.0}, a4[2] = {0.0, 0.0}, aS[2] = {0.0, 0.0};
-    for (int i = warp; i < N; i += NW) {
-      const double wfi = vw[i], ty = vy3[i];
-      double rsum = 0.0;
-      if (vj) {
-        const unsigned o = (unsigned)i * (unsigned)N + jc;
-        const double2 xv = *reinterpret_cast<const double2*>(xs_ + o);
-        const double2 sv = *reinterpret_cast<const double2*>(ss_ + o);
-        const double2 dv = *reinterpret_cast<const double2*>(d_ + o);
-        double xn[2], sn[2];
+    // kRows rows of a warp are in flight together (independent dependency chains: the arithmetic is latency-bound);
+    // a column's sums still take its rows in increasing order
+    for (int i0 = warp; i0 < N; i0 += kRows * NW) {
+      double wfi[kRows], ty[kRows]; double2 xv[kRows], sv[kRows], dv[kRows], xq[kRows], sq[kRows];
+      bool ok[kRows]; unsigned o[kRows];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const double xo = e ? xv.y : xv.x, so = e ? sv.y : sv.x, de = e ? dv.y : dv.x;
-          const double wr = fabs(wfi * rj[e]);
-          const double g = __dmul_rn(de, wfi) + y1j[e] + ty + wfi * rr4[e] + so;
-          double x1 = xo - tau * g * mf_rcp(3.0 + wr);
-          x1 = fmin(fmax(x1, 0.0), 1.0);
-          const double xb = 2.0 * x1 - xo;
-          const double s1 = fmax(so + shalf * (xb - cb[e]), 0.0);
-          xn[e] = x1; sn[e] = s1;
-          a1[e] += xb; a4[e] += wfi * xb; aS[e] += s1; rsum += xb;
-        }
-        *reinterpret_cast<double2*>(xs_ + o) = make_double2(xn[0], xn[1]);
-        *reinterpret_cast<double2*>(ss_ + o) = make_double2(sn[0], sn[1]);
+      for (int u = 0; u < kRows; ++u) {
+        const int i = i0 + u * NW;
+        ok[u] = i < N;
+        const int ir = ok[u] ? i : i0;
+        wfi[u] = vw[ir]; ty[u] = vy3[ir];
+        o[u] = (unsigned)ir * (unsigned)N + jl;
+        xv[u] = *reinterpret_cast<const double2*>(xs_ + o[u]);
+        sv[u] = *reinterpret_cast<const double2*>(ss_ + o[u]);
+        dv[u] = *reinterpret_cast<const double2*>(d_ + o[u]);
         if (!RED) {
-          const double2 xq = *reinterpret_cast<const double2*>(xsum_ + o);
-          const double2 sq = *reinterpret_cast<const double2*>(ysum_ + o);
-          *reinterpret_cast<double2*>(xsum_ + o) = make_double2(xq.x + xn[0], xq.y + xn[1]);
-          *reinterpret_cast<double2*>(ysum_ + o) = make_double2(sq.x + sn[0], sq.y + sn[1]);
+          xq[u] = *reinterpret_cast<const double2*>(xsum_ + o[u]);
+          sq[u] = *reinterpret_cast<const double2*>(ysum_ + o[u]);
         }
       }
-      rsum = warp_sum(rsum);
-      if (lane == 0) P3[(int64_t)i * G.cti] = rsum;
+#pragma unroll
+      for (int u = 0; u < kRows; ++u) {
+        double rsum = 0.0;
+        if (vj && ok[u]) {
+          double xn[2], sn[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double xo = e ? xv[u].y : xv[u].x, so = e ? sv[u].y : sv[u].x, de = e ? dv[u].y : dv[u].x;
+            const double wr = fabs(wfi[u] * rj[e]);
+            const double g = __dmul_rn(de, wfi[u]) + y1j[e] + ty[u] + wfi[u] * rr4[e] + so;
+            double x1 = xo - tau * g * mf_rcp(3.0 + wr);
+            x1 = fmin(fmax(x1, 0.0), 1.0);
+            const double xb = 2.0 * x1 - xo;
+            const double s1 = fmax(so + shalf * (xb - cb[e]), 0.0);
+            xn[e] = x1; sn[e] = s1;
+            a1[e] += xb; a4[e] += wfi[u] * xb; aS[e] += s1; rsum += xb;
+          }
+          *reinterpret_cast<double2*>(xs_ + o[u]) = make_double2(xn[0], xn[1]);
+          *reinterpret_cast<double2*>(ss_ + o[u]) = make_double2(sn[0], sn[1]);
+          if (!RED) {
+            *reinterpret_cast<double2*>(xsum_ + o[u]) = make_double2(xq[u].x + xn[0], xq[u].y + xn[1]);
+            *reinterpret_cast<double2*>(ysum_ + o[u]) = make_double2(sq[u].x + sn[0], sq[u].y + sn[1]);
+          }
+        }
+        if (ok[u]) {          // uniform over the warp
+          rsum = warp_sum(rsum);
+          if (lane == 0) P3[(int64_t)(i0 + u * NW) * G.cti] = rsum;
+        }
+      }
     }
     // this warp's writes to the stage are done: make them visible to the async proxy, then release the stage
     fence_async_smem();
