@@ -1037,6 +1037,11 @@ static void mf_launch_eval(const MfPlan& P, int which, int only_ps) {
 // every cbar of the instance, so it is a launch of its own
 static void mf_launch_small(const MfPlan& P, int mask, const int* skip_post) {
   dim3 g(P.small_blocks, P.B);
+  if (P.diag & 4) {          // tools (small-vector kernel alone): NEPTUNE_SMALL_MASK restricts the phases that run
+    const char* e = getenv("NEPTUNE_SMALL_MASK");
+    if (e && *e) mask &= atoi(e);
+    if (!mask) return;
+  }
   if (P.fused) {
     const int threads = P.G.C >= 512 ? 512 : (P.G.C <= 64 ? 64 : (int)((P.G.C + 31) / 32) * 32);
     k_mf_small<<<g, threads, 0, P.s>>>(P.G, P.in, P.st, P.ctl, mask, skip_post, 1); NEPTUNE_COUNT(1);

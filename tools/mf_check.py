@@ -132,6 +132,19 @@ def bulk_diag():
     print("BDIAG small-vector kernel alone us/iter %.1f" % (1e3 * ms / iters), flush=True)
 
 
+def small_phases():
+    """the small-vector kernel alone, phase by phase (NEPTUNE_SMALL_MASK: 1 POST, 2 PREC, 4 Y2), at C3 and the C4 share"""
+    for name, inst, iters in (("C3 500x50", synth_batch(500, 50, 1), 256), ("C4 share 2000x25", synth_batch(2000, 25, 1), 64)):
+        for mask in (7, 1, 2, 4, 3):
+            os.environ["NEPTUNE_SMALL_MASK"] = str(mask)
+            device.pdhg_mf_solve(inst, max_iters=32, check_every=32, _diag=4)
+            _, ms = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14, _diag=4))
+            print("SMALL", name, "phases mask", mask, "us/iter %.1f" % (1e3 * ms / iters), flush=True)
+        os.environ.pop("NEPTUNE_SMALL_MASK", None)
+        _, ms = timed(lambda: device.pdhg_mf_solve(inst, max_iters=iters, check_every=iters, eps_rel=1e-12, eps_abs=1e-14))
+        print("SMALL", name, "whole iteration us/iter %.1f GB/s %.0f" % (1e3 * ms / iters, bytes_iter(inst) * iters / ms / 1e6), flush=True)
+
+
 def ceiling():
     """what plain torch kernels reach on this box for copy / read-modify-write streams"""
     n = 1 << 27
@@ -164,6 +177,8 @@ if __name__ == "__main__":
     t0 = time.time()
     if "--variants" in sys.argv:
         variants()
+    if "--small-phases" in sys.argv:
+        small_phases()
     if "--bulk-diag" in sys.argv:
         bulk_diag()
     if "--bulk" in sys.argv:
