@@ -850,6 +850,20 @@ __global__ void k_mf_restart_norms(int B, int nblk, const double* __restrict__ p
   ctl[b].acc[ACC_DX2] = dx2; ctl[b].acc[ACC_DY2] = dy2;
 }
 
+// the instances still iterating, in increasing order: out[0] = count, out[1..] = indices (one warp, ordered compaction)
+__global__ void k_mf_live(int B, const Ctl* __restrict__ ctl, int* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  int count = 0;
+  for (int base = 0; base < B; base += 32) {
+    const int b = base + lane;
+    const bool on = b < B && !ctl[b].converged;
+    const unsigned mask = __ballot_sync(0xffffffffu, on);
+    if (on) out[1 + count + __popc(mask & ((1u << lane) - 1u))] = b;
+    count += __popc(mask);
+  }
+  if (lane == 0) out[0] = count;
+}
+
 static inline size_t mf_align(size_t v) { return (v + 255) & ~(size_t)255; }
 constexpr int kMfRestartBlocks = 64;       // blocks per instance of k_mf_apply_restart / k_mf_setup (upper bound)
 
@@ -873,7 +887,7 @@ static MfWs mf_layout(int B, const MfGeo& G) {
   W.part = take((size_t)B * kMfRestartBlocks * 2 * 8);
   W.ctl = take((size_t)B * sizeof(Ctl));
   W.flag = take(256);
-  W.cnt = take((size_t)B * 2 * sizeof(int));
+  W.cnt = take(((size_t)B + 1) * 2 * sizeof(int));     // live list of the bulk pass: count + indices
   // the two small-state buffers the fused launches of a chunk alternate between: y rows [0, rs) | c | cbar per instance
   W.q0 = take((size_t)B * (G.rs + 2 * G.C) * 8); W.q1 = take((size_t)B * (G.rs + 2 * G.C) * 8);
   // ... and the second set of partial sums (a fused launch reads the set the launch before wrote, writes the other)
@@ -900,6 +914,7 @@ struct MfPlan {
   int allow_fuse;                // the caller runs whole chunks (mf_solve_impl): the small-vector update may run inside the pass
   int fuse;                      // ... and does: no k_mf_small launch between the passes of a chunk
   double* q[2];                  // the two small-state buffers of the fused launches
+  const int* live;               // [1 + B] count and indices of the instances still iterating (bulk pass), or null
   double *aP1, *aP4, *aPS, *aP3i; // the second set of partial sums (launch k writes set k & 1; set 1 = st.P1, st.P4, st.PS, st.P3i)
   int diag;                      // tools only: bit 2 = time the small-vector kernel alone
 };
@@ -910,8 +925,8 @@ static void mf_launch_iter(const MfPlan& P) {
   const int g = (int)(total < P.grid_iter ? total : P.grid_iter);
   if (P.bulk) {
     const int threads = (P.bcfg.nw + 1) * 32;
-    if (P.bulk == 2) k_mf_iter_bulk<true, false><<<g, threads, P.bcfg.smem, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, P.bcfg, BulkFuse{});
-    else k_mf_iter_bulk<false, false><<<g, threads, P.bcfg.smem, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, P.bcfg, BulkFuse{});
+    if (P.bulk == 2) k_mf_iter_bulk<true, false><<<g, threads, P.bcfg.smem, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, P.bcfg, BulkFuse{}, P.live);
+    else k_mf_iter_bulk<false, false><<<g, threads, P.bcfg.smem, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, P.bcfg, BulkFuse{}, P.live);
     NEPTUNE_COUNT(1);
     return;
   }
@@ -948,8 +963,8 @@ static void mf_launch_fused(const MfPlan& P, int k, const int* first_flag, int f
     fz.rP1 = P.st.P1; fz.rP4 = P.st.P4; fz.rPS = P.st.PS; fz.rP3 = P.st.P3i;
     fz.wP1 = P.aP1; fz.wP4 = P.aP4; fz.wPS = P.aPS; fz.wP3 = P.aP3i;
   }
-  if (P.bulk == 2) k_mf_iter_bulk<true, true><<<g, threads, P.bcfg.smem, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, P.bcfg, fz);
-  else k_mf_iter_bulk<false, true><<<g, threads, P.bcfg.smem, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, P.bcfg, fz);
+  if (P.bulk == 2) k_mf_iter_bulk<true, true><<<g, threads, P.bcfg.smem, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, P.bcfg, fz, P.live);
+  else k_mf_iter_bulk<false, true><<<g, threads, P.bcfg.smem, P.s>>>(P.G, P.in, P.st, P.ctl, P.B, P.bcfg, fz, P.live);
   NEPTUNE_COUNT(1);
 }
 
@@ -1148,6 +1163,7 @@ static int mf_solve_impl(int B, int N, int F, int kind, const double* d, const d
   // of launches
   P.allow_fuse = ((check_every < 32 ? check_every : 32) & 1) == 0;
   mf_choose_pass(P, prm->reserved, x, y, d);
+  P.live = P.bulk ? (const int*)(base + W.cnt) : nullptr;
   // small vectors: one block per instance does POST + PREC + Y2 in one launch while F*N is small; larger
   // instances spread over several blocks and take the C2 dual in a second launch
   P.fused = G.C <= 4096;
@@ -1161,6 +1177,7 @@ static int mf_solve_impl(int B, int N, int F, int kind, const double* d, const d
   { k_mf_setup<<<dim3(nblk, B), 256, 0, s>>>(G, P.in, P.st, nblk); NEPTUNE_COUNT(1); }
   { k_mf_setup_norms<<<(B + 127) / 128, 128, 0, s>>>(G, P.in, P.st, ctl, B, nblk); NEPTUNE_COUNT(1); }
   { k_ctl_init<<<(B + 127) / 128, 128, 0, s>>>(B, ctl, 0.99); NEPTUNE_COUNT(1); }
+  if (P.bulk) { k_mf_live<<<1, 32, 0, s>>>(B, ctl, (int*)(base + W.cnt)); NEPTUNE_COUNT(1); }
   NEPTUNE_CUDA_OK(cudaMemsetAsync(P.st.xsum, 0, cb, s));
   NEPTUNE_CUDA_OK(cudaMemsetAsync(P.st.ysum, 0, rb, s));
   NEPTUNE_CUDA_OK(cudaMemcpyAsync(xres, x, cb, cudaMemcpyDeviceToDevice, s));
@@ -1228,6 +1245,7 @@ static int mf_solve_impl(int B, int N, int F, int kind, const double* d, const d
     { k_ctl_after_restart<<<(B + 127) / 128, 128, 0, s>>>(B, ctl); NEPTUNE_COUNT(1); }
     mf_launch_eval(P, 0, 1);                    // PS of the (possibly replaced) yS for the next PREC
     { k_all_done<<<1, 1, 0, s>>>(B, ctl, d_flag); NEPTUNE_COUNT(1); }
+    if (P.bulk) { k_mf_live<<<1, 32, 0, s>>>(B, ctl, (int*)(base + W.cnt)); NEPTUNE_COUNT(1); }
     NEPTUNE_CUDA_OK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, s));
     NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
   }

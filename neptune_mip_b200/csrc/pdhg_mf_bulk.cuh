@@ -274,12 +274,19 @@ __device__ __forceinline__ void bulk_small_y2(const MfGeo& G, const MfIn& in, co
 // tile cost 4.5 us of dependent L2 round trips, all warps in lockstep).
 template <bool RED, bool FUSE>
 __global__ void __launch_bounds__((kBulkMaxWarps + 1) * 32, 1)
-k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, BulkCfg cfg, BulkFuse fz) {
+k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, BulkCfg cfg, BulkFuse fz,
+               const int* __restrict__ live) {
   extern __shared__ __align__(128) unsigned char bulk_smem_raw[];
   const int N = G.N, F = G.F, NW = cfg.nw, S = cfg.stages;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t NN = (int64_t)N * N;
-  const int64_t total = (int64_t)B * F;
+  // `live` (or null): live[0] = number of instances still iterating, live[1..] = their indices in increasing order (rebuilt
+  // at every KKT check, constant during a chunk).  Slabs are enumerated over the live instances only, so the work of a
+  // batch whose instances converge one by one stays spread over every SM (the last live instance of a batch of 48 would
+  // otherwise sit in three blocks).
+  const int n_inst = live ? live[0] : B;
+  const int64_t total = (int64_t)n_inst * F;
+  auto inst_of = [&](int64_t slab, int& f) { const int q = (int)(slab / F); f = (int)(slab - (int64_t)q * F); return live ? live[1 + q] : q; };
   // shared-memory carve: [barriers 256 B][column partials 3 * NW * N doubles][per-instance vectors (FUSE)][stages]
   unsigned char* base = bulk_smem_raw;
   double* colbuf = reinterpret_cast<double*>(base + 256);
@@ -315,13 +322,13 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
       struct Prep { double tau, shalf; int conv; };
       auto prep_tile = [&](int n) {          // the control block of the tile's instance (requested ahead of the waits)
         const int64_t slab = first + (int64_t)n * step;
-        const int b = (int)(slab / F);
+        int f_; const int b = inst_of(slab, f_);
         Prep p; p.tau = ctl[b].tau; p.shalf = 0.5 * ctl[b].sigma; p.conv = ctl[b].converged;
         return p;
       };
       auto load_tile = [&](int n, const Prep& pr) {
         const int64_t slab = first + (int64_t)n * step;
-        const int b = (int)(slab / F), f = (int)(slab - (int64_t)b * F);
+        int f; const int b = inst_of(slab, f);
         const int s = n % S;
         const uint32_t bar = bar_full + 8u * s, dst = stage0 + (uint32_t)s * stage_bytes;
         double* hdr = reinterpret_cast<double*>(base + (dst - base_addr) + cfg.vec_off) + 7 * N;
@@ -350,7 +357,7 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
       };
       auto store_tile = [&](int n) {
         const int64_t slab = first + (int64_t)n * step;
-        const int b = (int)(slab / F), f = (int)(slab - (int64_t)b * F);
+        int f; const int b = inst_of(slab, f);
         if (!ctl[b].converged && cfg.diag != 1 && cfg.diag != 3) {
           double* xg = st.x + (int64_t)b * G.cols + (int64_t)f * NN;
           double* sg = st.y + (int64_t)b * G.rows + G.rs + (int64_t)f * NN;
@@ -398,7 +405,7 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
     int m = 0;
     for (int n = 0; n < T; ++n) {
       const int64_t slab = first + n;
-      const int b = (int)(slab / F), f = (int)(slab - (int64_t)b * F);
+      int f; const int b = inst_of(slab, f);
       if (!(n == 0 || f == 0)) continue;
       const uint32_t ib = (uint32_t)(m & 1);
       if (m >= 2) mbar_wait(bar_ifree + 8u * ib, (uint32_t)(((m - 2) >> 1) & 1));
@@ -438,7 +445,7 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
   int m_inst = 0; uint32_t cur_ib = 0;
   for (int n = 0; n < T; ++n) {
     const int64_t slab = first + (int64_t)n * step;
-    const int b = (int)(slab / F), f = (int)(slab - (int64_t)b * F);
+    int f; const int b = inst_of(slab, f);
     const int s = n % S;
     const uint32_t ph = (uint32_t)((n / S) & 1);
     const bool inst_last = FUSE && (f == F - 1 || n == T - 1);
