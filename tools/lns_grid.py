@@ -30,6 +30,9 @@ GRID = [
     ("phases-4-cool-0.8", dict(lns_phases=4, lns_cooling=0.8)),
     ("final-k4-6000-hot", dict(lns_final_k4=6000, lns_final_noise=0.6)),
     ("no-cut-guide", dict(lp_cut=False)),
+    ("noise-0.07", dict(lns_noise=0.07)),
+    ("k2-40000", dict(lns_k=2, lns_rounds=40000)),
+    ("noise-0.05-final-hot", dict(lns_noise=0.05, lns_final_noise=0.6)),
     ("rng-2", dict(rng_seed=2)),
     ("rng-3", dict(rng_seed=3)),
 ]

@@ -1,6 +1,6 @@
 """torchrun entry: function-block-sharded PDHG vs the unsharded iteration (parity) and timing.
   python -m torch.distributed.run --nproc-per-node 2 tools/sharded_run.py parity|solve|time|mf-parity|mf-solve|mf-time N F [iters]
-(the mf-* modes drive the EXPERIMENTAL matrix-free sharded solver, neptune_mip_b200/sharded_mf.py)"""
+(the mf-* modes drive the matrix-free sharded solver, neptune_mip_b200/sharded_mf.py)"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
