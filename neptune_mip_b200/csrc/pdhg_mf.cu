@@ -24,11 +24,17 @@
 //   = 64*X, + 112*F*N (small vectors) + 8*N*N (d, re-read per function from L1/L2)  [X = F*N*N]; the CSR solver
 //   moves 16*nnz + 88*cols + 72*rows ~ 260*X for the same iteration.
 //
-// Two iteration passes, both parity-tested against the numpy statement (tests/test_pdhg_mf_gpu.py): k_mf_iter2<KP, U>
-// (even N in 33..64: a lane owns pairs of adjacent columns, 16-byte accesses, cheap reciprocal) and k_mf_iter<K, U>
-// (every other shape: lanes own K strided columns, 8-byte accesses); U rows of a warp are in flight.  Round 2
-// measured five further variants on B200 (bulk-copy staging, strided 16-byte, cp.async ring, fused small vectors,
-// pointer bumping: profiles/r02_pdhg_variants.md) -- none beat these two and they were removed.
+// Three iteration passes, all parity-tested against the numpy statement (tests/test_pdhg_mf_gpu.py):
+//   k_mf_iter_bulk<RED, FUSE> (pdhg_mf_bulk.cuh; even N <= 64, the default for even N in 34..64, i.e. C2): the streams
+//     staged through shared memory by the bulk-copy engine (cp.async.bulk + mbarrier), running sums by
+//     cp.reduce.async.bulk add.f64, the small-vector update inside the same launch -- 0.75-0.79 of the measured HBM peak
+//     where the register passes reach 0.52-0.56 (profiles/r02c_pdhg_bulk.md);
+//   k_mf_iter2<KP, U> (even N in 33..64: a lane owns pairs of adjacent columns, 16-byte accesses, cheap reciprocal) and
+//   k_mf_iter<K, U> (every other shape: lanes own K strided columns, 8-byte accesses); U rows of a warp are in flight.
+// Round 2 measured five further register / staging variants on B200 (bulk-copy staging of 8 KB tiles, strided 16-byte,
+// cp.async ring, fused small vectors, pointer bumping: profiles/r02_pdhg_variants.md) -- none beat the two register passes
+// and they were removed; what did was taking EVERY consumer input out of global memory and the small-vector kernel out of
+// the iteration (pdhg_mf_bulk.cuh).  NEPTUNE_MF_PASS = pair | bulk | bulkred overrides the default pass (measurements).
 #include "common.cuh"
 #include "pdhg_ctl.cuh"
 #include <stdlib.h>
