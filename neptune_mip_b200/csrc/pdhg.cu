@@ -723,7 +723,7 @@ extern "C" int neptune_pdhg_solve(int B, int64_t rows, int64_t cols, int64_t nnz
       { k_apply_restart<<<gr, 256, 0, s>>>(rows, 0, ctl, y, ysum, yres, S); NEPTUNE_COUNT(1); }
     }
     { k_ctl_after_restart<<<(B + 127) / 128, 128, 0, s>>>(B, ctl); NEPTUNE_COUNT(1); }
-    { k_all_done<<<1, 1, 0, s>>>(B, ctl, d_flag); NEPTUNE_COUNT(1); }
+    { k_all_done<<<1, 32, 0, s>>>(B, ctl, d_flag); NEPTUNE_COUNT(1); }
     NEPTUNE_CUDA_OK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, s));
     NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));
   }

@@ -1250,7 +1250,7 @@ static int mf_solve_impl(int B, int N, int F, int kind, const double* d, const d
     { k_mf_restart_norms<<<(B + 127) / 128, 128, 0, s>>>(B, kMfRestartBlocks, part, ctl); NEPTUNE_COUNT(1); }
     { k_ctl_after_restart<<<(B + 127) / 128, 128, 0, s>>>(B, ctl); NEPTUNE_COUNT(1); }
     mf_launch_eval(P, 0, 1);                    // PS of the (possibly replaced) yS for the next PREC
-    { k_all_done<<<1, 1, 0, s>>>(B, ctl, d_flag); NEPTUNE_COUNT(1); }
+    { k_all_done<<<1, 32, 0, s>>>(B, ctl, d_flag); NEPTUNE_COUNT(1); }
     if (P.bulk) { k_mf_live<<<1, 32, 0, s>>>(B, ctl, (int*)(base + W.cnt)); NEPTUNE_COUNT(1); }
     NEPTUNE_CUDA_OK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, s));
     NEPTUNE_CUDA_OK(cudaStreamSynchronize(s));

@@ -261,6 +261,11 @@ __device__ __forceinline__ void bulk_small_y2(const MfGeo& G, const MfIn& in, co
   }
 }
 
+// projections as compare-and-select (fmin / fmax on doubles cost six instructions each for their NaN rules; the iterates are
+// finite, and for finite arguments the value is the same -- only the sign of a zero may differ)
+__device__ __forceinline__ double clip01(double v) { v = v < 0.0 ? 0.0 : v; return v > 1.0 ? 1.0 : v; }
+__device__ __forceinline__ double max0(double v) { return v < 0.0 ? 0.0 : v; }
+
 // ---- the pass -------------------------------------------------------------------------------------------------
 // grid: one block per SM (at most one block per tile); block: (cfg.nw + 1) warps, the LAST warp is the producer.
 // Tiles: slab = b * F + f.  !FUSE: tile n of block k is slab k + n * gridDim.x.  FUSE: a block owns a CONTIGUOUS run of
@@ -516,9 +521,9 @@ k_mf_iter_bulk(MfGeo G, MfIn in, MfSt st, const Ctl* __restrict__ ctl, int B, Bu
             const double wr = fabs(wfi[u] * rj[e]);
             const double g = __dmul_rn(de, wfi[u]) + y1j[e] + ty[u] + wfi[u] * rr4[e] + so;
             double x1 = xo - tau * g * mf_rcp(3.0 + wr);
-            x1 = fmin(fmax(x1, 0.0), 1.0);
+            x1 = clip01(x1);
             const double xb = 2.0 * x1 - xo;
-            const double s1 = fmax(so + shalf * (xb - cb[e]), 0.0);
+            const double s1 = max0(so + shalf * (xb - cb[e]));
             xn[e] = x1; sn[e] = s1;
             a1[e] += xb; a4[e] += wfi[u] * xb; aS[e] += s1; rsum += xb;
           }
