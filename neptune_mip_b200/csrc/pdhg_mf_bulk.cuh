@@ -7,8 +7,12 @@
 // loads (long scoreboard 7.8 of 9.6 stalled warps per issue, profiles/r02_pdhg_variants.md).  Here the bytes in flight live
 // in shared memory (up to 200 KB per SM) and are requested by one thread:
 //
-//   * a persistent block per SM: one producer warp (one elected lane) + NW consumer warps; a tile is the whole N x N slab
-//     of one (instance, function), contiguous in every stream, so a tile is 4 (or 2) one-dimensional bulk copies;
+//   * a persistent block per SM: one producer warp (one elected lane) + NW consumer warps (+ two small-vector warps, FUSE);
+//     a tile is the whole N x N slab of one (instance, function), contiguous in every stream, so a tile is a handful of
+//     one-dimensional bulk copies: x, yS (xsum, ysum), the delay matrix, w[f,:], r[f,:] (and, without FUSE, y3[f,:], y4,
+//     cbar[f,:], the multiplier pairs of C1) plus a header {tau, sigma / 2, live} the producer writes -- on the tile path a
+//     consumer reads NOTHING from global memory (with the vectors read from global a tile cost 4.5 us of dependent L2 round
+//     trips, all warps in lockstep);
 //   * STAGES stages, each with a `full` mbarrier (producer: arrive.expect_tx, the copies complete the transaction count)
 //     and a `done` mbarrier (one arrival per consumer warp, after fence.proxy.async: the stores of the async proxy read
 //     what the generic proxy wrote);
@@ -17,12 +21,18 @@
 //     cp.async.bulk.wait_group.read;
 //   * RED = true: the running sums xsum, ysum are never loaded -- `cp.reduce.async.bulk ... add.f64` adds the new x / yS
 //     from the same shared-memory buffers to them in L2 (one IEEE addition per element and iteration, so the value equals
-//     xsum + x+ of the other passes bit for bit); a stage is then two streams, and twice as many stages fit;
-//     RED = false: xsum, ysum travel through the stage like x and yS (four streams);
+//     xsum + x+ of the other passes bit for bit); a stage is then two read-write slabs, and more stages fit;
+//     RED = false: xsum, ysum travel through the stage like x and yS (four read-write slabs);
 //   * column sums: per-lane accumulators over the rows of a warp, then one cross-warp reduction per tile through a small
-//     shared buffer in warp order (fixed summation order: runs are bit-reproducible); row sums by warp shuffle.
-// The partial-sum buffers (P1, P4, PS: one row tile per slab, P3i: one column segment) are the ones k_mf_iter2 fills, so
+//     shared buffer in warp order (fixed summation order: runs are bit-reproducible); row sums by warp shuffle;
+//   * FUSE = true: the small-vector update (k_mf_small's arithmetic) runs inside the launch -- two small-vector warps, one
+//     instance ahead of the consumers, two shared buffers handed over by mbarriers; small state and partial sums alternate
+//     between two sets from launch to launch (bulk_small_pre, BulkFuse); the chunk ends with k_mf_small_from.  An
+//     iteration is then ONE launch: 87.6 us at C2 x 256 against 94.6 with k_mf_small launches and 125 for the pair pass;
+//   * slabs are enumerated over the instances still iterating (`live`, rebuilt by k_mf_live at every KKT check).
+// The partial-sum buffers (P1, P4, PS: one row tile per slab, P3i: one column segment) have the layout k_mf_iter2 fills, so
 // k_mf_small and the KKT passes are shared.  Every spin on an mbarrier is bounded (trap after ~2 s of SM clocks).
+// Measurements, step by step: profiles/r02c_pdhg_bulk.md.
 #pragma once
 
 namespace neptune {
