@@ -449,7 +449,7 @@ def c3_pdhg(peak):
 
     from neptune_mip_b200 import device, synth
     from neptune_mip_b200.core.utils import data_to_solver_input
-    N, F, iters = 500, 50, 512
+    N, F, iters = 500, 50, 2048          # long enough for the solve's set-up and KKT passes (one set per call) to be ~1 % of it
     inst = device.InstanceBatch.from_datas([data_to_solver_input(synth.config_payload("C3", 0), 1, with_db=False)])
     lp = device.slot_relaxation(inst)
     device.pdhg_mf_solve(lp, max_iters=32, check_every=32)
